@@ -1,0 +1,190 @@
+"""ctypes binding of oracle/liboracle.so -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module (see oracle/jpeg_oracle.h for what the oracle restates:
+the codec work below /root/reference/src/compressor.rs:287-306).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liboracle.so")
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB
+
+
+class OrcJpeg(C.Structure):
+    _fields_ = [
+        ("width", C.c_int), ("height", C.c_int), ("ncomp", C.c_int), ("progressive", C.c_int),
+        ("hs", C.c_int * 4), ("vs", C.c_int * 4), ("tq", C.c_int * 4), ("cid", C.c_int * 4),
+        ("hmax", C.c_int), ("vmax", C.c_int), ("mcux", C.c_int), ("mcuy", C.c_int),
+        ("bw", C.c_int * 4), ("bh", C.c_int * 4), ("rbw", C.c_int * 4), ("rbh", C.c_int * 4),
+        ("cw", C.c_int * 4), ("ch", C.c_int * 4),
+        ("qt", (C.c_uint16 * 64) * 4), ("qt_present", C.c_int * 4),
+        ("coef", C.POINTER(C.c_int16) * 4),
+        ("restart_interval", C.c_int), ("nscans", C.c_int),
+        ("scan_script", (C.c_int * 8) * 64),
+        ("jfif", C.c_int), ("adobe", C.c_int), ("adobe_transform", C.c_int),
+        ("markers", C.POINTER(C.c_uint8)), ("markers_len", C.c_size_t),
+        ("icc_markers", C.POINTER(C.c_uint8)), ("icc_len", C.c_size_t),
+    ]
+
+
+class OrcJpegParams(C.Structure):
+    _fields_ = [("quality", C.c_int), ("subsampling", C.c_int), ("progressive", C.c_int),
+                ("keep_metadata", C.c_int), ("preserve_icc", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+        _lib.orc_jpeg_read.restype = C.c_int
+        _lib.orc_jpeg_lossy.restype = C.c_int
+        _lib.orc_jpeg_lossless.restype = C.c_int
+        _lib.orc_jpeg_write.restype = C.c_int
+        _lib.orc_jpeg_forward.restype = C.c_int
+        _lib.orc_jpeg_decode_native.restype = C.c_int
+    return _lib
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+def _buf(data):
+    return (C.c_uint8 * len(data)).from_buffer_copy(data)
+
+
+def quant_table(quality, which=0):
+    out = (C.c_uint16 * 64)()
+    lib().orc_quant_table(int(quality), int(which), out)
+    return np.frombuffer(out, dtype=np.uint16).copy()
+
+
+def idct_islow(coef, q):
+    coef = np.ascontiguousarray(coef, dtype=np.int16).reshape(64)
+    q = np.ascontiguousarray(q, dtype=np.uint16).reshape(64)
+    out = np.zeros(64, dtype=np.uint8)
+    lib().orc_idct_islow(coef.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out.reshape(8, 8)
+
+
+def fdct_quant(px, q):
+    px = np.ascontiguousarray(px, dtype=np.uint8).reshape(64)
+    q = np.ascontiguousarray(q, dtype=np.uint16).reshape(64)
+    dct = np.zeros(64, dtype=np.int32)
+    out = np.zeros(64, dtype=np.int16)
+    lib().orc_fdct_islow(px.ctypes.data_as(C.c_void_p), dct.ctypes.data_as(C.c_void_p))
+    lib().orc_quantize(dct.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return dct.reshape(8, 8), out.reshape(8, 8)
+
+
+class Jpeg:
+    """Decoded coefficient-domain view of a JPEG file (orc_jpeg_read)."""
+
+    def __init__(self, data=None):
+        self.s = OrcJpeg()
+        self._owned = False
+        if data is not None:
+            err = C.create_string_buffer(256)
+            if lib().orc_jpeg_read(_buf(data), C.c_size_t(len(data)), C.byref(self.s), err):
+                raise OracleError(err.value.decode())
+            self._owned = True
+
+    def __del__(self):
+        if self._owned:
+            lib().orc_jpeg_free(C.byref(self.s))
+            self._owned = False
+
+    @property
+    def ncomp(self):
+        return self.s.ncomp
+
+    def coef(self, c):
+        """[bh, bw, 64] int16, natural order, quantised (padded to whole MCUs)."""
+        n = self.s.bh[c] * self.s.bw[c] * 64
+        a = np.ctypeslib.as_array(self.s.coef[c], shape=(n,)).copy()
+        return a.reshape(self.s.bh[c], self.s.bw[c], 64)
+
+    def qtable(self, c):
+        return np.frombuffer(self.s.qt[self.s.tq[c]], dtype=np.uint16).copy()
+
+    def scans(self):
+        return [tuple(self.s.scan_script[i]) for i in range(self.s.nscans)]
+
+    def component_plane(self, c):
+        """dequant + IDCT of every allocated block: (bh*8, bw*8) uint8."""
+        out = np.zeros((self.s.bh[c] * 8, self.s.bw[c] * 8), dtype=np.uint8)
+        lib().orc_jpeg_idct_component(C.byref(self.s), c, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def decode_native(self):
+        """[ncomp, H, W] uint8 in the file's own colour space (fancy upsampling)."""
+        out = np.zeros((self.s.ncomp, self.s.height, self.s.width), dtype=np.uint8)
+        ptrs = (C.c_void_p * 4)(*[out[c].ctypes.data if c < self.s.ncomp else None for c in range(4)])
+        err = C.create_string_buffer(256)
+        if lib().orc_jpeg_decode_native(C.byref(self.s), ptrs, err):
+            raise OracleError(err.value.decode())
+        return out
+
+
+def params(quality=80, subsampling=0, progressive=True, keep_metadata=False, preserve_icc=True):
+    return OrcJpegParams(int(quality), int(subsampling), int(bool(progressive)), int(bool(keep_metadata)), int(bool(preserve_icc)))
+
+
+def forward(planes, p):
+    """planes [ncomp,H,W] uint8 -> Jpeg holding quantised coefficients (orc_jpeg_forward)."""
+    planes = np.ascontiguousarray(planes, dtype=np.uint8)
+    n, h, w = planes.shape
+    ptrs = (C.c_void_p * 4)(*[planes[c].ctypes.data if c < n else None for c in range(4)])
+    j = Jpeg()
+    err = C.create_string_buffer(256)
+    if lib().orc_jpeg_forward(ptrs, w, h, n, C.byref(p), C.byref(j.s), err):
+        raise OracleError(err.value.decode())
+    j._owned = True
+    return j
+
+
+def _take(outp, outl):
+    data = C.string_at(outp, outl.value)
+    lib().orc_free(outp)
+    return data
+
+
+def write(j, p, meta=None):
+    outp, outl = C.POINTER(C.c_uint8)(), C.c_size_t()
+    err = C.create_string_buffer(256)
+    if lib().orc_jpeg_write(C.byref(j.s), C.byref(p), C.byref(meta.s) if meta is not None else None, C.byref(outp), C.byref(outl), err):
+        raise OracleError(err.value.decode())
+    return _take(outp, outl)
+
+
+def jpeg_lossy(data, p):
+    """libcaesium jpeg::lossy restated (compress_in_memory, jpeg.optimize == false)."""
+    outp, outl = C.POINTER(C.c_uint8)(), C.c_size_t()
+    err = C.create_string_buffer(256)
+    if lib().orc_jpeg_lossy(_buf(data), C.c_size_t(len(data)), C.byref(p), C.byref(outp), C.byref(outl), err):
+        raise OracleError(err.value.decode())
+    return _take(outp, outl)
+
+
+def jpeg_lossless(data, p):
+    """libcaesium jpeg::lossless restated (jpegtran-style transcode)."""
+    outp, outl = C.POINTER(C.c_uint8)(), C.c_size_t()
+    err = C.create_string_buffer(256)
+    if lib().orc_jpeg_lossless(_buf(data), C.c_size_t(len(data)), C.byref(p), C.byref(outp), C.byref(outl), err):
+        raise OracleError(err.value.decode())
+    return _take(outp, outl)
