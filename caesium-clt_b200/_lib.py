@@ -1,0 +1,247 @@
+"""ctypes binding of libb200caesium.so (include/b200_caesium.h).
+
+This is the only way Python code in this repo reaches the product: through the same C-ABI a
+Rust maintainer would bind at /root/reference/src/compressor.rs:287-306.  There is no Python or
+CPU fallback -- if the shared library is missing, loading raises; if no B200 is visible, every
+codec call returns B200_ERR_NO_DEVICE.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200caesium.so")
+
+OK, ERR_INVALID_ARGUMENT, ERR_UNKNOWN_FORMAT, ERR_UNSUPPORTED, ERR_CORRUPT_INPUT = 0, 1, 2, 3, 4
+ERR_NO_DEVICE, ERR_CUDA, ERR_OUT_OF_MEMORY, ERR_SAME_FORMAT, ERR_TOO_LARGE = 5, 6, 7, 8, 9
+FMT_JPEG, FMT_PNG, FMT_GIF, FMT_WEBP, FMT_TIFF, FMT_UNKNOWN = 0, 1, 2, 3, 4, 5
+
+
+class Status(C.Structure):
+    _fields_ = [("code", C.c_int32), ("message", C.c_void_p)]
+
+
+class Params(C.Structure):
+    """b200_params == caesium::parameters::CSParameters as compressor.rs:411-446 fills it."""
+    _fields_ = [
+        ("keep_metadata", C.c_uint8), ("jpeg_quality", C.c_uint32), ("jpeg_chroma_subsampling", C.c_uint32),
+        ("jpeg_progressive", C.c_uint8), ("jpeg_optimize", C.c_uint8), ("jpeg_preserve_icc", C.c_uint8),
+        ("png_quality", C.c_uint32), ("png_optimization_level", C.c_uint32), ("png_force_zopfli", C.c_uint8),
+        ("png_optimize", C.c_uint8), ("gif_quality", C.c_uint32), ("webp_quality", C.c_uint32),
+        ("webp_lossless", C.c_uint8), ("width", C.c_uint32), ("height", C.c_uint32),
+    ]
+
+
+class JpegLayout(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("ncomp", C.c_int32), ("progressive", C.c_int32),
+        ("hs", C.c_int32 * 4), ("vs", C.c_int32 * 4), ("bw", C.c_int32 * 4), ("bh", C.c_int32 * 4),
+        ("rbw", C.c_int32 * 4), ("rbh", C.c_int32 * 4), ("comp_offset", C.c_int64 * 4), ("total_coefs", C.c_int64),
+        ("qt", (C.c_uint16 * 64) * 4),
+    ]
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(message)
+        self.code = code
+
+
+def build(force=False):
+    """Compile the CUDA + C++ sources in-tree (nvcc -gencode arch=compute_100a,code=sm_100a)."""
+    if force:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "clean"])
+    subprocess.check_call(["make", "-C", _HERE, "-s", "-j8"])
+    return LIB_PATH
+
+
+_lib = None
+
+_SYMBOLS = [
+    "b200_params_default", "b200_init", "b200_init_device", "b200_shutdown", "b200_device_count", "b200_version", "b200_free",
+    "b200_compress_in_memory", "b200_convert_in_memory", "b200_compress_to_size_in_memory", "b200_compress_batch",
+    "b200_sniff_format", "b200_jpeg_decode_coefficients", "b200_jpeg_output_layout", "b200_jpeg_requantize",
+    "b200_jpeg_encode_coefficients", "b200_jpeg_decode_planes", "b200_jpeg_quant_table",
+    "b200_jpeg_batch_create", "b200_jpeg_batch_upload", "b200_jpeg_batch_run", "b200_jpeg_batch_download",
+    "b200_jpeg_batch_time", "b200_jpeg_batch_destroy",
+]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no Python/CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name in _SYMBOLS:
+            getattr(L, name)  # raises AttributeError if the ABI is incomplete
+        for f in ("b200_compress_in_memory", "b200_convert_in_memory", "b200_compress_to_size_in_memory",
+                  "b200_jpeg_decode_coefficients", "b200_jpeg_output_layout", "b200_jpeg_requantize",
+                  "b200_jpeg_encode_coefficients", "b200_jpeg_decode_planes", "b200_jpeg_batch_create",
+                  "b200_jpeg_batch_upload", "b200_jpeg_batch_run", "b200_jpeg_batch_download", "b200_jpeg_batch_time"):
+            getattr(L, f).restype = Status
+        L.b200_version.restype = C.c_char_p
+        L.b200_sniff_format.restype = C.c_uint32
+        L.b200_free.argtypes = [C.c_void_p]
+        L.b200_jpeg_batch_destroy.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _check(st):
+    if st.code != 0:
+        msg = C.string_at(st.message).decode() if st.message else f"error {st.code}"
+        lib().b200_free(st.message)
+        raise B200Error(st.code, msg)
+
+
+def default_params():
+    p = Params()
+    lib().b200_params_default(C.byref(p))
+    return p
+
+
+def _take(outp, outl):
+    data = C.string_at(outp, outl.value)
+    lib().b200_free(outp)
+    return data
+
+
+def compress_in_memory(data, params):
+    """caesium::compress_in_memory (compressor.rs:305)."""
+    outp, outl = C.c_void_p(), C.c_size_t()
+    _check(lib().b200_compress_in_memory(data, C.c_size_t(len(data)), C.byref(params), C.byref(outp), C.byref(outl)))
+    return _take(outp, outl)
+
+
+def convert_in_memory(data, params, fmt):
+    """caesium::convert_in_memory (compressor.rs:289, :300)."""
+    outp, outl = C.c_void_p(), C.c_size_t()
+    _check(lib().b200_convert_in_memory(data, C.c_size_t(len(data)), C.byref(params), C.c_uint32(fmt), C.byref(outp), C.byref(outl)))
+    return _take(outp, outl)
+
+
+def compress_to_size_in_memory(data, params, max_size, return_smallest=True):
+    """caesium::compress_to_size_in_memory (compressor.rs:295, :298); params.jpeg_quality may be updated."""
+    outp, outl = C.c_void_p(), C.c_size_t()
+    _check(lib().b200_compress_to_size_in_memory(data, C.c_size_t(len(data)), C.byref(params), C.c_size_t(max_size),
+                                                 C.c_uint8(1 if return_smallest else 0), C.byref(outp), C.byref(outl)))
+    return _take(outp, outl)
+
+
+def compress_batch(datas, params, n_threads=0):
+    """Batch form of start_compression's par_iter (compressor.rs:74-101): returns [(bytes | None, code, message)]."""
+    n = len(datas)
+    ins = (C.c_char_p * n)(*datas)
+    lens = (C.c_size_t * n)(*[len(d) for d in datas])
+    outs = (C.c_void_p * n)()
+    outl = (C.c_size_t * n)()
+    sts = (Status * n)()
+    lib().b200_compress_batch(ins, lens, n, C.byref(params), int(n_threads), outs, outl, sts)
+    res = []
+    for i in range(n):
+        if sts[i].code == 0:
+            res.append((C.string_at(outs[i], outl[i]), 0, ""))
+            lib().b200_free(outs[i])
+        else:
+            msg = C.string_at(sts[i].message).decode() if sts[i].message else ""
+            lib().b200_free(sts[i].message)
+            res.append((None, sts[i].code, msg))
+    return res
+
+
+def sniff_format(data):
+    return lib().b200_sniff_format(data, C.c_size_t(len(data)))
+
+
+def jpeg_quant_table(quality, which=0):
+    out = (C.c_uint16 * 64)()
+    lib().b200_jpeg_quant_table(int(quality), int(which), out)
+    return np.frombuffer(out, dtype=np.uint16).copy()
+
+
+def jpeg_decode_coefficients(data):
+    """Host entropy decode -> (JpegLayout, int16 array of total_coefs, zigzag order)."""
+    lay = JpegLayout()
+    ptr = C.c_void_p()
+    _check(lib().b200_jpeg_decode_coefficients(data, C.c_size_t(len(data)), C.byref(lay), C.byref(ptr)))
+    arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_int16)), shape=(lay.total_coefs,)).copy()
+    lib().b200_free(ptr)
+    return lay, arr
+
+
+def jpeg_output_layout(in_layout, params):
+    out = JpegLayout()
+    _check(lib().b200_jpeg_output_layout(C.byref(in_layout), C.byref(params), C.byref(out)))
+    return out
+
+
+def jpeg_requantize(in_layout, in_coefs, out_layout):
+    """Device: dequant -> IDCT -> resample -> FDCT -> quantise -> zigzag (host buffers in/out)."""
+    in_coefs = np.ascontiguousarray(in_coefs, dtype=np.int16)
+    out = np.zeros(out_layout.total_coefs, dtype=np.int16)
+    _check(lib().b200_jpeg_requantize(C.byref(in_layout), in_coefs.ctypes.data_as(C.c_void_p), C.byref(out_layout), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def jpeg_encode_coefficients(layout, coefs, progressive=True):
+    coefs = np.ascontiguousarray(coefs, dtype=np.int16)
+    outp, outl = C.c_void_p(), C.c_size_t()
+    _check(lib().b200_jpeg_encode_coefficients(C.byref(layout), coefs.ctypes.data_as(C.c_void_p), int(bool(progressive)), C.byref(outp), C.byref(outl)))
+    return _take(outp, outl)
+
+
+def jpeg_decode_planes(in_layout, in_coefs):
+    """Device: dequant + IDCT + fancy upsample -> [ncomp, H, W] uint8 in the file's colour space."""
+    in_coefs = np.ascontiguousarray(in_coefs, dtype=np.int16)
+    out = np.zeros((in_layout.ncomp, in_layout.height, in_layout.width), dtype=np.uint8)
+    _check(lib().b200_jpeg_decode_planes(C.byref(in_layout), in_coefs.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def component_view(layout, coefs, c):
+    """[bh, bw, 64] view (zigzag order) of component c inside a flat coefficient buffer."""
+    o = layout.comp_offset[c]
+    n = layout.bw[c] * layout.bh[c] * 64
+    return coefs[o:o + n].reshape(layout.bh[c], layout.bw[c], 64)
+
+
+class JpegBatch:
+    """Device-resident megabatch of n same-layout images (bench.py's HBM-resident `value`)."""
+
+    def __init__(self, in_layout, out_layout, n):
+        self.h = C.c_void_p()
+        self.in_layout, self.out_layout, self.n = in_layout, out_layout, n
+        _check(lib().b200_jpeg_batch_create(C.byref(in_layout), C.byref(out_layout), int(n), C.byref(self.h)))
+
+    def upload(self, i, coefs):
+        coefs = np.ascontiguousarray(coefs, dtype=np.int16)
+        _check(lib().b200_jpeg_batch_upload(self.h, int(i), coefs.ctypes.data_as(C.c_void_p)))
+
+    def run(self, stream=None):
+        n = C.c_int(0)
+        _check(lib().b200_jpeg_batch_run(self.h, C.c_void_p(stream), C.byref(n)))
+        return n.value
+
+    def download(self, i):
+        out = np.zeros(self.out_layout.total_coefs, dtype=np.int16)
+        _check(lib().b200_jpeg_batch_download(self.h, int(i), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def time(self, which=0, iters=10):
+        ms = C.c_float(0)
+        _check(lib().b200_jpeg_batch_time(self.h, int(which), int(iters), C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if self.h:
+            lib().b200_jpeg_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

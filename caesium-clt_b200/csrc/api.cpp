@@ -1,0 +1,374 @@
+// api.cpp -- the C-ABI of include/b200_caesium.h: format dispatch, parameter mapping and error mapping that
+// libcaesium's lib.rs performs behind caesium::{compress,convert,compress_to_size}_in_memory
+// (call sites /root/reference/src/compressor.rs:287-306).  No CPU codec fallback exists anywhere below.
+#include "../../include/b200_caesium.h"
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <exception>
+#include <fstream>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+#include "jpeg_device.h"
+#include "jpeg_host.h"
+
+using namespace b200;
+
+namespace {
+
+b200_status ok_status() { b200_status s; s.code = B200_OK; s.message = nullptr; return s; }
+b200_status make_status(int code, const std::string &msg)
+{   // CaesiumError Display: "{message} [{code}]"
+    b200_status s; s.code = code;
+    std::string m = msg + " [" + std::to_string(code) + "]";
+    s.message = (char *)malloc(m.size() + 1);
+    if (s.message) memcpy(s.message, m.c_str(), m.size() + 1);
+    return s;
+}
+
+std::once_flag g_once;
+std::string g_init_err;
+int g_forced_device = -1, g_forced_ngpus = 0;
+
+bool ensure_runtime(std::string &err)
+{
+    std::call_once(g_once, [] { runtime_init(g_forced_ngpus, g_forced_device, g_init_err); });
+    if (runtime_device_count() <= 0) { err = g_init_err.empty() ? "no CUDA device available; this build has no CPU fallback" : g_init_err; return false; }
+    return true;
+}
+
+void layout_from_geom(const JpegGeom &g, b200_jpeg_layout *l)
+{
+    memset(l, 0, sizeof(*l));
+    l->width = g.width; l->height = g.height; l->ncomp = g.ncomp; l->progressive = g.progressive;
+    for (int c = 0; c < g.ncomp; c++) {
+        l->hs[c] = g.hs[c]; l->vs[c] = g.vs[c]; l->bw[c] = g.bw[c]; l->bh[c] = g.bh[c]; l->rbw[c] = g.rbw[c]; l->rbh[c] = g.rbh[c];
+        l->comp_offset[c] = g.comp_offset[c];
+        memcpy(l->qt[c], g.qt[g.tq[c]], 128);
+    }
+    l->total_coefs = g.total_coefs;
+}
+
+bool geom_from_layout(const b200_jpeg_layout *l, JpegGeom &g, std::string &err)
+{
+    g = JpegGeom();
+    if (!l || l->width <= 0 || l->height <= 0 || (l->ncomp != 1 && l->ncomp != 3)) { err = "invalid JPEG layout"; return false; }
+    g.width = l->width; g.height = l->height; g.ncomp = l->ncomp; g.progressive = l->progressive != 0;
+    int nslots = 0;
+    for (int c = 0; c < l->ncomp; c++) {
+        if (l->hs[c] < 1 || l->hs[c] > 4 || l->vs[c] < 1 || l->vs[c] > 4) { err = "invalid sampling factors"; return false; }
+        g.cid[c] = c + 1; g.hs[c] = l->hs[c]; g.vs[c] = l->vs[c];
+        int slot = -1;
+        for (int t = 0; t < nslots; t++) if (!memcmp(g.qt[t], l->qt[c], 128)) slot = t;
+        if (c == 1 && slot == 0 && nslots == 1) slot = -1;          // keep luma / chroma in separate slots like jpeg_set_defaults
+        if (slot < 0) { slot = nslots++; memcpy(g.qt[slot], l->qt[c], 128); g.qt_present[slot] = true; }
+        g.tq[c] = slot;
+    }
+    g.finalize();
+    for (int c = 0; c < l->ncomp; c++) if (l->bw[c] != g.bw[c] || l->bh[c] != g.bh[c] || l->comp_offset[c] != g.comp_offset[c]) { err = "layout block counts do not match its dimensions"; return false; }
+    return true;
+}
+
+int usable_cores()
+{   // cgroup v2 quota if any (the GPU boxes expose 128 logical CPUs but cap the container), else hardware_concurrency
+    unsigned hc = std::thread::hardware_concurrency(); if (!hc) hc = 1;
+    std::ifstream f("/sys/fs/cgroup/cpu.max");
+    std::string a; long long period = 0;
+    if (f && (f >> a >> period) && a != "max" && period > 0) {
+        long long q = atoll(a.c_str());
+        if (q > 0) { unsigned n = (unsigned)((q + period - 1) / period); if (n >= 1 && n < hc) hc = n; }
+    }
+    return (int)hc;
+}
+
+// ---- JPEG through the device ---------------------------------------------------------------------------------
+b200_status jpeg_compress(const uint8_t *in, size_t in_len, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
+{
+    std::string err;
+    JpegReader rd(in, in_len);
+    if (!rd.read_header(err)) return make_status(B200_ERR_CORRUPT_INPUT, err);
+    const JpegGeom &gin = rd.geom();
+    if (p->width || p->height) return make_status(B200_ERR_UNSUPPORTED, "JPEG resize is not implemented on the GPU path yet");
+    JpegWriteOptions wo; wo.progressive = p->jpeg_progressive != 0; wo.keep_metadata = p->keep_metadata != 0; wo.preserve_icc = p->jpeg_preserve_icc != 0;
+    if (p->jpeg_optimize) {
+        // libcaesium jpeg::lossless: coefficient-domain transcode, nothing numeric to do on the device
+        std::vector<int16_t> coefs((size_t)gin.total_coefs);
+        if (!rd.decode(coefs.data(), err)) return make_status(B200_ERR_CORRUPT_INPUT, err);
+        jpeg_fill_dummy_blocks(gin, coefs.data());
+        wo.copy_jfif = true;
+        if (!jpeg_write(gin, coefs.data(), wo, &rd.meta(), out, err)) return make_status(B200_ERR_INVALID_ARGUMENT, err);
+        return ok_status();
+    }
+    if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
+    JpegGeom gout;
+    if (!jpeg_output_geom(gin, (int)p->jpeg_quality, (int)p->jpeg_chroma_subsampling, gout, err)) return make_status(B200_ERR_INVALID_ARGUMENT, err);
+    ImagePlan plan;
+    if (!plan_image(gin, gout, plan, err)) return make_status(B200_ERR_UNSUPPORTED, err);
+    Slot *s = slot_acquire(prefer_dev < 0 ? runtime_next_device() : prefer_dev, err);
+    if (!s) return make_status(B200_ERR_CUDA, err);
+    b200_status st = ok_status();
+    do {
+        if (!s->ensure(plan.in_bytes, plan.out_bytes, plan.scratch_bytes(), 1 << 14, err)) { st = make_status(B200_ERR_OUT_OF_MEMORY, err); break; }
+        if (!rd.decode(s->h_in, err)) { st = make_status(B200_ERR_CORRUPT_INPUT, err); break; }
+        if (!slot_transform(s, gin, gout, err)) { st = make_status(B200_ERR_CUDA, err); break; }
+        jpeg_fill_dummy_blocks(gout, s->h_out);
+        if (!jpeg_write(gout, s->h_out, wo, &rd.meta(), out, err)) { st = make_status(B200_ERR_INVALID_ARGUMENT, err); break; }
+    } while (0);
+    slot_release(s);
+    return st;
+}
+
+b200_status give(std::vector<uint8_t> &v, uint8_t **out, size_t *out_len)
+{
+    *out = (uint8_t *)malloc(v.size() ? v.size() : 1);
+    if (!*out) return make_status(B200_ERR_OUT_OF_MEMORY, "out of memory");
+    memcpy(*out, v.data(), v.size()); *out_len = v.size();
+    return ok_status();
+}
+
+b200_status compress_dispatch(const uint8_t *in, size_t in_len, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
+{
+    switch (b200_sniff_format(in, in_len)) {
+        case B200_FMT_JPEG: return jpeg_compress(in, in_len, p, prefer_dev, out);
+        case B200_FMT_PNG: return make_status(B200_ERR_UNSUPPORTED, "PNG is not implemented on the GPU path yet");
+        case B200_FMT_WEBP: return make_status(B200_ERR_UNSUPPORTED, "WebP is not implemented on the GPU path yet");
+        case B200_FMT_GIF: return make_status(B200_ERR_UNSUPPORTED, "GIF is outside the GPU path (route to caesium::compress_in_memory)");
+        case B200_FMT_TIFF: return make_status(B200_ERR_UNSUPPORTED, "TIFF is outside the GPU path (route to caesium::compress_in_memory)");
+        default: return make_status(B200_ERR_UNKNOWN_FORMAT, "Unknown file type");
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+void b200_params_default(b200_params *p)
+{   // CSParameters::new(): jpeg q80 auto-subsampling progressive, png q80 level 3, gif 80, webp 60... caesiumclt overwrites the qualities (compressor.rs:415-417)
+    memset(p, 0, sizeof(*p));
+    p->jpeg_quality = 80; p->jpeg_chroma_subsampling = B200_CS_AUTO; p->jpeg_progressive = 1; p->jpeg_preserve_icc = 1;
+    p->png_quality = 80; p->png_optimization_level = 3; p->gif_quality = 80; p->webp_quality = 80;
+}
+
+int b200_init(int n_gpus) { g_forced_ngpus = n_gpus; std::string e; return ensure_runtime(e) ? B200_OK : B200_ERR_NO_DEVICE; }
+int b200_init_device(int ordinal) { g_forced_device = ordinal; std::string e; return ensure_runtime(e) ? B200_OK : B200_ERR_NO_DEVICE; }
+void b200_shutdown(void) { runtime_shutdown(); }
+int b200_device_count(void) { return runtime_device_count(); }
+const char *b200_version(void) { return "b200-caesium 0.1.0 (sm_100a)"; }
+void b200_free(void *p) { free(p); }
+
+uint32_t b200_sniff_format(const uint8_t *d, size_t n)
+{   // the magic numbers `infer` checks (scan_files.rs:30-40, compressor.rs:259-264)
+    if (!d) return B200_FMT_UNKNOWN;
+    if (n >= 3 && d[0] == 0xFF && d[1] == 0xD8 && d[2] == 0xFF) return B200_FMT_JPEG;
+    if (n >= 8 && !memcmp(d, "\x89PNG\r\n\x1a\n", 8)) return B200_FMT_PNG;
+    if (n >= 6 && (!memcmp(d, "GIF87a", 6) || !memcmp(d, "GIF89a", 6))) return B200_FMT_GIF;
+    if (n >= 12 && !memcmp(d, "RIFF", 4) && !memcmp(d + 8, "WEBP", 4)) return B200_FMT_WEBP;
+    if (n >= 4 && (!memcmp(d, "II*\0", 4) || !memcmp(d, "MM\0*", 4))) return B200_FMT_TIFF;
+    return B200_FMT_UNKNOWN;
+}
+
+b200_status b200_compress_in_memory(const uint8_t *in, size_t in_len, const b200_params *params, uint8_t **out, size_t *out_len)
+{
+    if (!in || !params || !out || !out_len) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr; *out_len = 0;
+    try {
+        std::vector<uint8_t> v;
+        b200_status s = compress_dispatch(in, in_len, params, -1, v);
+        if (s.code) return s;
+        return give(v, out, out_len);
+    } catch (const std::exception &e) { return make_status(B200_ERR_OUT_OF_MEMORY, e.what()); } catch (...) { return make_status(B200_ERR_INVALID_ARGUMENT, "unexpected failure"); }
+}
+
+b200_status b200_convert_in_memory(const uint8_t *in, size_t in_len, const b200_params *params, uint32_t fmt, uint8_t **out, size_t *out_len)
+{
+    if (!in || !params || !out || !out_len) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr; *out_len = 0;
+    uint32_t src = b200_sniff_format(in, in_len);
+    if (src == B200_FMT_UNKNOWN) return make_status(B200_ERR_UNKNOWN_FORMAT, "Unknown file type");
+    if (src == fmt) return make_status(B200_ERR_SAME_FORMAT, "Cannot convert to the same format");
+    return make_status(B200_ERR_UNSUPPORTED, "format conversion is not implemented on the GPU path yet");
+}
+
+b200_status b200_compress_to_size_in_memory(const uint8_t *in, size_t in_len, b200_params *params, size_t max_output_size, uint8_t return_smallest,
+                                            uint8_t **out, size_t *out_len)
+{
+    if (!in || !params || !out || !out_len) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr; *out_len = 0;
+    try {
+        // libcaesium compress_to_size: input already small enough is returned unchanged; otherwise bisect quality in
+        // [1, 100] from 80 (at most 10 tries, 2 % tolerance), keeping the largest result under the limit.
+        if (in_len <= max_output_size) { std::vector<uint8_t> v(in, in + in_len); return give(v, out, out_len); }
+        uint32_t fmt = b200_sniff_format(in, in_len);
+        if (fmt != B200_FMT_JPEG) return make_status(fmt == B200_FMT_UNKNOWN ? B200_ERR_UNKNOWN_FORMAT : B200_ERR_UNSUPPORTED, "compress_to_size is implemented for JPEG only on the GPU path");
+        const size_t tolerance = max_output_size / 50;
+        int lo = 1, hi = 100, q = 80;
+        std::vector<uint8_t> best, smallest, cur;
+        for (int tries = 0; tries < 10 && lo <= hi; tries++) {
+            b200_params p = *params; p.jpeg_quality = (uint32_t)q; p.jpeg_optimize = 0;
+            b200_status s = compress_dispatch(in, in_len, &p, -1, cur);
+            if (s.code) return s;
+            if (smallest.empty() || cur.size() < smallest.size()) smallest = cur;
+            if (cur.size() <= max_output_size) {
+                if (cur.size() > best.size()) { best = cur; params->jpeg_quality = (uint32_t)q; }
+                if (max_output_size - cur.size() <= tolerance) break;
+                lo = q + 1;
+            } else hi = q - 1;
+            q = (lo + hi) / 2;
+        }
+        if (!best.empty()) return give(best, out, out_len);
+        if (return_smallest && !smallest.empty()) return give(smallest, out, out_len);
+        return make_status(B200_ERR_TOO_LARGE, "Cannot compress to desired size");
+    } catch (const std::exception &e) { return make_status(B200_ERR_OUT_OF_MEMORY, e.what()); } catch (...) { return make_status(B200_ERR_INVALID_ARGUMENT, "unexpected failure"); }
+}
+
+int b200_compress_batch(const uint8_t *const *in, const size_t *in_len, int n, const b200_params *params, int n_threads,
+                        uint8_t **out, size_t *out_len, b200_status *status)
+{
+    if (!in || !in_len || !params || !out || !out_len || !status || n < 0) return -1;
+    if (n_threads <= 0) n_threads = usable_cores();
+    if (n_threads > n) n_threads = n;
+    std::atomic<int> next{0}, failed{0};
+    const int ndev = std::max(1, runtime_device_count());
+    auto worker = [&]() {
+        for (;;) {
+            int i = next.fetch_add(1);
+            if (i >= n) break;
+            out[i] = nullptr; out_len[i] = 0;
+            try {
+                std::vector<uint8_t> v;
+                status[i] = compress_dispatch(in[i], in_len[i], params, i % ndev, v);
+                if (!status[i].code) status[i] = give(v, &out[i], &out_len[i]);
+            } catch (const std::exception &e) { status[i] = make_status(B200_ERR_OUT_OF_MEMORY, e.what()); } catch (...) { status[i] = make_status(B200_ERR_INVALID_ARGUMENT, "unexpected failure"); }
+            if (status[i].code) failed++;
+        }
+    };
+    { std::string e; ensure_runtime(e); }
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; t++) th.emplace_back(worker);
+    worker();
+    for (auto &t : th) t.join();
+    return failed.load();
+}
+
+// ---- JPEG stage entry points ------------------------------------------------------------------------------------
+b200_status b200_jpeg_decode_coefficients(const uint8_t *in, size_t in_len, b200_jpeg_layout *layout, int16_t **coefs)
+{
+    if (!in || !layout || !coefs) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    *coefs = nullptr;
+    std::string err;
+    JpegReader rd(in, in_len);
+    if (!rd.read_header(err)) return make_status(B200_ERR_CORRUPT_INPUT, err);
+    int16_t *c = (int16_t *)malloc((size_t)rd.geom().total_coefs * 2 + 16);
+    if (!c) return make_status(B200_ERR_OUT_OF_MEMORY, "out of memory");
+    if (!rd.decode(c, err)) { free(c); return make_status(B200_ERR_CORRUPT_INPUT, err); }
+    layout_from_geom(rd.geom(), layout);
+    *coefs = c;
+    return ok_status();
+}
+
+b200_status b200_jpeg_output_layout(const b200_jpeg_layout *in_layout, const b200_params *params, b200_jpeg_layout *out_layout)
+{
+    if (!in_layout || !params || !out_layout) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    std::string err; JpegGeom gin, gout;
+    if (!geom_from_layout(in_layout, gin, err)) return make_status(B200_ERR_INVALID_ARGUMENT, err);
+    if (!jpeg_output_geom(gin, (int)params->jpeg_quality, (int)params->jpeg_chroma_subsampling, gout, err)) return make_status(B200_ERR_INVALID_ARGUMENT, err);
+    gout.progressive = params->jpeg_progressive != 0;
+    layout_from_geom(gout, out_layout);
+    return ok_status();
+}
+
+b200_status b200_jpeg_requantize(const b200_jpeg_layout *in_layout, const int16_t *in_coefs, const b200_jpeg_layout *out_layout, int16_t *out_coefs)
+{
+    if (!in_layout || !in_coefs || !out_layout || !out_coefs) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    std::string err; JpegGeom gin, gout;
+    if (!geom_from_layout(in_layout, gin, err) || !geom_from_layout(out_layout, gout, err)) return make_status(B200_ERR_INVALID_ARGUMENT, err);
+    if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
+    ImagePlan plan;
+    if (!plan_image(gin, gout, plan, err)) return make_status(B200_ERR_UNSUPPORTED, err);
+    Slot *s = slot_acquire(runtime_next_device(), err);
+    if (!s) return make_status(B200_ERR_CUDA, err);
+    b200_status st = ok_status();
+    do {
+        if (!s->ensure(plan.in_bytes, plan.out_bytes, plan.scratch_bytes(), 1 << 14, err)) { st = make_status(B200_ERR_OUT_OF_MEMORY, err); break; }
+        memcpy(s->h_in, in_coefs, plan.in_bytes);
+        memset(s->h_out, 0, plan.out_bytes);
+        if (!slot_transform(s, gin, gout, err)) { st = make_status(B200_ERR_CUDA, err); break; }
+        jpeg_fill_dummy_blocks(gout, s->h_out);
+        memcpy(out_coefs, s->h_out, plan.out_bytes);
+    } while (0);
+    slot_release(s);
+    return st;
+}
+
+b200_status b200_jpeg_encode_coefficients(const b200_jpeg_layout *layout, const int16_t *coefs, int progressive, uint8_t **out, size_t *out_len)
+{
+    if (!layout || !coefs || !out || !out_len) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    std::string err; JpegGeom g;
+    if (!geom_from_layout(layout, g, err)) return make_status(B200_ERR_INVALID_ARGUMENT, err);
+    JpegWriteOptions wo; wo.progressive = progressive != 0;
+    std::vector<uint8_t> v;
+    if (!jpeg_write(g, coefs, wo, nullptr, v, err)) return make_status(B200_ERR_INVALID_ARGUMENT, err);
+    return give(v, out, out_len);
+}
+
+b200_status b200_jpeg_decode_planes(const b200_jpeg_layout *in_layout, const int16_t *in_coefs, uint8_t *planes)
+{
+    if (!in_layout || !in_coefs || !planes) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    std::string err; JpegGeom gin;
+    if (!geom_from_layout(in_layout, gin, err)) return make_status(B200_ERR_INVALID_ARGUMENT, err);
+    if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
+    Slot *s = slot_acquire(runtime_next_device(), err);
+    if (!s) return make_status(B200_ERR_CUDA, err);
+    b200_status st = ok_status();
+    do {
+        if (!s->ensure((size_t)gin.total_coefs * 2, 256, 256, 1 << 14, err)) { st = make_status(B200_ERR_OUT_OF_MEMORY, err); break; }
+        memcpy(s->h_in, in_coefs, (size_t)gin.total_coefs * 2);
+        if (!slot_decode_planes(s, gin, planes, err)) { st = make_status(B200_ERR_CUDA, err); break; }
+    } while (0);
+    slot_release(s);
+    return st;
+}
+
+void b200_jpeg_quant_table(int quality, int which, uint16_t out[64]) { jpeg_quant_table(quality, which, out); }
+
+// ---- megabatch --------------------------------------------------------------------------------------------------
+struct b200_jpeg_batch { JpegBatch *b; };
+
+b200_status b200_jpeg_batch_create(const b200_jpeg_layout *in_layout, const b200_jpeg_layout *out_layout, int n, b200_jpeg_batch **batch)
+{
+    if (!in_layout || !out_layout || !batch) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    *batch = nullptr;
+    std::string err; JpegGeom gin, gout;
+    if (!geom_from_layout(in_layout, gin, err) || !geom_from_layout(out_layout, gout, err)) return make_status(B200_ERR_INVALID_ARGUMENT, err);
+    if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
+    JpegBatch *b = batch_create(gin, gout, n, err);
+    if (!b) return make_status(B200_ERR_CUDA, err);
+    *batch = new b200_jpeg_batch{b};
+    return ok_status();
+}
+b200_status b200_jpeg_batch_upload(b200_jpeg_batch *b, int index, const int16_t *in_coefs)
+{
+    std::string err; if (!b || !in_coefs) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    return batch_upload(b->b, index, in_coefs, err) ? ok_status() : make_status(B200_ERR_CUDA, err);
+}
+b200_status b200_jpeg_batch_run(b200_jpeg_batch *b, void *cuda_stream, int *launches)
+{
+    std::string err; if (!b) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    return batch_run(b->b, cuda_stream, 0, launches, err) ? ok_status() : make_status(B200_ERR_CUDA, err);
+}
+b200_status b200_jpeg_batch_download(b200_jpeg_batch *b, int index, int16_t *out_coefs)
+{
+    std::string err; if (!b || !out_coefs) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    return batch_download(b->b, index, out_coefs, err) ? ok_status() : make_status(B200_ERR_CUDA, err);
+}
+b200_status b200_jpeg_batch_time(b200_jpeg_batch *b, int which, int iters, float *ms_per_run)
+{
+    std::string err; if (!b || !ms_per_run) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    return batch_time(b->b, which, iters, ms_per_run, err) ? ok_status() : make_status(B200_ERR_CUDA, err);
+}
+void b200_jpeg_batch_destroy(b200_jpeg_batch *b) { if (b) { batch_destroy(b->b); delete b; } }
+
+} // extern "C"

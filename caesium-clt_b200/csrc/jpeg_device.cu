@@ -1,0 +1,375 @@
+// jpeg_device.cu -- see jpeg_device.h.  Device runtime for the JPEG path of caesium::compress_in_memory
+// (/root/reference/src/compressor.rs:305): one pool of "slots" per GPU so that the blocking, one-image-per-thread
+// callers of the reference's rayon map (compressor.rs:81-83) each get a private stream, pinned staging buffers and
+// HBM buffers; images are sharded round-robin over the initialised GPUs (no cross-GPU traffic on this path).
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include <atomic>
+#include "jpeg_device.h"
+
+namespace b200 {
+
+#define CU(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(e_); return false; } } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+bool plan_image(const JpegGeom &gin, const JpegGeom &gout, ImagePlan &p, std::string &err)
+{
+    p = ImagePlan();
+    if (gin.ncomp != gout.ncomp || gin.width != gout.width || gin.height != gout.height) { err = "geometry mismatch between decode and encode side"; return false; }
+    p.in_bytes = (size_t)gin.total_coefs * 2; p.out_bytes = (size_t)gout.total_coefs * 2;
+    size_t off_plane = 0, off_full = 0, off_d = 0;
+    for (int c = 0; c < gin.ncomp; c++) {
+        if (gin.hmax % gin.hs[c] || gin.vmax % gin.vs[c] || gout.hmax % gout.hs[c] || gout.vmax % gout.vs[c]) { err = "fractional sampling ratio unsupported"; return false; }
+        int uhx = gin.hmax / gin.hs[c], uvx = gin.vmax / gin.vs[c], dhx = gout.hmax / gout.hs[c], dvx = gout.vmax / gout.vs[c];
+        if (uhx == 1 && uvx == 1 && dhx == 1 && dvx == 1) p.path[c] = PATH_FUSED;
+        else if (uhx == 2 && uvx == 2 && dhx == 2 && dvx == 2) p.path[c] = PATH_C420;
+        else p.path[c] = PATH_GENERIC;
+        if (p.path[c] != PATH_FUSED) { p.plane_off[c] = off_plane; off_plane += align_up((size_t)gin.bw[c] * 8 * gin.bh[c] * 8, 256); }
+        if (p.path[c] == PATH_GENERIC) {
+            p.full_off[c] = off_full; off_full += align_up((size_t)gin.width * gin.height, 256);
+            p.dplane_off[c] = off_d; off_d += align_up((size_t)gout.rbw[c] * 8 * gout.rbh[c] * 8, 256);
+        }
+    }
+    p.plane_bytes = off_plane; p.full_bytes = off_full; p.dplane_bytes = off_d;
+    return true;
+}
+
+void append_image_work(const JpegGeom &gin, const JpegGeom &gout, const ImagePlan &plan,
+                       const int16_t *d_in, int16_t *d_out, uint8_t *d_scratch,
+                       const uint16_t *d_dq, const QuantDev *d_q, WorkLists &wl)
+{
+    for (int c = 0; c < gin.ncomp; c++) {
+        CompWork w; memset(&w, 0, sizeof(w));
+        w.cin = d_in + gin.comp_offset[c]; w.cout = d_out + gout.comp_offset[c];
+        w.dq = d_dq + 64 * c; w.q = d_q + gout.tq[c];
+        w.bw_in = gin.bw[c]; w.bh_in = gin.bh[c]; w.rbw_in = gin.rbw[c]; w.rbh_in = gin.rbh[c]; w.cw = gin.cw[c]; w.ch = gin.ch[c];
+        w.bw_out = gout.bw[c]; w.bh_out = gout.bh[c]; w.rbw_out = gout.rbw[c]; w.rbh_out = gout.rbh[c];
+        w.W = gin.width; w.H = gin.height;
+        w.pstride = gin.bw[c] * 8; w.fstride = gin.width;
+        w.up_hx = gin.hmax / gin.hs[c]; w.up_vx = gin.vmax / gin.vs[c];
+        w.dn_hx = gout.hmax / gout.hs[c]; w.dn_vx = gout.vmax / gout.vs[c];
+        if (plan.path[c] != PATH_FUSED) w.plane = d_scratch + plan.plane_off[c];
+        if (plan.path[c] == PATH_GENERIC) {
+            w.full = d_scratch + plan.plane_bytes + plan.full_off[c];
+            w.dplane = d_scratch + plan.plane_bytes + plan.full_bytes + plan.dplane_off[c];
+        }
+        const int t_in = work_tiles(w.rbw_in, w.rbh_in), t_out = work_tiles(w.rbw_out, w.rbh_out);
+        switch (plan.path[c]) {
+            case PATH_FUSED: wl.fused.push_back(w); wl.max_fused = std::max(wl.max_fused, t_out); break;
+            case PATH_C420:
+                wl.idct.push_back(w); wl.max_idct = std::max(wl.max_idct, t_in);
+                wl.c420.push_back(w); wl.max_c420 = std::max(wl.max_c420, t_out);
+                break;
+            default:
+                wl.idct.push_back(w); wl.max_idct = std::max(wl.max_idct, t_in);
+                wl.up.push_back(w); wl.max_up_w = std::max(wl.max_up_w, w.W); wl.max_up_h = std::max(wl.max_up_h, w.H);
+                wl.down.push_back(w); wl.max_dn_w = std::max(wl.max_dn_w, w.rbw_out * 8); wl.max_dn_h = std::max(wl.max_dn_h, w.rbh_out * 8);
+                wl.fdct.push_back(w); wl.max_fdct = std::max(wl.max_fdct, t_out);
+        }
+    }
+}
+
+size_t flatten_work(const WorkLists &wl, CompWork *h)
+{
+    size_t n = 0;
+    for (const auto *v : {&wl.fused, &wl.idct, &wl.c420, &wl.up, &wl.down, &wl.fdct}) { if (!v->empty()) memcpy(h + n, v->data(), v->size() * sizeof(CompWork)); n += v->size(); }
+    return n;
+}
+
+int launch_work(const WorkLists &wl, const CompWork *d, void *stream, int which, int *launches)
+{
+    int rc = 0, n = 0;
+    const CompWork *p_fused = d, *p_idct = p_fused + wl.fused.size(), *p_c420 = p_idct + wl.idct.size();
+    const CompWork *p_up = p_c420 + wl.c420.size(), *p_down = p_up + wl.up.size(), *p_fdct = p_down + wl.down.size();
+    if ((which == 0 || which == 1) && !wl.fused.empty()) { rc = launch_fused_same(p_fused, (int)wl.fused.size(), wl.max_fused, stream); n++; if (rc) return rc; }
+    if ((which == 0 || which == 2) && !wl.idct.empty()) { rc = launch_idct_plane(p_idct, (int)wl.idct.size(), wl.max_idct, stream); n++; if (rc) return rc; }
+    if ((which == 0 || which == 3) && !wl.c420.empty()) { rc = launch_chroma420_refdct(p_c420, (int)wl.c420.size(), wl.max_c420, stream); n++; if (rc) return rc; }
+    if (which == 0 || which == 3) {
+        if (!wl.up.empty()) { rc = launch_upsample(p_up, (int)wl.up.size(), wl.max_up_w, wl.max_up_h, stream); n++; if (rc) return rc; }
+        if (!wl.down.empty()) { rc = launch_downsample(p_down, (int)wl.down.size(), wl.max_dn_w, wl.max_dn_h, stream); n++; if (rc) return rc; }
+        if (!wl.fdct.empty()) { rc = launch_fdct_plane(p_fdct, (int)wl.fdct.size(), wl.max_fdct, stream); n++; if (rc) return rc; }
+    }
+    if (launches) *launches = n;
+    return 0;
+}
+
+// ================================================================================================================
+// runtime: devices and slots
+// ================================================================================================================
+namespace {
+struct DevicePool {
+    int ordinal = 0;
+    std::mutex mu; std::condition_variable cv;
+    std::vector<Slot *> free_slots; int created = 0; int max_slots = 48;
+};
+std::mutex g_mu;
+std::vector<DevicePool *> g_devs;
+std::atomic<unsigned> g_rr{0};
+bool g_inited = false;
+}
+
+int runtime_init(int n_gpus, int only_device, std::string &err)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_inited) return (int)g_devs.size();
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) { err = std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") + "); this build has no CPU fallback"; return 0; }
+    std::vector<int> ords;
+    if (only_device >= 0) { if (only_device >= count) { err = "CUDA device ordinal out of range"; return 0; } ords.push_back(only_device); }
+    else { int n = n_gpus <= 0 ? count : std::min(n_gpus, count); for (int i = 0; i < n; i++) ords.push_back(i); }
+    for (int o : ords) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, o) != cudaSuccess) { err = "cudaGetDeviceProperties failed"; return 0; }
+        if (prop.major != 10) { err = "device " + std::to_string(o) + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + "; this library ships sm_100a kernels only"; for (auto *d : g_devs) delete d; g_devs.clear(); return 0; }
+        auto *d = new DevicePool(); d->ordinal = o; g_devs.push_back(d);
+    }
+    g_inited = true;
+    return (int)g_devs.size();
+}
+
+void runtime_shutdown()
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto *d : g_devs) {
+        cudaSetDevice(d->ordinal);
+        for (Slot *s : d->free_slots) {
+            if (s->stream) cudaStreamDestroy((cudaStream_t)s->stream);
+            cudaFreeHost(s->h_in); cudaFreeHost(s->h_out); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_scratch); cudaFreeHost(s->h_par); cudaFree(s->d_par);
+            delete s;
+        }
+        delete d;
+    }
+    g_devs.clear(); g_inited = false;
+}
+
+int runtime_device_count() { std::lock_guard<std::mutex> lk(g_mu); return g_inited ? (int)g_devs.size() : 0; }
+int runtime_next_device() { size_t n = g_devs.size(); return n ? (int)(g_rr.fetch_add(1) % n) : 0; }
+
+Slot *slot_acquire(int prefer, std::string &err)
+{
+    if (g_devs.empty()) { err = "library not initialised (no CUDA device)"; return nullptr; }
+    DevicePool *d = g_devs[(size_t)prefer % g_devs.size()];
+    std::unique_lock<std::mutex> lk(d->mu);
+    for (;;) {
+        if (!d->free_slots.empty()) { Slot *s = d->free_slots.back(); d->free_slots.pop_back(); lk.unlock(); cudaSetDevice(d->ordinal); return s; }
+        if (d->created < d->max_slots) {
+            d->created++; lk.unlock();
+            cudaSetDevice(d->ordinal);
+            Slot *s = new Slot(); s->dev = (int)((size_t)prefer % g_devs.size());
+            cudaStream_t st;
+            if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { delete s; err = "cudaStreamCreate failed"; lk.lock(); d->created--; return nullptr; }
+            s->stream = st;
+            return s;
+        }
+        d->cv.wait(lk);
+    }
+}
+
+void slot_release(Slot *s)
+{
+    if (!s) return;
+    DevicePool *d = g_devs[(size_t)s->dev];
+    { std::lock_guard<std::mutex> lk(d->mu); d->free_slots.push_back(s); }
+    d->cv.notify_one();
+}
+
+template <typename T> static bool grow_host(T *&p, size_t &cap, size_t need, std::string &err)
+{
+    if (need <= cap) return true;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = align_up(need + need / 8, 1 << 16);
+    void *q = nullptr;
+    cudaError_t e = cudaHostAlloc(&q, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) { err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); return false; }
+    p = (T *)q; cap = want; return true;
+}
+template <typename T> static bool grow_dev(T *&p, size_t &cap, size_t need, std::string &err)
+{
+    if (need <= cap) return true;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = align_up(need + need / 8, 1 << 16);
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, want);
+    if (e != cudaSuccess) { err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return false; }
+    p = (T *)q; cap = want; return true;
+}
+
+bool Slot::ensure(size_t in_bytes, size_t out_bytes, size_t scratch_bytes, size_t par_bytes, std::string &err)
+{
+    return grow_host(h_in, h_in_cap, in_bytes, err) && grow_host(h_out, h_out_cap, out_bytes, err) &&
+           grow_dev(d_in, d_in_cap, in_bytes, err) && grow_dev(d_out, d_out_cap, out_bytes, err) &&
+           grow_dev(d_scratch, d_scratch_cap, std::max<size_t>(scratch_bytes, 256), err) &&
+           grow_host(h_par, par_cap, par_bytes, err) && grow_dev(d_par, d_par_cap, par_bytes, err);
+}
+
+// parameter block layout: QuantDev q[4] | uint16 dq[4][64] | CompWork work[...]
+static const size_t PAR_Q = 0, PAR_DQ = sizeof(QuantDev) * 4, PAR_WORK = PAR_DQ + sizeof(uint16_t) * 256;
+static size_t par_bytes_for(size_t nwork) { return PAR_WORK + nwork * sizeof(CompWork); }
+
+static void fill_tables(uint8_t *h_par, const JpegGeom &gin, const JpegGeom *gout)
+{
+    QuantDev *q = reinterpret_cast<QuantDev *>(h_par + PAR_Q);
+    uint16_t *dq = reinterpret_cast<uint16_t *>(h_par + PAR_DQ);
+    if (gout) for (int t = 0; t < 4; t++) if (gout->qt_present[t]) make_quant_dev(gout->qt[t], &q[t]);
+    for (int c = 0; c < gin.ncomp; c++) memcpy(dq + 64 * c, gin.qt[gin.tq[c]], 128);
+}
+
+bool slot_transform(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err)
+{
+    ImagePlan plan;
+    if (!plan_image(gin, gout, plan, err)) return false;
+    cudaStream_t st = (cudaStream_t)s->stream;
+    const size_t pbytes = par_bytes_for(4 * 6);
+    if (!s->ensure(plan.in_bytes, plan.out_bytes, plan.scratch_bytes(), pbytes, err)) return false;
+    fill_tables(s->h_par, gin, &gout);
+    WorkLists wl;
+    append_image_work(gin, gout, plan, s->d_in, s->d_out, s->d_scratch,
+                      reinterpret_cast<const uint16_t *>(s->d_par + PAR_DQ), reinterpret_cast<const QuantDev *>(s->d_par + PAR_Q), wl);
+    size_t nw = flatten_work(wl, reinterpret_cast<CompWork *>(s->h_par + PAR_WORK));
+    CU(cudaMemcpyAsync(s->d_par, s->h_par, par_bytes_for(nw), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s->d_in, s->h_in, plan.in_bytes, cudaMemcpyHostToDevice, st));
+    int rc = launch_work(wl, reinterpret_cast<const CompWork *>(s->d_par + PAR_WORK), st, 0, nullptr);
+    if (rc) { err = std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)rc); return false; }
+    CU(cudaMemcpyAsync(s->h_out, s->d_out, plan.out_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return true;
+}
+
+bool slot_decode_planes(Slot *s, const JpegGeom &gin, uint8_t *planes, std::string &err)
+{
+    // route every component through idct (+ upsample) by planning against a 4:4:4 output of the same size
+    JpegGeom gout = gin;
+    for (int c = 0; c < gin.ncomp; c++) { gout.hs[c] = gout.vs[c] = 1; }
+    gout.finalize();
+    cudaStream_t st = (cudaStream_t)s->stream;
+    ImagePlan plan; plan = ImagePlan();
+    size_t off_plane = 0, off_full = 0;
+    for (int c = 0; c < gin.ncomp; c++) {
+        if (gin.hmax % gin.hs[c] || gin.vmax % gin.vs[c]) { err = "fractional sampling ratio unsupported"; return false; }
+        plan.path[c] = PATH_GENERIC;
+        plan.plane_off[c] = off_plane; off_plane += align_up((size_t)gin.bw[c] * 8 * gin.bh[c] * 8, 256);
+        plan.full_off[c] = off_full; off_full += align_up((size_t)gin.width * gin.height, 256);
+    }
+    plan.plane_bytes = off_plane; plan.full_bytes = off_full; plan.dplane_bytes = 0;
+    plan.in_bytes = (size_t)gin.total_coefs * 2; plan.out_bytes = 256;
+    const size_t pbytes = par_bytes_for(4 * 6);
+    if (!s->ensure(plan.in_bytes, std::max(plan.out_bytes, plan.full_bytes), plan.scratch_bytes(), pbytes, err)) return false;
+    fill_tables(s->h_par, gin, nullptr);
+    WorkLists wl;
+    append_image_work(gin, gout, plan, s->d_in, s->d_out, s->d_scratch,
+                      reinterpret_cast<const uint16_t *>(s->d_par + PAR_DQ), reinterpret_cast<const QuantDev *>(s->d_par + PAR_Q), wl);
+    wl.down.clear(); wl.fdct.clear();
+    size_t nw = flatten_work(wl, reinterpret_cast<CompWork *>(s->h_par + PAR_WORK));
+    CU(cudaMemcpyAsync(s->d_par, s->h_par, par_bytes_for(nw), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s->d_in, s->h_in, plan.in_bytes, cudaMemcpyHostToDevice, st));
+    int rc = launch_work(wl, reinterpret_cast<const CompWork *>(s->d_par + PAR_WORK), st, 0, nullptr);
+    if (rc) { err = std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)rc); return false; }
+    uint8_t *h = reinterpret_cast<uint8_t *>(s->h_out);
+    for (int c = 0; c < gin.ncomp; c++)
+        CU(cudaMemcpyAsync(h + (size_t)c * gin.width * gin.height, s->d_scratch + plan.plane_bytes + plan.full_off[c], (size_t)gin.width * gin.height, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(planes, h, (size_t)gin.ncomp * gin.width * gin.height);
+    return true;
+}
+
+// ================================================================================================================
+// megabatch
+// ================================================================================================================
+JpegBatch *batch_create(const JpegGeom &gin, const JpegGeom &gout, int n, std::string &err)
+{
+    if (g_devs.empty()) { err = "library not initialised (no CUDA device)"; return nullptr; }
+    if (n <= 0) { err = "empty batch"; return nullptr; }
+    auto *b = new JpegBatch();
+    b->dev = 0; b->n = n; b->gin = gin; b->gout = gout;
+    auto fail = [&](const std::string &m) -> JpegBatch * { err = m; batch_destroy(b); return nullptr; };
+    if (!plan_image(gin, gout, b->plan, err)) { batch_destroy(b); return nullptr; }
+    cudaSetDevice(g_devs[0]->ordinal);
+    const size_t in_b = align_up(b->plan.in_bytes, 256), out_b = align_up(b->plan.out_bytes, 256), sc_b = align_up(std::max<size_t>(b->plan.scratch_bytes(), 256), 256);
+    void *p = nullptr;
+    if (cudaMalloc(&p, in_b * n) != cudaSuccess) return fail("cudaMalloc (batch input) failed"); b->d_in = (int16_t *)p;
+    if (cudaMalloc(&p, out_b * n) != cudaSuccess) return fail("cudaMalloc (batch output) failed"); b->d_out = (int16_t *)p;
+    if (cudaMalloc(&p, sc_b * n) != cudaSuccess) return fail("cudaMalloc (batch scratch) failed"); b->d_scratch = (uint8_t *)p;
+    cudaStream_t st; if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed"); b->stream = st;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); b->ev0 = e0; b->ev1 = e1;
+    size_t nwork_max = (size_t)n * 4 * 6;
+    size_t pbytes = par_bytes_for(nwork_max);
+    std::vector<uint8_t> hpar(pbytes);
+    if (cudaMalloc(&p, pbytes) != cudaSuccess) return fail("cudaMalloc (batch params) failed"); b->d_par = (uint8_t *)p;
+    fill_tables(hpar.data(), gin, &gout);
+    for (int i = 0; i < n; i++)
+        append_image_work(gin, gout, b->plan, (const int16_t *)((const uint8_t *)b->d_in + in_b * i), (int16_t *)((uint8_t *)b->d_out + out_b * i), b->d_scratch + sc_b * i,
+                          reinterpret_cast<const uint16_t *>(b->d_par + PAR_DQ), reinterpret_cast<const QuantDev *>(b->d_par + PAR_Q), b->wl);
+    size_t nw = flatten_work(b->wl, reinterpret_cast<CompWork *>(hpar.data() + PAR_WORK));
+    if (cudaMemcpy(b->d_par, hpar.data(), par_bytes_for(nw), cudaMemcpyHostToDevice) != cudaSuccess) return fail("cudaMemcpy (batch params) failed");
+    b->d_work = reinterpret_cast<const CompWork *>(b->d_par + PAR_WORK);
+    cudaMemset(b->d_in, 0, in_b * n);
+    return b;
+}
+
+bool batch_upload(JpegBatch *b, int idx, const int16_t *coefs, std::string &err)
+{
+    if (!b || idx < 0 || idx >= b->n) { err = "bad batch index"; return false; }
+    cudaSetDevice(g_devs[0]->ordinal);
+    const size_t in_b = align_up(b->plan.in_bytes, 256);
+    CU(cudaMemcpy((uint8_t *)b->d_in + in_b * idx, coefs, b->plan.in_bytes, cudaMemcpyHostToDevice));
+    return true;
+}
+
+bool batch_run(JpegBatch *b, void *stream, int which, int *launches, std::string &err)
+{
+    if (!b) { err = "null batch"; return false; }
+    cudaSetDevice(g_devs[0]->ordinal);
+    int rc = launch_work(b->wl, b->d_work, stream ? stream : b->stream, which, launches);
+    if (rc) { err = std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)rc); return false; }
+    return true;
+}
+
+bool batch_download(JpegBatch *b, int idx, int16_t *coefs, std::string &err)
+{
+    if (!b || idx < 0 || idx >= b->n) { err = "bad batch index"; return false; }
+    cudaSetDevice(g_devs[0]->ordinal);
+    CU(cudaStreamSynchronize((cudaStream_t)b->stream));
+    CU(cudaDeviceSynchronize());
+    const size_t out_b = align_up(b->plan.out_bytes, 256);
+    CU(cudaMemcpy(coefs, (uint8_t *)b->d_out + out_b * idx, b->plan.out_bytes, cudaMemcpyDeviceToHost));
+    return true;
+}
+
+bool batch_time(JpegBatch *b, int which, int iters, float *ms, std::string &err)
+{
+    if (!b || iters <= 0) { err = "bad arguments"; return false; }
+    cudaSetDevice(g_devs[0]->ordinal);
+    cudaStream_t st = (cudaStream_t)b->stream;
+    CU(cudaStreamSynchronize(st));
+    CU(cudaEventRecord((cudaEvent_t)b->ev0, st));
+    for (int i = 0; i < iters; i++) {
+        int rc = launch_work(b->wl, b->d_work, st, which, nullptr);
+        if (rc) { err = std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)rc); return false; }
+    }
+    CU(cudaEventRecord((cudaEvent_t)b->ev1, st));
+    CU(cudaEventSynchronize((cudaEvent_t)b->ev1));
+    float t = 0; CU(cudaEventElapsedTime(&t, (cudaEvent_t)b->ev0, (cudaEvent_t)b->ev1));
+    *ms = t / iters;
+    return true;
+}
+
+void batch_destroy(JpegBatch *b)
+{
+    if (!b) return;
+    if (!g_devs.empty()) cudaSetDevice(g_devs[0]->ordinal);
+    cudaFree(b->d_in); cudaFree(b->d_out); cudaFree(b->d_scratch); cudaFree(b->d_par);
+    if (b->stream) cudaStreamDestroy((cudaStream_t)b->stream);
+    if (b->ev0) cudaEventDestroy((cudaEvent_t)b->ev0);
+    if (b->ev1) cudaEventDestroy((cudaEvent_t)b->ev1);
+    delete b;
+}
+
+} // namespace b200

@@ -1,0 +1,80 @@
+// jpeg_device.h -- device side of the JPEG path: per-GPU slot pools (stream + pinned staging + HBM buffers),
+// work-list construction for the transform kernels, and the device-resident megabatch.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <string>
+#include <vector>
+#include "jpeg_host.h"
+#include "jpeg_kernels.h"
+
+namespace b200 {
+
+enum CompPath { PATH_FUSED = 0, PATH_C420 = 1, PATH_GENERIC = 2 };
+
+// Per-image HBM footprint and per-component routing for an (input geometry, output geometry) pair.
+struct ImagePlan {
+    int path[4] = {0, 0, 0, 0};
+    size_t in_bytes = 0, out_bytes = 0;
+    size_t plane_off[4] = {0}, full_off[4] = {0}, dplane_off[4] = {0};
+    size_t plane_bytes = 0, full_bytes = 0, dplane_bytes = 0;
+    size_t scratch_bytes() const { return plane_bytes + full_bytes + dplane_bytes; }
+};
+bool plan_image(const JpegGeom &gin, const JpegGeom &gout, ImagePlan &plan, std::string &err);
+
+// Work lists for one launch group (any number of images).
+struct WorkLists {
+    std::vector<CompWork> fused, idct, c420, up, down, fdct;
+    int max_fused = 0, max_idct = 0, max_c420 = 0, max_fdct = 0, max_up_w = 0, max_up_h = 0, max_dn_w = 0, max_dn_h = 0;
+    size_t total() const { return fused.size() + idct.size() + c420.size() + up.size() + down.size() + fdct.size(); }
+    void clear() { fused.clear(); idct.clear(); c420.clear(); up.clear(); down.clear(); fdct.clear(); max_fused = max_idct = max_c420 = max_fdct = max_up_w = max_up_h = max_dn_w = max_dn_h = 0; }
+};
+// Append one image's work.  d_dq: device uint16[4][64] (per input component, zigzag); d_q: device QuantDev[4] (per output slot).
+void append_image_work(const JpegGeom &gin, const JpegGeom &gout, const ImagePlan &plan,
+                       const int16_t *d_in, int16_t *d_out, uint8_t *d_scratch,
+                       const uint16_t *d_dq, const QuantDev *d_q, WorkLists &wl);
+// Copy lists into `h_work` (contiguous, order fused|idct|c420|up|down|fdct); returns count.
+size_t flatten_work(const WorkLists &wl, CompWork *h_work);
+// Launch every non-empty list; d_work is the device copy of the flattened array.  which: 0 all, 1 fused, 2 idct, 3 c420(+generic tail).
+int launch_work(const WorkLists &wl, const CompWork *d_work, void *stream, int which, int *launches);
+
+// ---- device runtime ------------------------------------------------------------------------------------------
+struct Slot {
+    int dev = 0;
+    void *stream = nullptr;
+    int16_t *h_in = nullptr, *h_out = nullptr; size_t h_in_cap = 0, h_out_cap = 0;       // pinned
+    int16_t *d_in = nullptr, *d_out = nullptr; size_t d_in_cap = 0, d_out_cap = 0;
+    uint8_t *d_scratch = nullptr; size_t d_scratch_cap = 0;
+    uint8_t *h_par = nullptr, *d_par = nullptr; size_t par_cap = 0, d_par_cap = 0;      // parameter block
+    bool ensure(size_t in_bytes, size_t out_bytes, size_t scratch_bytes, size_t par_bytes, std::string &err);
+};
+
+int  runtime_init(int n_gpus, int only_device, std::string &err);   // returns device count (>0) or 0 with err
+void runtime_shutdown();
+int  runtime_device_count();
+Slot *slot_acquire(int prefer_dev, std::string &err);               // blocks while all slots of the device are busy
+void slot_release(Slot *s);
+int  runtime_next_device();                                         // round-robin shard assignment
+
+// Run the transform for ONE image whose input coefficients already sit in s->h_in; result lands in s->h_out.
+bool slot_transform(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err);
+// Same front end, but stop after IDCT + upsample and copy planar full-res samples into `planes` (host).
+bool slot_decode_planes(Slot *s, const JpegGeom &gin, uint8_t *planes, std::string &err);
+
+// ---- device-resident megabatch ---------------------------------------------------------------------------------
+struct JpegBatch {
+    int dev = 0, n = 0;
+    JpegGeom gin, gout; ImagePlan plan;
+    int16_t *d_in = nullptr, *d_out = nullptr; uint8_t *d_scratch = nullptr;
+    uint8_t *d_par = nullptr;
+    WorkLists wl; const CompWork *d_work = nullptr;
+    void *stream = nullptr; void *ev0 = nullptr, *ev1 = nullptr;
+};
+JpegBatch *batch_create(const JpegGeom &gin, const JpegGeom &gout, int n, std::string &err);
+bool batch_upload(JpegBatch *b, int idx, const int16_t *coefs, std::string &err);
+bool batch_run(JpegBatch *b, void *stream, int which, int *launches, std::string &err);
+bool batch_download(JpegBatch *b, int idx, int16_t *coefs, std::string &err);
+bool batch_time(JpegBatch *b, int which, int iters, float *ms, std::string &err);
+void batch_destroy(JpegBatch *b);
+
+} // namespace b200

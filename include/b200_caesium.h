@@ -1,0 +1,153 @@
+/*
+ * b200_caesium.h -- C-ABI of libb200caesium.so, the B200-native replacement for the
+ * `libcaesium` crate calls made by caesiumclt's per-image hot path.
+ *
+ * The reference has no FFI of its own; the seam is the Rust crate boundary in
+ * /root/reference/src/compressor.rs:287-306:
+ *     caesium::compress_in_memory(Vec<u8>, &CSParameters)                        (compressor.rs:305)
+ *     caesium::convert_in_memory(Vec<u8>, &CSParameters, SupportedFileTypes)     (compressor.rs:289,300)
+ *     caesium::compress_to_size_in_memory(Vec<u8>, &mut CSParameters, usize, bool)(compressor.rs:295,298)
+ * Each entry point below names the call it replaces.  All functions are thread-safe and
+ * re-entrant (the caller is a rayon par_iter, compressor.rs:81-83), never abort, and never
+ * fall back to a CPU codec: if no CUDA device / kernel image is available they return
+ * B200_ERR_NO_DEVICE.  Inputs are borrowed for the duration of the call; outputs are
+ * allocated by the library and released with b200_free().
+ */
+#ifndef B200_CAESIUM_H
+#define B200_CAESIUM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (CaesiumError.code analogue; message mirrors "{message} [{code}]") ---- */
+enum {
+    B200_OK = 0,
+    B200_ERR_INVALID_ARGUMENT = 1,
+    B200_ERR_UNKNOWN_FORMAT = 2,     /* input sniffed as none of jpeg/png/webp/gif/tiff */
+    B200_ERR_UNSUPPORTED = 3,        /* recognised, but this path is not implemented on the GPU build:
+                                        the Rust host may route the file to caesium::* instead */
+    B200_ERR_CORRUPT_INPUT = 4,
+    B200_ERR_NO_DEVICE = 5,          /* no CUDA device / sm_100a image -- there is NO CPU fallback */
+    B200_ERR_CUDA = 6,
+    B200_ERR_OUT_OF_MEMORY = 7,
+    B200_ERR_SAME_FORMAT = 8,        /* convert_in_memory asked for the input's own format */
+    B200_ERR_TOO_LARGE = 9           /* compress_to_size could not reach max_output_size */
+};
+
+typedef struct {
+    int32_t code;        /* B200_OK or B200_ERR_* */
+    char *message;       /* NULL when code == 0; malloc'd, release with b200_free() */
+} b200_status;
+
+/* caesium::SupportedFileTypes (compressor.rs:589-598 map_supported_formats) */
+enum { B200_FMT_JPEG = 0, B200_FMT_PNG = 1, B200_FMT_GIF = 2, B200_FMT_WEBP = 3, B200_FMT_TIFF = 4, B200_FMT_UNKNOWN = 5 };
+
+/* caesium::parameters::ChromaSubsampling as libcaesium's C interface spells it */
+enum { B200_CS_AUTO = 0, B200_CS_444 = 444, B200_CS_422 = 422, B200_CS_420 = 420, B200_CS_411 = 411 };
+
+/* caesium::parameters::CSParameters -- exactly the 15 fields compressor.rs:411-446 and :503-536 set */
+typedef struct {
+    uint8_t  keep_metadata;             /* compressor.rs:431  (options.exif) */
+    uint32_t jpeg_quality;              /* :415 */
+    uint32_t jpeg_chroma_subsampling;   /* :433  B200_CS_* */
+    uint8_t  jpeg_progressive;          /* :434  (!jpeg_baseline) */
+    uint8_t  jpeg_optimize;             /* :427  (lossless => coefficient-domain transcode) */
+    uint8_t  jpeg_preserve_icc;         /* :425  (!strip_icc) */
+    uint32_t png_quality;               /* :416 */
+    uint32_t png_optimization_level;    /* :436  0..6 */
+    uint8_t  png_force_zopfli;          /* :437 */
+    uint8_t  png_optimize;              /* :428  (lossless) */
+    uint32_t gif_quality;               /* :418-424 */
+    uint32_t webp_quality;              /* :417 */
+    uint8_t  webp_lossless;             /* :429 */
+    uint32_t width;                     /* :512-528, 0 = keep aspect */
+    uint32_t height;
+} b200_params;
+
+/* CSParameters::new() defaults */
+void b200_params_default(b200_params *p);
+
+/* ---- lifecycle -------------------------------------------------------------------------------- */
+/* Optional (every entry point lazily initialises): n_gpus = 0 means all visible devices.  A maintainer
+ * would call this after the rayon pool is built (main.rs:65).  Returns B200_OK or B200_ERR_NO_DEVICE. */
+int  b200_init(int n_gpus);
+/* One-process-per-GPU launchers (torchrun): bind the library to exactly this CUDA ordinal. */
+int  b200_init_device(int device_ordinal);
+void b200_shutdown(void);
+int  b200_device_count(void);         /* devices the library is driving (0 before init / without GPU) */
+const char *b200_version(void);
+void b200_free(void *p);
+
+/* ---- the three calls of compressor.rs:287-306 -------------------------------------------------- */
+/* replaces caesium::compress_in_memory (compressor.rs:305) */
+b200_status b200_compress_in_memory(const uint8_t *in, size_t in_len, const b200_params *params,
+                                    uint8_t **out, size_t *out_len);
+/* replaces caesium::convert_in_memory (compressor.rs:289, :300); fmt = B200_FMT_* */
+b200_status b200_convert_in_memory(const uint8_t *in, size_t in_len, const b200_params *params, uint32_t fmt,
+                                   uint8_t **out, size_t *out_len);
+/* replaces caesium::compress_to_size_in_memory (compressor.rs:295, :298); may mutate params->*_quality */
+b200_status b200_compress_to_size_in_memory(const uint8_t *in, size_t in_len, b200_params *params,
+                                            size_t max_output_size, uint8_t return_smallest,
+                                            uint8_t **out, size_t *out_len);
+
+/* ---- batch form of start_compression's par_iter (compressor.rs:74-101) -------------------------
+ * Blocking; runs the n images on an internal worker pool (n_threads = 0: one per usable host core)
+ * and shards them round-robin over the initialised GPUs.  status[i]/out[i]/out_len[i] per image,
+ * input order preserved like par_iter().collect().  Returns the number of failed images. */
+int b200_compress_batch(const uint8_t *const *in, const size_t *in_len, int n, const b200_params *params,
+                        int n_threads, uint8_t **out, size_t *out_len, b200_status *status);
+
+/* ---- format sniff (infer::get in compressor.rs:259-264 / scan_files.rs:30-40) ------------------ */
+uint32_t b200_sniff_format(const uint8_t *in, size_t in_len);
+
+/* ---- JPEG stage entry points (the pieces compress_in_memory is assembled from) ----------------
+ * Coefficient buffers are int16, one 64-entry block after another in ZIGZAG order, blocks in raster
+ * order per component, components back to back, each component padded to whole MCUs. */
+typedef struct {
+    int32_t width, height, ncomp, progressive;
+    int32_t hs[4], vs[4];             /* sampling factors */
+    int32_t bw[4], bh[4];             /* allocated blocks across / down (padded to MCUs) */
+    int32_t rbw[4], rbh[4];           /* real blocks: ceil(component samples / 8) */
+    int64_t comp_offset[4];           /* offset of the component's first coefficient, in int16 units */
+    int64_t total_coefs;              /* int16 count of the whole buffer */
+    uint16_t qt[4][64];               /* quantisation table of each COMPONENT, zigzag order */
+} b200_jpeg_layout;
+
+/* host: markers + Huffman decode (baseline and progressive).  *coefs is library-allocated. */
+b200_status b200_jpeg_decode_coefficients(const uint8_t *in, size_t in_len, b200_jpeg_layout *layout, int16_t **coefs);
+/* layout the encoder side of compress_in_memory would produce for an input layout + params */
+b200_status b200_jpeg_output_layout(const b200_jpeg_layout *in_layout, const b200_params *params, b200_jpeg_layout *out_layout);
+/* device: dequant -> IDCT -> chroma upsample -> downsample -> FDCT -> quantise -> zigzag, host buffers in/out
+ * (H2D, kernels, D2H on an internal stream).  out_coefs must hold out_layout->total_coefs int16. */
+b200_status b200_jpeg_requantize(const b200_jpeg_layout *in_layout, const int16_t *in_coefs,
+                                 const b200_jpeg_layout *out_layout, int16_t *out_coefs);
+/* host: entropy-code coefficients (optimised Huffman tables; progressive = mozjpeg-style 8-scan script) */
+b200_status b200_jpeg_encode_coefficients(const b200_jpeg_layout *layout, const int16_t *coefs, int progressive,
+                                          uint8_t **out, size_t *out_len);
+/* device: dequant + IDCT + fancy upsample to planar full-resolution native-space planes [ncomp][H][W] */
+b200_status b200_jpeg_decode_planes(const b200_jpeg_layout *in_layout, const int16_t *in_coefs, uint8_t *planes);
+/* mozjpeg table idx 3 scaled by jpeg_set_quality(q, FALSE); natural order */
+void b200_jpeg_quant_table(int quality, int which, uint16_t out[64]);
+
+/* ---- device-resident megabatch (bench "value": inputs already in HBM) -------------------------- */
+typedef struct b200_jpeg_batch b200_jpeg_batch;
+/* n images that share one layout (the BASELINE megabatch: n x 3840x2160 4:2:0) */
+b200_status b200_jpeg_batch_create(const b200_jpeg_layout *in_layout, const b200_jpeg_layout *out_layout, int n, b200_jpeg_batch **batch);
+b200_status b200_jpeg_batch_upload(b200_jpeg_batch *b, int index, const int16_t *in_coefs);
+/* enqueue the whole hot path for every image of the batch on `cuda_stream` (a cudaStream_t; NULL = the
+ * library's own stream); asynchronous.  *launches receives the number of kernels enqueued. */
+b200_status b200_jpeg_batch_run(b200_jpeg_batch *b, void *cuda_stream, int *launches);
+b200_status b200_jpeg_batch_download(b200_jpeg_batch *b, int index, int16_t *out_coefs);
+/* time `iters` back-to-back runs of kernel group `which` (0 = whole path, 1 = fused luma IDCT->FDCT,
+ * 2 = chroma IDCT, 3 = chroma resample+FDCT) with CUDA events on the launching stream; ms per run */
+b200_status b200_jpeg_batch_time(b200_jpeg_batch *b, int which, int iters, float *ms_per_run);
+void b200_jpeg_batch_destroy(b200_jpeg_batch *b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_CAESIUM_H */
