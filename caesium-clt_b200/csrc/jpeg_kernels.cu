@@ -233,6 +233,19 @@ __global__ void __launch_bounds__(THREADS) k_fused_same(const CompWork *__restri
     int v[64];
     dequant_dezigzag(r, tab, v);
     idct_block(v);
+    // The decoder crops to W x H and the encoder re-pads by edge replication (jcsample.c expand_right_edge,
+    // jcprepct.c expand_bottom_edge): blocks straddling the right / bottom image edge lose their decoded padding.
+    const int vc = w.cw - (t.bx0 + lane) * 8, vr = w.ch - t.by * 8;
+    if (vc < 8 || vr < 8) {
+#pragma unroll
+        for (int y = 0; y < 8; y++)
+#pragma unroll
+            for (int x = 1; x < 8; x++) if (x >= vc) v[8 * y + x] = v[8 * y + x - 1];
+#pragma unroll
+        for (int y = 1; y < 8; y++)
+#pragma unroll
+            for (int x = 0; x < 8; x++) if (y >= vr) v[8 * y + x] = v[8 * (y - 1) + x];
+    }
     fdct_block(v);
     quant_zigzag(v, tab, r);
     warp_store_blocks(reinterpret_cast<int4 *>(w.cout) + ((size_t)t.by * w.bw_out + t.bx0) * 8, t.nvalid, st, lane, r);
