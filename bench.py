@@ -198,8 +198,9 @@ def main():
     batch = L.JpegBatch(lay, olay, B)
     for i in range(B):
         batch.upload(i, decoded[i % len(decoded)][1])
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()            # a real (non-NULL) stream: the kernels are launched on it and the events recorded on it
     sh = stream.cuda_stream
+    assert sh != 0
 
     def barrier():
         torch.cuda.synchronize()

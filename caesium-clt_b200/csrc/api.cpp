@@ -14,6 +14,7 @@
 #include <vector>
 #include "jpeg_device.h"
 #include "jpeg_host.h"
+#include "resize_kernels.h"
 
 using namespace b200;
 
@@ -91,7 +92,6 @@ b200_status jpeg_compress(const uint8_t *in, size_t in_len, const b200_params *p
     JpegReader rd(in, in_len);
     if (!rd.read_header(err)) return make_status(B200_ERR_CORRUPT_INPUT, err);
     const JpegGeom &gin = rd.geom();
-    if (p->width || p->height) return make_status(B200_ERR_UNSUPPORTED, "JPEG resize is not implemented on the GPU path yet");
     JpegWriteOptions wo; wo.progressive = p->jpeg_progressive != 0; wo.keep_metadata = p->keep_metadata != 0; wo.preserve_icc = p->jpeg_preserve_icc != 0;
     if (p->jpeg_optimize) {
         // libcaesium jpeg::lossless: coefficient-domain transcode, nothing numeric to do on the device
@@ -105,15 +105,23 @@ b200_status jpeg_compress(const uint8_t *in, size_t in_len, const b200_params *p
     if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
     JpegGeom gout;
     if (!jpeg_output_geom(gin, (int)p->jpeg_quality, (int)p->jpeg_chroma_subsampling, gout, err)) return make_status(B200_ERR_INVALID_ARGUMENT, err);
+    const bool resize = p->width || p->height;
+    if (resize) {   // libcaesium resize::resize_image -> compute_dimensions
+        uint32_t nw = 0, nh = 0;
+        compute_resize_dimensions((uint32_t)gin.width, (uint32_t)gin.height, p->width, p->height, nw, nh);
+        if (nw == 0 || nh == 0 || nw > 65535 || nh > 65535) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid target dimensions");
+        gout.width = (int)nw; gout.height = (int)nh; gout.finalize();
+    }
     ImagePlan plan;
-    if (!plan_image(gin, gout, plan, err)) return make_status(B200_ERR_UNSUPPORTED, err);
+    if (!resize && !plan_image(gin, gout, plan, err)) return make_status(B200_ERR_UNSUPPORTED, err);
+    if (resize) { plan.in_bytes = (size_t)gin.total_coefs * 2; plan.out_bytes = (size_t)gout.total_coefs * 2; }
     Slot *s = slot_acquire(prefer_dev < 0 ? runtime_next_device() : prefer_dev, err);
     if (!s) return make_status(B200_ERR_CUDA, err);
     b200_status st = ok_status();
     do {
         if (!s->ensure(plan.in_bytes, plan.out_bytes, plan.scratch_bytes(), 1 << 14, err)) { st = make_status(B200_ERR_OUT_OF_MEMORY, err); break; }
         if (!rd.decode(s->h_in, err)) { st = make_status(B200_ERR_CORRUPT_INPUT, err); break; }
-        if (!slot_transform(s, gin, gout, err)) { st = make_status(B200_ERR_CUDA, err); break; }
+        if (!(resize ? slot_transform_resized(s, gin, gout, err) : slot_transform(s, gin, gout, err))) { st = make_status(B200_ERR_CUDA, err); break; }
         jpeg_fill_dummy_blocks(gout, s->h_out);
         if (!jpeg_write(gout, s->h_out, wo, &rd.meta(), out, err)) { st = make_status(B200_ERR_INVALID_ARGUMENT, err); break; }
     } while (0);

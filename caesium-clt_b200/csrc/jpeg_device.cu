@@ -10,6 +10,7 @@
 #include <vector>
 #include <atomic>
 #include "jpeg_device.h"
+#include "resize_kernels.h"
 
 namespace b200 {
 
@@ -277,6 +278,89 @@ bool slot_decode_planes(Slot *s, const JpegGeom &gin, uint8_t *planes, std::stri
         CU(cudaMemcpyAsync(h + (size_t)c * gin.width * gin.height, s->d_scratch + plan.plane_bytes + plan.full_off[c], (size_t)gin.width * gin.height, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     memcpy(planes, h, (size_t)gin.ncomp * gin.width * gin.height);
+    return true;
+}
+
+// ---- resize path: decode -> (YCbCr->RGB) -> Lanczos3 -> (RGB->YCbCr) -> encode side --------------------------------
+bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err)
+{
+    const int W = gin.width, H = gin.height, NW = gout.width, NH = gout.height, nc = gin.ncomp;
+    if (gout.ncomp != nc) { err = "component count mismatch"; return false; }
+    cudaStream_t st = (cudaStream_t)s->stream;
+    ResizeAxis av, ah;
+    make_resize_axis(H, NH, av);
+    make_resize_axis(W, NW, ah);
+    // scratch layout
+    size_t off = 0, plane_off[4], full_off[4], rz_off[4], dpl_off[4];
+    for (int c = 0; c < nc; c++) {
+        if (gin.hmax % gin.hs[c] || gin.vmax % gin.vs[c] || gout.hmax % gout.hs[c] || gout.vmax % gout.vs[c]) { err = "fractional sampling ratio unsupported"; return false; }
+        plane_off[c] = off; off += align_up((size_t)gin.bw[c] * 8 * gin.bh[c] * 8, 256);
+    }
+    for (int c = 0; c < nc; c++) { full_off[c] = off; off += align_up((size_t)W * H, 256); }
+    for (int c = 0; c < nc; c++) { rz_off[c] = off; off += align_up((size_t)NW * NH, 256); }
+    for (int c = 0; c < nc; c++) { dpl_off[c] = off; off += align_up((size_t)gout.rbw[c] * 8 * gout.rbh[c] * 8, 256); }
+    const size_t tmp_off = off; off += align_up((size_t)NH * W * sizeof(float), 256);
+    // parameter block: tables | work | axis tables
+    const size_t nwork = (size_t)nc * 4;
+    size_t p_axis = align_up(par_bytes_for(nwork), 256);
+    const size_t lv = p_axis, cv = lv + align_up(sizeof(int) * NH, 256), wv = cv + align_up(sizeof(int) * NH, 256);
+    const size_t lh = wv + align_up(sizeof(float) * av.weights.size(), 256), chh = lh + align_up(sizeof(int) * NW, 256), wh = chh + align_up(sizeof(int) * NW, 256);
+    const size_t pbytes = wh + align_up(sizeof(float) * ah.weights.size(), 256);
+    const size_t in_bytes = (size_t)gin.total_coefs * 2, out_bytes = (size_t)gout.total_coefs * 2;
+    if (!s->ensure(in_bytes, out_bytes, off, pbytes, err)) return false;
+    fill_tables(s->h_par, gin, &gout);
+    memcpy(s->h_par + lv, av.left.data(), sizeof(int) * NH); memcpy(s->h_par + cv, av.count.data(), sizeof(int) * NH);
+    memcpy(s->h_par + wv, av.weights.data(), sizeof(float) * av.weights.size());
+    memcpy(s->h_par + lh, ah.left.data(), sizeof(int) * NW); memcpy(s->h_par + chh, ah.count.data(), sizeof(int) * NW);
+    memcpy(s->h_par + wh, ah.weights.data(), sizeof(float) * ah.weights.size());
+    WorkLists wl;
+    const uint16_t *d_dq = reinterpret_cast<const uint16_t *>(s->d_par + PAR_DQ);
+    const QuantDev *d_q = reinterpret_cast<const QuantDev *>(s->d_par + PAR_Q);
+    for (int c = 0; c < nc; c++) {
+        CompWork d; memset(&d, 0, sizeof(d));   // decode side
+        d.cin = s->d_in + gin.comp_offset[c]; d.dq = d_dq + 64 * c; d.q = d_q;
+        d.bw_in = gin.bw[c]; d.bh_in = gin.bh[c]; d.rbw_in = gin.rbw[c]; d.rbh_in = gin.rbh[c]; d.cw = gin.cw[c]; d.ch = gin.ch[c];
+        d.W = W; d.H = H; d.pstride = gin.bw[c] * 8; d.fstride = W;
+        d.up_hx = gin.hmax / gin.hs[c]; d.up_vx = gin.vmax / gin.vs[c]; d.dn_hx = d.dn_vx = 1;
+        d.plane = s->d_scratch + plane_off[c]; d.full = s->d_scratch + full_off[c];
+        wl.idct.push_back(d); wl.max_idct = std::max(wl.max_idct, work_tiles(d.rbw_in, d.rbh_in));
+        wl.up.push_back(d); wl.max_up_w = W; wl.max_up_h = H;
+        CompWork e; memset(&e, 0, sizeof(e));   // encode side
+        e.cout = s->d_out + gout.comp_offset[c]; e.dq = d_dq; e.q = d_q + gout.tq[c];
+        e.bw_out = gout.bw[c]; e.bh_out = gout.bh[c]; e.rbw_out = gout.rbw[c]; e.rbh_out = gout.rbh[c];
+        e.W = NW; e.H = NH; e.fstride = NW; e.full = s->d_scratch + rz_off[c]; e.dplane = s->d_scratch + dpl_off[c];
+        e.dn_hx = gout.hmax / gout.hs[c]; e.dn_vx = gout.vmax / gout.vs[c]; e.up_hx = e.up_vx = 1;
+        wl.down.push_back(e); wl.max_dn_w = std::max(wl.max_dn_w, e.rbw_out * 8); wl.max_dn_h = std::max(wl.max_dn_h, e.rbh_out * 8);
+        wl.fdct.push_back(e); wl.max_fdct = std::max(wl.max_fdct, work_tiles(e.rbw_out, e.rbh_out));
+    }
+    size_t nw_ = flatten_work(wl, reinterpret_cast<CompWork *>(s->h_par + PAR_WORK));
+    (void)nw_;
+    CU(cudaMemcpyAsync(s->d_par, s->h_par, pbytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s->d_in, s->h_in, in_bytes, cudaMemcpyHostToDevice, st));
+    const CompWork *dw = reinterpret_cast<const CompWork *>(s->d_par + PAR_WORK);
+    const CompWork *p_idct = dw, *p_up = p_idct + wl.idct.size(), *p_down = p_up + wl.up.size(), *p_fdct = p_down + wl.down.size();
+    auto chk = [&](int rc, const char *what) { if (rc) { err = std::string(what) + ": " + cudaGetErrorString((cudaError_t)rc); return false; } return true; };
+    if (!chk(launch_idct_plane(p_idct, nc, wl.max_idct, st), "idct")) return false;
+    if (!chk(launch_upsample(p_up, nc, W, H, st), "upsample")) return false;
+    uint8_t *full[3] = {s->d_scratch + full_off[0], nc == 3 ? s->d_scratch + full_off[1] : nullptr, nc == 3 ? s->d_scratch + full_off[2] : nullptr};
+    uint8_t *rz[3] = {s->d_scratch + rz_off[0], nc == 3 ? s->d_scratch + rz_off[1] : nullptr, nc == 3 ? s->d_scratch + rz_off[2] : nullptr};
+    if (nc == 3 && !chk(launch_ycc_to_rgb(full[0], full[1], full[2], (size_t)W * H, st), "ycc_to_rgb")) return false;
+    float *tmp = reinterpret_cast<float *>(s->d_scratch + tmp_off);
+    for (int c = 0; c < nc; c++) {
+        if (NW == W && NH == H) {   // imageops::resize copies when the dimensions are unchanged
+            CU(cudaMemcpyAsync(rz[c], full[c], (size_t)W * H, cudaMemcpyDeviceToDevice, st));
+            continue;
+        }
+        if (!chk(launch_resize_v(full[c], W, H, W, tmp, NH, reinterpret_cast<const int *>(s->d_par + lv), reinterpret_cast<const int *>(s->d_par + cv),
+                                 reinterpret_cast<const float *>(s->d_par + wv), av.cap, st), "resize_v")) return false;
+        if (!chk(launch_resize_h(tmp, W, rz[c], NW, NH, NW, reinterpret_cast<const int *>(s->d_par + lh), reinterpret_cast<const int *>(s->d_par + chh),
+                                 reinterpret_cast<const float *>(s->d_par + wh), ah.cap, st), "resize_h")) return false;
+    }
+    if (nc == 3 && !chk(launch_rgb_to_ycc(rz[0], rz[1], rz[2], (size_t)NW * NH, st), "rgb_to_ycc")) return false;
+    if (!chk(launch_downsample(p_down, nc, wl.max_dn_w, wl.max_dn_h, st), "downsample")) return false;
+    if (!chk(launch_fdct_plane(p_fdct, nc, wl.max_fdct, st), "fdct")) return false;
+    CU(cudaMemcpyAsync(s->h_out, s->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return true;
 }
 

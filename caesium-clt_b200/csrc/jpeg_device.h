@@ -58,6 +58,8 @@ int  runtime_next_device();                                         // round-rob
 
 // Run the transform for ONE image whose input coefficients already sit in s->h_in; result lands in s->h_out.
 bool slot_transform(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err);
+// Resize path (CSParameters.width/height): gout carries the TARGET dimensions; decode -> RGB -> Lanczos3 -> YCbCr -> encode.
+bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err);
 // Same front end, but stop after IDCT + upsample and copy planar full-res samples into `planes` (host).
 bool slot_decode_planes(Slot *s, const JpegGeom &gin, uint8_t *planes, std::string &err);
 

@@ -217,7 +217,7 @@ __device__ __forceinline__ void quant_zigzag(const int (&v)[64], const Tables &t
 // K1->K5 fused: components whose sample grid is unchanged between decode and encode (luma always; chroma too when
 // neither side subsamples).  coefficients in -> coefficients out, 6 algorithmic bytes... per sample 4 B.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS) k_fused_same(const CompWork *__restrict__ work)
+__global__ void __launch_bounds__(THREADS, 2) k_fused_same(const CompWork *__restrict__ work)
 {
     __shared__ Tables tab;
     __shared__ int4 stage[WARPS_PER_CTA * STAGE_INT4_PER_WARP];
@@ -297,7 +297,25 @@ __device__ __forceinline__ int up_h2v2(const uint8_t *__restrict__ P, int pstrid
     return (3 * a + b + ((x & 1) ? 7 : 8)) >> 4;
 }
 
-__global__ void __launch_bounds__(THREADS) k_chroma420_refdct(const CompWork *__restrict__ work)
+// generic clamped evaluation of one 8x8 output block (image edges, odd dimensions, tiny planes) following the
+// jcprepct/jcsample padding rules (oracle orc_downsample); results are written as bytes to `mine` (64 B)
+__device__ __noinline__ void chroma420_edge_block(const CompWork &w, int bx, int by, uint8_t *mine)
+{
+    const uint8_t *__restrict__ P = w.plane;
+    const int ps = w.pstride, nreal = (w.H + 1) >> 1;
+    for (int i = 0; i < 64; i++) {
+        int Y = i >> 3, X = i & 7;
+        int yy = min(by * 8 + Y, nreal - 1);
+        int y0 = min(2 * yy, w.H - 1), y1 = min(2 * yy + 1, w.H - 1);
+        int xo = bx * 8 + X;
+        int x0 = min(2 * xo, w.W - 1), x1 = min(2 * xo + 1, w.W - 1);
+        int s = up_h2v2(P, ps, w.cw, w.ch, y0, x0) + up_h2v2(P, ps, w.cw, w.ch, y0, x1)
+              + up_h2v2(P, ps, w.cw, w.ch, y1, x0) + up_h2v2(P, ps, w.cw, w.ch, y1, x1);
+        mine[i] = (uint8_t)((s + 1 + (xo & 1)) >> 2);
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 2) k_chroma420_refdct(const CompWork *__restrict__ work)
 {
     __shared__ Tables tab;
     __shared__ int4 stage[WARPS_PER_CTA * STAGE_INT4_PER_WARP];
@@ -310,65 +328,53 @@ __global__ void __launch_bounds__(THREADS) k_chroma420_refdct(const CompWork *__
     const int by = t.by, bx = min(t.bx0 + lane, w.rbw_out - 1);
     const uint8_t *__restrict__ P = w.plane;
     const int ps = w.pstride;
-    const bool interior = bx * 8 >= 1 && bx * 8 + 8 <= w.cw - 1 && by * 8 >= 1 && by * 8 + 8 <= w.ch - 1;
+    // The register fast path is exact whenever every clamp of the generic formulas degenerates to "replicate the
+    // nearest decoded sample": the block lies wholly inside the decoded plane and, if it is the last block column /
+    // row, the image width / height is even (then x1 = 2X+1 and y1 = 2Y+1 never clamp).  Left and top edges always
+    // replicate.  Everything else (partial edge blocks, odd sizes, planes <= 2 samples wide) takes the generic path.
+    const bool fast = w.cw > 2 && bx * 8 + 8 <= w.cw && by * 8 + 8 <= w.ch &&
+                      (bx * 8 + 8 < w.cw || 2 * w.cw == w.W) && (by * 8 + 8 < w.ch || 2 * w.ch == w.H);
     int v[64];
-    // ---- fast path loads (executed by every lane so the shuffles are convergent; addresses clamped) ----
-    const int prow_max = w.bh_in * 8 - 1;
-    int prevL = 0, prevM0 = 0, prevM1 = 0, prevR = 0, curL = 0, curM0 = 0, curM1 = 0, curR = 0;
+    int pL = 0, pM0 = 0, pM1 = 0, pR = 0, cL = 0, cM0 = 0, cM1 = 0, cR = 0;
+    const bool edge_r = lane == 31 || lane == t.nvalid - 1;
 #pragma unroll
     for (int rr = 0; rr < 10; rr++) {
-        int gy = min(max(by * 8 + rr - 1, 0), prow_max);
+        const int gy = min(max(by * 8 + rr - 1, 0), w.ch - 1);
         const uint8_t *row = P + (size_t)gy * ps;
-        uint2 m = __ldg(reinterpret_cast<const uint2 *>(row + bx * 8));
-        int left = __shfl_up_sync(0xFFFFFFFFu, (int)(m.y >> 24), 1);
-        int right = __shfl_down_sync(0xFFFFFFFFu, (int)(m.x & 0xFF), 1);
-        if (lane == 0) left = row[max(bx * 8 - 1, 0)];
-        if (lane == 31) right = row[min(bx * 8 + 8, ps - 1)];
-        int nL = left, nM0 = (int)m.x, nM1 = (int)m.y, nR = right;
+        const uint2 m = __ldg(reinterpret_cast<const uint2 *>(row + bx * 8));
+        int nL = __shfl_up_sync(0xFFFFFFFFu, (int)(m.y >> 24), 1);
+        int nR = __shfl_down_sync(0xFFFFFFFFu, (int)(m.x & 0xFF), 1);
+        if (lane == 0) nL = row[max(bx * 8 - 1, 0)];
+        if (edge_r) nR = row[min(bx * 8 + 8, w.cw - 1)];
+        const int nM0 = (int)m.x, nM1 = (int)m.y;
         if (rr >= 2) {
-            // output row Y = rr - 2 uses plane rows (prev, cur, next) = (Y-1, Y, Y+1) relative to the block
+            // output row Y = rr - 2 uses plane rows (p, c, n) = (Y-1, Y, Y+1) of the block; su/sl are the column sums of
+            // the upper (y = 2Y: rows Y, Y-1) and lower (y = 2Y+1: rows Y, Y+1) full-resolution rows, columns -1..8
             const int Y = rr - 2;
-            // bytes of the three rows, columns -1..8
-            int p[10], c[10], n[10];
-            p[0] = prevL; c[0] = curL; n[0] = nL;
+            int su[10], sl[10];
+            su[0] = 3 * cL + pL; sl[0] = 3 * cL + nL;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                p[1 + k] = (prevM0 >> (8 * k)) & 0xFF; p[5 + k] = (prevM1 >> (8 * k)) & 0xFF;
-                c[1 + k] = (curM0 >> (8 * k)) & 0xFF;  c[5 + k] = (curM1 >> (8 * k)) & 0xFF;
-                n[1 + k] = (nM0 >> (8 * k)) & 0xFF;    n[5 + k] = (nM1 >> (8 * k)) & 0xFF;
+                const int c0 = (cM0 >> (8 * k)) & 0xFF, c1 = (cM1 >> (8 * k)) & 0xFF;
+                su[1 + k] = 3 * c0 + ((pM0 >> (8 * k)) & 0xFF); sl[1 + k] = 3 * c0 + ((nM0 >> (8 * k)) & 0xFF);
+                su[5 + k] = 3 * c1 + ((pM1 >> (8 * k)) & 0xFF); sl[5 + k] = 3 * c1 + ((nM1 >> (8 * k)) & 0xFF);
             }
-            p[9] = prevR; c[9] = curR; n[9] = nR;
-            // column sums for the upper (y = 2Y, uses rows Y and Y-1) and lower (y = 2Y+1, rows Y and Y+1) full-res rows
-            int su[10], sl[10];
-#pragma unroll
-            for (int k = 0; k < 10; k++) { su[k] = 3 * c[k] + p[k]; sl[k] = 3 * c[k] + n[k]; }
+            su[9] = 3 * cR + pR; sl[9] = 3 * cR + nR;
 #pragma unroll
             for (int X = 0; X < 8; X++) {
                 // full-res x0 = 2X (even: neighbour column X-1, bias 8), x1 = 2X+1 (odd: neighbour X+1, bias 7)
-                int u00 = (3 * su[X + 1] + su[X] + 8) >> 4, u01 = (3 * su[X + 1] + su[X + 2] + 7) >> 4;
-                int u10 = (3 * sl[X + 1] + sl[X] + 8) >> 4, u11 = (3 * sl[X + 1] + sl[X + 2] + 7) >> 4;
+                const int tu = 3 * su[X + 1], tl = 3 * sl[X + 1];
+                const int u00 = (tu + su[X] + 8) >> 4, u01 = (tu + su[X + 2] + 7) >> 4;
+                const int u10 = (tl + sl[X] + 8) >> 4, u11 = (tl + sl[X + 2] + 7) >> 4;
                 v[8 * Y + X] = ((u00 + u01 + u10 + u11 + 1 + (X & 1)) >> 2) - 128;   // bias 1,2,1,2 across output columns
             }
         }
-        prevL = curL; prevM0 = curM0; prevM1 = curM1; prevR = curR;
-        curL = nL; curM0 = nM0; curM1 = nM1; curR = nR;
+        pL = cL; pM0 = cM0; pM1 = cM1; pR = cR;
+        cL = nL; cM0 = nM0; cM1 = nM1; cR = nR;
     }
-    if (!interior) {
-        // generic clamped evaluation (image edges, tiny planes): jcprepct/jcsample padding rules of oracle orc_downsample
-        // Results go through this lane's private slice of the staging buffer (pitch 68 B) so that v[] keeps
-        // compile-time indices and stays in registers.
-        const int nreal = (w.H + 1) >> 1;
+    if (!fast) {
         uint8_t *mine = reinterpret_cast<uint8_t *>(stage + warp * STAGE_INT4_PER_WARP) + lane * 68;
-        for (int i = 0; i < 64; i++) {
-            int Y = i >> 3, X = i & 7;
-            int yy = min(by * 8 + Y, nreal - 1);
-            int y0 = min(2 * yy, w.H - 1), y1 = min(2 * yy + 1, w.H - 1);
-            int xo = bx * 8 + X;
-            int x0 = min(2 * xo, w.W - 1), x1 = min(2 * xo + 1, w.W - 1);
-            int s = up_h2v2(P, ps, w.cw, w.ch, y0, x0) + up_h2v2(P, ps, w.cw, w.ch, y0, x1)
-                  + up_h2v2(P, ps, w.cw, w.ch, y1, x0) + up_h2v2(P, ps, w.cw, w.ch, y1, x1);
-            mine[i] = (uint8_t)((s + 1 + (xo & 1)) >> 2);
-        }
+        chroma420_edge_block(w, bx, by, mine);
 #pragma unroll
         for (int j = 0; j < 16; j++) {
             uint32_t m4 = *reinterpret_cast<const uint32_t *>(mine + 4 * j);

@@ -181,6 +181,51 @@ def jpeg_lossy(data, p):
     return _take(outp, outl)
 
 
+def jpeg_lossy_resized(data, p, width, height):
+    """libcaesium JPEG compress with CSParameters.width/height (decode -> RGB -> Lanczos3 -> YCbCr -> encode)."""
+    outp, outl = C.POINTER(C.c_uint8)(), C.c_size_t()
+    err = C.create_string_buffer(256)
+    lib().orc_jpeg_lossy_resized.restype = C.c_int
+    if lib().orc_jpeg_lossy_resized(_buf(data), C.c_size_t(len(data)), C.byref(p), C.c_uint32(width), C.c_uint32(height), C.byref(outp), C.byref(outl), err):
+        raise OracleError(err.value.decode())
+    return _take(outp, outl)
+
+
+def compute_dimensions(ow, oh, dw, dh):
+    nw, nh = C.c_uint32(), C.c_uint32()
+    lib().orc_compute_dimensions(C.c_uint32(ow), C.c_uint32(oh), C.c_uint32(dw), C.c_uint32(dh), C.byref(nw), C.byref(nh))
+    return nw.value, nh.value
+
+
+def resize_plane(plane, nw, nh):
+    """One u8 channel through image-crate-style Lanczos3 (vertical pass to f32, then horizontal)."""
+    plane = np.ascontiguousarray(plane, dtype=np.uint8)
+    h, w = plane.shape
+    out = np.zeros((nh, nw), dtype=np.uint8)
+    lib().orc_resize_plane_lanczos3.restype = C.c_int
+    if lib().orc_resize_plane_lanczos3(plane.ctypes.data_as(C.c_void_p), w, h, w, out.ctypes.data_as(C.c_void_p), nw, nh, nw):
+        raise OracleError("resize failed")
+    return out
+
+
+def ycc_to_rgb(ycc):
+    ycc = np.ascontiguousarray(ycc, dtype=np.uint8)
+    out = np.zeros_like(ycc)
+    n = ycc[0].size
+    lib().orc_ycc_to_rgb(ycc[0].ctypes.data_as(C.c_void_p), ycc[1].ctypes.data_as(C.c_void_p), ycc[2].ctypes.data_as(C.c_void_p),
+                         out[0].ctypes.data_as(C.c_void_p), out[1].ctypes.data_as(C.c_void_p), out[2].ctypes.data_as(C.c_void_p), C.c_size_t(n))
+    return out
+
+
+def rgb_to_ycc(rgb):
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    out = np.zeros_like(rgb)
+    n = rgb[0].size
+    lib().orc_rgb_to_ycc(rgb[0].ctypes.data_as(C.c_void_p), rgb[1].ctypes.data_as(C.c_void_p), rgb[2].ctypes.data_as(C.c_void_p),
+                         out[0].ctypes.data_as(C.c_void_p), out[1].ctypes.data_as(C.c_void_p), out[2].ctypes.data_as(C.c_void_p), C.c_size_t(n))
+    return out
+
+
 def jpeg_lossless(data, p):
     """libcaesium jpeg::lossless restated (jpegtran-style transcode)."""
     outp, outl = C.POINTER(C.c_uint8)(), C.c_size_t()
