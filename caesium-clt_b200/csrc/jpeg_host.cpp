@@ -510,7 +510,6 @@ inline uint64_t nonzero_mask(const int16_t *blk)
     return ~m;
 }
 
-struct ScanDef { int ns, ci[3], Ss, Se, Ah, Al; };
 
 struct ProgState { unsigned eobrun = 0, BE = 0; int tbl = 0; uint8_t corr[1000 + 64]; };
 
@@ -666,13 +665,31 @@ void emit_tokens(std::vector<uint8_t> &out, const TokenBuf &t, const EncTab tabs
 
 } // namespace
 
-bool jpeg_write(const JpegGeom &g, const int16_t *coefs, const JpegWriteOptions &opt, const JpegMeta *meta,
-                std::vector<uint8_t> &out, std::string &err)
+int jpeg_scan_script(const JpegGeom &g, bool progressive, ScanDef sc[16])
 {
-    if (g.ncomp != 1 && g.ncomp != 3) { err = "unsupported component count"; return false; }
-    out.clear();
-    out.reserve((size_t)g.total_coefs / 6 + 4096);
-    ByteSink w(out);
+    int ns = 0;
+    if (!progressive) { sc[0].ns = g.ncomp; for (int c = 0; c < 3; c++) sc[0].ci[c] = c < g.ncomp ? c : 0; sc[0].Ss = 0; sc[0].Se = 63; sc[0].Ah = sc[0].Al = 0; return 1; }
+    sc[ns].ns = g.ncomp; for (int c = 0; c < 3; c++) sc[ns].ci[c] = c < g.ncomp ? c : 0; sc[ns].Ss = 0; sc[ns].Se = 0; sc[ns].Ah = 0; sc[ns].Al = 0; ns++;
+    sc[ns++] = ScanDef{1, {0, 0, 0}, 1, 2, 0, 1};
+    sc[ns++] = ScanDef{1, {0, 0, 0}, 3, 63, 0, 1};
+    for (int c = 1; c < g.ncomp; c++) sc[ns++] = ScanDef{1, {c, 0, 0}, 1, 63, 0, 1};
+    for (int c = 0; c < g.ncomp; c++) sc[ns++] = ScanDef{1, {c, 0, 0}, 1, 63, 1, 0};
+    return ns;
+}
+
+void jpeg_scan_tables_needed(const JpegGeom &, bool progressive, const ScanDef &s, bool need[2][2])
+{   // jcmarker.c write_scan_header: progressive scans define the DC table (Ss == 0, Ah == 0) or the AC table (Ss > 0)
+    need[0][0] = need[0][1] = need[1][0] = need[1][1] = false;
+    if (progressive && s.Ss == 0 && s.Ah != 0) return;     // DC refinement: no table
+    for (int i = 0; i < s.ns; i++) {
+        int t = s.ci[i] ? 1 : 0;
+        if (!progressive || s.Ss == 0) need[0][t] = true;
+        if (!progressive || s.Ss > 0) need[1][t] = true;
+    }
+}
+
+static void write_file_header(ByteSink &w, const JpegGeom &g, const JpegWriteOptions &opt, const JpegMeta *meta)
+{
     w.u16(0xFFD8);
     {   // jcmarker.c emit_jfif_app0
         uint8_t body[9] = {1, 1, 0, 0, 1, 0, 1, 0, 0};
@@ -696,16 +713,29 @@ bool jpeg_write(const JpegGeom &g, const int16_t *coefs, const JpegWriteOptions 
     w.u16(opt.progressive ? 0xFFC2 : 0xFFC0); w.u16(8 + 3 * g.ncomp); w.u8(8);
     w.u16(g.height); w.u16(g.width); w.u8(g.ncomp);
     for (int c = 0; c < g.ncomp; c++) { w.u8(g.cid[c]); w.u8((g.hs[c] << 4) | g.vs[c]); w.u8(g.tq[c]); }
+}
 
-    ScanDef sc[16]; int ns = 0;
-    if (!opt.progressive) { sc[0].ns = g.ncomp; for (int c = 0; c < g.ncomp; c++) sc[0].ci[c] = c; sc[0].Ss = 0; sc[0].Se = 63; sc[0].Ah = sc[0].Al = 0; ns = 1; }
-    else {   // the 8-scan script mozjpeg's optimize_scans settled on for samples/j0.JPG
-        sc[ns].ns = g.ncomp; for (int c = 0; c < g.ncomp; c++) sc[ns].ci[c] = c; sc[ns].Ss = 0; sc[ns].Se = 0; sc[ns].Ah = 0; sc[ns].Al = 0; ns++;
-        sc[ns++] = ScanDef{1, {0, 0, 0}, 1, 2, 0, 1};
-        sc[ns++] = ScanDef{1, {0, 0, 0}, 3, 63, 0, 1};
-        for (int c = 1; c < g.ncomp; c++) sc[ns++] = ScanDef{1, {c, 0, 0}, 1, 63, 0, 1};
-        for (int c = 0; c < g.ncomp; c++) sc[ns++] = ScanDef{1, {c, 0, 0}, 1, 63, 1, 0};
+static void write_sos(ByteSink &w, const JpegGeom &g, bool progressive, const ScanDef &s)
+{   // jcmarker.c emit_sos
+    w.u16(0xFFDA); w.u16(6 + 2 * s.ns); w.u8(s.ns);
+    for (int i = 0; i < s.ns; i++) {
+        int c = s.ci[i], td = c ? 1 : 0, ta = c ? 1 : 0;
+        if (progressive) { if (s.Ss == 0) { ta = 0; if (s.Ah != 0) td = 0; } else td = 0; }
+        w.u8(g.cid[c]); w.u8((td << 4) | ta);
     }
+    w.u8(s.Ss); w.u8(s.Se); w.u8((s.Ah << 4) | s.Al);
+}
+
+bool jpeg_write(const JpegGeom &g, const int16_t *coefs, const JpegWriteOptions &opt, const JpegMeta *meta,
+                std::vector<uint8_t> &out, std::string &err)
+{
+    if (g.ncomp != 1 && g.ncomp != 3) { err = "unsupported component count"; return false; }
+    out.clear();
+    out.reserve((size_t)g.total_coefs / 6 + 4096);
+    ByteSink w(out);
+    write_file_header(w, g, opt, meta);
+    ScanDef sc[16];
+    const int ns = jpeg_scan_script(g, opt.progressive, sc);
     static thread_local TokenBuf tb;
     int64_t nblocks = 0; for (int c = 0; c < g.ncomp; c++) nblocks += g.blocks(c);
     for (int si = 0; si < ns; si++) {
@@ -713,27 +743,39 @@ bool jpeg_write(const JpegGeom &g, const int16_t *coefs, const JpegWriteOptions 
         tb.reset((size_t)nblocks * 12 + 4096);
         tokenize_scan(g, coefs, opt.progressive, s, tb);
         EncTab tabs[2][2];
-        const bool dc_refine = opt.progressive && s.Ss == 0 && s.Ah != 0;
-        if (!dc_refine) {
-            bool need[2][2] = {{false, false}, {false, false}};
-            for (int i = 0; i < s.ns; i++) {
-                int t = s.ci[i] ? 1 : 0;
-                if (!opt.progressive || s.Ss == 0) need[0][t] = true;
-                if (!opt.progressive || s.Ss > 0) need[1][t] = true;
-            }
-            for (int t = 0; t < 2; t++) for (int kind = 0; kind < 2; kind++) if (need[kind][t]) {
-                gen_optimal_table(tabs[kind][t], tb.freq[kind][t]);
-                write_dht(w, kind, t, tabs[kind][t]);
-            }
+        bool need[2][2];
+        jpeg_scan_tables_needed(g, opt.progressive, s, need);
+        for (int t = 0; t < 2; t++) for (int kind = 0; kind < 2; kind++) if (need[kind][t]) {
+            gen_optimal_table(tabs[kind][t], tb.freq[kind][t]);
+            write_dht(w, kind, t, tabs[kind][t]);
         }
-        w.u16(0xFFDA); w.u16(6 + 2 * s.ns); w.u8(s.ns);
-        for (int i = 0; i < s.ns; i++) {
-            int c = s.ci[i], td = c ? 1 : 0, ta = c ? 1 : 0;
-            if (opt.progressive) { if (s.Ss == 0) { ta = 0; if (s.Ah != 0) td = 0; } else td = 0; }
-            w.u8(g.cid[c]); w.u8((td << 4) | ta);
-        }
-        w.u8(s.Ss); w.u8(s.Se); w.u8((s.Ah << 4) | s.Al);
+        write_sos(w, g, opt.progressive, s);
         emit_tokens(out, tb, tabs);
+    }
+    w.u16(0xFFD9);
+    return true;
+}
+
+bool jpeg_assemble(const JpegGeom &g, const JpegWriteOptions &opt, const JpegMeta *meta, const EncodedScan *scans, int nscans,
+                   std::vector<uint8_t> &out, std::string &err)
+{
+    if (g.ncomp != 1 && g.ncomp != 3) { err = "unsupported component count"; return false; }
+    out.clear();
+    size_t total = 4096;
+    for (int i = 0; i < nscans; i++) total += scans[i].len + 1200;
+    if (meta) total += meta->app_markers.size() + meta->icc_markers.size();
+    out.reserve(total);
+    ByteSink w(out);
+    write_file_header(w, g, opt, meta);
+    for (int si = 0; si < nscans; si++) {
+        const EncodedScan &e = scans[si];
+        for (int t = 0; t < 2; t++) for (int kind = 0; kind < 2; kind++) if (e.has_tab[kind][t]) {
+            w.u16(0xFFC4); w.u16(2 + 1 + 16 + e.nvals[kind][t]); w.u8((kind << 4) | t);
+            for (int l = 1; l <= 16; l++) w.u8(e.bits[kind][t][l]);
+            w.raw(e.vals[kind][t], e.nvals[kind][t]);
+        }
+        write_sos(w, g, opt.progressive, e.def);
+        w.raw(e.data, e.len);
     }
     w.u16(0xFFD9);
     return true;

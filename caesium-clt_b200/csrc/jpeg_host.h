@@ -78,6 +78,24 @@ void jpeg_fill_dummy_blocks(const JpegGeom &g, int16_t *coefs);
 bool jpeg_write(const JpegGeom &g, const int16_t *coefs, const JpegWriteOptions &opt, const JpegMeta *meta,
                 std::vector<uint8_t> &out, std::string &err);
 
+// The scan script both encoders (host writer, GPU entropy encoder) follow: sequential = one interleaved scan;
+// progressive = the 8-scan script mozjpeg's optimize_scans settled on for samples/j0.JPG.
+struct ScanDef { int ns, ci[3], Ss, Se, Ah, Al; };
+int jpeg_scan_script(const JpegGeom &g, bool progressive, ScanDef out[16]);
+// which of the four tables [kind 0 DC / 1 AC][tbl 0 luma / 1 chroma] a scan defines (emitted as DHT before its SOS)
+void jpeg_scan_tables_needed(const JpegGeom &g, bool progressive, const ScanDef &s, bool need[2][2]);
+
+// A scan whose entropy-coded segment was produced elsewhere (the GPU encoder): DHT payloads + stuffed bytes.
+struct EncodedScan {
+    ScanDef def;
+    bool has_tab[2][2];
+    uint8_t bits[2][2][17]; uint8_t vals[2][2][256]; int nvals[2][2];
+    const uint8_t *data; size_t len;
+};
+// Same file layout as jpeg_write (SOI, JFIF, carried markers, DQT, SOF, then per scan DHT* + SOS + data, EOI).
+bool jpeg_assemble(const JpegGeom &g, const JpegWriteOptions &opt, const JpegMeta *meta, const EncodedScan *scans, int nscans,
+                   std::vector<uint8_t> &out, std::string &err);
+
 // mozjpeg base table idx 3 scaled by jpeg_set_quality(q, force_baseline = FALSE); natural order
 void jpeg_quant_table(int quality, int which, uint16_t out_natural[64]);
 extern const uint8_t kZigzag[64];   // zigzag index -> natural position
