@@ -60,7 +60,7 @@ def build(force=False):
 _lib = None
 
 _SYMBOLS = [
-    "b200_params_default", "b200_init", "b200_init_device", "b200_shutdown", "b200_device_count", "b200_version", "b200_free",
+    "b200_params_default", "b200_set_entropy_mode", "b200_init", "b200_init_device", "b200_shutdown", "b200_device_count", "b200_version", "b200_free",
     "b200_compress_in_memory", "b200_convert_in_memory", "b200_compress_to_size_in_memory", "b200_compress_batch",
     "b200_sniff_format", "b200_jpeg_decode_coefficients", "b200_jpeg_output_layout", "b200_jpeg_requantize",
     "b200_jpeg_encode_coefficients", "b200_jpeg_decode_planes", "b200_jpeg_quant_table",
@@ -191,6 +191,21 @@ def jpeg_encode_coefficients(layout, coefs, progressive=True):
     outp, outl = C.c_void_p(), C.c_size_t()
     _check(lib().b200_jpeg_encode_coefficients(C.byref(layout), coefs.ctypes.data_as(C.c_void_p), int(bool(progressive)), C.byref(outp), C.byref(outl)))
     return _take(outp, outl)
+
+
+def jpeg_encode_coefficients_device(layout, coefs, progressive=True):
+    """Same encoder on the GPU (block-parallel statistics / tables / bit packing / stuffing); bytes identical."""
+    coefs = np.ascontiguousarray(coefs, dtype=np.int16)
+    outp, outl = C.c_void_p(), C.c_size_t()
+    f = lib().b200_jpeg_encode_coefficients_device
+    f.restype = Status
+    _check(f(C.byref(layout), coefs.ctypes.data_as(C.c_void_p), int(bool(progressive)), C.byref(outp), C.byref(outl)))
+    return _take(outp, outl)
+
+
+def set_entropy_mode(mode):
+    """1 = device entropy encoder (default), 0 = host encoder."""
+    return lib().b200_set_entropy_mode(int(mode))
 
 
 def jpeg_decode_planes(in_layout, in_coefs):

@@ -14,6 +14,7 @@
 #include <vector>
 #include "jpeg_device.h"
 #include "jpeg_host.h"
+#include "jpeg_gpuenc.h"
 #include "resize_kernels.h"
 
 using namespace b200;
@@ -33,6 +34,7 @@ b200_status make_status(int code, const std::string &msg)
 std::once_flag g_once;
 std::string g_init_err;
 int g_forced_device = -1, g_forced_ngpus = 0;
+std::atomic<int> g_entropy_mode{-1};     // -1 unset (env B200_ENTROPY, default gpu), 0 host encoder, 1 device encoder
 
 bool ensure_runtime(std::string &err)
 {
@@ -103,6 +105,7 @@ b200_status jpeg_compress(const uint8_t *in, size_t in_len, const b200_params *p
         return ok_status();
     }
     if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
+    if (g_entropy_mode.load() < 0) { const char *e = getenv("B200_ENTROPY"); g_entropy_mode.store(e && !strcmp(e, "host") ? 0 : 1); }
     JpegGeom gout;
     if (!jpeg_output_geom(gin, (int)p->jpeg_quality, (int)p->jpeg_chroma_subsampling, gout, err)) return make_status(B200_ERR_INVALID_ARGUMENT, err);
     const bool resize = p->width || p->height;
@@ -121,7 +124,19 @@ b200_status jpeg_compress(const uint8_t *in, size_t in_len, const b200_params *p
     do {
         if (!s->ensure(plan.in_bytes, plan.out_bytes, plan.scratch_bytes(), 1 << 14, err)) { st = make_status(B200_ERR_OUT_OF_MEMORY, err); break; }
         if (!rd.decode(s->h_in, err)) { st = make_status(B200_ERR_CORRUPT_INPUT, err); break; }
-        if (!(resize ? slot_transform_resized(s, gin, gout, err) : slot_transform(s, gin, gout, err))) { st = make_status(B200_ERR_CUDA, err); break; }
+        const bool gpu_entropy = g_entropy_mode.load() == 1;
+        if (!(resize ? slot_transform_resized(s, gin, gout, err, !gpu_entropy) : slot_transform(s, gin, gout, err, !gpu_entropy))) { st = make_status(B200_ERR_CUDA, err); break; }
+        if (gpu_entropy) {
+            // Huffman statistics, table construction, bit packing and 0xFF stuffing on the device (jpeg_gpuenc.cu); the
+            // host only frames the scans.  A scan that outgrows its device buffer falls back to the host ENCODER
+            // (still the same coefficients from the CUDA transform).
+            if (slot_gpu_encode(s, gout, wo.progressive, err)) {
+                if (!jpeg_assemble(gout, wo, &rd.meta(), s->enc->results.data(), (int)s->enc->results.size(), out, err)) st = make_status(B200_ERR_INVALID_ARGUMENT, err);
+                break;
+            }
+            if (!s->enc || !s->enc->overflow) { st = make_status(B200_ERR_CUDA, err); break; }
+            if (!slot_download_coefs(s, plan.out_bytes, err)) { st = make_status(B200_ERR_CUDA, err); break; }
+        }
         jpeg_fill_dummy_blocks(gout, s->h_out);
         if (!jpeg_write(gout, s->h_out, wo, &rd.meta(), out, err)) { st = make_status(B200_ERR_INVALID_ARGUMENT, err); break; }
     } while (0);
@@ -166,6 +181,7 @@ void b200_shutdown(void) { runtime_shutdown(); }
 int b200_device_count(void) { return runtime_device_count(); }
 const char *b200_version(void) { return "b200-caesium 0.1.0 (sm_100a)"; }
 void b200_free(void *p) { free(p); }
+int b200_set_entropy_mode(int mode) { if (mode != 0 && mode != 1) return B200_ERR_INVALID_ARGUMENT; g_entropy_mode.store(mode); return B200_OK; }
 
 uint32_t b200_sniff_format(const uint8_t *d, size_t n)
 {   // the magic numbers `infer` checks (scan_files.rs:30-40, compressor.rs:259-264)
@@ -319,6 +335,30 @@ b200_status b200_jpeg_encode_coefficients(const b200_jpeg_layout *layout, const 
     JpegWriteOptions wo; wo.progressive = progressive != 0;
     std::vector<uint8_t> v;
     if (!jpeg_write(g, coefs, wo, nullptr, v, err)) return make_status(B200_ERR_INVALID_ARGUMENT, err);
+    return give(v, out, out_len);
+}
+
+b200_status b200_jpeg_encode_coefficients_device(const b200_jpeg_layout *layout, const int16_t *coefs, int progressive, uint8_t **out, size_t *out_len)
+{
+    if (!layout || !coefs || !out || !out_len) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    std::string err; JpegGeom g;
+    if (!geom_from_layout(layout, g, err)) return make_status(B200_ERR_INVALID_ARGUMENT, err);
+    if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
+    Slot *s = slot_acquire(runtime_next_device(), err);
+    if (!s) return make_status(B200_ERR_CUDA, err);
+    b200_status st = ok_status();
+    std::vector<uint8_t> v;
+    do {
+        const size_t bytes = (size_t)g.total_coefs * 2;
+        if (!s->ensure(256, bytes, 256, 1 << 14, err)) { st = make_status(B200_ERR_OUT_OF_MEMORY, err); break; }
+        memcpy(s->h_out, coefs, bytes);
+        if (!slot_upload_out_coefs(s, bytes, err)) { st = make_status(B200_ERR_CUDA, err); break; }
+        JpegWriteOptions wo; wo.progressive = progressive != 0;
+        if (!slot_gpu_encode(s, g, wo.progressive, err)) { st = make_status(B200_ERR_CUDA, err); break; }
+        if (!jpeg_assemble(g, wo, nullptr, s->enc->results.data(), (int)s->enc->results.size(), v, err)) { st = make_status(B200_ERR_INVALID_ARGUMENT, err); break; }
+    } while (0);
+    slot_release(s);
+    if (st.code) return st;
     return give(v, out, out_len);
 }
 

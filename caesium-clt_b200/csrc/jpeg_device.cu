@@ -11,6 +11,7 @@
 #include <atomic>
 #include "jpeg_device.h"
 #include "resize_kernels.h"
+#include "jpeg_gpuenc.h"
 
 namespace b200 {
 
@@ -141,7 +142,7 @@ void runtime_shutdown()
         cudaSetDevice(d->ordinal);
         for (Slot *s : d->free_slots) {
             if (s->stream) cudaStreamDestroy((cudaStream_t)s->stream);
-            cudaFreeHost(s->h_in); cudaFreeHost(s->h_out); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_scratch); cudaFreeHost(s->h_par); cudaFree(s->d_par);
+            cudaFreeHost(s->h_in); cudaFreeHost(s->h_out); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_scratch); cudaFreeHost(s->h_par); cudaFree(s->d_par); delete s->enc;
             delete s;
         }
         delete d;
@@ -223,7 +224,7 @@ static void fill_tables(uint8_t *h_par, const JpegGeom &gin, const JpegGeom *gou
     for (int c = 0; c < gin.ncomp; c++) memcpy(dq + 64 * c, gin.qt[gin.tq[c]], 128);
 }
 
-bool slot_transform(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err)
+bool slot_transform(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err, bool download)
 {
     ImagePlan plan;
     if (!plan_image(gin, gout, plan, err)) return false;
@@ -239,9 +240,32 @@ bool slot_transform(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::str
     CU(cudaMemcpyAsync(s->d_in, s->h_in, plan.in_bytes, cudaMemcpyHostToDevice, st));
     int rc = launch_work(wl, reinterpret_cast<const CompWork *>(s->d_par + PAR_WORK), st, 0, nullptr);
     if (rc) { err = std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)rc); return false; }
+    if (!download) return true;          // the coefficients stay in HBM for the device entropy encoder
     CU(cudaMemcpyAsync(s->h_out, s->d_out, plan.out_bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return true;
+}
+
+bool slot_download_coefs(Slot *s, size_t out_bytes, std::string &err)
+{
+    cudaStream_t st = (cudaStream_t)s->stream;
+    CU(cudaMemcpyAsync(s->h_out, s->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return true;
+}
+
+bool slot_upload_out_coefs(Slot *s, size_t bytes, std::string &err)
+{
+    cudaStream_t st = (cudaStream_t)s->stream;
+    CU(cudaMemcpyAsync(s->d_out, s->h_out, bytes, cudaMemcpyHostToDevice, st));
+    return true;
+}
+
+bool slot_gpu_encode(Slot *s, const JpegGeom &gout, bool progressive, std::string &err)
+{
+    if (!s->enc) s->enc = new GpuEncoder();
+    int16_t *base = s->d_out;
+    return s->enc->encode(gout, progressive, &base, 1, s->stream, true, err);
 }
 
 bool slot_decode_planes(Slot *s, const JpegGeom &gin, uint8_t *planes, std::string &err)
@@ -282,7 +306,7 @@ bool slot_decode_planes(Slot *s, const JpegGeom &gin, uint8_t *planes, std::stri
 }
 
 // ---- resize path: decode -> (YCbCr->RGB) -> Lanczos3 -> (RGB->YCbCr) -> encode side --------------------------------
-bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err)
+bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err, bool download)
 {
     const int W = gin.width, H = gin.height, NW = gout.width, NH = gout.height, nc = gin.ncomp;
     if (gout.ncomp != nc) { err = "component count mismatch"; return false; }
@@ -359,6 +383,7 @@ bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, 
     if (nc == 3 && !chk(launch_rgb_to_ycc(rz[0], rz[1], rz[2], (size_t)NW * NH, st), "rgb_to_ycc")) return false;
     if (!chk(launch_downsample(p_down, nc, wl.max_dn_w, wl.max_dn_h, st), "downsample")) return false;
     if (!chk(launch_fdct_plane(p_fdct, nc, wl.max_fdct, st), "fdct")) return false;
+    if (!download) return true;
     CU(cudaMemcpyAsync(s->h_out, s->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return true;

@@ -1,0 +1,390 @@
+// jpeg_gpuenc.cu -- the block-parallel JPEG entropy encoder on the device.  Every pass is a thin
+// CUDA wrapper around a body from jpeg_gpuenc_core.h (the same bodies tests/emul/ runs serially on the CPU); the
+// cross-block dependencies of jchuff.c / jcphuff.c (DC prediction, EOB runs, buffered correction bits, bit positions,
+// 0xFF stuffing) are resolved with prefix scans (CUB DeviceScan -- plumbing, not one of the path's named kernels).
+//
+// Passes (one launch each for ANY number of images x scans; blockIdx.y = scan):
+//   classify -> [max-scan: previous event] [sum-scan: trailing correction bits] -> groups -> histogram -> tables ->
+//   lengths -> [sum-scan: bit offsets] -> totals | host sync: sizes | zero -> emit -> ffcount -> [sum-scan] -> layout ->
+//   scatter (byte stuffing) | D2H: stuffed scans + DHT payloads.
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+#include <algorithm>
+#include <cstring>
+#include "jpeg_gpuenc.h"
+
+namespace b200 {
+
+using namespace ge;
+
+#define CU(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(e_); return false; } } while (0)
+
+// ---- kernels ------------------------------------------------------------------------------------------------------
+__global__ void k_ge_classify(const Scan *__restrict__ scans, uint32_t *__restrict__ meta, int *__restrict__ evkey, uint32_t *__restrict__ tail)
+{
+    const Scan s = scans[blockIdx.y];
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= s.nblocks) return;
+    const BlockRef b = locate(s, u);
+    const uint32_t m = classify(s, b.blk);
+    const long long g = s.unit_base + u;
+    meta[g] = m;
+    evkey[g] = meta_event(m) ? (int)g : -1;
+    tail[g] = (uint32_t)meta_tail(m);
+}
+
+__global__ void k_ge_groups(const Scan *__restrict__ scans, const uint32_t *__restrict__ meta, const int *__restrict__ evkey,
+                            const int *__restrict__ prev, const uint32_t *__restrict__ tsum, uint32_t *__restrict__ gcount)
+{
+    const Scan s = scans[blockIdx.y];
+    if (s.mode != MODE_AC_FIRST && s.mode != MODE_AC_REFINE) return;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > s.nblocks) return;
+    int pg;
+    if (b < s.nblocks) { if (!meta_event(meta[s.unit_base + b])) return; pg = prev[s.unit_base + b]; }
+    else { const long long last = s.unit_base + s.nblocks - 1; pg = max(prev[last], evkey[last]); }
+    const int pl = pg >= s.unit_base ? (int)(pg - s.unit_base) : -1;
+    assign_groups(meta + s.unit_base, tsum + s.unit_base, s.nblocks, pl, b, gcount + s.unit_base);
+}
+
+__global__ void k_ge_hist(const Scan *__restrict__ scans, const uint32_t *__restrict__ gcount, uint32_t *__restrict__ hist)
+{
+    __shared__ uint32_t h[4 * 256];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    const Scan s = scans[blockIdx.y];
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < s.nblocks) {
+        auto add = [&](int idx) { atomicAdd(&h[idx], 1u); };
+        HistSink<decltype(add)> sk(add);
+        gen_block(s, locate(s, u), gcount[s.unit_base + u], sk);
+    }
+    __syncthreads();
+    uint32_t *g = hist + (size_t)s.tab_base * 256;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) if (h[i]) atomicAdd(&g[i], h[i]);
+}
+
+// jchuff.c jpeg_gen_optimal_table with the two minimum searches spread over a warp (ties resolve to the LARGEST index,
+// exactly like the sequential `<=` scans); the chain merges and the canonical code assignment stay on lane 0.
+__global__ void k_ge_tables(const uint32_t *__restrict__ hist, Table *__restrict__ tabs, DhtOut *__restrict__ dht)
+{
+    __shared__ long long freq[257];
+    __shared__ int codesize[257], others[257];
+    __shared__ uint8_t bits[33];
+    const int t = blockIdx.x, lane = threadIdx.x;
+    const uint32_t *f = hist + (size_t)t * 256;
+    for (int i = lane; i < 257; i += 32) { freq[i] = i < 256 ? (long long)f[i] : 1; codesize[i] = 0; others[i] = -1; }
+    if (lane == 0) for (int i = 0; i < 33; i++) bits[i] = 0;
+    __syncwarp();
+    for (;;) {
+        // c1 = argmin over freq > 0, largest index among ties
+        long long v1 = 1000000000LL; int c1 = -1;
+        for (int i = lane; i < 257; i += 32) { const long long fi = freq[i]; if (fi && fi <= v1) { v1 = fi; c1 = i; } }
+        for (int o = 16; o; o >>= 1) {
+            const long long ov = __shfl_xor_sync(0xFFFFFFFFu, v1, o); const int oc = __shfl_xor_sync(0xFFFFFFFFu, c1, o);
+            if (oc >= 0 && (c1 < 0 || ov < v1 || (ov == v1 && oc > c1))) { v1 = ov; c1 = oc; }
+        }
+        long long v2 = 1000000000LL; int c2 = -1;
+        for (int i = lane; i < 257; i += 32) { const long long fi = freq[i]; if (fi && fi <= v2 && i != c1) { v2 = fi; c2 = i; } }
+        for (int o = 16; o; o >>= 1) {
+            const long long ov = __shfl_xor_sync(0xFFFFFFFFu, v2, o); const int oc = __shfl_xor_sync(0xFFFFFFFFu, c2, o);
+            if (oc >= 0 && (c2 < 0 || ov < v2 || (ov == v2 && oc > c2))) { v2 = ov; c2 = oc; }
+        }
+        if (c2 < 0) break;
+        if (lane == 0) {
+            int a = c1, b = c2;
+            freq[a] += freq[b]; freq[b] = 0;
+            codesize[a]++; while (others[a] >= 0) { a = others[a]; codesize[a]++; }
+            others[a] = b;
+            codesize[b]++; while (others[b] >= 0) { b = others[b]; codesize[b]++; }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        Table &T = tabs[t];
+        for (int i = 0; i <= 256; i++) if (codesize[i]) bits[codesize[i] > 32 ? 32 : codesize[i]]++;
+        for (int i = 32; i > 16; i--) while (bits[i] > 0) {
+            int j = i - 2; while (bits[j] == 0) j--;
+            bits[i] -= 2; bits[i - 1]++; bits[j + 1] += 2; bits[j]--;
+        }
+        int i = 16; while (i > 0 && bits[i] == 0) i--;
+        if (i > 0) bits[i]--;
+        int p = 0;
+        for (int l = 1; l <= 32; l++) for (int s = 0; s <= 255; s++) if (codesize[s] == l) T.vals[p++] = (uint8_t)s;
+        T.nvals = p;
+        for (int k = 0; k < 17; k++) T.bits[k] = bits[k];
+        for (int s = 0; s < 256; s++) { T.code[s] = 0; T.size[s] = 0; }
+        uint32_t code = 0; int k = 0;
+        for (int l = 1; l <= 16; l++) { for (int n = 0; n < bits[l]; n++, k++) { T.code[T.vals[k]] = code++; T.size[T.vals[k]] = (uint8_t)l; } code <<= 1; }
+        DhtOut &D = dht[t];
+        D.nvals = p;
+        for (int k2 = 0; k2 < 17; k2++) D.bits[k2] = bits[k2];
+        for (int k2 = 0; k2 < p; k2++) D.vals[k2] = T.vals[k2];
+    }
+}
+
+__global__ void k_ge_len(const Scan *__restrict__ scans, const uint32_t *__restrict__ gcount, const Table *__restrict__ tabs, uint32_t *__restrict__ bitlen)
+{
+    const Scan s = scans[blockIdx.y];
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= s.nblocks) return;
+    LenSink sk; sk.tabs = tabs + s.tab_base;
+    gen_block(s, locate(s, u), gcount[s.unit_base + u], sk);
+    bitlen[s.unit_base + u] = (uint32_t)sk.bits;
+}
+
+__global__ void k_ge_totals(const Scan *__restrict__ scans, int nscans, const uint32_t *__restrict__ bitlen, const uint32_t *__restrict__ bitoff, uint32_t *__restrict__ total)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nscans) return;
+    const Scan s = scans[i];
+    const long long last = s.unit_base + s.nblocks - 1;
+    total[i] = s.nblocks ? bitoff[last] + bitlen[last] - bitoff[s.unit_base] : 0;
+}
+
+__global__ void k_ge_zero(const Scan *__restrict__ scans, const ScanOut *__restrict__ so, uint32_t *__restrict__ words)
+{
+    const Scan s = scans[blockIdx.y];
+    const long long n = ((long long)so[blockIdx.y].total_bits + 31) / 32 + 1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n && i < s.word_cap; i += (long long)gridDim.x * blockDim.x) words[s.word_base + i] = 0;
+}
+
+__global__ void k_ge_emit(const Scan *__restrict__ scans, const uint32_t *__restrict__ gcount, const Table *__restrict__ tabs,
+                          const uint32_t *__restrict__ bitoff, uint32_t *__restrict__ words)
+{
+    const Scan s = scans[blockIdx.y];
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= s.nblocks) return;
+    auto orw = [&](long long i, uint32_t v) { if (v) atomicOr(&words[i], v); };
+    EmitSink<decltype(orw)> sk(tabs + s.tab_base, orw, s.word_base, (unsigned long long)(bitoff[s.unit_base + u] - bitoff[s.unit_base]));
+    gen_block(s, locate(s, u), gcount[s.unit_base + u], sk);
+    sk.finish();
+}
+
+// byte i of a scan's unstuffed stream (big-endian within words), with flush_bits' padding ones in the last byte
+__device__ __forceinline__ uint32_t scan_byte(const uint32_t *__restrict__ w, uint32_t i, uint32_t nbytes, uint32_t total_bits)
+{
+    uint32_t b = (w[i >> 2] >> (24 - 8 * (i & 3))) & 0xFF;
+    if (i == nbytes - 1 && (total_bits & 7)) b |= (1u << (8 - (total_bits & 7))) - 1u;
+    return b;
+}
+
+__global__ void k_ge_ffcount(const Scan *__restrict__ scans, const ScanOut *__restrict__ so, const uint32_t *__restrict__ words, uint32_t *__restrict__ ffcount)
+{
+    const ScanOut o = so[blockIdx.y];
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= o.ngroups) return;
+    const uint32_t *w = words + scans[blockIdx.y].word_base;
+    uint32_t n = 0;
+    for (uint32_t i = g * 16; i < g * 16 + 16 && i < o.nbytes; i++) n += scan_byte(w, i, o.nbytes, o.total_bits) == 0xFF;
+    ffcount[o.group_base + g] = n;
+}
+
+// per image: lay its scans out back to back in the output buffer; out_off / out_len per scan
+__global__ void k_ge_layout(const ScanOut *__restrict__ so, int scans_per_image, int nimages, const uint32_t *__restrict__ ffcount, const uint32_t *__restrict__ ffoff,
+                            uint32_t *__restrict__ out_off, uint32_t *__restrict__ out_len)
+{
+    const int im = blockIdx.x * blockDim.x + threadIdx.x;
+    if (im >= nimages) return;
+    uint32_t off = 0;
+    for (int k = 0; k < scans_per_image; k++) {
+        const int si = im * scans_per_image + k;
+        const ScanOut o = so[si];
+        uint32_t ff = 0;
+        if (o.ngroups) { const uint32_t lastg = o.group_base + o.ngroups - 1; ff = ffoff[lastg] + ffcount[lastg] - ffoff[o.group_base]; }
+        out_off[si] = off; out_len[si] = o.nbytes + ff;
+        off += o.nbytes + ff;
+    }
+}
+
+__global__ void k_ge_scatter(const Scan *__restrict__ scans, const ScanOut *__restrict__ so, const uint32_t *__restrict__ words, const uint32_t *__restrict__ ffoff,
+                             const uint32_t *__restrict__ out_off, uint8_t *__restrict__ out, int scans_per_image, size_t out_image_stride)
+{
+    const ScanOut o = so[blockIdx.y];
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= o.ngroups) return;
+    const uint32_t *w = words + scans[blockIdx.y].word_base;
+    uint8_t *dst = out + (size_t)(blockIdx.y / scans_per_image) * out_image_stride + out_off[blockIdx.y] + (size_t)g * 16 + (ffoff[o.group_base + g] - ffoff[o.group_base]);
+    for (uint32_t i = g * 16; i < g * 16 + 16 && i < o.nbytes; i++) {
+        const uint32_t b = scan_byte(w, i, o.nbytes, o.total_bits);
+        *dst++ = (uint8_t)b;
+        if (b == 0xFF) *dst++ = 0;
+    }
+}
+
+// dummy blocks of partial MCUs (jccoefct.c / jctrans.c rule, jpeg_fill_dummy_blocks on the host): AC = 0, DC copied
+__global__ void k_ge_fill_dummy(int16_t *__restrict__ coef, long long comp_off, int bw, int bh, int rbw, int rbh, int hs)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= bw * bh) return;
+    const int row = i / bw, col = i - row * bw;
+    if (row < rbh && col < rbw) return;
+    int r = row, c = col;
+    while (r >= rbh || c >= rbw) { if (r >= rbh) { c = (c / hs) * hs + hs - 1; r--; } else c = rbw - 1; }
+    int16_t *base = coef + comp_off;
+    int16_t *dst = base + ((long long)row * bw + col) * 64;
+    const int16_t dc = base[((long long)r * bw + c) * 64];
+    for (int k = 1; k < 64; k++) dst[k] = 0;
+    dst[0] = dc;
+}
+
+// ---- host orchestration ---------------------------------------------------------------------------------------------
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+template <typename T> static bool grow(T *&p, size_t &cap, size_t need, bool host, std::string &err)
+{
+    if (need <= cap) return true;
+    if (p) { if (host) cudaFreeHost(p); else cudaFree(p); }
+    p = nullptr; cap = 0;
+    size_t want = align_up(need + need / 4, 1 << 12);
+    void *q = nullptr;
+    cudaError_t e = host ? cudaHostAlloc(&q, want, cudaHostAllocDefault) : cudaMalloc(&q, want);
+    if (e != cudaSuccess) { err = std::string(host ? "cudaHostAlloc: " : "cudaMalloc: ") + cudaGetErrorString(e); return false; }
+    p = (T *)q; cap = want; return true;
+}
+
+GpuEncoder::~GpuEncoder()
+{
+    cudaFree(d_scans); cudaFree(d_meta); cudaFree(d_evkey); cudaFree(d_prev); cudaFree(d_tail); cudaFree(d_tsum); cudaFree(d_gcount);
+    cudaFree(d_bitlen); cudaFree(d_bitoff); cudaFree(d_hist); cudaFree(d_tabs); cudaFree(d_dht); cudaFree(d_total); cudaFree(d_so);
+    cudaFree(d_words); cudaFree(d_ffcount); cudaFree(d_ffoff); cudaFree(d_outoff); cudaFree(d_outlen); cudaFree(d_out); cudaFree(d_temp);
+    cudaFreeHost(h_small); cudaFreeHost(h_out);
+}
+
+bool GpuEncoder::encode(const JpegGeom &g, bool progressive, int16_t *const *d_coefs, int nimages, void *stream_, bool fill_dummy, std::string &err)
+{
+    cudaStream_t st = (cudaStream_t)stream_;
+    std::vector<const int16_t *> bases(d_coefs, d_coefs + nimages);
+    gpuenc_plan(g, progressive, bases.data(), nimages, plan);
+    nimg = nimages;
+    const int NS = (int)plan.scans.size();
+    const long long U = plan.total_units;
+    if (U >= (1ll << 31)) { err = "batch too large for the entropy encoder"; return false; }
+    int max_units = 0; for (auto &s : plan.scans) max_units = std::max(max_units, s.nblocks);
+    // ---- buffers
+    size_t c;
+    c = cap_scans; if (!grow(d_scans, c, NS * sizeof(Scan), false, err)) return false; cap_scans = c;
+    c = cap_u[0]; if (!grow(d_meta, c, U * 4, false, err)) return false; cap_u[0] = c;
+    c = cap_u[1]; if (!grow(d_evkey, c, U * 4, false, err)) return false; cap_u[1] = c;
+    c = cap_u[2]; if (!grow(d_prev, c, U * 4, false, err)) return false; cap_u[2] = c;
+    c = cap_u[3]; if (!grow(d_tail, c, U * 4, false, err)) return false; cap_u[3] = c;
+    c = cap_u[4]; if (!grow(d_tsum, c, U * 4, false, err)) return false; cap_u[4] = c;
+    c = cap_u[5]; if (!grow(d_gcount, c, U * 4, false, err)) return false; cap_u[5] = c;
+    c = cap_u[6]; if (!grow(d_bitlen, c, U * 4, false, err)) return false; cap_u[6] = c;
+    c = cap_u[7]; if (!grow(d_bitoff, c, U * 4, false, err)) return false; cap_u[7] = c;
+    c = cap_hist; if (!grow(d_hist, c, (size_t)NS * 4 * 256 * 4, false, err)) return false; cap_hist = c;
+    c = cap_tabs; if (!grow(d_tabs, c, (size_t)NS * 4 * sizeof(Table), false, err)) return false; cap_tabs = c;
+    c = cap_dht; if (!grow(d_dht, c, (size_t)NS * 4 * sizeof(DhtOut), false, err)) return false; cap_dht = c;
+    c = cap_total; if (!grow(d_total, c, (size_t)NS * 4, false, err)) return false; cap_total = c;
+    c = cap_so; if (!grow(d_so, c, (size_t)NS * sizeof(ScanOut), false, err)) return false; cap_so = c;
+    c = cap_oo; if (!grow(d_outoff, c, (size_t)NS * 4, false, err)) return false; cap_oo = c;
+    c = cap_ol; if (!grow(d_outlen, c, (size_t)NS * 4, false, err)) return false; cap_ol = c;
+    c = cap_words; if (!grow(d_words, c, (size_t)plan.total_words * 4, false, err)) return false; cap_words = c;
+    const size_t small_bytes = align_up((size_t)NS * sizeof(Scan), 256) + align_up((size_t)NS * sizeof(ScanOut), 256) + align_up((size_t)NS * 4, 256) * 2 + align_up((size_t)NS * 4 * sizeof(DhtOut), 256);
+    c = cap_small; if (!grow(h_small, c, small_bytes, true, err)) return false; cap_small = c;
+    size_t tb1 = 0, tb2 = 0;
+    cub::DeviceScan::ExclusiveScan((void *)nullptr, tb1, d_evkey, d_prev, cub::Max(), -1, (int)U, st);
+    cub::DeviceScan::ExclusiveSum((void *)nullptr, tb2, d_tail, d_tsum, (int)U, st);
+    c = cap_temp; if (!grow(d_temp, c, std::max(tb1, tb2) + 256, false, err)) return false; cap_temp = c;
+    uint8_t *hp = h_small;
+    Scan *h_scans = reinterpret_cast<Scan *>(hp); hp += align_up((size_t)NS * sizeof(Scan), 256);
+    ScanOut *h_so = reinterpret_cast<ScanOut *>(hp); hp += align_up((size_t)NS * sizeof(ScanOut), 256);
+    uint32_t *h_total = reinterpret_cast<uint32_t *>(hp); hp += align_up((size_t)NS * 4, 256);
+    uint32_t *h_outlen = reinterpret_cast<uint32_t *>(hp); hp += align_up((size_t)NS * 4, 256);
+    DhtOut *h_dht = reinterpret_cast<DhtOut *>(hp);
+    memcpy(h_scans, plan.scans.data(), NS * sizeof(Scan));
+    CU(cudaMemcpyAsync(d_scans, h_scans, NS * sizeof(Scan), cudaMemcpyHostToDevice, st));
+    if (fill_dummy) {
+        for (int im = 0; im < nimages; im++) for (int cc = 0; cc < g.ncomp; cc++) {
+            if (g.rbw[cc] == g.bw[cc] && g.rbh[cc] == g.bh[cc]) continue;
+            k_ge_fill_dummy<<<cdiv((long long)g.bw[cc] * g.bh[cc], 256), 256, 0, st>>>(d_coefs[im], g.comp_offset[cc], g.bw[cc], g.bh[cc], g.rbw[cc], g.rbh[cc], g.hs[cc]);
+        }
+    }
+    const dim3 gu(cdiv(max_units, 128), NS), gu1(cdiv(max_units + 1, 128), NS);
+    k_ge_classify<<<gu, 128, 0, st>>>(d_scans, d_meta, d_evkey, d_tail);
+    size_t tb = cap_temp;
+    cub::DeviceScan::ExclusiveScan(d_temp, tb, d_evkey, d_prev, cub::Max(), -1, (int)U, st);
+    tb = cap_temp;
+    cub::DeviceScan::ExclusiveSum(d_temp, tb, d_tail, d_tsum, (int)U, st);
+    CU(cudaMemsetAsync(d_gcount, 0, U * 4, st));
+    k_ge_groups<<<gu1, 128, 0, st>>>(d_scans, d_meta, d_evkey, d_prev, d_tsum, d_gcount);
+    CU(cudaMemsetAsync(d_hist, 0, (size_t)NS * 4 * 256 * 4, st));
+    k_ge_hist<<<gu, 128, 0, st>>>(d_scans, d_gcount, d_hist);
+    k_ge_tables<<<NS * 4, 32, 0, st>>>(d_hist, d_tabs, d_dht);
+    k_ge_len<<<gu, 128, 0, st>>>(d_scans, d_gcount, d_tabs, d_bitlen);
+    tb = cap_temp;
+    cub::DeviceScan::ExclusiveSum(d_temp, tb, d_bitlen, d_bitoff, (int)U, st);
+    k_ge_totals<<<cdiv(NS, 128), 128, 0, st>>>(d_scans, NS, d_bitlen, d_bitoff, d_total);
+    CU(cudaMemcpyAsync(h_total, d_total, (size_t)NS * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    // ---- sizes are known: lay out the stuffing stage
+    uint32_t groups = 0; size_t img_bytes_max = 0, img_bytes = 0; uint32_t max_groups = 0; long long max_words = 0;
+    for (int si = 0; si < NS; si++) {
+        if ((long long)((h_total[si] + 31) / 32) + 1 > plan.scans[si].word_cap) { err = "entropy-coded scan exceeds its device buffer"; overflow = true; return false; }
+        ScanOut &o = h_so[si];
+        o.total_bits = h_total[si]; o.nbytes = (h_total[si] + 7) / 8; o.ngroups = (o.nbytes + 15) / 16; o.group_base = groups;
+        groups += o.ngroups; max_groups = std::max(max_groups, o.ngroups); max_words = std::max<long long>(max_words, (h_total[si] + 31) / 32 + 1);
+        img_bytes += o.nbytes;
+        if ((si + 1) % plan.scans_per_image == 0) { img_bytes_max = std::max(img_bytes_max, img_bytes); img_bytes = 0; }
+    }
+    overflow = false;
+    out_stride = align_up(img_bytes_max * 2 + 64, 256);            // worst case: every byte stuffed
+    copy_bytes = std::min(out_stride, align_up(img_bytes_max + img_bytes_max / 8 + 256, 256));
+    c = cap_ff[0]; if (!grow(d_ffcount, c, (size_t)groups * 4 + 4, false, err)) return false; cap_ff[0] = c;
+    c = cap_ff[1]; if (!grow(d_ffoff, c, (size_t)groups * 4 + 4, false, err)) return false; cap_ff[1] = c;
+    c = cap_out; if (!grow(d_out, c, out_stride * nimages, false, err)) return false; cap_out = c;
+    c = cap_hout; if (!grow(h_out, c, copy_bytes * nimages, true, err)) return false; cap_hout = c;
+    size_t tb3 = 0; cub::DeviceScan::ExclusiveSum((void *)nullptr, tb3, d_ffcount, d_ffoff, (int)groups, st);
+    c = cap_temp; if (!grow(d_temp, c, tb3 + 256, false, err)) return false; cap_temp = c;
+    CU(cudaMemcpyAsync(d_so, h_so, (size_t)NS * sizeof(ScanOut), cudaMemcpyHostToDevice, st));
+    k_ge_zero<<<dim3(std::max(1, std::min(cdiv(max_words, 256), 256)), NS), 256, 0, st>>>(d_scans, d_so, d_words);
+    k_ge_emit<<<gu, 128, 0, st>>>(d_scans, d_gcount, d_tabs, d_bitoff, d_words);
+    if (groups) {
+        const dim3 gg(cdiv(max_groups, 128), NS);
+        k_ge_ffcount<<<gg, 128, 0, st>>>(d_scans, d_so, d_words, d_ffcount);
+        tb = cap_temp;
+        cub::DeviceScan::ExclusiveSum(d_temp, tb, d_ffcount, d_ffoff, (int)groups, st);
+        k_ge_layout<<<cdiv(nimages, 64), 64, 0, st>>>(d_so, plan.scans_per_image, nimages, d_ffcount, d_ffoff, d_outoff, d_outlen);
+        k_ge_scatter<<<gg, 128, 0, st>>>(d_scans, d_so, d_words, d_ffoff, d_outoff, d_out, plan.scans_per_image, out_stride);
+    } else {
+        k_ge_layout<<<cdiv(nimages, 64), 64, 0, st>>>(d_so, plan.scans_per_image, nimages, d_ffcount, d_ffoff, d_outoff, d_outlen);
+    }
+    CU(cudaMemcpyAsync(h_outlen, d_outlen, (size_t)NS * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_dht, d_dht, (size_t)NS * 4 * sizeof(DhtOut), cudaMemcpyDeviceToHost, st));
+    for (int im = 0; im < nimages; im++) CU(cudaMemcpyAsync(h_out + (size_t)im * copy_bytes, d_out + (size_t)im * out_stride, copy_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    // rare: an image stuffed more than the copied margin -> fetch the rest
+    for (int im = 0; im < nimages; im++) {
+        size_t tot = 0; for (int k = 0; k < plan.scans_per_image; k++) tot += h_outlen[im * plan.scans_per_image + k];
+        if (tot > copy_bytes) {
+            c = cap_hout; // grow keeps no data: re-copy everything at full stride
+            std::vector<uint8_t> keep;  (void)keep;
+            if (!grow(h_out, c, out_stride * nimages, true, err)) return false; cap_hout = c;
+            copy_bytes = out_stride;
+            for (int j = 0; j < nimages; j++) CU(cudaMemcpyAsync(h_out + (size_t)j * copy_bytes, d_out + (size_t)j * out_stride, copy_bytes, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            break;
+        }
+    }
+    // ---- describe the result
+    results.assign((size_t)NS, EncodedScan());
+    for (int si = 0; si < NS; si++) {
+        EncodedScan &e = results[si];
+        const int im = si / plan.scans_per_image, k = si % plan.scans_per_image;
+        e.def = plan.defs[k];
+        size_t off = 0; for (int j = 0; j < k; j++) off += h_outlen[im * plan.scans_per_image + j];
+        e.data = h_out + (size_t)im * copy_bytes + off; e.len = h_outlen[si];
+        bool need[2][2]; jpeg_scan_tables_needed(g, progressive, e.def, need);
+        for (int kind = 0; kind < 2; kind++) for (int t = 0; t < 2; t++) {
+            e.has_tab[kind][t] = need[kind][t];
+            const DhtOut &D = h_dht[(size_t)si * 4 + kind * 2 + t];
+            memcpy(e.bits[kind][t], D.bits, 17); memcpy(e.vals[kind][t], D.vals, 256); e.nvals[kind][t] = D.nvals;
+        }
+    }
+    return true;
+}
+
+} // namespace b200

@@ -1,0 +1,50 @@
+// jpeg_gpuenc.h -- device-side JPEG entropy encoder (see jpeg_gpuenc.cu / jpeg_gpuenc_core.h).
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <string>
+#include <vector>
+#include "jpeg_gpuenc_plan.h"
+
+namespace b200 {
+
+struct DhtOut { uint8_t bits[17]; uint8_t vals[256]; int32_t nvals; };
+struct ScanOut { uint32_t total_bits, nbytes, ngroups, group_base; };
+
+// One encoder instance per slot (or per megabatch): owns its device / pinned buffers and grows them on demand.
+class GpuEncoder {
+public:
+    GpuEncoder() = default;
+    ~GpuEncoder();
+    GpuEncoder(const GpuEncoder &) = delete;
+    GpuEncoder &operator=(const GpuEncoder &) = delete;
+    // Entropy-code `nimages` coefficient buffers of geometry g that already sit in device memory.  Blocking on `stream`
+    // (two short host syncs: scan sizes, then the stuffed bytes).  On success results[image * scans_per_image + k]
+    // describes scan k (pointers into this object's pinned buffer, valid until the next call).
+    bool encode(const JpegGeom &g, bool progressive, int16_t *const *d_coefs, int nimages, void *stream, bool fill_dummy, std::string &err);
+    std::vector<EncodedScan> results;
+    GpuEncPlan plan;
+    bool overflow = false;      // the failure was "scan larger than its buffer": the caller may use the host encoder
+    int launches = 0;
+private:
+    int nimg = 0;
+    ge::Scan *d_scans = nullptr; size_t cap_scans = 0;
+    uint32_t *d_meta = nullptr, *d_tail = nullptr, *d_tsum = nullptr, *d_gcount = nullptr, *d_bitlen = nullptr, *d_bitoff = nullptr;
+    int *d_evkey = nullptr, *d_prev = nullptr;
+    size_t cap_u[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t *d_hist = nullptr; size_t cap_hist = 0;
+    ge::Table *d_tabs = nullptr; size_t cap_tabs = 0;
+    DhtOut *d_dht = nullptr; size_t cap_dht = 0;
+    uint32_t *d_total = nullptr; size_t cap_total = 0;
+    ScanOut *d_so = nullptr; size_t cap_so = 0;
+    uint32_t *d_words = nullptr; size_t cap_words = 0;
+    uint32_t *d_ffcount = nullptr, *d_ffoff = nullptr; size_t cap_ff[2] = {0, 0};
+    uint32_t *d_outoff = nullptr, *d_outlen = nullptr; size_t cap_oo = 0, cap_ol = 0;
+    uint8_t *d_out = nullptr; size_t cap_out = 0;
+    uint8_t *d_temp = nullptr; size_t cap_temp = 0;
+    uint8_t *h_small = nullptr; size_t cap_small = 0;
+    uint8_t *h_out = nullptr; size_t cap_hout = 0;
+    size_t out_stride = 0, copy_bytes = 0;
+};
+
+} // namespace b200

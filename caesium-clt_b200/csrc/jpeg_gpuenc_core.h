@@ -181,8 +181,7 @@ GE_HD void gen_block(const Scan &s, const BlockRef &b, unsigned group_count, Sin
     int EOB = 0;
     for (int k = s.Ss; k <= s.Se; k++) { int t = blk[k]; if (t < 0) t = -t; if ((t >> s.Al) == 1) EOB = k; }
     int r = 0;
-    unsigned pend = 0; int npend = 0;           // pending correction bits of this block (at most 63)
-    unsigned long long pend64 = 0;
+    int npend = 0; unsigned long long pend64 = 0;   // pending correction bits of this block (at most 63)
     for (int k = s.Ss; k <= s.Se; k++) {
         int t = blk[k]; if (t < 0) t = -t; t >>= s.Al;
         if (t == 0) { r++; continue; }
@@ -195,7 +194,6 @@ GE_HD void gen_block(const Scan &s, const BlockRef &b, unsigned group_count, Sin
         if (npend) { sk.raw64(npend, pend64); npend = 0; pend64 = 0; }
         r = 0;
     }
-    (void)pend;
     if (group_count) gen_eob_token(group_count, tbl, sk);
     if (npend) sk.raw64(npend, pend64);         // T_j: trailing correction bits, after the group's EOBn symbol
 }
@@ -247,14 +245,14 @@ struct EmitSink {
 // ---- EOB groups (pass "groups"): called for every event unit b and once for b == nblocks (end of scan) -------------
 // prev_ev = index of the last event unit before b (-1 if none); meta/tsum are the scan's per-unit arrays (tsum =
 // exclusive prefix sum of trailing correction bits); writes gcount[j] = block count of the group opened at j.
-GE_HD void assign_groups(const uint32_t *meta, const unsigned long long *tsum, int nblocks, int prev_ev, int b, uint32_t *gcount)
+GE_HD void assign_groups(const uint32_t *meta, const uint32_t *tsum, int nblocks, int prev_ev, int b, uint32_t *gcount)
 {
     int gs = prev_ev < 0 ? 0 : (meta_contrib(meta[prev_ev]) ? prev_ev : prev_ev + 1);   // first contributor of the run
     if (gs >= b) return;
     const int count = b - gs;
-    const unsigned long long tend = b < nblocks ? tsum[b] : tsum[nblocks - 1] + (unsigned long long)meta_tail(meta[nblocks - 1]);
-    const unsigned long long tailbits = tend - tsum[gs];
-    if (count < EOBRUN_MAX && tailbits <= (unsigned long long)CORR_FLUSH) { gcount[gs] = (uint32_t)count; return; }
+    const uint32_t tend = b < nblocks ? tsum[b] : tsum[nblocks - 1] + (uint32_t)meta_tail(meta[nblocks - 1]);
+    const uint32_t tailbits = tend - tsum[gs];          // modular difference: exact while a run holds < 2^32 bits
+    if (count < EOBRUN_MAX && tailbits <= (uint32_t)CORR_FLUSH) { gcount[gs] = (uint32_t)count; return; }
     // rare: the run overflows a counter; replay jcphuff.c's sequential rule over it
     int start = gs, n = 0; unsigned be = 0;
     for (int j = gs; j < b; j++) {

@@ -81,6 +81,9 @@ void b200_shutdown(void);
 int  b200_device_count(void);         /* devices the library is driving (0 before init / without GPU) */
 const char *b200_version(void);
 void b200_free(void *p);
+/* Where the JPEG entropy ENCODER runs: 1 (default; env B200_ENTROPY=gpu) = on the device next to the transform kernels,
+ * 0 (B200_ENTROPY=host) = jchuff/jcphuff-style encoder on the calling host thread.  Output bytes are identical. */
+int  b200_set_entropy_mode(int mode);
 
 /* ---- the three calls of compressor.rs:287-306 -------------------------------------------------- */
 /* replaces caesium::compress_in_memory (compressor.rs:305) */
@@ -128,6 +131,10 @@ b200_status b200_jpeg_requantize(const b200_jpeg_layout *in_layout, const int16_
 /* host: entropy-code coefficients (optimised Huffman tables; progressive = mozjpeg-style 8-scan script) */
 b200_status b200_jpeg_encode_coefficients(const b200_jpeg_layout *layout, const int16_t *coefs, int progressive,
                                           uint8_t **out, size_t *out_len);
+/* device: the same encoder as b200_jpeg_encode_coefficients run on the GPU (statistics, optimal tables, bit packing, byte
+ * stuffing as block-parallel kernels); output bytes are identical */
+b200_status b200_jpeg_encode_coefficients_device(const b200_jpeg_layout *layout, const int16_t *coefs, int progressive,
+                                                 uint8_t **out, size_t *out_len);
 /* device: dequant + IDCT + fancy upsample to planar full-resolution native-space planes [ncomp][H][W] */
 b200_status b200_jpeg_decode_planes(const b200_jpeg_layout *in_layout, const int16_t *in_coefs, uint8_t *planes);
 /* mozjpeg table idx 3 scaled by jpeg_set_quality(q, FALSE); natural order */

@@ -25,7 +25,7 @@ extern "C" int emul_gpu_transcode(const uint8_t *jpeg, size_t len, int progressi
     const long long U = plan.total_units;
     std::vector<uint32_t> meta(U), gcount(U, 0), bitlen(U);
     std::vector<long long> evkey(U), prev_ev(U);
-    std::vector<unsigned long long> tsum(U), bitoff(U);
+    std::vector<uint32_t> tsum(U); std::vector<unsigned long long> bitoff(U);
     // pass: classify
     for (const ge::Scan &s : plan.scans) for (int u = 0; u < s.nblocks; u++) {
         ge::BlockRef b = ge::locate(s, u);
@@ -35,7 +35,7 @@ extern "C" int emul_gpu_transcode(const uint8_t *jpeg, size_t len, int progressi
     }
     // scans (global, as CUB would do them)
     { long long run = -1; for (long long i = 0; i < U; i++) { prev_ev[i] = run; if (evkey[i] > run) run = evkey[i]; } }
-    { unsigned long long run = 0; for (long long i = 0; i < U; i++) { tsum[i] = run; run += (unsigned)ge::meta_tail(meta[i]); } }
+    { uint32_t run = 0; for (long long i = 0; i < U; i++) { tsum[i] = run; run += (uint32_t)ge::meta_tail(meta[i]); } }
     // pass: groups
     for (const ge::Scan &s : plan.scans) {
         if (s.mode != ge::MODE_AC_FIRST && s.mode != ge::MODE_AC_REFINE) continue;
