@@ -282,7 +282,8 @@ def main():
     coef_bytes = int(lay.total_coefs) * 2
     e2e = {"value": round(e2e_val, 2), "unit": "MP/s", "h2d_bytes_per_step": Be * coef_bytes, "d2h_bytes_per_step": Be * int(olay.total_coefs) * 2,
            "images_per_sec": round(e2e_val / MP_PER_IMAGE, 2), "host_threads": threads, "in_bytes_per_step": sum(len(w) for w in work), "out_bytes_per_step": out_bytes,
-           "note": "JPEG bytes -> JPEG bytes via b200_compress_batch; Huffman decode/encode on host threads inside the timed region"}
+           "entropy_encoder": os.environ.get("B200_ENTROPY", "gpu"),
+           "note": "JPEG bytes -> JPEG bytes via b200_compress_batch, all inside the timed region: host Huffman decode on the caller threads, pinned H2D of coefficients, transform kernels, entropy ENCODE (device by default: only the stuffed scans cross PCIe back; B200_ENTROPY=host moves it to the host and D2H carries the coefficients)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
