@@ -34,7 +34,7 @@ b200_status make_status(int code, const std::string &msg)
 std::once_flag g_once;
 std::string g_init_err;
 int g_forced_device = -1, g_forced_ngpus = 0;
-std::atomic<int> g_entropy_mode{-1};     // -1 unset (env B200_ENTROPY, default gpu), 0 host encoder, 1 device encoder
+std::atomic<int> g_entropy_mode{-1};     // -1 unset (env B200_ENTROPY); bit 0 = device entropy encoder, bit 1 = device entropy decoder (default 3)
 
 bool ensure_runtime(std::string &err)
 {
@@ -105,7 +105,10 @@ b200_status jpeg_compress(const uint8_t *in, size_t in_len, const b200_params *p
         return ok_status();
     }
     if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
-    if (g_entropy_mode.load() < 0) { const char *e = getenv("B200_ENTROPY"); g_entropy_mode.store(e && !strcmp(e, "host") ? 0 : 1); }
+    if (g_entropy_mode.load() < 0) {
+        const char *e = getenv("B200_ENTROPY");
+        g_entropy_mode.store(!e ? 3 : !strcmp(e, "host") ? 0 : !strcmp(e, "gpuenc") ? 1 : !strcmp(e, "gpudec") ? 2 : 3);
+    }
     JpegGeom gout;
     if (!jpeg_output_geom(gin, (int)p->jpeg_quality, (int)p->jpeg_chroma_subsampling, gout, err)) return make_status(B200_ERR_INVALID_ARGUMENT, err);
     const bool resize = p->width || p->height;
@@ -123,9 +126,20 @@ b200_status jpeg_compress(const uint8_t *in, size_t in_len, const b200_params *p
     b200_status st = ok_status();
     do {
         if (!s->ensure(plan.in_bytes, plan.out_bytes, plan.scratch_bytes(), 1 << 14, err)) { st = make_status(B200_ERR_OUT_OF_MEMORY, err); break; }
-        if (!rd.decode(s->h_in, err)) { st = make_status(B200_ERR_CORRUPT_INPUT, err); break; }
-        const bool gpu_entropy = g_entropy_mode.load() == 1;
-        if (!(resize ? slot_transform_resized(s, gin, gout, err, !gpu_entropy) : slot_transform(s, gin, gout, err, !gpu_entropy))) { st = make_status(B200_ERR_CUDA, err); break; }
+        const int mode = g_entropy_mode.load();
+        const bool gpu_entropy = (mode & 1) != 0;
+        // Entropy DECODE on the device for baseline single-scan files (jpeg_gpudec.cu): the scan's bytes go up, the
+        // coefficients are born in HBM.  Progressive / multi-scan / restart-interval files, and the rare stream whose
+        // parallel decode does not settle, are Huffman-decoded here on the calling thread instead.
+        bool on_device = false;
+        JpegReader::DeviceScan ds;
+        if ((mode & 2) && rd.device_decodable(ds)) {
+            const int r = slot_gpu_decode(s, rd, ds, err);
+            if (r == 0) on_device = true;
+            else if (r != 1) { st = make_status(B200_ERR_CUDA, err); break; }
+        }
+        if (!on_device && !rd.decode(s->h_in, err)) { st = make_status(B200_ERR_CORRUPT_INPUT, err); break; }
+        if (!(resize ? slot_transform_resized(s, gin, gout, err, !gpu_entropy, !on_device) : slot_transform(s, gin, gout, err, !gpu_entropy, !on_device))) { st = make_status(B200_ERR_CUDA, err); break; }
         if (gpu_entropy) {
             // Huffman statistics, table construction, bit packing and 0xFF stuffing on the device (jpeg_gpuenc.cu); the
             // host only frames the scans.  A scan that outgrows its device buffer falls back to the host ENCODER
@@ -181,7 +195,7 @@ void b200_shutdown(void) { runtime_shutdown(); }
 int b200_device_count(void) { return runtime_device_count(); }
 const char *b200_version(void) { return "b200-caesium 0.1.0 (sm_100a)"; }
 void b200_free(void *p) { free(p); }
-int b200_set_entropy_mode(int mode) { if (mode != 0 && mode != 1) return B200_ERR_INVALID_ARGUMENT; g_entropy_mode.store(mode); return B200_OK; }
+int b200_set_entropy_mode(int mode) { if (mode < 0 || mode > 3) return B200_ERR_INVALID_ARGUMENT; g_entropy_mode.store(mode); return B200_OK; }
 
 uint32_t b200_sniff_format(const uint8_t *d, size_t n)
 {   // the magic numbers `infer` checks (scan_files.rs:30-40, compressor.rs:259-264)

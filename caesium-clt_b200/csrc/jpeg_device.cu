@@ -12,6 +12,7 @@
 #include "jpeg_device.h"
 #include "resize_kernels.h"
 #include "jpeg_gpuenc.h"
+#include "jpeg_gpudec.h"
 
 namespace b200 {
 
@@ -142,7 +143,7 @@ void runtime_shutdown()
         cudaSetDevice(d->ordinal);
         for (Slot *s : d->free_slots) {
             if (s->stream) cudaStreamDestroy((cudaStream_t)s->stream);
-            cudaFreeHost(s->h_in); cudaFreeHost(s->h_out); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_scratch); cudaFreeHost(s->h_par); cudaFree(s->d_par); delete s->enc;
+            cudaFreeHost(s->h_in); cudaFreeHost(s->h_out); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_scratch); cudaFreeHost(s->h_par); cudaFree(s->d_par); delete s->enc; delete s->dec;
             delete s;
         }
         delete d;
@@ -224,7 +225,7 @@ static void fill_tables(uint8_t *h_par, const JpegGeom &gin, const JpegGeom *gou
     for (int c = 0; c < gin.ncomp; c++) memcpy(dq + 64 * c, gin.qt[gin.tq[c]], 128);
 }
 
-bool slot_transform(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err, bool download)
+bool slot_transform(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err, bool download, bool upload)
 {
     ImagePlan plan;
     if (!plan_image(gin, gout, plan, err)) return false;
@@ -237,7 +238,7 @@ bool slot_transform(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::str
                       reinterpret_cast<const uint16_t *>(s->d_par + PAR_DQ), reinterpret_cast<const QuantDev *>(s->d_par + PAR_Q), wl);
     size_t nw = flatten_work(wl, reinterpret_cast<CompWork *>(s->h_par + PAR_WORK));
     CU(cudaMemcpyAsync(s->d_par, s->h_par, par_bytes_for(nw), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(s->d_in, s->h_in, plan.in_bytes, cudaMemcpyHostToDevice, st));
+    if (upload) CU(cudaMemcpyAsync(s->d_in, s->h_in, plan.in_bytes, cudaMemcpyHostToDevice, st));
     int rc = launch_work(wl, reinterpret_cast<const CompWork *>(s->d_par + PAR_WORK), st, 0, nullptr);
     if (rc) { err = std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)rc); return false; }
     if (!download) return true;          // the coefficients stay in HBM for the device entropy encoder
@@ -252,6 +253,12 @@ bool slot_download_coefs(Slot *s, size_t out_bytes, std::string &err)
     CU(cudaMemcpyAsync(s->h_out, s->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return true;
+}
+
+int slot_gpu_decode(Slot *s, const JpegReader &rd, const JpegReader::DeviceScan &ds, std::string &err)
+{   // 0 = coefficients are in s->d_in, 1 = not converged (decode on the host instead), 2 = failure
+    if (!s->dec) s->dec = new GpuDecoder();
+    return (int)s->dec->decode(rd, ds, s->d_in, s->stream, err);
 }
 
 bool slot_upload_out_coefs(Slot *s, size_t bytes, std::string &err)
@@ -306,7 +313,7 @@ bool slot_decode_planes(Slot *s, const JpegGeom &gin, uint8_t *planes, std::stri
 }
 
 // ---- resize path: decode -> (YCbCr->RGB) -> Lanczos3 -> (RGB->YCbCr) -> encode side --------------------------------
-bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err, bool download)
+bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err, bool download, bool upload)
 {
     const int W = gin.width, H = gin.height, NW = gout.width, NH = gout.height, nc = gin.ncomp;
     if (gout.ncomp != nc) { err = "component count mismatch"; return false; }
@@ -360,7 +367,7 @@ bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, 
     size_t nw_ = flatten_work(wl, reinterpret_cast<CompWork *>(s->h_par + PAR_WORK));
     (void)nw_;
     CU(cudaMemcpyAsync(s->d_par, s->h_par, pbytes, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(s->d_in, s->h_in, in_bytes, cudaMemcpyHostToDevice, st));
+    if (upload) CU(cudaMemcpyAsync(s->d_in, s->h_in, in_bytes, cudaMemcpyHostToDevice, st));
     const CompWork *dw = reinterpret_cast<const CompWork *>(s->d_par + PAR_WORK);
     const CompWork *p_idct = dw, *p_up = p_idct + wl.idct.size(), *p_down = p_up + wl.up.size(), *p_fdct = p_down + wl.down.size();
     auto chk = [&](int rc, const char *what) { if (rc) { err = std::string(what) + ": " + cudaGetErrorString((cudaError_t)rc); return false; } return true; };

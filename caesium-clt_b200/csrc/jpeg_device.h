@@ -11,6 +11,8 @@
 namespace b200 {
 
 class GpuEncoder;
+class GpuDecoder;
+class JpegReader;
 
 enum CompPath { PATH_FUSED = 0, PATH_C420 = 1, PATH_GENERIC = 2 };
 
@@ -49,6 +51,7 @@ struct Slot {
     uint8_t *d_scratch = nullptr; size_t d_scratch_cap = 0;
     uint8_t *h_par = nullptr, *d_par = nullptr; size_t par_cap = 0, d_par_cap = 0;      // parameter block
     class GpuEncoder *enc = nullptr;                                                     // device entropy encoder (lazy)
+    class GpuDecoder *dec = nullptr;                                                     // device entropy decoder (lazy)
     bool ensure(size_t in_bytes, size_t out_bytes, size_t scratch_bytes, size_t par_bytes, std::string &err);
 };
 
@@ -60,15 +63,17 @@ void slot_release(Slot *s);
 int  runtime_next_device();                                         // round-robin shard assignment
 
 // Run the transform for ONE image whose input coefficients already sit in s->h_in; result lands in s->h_out.
-bool slot_transform(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err, bool download = true);
+bool slot_transform(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err, bool download = true, bool upload = true);
 // D2H of the output coefficients left in HBM by a download=false transform (host-encoder fallback)
 bool slot_download_coefs(Slot *s, size_t out_bytes, std::string &err);
+// Entropy-decode a baseline single-scan file on the device into s->d_in (0 ok, 1 not converged -> host decode, 2 failed)
+int slot_gpu_decode(Slot *s, const JpegReader &rd, const JpegReader::DeviceScan &ds, std::string &err);
 // H2D of s->h_out into s->d_out (entry point that encodes caller-supplied coefficients on the device)
 bool slot_upload_out_coefs(Slot *s, size_t bytes, std::string &err);
 // Entropy-code the output coefficients sitting in s->d_out on the device; result in s->enc->results
 bool slot_gpu_encode(Slot *s, const JpegGeom &gout, bool progressive, std::string &err);
 // Resize path (CSParameters.width/height): gout carries the TARGET dimensions; decode -> RGB -> Lanczos3 -> YCbCr -> encode.
-bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err, bool download = true);
+bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err, bool download = true, bool upload = true);
 // Same front end, but stop after IDCT + upsample and copy planar full-res samples into `planes` (host).
 bool slot_decode_planes(Slot *s, const JpegGeom &gin, uint8_t *planes, std::string &err);
 

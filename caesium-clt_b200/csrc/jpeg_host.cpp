@@ -390,6 +390,41 @@ bool JpegReader::decode_scan(const uint8_t *seg, size_t sl, const uint8_t *ecs, 
     return true;
 }
 
+bool JpegReader::device_decodable(DeviceScan &ds)
+{
+    if (!have_sof_ || g_.progressive || restart_interval_ != 0) return false;
+    if (pos_ + 4 > n_ || d_[pos_] != 0xFF || d_[pos_ + 1] != 0xDA) return false;
+    const size_t L = rd16(d_ + pos_ + 2);
+    if (L < 2 || pos_ + 2 + L > n_) return false;
+    const uint8_t *seg = d_ + pos_ + 4;
+    ds.ns = seg[0];
+    if (ds.ns != g_.ncomp || L - 2 < (size_t)(4 + 2 * ds.ns)) return false;
+    for (int k = 0; k < ds.ns; k++) {
+        ds.ci[k] = -1;
+        for (int c = 0; c < g_.ncomp; c++) if (g_.cid[c] == seg[1 + 2 * k]) ds.ci[k] = c;
+        if (ds.ci[k] != k) return false;                       // components must appear in frame order
+        ds.td[k] = seg[2 + 2 * k] >> 4; ds.ta[k] = seg[2 + 2 * k] & 15;
+        if (ds.td[k] > 3 || ds.ta[k] > 3 || !dc_[ds.td[k]].present || !ac_[ds.ta[k]].present) return false;
+    }
+    for (int c = 0; c < g_.ncomp; c++) if (!g_.qt_present[g_.tq[c]]) return false;
+    ds.ecs_begin = pos_ + 2 + L;
+    // the segment ends at the first marker that is not a stuffed zero; anything but EOI right there disqualifies the file
+    size_t q = ds.ecs_begin;
+    ds.stuffed = 0;
+    for (;;) {
+        const uint8_t *f = (const uint8_t *)memchr(d_ + q, 0xFF, n_ - q);
+        if (!f) return false;
+        q = (size_t)(f - d_);
+        if (q + 1 >= n_) return false;
+        if (d_[q + 1] == 0x00) { ds.stuffed++; q += 2; continue; }
+        if (d_[q + 1] == 0xFF) return false;               // fill bytes: rare, host path
+        break;
+    }
+    if (d_[q + 1] != 0xD9) return false;                      // RSTn, DNL or another scan: leave it to the host decoder
+    ds.ecs_end = q;
+    return ds.ecs_end > ds.ecs_begin;
+}
+
 bool JpegReader::decode(int16_t *coefs, std::string &err)
 {
     if (!have_sof_) { err = "no frame header"; return false; }

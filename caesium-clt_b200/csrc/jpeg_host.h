@@ -45,6 +45,16 @@ public:
     bool decode(int16_t *coefs, std::string &err);   // coefs: geom().total_coefs int16, fully overwritten
     const JpegGeom &geom() const { return g_; }
     const JpegMeta &meta() const { return m_; }
+    // After read_header(): is this file decodable by the device entropy decoder?  (baseline process, exactly one scan
+    // that carries every component, no restart interval.)  Fills the scan's table selectors and the byte range of its
+    // entropy-coded segment; on true, the reader is positioned after the scan so later markers are still parsed by
+    // finish_after_device_decode().
+    struct DeviceScan { int ns; int ci[4], td[4], ta[4]; size_t ecs_begin, ecs_end, stuffed; };
+    bool device_decodable(DeviceScan &ds);
+    const uint8_t *dht_bits(int kind, int id) const { return kind ? ac_[id].bits : dc_[id].bits; }
+    const uint8_t *dht_vals(int kind, int id) const { return kind ? ac_[id].vals : dc_[id].vals; }
+    bool dht_present(int kind, int id) const { return kind ? ac_[id].present : dc_[id].present; }
+    const uint8_t *data() const { return d_; }
     struct Huff {
         uint8_t bits[17]; uint8_t vals[256]; bool present = false;
         // decode acceleration

@@ -81,8 +81,10 @@ void b200_shutdown(void);
 int  b200_device_count(void);         /* devices the library is driving (0 before init / without GPU) */
 const char *b200_version(void);
 void b200_free(void *p);
-/* Where the JPEG entropy ENCODER runs: 1 (default; env B200_ENTROPY=gpu) = on the device next to the transform kernels,
- * 0 (B200_ENTROPY=host) = jchuff/jcphuff-style encoder on the calling host thread.  Output bytes are identical. */
+/* Where JPEG entropy coding runs.  Bit 0: Huffman ENCODE on the device; bit 1: Huffman DECODE on the device (baseline
+ * single-scan inputs; anything else is decoded on the calling thread).  Default 3 (env B200_ENTROPY=gpu); 0
+ * (B200_ENTROPY=host) keeps both on the host as north_star words it; gpuenc = 1, gpudec = 2.  Output bytes are identical
+ * in every mode. */
 int  b200_set_entropy_mode(int mode);
 
 /* ---- the three calls of compressor.rs:287-306 -------------------------------------------------- */

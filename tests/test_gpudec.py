@@ -1,0 +1,133 @@
+"""Device entropy DECODER (self-synchronising parallel Huffman decoding, jpeg_gpudec_core.h).
+
+CPU part: the kernel bodies run serially (tests/emul/gpudec_emul.cpp) must reproduce the host decoder's coefficients,
+for several subsequence sizes; ineligible inputs (progressive, restart intervals) are refused; degenerate periodic
+streams report non-convergence (the product then decodes on the host).
+GPU part (-m gpu): the same through the library, end to end against the oracle, in every entropy mode."""
+import ctypes as C
+import io
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from PIL import Image
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL_DIR = os.path.join(ROOT, "tests", "emul")
+BASELINE_INPUTS = ["in_420_base_355x237.jpg", "in_444_base_355x237.jpg", "in_422_base_355x237.jpg", "in_gray_base_355x237.jpg",
+                   "in_420_base_640x480.jpg", "in_420_tiny_17x9.jpg", "in_420_tiny_3x3.jpg"]
+
+
+@pytest.fixture(scope="module")
+def emul():
+    so = os.path.join(EMUL_DIR, "libgpudec_emul.so")
+    srcs = [os.path.join(EMUL_DIR, "gpudec_emul.cpp"), os.path.join(ROOT, "caesium-clt_b200", "csrc", "jpeg_host.cpp"),
+            os.path.join(ROOT, "caesium-clt_b200", "csrc", "jpeg_gpudec_core.h"), os.path.join(ROOT, "caesium-clt_b200", "csrc", "jpeg_gpuenc_core.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-msse2", "-Wno-unknown-pragmas", "-o", so, srcs[0], srcs[1]])
+    return C.CDLL(so)
+
+
+def emul_decode(emul, data, total_coefs, subseq=1024, max_rounds=64):
+    out = np.zeros(total_coefs, dtype=np.int16)
+    r = C.c_int(0)
+    rc = emul.emul_gpu_decode(data, C.c_size_t(len(data)), subseq, max_rounds, out.ctypes.data_as(C.c_void_p), C.c_longlong(out.size), C.byref(r))
+    return rc, out, r.value
+
+
+@pytest.mark.parametrize("name", BASELINE_INPUTS)
+@pytest.mark.parametrize("subseq", [128, 1024, 4096])
+def test_parallel_decode_matches_host_decoder(L, emul, golden, name, subseq):
+    data = golden(name)
+    lay, ref = L.jpeg_decode_coefficients(data)
+    rc, out, rounds = emul_decode(emul, data, lay.total_coefs, subseq, 256)
+    assert rc == 0
+    assert np.array_equal(out, ref)
+
+
+def test_ineligible_inputs_are_refused(L, emul, golden):
+    data = golden("in_420_prog_355x237.jpg")                       # progressive
+    lay, _ = L.jpeg_decode_coefficients(data)
+    assert emul_decode(emul, data, lay.total_coefs)[0] == 10
+    b = io.BytesIO()                                                 # restart interval
+    Image.open(io.BytesIO(golden("in_420_base_640x480.jpg"))).save(b, "JPEG", quality=80, restart_marker_blocks=7)
+    d2 = b.getvalue()
+    if b"\xff\xdd" in d2:                                           # Pillow wrote a DRI segment
+        lay, _ = L.jpeg_decode_coefficients(d2)
+        assert emul_decode(emul, d2, lay.total_coefs)[0] == 10
+
+
+def test_optimised_tables_and_high_quality(L, emul):
+    """Files with per-image optimised Huffman tables and long codes (q=100) decode identically."""
+    from tools.synth import synth_rgb
+    for q, kw in [(100, {}), (30, {"optimize": True}), (95, {"optimize": True, "subsampling": "4:4:4"})]:
+        b = io.BytesIO()
+        Image.fromarray(synth_rgb(333, 211, 40 + q), "RGB").save(b, "JPEG", quality=q, **kw)
+        data = b.getvalue()
+        lay, ref = L.jpeg_decode_coefficients(data)
+        rc, out, _ = emul_decode(emul, data, lay.total_coefs, 512, 256)
+        assert rc == 0 and np.array_equal(out, ref)
+
+
+def test_flat_image_reports_non_convergence_or_matches(L, emul):
+    """A constant image is a periodic bit stream: a wrong phase can persist, so the round budget may run out.  Whatever
+    the outcome, a 0 return code must mean identical coefficients."""
+    b = io.BytesIO()
+    Image.new("RGB", (1024, 1024), (90, 140, 200)).save(b, "JPEG", quality=90)
+    data = b.getvalue()
+    lay, ref = L.jpeg_decode_coefficients(data)
+    rc, out, rounds = emul_decode(emul, data, lay.total_coefs, 1024, 8)
+    assert rc in (0, 11)
+    if rc == 0:
+        assert np.array_equal(out, ref)
+    rc, out, rounds = emul_decode(emul, data, lay.total_coefs, 1024, 100000)
+    assert rc == 0 and np.array_equal(out, ref)
+
+
+# ---------------------------------------------------------------------------------------------------------------- GPU
+def _params(L, q=80, ss=420, prog=True):
+    p = L.default_params()
+    p.jpeg_quality, p.jpeg_chroma_subsampling, p.jpeg_progressive = q, ss, int(prog)
+    return p
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", BASELINE_INPUTS + ["in_420_prog_355x237.jpg"])
+def test_device_decode_end_to_end_all_modes(L, O, golden, name):
+    data = golden(name)
+    ref = O.jpeg_lossy(data, O.params(80, 420, True))
+    try:
+        for mode in (3, 2, 1, 0):
+            L.set_entropy_mode(mode)
+            assert L.compress_in_memory(data, _params(L)) == ref, f"entropy mode {mode}"
+    finally:
+        L.set_entropy_mode(3)
+
+
+@pytest.mark.gpu
+def test_device_decode_4k_and_flat_fallback(L, O):
+    from tools.synth import synth_jpeg
+    L.set_entropy_mode(3)
+    data = synth_jpeg(3840, 2160, 2)
+    assert L.compress_in_memory(data, _params(L)) == O.jpeg_lossy(data, O.params(80, 420, True))
+    b = io.BytesIO()
+    Image.new("RGB", (2048, 2048), (90, 140, 200)).save(b, "JPEG", quality=90)       # periodic stream: host fallback path
+    flat = b.getvalue()
+    assert L.compress_in_memory(flat, _params(L)) == O.jpeg_lossy(flat, O.params(80, 420, True))
+    for q, kw in [(100, {}), (30, {"optimize": True})]:
+        from tools.synth import synth_rgb
+        b = io.BytesIO()
+        Image.fromarray(synth_rgb(1333, 811, 77), "RGB").save(b, "JPEG", quality=q, **kw)
+        d = b.getvalue()
+        assert L.compress_in_memory(d, _params(L, 70, 444, False)) == O.jpeg_lossy(d, O.params(70, 444, False))
+
+
+@pytest.mark.gpu
+def test_device_decode_concurrent(L, O, golden):
+    datas = [golden(n) for n in BASELINE_INPUTS] * 8
+    L.set_entropy_mode(3)
+    res = L.compress_batch(datas, _params(L, 85, 0, True), n_threads=16)
+    for d, (out, code, msg) in zip(datas, res):
+        assert code == 0, msg
+        assert out == O.jpeg_lossy(d, O.params(85, 0, True))
