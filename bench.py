@@ -26,6 +26,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the library drives one CUDA stream per in-flight image; give them separate hardware queues (must precede CUDA init,
+# and torch may create the context before the library does)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 W4K, H4K = 3840, 2160
 MP_PER_IMAGE = W4K * H4K / 1e6

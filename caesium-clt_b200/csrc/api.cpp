@@ -3,11 +3,13 @@
 // (call sites /root/reference/src/compressor.rs:287-306).  No CPU codec fallback exists anywhere below.
 #include "../../include/b200_caesium.h"
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <exception>
 #include <fstream>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -87,6 +89,22 @@ int usable_cores()
     return (int)hc;
 }
 
+// B200_TRACE=1: wall-clock per stage of the per-image call, summed over all images, printed by b200_shutdown()
+std::atomic<long long> g_stage_ns[8];
+std::atomic<long long> g_stage_n{0};
+const bool g_trace = getenv("B200_TRACE") != nullptr;
+struct StageTimer {
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(int i) { if (!g_trace) return; auto n = std::chrono::steady_clock::now(); g_stage_ns[i] += std::chrono::duration_cast<std::chrono::nanoseconds>(n - t).count(); t = n; if (i == 5) g_stage_n++; }
+};
+void print_trace()
+{
+    if (!g_trace || !g_stage_n.load()) return;
+    static const char *names[] = {"parse+scan-for-markers", "device entropy decode (incl. syncs)", "host entropy decode", "transform launch", "device entropy encode (incl. syncs)", "assemble file"};
+    fprintf(stderr, "[b200 trace] %lld images; mean ms per image and stage:\n", g_stage_n.load());
+    for (int i = 0; i < 6; i++) fprintf(stderr, "[b200 trace]   %-38s %8.3f\n", names[i], g_stage_ns[i].load() / 1e6 / (double)g_stage_n.load());
+}
+
 // ---- JPEG through the device ---------------------------------------------------------------------------------
 b200_status jpeg_compress(const uint8_t *in, size_t in_len, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
 {
@@ -133,19 +151,26 @@ b200_status jpeg_compress(const uint8_t *in, size_t in_len, const b200_params *p
         // parallel decode does not settle, are Huffman-decoded here on the calling thread instead.
         bool on_device = false;
         JpegReader::DeviceScan ds;
+        StageTimer tm;
         if ((mode & 2) && rd.device_decodable(ds)) {
+            tm.lap(0);
             const int r = slot_gpu_decode(s, rd, ds, err);
+            tm.lap(1);
             if (r == 0) on_device = true;
             else if (r != 1) { st = make_status(B200_ERR_CUDA, err); break; }
         }
         if (!on_device && !rd.decode(s->h_in, err)) { st = make_status(B200_ERR_CORRUPT_INPUT, err); break; }
+        tm.lap(2);
         if (!(resize ? slot_transform_resized(s, gin, gout, err, !gpu_entropy, !on_device) : slot_transform(s, gin, gout, err, !gpu_entropy, !on_device))) { st = make_status(B200_ERR_CUDA, err); break; }
+        tm.lap(3);
         if (gpu_entropy) {
             // Huffman statistics, table construction, bit packing and 0xFF stuffing on the device (jpeg_gpuenc.cu); the
             // host only frames the scans.  A scan that outgrows its device buffer falls back to the host ENCODER
             // (still the same coefficients from the CUDA transform).
             if (slot_gpu_encode(s, gout, wo.progressive, err)) {
+                tm.lap(4);
                 if (!jpeg_assemble(gout, wo, &rd.meta(), s->enc->results.data(), (int)s->enc->results.size(), out, err)) st = make_status(B200_ERR_INVALID_ARGUMENT, err);
+                tm.lap(5);
                 break;
             }
             if (!s->enc || !s->enc->overflow) { st = make_status(B200_ERR_CUDA, err); break; }
@@ -164,6 +189,74 @@ b200_status give(std::vector<uint8_t> &v, uint8_t **out, size_t *out_len)
     if (!*out) return make_status(B200_ERR_OUT_OF_MEMORY, "out of memory");
     memcpy(*out, v.data(), v.size()); *out_len = v.size();
     return ok_status();
+}
+
+// One megabatch: the images idx[] that are baseline single-scan JPEGs of one shape are decoded, transformed and encoded by
+// ONE sequence of kernel launches on one slot.  done[k] = 1 for every image this function finished (successfully or with
+// a final error in status[]); the caller runs the others through the per-image path.
+void jpeg_compress_group(const uint8_t *const *in, const size_t *in_len, const std::vector<int> &idx, const b200_params *p, int dev,
+                         uint8_t **out, size_t *out_len, b200_status *status, std::vector<char> &done)
+{
+    const int M = (int)idx.size();
+    std::vector<std::unique_ptr<JpegReader>> rd((size_t)M);
+    std::vector<JpegReader::DeviceScan> ds((size_t)M);
+    std::vector<int> members;                       // positions k (into idx) that join the group
+    std::string err;
+    for (int k = 0; k < M; k++) {
+        const int i = idx[k];
+        if (b200_sniff_format(in[i], in_len[i]) != B200_FMT_JPEG) continue;
+        rd[k].reset(new JpegReader(in[i], in_len[i]));
+        if (!rd[k]->read_header(err) || !rd[k]->device_decodable(ds[k])) continue;
+        if (!members.empty()) {
+            const JpegGeom &a = rd[members[0]]->geom(), &b = rd[k]->geom();
+            bool same = a.width == b.width && a.height == b.height && a.ncomp == b.ncomp;
+            for (int c = 0; same && c < a.ncomp; c++) same = a.hs[c] == b.hs[c] && a.vs[c] == b.vs[c];
+            if (!same) continue;
+        }
+        members.push_back(k);
+    }
+    if (members.size() < 2) return;
+    const JpegGeom &gin0 = rd[members[0]]->geom();
+    JpegGeom gout;
+    if (!jpeg_output_geom(gin0, (int)p->jpeg_quality, (int)p->jpeg_chroma_subsampling, gout, err)) return;
+    Slot *s = slot_acquire(dev, err);
+    if (!s) return;
+    const int Kg = (int)members.size();
+    bool ok = false;
+    do {
+        GroupLayout L;
+        if (!slot_group_layout(s, gin0, gout, Kg, L, err)) break;
+        std::vector<GpuDecoder::Item> items((size_t)Kg);
+        std::vector<const JpegGeom *> gins((size_t)Kg);
+        for (int m = 0; m < Kg; m++) {
+            const int k = members[m];
+            items[m].rd = rd[k].get(); items[m].ds = &ds[k]; items[m].result = GpuDecoder::FAILED;
+            items[m].d_coefs = reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(s->d_in) + L.in_stride * m);
+            gins[m] = &rd[k]->geom();
+        }
+        StageTimer tm; tm.lap(0);
+        if (!slot_decode_group(s, items, err)) break;
+        tm.lap(1);
+        if (!slot_transform_group(s, gins.data(), gout, L, err)) break;
+        tm.lap(3);
+        JpegWriteOptions wo; wo.progressive = p->jpeg_progressive != 0; wo.keep_metadata = p->keep_metadata != 0; wo.preserve_icc = p->jpeg_preserve_icc != 0;
+        if (!slot_encode_group(s, gout, wo.progressive, L, err)) break;
+        tm.lap(4);
+        const int spi = s->enc->plan.scans_per_image;
+        for (int m = 0; m < Kg; m++) {
+            const int k = members[m], i = idx[k];
+            if (items[m].result != GpuDecoder::OK) continue;          // not converged: the per-image path decodes it on the host
+            std::vector<uint8_t> v;
+            out[i] = nullptr; out_len[i] = 0;
+            if (!jpeg_assemble(gout, wo, &rd[k]->meta(), s->enc->results.data() + (size_t)m * spi, spi, v, err)) status[i] = make_status(B200_ERR_INVALID_ARGUMENT, err);
+            else status[i] = give(v, &out[i], &out_len[i]);
+            done[k] = 1;
+        }
+        tm.lap(5);
+        ok = true;
+    } while (0);
+    (void)ok;
+    slot_release(s);
 }
 
 b200_status compress_dispatch(const uint8_t *in, size_t in_len, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
@@ -191,7 +284,7 @@ void b200_params_default(b200_params *p)
 
 int b200_init(int n_gpus) { g_forced_ngpus = n_gpus; std::string e; return ensure_runtime(e) ? B200_OK : B200_ERR_NO_DEVICE; }
 int b200_init_device(int ordinal) { g_forced_device = ordinal; std::string e; return ensure_runtime(e) ? B200_OK : B200_ERR_NO_DEVICE; }
-void b200_shutdown(void) { runtime_shutdown(); }
+void b200_shutdown(void) { print_trace(); runtime_shutdown(); }
 int b200_device_count(void) { return runtime_device_count(); }
 const char *b200_version(void) { return "b200-caesium 0.1.0 (sm_100a)"; }
 void b200_free(void *p) { free(p); }
@@ -268,22 +361,37 @@ int b200_compress_batch(const uint8_t *const *in, const size_t *in_len, int n, c
     if (!in || !in_len || !params || !out || !out_len || !status || n < 0) return -1;
     if (n_threads <= 0) n_threads = usable_cores();
     if (n_threads > n) n_threads = n;
-    std::atomic<int> next{0}, failed{0};
+    std::atomic<int> next{0}, failed{0}, chunk_id{0};
+    { std::string e; ensure_runtime(e); }
     const int ndev = std::max(1, runtime_device_count());
+    if (g_entropy_mode.load() < 0) { const char *e = getenv("B200_ENTROPY"); g_entropy_mode.store(!e ? 3 : !strcmp(e, "host") ? 0 : !strcmp(e, "gpuenc") ? 1 : !strcmp(e, "gpudec") ? 2 : 3); }
+    // Megabatches: with both entropy stages on the device, consecutive images are processed K at a time -- one launch
+    // sequence (decode rounds, transform, encode passes) for the whole group instead of one per image.  Images that do not
+    // fit the group path (other formats, progressive input, resize, odd one out in shape) go through the per-image path.
+    int K = 8; { const char *e = getenv("B200_MEGABATCH"); if (e) K = std::max(1, std::min(64, atoi(e))); }
+    const bool grouped = runtime_device_count() > 0 && g_entropy_mode.load() == 3 && K > 1 && !params->jpeg_optimize && !params->width && !params->height;
+    auto one = [&](int i, int dev) {
+        out[i] = nullptr; out_len[i] = 0;
+        try {
+            std::vector<uint8_t> v;
+            status[i] = compress_dispatch(in[i], in_len[i], params, dev, v);
+            if (!status[i].code) status[i] = give(v, &out[i], &out_len[i]);
+        } catch (const std::exception &e) { status[i] = make_status(B200_ERR_OUT_OF_MEMORY, e.what()); } catch (...) { status[i] = make_status(B200_ERR_INVALID_ARGUMENT, "unexpected failure"); }
+        if (status[i].code) failed++;
+    };
     auto worker = [&]() {
+        if (!grouped) { for (;;) { int i = next.fetch_add(1); if (i >= n) break; one(i, i % ndev); } return; }
         for (;;) {
-            int i = next.fetch_add(1);
-            if (i >= n) break;
-            out[i] = nullptr; out_len[i] = 0;
-            try {
-                std::vector<uint8_t> v;
-                status[i] = compress_dispatch(in[i], in_len[i], params, i % ndev, v);
-                if (!status[i].code) status[i] = give(v, &out[i], &out_len[i]);
-            } catch (const std::exception &e) { status[i] = make_status(B200_ERR_OUT_OF_MEMORY, e.what()); } catch (...) { status[i] = make_status(B200_ERR_INVALID_ARGUMENT, "unexpected failure"); }
-            if (status[i].code) failed++;
+            const int i0 = next.fetch_add(K);
+            if (i0 >= n) break;
+            const int i1 = std::min(n, i0 + K), dev = chunk_id.fetch_add(1) % ndev;
+            std::vector<int> idx; for (int i = i0; i < i1; i++) idx.push_back(i);
+            std::vector<char> done(idx.size(), 0);
+            try { jpeg_compress_group(in, in_len, idx, params, dev, out, out_len, status, done); } catch (...) {}
+            for (size_t k = 0; k < idx.size(); k++) { if (!done[k]) one(idx[k], dev); else if (status[idx[k]].code) failed++; }
         }
     };
-    { std::string e; ensure_runtime(e); }
+    if (grouped) n_threads = std::max(1, std::min(n_threads, std::min(8, (n + K - 1) / K)));
     std::vector<std::thread> th;
     for (int t = 1; t < n_threads; t++) th.emplace_back(worker);
     worker();

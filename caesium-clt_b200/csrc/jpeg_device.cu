@@ -121,12 +121,21 @@ int runtime_init(int n_gpus, int only_device, std::string &err)
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_inited) return (int)g_devs.size();
     int count = 0;
+    // Callers block in cudaStreamSynchronize a few times per image; with the default spin-wait, N caller threads burn N
+    // cores doing nothing (and trip cgroup CPU quotas).  Blocking waits leave the cores to the threads that have work.
+    // B200_SYNC=spin restores the driver default.  Harmless no-op if a context already exists (e.g. created by torch).
+    // One stream per in-flight image, dozens in flight: with the default 8 hardware work queues, streams alias onto the
+    // same queue and serialise behind each other.  32 is the maximum; only effective if set before the context exists.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    const char *sy = getenv("B200_SYNC");
+    const bool blocking = !(sy && !strcmp(sy, "spin"));
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count <= 0) { err = std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") + "); this build has no CPU fallback"; return 0; }
     std::vector<int> ords;
     if (only_device >= 0) { if (only_device >= count) { err = "CUDA device ordinal out of range"; return 0; } ords.push_back(only_device); }
     else { int n = n_gpus <= 0 ? count : std::min(n_gpus, count); for (int i = 0; i < n; i++) ords.push_back(i); }
     for (int o : ords) {
+        if (blocking && cudaSetDevice(o) == cudaSuccess) { cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync); cudaGetLastError(); }
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, o) != cudaSuccess) { err = "cudaGetDeviceProperties failed"; return 0; }
         if (prop.major != 10) { err = "device " + std::to_string(o) + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + "; this library ships sm_100a kernels only"; for (auto *d : g_devs) delete d; g_devs.clear(); return 0; }
@@ -205,6 +214,13 @@ template <typename T> static bool grow_dev(T *&p, size_t &cap, size_t need, std:
     p = (T *)q; cap = want; return true;
 }
 
+bool Slot::ensure_device(size_t in_bytes, size_t out_bytes, size_t scratch_bytes, size_t par_bytes, std::string &err)
+{   // megabatch path: coefficients never visit the host, so only the HBM side (and the small parameter block) grows
+    return grow_dev(d_in, d_in_cap, in_bytes, err) && grow_dev(d_out, d_out_cap, out_bytes, err) &&
+           grow_dev(d_scratch, d_scratch_cap, std::max<size_t>(scratch_bytes, 256), err) &&
+           grow_host(h_par, par_cap, par_bytes, err) && grow_dev(d_par, d_par_cap, par_bytes, err);
+}
+
 bool Slot::ensure(size_t in_bytes, size_t out_bytes, size_t scratch_bytes, size_t par_bytes, std::string &err)
 {
     return grow_host(h_in, h_in_cap, in_bytes, err) && grow_host(h_out, h_out_cap, out_bytes, err) &&
@@ -247,6 +263,58 @@ bool slot_transform(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::str
     return true;
 }
 
+// ---- megabatch: K same-shaped images per launch sequence (b200_compress_batch) -------------------------------------
+// Buffers of image k live at d_in + k * in_stride etc.; the input coefficients are already in HBM (device decoder) and
+// the output coefficients stay there (device encoder).  Parameter block: QuantDev q[4] | dq[K][4][64] | CompWork[].
+bool slot_group_layout(Slot *s, const JpegGeom &gin, const JpegGeom &gout, int K, GroupLayout &L, std::string &err)
+{
+    ImagePlan plan;
+    if (!plan_image(gin, gout, plan, err)) return false;
+    L.K = K;
+    L.in_stride = align_up(plan.in_bytes, 256); L.out_stride = align_up(plan.out_bytes, 256); L.scratch_stride = align_up(std::max<size_t>(plan.scratch_bytes(), 256), 256);
+    const size_t par = align_up(sizeof(QuantDev) * 4, 256) + align_up(sizeof(uint16_t) * 256 * K, 256) + sizeof(CompWork) * (size_t)K * 4 * 6 + 256;
+    return s->ensure_device(L.in_stride * K, L.out_stride * K, L.scratch_stride * K, par, err);
+}
+
+bool slot_transform_group(Slot *s, const JpegGeom *const *gins, const JpegGeom &gout, const GroupLayout &L, std::string &err)
+{
+    cudaStream_t st = (cudaStream_t)s->stream;
+    const int K = L.K;
+    const size_t o_q = 0, o_dq = align_up(sizeof(QuantDev) * 4, 256), o_work = o_dq + align_up(sizeof(uint16_t) * 256 * K, 256);
+    QuantDev *q = reinterpret_cast<QuantDev *>(s->h_par + o_q);
+    for (int t = 0; t < 4; t++) if (gout.qt_present[t]) make_quant_dev(gout.qt[t], &q[t]);
+    WorkLists wl;
+    for (int k = 0; k < K; k++) {
+        const JpegGeom &gin = *gins[k];
+        ImagePlan plan;
+        if (!plan_image(gin, gout, plan, err)) return false;
+        uint16_t *dq = reinterpret_cast<uint16_t *>(s->h_par + o_dq) + 256 * k;
+        for (int c = 0; c < gin.ncomp; c++) memcpy(dq + 64 * c, gin.qt[gin.tq[c]], 128);
+        append_image_work(gin, gout, plan, reinterpret_cast<const int16_t *>(reinterpret_cast<const uint8_t *>(s->d_in) + L.in_stride * k),
+                          reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(s->d_out) + L.out_stride * k), s->d_scratch + L.scratch_stride * k,
+                          reinterpret_cast<const uint16_t *>(s->d_par + o_dq) + 256 * k, reinterpret_cast<const QuantDev *>(s->d_par + o_q), wl);
+    }
+    const size_t nw = flatten_work(wl, reinterpret_cast<CompWork *>(s->h_par + o_work));
+    CU(cudaMemcpyAsync(s->d_par, s->h_par, o_work + nw * sizeof(CompWork), cudaMemcpyHostToDevice, st));
+    int rc = launch_work(wl, reinterpret_cast<const CompWork *>(s->d_par + o_work), st, 0, nullptr);
+    if (rc) { err = std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)rc); return false; }
+    return true;
+}
+
+bool slot_decode_group(Slot *s, std::vector<GpuDecoder::Item> &items, std::string &err)
+{
+    if (!s->dec) s->dec = new GpuDecoder();
+    return s->dec->decode(items, s->stream, err);
+}
+
+bool slot_encode_group(Slot *s, const JpegGeom &gout, bool progressive, const GroupLayout &L, std::string &err)
+{
+    if (!s->enc) s->enc = new GpuEncoder();
+    std::vector<int16_t *> bases((size_t)L.K);
+    for (int k = 0; k < L.K; k++) bases[k] = reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(s->d_out) + L.out_stride * k);
+    return s->enc->encode(gout, progressive, bases.data(), L.K, s->stream, true, err);
+}
+
 bool slot_download_coefs(Slot *s, size_t out_bytes, std::string &err)
 {
     cudaStream_t st = (cudaStream_t)s->stream;
@@ -258,7 +326,10 @@ bool slot_download_coefs(Slot *s, size_t out_bytes, std::string &err)
 int slot_gpu_decode(Slot *s, const JpegReader &rd, const JpegReader::DeviceScan &ds, std::string &err)
 {   // 0 = coefficients are in s->d_in, 1 = not converged (decode on the host instead), 2 = failure
     if (!s->dec) s->dec = new GpuDecoder();
-    return (int)s->dec->decode(rd, ds, s->d_in, s->stream, err);
+    std::vector<GpuDecoder::Item> items(1);
+    items[0].rd = &rd; items[0].ds = &ds; items[0].d_coefs = s->d_in; items[0].result = GpuDecoder::FAILED;
+    if (!s->dec->decode(items, s->stream, err)) return 2;
+    return (int)items[0].result;
 }
 
 bool slot_upload_out_coefs(Slot *s, size_t bytes, std::string &err)

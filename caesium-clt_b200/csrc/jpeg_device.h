@@ -7,12 +7,10 @@
 #include <vector>
 #include "jpeg_host.h"
 #include "jpeg_kernels.h"
+#include "jpeg_gpudec.h"
+#include "jpeg_gpuenc.h"
 
 namespace b200 {
-
-class GpuEncoder;
-class GpuDecoder;
-class JpegReader;
 
 enum CompPath { PATH_FUSED = 0, PATH_C420 = 1, PATH_GENERIC = 2 };
 
@@ -53,6 +51,7 @@ struct Slot {
     class GpuEncoder *enc = nullptr;                                                     // device entropy encoder (lazy)
     class GpuDecoder *dec = nullptr;                                                     // device entropy decoder (lazy)
     bool ensure(size_t in_bytes, size_t out_bytes, size_t scratch_bytes, size_t par_bytes, std::string &err);
+    bool ensure_device(size_t in_bytes, size_t out_bytes, size_t scratch_bytes, size_t par_bytes, std::string &err);
 };
 
 int  runtime_init(int n_gpus, int only_device, std::string &err);   // returns device count (>0) or 0 with err
@@ -68,6 +67,12 @@ bool slot_transform(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::str
 bool slot_download_coefs(Slot *s, size_t out_bytes, std::string &err);
 // Entropy-decode a baseline single-scan file on the device into s->d_in (0 ok, 1 not converged -> host decode, 2 failed)
 int slot_gpu_decode(Slot *s, const JpegReader &rd, const JpegReader::DeviceScan &ds, std::string &err);
+// ---- megabatch (K same-shaped images per launch sequence; used by b200_compress_batch) ---------------------------------
+struct GroupLayout { int K = 0; size_t in_stride = 0, out_stride = 0, scratch_stride = 0; };
+bool slot_group_layout(Slot *s, const JpegGeom &gin, const JpegGeom &gout, int K, GroupLayout &L, std::string &err);   // sizes + ensure()
+bool slot_decode_group(Slot *s, std::vector<GpuDecoder::Item> &items, std::string &err);      // items[k].d_coefs = d_in + k * in_stride
+bool slot_transform_group(Slot *s, const JpegGeom *const *gins, const JpegGeom &gout, const GroupLayout &L, std::string &err);
+bool slot_encode_group(Slot *s, const JpegGeom &gout, bool progressive, const GroupLayout &L, std::string &err);      // results in s->enc->results
 // H2D of s->h_out into s->d_out (entry point that encodes caller-supplied coefficients on the device)
 bool slot_upload_out_coefs(Slot *s, size_t bytes, std::string &err);
 // Entropy-code the output coefficients sitting in s->d_out on the device; result in s->enc->results

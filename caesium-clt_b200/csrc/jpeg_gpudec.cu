@@ -1,7 +1,9 @@
 // jpeg_gpudec.cu -- device entropy DECODER for baseline single-scan JPEG files: CUDA wrappers around the bodies in
 // jpeg_gpudec_core.h (self-synchronising parallel Huffman decoding) plus byte un-stuffing and the DC prefix sums.
+// Batched: every pass is one launch for all images of the batch (blockIdx.y = image), which is what keeps the launch
+// count per image low when b200_compress_batch packs images into megabatches.
 // Pass order: unstuff (count, scan, scatter) -> round 0 -> rounds (in groups, one host check per group) -> block-count
-// scan -> write -> DC gather / scan / scatter.  Coefficients land directly in the transform kernels' input buffer, so the
+// scan -> write -> DC gather / scan / scatter.  Coefficients land directly in the transform kernels' input buffers, so the
 // host never sees them.
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
@@ -14,100 +16,141 @@ namespace b200 {
 
 using namespace gd;
 
-#define CUD(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(e_); return FAILED; } } while (0)
+#define CUD(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(e_); return false; } } while (0)
 
 // ---- un-stuffing: drop the 0x00 that follows every 0xFF -----------------------------------------------------------------
-__global__ void k_gd_unstuff_count(const uint8_t *__restrict__ raw, uint32_t n, uint32_t *__restrict__ cnt)
+__global__ void k_gd_unstuff_count(const DecImage *__restrict__ imgs, const uint8_t *__restrict__ raw_all, uint32_t *__restrict__ cnt)
 {
+    const DecImage &im = imgs[blockIdx.y];
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g * 16 >= n) return;
+    if (g >= im.ngrp) return;
+    const uint8_t *raw = raw_all + im.raw_off;
     uint32_t c = 0;
-    for (uint32_t j = g * 16; j < g * 16 + 16 && j < n; j++) c += (j > 0 && raw[j] == 0 && raw[j - 1] == 0xFF);
-    cnt[g] = c;
+    for (uint32_t j = g * 16; j < g * 16 + 16 && j < im.nraw; j++) c += (j > 0 && raw[j] == 0 && raw[j - 1] == 0xFF);
+    cnt[im.grp_off + g] = c;
 }
-__global__ void k_gd_unstuff_scatter(const uint8_t *__restrict__ raw, uint32_t n, const uint32_t *__restrict__ off, uint8_t *__restrict__ out)
+__global__ void k_gd_unstuff_scatter(const DecImage *__restrict__ imgs, const uint8_t *__restrict__ raw_all, const uint32_t *__restrict__ off, uint8_t *__restrict__ stream_all)
 {
+    const DecImage &im = imgs[blockIdx.y];
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g * 16 >= n) return;
-    uint32_t o = g * 16 - off[g];
-    for (uint32_t j = g * 16; j < g * 16 + 16 && j < n; j++) { if (j > 0 && raw[j] == 0 && raw[j - 1] == 0xFF) continue; out[o++] = raw[j]; }
+    if (g >= im.ngrp) return;
+    const uint8_t *raw = raw_all + im.raw_off;
+    uint8_t *out = stream_all + im.stream_off;
+    uint32_t o = g * 16 - (off[im.grp_off + g] - off[im.grp_off]);
+    for (uint32_t j = g * 16; j < g * 16 + 16 && j < im.nraw; j++) { if (j > 0 && raw[j] == 0 && raw[j - 1] == 0xFF) continue; out[o++] = raw[j]; }
+    if (g == im.ngrp - 1) { const uint32_t ns = im.g.nbits >> 3; for (uint32_t j = ns; j < ((ns + 3) & ~3u) + 16; j++) out[j] = 0xFF; }   // pad: peek32 reads whole words past the end
 }
 
 // ---- synchronisation rounds ------------------------------------------------------------------------------------------------
-__global__ void k_gd_round0(const uint8_t *__restrict__ stream, const Geometry *__restrict__ gp, const DecTable *__restrict__ tabs,
-                            DecState *__restrict__ A, uint8_t *__restrict__ chg, uint32_t *__restrict__ nblk)
+// Geometry and the Huffman tables are staged in shared memory: the decode loop indexes both dynamically.
+struct DecShared { Geometry g; DecTable tabs[8]; };
+__device__ __forceinline__ void stage_shared(DecShared &sh, const DecImage &im, const DecTable *__restrict__ tabs)
 {
-    const Geometry g = *gp;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(&im.g);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&sh.g);
+    for (int i = threadIdx.x; i < (int)(sizeof(Geometry) / 4); i += blockDim.x) dst[i] = src[i];
+    src = reinterpret_cast<const uint32_t *>(tabs); dst = reinterpret_cast<uint32_t *>(sh.tabs);
+    for (int i = threadIdx.x; i < (int)(sizeof(DecTable) * 8 / 4); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(64) k_gd_round0(const DecImage *__restrict__ imgs, const uint8_t *__restrict__ stream_all, const DecTable *__restrict__ tabs_all,
+                                                  DecState *__restrict__ A, uint8_t *__restrict__ chg, uint32_t *__restrict__ nblk)
+{
+    __shared__ DecShared sh;
+    const DecImage &im = imgs[blockIdx.y];
+    if (blockIdx.x * blockDim.x >= im.g.nsub) return;
+    stage_shared(sh, im, tabs_all + 8 * blockIdx.y);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= g.nsub) return;
-    NullSink sk; DecState st; st.p = i * g.subseq_bits; st.k = 0; st.b = 0;
-    A[i] = decode_subsequence(stream, g, tabs, i, st, sk);
-    nblk[i] = sk.nblk; chg[i] = 1;
+    if (i >= sh.g.nsub) return;
+    NullSink sk; DecState st; st.p = i * sh.g.subseq_bits; st.k = 0; st.b = 0;
+    A[im.sub_off + i] = decode_subsequence(stream_all + im.stream_off, sh.g, sh.tabs, i, st, sk);
+    nblk[im.sub_off + i] = sk.nblk; chg[im.sub_off + i] = 1;
 }
 
 // thread i restarts from exit i-1 of the previous round; if that exit did not change last round, neither can ours
-__global__ void k_gd_round(const uint8_t *__restrict__ stream, const Geometry *__restrict__ gp, const DecTable *__restrict__ tabs,
-                           const DecState *__restrict__ A, DecState *__restrict__ B, const uint8_t *__restrict__ chg_in, uint8_t *__restrict__ chg_out,
-                           uint32_t *__restrict__ nblk, uint32_t *__restrict__ any_changed)
+__global__ void __launch_bounds__(64) k_gd_round(const DecImage *__restrict__ imgs, const uint8_t *__restrict__ stream_all, const DecTable *__restrict__ tabs_all,
+                                                 const DecState *__restrict__ A, DecState *__restrict__ B, const uint8_t *__restrict__ chg_in, uint8_t *__restrict__ chg_out,
+                                                 uint32_t *__restrict__ nblk, uint32_t *__restrict__ any_changed /*[image]*/)
 {
-    const Geometry g = *gp;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= g.nsub) return;
-    if (i > 0 && !chg_in[i - 1]) { B[i] = A[i]; chg_out[i] = 0; return; }
+    __shared__ DecShared sh;
+    __shared__ int work;
+    const DecImage &im = imgs[blockIdx.y];
+    const uint32_t nsub = im.g.nsub;
+    if (blockIdx.x * blockDim.x >= nsub) return;
+    if (threadIdx.x == 0) work = 0;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, gi = im.sub_off + i;
+    const bool mine = i < nsub && (i == 0 || chg_in[gi - 1]);
+    if (i < nsub && !mine) { B[gi] = A[gi]; chg_out[gi] = 0; }
+    if (mine) work = 1;
+    __syncthreads();
+    if (!work) return;                              // nobody in this CTA has to re-decode: skip the table staging too
+    stage_shared(sh, im, tabs_all + 8 * blockIdx.y);
+    if (!mine) return;
     NullSink sk; DecState st;
-    if (i == 0) { st.p = 0; st.k = 0; st.b = 0; } else st = A[i - 1];
-    const DecState o = decode_subsequence(stream, g, tabs, i, st, sk);
-    B[i] = o; nblk[i] = sk.nblk;
-    const bool c = !same_state(o, A[i]);
-    chg_out[i] = c ? 1 : 0;
-    if (c) atomicOr(any_changed, 1u);
+    if (i == 0) { st.p = 0; st.k = 0; st.b = 0; } else st = A[gi - 1];
+    const DecState o = decode_subsequence(stream_all + im.stream_off, sh.g, sh.tabs, i, st, sk);
+    B[gi] = o; nblk[gi] = sk.nblk;
+    const bool c = !same_state(o, A[gi]);
+    chg_out[gi] = c ? 1 : 0;
+    if (c) atomicOr(&any_changed[blockIdx.y], 1u);
 }
 
 struct DevWriteSink {
-    const ge::Scan *scan; uint32_t cur, total;
-    __device__ __forceinline__ void coef(int k, int v) { if (cur < total) { const ge::BlockRef r = ge::locate(*scan, (int)cur); const_cast<int16_t *>(r.blk)[k] = (int16_t)v; } }
-    __device__ __forceinline__ void block_done() { cur++; }
+    const ge::Scan *scan; uint32_t cur, total; int16_t *ptr;
+    __device__ __forceinline__ void seek() { ptr = cur < total ? const_cast<int16_t *>(ge::locate(*scan, (int)cur).blk) : nullptr; }
+    __device__ __forceinline__ void coef(int k, int v) { if (ptr) ptr[k] = (int16_t)v; }
+    __device__ __forceinline__ void block_done() { cur++; seek(); }
 };
 
-__global__ void k_gd_write(const uint8_t *__restrict__ stream, const Geometry *__restrict__ gp, const DecTable *__restrict__ tabs,
-                           const DecState *__restrict__ A, const uint32_t *__restrict__ first, const ge::Scan *__restrict__ scan)
+__global__ void __launch_bounds__(64) k_gd_write(const DecImage *__restrict__ imgs, const uint8_t *__restrict__ stream_all, const DecTable *__restrict__ tabs_all,
+                                                 const DecState *__restrict__ A, const uint32_t *__restrict__ first)
 {
-    const Geometry g = *gp;
+    __shared__ DecShared sh;
+    __shared__ ge::Scan ssc;
+    const DecImage &im = imgs[blockIdx.y];
+    if (blockIdx.x * blockDim.x >= im.g.nsub) return;
+    stage_shared(sh, im, tabs_all + 8 * blockIdx.y);
+    if (threadIdx.x == 0) ssc = im.scan;
+    __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= g.nsub) return;
-    DevWriteSink sk{scan, first[i], g.total_blocks};
+    if (i >= sh.g.nsub) return;
+    DevWriteSink sk{&ssc, first[im.sub_off + i] - first[im.sub_off], sh.g.total_blocks, nullptr};
+    sk.seek();
     DecState st;
-    if (i == 0) { st.p = 0; st.k = 0; st.b = 0; } else st = A[i - 1];
-    decode_subsequence(stream, g, tabs, i, st, sk);
+    if (i == 0) { st.p = 0; st.k = 0; st.b = 0; } else st = A[im.sub_off + i - 1];
+    decode_subsequence(stream_all + im.stream_off, sh.g, sh.tabs, i, st, sk);
 }
 
 // ---- DC: gather differences component-major, inclusive scan, subtract the component's base, scatter ------------------
-__device__ __forceinline__ uint32_t dc_slot_index(const ge::Scan &s, uint32_t u, int *slot, uint32_t *comp_start)
-{   // position of scan-order unit u inside the component-major difference array
-    if (s.ns == 1) { *slot = 0; *comp_start = 0; return u; }
+__device__ __forceinline__ uint32_t dc_slot_index(const ge::Scan &s, uint32_t u, uint32_t *comp_start)
+{   // position of scan-order unit u inside the image's component-major difference array
+    if (s.ns == 1) { *comp_start = 0; return u; }
     const uint32_t m = u / s.blocks_per_mcu; int q = (int)(u - m * s.blocks_per_mcu), i = 0; uint32_t start = 0;
     const uint32_t mcus = (uint32_t)s.mcux * s.mcuy;
     while (q >= s.hs[i] * s.vs[i]) { q -= s.hs[i] * s.vs[i]; start += mcus * s.hs[i] * s.vs[i]; i++; }
-    *slot = i; *comp_start = start;
+    *comp_start = start;
     return start + m * s.hs[i] * s.vs[i] + q;
 }
-__global__ void k_gd_dc_gather(const ge::Scan *__restrict__ scan, uint32_t total, int32_t *__restrict__ d)
+__global__ void k_gd_dc_gather(const DecImage *__restrict__ imgs, int32_t *__restrict__ d)
 {
+    const DecImage &im = imgs[blockIdx.y];
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= total) return;
-    const ge::Scan s = *scan;
-    int slot; uint32_t cs;
-    d[dc_slot_index(s, u, &slot, &cs)] = ge::locate(s, (int)u).blk[0];
+    if (u >= im.g.total_blocks) return;
+    uint32_t cs;
+    d[im.blk_off + dc_slot_index(im.scan, u, &cs)] = ge::locate(im.scan, (int)u).blk[0];
 }
-__global__ void k_gd_dc_scatter(const ge::Scan *__restrict__ scan, uint32_t total, const int32_t *__restrict__ sum)
+__global__ void k_gd_dc_scatter(const DecImage *__restrict__ imgs, const int32_t *__restrict__ sum)
 {
+    const DecImage &im = imgs[blockIdx.y];
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= total) return;
-    const ge::Scan s = *scan;
-    int slot; uint32_t cs;
-    const uint32_t idx = dc_slot_index(s, u, &slot, &cs);
-    const int32_t base = cs ? sum[cs - 1] : 0;
-    const_cast<int16_t *>(ge::locate(s, (int)u).blk)[0] = (int16_t)(sum[idx] - base);
+    if (u >= im.g.total_blocks) return;
+    uint32_t cs;
+    const uint32_t idx = dc_slot_index(im.scan, u, &cs);
+    const uint32_t b = im.blk_off + cs;
+    const int32_t base = b ? sum[b - 1] : 0;
+    const_cast<int16_t *>(ge::locate(im.scan, (int)u).blk)[0] = (int16_t)(sum[im.blk_off + idx] - base);
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------------------------
@@ -118,7 +161,9 @@ template <typename T> static bool growd(T *&p, size_t &cap, size_t need, bool ho
     if (need <= cap) return true;
     if (p) { if (host) cudaFreeHost(p); else cudaFree(p); }
     p = nullptr; cap = 0;
-    size_t want = align_up(need + need / 4, 1 << 12);
+    // sizes here depend on image CONTENT (bytes of entropy-coded data); round up to a power of two with headroom so a
+    // slot stops reallocating after its first image of a given class (cudaFree / cudaHostAlloc stall every stream)
+    size_t want = 1 << 16; while (want < need + need / 2) want <<= 1;
     void *q = nullptr;
     cudaError_t e = host ? cudaHostAlloc(&q, want, cudaHostAllocDefault) : cudaMalloc(&q, want);
     if (e != cudaSuccess) { err = std::string(host ? "cudaHostAlloc: " : "cudaMalloc: ") + cudaGetErrorString(e); return false; }
@@ -131,87 +176,107 @@ GpuDecoder::~GpuDecoder()
     cudaFree(d_nblk); cudaFree(d_first); cudaFree(d_dc); cudaFree(d_dcs); cudaFree(d_par); cudaFreeHost(h_par); cudaFree(d_temp);
 }
 
-GpuDecoder::Result GpuDecoder::decode(const JpegReader &rd, const JpegReader::DeviceScan &ds, int16_t *d_coefs, void *stream_, std::string &err)
+bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &err)
 {
     cudaStream_t st = (cudaStream_t)stream_;
-    const JpegGeom &g = rd.geom();
-    const size_t nraw = ds.ecs_end - ds.ecs_begin;
-    if (nraw >= (1ull << 28)) { err = "entropy-coded segment too large for the device decoder"; return FAILED; }
-    const uint32_t nstream = (uint32_t)(nraw - ds.stuffed);
-    Geometry G{};
-    int q = 0;
-    for (int c = 0; c < g.ncomp; c++) for (int k = 0; k < (g.ncomp == 1 ? 1 : g.hs[c] * g.vs[c]); k++) { if (q >= 10) { err = "MCU too large"; return FAILED; } G.dc_tbl[q] = ds.td[c]; G.ac_tbl[q] = ds.ta[c]; q++; }
-    G.blocks_per_mcu = q;
-    G.total_blocks = g.ncomp == 1 ? (uint32_t)(g.rbw[0] * g.rbh[0]) : (uint32_t)(g.mcux * g.mcuy * q);
-    G.nbits = nstream * 8; G.subseq_bits = SUBSEQ_BITS; G.nsub = (G.nbits + G.subseq_bits - 1) / G.subseq_bits;
-    if (G.nsub == 0) { err = "empty scan"; return FAILED; }
-    GpuEncPlan plan; const int16_t *base = d_coefs;
-    gpuenc_plan(g, false, &base, 1, plan);
-    const uint32_t ngroups = (uint32_t)((nraw + 15) / 16);
+    const int N = (int)items.size();
+    if (N == 0) return true;
+    // ---- per-image descriptors
+    std::vector<DecImage> imgs((size_t)N);
+    size_t raw_total = 0, stream_total = 0; uint32_t grp_total = 0, sub_total = 0, blk_total = 0, max_grp = 0, max_sub = 0, max_blk = 0;
+    for (int n = 0; n < N; n++) {
+        const JpegReader &rd = *items[n].rd; const JpegReader::DeviceScan &ds = *items[n].ds; const JpegGeom &g = rd.geom();
+        items[n].result = FAILED;
+        DecImage &im = imgs[n]; memset(&im, 0, sizeof(im));
+        const size_t nraw = ds.ecs_end - ds.ecs_begin;
+        if (nraw >= (1ull << 28)) { err = "entropy-coded segment too large for the device decoder"; return false; }
+        const uint32_t nstream = (uint32_t)(nraw - ds.stuffed);
+        Geometry &G = im.g;
+        int q = 0;
+        for (int c = 0; c < g.ncomp; c++) for (int k = 0; k < (g.ncomp == 1 ? 1 : g.hs[c] * g.vs[c]); k++) { if (q >= 10) { err = "MCU too large"; return false; } G.dc_tbl[q] = ds.td[c]; G.ac_tbl[q] = ds.ta[c]; q++; }
+        G.blocks_per_mcu = q;
+        G.total_blocks = g.ncomp == 1 ? (uint32_t)(g.rbw[0] * g.rbh[0]) : (uint32_t)(g.mcux * g.mcuy * q);
+        G.nbits = nstream * 8; G.subseq_bits = SUBSEQ_BITS; G.nsub = (G.nbits + G.subseq_bits - 1) / G.subseq_bits;
+        if (G.nsub == 0) { err = "empty scan"; return false; }
+        GpuEncPlan plan; const int16_t *base = items[n].d_coefs;
+        gpuenc_plan(g, false, &base, 1, plan);
+        im.scan = plan.scans[0];
+        im.raw_off = (uint32_t)raw_total; im.nraw = (uint32_t)nraw; raw_total += align_up(nraw + 16, 16);
+        im.stream_off = (uint32_t)stream_total; stream_total += align_up((size_t)nstream + 32, 16);
+        im.grp_off = grp_total; im.ngrp = (uint32_t)((nraw + 15) / 16); grp_total += im.ngrp;
+        im.sub_off = sub_total; sub_total += G.nsub;
+        im.blk_off = blk_total; blk_total += G.total_blocks;
+        max_grp = std::max(max_grp, im.ngrp); max_sub = std::max(max_sub, G.nsub); max_blk = std::max(max_blk, G.total_blocks);
+    }
+    if (raw_total >= (1ull << 31) || stream_total >= (1ull << 31)) { err = "decode batch too large"; return false; }
     // ---- buffers
-    const size_t par_bytes = align_up(sizeof(Geometry), 256) + align_up(sizeof(ge::Scan), 256) + align_up(sizeof(DecTable) * 8, 256) + align_up(4 * (MAX_ROUNDS + 2), 256);
-    if (!growd(h_raw, cap_hraw, nraw + 64, true, err) || !growd(d_raw, cap_raw, nraw + 64, false, err) || !growd(d_stream, cap_stream, (size_t)nstream + 64, false, err) ||
-        !growd(d_cnt, cap_cnt, (size_t)ngroups * 4 + 4, false, err) || !growd(d_off, cap_off, (size_t)ngroups * 4 + 4, false, err) ||
-        !growd(d_A, cap_A, (size_t)G.nsub * sizeof(DecState), false, err) || !growd(d_B, cap_B, (size_t)G.nsub * sizeof(DecState), false, err) ||
-        !growd(d_chgA, cap_chgA, G.nsub, false, err) || !growd(d_chgB, cap_chgB, G.nsub, false, err) ||
-        !growd(d_nblk, cap_nblk, (size_t)G.nsub * 4, false, err) || !growd(d_first, cap_first, (size_t)G.nsub * 4, false, err) ||
-        !growd(d_dc, cap_dc, (size_t)G.total_blocks * 4, false, err) || !growd(d_dcs, cap_dcs, (size_t)G.total_blocks * 4, false, err) ||
-        !growd(d_par, cap_par, par_bytes, false, err) || !growd(h_par, cap_hpar, par_bytes, true, err)) return FAILED;
+    const size_t o_img = 0, o_tab = align_up(sizeof(DecImage) * N, 256), o_flag = o_tab + align_up(sizeof(DecTable) * 8 * N, 256);
+    const size_t par_bytes = o_flag + align_up((size_t)4 * N * (MAX_ROUNDS + 2), 256);
+    if (!growd(h_raw, cap_hraw, raw_total + 64, true, err) || !growd(d_raw, cap_raw, raw_total + 64, false, err) || !growd(d_stream, cap_stream, stream_total + 64, false, err) ||
+        !growd(d_cnt, cap_cnt, (size_t)grp_total * 4 + 4, false, err) || !growd(d_off, cap_off, (size_t)grp_total * 4 + 4, false, err) ||
+        !growd(d_A, cap_A, (size_t)sub_total * sizeof(DecState), false, err) || !growd(d_B, cap_B, (size_t)sub_total * sizeof(DecState), false, err) ||
+        !growd(d_chgA, cap_chgA, sub_total, false, err) || !growd(d_chgB, cap_chgB, sub_total, false, err) ||
+        !growd(d_nblk, cap_nblk, (size_t)sub_total * 4, false, err) || !growd(d_first, cap_first, (size_t)sub_total * 4, false, err) ||
+        !growd(d_dc, cap_dc, (size_t)blk_total * 4, false, err) || !growd(d_dcs, cap_dcs, (size_t)blk_total * 4, false, err) ||
+        !growd(d_par, cap_par, par_bytes, false, err) || !growd(h_par, cap_hpar, par_bytes, true, err)) return false;
     size_t t1 = 0, t2 = 0, t3 = 0;
-    cub::DeviceScan::ExclusiveSum((void *)nullptr, t1, d_cnt, d_off, (int)ngroups, st);
-    cub::DeviceScan::ExclusiveSum((void *)nullptr, t2, d_nblk, d_first, (int)G.nsub, st);
-    cub::DeviceScan::InclusiveSum((void *)nullptr, t3, d_dc, d_dcs, (int)G.total_blocks, st);
-    if (!growd(d_temp, cap_temp, std::max(t1, std::max(t2, t3)) + 256, false, err)) return FAILED;
-    // ---- parameters
-    uint8_t *hp = h_par;
-    const size_t o_geo = 0, o_scan = align_up(sizeof(Geometry), 256), o_tab = o_scan + align_up(sizeof(ge::Scan), 256), o_flag = o_tab + align_up(sizeof(DecTable) * 8, 256);
-    memcpy(hp + o_geo, &G, sizeof(G));
-    memcpy(hp + o_scan, &plan.scans[0], sizeof(ge::Scan));
-    DecTable *ht = reinterpret_cast<DecTable *>(hp + o_tab);
-    memset(ht, 0, sizeof(DecTable) * 8);
-    for (int id = 0; id < 4; id++) for (int kind = 0; kind < 2; kind++) if (rd.dht_present(kind, id)) build_dec_table(rd.dht_bits(kind, id), rd.dht_vals(kind, id), ht[kind * 4 + id]);
-    memset(hp + o_flag, 0, 4 * (MAX_ROUNDS + 2));
-    memcpy(h_raw, rd.data() + ds.ecs_begin, nraw);
+    cub::DeviceScan::ExclusiveSum((void *)nullptr, t1, d_cnt, d_off, (int)grp_total, st);
+    cub::DeviceScan::ExclusiveSum((void *)nullptr, t2, d_nblk, d_first, (int)sub_total, st);
+    cub::DeviceScan::InclusiveSum((void *)nullptr, t3, d_dc, d_dcs, (int)blk_total, st);
+    if (!growd(d_temp, cap_temp, std::max(t1, std::max(t2, t3)) + 256, false, err)) return false;
+    // ---- parameters + raw bytes
+    memcpy(h_par + o_img, imgs.data(), sizeof(DecImage) * N);
+    DecTable *ht = reinterpret_cast<DecTable *>(h_par + o_tab);
+    memset(ht, 0, sizeof(DecTable) * 8 * N);
+    for (int n = 0; n < N; n++) {
+        const JpegReader &rd = *items[n].rd;
+        for (int id = 0; id < 4; id++) for (int kind = 0; kind < 2; kind++) if (rd.dht_present(kind, id)) build_dec_table(rd.dht_bits(kind, id), rd.dht_vals(kind, id), ht[8 * n + kind * 4 + id]);
+        memcpy(h_raw + imgs[n].raw_off, rd.data() + items[n].ds->ecs_begin, imgs[n].nraw);
+    }
+    memset(h_par + o_flag, 0, (size_t)4 * N * (MAX_ROUNDS + 2));
     CUD(cudaMemcpyAsync(d_par, h_par, par_bytes, cudaMemcpyHostToDevice, st));
-    CUD(cudaMemcpyAsync(d_raw, h_raw, nraw, cudaMemcpyHostToDevice, st));
-    const Geometry *dG = reinterpret_cast<const Geometry *>(d_par + o_geo);
-    const ge::Scan *dS = reinterpret_cast<const ge::Scan *>(d_par + o_scan);
+    CUD(cudaMemcpyAsync(d_raw, h_raw, raw_total, cudaMemcpyHostToDevice, st));
+    const DecImage *dI = reinterpret_cast<const DecImage *>(d_par + o_img);
     const DecTable *dT = reinterpret_cast<const DecTable *>(d_par + o_tab);
     uint32_t *dF = reinterpret_cast<uint32_t *>(d_par + o_flag);
     uint32_t *hF = reinterpret_cast<uint32_t *>(h_par + o_flag);
     // ---- unstuff
-    k_gd_unstuff_count<<<cdiv(ngroups, 128), 128, 0, st>>>(d_raw, (uint32_t)nraw, d_cnt);
+    const dim3 gg(cdiv(max_grp, 128), N);
+    k_gd_unstuff_count<<<gg, 128, 0, st>>>(dI, d_raw, d_cnt);
     size_t tb = cap_temp;
-    cub::DeviceScan::ExclusiveSum(d_temp, tb, d_cnt, d_off, (int)ngroups, st);
-    k_gd_unstuff_scatter<<<cdiv(ngroups, 128), 128, 0, st>>>(d_raw, (uint32_t)nraw, d_off, d_stream);
-    CUD(cudaMemsetAsync(d_coefs, 0, (size_t)g.total_coefs * 2, st));
+    cub::DeviceScan::ExclusiveSum(d_temp, tb, d_cnt, d_off, (int)grp_total, st);
+    k_gd_unstuff_scatter<<<gg, 128, 0, st>>>(dI, d_raw, d_off, d_stream);
+    for (int n = 0; n < N; n++) CUD(cudaMemsetAsync(items[n].d_coefs, 0, (size_t)items[n].rd->geom().total_coefs * 2, st));
     // ---- rounds
-    const int gs = cdiv(G.nsub, 64);
-    k_gd_round0<<<gs, 64, 0, st>>>(d_stream, dG, dT, d_A, d_chgA, d_nblk);
+    const dim3 gs(cdiv(max_sub, 64), N);
+    k_gd_round0<<<gs, 64, 0, st>>>(dI, d_stream, dT, d_A, d_chgA, d_nblk);
     DecState *A = d_A, *B = d_B; uint8_t *cA = d_chgA, *cB = d_chgB;
-    int rounds = 0; bool converged = false;
-    while (!converged && rounds < MAX_ROUNDS) {
+    int rounds = 0; std::vector<char> conv((size_t)N, 0); int nconv = 0;
+    while (nconv < N && rounds < MAX_ROUNDS) {
         const int first_round = rounds;
         for (int r = 0; r < ROUNDS_PER_GROUP && rounds < MAX_ROUNDS; r++, rounds++) {
-            k_gd_round<<<gs, 64, 0, st>>>(d_stream, dG, dT, A, B, cA, cB, d_nblk, dF + rounds);
+            k_gd_round<<<gs, 64, 0, st>>>(dI, d_stream, dT, A, B, cA, cB, d_nblk, dF + (size_t)rounds * N);
             std::swap(A, B); std::swap(cA, cB);
         }
-        CUD(cudaMemcpyAsync(hF + first_round, dF + first_round, 4 * (rounds - first_round), cudaMemcpyDeviceToHost, st));
+        CUD(cudaMemcpyAsync(hF + (size_t)first_round * N, dF + (size_t)first_round * N, (size_t)4 * N * (rounds - first_round), cudaMemcpyDeviceToHost, st));
         CUD(cudaStreamSynchronize(st));
-        for (int r = first_round; r < rounds; r++) if (hF[r] == 0) { converged = true; break; }
+        for (int n = 0; n < N; n++) if (!conv[n]) for (int r = first_round; r < rounds; r++) if (hF[(size_t)r * N + n] == 0) { conv[n] = 1; nconv++; break; }
     }
     rounds_used = rounds;
-    if (!converged) return NOT_CONVERGED;
-    // ---- block counts -> first block of each subsequence -> write -> DC
+    for (int n = 0; n < N; n++) items[n].result = conv[n] ? OK : NOT_CONVERGED;
+    if (nconv == 0) return true;
+    // ---- block counts -> first block of each subsequence -> write -> DC (images that did not converge produce garbage
+    //      that their caller discards)
     tb = cap_temp;
-    cub::DeviceScan::ExclusiveSum(d_temp, tb, d_nblk, d_first, (int)G.nsub, st);
-    k_gd_write<<<gs, 64, 0, st>>>(d_stream, dG, dT, A, d_first, dS);
-    k_gd_dc_gather<<<cdiv(G.total_blocks, 128), 128, 0, st>>>(dS, G.total_blocks, d_dc);
+    cub::DeviceScan::ExclusiveSum(d_temp, tb, d_nblk, d_first, (int)sub_total, st);
+    k_gd_write<<<gs, 64, 0, st>>>(dI, d_stream, dT, A, d_first);
+    const dim3 gb(cdiv(max_blk, 128), N);
+    k_gd_dc_gather<<<gb, 128, 0, st>>>(dI, d_dc);
     tb = cap_temp;
-    cub::DeviceScan::InclusiveSum(d_temp, tb, d_dc, d_dcs, (int)G.total_blocks, st);
-    k_gd_dc_scatter<<<cdiv(G.total_blocks, 128), 128, 0, st>>>(dS, G.total_blocks, d_dcs);
+    cub::DeviceScan::InclusiveSum(d_temp, tb, d_dc, d_dcs, (int)blk_total, st);
+    k_gd_dc_scatter<<<gb, 128, 0, st>>>(dI, d_dcs);
     CUD(cudaGetLastError());
-    return OK;
+    return true;
 }
 
 } // namespace b200

@@ -1,4 +1,5 @@
-// jpeg_gpudec.h -- device-side JPEG entropy DECODER for baseline single-scan files (see jpeg_gpudec_core.h).
+// jpeg_gpudec.h -- device-side JPEG entropy DECODER for baseline single-scan files (see jpeg_gpudec_core.h), batched:
+// one pass sequence decodes any number of images (blockIdx.y = image).
 #pragma once
 #include <cstdint>
 #include <cstddef>
@@ -9,6 +10,16 @@
 
 namespace b200 {
 
+struct DecImage {               // one image of a decode batch (device-visible)
+    uint32_t raw_off, nraw;     // entropy-coded segment inside the batch's raw buffer
+    uint32_t stream_off;        // unstuffed stream inside the batch's stream buffer (word aligned, 0xFF padded)
+    uint32_t grp_off, ngrp;     // 16-byte groups of the raw segment (un-stuffing)
+    uint32_t sub_off;           // first subsequence of this image in the state arrays
+    uint32_t blk_off;           // first block of this image in the DC arrays
+    gd::Geometry g;
+    ge::Scan scan;              // output addressing (scan.coef = this image's coefficient buffer)
+};
+
 class GpuDecoder {
 public:
     GpuDecoder() = default;
@@ -16,22 +27,23 @@ public:
     GpuDecoder(const GpuDecoder &) = delete;
     GpuDecoder &operator=(const GpuDecoder &) = delete;
     enum Result { OK = 0, NOT_CONVERGED = 1, FAILED = 2 };
-    // Decode the scan described by `ds` of the file behind `rd` straight into d_coefs (device, geometry rd.geom(), zigzag,
-    // fully overwritten).  NOT_CONVERGED: the self-synchronisation did not settle within the round budget (degenerate
-    // periodic streams) -- the caller decodes on the host instead.  Blocking on `stream` (one short host sync per group
-    // of rounds).
-    Result decode(const JpegReader &rd, const JpegReader::DeviceScan &ds, int16_t *d_coefs, void *stream, std::string &err);
+    struct Item { const JpegReader *rd; const JpegReader::DeviceScan *ds; int16_t *d_coefs; Result result; };
+    // Decode every item's scan straight into its d_coefs (device; fully overwritten).  Per item: OK, or NOT_CONVERGED
+    // (the self-synchronisation did not settle within the round budget -- degenerate periodic streams -- the caller
+    // decodes that image on the host instead).  Returns false on a CUDA failure.  Asynchronous work on `stream`, with one
+    // short host sync per group of rounds.
+    bool decode(std::vector<Item> &items, void *stream, std::string &err);
     int rounds_used = 0;
-    static constexpr int SUBSEQ_BITS = 1024, ROUNDS_PER_GROUP = 6, MAX_ROUNDS = 48;
+    static constexpr int SUBSEQ_BITS = 1024, ROUNDS_PER_GROUP = 16, MAX_ROUNDS = 64;
 private:
-    uint8_t *h_raw = nullptr; size_t cap_hraw = 0;          // pinned staging of the entropy-coded segment
+    uint8_t *h_raw = nullptr; size_t cap_hraw = 0;          // pinned staging of the entropy-coded segments
     uint8_t *d_raw = nullptr, *d_stream = nullptr; size_t cap_raw = 0, cap_stream = 0;
     uint32_t *d_cnt = nullptr, *d_off = nullptr; size_t cap_cnt = 0, cap_off = 0;
     gd::DecState *d_A = nullptr, *d_B = nullptr; size_t cap_A = 0, cap_B = 0;
     uint8_t *d_chgA = nullptr, *d_chgB = nullptr; size_t cap_chgA = 0, cap_chgB = 0;
     uint32_t *d_nblk = nullptr, *d_first = nullptr; size_t cap_nblk = 0, cap_first = 0;
     int32_t *d_dc = nullptr, *d_dcs = nullptr; size_t cap_dc = 0, cap_dcs = 0;
-    uint8_t *d_par = nullptr, *h_par = nullptr; size_t cap_par = 0, cap_hpar = 0;   // Geometry | Scan | tables | round flags
+    uint8_t *d_par = nullptr, *h_par = nullptr; size_t cap_par = 0, cap_hpar = 0;   // DecImage[] | DecTable[8][] | round flags
     uint8_t *d_temp = nullptr; size_t cap_temp = 0;
 };
 

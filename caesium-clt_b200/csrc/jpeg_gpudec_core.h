@@ -33,15 +33,23 @@ struct DecState { uint32_t p; uint16_t k; uint16_t b; };   // 8 bytes
 
 GE_HD bool same_state(const DecState &a, const DecState &b) { return a.p == b.p && a.k == b.k && a.b == b.b; }
 
-// 32 bits of the unstuffed stream starting at bit position p (big-endian bit order); bits past the end read as 1s
-GE_HD uint32_t peek32(const uint8_t *__restrict__ s, uint32_t nbits_total, uint32_t p)
+// 32 bits of the unstuffed stream starting at bit position p (big-endian bit order).  The stream buffer is 4-byte
+// aligned and followed by at least 8 bytes of 0xFF padding, so bits past the end read as 1s (like jdhuff.c's padding)
+// and two aligned word loads always suffice.
+GE_HD uint32_t load_be32(const uint8_t *__restrict__ s, uint32_t word)
 {
-    const uint32_t byte = p >> 3, sh = p & 7;
-    const uint32_t nbytes = (nbits_total + 7) >> 3;
-    uint64_t w = 0;
-#pragma unroll
-    for (int i = 0; i < 5; i++) { const uint32_t bi = byte + i; w = (w << 8) | (bi < nbytes ? s[bi] : 0xFFu); }
-    return (uint32_t)(w >> (8 - sh));
+    const uint32_t w = reinterpret_cast<const uint32_t *>(s)[word];
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(w, 0, 0x0123);
+#else
+    return __builtin_bswap32(w);
+#endif
+}
+GE_HD uint32_t peek32(const uint8_t *__restrict__ s, uint32_t /*nbits_total*/, uint32_t p)
+{
+    const uint32_t wi = p >> 5, sh = p & 31;
+    const uint32_t w0 = load_be32(s, wi), w1 = load_be32(s, wi + 1);
+    return sh ? (w0 << sh) | (w1 >> (32 - sh)) : w0;
 }
 
 // decode one Huffman symbol from the top bits of `bits` (32 valid bits); returns symbol, *len = code length (>= 1)

@@ -109,8 +109,13 @@ __global__ void k_ge_tables(const uint32_t *__restrict__ hist, Table *__restrict
         }
         int i = 16; while (i > 0 && bits[i] == 0) i--;
         if (i > 0) bits[i]--;
-        int p = 0;
-        for (int l = 1; l <= 32; l++) for (int s = 0; s <= 255; s++) if (codesize[s] == l) T.vals[p++] = (uint8_t)s;
+        // symbols sorted by (code length, symbol value): counting sort on the UNLIMITED lengths, as the IJG loop orders them
+        int start[34];
+        for (int l = 0; l < 34; l++) start[l] = 0;
+        for (int s = 0; s <= 255; s++) if (codesize[s]) start[min(codesize[s], 32) + 1]++;
+        for (int l = 1; l < 34; l++) start[l] += start[l - 1];
+        const int p = start[33];
+        for (int s = 0; s <= 255; s++) if (codesize[s]) T.vals[start[min(codesize[s], 32)]++] = (uint8_t)s;
         T.nvals = p;
         for (int k = 0; k < 17; k++) T.bits[k] = bits[k];
         for (int s = 0; s < 256; s++) { T.code[s] = 0; T.size[s] = 0; }
@@ -237,7 +242,9 @@ template <typename T> static bool grow(T *&p, size_t &cap, size_t need, bool hos
     if (need <= cap) return true;
     if (p) { if (host) cudaFreeHost(p); else cudaFree(p); }
     p = nullptr; cap = 0;
-    size_t want = align_up(need + need / 4, 1 << 12);
+    // several sizes depend on image CONTENT (bytes of entropy-coded output); round up to a power of two with headroom so
+    // a slot stops reallocating after its first image of a given class (cudaFree / cudaHostAlloc stall every stream)
+    size_t want = 1 << 16; while (want < need + need / 2) want <<= 1;
     void *q = nullptr;
     cudaError_t e = host ? cudaHostAlloc(&q, want, cudaHostAllocDefault) : cudaMalloc(&q, want);
     if (e != cudaSuccess) { err = std::string(host ? "cudaHostAlloc: " : "cudaMalloc: ") + cudaGetErrorString(e); return false; }

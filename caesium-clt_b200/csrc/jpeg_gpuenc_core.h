@@ -102,23 +102,78 @@ GE_HD BlockRef locate(const Scan &s, int u)
     return r;
 }
 
+// ---- bit masks over a block: bit k of mask(T) is set iff |coef[k]| >= T ----------------------------------------------
+// The scans only ever ask "is |c| >> Al zero / one / more", i.e. threshold tests against 2^Al and 2^(Al+1); with the
+// masks in hand every loop below visits the non-zero coefficients only (a handful per block) instead of all 63.
+GE_HD int ctz64(unsigned long long m)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)m) - 1;
+#else
+    return __builtin_ctzll(m);
+#endif
+}
+GE_HD int msb64(unsigned long long m)       // index of the highest set bit, -1 for 0
+{
+#if defined(__CUDA_ARCH__)
+    return 63 - __clzll((long long)m);
+#else
+    return m ? 63 - __builtin_clzll(m) : -1;
+#endif
+}
+GE_HD int popc64(unsigned long long m)
+{
+#if defined(__CUDA_ARCH__)
+    return __popcll(m);
+#else
+    return __builtin_popcountll(m);
+#endif
+}
+GE_HD unsigned long long band_mask(int Ss, int Se) { return (Se >= 63 ? ~0ull : ((1ull << (Se + 1)) - 1ull)) & ~((1ull << Ss) - 1ull); }
+
+GE_HD void make_masks(const int16_t *__restrict__ blk, int T1, int T2, unsigned long long &m1, unsigned long long &m2)
+{
+#if defined(__CUDA_ARCH__)
+    const uint4 *v = reinterpret_cast<const uint4 *>(blk);          // 8 x 128-bit loads, two coefficients per 32-bit word
+    const unsigned t1 = (unsigned)T1 * 0x00010001u, t2 = (unsigned)T2 * 0x00010001u;
+    unsigned lo1 = 0, hi1 = 0, lo2 = 0, hi2 = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint4 q = v[j];
+        const unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const unsigned a = __vabsss2(w[i]);
+            const unsigned c1 = __vcmpgeu2(a, t1), c2 = __vcmpgeu2(a, t2);
+            const unsigned b1 = (c1 & 1u) | ((c1 >> 15) & 2u), b2 = (c2 & 1u) | ((c2 >> 15) & 2u);
+            const int sh = 2 * ((4 * j + i) & 15);
+            if (j < 4) { lo1 |= b1 << sh; lo2 |= b2 << sh; } else { hi1 |= b1 << sh; hi2 |= b2 << sh; }
+        }
+    }
+    m1 = ((unsigned long long)hi1 << 32) | lo1; m2 = ((unsigned long long)hi2 << 32) | lo2;
+#else
+    m1 = m2 = 0;
+    for (int k = 0; k < 64; k++) { int a = blk[k]; if (a < 0) a = -a; if (a >= T1) m1 |= 1ull << k; if (a >= T2) m2 |= 1ull << k; }
+#endif
+}
+
 // ---- classification (pass 0) ------------------------------------------------------------------------------------
 GE_HD uint32_t classify(const Scan &s, const int16_t *blk)
 {
     if (s.mode == MODE_SEQ || s.mode == MODE_DC_FIRST) return meta_pack(true, false, 0);
-    if (s.mode == MODE_AC_FIRST) {
-        int last = -1;
-        for (int k = s.Ss; k <= s.Se; k++) { int t = blk[k]; if (t < 0) t = -t; if ((t >> s.Al) != 0) last = k; }
-        return meta_pack(last >= 0, last < s.Se, 0);
-    }
+    unsigned long long mA, mB;
+    make_masks(blk, 1 << s.Al, 2 << s.Al, mA, mB);
+    const unsigned long long band = band_mask(s.Ss, s.Se);
+    mA &= band; mB &= band;
+    if (s.mode == MODE_AC_FIRST) { const int last = msb64(mA); return meta_pack(last >= 0, last < s.Se, 0); }
     // AC refinement: inline symbols exist iff some coefficient becomes non-zero in this scan (|c| >> Al == 1).  After
     // the last such coefficient every remaining position is either zero (r++) or already non-zero (a pending correction
     // bit), so the block joins an EOB group (jcphuff.c: r > 0 || BR > 0) exactly when that coefficient is not at Se.
-    int last_new = -1, tail = 0;
-    for (int k = s.Ss; k <= s.Se; k++) {
-        int t = blk[k]; if (t < 0) t = -t; t >>= s.Al;
-        if (t == 1) { last_new = k; tail = 0; } else if (t > 1) tail++;
-    }
+    const int last_new = msb64(mA & ~mB);
+    int tail;                                   // already-non-zero coefficients after the last newly non-zero one
+    if (last_new < 0) tail = popc64(mB);
+    else if (last_new >= 63) tail = 0;
+    else tail = popc64(mB & ~((2ull << last_new) - 1ull));
     return meta_pack(last_new >= 0, last_new < s.Se, tail);
 }
 
@@ -146,51 +201,60 @@ GE_HD void gen_block(const Scan &s, const BlockRef &b, unsigned group_count, Sin
 {
     const int16_t *blk = b.blk;
     const int tbl = s.tbl[b.slot];
+    if (s.mode == MODE_DC_FIRST) { gen_dc(blk[0] >> s.Al, b.prev ? (b.prev[0] >> s.Al) : 0, tbl, sk); return; }
+    unsigned long long mA, mB;                  // |c| >= 2^Al, |c| >= 2^(Al+1)
     if (s.mode == MODE_SEQ) {
+        make_masks(blk, 1, 2, mA, mB);
         gen_dc(blk[0], b.prev ? b.prev[0] : 0, tbl, sk);
-        int r = 0;
-        for (int k = 1; k < 64; k++) {
-            int t = blk[k];
-            if (t == 0) { r++; continue; }
+        int prevk = 0;
+        for (unsigned long long m = mA & ~1ull; m; m &= m - 1) {
+            const int k = ctz64(m);
+            int r = k - prevk - 1; prevk = k;
             while (r > 15) { sk.sym(1, tbl, 0xF0, 0, 0); r -= 16; }
-            int t2 = t; if (t < 0) { t = -t; t2--; }
+            int t = blk[k], t2 = t; if (t < 0) { t = -t; t2--; }
             const int nb = nbits_of((unsigned)t);
             sk.sym(1, tbl, (r << 4) + nb, nb, (unsigned)t2);
-            r = 0;
         }
-        if (r > 0) sk.sym(1, tbl, 0, 0, 0);
+        if (prevk != 63) sk.sym(1, tbl, 0, 0, 0);
         return;
     }
-    if (s.mode == MODE_DC_FIRST) { gen_dc(blk[0] >> s.Al, b.prev ? (b.prev[0] >> s.Al) : 0, tbl, sk); return; }
+    make_masks(blk, 1 << s.Al, 2 << s.Al, mA, mB);
+    const unsigned long long band = band_mask(s.Ss, s.Se);
+    mA &= band; mB &= band;
     if (s.mode == MODE_AC_FIRST) {
-        int r = 0;
-        for (int k = s.Ss; k <= s.Se; k++) {
-            int t = blk[k], t2;
-            if (t == 0) { r++; continue; }
-            if (t < 0) { t = -t; t >>= s.Al; t2 = ~t; } else { t >>= s.Al; t2 = t; }
-            if (t == 0) { r++; continue; }
+        int prevk = s.Ss - 1;
+        for (unsigned long long m = mA; m; m &= m - 1) {
+            const int k = ctz64(m);
+            int r = k - prevk - 1; prevk = k;
             while (r > 15) { sk.sym(1, tbl, 0xF0, 0, 0); r -= 16; }
+            int t = blk[k], t2;
+            if (t < 0) { t = (-t) >> s.Al; t2 = ~t; } else { t >>= s.Al; t2 = t; }
             const int nb = nbits_of((unsigned)t);
             sk.sym(1, tbl, (r << 4) + nb, nb, (unsigned)t2);
-            r = 0;
         }
         if (group_count) gen_eob_token(group_count, tbl, sk);
         return;
     }
-    // MODE_AC_REFINE (jcphuff.c encode_mcu_AC_refine): pending correction bits are emitted right after each inline symbol
-    int EOB = 0;
-    for (int k = s.Ss; k <= s.Se; k++) { int t = blk[k]; if (t < 0) t = -t; if ((t >> s.Al) == 1) EOB = k; }
-    int r = 0;
+    // MODE_AC_REFINE (jcphuff.c encode_mcu_AC_refine): pending correction bits are emitted right after each inline symbol.
+    // mA & ~mB = coefficients that become non-zero in this scan, mB = already non-zero ones (one correction bit each).
+    const unsigned long long newm = mA & ~mB;
+    const int last_new = msb64(newm);
+    const int EOB = last_new < 0 ? 0 : last_new;
+    int r = 0, prevk = s.Ss - 1;
     int npend = 0; unsigned long long pend64 = 0;   // pending correction bits of this block (at most 63)
-    for (int k = s.Ss; k <= s.Se; k++) {
-        int t = blk[k]; if (t < 0) t = -t; t >>= s.Al;
-        if (t == 0) { r++; continue; }
+    for (unsigned long long m = mA; m; m &= m - 1) {
+        const int k = ctz64(m);
+        r += k - prevk - 1; prevk = k;
         while (r > 15 && k <= EOB) {
             sk.sym(1, tbl, 0xF0, 0, 0); r -= 16;
             if (npend) { sk.raw64(npend, pend64); npend = 0; pend64 = 0; }
         }
-        if (t > 1) { pend64 = (pend64 << 1) | (unsigned)(t & 1); npend++; continue; }
-        sk.sym(1, tbl, (r << 4) + 1, 1, blk[k] < 0 ? 0u : 1u);
+        int t = blk[k];
+        const bool neg = t < 0;
+        if (neg) t = -t;
+        t >>= s.Al;
+        if ((mB >> k) & 1ull) { pend64 = (pend64 << 1) | (unsigned)(t & 1); npend++; continue; }
+        sk.sym(1, tbl, (r << 4) + 1, 1, neg ? 0u : 1u);
         if (npend) { sk.raw64(npend, pend64); npend = 0; pend64 = 0; }
         r = 0;
     }

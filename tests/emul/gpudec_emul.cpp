@@ -30,12 +30,14 @@ extern "C" int emul_gpu_decode(const uint8_t *jpeg, size_t len, int subseq_bits,
     // pass: unstuff
     std::vector<uint8_t> stream;
     for (size_t i = ds.ecs_begin; i < ds.ecs_end; i++) { stream.push_back(jpeg[i]); if (jpeg[i] == 0xFF && i + 1 < ds.ecs_end && jpeg[i + 1] == 0) i++; }
+    const size_t stream_bytes = stream.size();
+    stream.resize((stream_bytes + 3) / 4 * 4 + 16, 0xFF);          // word alignment + 0xFF padding, as the device buffer has
     gd::Geometry G{};
     int q = 0;
     for (int c = 0; c < g.ncomp; c++) for (int k = 0; k < (g.ncomp == 1 ? 1 : g.hs[c] * g.vs[c]); k++) { G.dc_tbl[q] = ds.td[c]; G.ac_tbl[q] = ds.ta[c]; q++; }
     G.blocks_per_mcu = q;
     G.total_blocks = g.ncomp == 1 ? (uint32_t)(g.rbw[0] * g.rbh[0]) : (uint32_t)(g.mcux * g.mcuy * q);
-    G.nbits = (uint32_t)stream.size() * 8; G.subseq_bits = (uint32_t)subseq_bits; G.nsub = (G.nbits + G.subseq_bits - 1) / G.subseq_bits;
+    G.nbits = (uint32_t)stream_bytes * 8; G.subseq_bits = (uint32_t)subseq_bits; G.nsub = (G.nbits + G.subseq_bits - 1) / G.subseq_bits;
     std::vector<gd::DecTable> tabs(8);
     for (int id = 0; id < 4; id++) for (int kind = 0; kind < 2; kind++) if (rd.dht_present(kind, id)) gd::build_dec_table(rd.dht_bits(kind, id), rd.dht_vals(kind, id), tabs[kind * 4 + id]);
     memset(out, 0, (size_t)g.total_coefs * 2);

@@ -124,6 +124,31 @@ def test_device_decode_4k_and_flat_fallback(L, O):
 
 
 @pytest.mark.gpu
+def test_megabatch_groups_mixed_inputs(L, O, golden):
+    """b200_compress_batch packs consecutive same-shaped baseline JPEGs into one launch sequence; everything else in the
+    chunk (other shapes, progressive files, periodic streams, non-images) must still come out right, in input order."""
+    from tools.synth import synth_rgb
+    L.set_entropy_mode(3)
+    same = []
+    for i in range(11):                                  # 11 same-shaped baseline files with different content / quality
+        b = io.BytesIO()
+        Image.fromarray(synth_rgb(322, 199, 200 + i), "RGB").save(b, "JPEG", quality=70 + 2 * i, subsampling="4:2:0")
+        same.append(b.getvalue())
+    b = io.BytesIO()
+    Image.new("RGB", (322, 199), (10, 200, 90)).save(b, "JPEG", quality=90, subsampling="4:2:0")     # same shape, periodic stream
+    flat = b.getvalue()
+    datas = same[:3] + [golden("in_420_prog_355x237.jpg")] + same[3:6] + [b"not an image"] + [flat] + same[6:] + [golden("in_444_base_355x237.jpg"), golden("in_gray_base_355x237.jpg")]
+    for q, ss, prog in [(80, 420, True), (60, 444, False)]:
+        res = L.compress_batch(datas, _params(L, q, ss, prog), n_threads=4)
+        for d, (out, code, msg) in zip(datas, res):
+            if d == b"not an image":
+                assert code == L.ERR_UNKNOWN_FORMAT
+            else:
+                assert code == 0, msg
+                assert out == O.jpeg_lossy(d, O.params(q, ss, prog))
+
+
+@pytest.mark.gpu
 def test_device_decode_concurrent(L, O, golden):
     datas = [golden(n) for n in BASELINE_INPUTS] * 8
     L.set_entropy_mode(3)

@@ -1,0 +1,30 @@
+"""Throughput probe: b200_compress_batch over synthetic 4K JPEGs with different host thread counts (B200_TRACE=1 for
+the per-stage wall-clock breakdown printed at shutdown)."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+
+if __name__ == "__main__":
+    threads_list = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "8,16,32").split(",")]
+    n_images = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+    datas = bench.make_inputs(8, 0)
+    L = bench.load_pkg()
+    L.lib().b200_init_device(0)
+    p = L.default_params()
+    p.jpeg_quality, p.jpeg_chroma_subsampling, p.jpeg_progressive = 80, 420, 1
+    work = [datas[i % len(datas)] for i in range(n_images)]
+    L.compress_batch(work[:48], p, 48)          # warm every slot
+    for th in threads_list:
+        c0 = os.times()
+        t0 = time.perf_counter()
+        res = L.compress_batch(work, p, th)
+        dt = time.perf_counter() - t0
+        c1 = os.times()
+        assert all(r[1] == 0 for r in res)
+        cpu = (c1.user - c0.user + c1.system - c0.system) / dt
+        print(f"threads={th:3d}: {n_images / dt:8.1f} img/s  {n_images * bench.MP_PER_IMAGE / dt:9.1f} MP/s   host CPU busy: {cpu:5.1f} cores "
+              f"(user {(c1.user - c0.user) / dt:.1f}, sys {(c1.system - c0.system) / dt:.1f})", flush=True)
+    L.lib().b200_shutdown()
