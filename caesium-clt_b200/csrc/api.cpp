@@ -95,7 +95,16 @@ std::atomic<long long> g_stage_n{0};
 const bool g_trace = getenv("B200_TRACE") != nullptr;
 struct StageTimer {
     std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
-    void lap(int i) { if (!g_trace) return; auto n = std::chrono::steady_clock::now(); g_stage_ns[i] += std::chrono::duration_cast<std::chrono::nanoseconds>(n - t).count(); t = n; if (i == 5) g_stage_n++; }
+    void lap(int i)
+    {
+        if (!g_trace) return;
+        auto n = std::chrono::steady_clock::now();
+        const long long ns = std::chrono::duration_cast<std::chrono::nanoseconds>(n - t).count();
+        g_stage_ns[i] += ns; t = n;
+        if (i == 5) g_stage_n++;
+        static const bool verbose = getenv("B200_TRACE") && atoi(getenv("B200_TRACE")) >= 2;
+        if (verbose) fprintf(stderr, "[b200 trace] stage %d: %.3f ms\n", i, ns / 1e6);
+    }
 };
 void print_trace()
 {
@@ -198,6 +207,7 @@ void jpeg_compress_group(const uint8_t *const *in, const size_t *in_len, const s
                          uint8_t **out, size_t *out_len, b200_status *status, std::vector<char> &done)
 {
     const int M = (int)idx.size();
+    StageTimer tm;
     std::vector<std::unique_ptr<JpegReader>> rd((size_t)M);
     std::vector<JpegReader::DeviceScan> ds((size_t)M);
     std::vector<int> members;                       // positions k (into idx) that join the group
@@ -234,7 +244,7 @@ void jpeg_compress_group(const uint8_t *const *in, const size_t *in_len, const s
             items[m].d_coefs = reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(s->d_in) + L.in_stride * m);
             gins[m] = &rd[k]->geom();
         }
-        StageTimer tm; tm.lap(0);
+        tm.lap(0);
         if (!slot_decode_group(s, items, err)) break;
         tm.lap(1);
         if (!slot_transform_group(s, gins.data(), gout, L, err)) break;

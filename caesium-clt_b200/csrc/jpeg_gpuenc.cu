@@ -166,6 +166,104 @@ __global__ void k_ge_emit(const Scan *__restrict__ scans, const uint32_t *__rest
     sk.finish();
 }
 
+// ---- block-major passes: one thread per block; the block is read (and its threshold masks built) once per pass and
+// serves every scan that visits it ------------------------------------------------------------------------------------
+__device__ __forceinline__ int unit_of(const Scan &s, const BlockComp &bc, int row, int col)
+{
+    if (s.ns == 1) return (row < bc.rbh && col < bc.rbw) ? row * bc.rbw + col : -1;
+    const int m = (row / bc.vs) * bc.mcux + col / bc.hs, q = bc.q_base + (row % bc.vs) * bc.hs + (col % bc.hs);
+    return m * bc.blocks_per_mcu + q;
+}
+__device__ __forceinline__ BlockRef ref_of(const Scan &s, int u, const int16_t *blk)
+{
+    if (s.mode == MODE_SEQ || s.mode == MODE_DC_FIRST || s.ns > 1) return locate(s, u);   // needs the DC predecessor / the slot
+    BlockRef r; r.blk = blk; r.prev = nullptr; r.slot = 0; return r;
+}
+
+__global__ void k_geb_classify(const BlockComp *__restrict__ comps, const Scan *__restrict__ scans, uint32_t *__restrict__ meta, int *__restrict__ evkey, uint32_t *__restrict__ tail)
+{
+    const BlockComp bc = comps[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= bc.bw * bc.bh) return;
+    const int row = i / bc.bw, col = i - row * bc.bw;
+    const int16_t *blk = bc.coef + bc.comp_off + ((long long)row * bc.bw + col) * 64;
+    const Masks3 M = make_masks3(blk);
+    for (int j = 0; j < bc.nscan; j++) {
+        const Scan &s = scans[bc.scan_idx[j]];
+        const int u = unit_of(s, bc, row, col);
+        if (u < 0) continue;
+        const uint32_t m = classify_m(s, M);
+        const long long g = s.unit_base + u;
+        meta[g] = m; evkey[g] = meta_event(m) ? (int)g : -1; tail[g] = (uint32_t)meta_tail(m);
+    }
+}
+
+__global__ void k_geb_hist(const BlockComp *__restrict__ comps, const Scan *__restrict__ scans, const uint32_t *__restrict__ gcount, uint32_t *__restrict__ hist)
+{
+    __shared__ uint32_t h[4][1024];
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) (&h[0][0])[i] = 0;
+    __syncthreads();
+    const BlockComp bc = comps[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < bc.bw * bc.bh) {
+        const int row = i / bc.bw, col = i - row * bc.bw;
+        const int16_t *blk = bc.coef + bc.comp_off + ((long long)row * bc.bw + col) * 64;
+        const Masks3 M = make_masks3(blk);
+        for (int j = 0; j < bc.nscan; j++) {
+            const Scan &s = scans[bc.scan_idx[j]];
+            const int u = unit_of(s, bc, row, col);
+            if (u < 0) continue;
+            uint32_t *hj = j < 4 ? h[j] : hist + (size_t)s.tab_base * 256;
+            auto add = [&](int idx) { atomicAdd(&hj[idx], 1u); };
+            HistSink<decltype(add)> sk(add);
+            gen_block_m(s, ref_of(s, u, blk), M, gcount[s.unit_base + u], sk);
+        }
+    }
+    __syncthreads();
+    for (int j = 0; j < bc.nscan && j < 4; j++) {
+        uint32_t *g = hist + (size_t)scans[bc.scan_idx[j]].tab_base * 256;
+        for (int k = threadIdx.x; k < 1024; k += blockDim.x) if (h[j][k]) atomicAdd(&g[k], h[j][k]);
+    }
+}
+
+__global__ void k_geb_len(const BlockComp *__restrict__ comps, const Scan *__restrict__ scans, const uint32_t *__restrict__ gcount, const Table *__restrict__ tabs, uint32_t *__restrict__ bitlen)
+{
+    const BlockComp bc = comps[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= bc.bw * bc.bh) return;
+    const int row = i / bc.bw, col = i - row * bc.bw;
+    const int16_t *blk = bc.coef + bc.comp_off + ((long long)row * bc.bw + col) * 64;
+    const Masks3 M = make_masks3(blk);
+    for (int j = 0; j < bc.nscan; j++) {
+        const Scan &s = scans[bc.scan_idx[j]];
+        const int u = unit_of(s, bc, row, col);
+        if (u < 0) continue;
+        LenSink sk; sk.tabs = tabs + s.tab_base;
+        gen_block_m(s, ref_of(s, u, blk), M, gcount[s.unit_base + u], sk);
+        bitlen[s.unit_base + u] = (uint32_t)sk.bits;
+    }
+}
+
+__global__ void k_geb_emit(const BlockComp *__restrict__ comps, const Scan *__restrict__ scans, const uint32_t *__restrict__ gcount, const Table *__restrict__ tabs,
+                           const uint32_t *__restrict__ bitoff, uint32_t *__restrict__ words)
+{
+    const BlockComp bc = comps[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= bc.bw * bc.bh) return;
+    const int row = i / bc.bw, col = i - row * bc.bw;
+    const int16_t *blk = bc.coef + bc.comp_off + ((long long)row * bc.bw + col) * 64;
+    const Masks3 M = make_masks3(blk);
+    auto orw = [&](long long w, uint32_t v) { if (v) atomicOr(&words[w], v); };
+    for (int j = 0; j < bc.nscan; j++) {
+        const Scan &s = scans[bc.scan_idx[j]];
+        const int u = unit_of(s, bc, row, col);
+        if (u < 0) continue;
+        EmitSink<decltype(orw)> sk(tabs + s.tab_base, orw, s.word_base, (unsigned long long)(bitoff[s.unit_base + u] - bitoff[s.unit_base]));
+        gen_block_m(s, ref_of(s, u, blk), M, gcount[s.unit_base + u], sk);
+        sk.finish();
+    }
+}
+
 // byte i of a scan's unstuffed stream (big-endian within words), with flush_bits' padding ones in the last byte
 __device__ __forceinline__ uint32_t scan_byte(const uint32_t *__restrict__ w, uint32_t i, uint32_t nbytes, uint32_t total_bits)
 {
@@ -253,7 +351,7 @@ template <typename T> static bool grow(T *&p, size_t &cap, size_t need, bool hos
 
 GpuEncoder::~GpuEncoder()
 {
-    cudaFree(d_scans); cudaFree(d_meta); cudaFree(d_evkey); cudaFree(d_prev); cudaFree(d_tail); cudaFree(d_tsum); cudaFree(d_gcount);
+    cudaFree(d_scans); cudaFree(d_comps); cudaFree(d_meta); cudaFree(d_evkey); cudaFree(d_prev); cudaFree(d_tail); cudaFree(d_tsum); cudaFree(d_gcount);
     cudaFree(d_bitlen); cudaFree(d_bitoff); cudaFree(d_hist); cudaFree(d_tabs); cudaFree(d_dht); cudaFree(d_total); cudaFree(d_so);
     cudaFree(d_words); cudaFree(d_ffcount); cudaFree(d_ffoff); cudaFree(d_outoff); cudaFree(d_outlen); cudaFree(d_out); cudaFree(d_temp);
     cudaFreeHost(h_small); cudaFreeHost(h_out);
@@ -272,6 +370,9 @@ bool GpuEncoder::encode(const JpegGeom &g, bool progressive, int16_t *const *d_c
     // ---- buffers
     size_t c;
     c = cap_scans; if (!grow(d_scans, c, NS * sizeof(Scan), false, err)) return false; cap_scans = c;
+    const int NC = (int)plan.comps.size();
+    c = cap_comps; if (!grow(d_comps, c, NC * sizeof(BlockComp), false, err)) return false; cap_comps = c;
+    for (auto &sc_ : plan.scans) if (!masks_cover(sc_.mode, sc_.Al)) { err = "scan script outside the device encoder's mask range"; overflow = true; return false; }
     c = cap_u[0]; if (!grow(d_meta, c, U * 4, false, err)) return false; cap_u[0] = c;
     c = cap_u[1]; if (!grow(d_evkey, c, U * 4, false, err)) return false; cap_u[1] = c;
     c = cap_u[2]; if (!grow(d_prev, c, U * 4, false, err)) return false; cap_u[2] = c;
@@ -288,7 +389,8 @@ bool GpuEncoder::encode(const JpegGeom &g, bool progressive, int16_t *const *d_c
     c = cap_oo; if (!grow(d_outoff, c, (size_t)NS * 4, false, err)) return false; cap_oo = c;
     c = cap_ol; if (!grow(d_outlen, c, (size_t)NS * 4, false, err)) return false; cap_ol = c;
     c = cap_words; if (!grow(d_words, c, (size_t)plan.total_words * 4, false, err)) return false; cap_words = c;
-    const size_t small_bytes = align_up((size_t)NS * sizeof(Scan), 256) + align_up((size_t)NS * sizeof(ScanOut), 256) + align_up((size_t)NS * 4, 256) * 2 + align_up((size_t)NS * 4 * sizeof(DhtOut), 256);
+    const size_t small_bytes = align_up((size_t)NS * sizeof(Scan), 256) + align_up((size_t)NS * sizeof(ScanOut), 256) + align_up((size_t)NS * 4, 256) * 2 + align_up((size_t)NS * 4 * sizeof(DhtOut), 256) +
+                               align_up((size_t)NC * sizeof(BlockComp), 256);
     c = cap_small; if (!grow(h_small, c, small_bytes, true, err)) return false; cap_small = c;
     size_t tb1 = 0, tb2 = 0;
     cub::DeviceScan::ExclusiveScan((void *)nullptr, tb1, d_evkey, d_prev, cub::Max(), -1, (int)U, st);
@@ -299,9 +401,13 @@ bool GpuEncoder::encode(const JpegGeom &g, bool progressive, int16_t *const *d_c
     ScanOut *h_so = reinterpret_cast<ScanOut *>(hp); hp += align_up((size_t)NS * sizeof(ScanOut), 256);
     uint32_t *h_total = reinterpret_cast<uint32_t *>(hp); hp += align_up((size_t)NS * 4, 256);
     uint32_t *h_outlen = reinterpret_cast<uint32_t *>(hp); hp += align_up((size_t)NS * 4, 256);
-    DhtOut *h_dht = reinterpret_cast<DhtOut *>(hp);
+    DhtOut *h_dht = reinterpret_cast<DhtOut *>(hp); hp += align_up((size_t)NS * 4 * sizeof(DhtOut), 256);
+    BlockComp *h_comps = reinterpret_cast<BlockComp *>(hp);
     memcpy(h_scans, plan.scans.data(), NS * sizeof(Scan));
+    memcpy(h_comps, plan.comps.data(), NC * sizeof(BlockComp));
     CU(cudaMemcpyAsync(d_scans, h_scans, NS * sizeof(Scan), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_comps, h_comps, NC * sizeof(BlockComp), cudaMemcpyHostToDevice, st));
+    const dim3 gb(cdiv(plan.max_comp_blocks, 128), NC);
     if (fill_dummy) {
         for (int im = 0; im < nimages; im++) for (int cc = 0; cc < g.ncomp; cc++) {
             if (g.rbw[cc] == g.bw[cc] && g.rbh[cc] == g.bh[cc]) continue;
@@ -309,7 +415,7 @@ bool GpuEncoder::encode(const JpegGeom &g, bool progressive, int16_t *const *d_c
         }
     }
     const dim3 gu(cdiv(max_units, 128), NS), gu1(cdiv(max_units + 1, 128), NS);
-    k_ge_classify<<<gu, 128, 0, st>>>(d_scans, d_meta, d_evkey, d_tail);
+    k_geb_classify<<<gb, 128, 0, st>>>(d_comps, d_scans, d_meta, d_evkey, d_tail);
     size_t tb = cap_temp;
     cub::DeviceScan::ExclusiveScan(d_temp, tb, d_evkey, d_prev, cub::Max(), -1, (int)U, st);
     tb = cap_temp;
@@ -317,9 +423,9 @@ bool GpuEncoder::encode(const JpegGeom &g, bool progressive, int16_t *const *d_c
     CU(cudaMemsetAsync(d_gcount, 0, U * 4, st));
     k_ge_groups<<<gu1, 128, 0, st>>>(d_scans, d_meta, d_evkey, d_prev, d_tsum, d_gcount);
     CU(cudaMemsetAsync(d_hist, 0, (size_t)NS * 4 * 256 * 4, st));
-    k_ge_hist<<<gu, 128, 0, st>>>(d_scans, d_gcount, d_hist);
+    k_geb_hist<<<gb, 128, 0, st>>>(d_comps, d_scans, d_gcount, d_hist);
     k_ge_tables<<<NS * 4, 32, 0, st>>>(d_hist, d_tabs, d_dht);
-    k_ge_len<<<gu, 128, 0, st>>>(d_scans, d_gcount, d_tabs, d_bitlen);
+    k_geb_len<<<gb, 128, 0, st>>>(d_comps, d_scans, d_gcount, d_tabs, d_bitlen);
     tb = cap_temp;
     cub::DeviceScan::ExclusiveSum(d_temp, tb, d_bitlen, d_bitoff, (int)U, st);
     k_ge_totals<<<cdiv(NS, 128), 128, 0, st>>>(d_scans, NS, d_bitlen, d_bitoff, d_total);
@@ -347,7 +453,7 @@ bool GpuEncoder::encode(const JpegGeom &g, bool progressive, int16_t *const *d_c
     c = cap_temp; if (!grow(d_temp, c, tb3 + 256, false, err)) return false; cap_temp = c;
     CU(cudaMemcpyAsync(d_so, h_so, (size_t)NS * sizeof(ScanOut), cudaMemcpyHostToDevice, st));
     k_ge_zero<<<dim3(std::max(1, std::min(cdiv(max_words, 256), 256)), NS), 256, 0, st>>>(d_scans, d_so, d_words);
-    k_ge_emit<<<gu, 128, 0, st>>>(d_scans, d_gcount, d_tabs, d_bitoff, d_words);
+    k_geb_emit<<<gb, 128, 0, st>>>(d_comps, d_scans, d_gcount, d_tabs, d_bitoff, d_words);
     if (groups) {
         const dim3 gg(cdiv(max_groups, 128), NS);
         k_ge_ffcount<<<gg, 128, 0, st>>>(d_scans, d_so, d_words, d_ffcount);

@@ -29,6 +29,7 @@ public:
 private:
     int nimg = 0;
     ge::Scan *d_scans = nullptr; size_t cap_scans = 0;
+    BlockComp *d_comps = nullptr; size_t cap_comps = 0;
     uint32_t *d_meta = nullptr, *d_tail = nullptr, *d_tsum = nullptr, *d_gcount = nullptr, *d_bitlen = nullptr, *d_bitoff = nullptr;
     int *d_evkey = nullptr, *d_prev = nullptr;
     size_t cap_u[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -131,12 +131,17 @@ GE_HD int popc64(unsigned long long m)
 }
 GE_HD unsigned long long band_mask(int Ss, int Se) { return (Se >= 63 ? ~0ull : ((1ull << (Se + 1)) - 1ull)) & ~((1ull << Ss) - 1ull); }
 
-GE_HD void make_masks(const int16_t *__restrict__ blk, int T1, int T2, unsigned long long &m1, unsigned long long &m2)
+// Masks for the thresholds 1, 2 and 4: enough for first scans with Al <= 2 and refinement scans with Al <= 1 (the scripts
+// in jpeg_scan_script use Al <= 1 / Al = 0).  One block read serves every scan that visits the block.
+struct Masks3 { unsigned long long m[3]; };
+GE_HD bool masks_cover(int mode, int Al) { return mode == MODE_AC_REFINE ? Al <= 1 : Al <= 2; }
+
+GE_HD Masks3 make_masks3(const int16_t *__restrict__ blk)
 {
+    Masks3 M;
 #if defined(__CUDA_ARCH__)
     const uint4 *v = reinterpret_cast<const uint4 *>(blk);          // 8 x 128-bit loads, two coefficients per 32-bit word
-    const unsigned t1 = (unsigned)T1 * 0x00010001u, t2 = (unsigned)T2 * 0x00010001u;
-    unsigned lo1 = 0, hi1 = 0, lo2 = 0, hi2 = 0;
+    unsigned lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         const uint4 q = v[j];
@@ -144,27 +149,30 @@ GE_HD void make_masks(const int16_t *__restrict__ blk, int T1, int T2, unsigned 
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const unsigned a = __vabsss2(w[i]);
-            const unsigned c1 = __vcmpgeu2(a, t1), c2 = __vcmpgeu2(a, t2);
-            const unsigned b1 = (c1 & 1u) | ((c1 >> 15) & 2u), b2 = (c2 & 1u) | ((c2 >> 15) & 2u);
             const int sh = 2 * ((4 * j + i) & 15);
-            if (j < 4) { lo1 |= b1 << sh; lo2 |= b2 << sh; } else { hi1 |= b1 << sh; hi2 |= b2 << sh; }
+#pragma unroll
+            for (int t = 0; t < 3; t++) {
+                const unsigned c = __vcmpgeu2(a, 0x00010001u << t);
+                const unsigned b = (c & 1u) | ((c >> 15) & 2u);
+                if (j < 4) lo[t] |= b << sh; else hi[t] |= b << sh;
+            }
         }
     }
-    m1 = ((unsigned long long)hi1 << 32) | lo1; m2 = ((unsigned long long)hi2 << 32) | lo2;
+#pragma unroll
+    for (int t = 0; t < 3; t++) M.m[t] = ((unsigned long long)hi[t] << 32) | lo[t];
 #else
-    m1 = m2 = 0;
-    for (int k = 0; k < 64; k++) { int a = blk[k]; if (a < 0) a = -a; if (a >= T1) m1 |= 1ull << k; if (a >= T2) m2 |= 1ull << k; }
+    M.m[0] = M.m[1] = M.m[2] = 0;
+    for (int k = 0; k < 64; k++) { int a = blk[k]; if (a < 0) a = -a; for (int t = 0; t < 3; t++) if (a >= (1 << t)) M.m[t] |= 1ull << k; }
 #endif
+    return M;
 }
 
 // ---- classification (pass 0) ------------------------------------------------------------------------------------
-GE_HD uint32_t classify(const Scan &s, const int16_t *blk)
+GE_HD uint32_t classify_m(const Scan &s, const Masks3 &M)
 {
     if (s.mode == MODE_SEQ || s.mode == MODE_DC_FIRST) return meta_pack(true, false, 0);
-    unsigned long long mA, mB;
-    make_masks(blk, 1 << s.Al, 2 << s.Al, mA, mB);
     const unsigned long long band = band_mask(s.Ss, s.Se);
-    mA &= band; mB &= band;
+    const unsigned long long mA = M.m[s.Al] & band, mB = (s.mode == MODE_AC_REFINE ? M.m[s.Al + 1] : 0ull) & band;
     if (s.mode == MODE_AC_FIRST) { const int last = msb64(mA); return meta_pack(last >= 0, last < s.Se, 0); }
     // AC refinement: inline symbols exist iff some coefficient becomes non-zero in this scan (|c| >> Al == 1).  After
     // the last such coefficient every remaining position is either zero (r++) or already non-zero (a pending correction
@@ -175,6 +183,11 @@ GE_HD uint32_t classify(const Scan &s, const int16_t *blk)
     else if (last_new >= 63) tail = 0;
     else tail = popc64(mB & ~((2ull << last_new) - 1ull));
     return meta_pack(last_new >= 0, last_new < s.Se, tail);
+}
+GE_HD uint32_t classify(const Scan &s, const int16_t *blk)
+{
+    if (s.mode == MODE_SEQ || s.mode == MODE_DC_FIRST) return meta_pack(true, false, 0);
+    return classify_m(s, make_masks3(blk));
 }
 
 // ---- symbol generation: one template, three sinks (histogram, length, emit) -----------------------------------------
@@ -197,17 +210,15 @@ GE_HD void gen_eob_token(unsigned count, int tbl, Sink &sk)
 
 // group_count: >0 iff this block opens an EOB group (then E_j carries that count)
 template <class Sink>
-GE_HD void gen_block(const Scan &s, const BlockRef &b, unsigned group_count, Sink &sk)
+GE_HD void gen_block_m(const Scan &s, const BlockRef &b, const Masks3 &M, unsigned group_count, Sink &sk)
 {
     const int16_t *blk = b.blk;
     const int tbl = s.tbl[b.slot];
     if (s.mode == MODE_DC_FIRST) { gen_dc(blk[0] >> s.Al, b.prev ? (b.prev[0] >> s.Al) : 0, tbl, sk); return; }
-    unsigned long long mA, mB;                  // |c| >= 2^Al, |c| >= 2^(Al+1)
     if (s.mode == MODE_SEQ) {
-        make_masks(blk, 1, 2, mA, mB);
         gen_dc(blk[0], b.prev ? b.prev[0] : 0, tbl, sk);
         int prevk = 0;
-        for (unsigned long long m = mA & ~1ull; m; m &= m - 1) {
+        for (unsigned long long m = M.m[0] & ~1ull; m; m &= m - 1) {
             const int k = ctz64(m);
             int r = k - prevk - 1; prevk = k;
             while (r > 15) { sk.sym(1, tbl, 0xF0, 0, 0); r -= 16; }
@@ -218,9 +229,9 @@ GE_HD void gen_block(const Scan &s, const BlockRef &b, unsigned group_count, Sin
         if (prevk != 63) sk.sym(1, tbl, 0, 0, 0);
         return;
     }
-    make_masks(blk, 1 << s.Al, 2 << s.Al, mA, mB);
     const unsigned long long band = band_mask(s.Ss, s.Se);
-    mA &= band; mB &= band;
+    const unsigned long long mA = M.m[s.Al] & band;                                              // |c| >= 2^Al
+    const unsigned long long mB = (s.mode == MODE_AC_REFINE ? M.m[s.Al + 1] : 0ull) & band;     // |c| >= 2^(Al+1)
     if (s.mode == MODE_AC_FIRST) {
         int prevk = s.Ss - 1;
         for (unsigned long long m = mA; m; m &= m - 1) {
@@ -260,6 +271,12 @@ GE_HD void gen_block(const Scan &s, const BlockRef &b, unsigned group_count, Sin
     }
     if (group_count) gen_eob_token(group_count, tbl, sk);
     if (npend) sk.raw64(npend, pend64);         // T_j: trailing correction bits, after the group's EOBn symbol
+}
+template <class Sink>
+GE_HD void gen_block(const Scan &s, const BlockRef &b, unsigned group_count, Sink &sk)
+{
+    if (s.mode == MODE_DC_FIRST) { Masks3 none; none.m[0] = none.m[1] = none.m[2] = 0; gen_block_m(s, b, none, group_count, sk); return; }
+    gen_block_m(s, b, make_masks3(b.blk), group_count, sk);
 }
 
 // ---- sinks --------------------------------------------------------------------------------------------------------

@@ -1,13 +1,26 @@
 // jpeg_gpuenc_plan.h -- host-side planning for the block-parallel entropy encoder: turns a geometry + scan script into
 // the ge::Scan descriptors the kernels (or the CPU emulation in tests/emul/) iterate.  Plain C++, no CUDA.
 #pragma once
+#include <algorithm>
 #include <vector>
 #include "jpeg_gpuenc_core.h"
 #include "jpeg_host.h"
 
 namespace b200 {
 
+// Block-major view used by the encoder passes: one descriptor per (image, component); a thread owns one block, reads it
+// once, and serves every scan that visits the block (e.g. luma: DC scan + two AC bands + the refinement scan).
+struct BlockComp {
+    const int16_t *coef;                // image base
+    long long comp_off;
+    int bw, bh, rbw, rbh, hs, vs;
+    int q_base, blocks_per_mcu, mcux;   // position of the component's first block inside an MCU (interleaved scans)
+    int nscan, scan_idx[6];             // indices into GpuEncPlan::scans
+};
+
 struct GpuEncPlan {
+    std::vector<BlockComp> comps;       // image-major
+    int max_comp_blocks = 0;
     std::vector<ge::Scan> scans;        // image-major: scans of image 0, then image 1, ...
     std::vector<ScanDef> defs;          // one script (shared by all images of the batch)
     int scans_per_image = 0;
@@ -50,6 +63,22 @@ inline void gpuenc_plan(const JpegGeom &g, bool progressive, const int16_t *cons
         if (im == 0) { p.units_per_image = unit; p.words_per_image = word; }
     }
     p.total_units = unit; p.total_words = word;
+    p.comps.clear(); p.max_comp_blocks = 0;
+    for (int im = 0; im < nimages; im++) {
+        int qb = 0;
+        for (int c = 0; c < g.ncomp; c++) {
+            BlockComp bc{};
+            bc.coef = coef_base[im]; bc.comp_off = g.comp_offset[c];
+            bc.bw = g.bw[c]; bc.bh = g.bh[c]; bc.rbw = g.rbw[c]; bc.rbh = g.rbh[c]; bc.hs = g.hs[c]; bc.vs = g.vs[c];
+            bc.q_base = qb; bc.mcux = g.mcux;
+            bc.blocks_per_mcu = 0; for (int cc = 0; cc < g.ncomp; cc++) bc.blocks_per_mcu += g.hs[cc] * g.vs[cc];
+            qb += g.hs[c] * g.vs[c];
+            bc.nscan = 0;
+            for (int si = 0; si < ns; si++) for (int i = 0; i < sc[si].ns; i++) if (sc[si].ci[i] == c && bc.nscan < 6) bc.scan_idx[bc.nscan++] = im * ns + si;
+            p.comps.push_back(bc);
+            p.max_comp_blocks = std::max(p.max_comp_blocks, bc.bw * bc.bh);
+        }
+    }
 }
 
 } // namespace b200
