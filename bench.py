@@ -283,10 +283,16 @@ def main():
     e2e_val = world * Be * MP_PER_IMAGE * args.steps / dt
     clk = clocks.stop()
     coef_bytes = int(lay.total_coefs) * 2
-    e2e = {"value": round(e2e_val, 2), "unit": "MP/s", "h2d_bytes_per_step": Be * coef_bytes, "d2h_bytes_per_step": Be * int(olay.total_coefs) * 2,
-           "images_per_sec": round(e2e_val / MP_PER_IMAGE, 2), "host_threads": threads, "in_bytes_per_step": sum(len(w) for w in work), "out_bytes_per_step": out_bytes,
-           "entropy_encoder": os.environ.get("B200_ENTROPY", "gpu"),
-           "note": "JPEG bytes -> JPEG bytes via b200_compress_batch, all inside the timed region: host Huffman decode on the caller threads, pinned H2D of coefficients, transform kernels, entropy ENCODE (device by default: only the stuffed scans cross PCIe back; B200_ENTROPY=host moves it to the host and D2H carries the coefficients)"}
+    ent = os.environ.get("B200_ENTROPY", "gpu")
+    in_bytes = sum(len(w) for w in work)
+    # what actually crosses PCIe per step: with the device entropy decoder the entropy-coded scan goes up (not the
+    # coefficients), with the device encoder the stuffed scans come back (not the coefficients)
+    h2d = in_bytes if ent in ("gpu", "gpudec") else Be * coef_bytes
+    d2h = out_bytes if ent in ("gpu", "gpuenc") else Be * int(olay.total_coefs) * 2
+    e2e = {"value": round(e2e_val, 2), "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "images_per_sec": round(e2e_val / MP_PER_IMAGE, 2), "host_threads": threads, "in_bytes_per_step": in_bytes, "out_bytes_per_step": out_bytes,
+           "entropy": ent, "megabatch": int(os.environ.get("B200_MEGABATCH", "8")),
+           "note": "JPEG bytes in host memory -> JPEG bytes in host memory via b200_compress_batch (the batch form of start_compression's par_iter), all inside the timed region: marker parsing, pinned H2D of the entropy-coded scans, device Huffman decode, transform kernels, device Huffman encode (statistics, optimal tables, bit packing, stuffing), D2H of the scans, file assembly. Output bytes are identical to the oracle's. B200_ENTROPY=host keeps both entropy stages on host threads."}
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:

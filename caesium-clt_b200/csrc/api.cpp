@@ -256,10 +256,9 @@ void jpeg_compress_group(const uint8_t *const *in, const size_t *in_len, const s
         for (int m = 0; m < Kg; m++) {
             const int k = members[m], i = idx[k];
             if (items[m].result != GpuDecoder::OK) continue;          // not converged: the per-image path decodes it on the host
-            std::vector<uint8_t> v;
             out[i] = nullptr; out_len[i] = 0;
-            if (!jpeg_assemble(gout, wo, &rd[k]->meta(), s->enc->results.data() + (size_t)m * spi, spi, v, err)) status[i] = make_status(B200_ERR_INVALID_ARGUMENT, err);
-            else status[i] = give(v, &out[i], &out_len[i]);
+            if (!jpeg_assemble_malloc(gout, wo, &rd[k]->meta(), s->enc->results.data() + (size_t)m * spi, spi, &out[i], &out_len[i], err)) status[i] = make_status(B200_ERR_INVALID_ARGUMENT, err);
+            else status[i] = ok_status();
             done[k] = 1;
         }
         tm.lap(5);

@@ -83,32 +83,30 @@ GE_HD DecState decode_subsequence(const uint8_t *__restrict__ stream, const Geom
 {
     const uint32_t end = (i + 1) * g.subseq_bits < g.nbits ? (i + 1) * g.subseq_bits : g.nbits;
     uint32_t p = st.p; int k = st.k, b = st.b;
+    // 64-bit bit buffer in registers, left aligned at position p, refilled one aligned word at a time: the stream load is
+    // off the critical path except once every 32 consumed bits (a symbol consumes at most 16 + 15 bits, so >= 32 buffered
+    // bits always suffice)
+    uint32_t nextw = (p >> 5) + 2;
+    unsigned long long buf = (((unsigned long long)load_be32(stream, p >> 5) << 32) | load_be32(stream, (p >> 5) + 1)) << (p & 31);
+    int have = 64 - (int)(p & 31);
+    uint32_t pbuf = p;                              // position the buffer is aligned to
     while (p < end) {
-        const uint32_t bits = peek32(stream, g.nbits, p);
+        { const int used = (int)(p - pbuf); if (used) { buf <<= used; have -= used; pbuf = p; } }
+        if (have < 32) { buf |= (unsigned long long)load_be32(stream, nextw++) << (32 - have); have += 32; }
+        const uint32_t bits = (uint32_t)(buf >> 32);
+        // One uniform body for DC and AC symbols (a DC symbol is "run 0, category s at index 0"), selects instead of
+        // branches: the lanes of a warp sit at unrelated points of their blocks, so divergent paths would serialise.
+        const bool dc = k == 0;
         int len;
-        if (k == 0) {
-            const int s = decode_symbol(tabs[g.dc_tbl[b]], bits, &len) & 15;            // DC category 0..11 (masked: garbage-safe)
-            int v = 0;
-            if (s) { const uint32_t ext = (bits << len) >> (32 - s); v = (int)ext < (1 << (s - 1)) ? (int)ext - (1 << s) + 1 : (int)ext; }
-            sk.coef(0, v);
-            p += (uint32_t)(len + s);
-            k = 1;
-        } else {
-            const int rs = decode_symbol(tabs[4 + g.ac_tbl[b]], bits, &len);
-            const int r = rs >> 4, s = rs & 15;
-            if (s == 0) {
-                p += (uint32_t)len;
-                if (r == 15) k += 16; else k = 64;
-            } else {
-                k += r;
-                if (k > 63) k = 63;                                                // corrupt / unsynchronised run: clamp
-                const uint32_t ext = (bits << len) >> (32 - s);
-                const int v = (int)ext < (1 << (s - 1)) ? (int)ext - (1 << s) + 1 : (int)ext;
-                sk.coef(k, v);
-                p += (uint32_t)(len + s);
-                k++;
-            }
-        }
+        const int sym = decode_symbol(tabs[dc ? g.dc_tbl[b] : 4 + g.ac_tbl[b]], bits, &len);
+        const int r = dc ? 0 : (sym >> 4), s = sym & 15;
+        const uint32_t ext = s ? (bits << len) >> (32 - s) : 0u;
+        const int v = s ? ((int)ext < (1 << (s - 1)) ? (int)ext - (1 << s) + 1 : (int)ext) : 0;
+        const bool eob_or_zrl = !dc && s == 0;                                     // AC symbol without a value: ZRL or EOB
+        int kw = k + r; if (kw > 63) kw = 63;                                       // corrupt / unsynchronised run: clamp
+        if (!eob_or_zrl) sk.coef(kw, v);
+        k = eob_or_zrl ? (r == 15 ? k + 16 : 64) : kw + 1;
+        p += (uint32_t)(len + s);
         if (k >= 64) { k = 0; b++; if (b == g.blocks_per_mcu) b = 0; sk.block_done(); }
     }
     DecState o; o.p = p; o.k = (uint16_t)k; o.b = (uint16_t)b;

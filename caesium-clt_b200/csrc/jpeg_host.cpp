@@ -411,14 +411,30 @@ bool JpegReader::device_decodable(DeviceScan &ds)
     // the segment ends at the first marker that is not a stuffed zero; anything but EOI right there disqualifies the file
     size_t q = ds.ecs_begin;
     ds.stuffed = 0;
-    for (;;) {
-        const uint8_t *f = (const uint8_t *)memchr(d_ + q, 0xFF, n_ - q);
-        if (!f) return false;
-        q = (size_t)(f - d_);
-        if (q + 1 >= n_) return false;
-        if (d_[q + 1] == 0x00) { ds.stuffed++; q += 2; continue; }
-        if (d_[q + 1] == 0xFF) return false;               // fill bytes: rare, host path
-        break;
+    {   // 16 bytes at a time: find 0xFF bytes, count the stuffed zeros behind them, stop at the first real marker
+        const __m128i ff = _mm_set1_epi8((char)0xFF);
+        bool found = false;
+        while (!found) {
+            if (q + 17 <= n_) {
+                unsigned m = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i *>(d_ + q)), ff));
+                if (!m) { q += 16; continue; }
+                size_t adv = 16;
+                while (m) {
+                    const int b = __builtin_ctz(m); m &= m - 1;
+                    const uint8_t nx = d_[q + b + 1];
+                    if (nx == 0x00) { ds.stuffed++; if (b == 15) adv = 17; continue; }
+                    if (nx == 0xFF) return false;           // fill bytes: rare, host path
+                    q += (size_t)b; found = true; break;
+                }
+                if (!found) q += adv;
+            } else {
+                if (q + 1 >= n_) return false;
+                if (d_[q] != 0xFF) { q++; continue; }
+                if (d_[q + 1] == 0x00) { ds.stuffed++; q += 2; continue; }
+                if (d_[q + 1] == 0xFF) return false;
+                found = true;
+            }
+        }
     }
     if (d_[q + 1] != 0xD9) return false;                      // RSTn, DNL or another scan: leave it to the host decoder
     ds.ecs_end = q;
@@ -788,6 +804,36 @@ bool jpeg_write(const JpegGeom &g, const int16_t *coefs, const JpegWriteOptions 
         emit_tokens(out, tb, tabs);
     }
     w.u16(0xFFD9);
+    return true;
+}
+
+bool jpeg_assemble_malloc(const JpegGeom &g, const JpegWriteOptions &opt, const JpegMeta *meta, const EncodedScan *scans, int nscans,
+                          uint8_t **out, size_t *out_len, std::string &err)
+{   // same bytes as jpeg_assemble, written once into an exactly-sized malloc'd buffer (the C-ABI's ownership convention)
+    if (g.ncomp != 1 && g.ncomp != 3) { err = "unsupported component count"; return false; }
+    std::vector<uint8_t> head; head.reserve(4096 + (meta ? meta->app_markers.size() + meta->icc_markers.size() : 0));
+    { ByteSink w(head); write_file_header(w, g, opt, meta); }
+    std::vector<std::vector<uint8_t>> pre((size_t)nscans);
+    size_t total = head.size() + 2;
+    for (int si = 0; si < nscans; si++) {
+        const EncodedScan &e = scans[si];
+        pre[si].reserve(1400);
+        ByteSink w(pre[si]);
+        for (int t = 0; t < 2; t++) for (int kind = 0; kind < 2; kind++) if (e.has_tab[kind][t]) {
+            w.u16(0xFFC4); w.u16(2 + 1 + 16 + e.nvals[kind][t]); w.u8((kind << 4) | t);
+            for (int l = 1; l <= 16; l++) w.u8(e.bits[kind][t][l]);
+            w.raw(e.vals[kind][t], e.nvals[kind][t]);
+        }
+        write_sos(w, g, opt.progressive, e.def);
+        total += pre[si].size() + e.len;
+    }
+    uint8_t *p = (uint8_t *)malloc(total);
+    if (!p) { err = "out of memory"; return false; }
+    uint8_t *q = p;
+    memcpy(q, head.data(), head.size()); q += head.size();
+    for (int si = 0; si < nscans; si++) { memcpy(q, pre[si].data(), pre[si].size()); q += pre[si].size(); memcpy(q, scans[si].data, scans[si].len); q += scans[si].len; }
+    *q++ = 0xFF; *q++ = 0xD9;
+    *out = p; *out_len = total;
     return true;
 }
 

@@ -106,6 +106,9 @@ struct EncodedScan {
 bool jpeg_assemble(const JpegGeom &g, const JpegWriteOptions &opt, const JpegMeta *meta, const EncodedScan *scans, int nscans,
                    std::vector<uint8_t> &out, std::string &err);
 
+bool jpeg_assemble_malloc(const JpegGeom &g, const JpegWriteOptions &opt, const JpegMeta *meta, const EncodedScan *scans, int nscans,
+                          uint8_t **out, size_t *out_len, std::string &err);
+
 // mozjpeg base table idx 3 scaled by jpeg_set_quality(q, force_baseline = FALSE); natural order
 void jpeg_quant_table(int quality, int which, uint16_t out_natural[64]);
 extern const uint8_t kZigzag[64];   // zigzag index -> natural position

@@ -16,7 +16,8 @@ if __name__ == "__main__":
     p = L.default_params()
     p.jpeg_quality, p.jpeg_chroma_subsampling, p.jpeg_progressive = 80, 420, 1
     work = [datas[i % len(datas)] for i in range(n_images)]
-    L.compress_batch(work[:48], p, 48)          # warm every slot
+    L.compress_batch(work[:48], p, 48)          # warm the per-image slots
+    L.compress_batch((work * 2)[:256], p, 16)   # and every megabatch worker's slot (buffers are allocated on first use)
     for th in threads_list:
         c0 = os.times()
         t0 = time.perf_counter()
