@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 # the library drives one CUDA stream per in-flight image; give them separate hardware queues (must precede CUDA init,
 # and torch may create the context before the library does)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
 
 W4K, H4K = 3840, 2160
 MP_PER_IMAGE = W4K * H4K / 1e6

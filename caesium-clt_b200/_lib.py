@@ -65,7 +65,8 @@ _SYMBOLS = [
     "b200_sniff_format", "b200_jpeg_decode_coefficients", "b200_jpeg_output_layout", "b200_jpeg_requantize",
     "b200_jpeg_encode_coefficients", "b200_jpeg_decode_planes", "b200_jpeg_quant_table",
     "b200_jpeg_batch_create", "b200_jpeg_batch_upload", "b200_jpeg_batch_run", "b200_jpeg_batch_download",
-    "b200_jpeg_batch_time", "b200_jpeg_batch_destroy",
+    "b200_jpeg_batch_time", "b200_jpeg_batch_destroy", "b200_jpeg_encode_coefficients_device",
+    "b200_png_decode", "b200_png_filter", "b200_png_lz77", "b200_png_deflate_tokens", "b200_png_level_strategies",
 ]
 
 
@@ -80,7 +81,8 @@ def lib():
         for f in ("b200_compress_in_memory", "b200_convert_in_memory", "b200_compress_to_size_in_memory",
                   "b200_jpeg_decode_coefficients", "b200_jpeg_output_layout", "b200_jpeg_requantize",
                   "b200_jpeg_encode_coefficients", "b200_jpeg_decode_planes", "b200_jpeg_batch_create",
-                  "b200_jpeg_batch_upload", "b200_jpeg_batch_run", "b200_jpeg_batch_download", "b200_jpeg_batch_time"):
+                  "b200_jpeg_batch_upload", "b200_jpeg_batch_run", "b200_jpeg_batch_download", "b200_jpeg_batch_time",
+                  "b200_png_decode", "b200_png_filter", "b200_png_lz77", "b200_png_deflate_tokens"):
             getattr(L, f).restype = Status
         L.b200_version.restype = C.c_char_p
         L.b200_sniff_format.restype = C.c_uint32
@@ -214,6 +216,57 @@ def jpeg_decode_planes(in_layout, in_coefs):
     out = np.zeros((in_layout.ncomp, in_layout.height, in_layout.width), dtype=np.uint8)
     _check(lib().b200_jpeg_decode_planes(C.byref(in_layout), in_coefs.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
     return out
+
+
+# ---- PNG stage entry points (lossless path) ----------------------------------------------------------------
+class PngInfo(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("bit_depth", C.c_int32), ("color_type", C.c_int32),
+                ("bpp", C.c_int32), ("row_bytes", C.c_uint64)]
+
+
+def png_decode(data):
+    """Host: parse + inflate + unfilter -> (PngInfo, raw uint8 [height, row_bytes])."""
+    info, raw = PngInfo(), C.POINTER(C.c_uint8)()
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    _check(lib().b200_png_decode(buf, C.c_size_t(len(data)), C.byref(info), C.byref(raw)))
+    n = info.height * info.row_bytes
+    arr = np.frombuffer(C.string_at(raw, n), dtype=np.uint8).reshape(info.height, info.row_bytes).copy()
+    lib().b200_free(raw)
+    return info, arr
+
+
+def png_filter(raw, bpp, strategy):
+    """Device K6: raw uint8 [h, row_bytes] -> filtered [h, row_bytes + 1]."""
+    raw = np.ascontiguousarray(raw, dtype=np.uint8)
+    h, rb = raw.shape
+    out = np.zeros((h, rb + 1), dtype=np.uint8)
+    _check(lib().b200_png_filter(raw.ctypes.data_as(C.c_void_p), h, rb, int(bpp), int(strategy), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def png_lz77(stream, bpp, stride):
+    """Device K7: filtered stream -> (tokens uint32[nt], hist uint32[316])."""
+    s = np.ascontiguousarray(stream, dtype=np.uint8).reshape(-1)
+    tok, nt = C.POINTER(C.c_uint32)(), C.c_size_t()
+    hist = np.zeros(316, dtype=np.uint32)
+    _check(lib().b200_png_lz77(s.ctypes.data_as(C.c_void_p), C.c_size_t(s.size), int(bpp), int(stride), C.byref(tok), C.byref(nt), hist.ctypes.data_as(C.c_void_p)))
+    out = np.frombuffer(C.string_at(tok, nt.value * 4), dtype=np.uint32).copy()
+    lib().b200_free(tok)
+    return out, hist
+
+
+def png_deflate_tokens(tokens, adler):
+    """Host: dynamic-Huffman DEFLATE + zlib framing of a token stream."""
+    tokens = np.ascontiguousarray(tokens, dtype=np.uint32)
+    outp, outl = C.POINTER(C.c_uint8)(), C.c_size_t()
+    _check(lib().b200_png_deflate_tokens(tokens.ctypes.data_as(C.c_void_p), C.c_size_t(tokens.size), C.c_uint32(adler), C.byref(outp), C.byref(outl)))
+    return _take(outp, outl)
+
+
+def png_level_strategies(level):
+    out = (C.c_int * 10)()
+    n = lib().b200_png_level_strategies(int(level), out)
+    return list(out[:n])
 
 
 def component_view(layout, coefs, c):

@@ -18,6 +18,8 @@
 #include "jpeg_host.h"
 #include "jpeg_gpuenc.h"
 #include "resize_kernels.h"
+#include "png_host.h"
+#include "png_device.h"
 
 using namespace b200;
 
@@ -268,11 +270,35 @@ void jpeg_compress_group(const uint8_t *const *in, const size_t *in_len, const s
     slot_release(s);
 }
 
+// ---- PNG (lossless) through the device ---------------------------------------------------------------------------
+// libcaesium png::compress: optimize == true -> png::lossless (oxipng, level = png.optimization_level); otherwise the lossy
+// palette quantiser (imagequant), which is outside this path.  Resizing a PNG goes through the image crate's decoder and is
+// likewise left to the reference.
+b200_status png_compress(const uint8_t *in, size_t in_len, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
+{
+    if (!p->png_optimize) return make_status(B200_ERR_UNSUPPORTED, "lossy PNG (imagequant) is outside the GPU path (route to caesium::compress_in_memory)");
+    if (p->width || p->height) return make_status(B200_ERR_UNSUPPORTED, "PNG resize is outside the GPU path (route to caesium::compress_in_memory)");
+    std::string err;
+    PngInfo info; std::vector<uint8_t> raw;
+    if (!png_decode(in, in_len, p->keep_metadata != 0, info, raw, err)) return make_status(err.find("interlace") != std::string::npos ? B200_ERR_UNSUPPORTED : B200_ERR_CORRUPT_INPUT, err);
+    if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
+    Slot *s = slot_acquire(prefer_dev < 0 ? runtime_next_device() : prefer_dev, err);
+    if (!s) return make_status(B200_ERR_CUDA, err);
+    if (!s->png) s->png = new PngDevice();
+    std::vector<uint8_t> z;
+    int level = (int)p->png_optimization_level; if (level > 6) level = 6;
+    const bool ok = s->png->compress(info, raw, level, s->stream, z, nullptr, err);
+    slot_release(s);
+    if (!ok) return make_status(B200_ERR_CUDA, err);
+    png_write(info, z, out);
+    return ok_status();
+}
+
 b200_status compress_dispatch(const uint8_t *in, size_t in_len, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
 {
     switch (b200_sniff_format(in, in_len)) {
         case B200_FMT_JPEG: return jpeg_compress(in, in_len, p, prefer_dev, out);
-        case B200_FMT_PNG: return make_status(B200_ERR_UNSUPPORTED, "PNG is not implemented on the GPU path yet");
+        case B200_FMT_PNG: return png_compress(in, in_len, p, prefer_dev, out);
         case B200_FMT_WEBP: return make_status(B200_ERR_UNSUPPORTED, "WebP is not implemented on the GPU path yet");
         case B200_FMT_GIF: return make_status(B200_ERR_UNSUPPORTED, "GIF is outside the GPU path (route to caesium::compress_in_memory)");
         case B200_FMT_TIFF: return make_status(B200_ERR_UNSUPPORTED, "TIFF is outside the GPU path (route to caesium::compress_in_memory)");
@@ -549,5 +575,60 @@ b200_status b200_jpeg_batch_time(b200_jpeg_batch *b, int which, int iters, float
     return batch_time(b->b, which, iters, ms_per_run, err) ? ok_status() : make_status(B200_ERR_CUDA, err);
 }
 void b200_jpeg_batch_destroy(b200_jpeg_batch *b) { if (b) { batch_destroy(b->b); delete b; } }
+
+// ---- PNG stage entry points ----------------------------------------------------------------------------------------
+b200_status b200_png_decode(const uint8_t *in, size_t in_len, b200_png_info *info, uint8_t **raw)
+{
+    if (!in || !info || !raw) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    std::string err; PngInfo pi; std::vector<uint8_t> r;
+    if (!png_decode(in, in_len, false, pi, r, err)) return make_status(err.find("interlace") != std::string::npos ? B200_ERR_UNSUPPORTED : B200_ERR_CORRUPT_INPUT, err);
+    info->width = pi.width; info->height = pi.height; info->bit_depth = pi.bit_depth; info->color_type = pi.color_type; info->bpp = pi.bpp; info->row_bytes = pi.row_bytes;
+    *raw = (uint8_t *)malloc(r.size() ? r.size() : 1);
+    if (!*raw) return make_status(B200_ERR_OUT_OF_MEMORY, "malloc failed");
+    memcpy(*raw, r.data(), r.size());
+    return ok_status();
+}
+b200_status b200_png_filter(const uint8_t *raw, int h, int row_bytes, int bpp, int strategy, uint8_t *filtered)
+{
+    if (!raw || !filtered || h <= 0 || row_bytes <= 0 || bpp < 1 || bpp > 8 || strategy < 0 || strategy > 9) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid argument");
+    std::string err;
+    if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
+    Slot *s = slot_acquire(runtime_next_device(), err);              // makes the slot's device current for this thread
+    if (!s) return make_status(B200_ERR_CUDA, err);
+    const bool ok = png_stage_filter(raw, h, row_bytes, bpp, strategy, filtered, err);
+    slot_release(s);
+    return ok ? ok_status() : make_status(B200_ERR_CUDA, err);
+}
+b200_status b200_png_lz77(const uint8_t *filtered, size_t n, int bpp, int stride, uint32_t **tokens, size_t *ntokens, uint32_t *hist)
+{
+    if (!filtered || !n || !tokens || !ntokens || !hist || bpp < 1 || stride < 1) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid argument");
+    std::string err;
+    if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
+    Slot *s = slot_acquire(runtime_next_device(), err);
+    if (!s) return make_status(B200_ERR_CUDA, err);
+    std::vector<uint32_t> t;
+    const bool ok = png_stage_lz77(filtered, n, bpp, stride, t, hist, err);
+    slot_release(s);
+    if (!ok) return make_status(B200_ERR_CUDA, err);
+    *tokens = (uint32_t *)malloc(t.size() * 4 + 4);
+    if (!*tokens) return make_status(B200_ERR_OUT_OF_MEMORY, "malloc failed");
+    memcpy(*tokens, t.data(), t.size() * 4); *ntokens = t.size();
+    return ok_status();
+}
+b200_status b200_png_deflate_tokens(const uint32_t *tokens, size_t ntokens, uint32_t adler, uint8_t **out, size_t *out_len)
+{
+    if ((!tokens && ntokens) || !out || !out_len) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    std::vector<uint8_t> z; deflate_tokens(tokens, ntokens, adler, z);
+    *out = (uint8_t *)malloc(z.size() + 1);
+    if (!*out) return make_status(B200_ERR_OUT_OF_MEMORY, "malloc failed");
+    memcpy(*out, z.data(), z.size()); *out_len = z.size();
+    return ok_status();
+}
+int b200_png_level_strategies(int level, int *out)
+{
+    const std::vector<int> v = png_level_strategies(level < 0 ? 0 : level > 6 ? 6 : level);
+    if (out) for (size_t i = 0; i < v.size(); i++) out[i] = v[i];
+    return (int)v.size();
+}
 
 } // extern "C"

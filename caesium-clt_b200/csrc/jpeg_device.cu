@@ -13,6 +13,7 @@
 #include "resize_kernels.h"
 #include "jpeg_gpuenc.h"
 #include "jpeg_gpudec.h"
+#include "png_device.h"
 
 namespace b200 {
 
@@ -152,7 +153,7 @@ void runtime_shutdown()
         cudaSetDevice(d->ordinal);
         for (Slot *s : d->free_slots) {
             if (s->stream) cudaStreamDestroy((cudaStream_t)s->stream);
-            cudaFreeHost(s->h_in); cudaFreeHost(s->h_out); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_scratch); cudaFreeHost(s->h_par); cudaFree(s->d_par); delete s->enc; delete s->dec;
+            cudaFreeHost(s->h_in); cudaFreeHost(s->h_out); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_scratch); cudaFreeHost(s->h_par); cudaFree(s->d_par); delete s->enc; delete s->dec; delete s->png;
             delete s;
         }
         delete d;

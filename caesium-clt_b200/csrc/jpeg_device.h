@@ -50,6 +50,7 @@ struct Slot {
     uint8_t *h_par = nullptr, *d_par = nullptr; size_t par_cap = 0, d_par_cap = 0;      // parameter block
     class GpuEncoder *enc = nullptr;                                                     // device entropy encoder (lazy)
     class GpuDecoder *dec = nullptr;                                                     // device entropy decoder (lazy)
+    struct PngDevice *png = nullptr;                                                     // lossless PNG state (lazy, png_device.cu)
     bool ensure(size_t in_bytes, size_t out_bytes, size_t scratch_bytes, size_t par_bytes, std::string &err);
     bool ensure_device(size_t in_bytes, size_t out_bytes, size_t scratch_bytes, size_t par_bytes, std::string &err);
 };

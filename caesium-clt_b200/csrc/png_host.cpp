@@ -1,0 +1,393 @@
+// png_host.cpp -- see png_host.h.  Formats: PNG (ISO/IEC 15948), zlib (RFC 1950), DEFLATE (RFC 1951).  Restates the host
+// duties of oxipng 9.1.5 + libdeflate (Cargo.lock:1161, :917) behind libcaesium png::lossless: decode the source, keep
+// the chunks StripChunks::Safe keeps, and wrap the re-compressed image data.
+#include "png_host.h"
+#include <algorithm>
+#include <cstring>
+
+namespace b200 {
+
+// ---- checksums ------------------------------------------------------------------------------------------------------
+static uint32_t g_crc[8][256];
+static bool g_crc_init = [] {
+    for (uint32_t i = 0; i < 256; i++) { uint32_t c = i; for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1; g_crc[0][i] = c; }
+    for (uint32_t i = 0; i < 256; i++) for (int t = 1; t < 8; t++) g_crc[t][i] = (g_crc[t - 1][i] >> 8) ^ g_crc[0][g_crc[t - 1][i] & 0xFF];
+    return true; }();
+
+uint32_t crc32_update(uint32_t crc, const uint8_t *p, size_t n)
+{
+    (void)g_crc_init;
+    crc = ~crc;
+    while (n >= 8) {
+        uint32_t a, b; memcpy(&a, p, 4); memcpy(&b, p + 4, 4); a ^= crc;
+        crc = g_crc[7][a & 0xFF] ^ g_crc[6][(a >> 8) & 0xFF] ^ g_crc[5][(a >> 16) & 0xFF] ^ g_crc[4][a >> 24] ^
+              g_crc[3][b & 0xFF] ^ g_crc[2][(b >> 8) & 0xFF] ^ g_crc[1][(b >> 16) & 0xFF] ^ g_crc[0][b >> 24];
+        p += 8; n -= 8;
+    }
+    while (n--) crc = g_crc[0][(crc ^ *p++) & 0xFF] ^ (crc >> 8);
+    return ~crc;
+}
+
+uint32_t adler32(const uint8_t *p, size_t n)
+{
+    uint32_t a = 1, b = 0;
+    while (n) {
+        size_t k = n < 5552 ? n : 5552; n -= k;
+        while (k--) { a += *p++; b += a; }
+        a %= 65521; b %= 65521;
+    }
+    return (b << 16) | a;
+}
+
+// ---- inflate -----------------------------------------------------------------------------------------------------------
+namespace {
+struct InfTable { uint16_t fast[1 << 10]; uint16_t count[16]; uint16_t symbol[320]; int maxlen; };   // fast: (len << 12) | sym, 0 = slow path
+
+bool build_inf(InfTable &t, const uint8_t *lens, int n)
+{
+    memset(t.count, 0, sizeof(t.count));
+    for (int i = 0; i < n; i++) t.count[lens[i]]++;
+    t.count[0] = 0;
+    int left = 1;
+    for (int l = 1; l <= 15; l++) { left <<= 1; left -= t.count[l]; if (left < 0) return false; }
+    uint16_t offs[16]; offs[1] = 0;
+    for (int l = 1; l < 15; l++) offs[l + 1] = offs[l] + t.count[l];
+    for (int i = 0; i < n; i++) if (lens[i]) t.symbol[offs[lens[i]]++] = (uint16_t)i;
+    memset(t.fast, 0, sizeof(t.fast));
+    // canonical codes, bit-reversed (DEFLATE packs Huffman codes starting from the LSB)
+    int code = 0, idx = 0; t.maxlen = 0;
+    for (int l = 1; l <= 15; l++) {
+        for (int k = 0; k < t.count[l]; k++, idx++, code++) {
+            t.maxlen = l;
+            if (l <= 10) {
+                int rev = 0; for (int b = 0; b < l; b++) if (code & (1 << b)) rev |= 1 << (l - 1 - b);
+                for (int f = rev; f < 1024; f += 1 << l) t.fast[f] = (uint16_t)((l << 12) | t.symbol[idx]);
+            }
+        }
+        code <<= 1;
+    }
+    return true;
+}
+
+struct InfBits {
+    const uint8_t *p, *end; uint64_t acc = 0; int n = 0;
+    inline void fill() { while (n <= 56 && p < end) { acc |= (uint64_t)*p++ << n; n += 8; } }
+    inline uint32_t peek(int k) { return (uint32_t)(acc & ((1ull << k) - 1)); }
+    inline void drop(int k) { acc >>= k; n -= k; }
+    inline uint32_t get(int k) { if (n < k) fill(); uint32_t v = peek(k); drop(k); return v; }
+};
+
+inline int inf_decode(InfBits &b, const InfTable &t)
+{
+    if (b.n < 15) b.fill();
+    uint32_t e = t.fast[b.peek(10)];
+    if (e) { b.drop(e >> 12); return e & 0xFFF; }
+    int code = 0, first = 0, index = 0;
+    for (int l = 1; l <= 15; l++) {
+        code |= (int)(b.acc & 1); b.drop(1);
+        int cnt = t.count[l];
+        if (code - cnt < first) return t.symbol[index + (code - first)];
+        index += cnt; first += cnt; first <<= 1; code <<= 1;
+    }
+    return -1;
+}
+
+const uint16_t kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+const uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+const uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+const uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+const uint8_t kClOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+} // namespace
+
+bool zlib_inflate(const uint8_t *in, size_t n, std::vector<uint8_t> &out, size_t size_hint, std::string &err)
+{
+    if (n < 6) { err = "zlib stream too short"; return false; }
+    if ((in[0] & 0x0F) != 8 || ((in[0] << 8) | in[1]) % 31 != 0 || (in[1] & 0x20)) { err = "bad zlib header"; return false; }
+    InfBits b; b.p = in + 2; b.end = in + n;
+    out.clear(); out.reserve(size_hint ? size_hint : n * 4);
+    static thread_local InfTable lit, dist;
+    for (;;) {
+        const uint32_t final = b.get(1), type = b.get(2);
+        if (type == 0) {
+            b.drop(b.n & 7);
+            // give back whole buffered bytes
+            while (b.n >= 8) { b.p--; b.n -= 8; } b.acc = 0; b.n = 0;
+            if (b.end - b.p < 4) { err = "truncated stored block"; return false; }
+            const uint32_t len = b.p[0] | (b.p[1] << 8), nlen = b.p[2] | (b.p[3] << 8);
+            if ((len ^ 0xFFFF) != nlen || (size_t)(b.end - b.p - 4) < len) { err = "bad stored block"; return false; }
+            out.insert(out.end(), b.p + 4, b.p + 4 + len); b.p += 4 + len;
+        } else if (type == 1 || type == 2) {
+            uint8_t lens[320];
+            if (type == 1) {
+                for (int i = 0; i < 288; i++) lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+                build_inf(lit, lens, 288);
+                for (int i = 0; i < 30; i++) lens[i] = 5;
+                build_inf(dist, lens, 30);
+            } else {
+                const int hlit = (int)b.get(5) + 257, hdist = (int)b.get(5) + 1, hclen = (int)b.get(4) + 4;
+                uint8_t cl[19] = {0};
+                for (int i = 0; i < hclen; i++) cl[kClOrder[i]] = (uint8_t)b.get(3);
+                static thread_local InfTable clt;
+                if (!build_inf(clt, cl, 19)) { err = "bad code-length code"; return false; }
+                int i = 0;
+                while (i < hlit + hdist) {
+                    int s = inf_decode(b, clt);
+                    if (s < 0) { err = "bad code-length symbol"; return false; }
+                    if (s < 16) lens[i++] = (uint8_t)s;
+                    else {
+                        int rep, val = 0;
+                        if (s == 16) { if (!i) { err = "repeat without previous length"; return false; } val = lens[i - 1]; rep = 3 + (int)b.get(2); }
+                        else if (s == 17) rep = 3 + (int)b.get(3); else rep = 11 + (int)b.get(7);
+                        if (i + rep > hlit + hdist) { err = "code lengths overflow"; return false; }
+                        while (rep--) lens[i++] = (uint8_t)val;
+                    }
+                }
+                if (!build_inf(lit, lens, hlit) || !build_inf(dist, lens + hlit, hdist)) { err = "bad Huffman code"; return false; }
+            }
+            for (;;) {
+                int s = inf_decode(b, lit);
+                if (s < 0) { err = "bad literal/length code"; return false; }
+                if (s < 256) out.push_back((uint8_t)s);
+                else if (s == 256) break;
+                else {
+                    s -= 257; if (s >= 29) { err = "bad length symbol"; return false; }
+                    const int len = kLenBase[s] + (int)b.get(kLenExtra[s]);
+                    const int ds = inf_decode(b, dist);
+                    if (ds < 0 || ds >= 30) { err = "bad distance code"; return false; }
+                    const size_t d = kDistBase[ds] + b.get(kDistExtra[ds]);
+                    if (d > out.size()) { err = "distance too far back"; return false; }
+                    const size_t start = out.size() - d;
+                    for (int k = 0; k < len; k++) out.push_back(out[start + k]);
+                }
+                if (b.p >= b.end && b.n <= 0) { err = "truncated deflate stream"; return false; }
+            }
+        } else { err = "bad block type"; return false; }
+        if (final) break;
+    }
+    b.drop(b.n & 7);
+    uint8_t tail[4]; for (int i = 0; i < 4; i++) tail[i] = (uint8_t)b.get(8);
+    const uint32_t want = ((uint32_t)tail[0] << 24) | (tail[1] << 16) | (tail[2] << 8) | tail[3];
+    if (want != adler32(out.data(), out.size())) { err = "Adler-32 mismatch"; return false; }
+    return true;
+}
+
+// ---- PNG container -------------------------------------------------------------------------------------------------------
+static uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | (p[1] << 16) | (p[2] << 8) | p[3]; }
+static void put32(std::vector<uint8_t> &o, uint32_t v) { o.push_back(v >> 24); o.push_back(v >> 16); o.push_back(v >> 8); o.push_back(v); }
+static void put_chunk(std::vector<uint8_t> &o, const char *type, const uint8_t *data, size_t n)
+{
+    put32(o, (uint32_t)n);
+    const size_t s = o.size();
+    o.insert(o.end(), type, type + 4); o.insert(o.end(), data, data + n);
+    put32(o, crc32_update(0, o.data() + s, 4 + n));
+}
+
+static inline int paeth(int a, int b, int c) { int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c); return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); }
+
+bool png_decode(const uint8_t *d, size_t n, bool keep_all, PngInfo &info, std::vector<uint8_t> &raw, std::string &err)
+{
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1A, '\n'};
+    if (n < 8 + 25 || memcmp(d, sig, 8)) { err = "not a PNG"; return false; }
+    info = PngInfo();
+    std::vector<uint8_t> idat;
+    size_t i = 8; bool have_ihdr = false, seen_idat = false, seen_end = false;
+    while (i + 12 <= n) {
+        const uint32_t L = be32(d + i);
+        if (L > n - i - 12) { err = "truncated PNG chunk"; return false; }
+        const uint8_t *type = d + i + 4, *data = d + i + 8;
+        if (be32(data + L) != crc32_update(0, type, 4 + L)) { err = "PNG chunk CRC mismatch"; return false; }
+        if (!memcmp(type, "IHDR", 4)) {
+            if (L != 13) { err = "bad IHDR"; return false; }
+            info.width = be32(data); info.height = be32(data + 4); info.bit_depth = data[8]; info.color_type = data[9]; info.interlace = data[12];
+            if (!info.width || !info.height || data[10] || data[11]) { err = "bad IHDR"; return false; }
+            static const int ch[7] = {1, 0, 3, 1, 2, 0, 4};
+            if (info.color_type > 6 || !ch[info.color_type]) { err = "bad colour type"; return false; }
+            info.channels = ch[info.color_type]; info.bits_per_pixel = info.channels * info.bit_depth;
+            info.bpp = std::max(1, info.bits_per_pixel / 8);
+            info.row_bytes = ((size_t)info.width * info.bits_per_pixel + 7) / 8;
+            have_ihdr = true;
+        } else if (!memcmp(type, "IDAT", 4)) { idat.insert(idat.end(), data, data + L); seen_idat = true; }
+        else if (!memcmp(type, "IEND", 4)) { seen_end = true; break; }
+        else if (!memcmp(type, "PLTE", 4)) info.plte.assign(data, data + L);
+        else if (!memcmp(type, "tRNS", 4)) info.trns.assign(data, data + L);
+        else {
+            // oxipng StripChunks::Safe keeps the chunks that affect rendering; with keep_metadata nothing is stripped
+            static const char *safe[] = {"cICP", "iCCP", "sRGB", "pHYs", "gAMA", "cHRM", "sBIT", "acTL", "fcTL", "fdAT"};
+            bool keep = keep_all;
+            for (const char *s : safe) if (!memcmp(type, s, 4)) keep = true;
+            if (keep) { std::vector<uint8_t> &dst = seen_idat ? info.kept_after_idat : info.kept_before_idat; dst.insert(dst.end(), d + i, d + i + 12 + L); }
+        }
+        i += 12 + L;
+    }
+    if (!have_ihdr || !seen_idat || !seen_end) { err = "incomplete PNG"; return false; }
+    if (info.interlace) { err = "interlaced PNG is not supported on the GPU path"; return false; }
+    std::vector<uint8_t> filt;
+    const size_t stride = info.row_bytes + 1;
+    if (!zlib_inflate(idat.data(), idat.size(), filt, stride * info.height, err)) return false;
+    if (filt.size() < stride * info.height) { err = "IDAT too short"; return false; }
+    raw.resize(info.row_bytes * info.height);
+    const int bpp = info.bpp; const size_t rb = info.row_bytes;
+    for (uint32_t y = 0; y < info.height; y++) {   // PNG 9.2 reconstruction
+        const uint8_t *f = filt.data() + (size_t)y * stride; const int ft = f[0]; f++;
+        uint8_t *r = raw.data() + (size_t)y * rb; const uint8_t *up = y ? r - rb : nullptr;
+        switch (ft) {
+            case 0: memcpy(r, f, rb); break;
+            case 1: for (size_t x = 0; x < rb; x++) r[x] = (uint8_t)(f[x] + (x >= (size_t)bpp ? r[x - bpp] : 0)); break;
+            case 2: for (size_t x = 0; x < rb; x++) r[x] = (uint8_t)(f[x] + (up ? up[x] : 0)); break;
+            case 3: for (size_t x = 0; x < rb; x++) r[x] = (uint8_t)(f[x] + (((x >= (size_t)bpp ? r[x - bpp] : 0) + (up ? up[x] : 0)) >> 1)); break;
+            case 4: for (size_t x = 0; x < rb; x++) { int a = x >= (size_t)bpp ? r[x - bpp] : 0, b = up ? up[x] : 0, c = (up && x >= (size_t)bpp) ? up[x - bpp] : 0; r[x] = (uint8_t)(f[x] + paeth(a, b, c)); } break;
+            default: err = "bad filter type"; return false;
+        }
+    }
+    return true;
+}
+
+void png_write(const PngInfo &info, const std::vector<uint8_t> &z, std::vector<uint8_t> &out)
+{
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1A, '\n'};
+    out.clear(); out.reserve(z.size() + 1024 + info.kept_before_idat.size() + info.kept_after_idat.size());
+    out.insert(out.end(), sig, sig + 8);
+    uint8_t ih[13]; ih[0] = info.width >> 24; ih[1] = info.width >> 16; ih[2] = info.width >> 8; ih[3] = info.width;
+    ih[4] = info.height >> 24; ih[5] = info.height >> 16; ih[6] = info.height >> 8; ih[7] = info.height;
+    ih[8] = (uint8_t)info.bit_depth; ih[9] = (uint8_t)info.color_type; ih[10] = 0; ih[11] = 0; ih[12] = 0;
+    put_chunk(out, "IHDR", ih, 13);
+    out.insert(out.end(), info.kept_before_idat.begin(), info.kept_before_idat.end());
+    if (!info.plte.empty()) put_chunk(out, "PLTE", info.plte.data(), info.plte.size());
+    if (!info.trns.empty()) put_chunk(out, "tRNS", info.trns.data(), info.trns.size());
+    put_chunk(out, "IDAT", z.data(), z.size());
+    out.insert(out.end(), info.kept_after_idat.begin(), info.kept_after_idat.end());
+    put_chunk(out, "IEND", nullptr, 0);
+}
+
+// ---- DEFLATE encoder over device-made LZ77 tokens --------------------------------------------------------------------------
+namespace {
+struct BitOut {
+    std::vector<uint8_t> &o; uint64_t acc = 0; int n = 0;
+    explicit BitOut(std::vector<uint8_t> &out) : o(out) {}
+    inline void put(uint32_t v, int k) { acc |= (uint64_t)v << n; n += k; while (n >= 8) { o.push_back((uint8_t)acc); acc >>= 8; n -= 8; } }
+    inline void flush() { if (n) { o.push_back((uint8_t)acc); acc = 0; n = 0; } }
+};
+
+// length-limited Huffman code lengths: plain Huffman, then the IJG/zlib style overflow repair, then lengths handed out by rank
+void huff_lengths(const uint32_t *freq, int n, int limit, uint8_t *len)
+{
+    struct Node { uint64_t w; int l, r; };
+    std::vector<Node> nodes; std::vector<int> alive;
+    for (int i = 0; i < n; i++) { len[i] = 0; if (freq[i]) { nodes.push_back({freq[i], -1, i}); alive.push_back((int)nodes.size() - 1); } }
+    if (alive.empty()) return;
+    if (alive.size() == 1) { len[nodes[alive[0]].r] = 1; return; }
+    auto cmp = [&](int a, int b) { return nodes[a].w > nodes[b].w || (nodes[a].w == nodes[b].w && a > b); };
+    std::make_heap(alive.begin(), alive.end(), cmp);
+    while (alive.size() > 1) {
+        std::pop_heap(alive.begin(), alive.end(), cmp); int a = alive.back(); alive.pop_back();
+        std::pop_heap(alive.begin(), alive.end(), cmp); int b = alive.back(); alive.pop_back();
+        nodes.push_back({nodes[a].w + nodes[b].w, a, b});
+        alive.push_back((int)nodes.size() - 1); std::push_heap(alive.begin(), alive.end(), cmp);
+    }
+    // depths
+    std::vector<int> depth(nodes.size(), 0); std::vector<int> order;
+    std::vector<int> stack{alive[0]};
+    int bl[64] = {0};
+    std::vector<std::pair<uint32_t, int>> leaves;   // (freq, symbol)
+    while (!stack.empty()) {
+        int x = stack.back(); stack.pop_back();
+        if (nodes[x].l < 0) { bl[std::min(depth[x], 63)]++; leaves.push_back({freq[nodes[x].r], nodes[x].r}); }
+        else { depth[nodes[x].l] = depth[nodes[x].r] = depth[x] + 1; stack.push_back(nodes[x].l); stack.push_back(nodes[x].r); }
+    }
+    for (int i = 63; i > limit; i--) while (bl[i] > 0) {
+        int j = i - 2; while (bl[j] == 0) j--;
+        bl[i] -= 2; bl[i - 1]++; bl[j + 1] += 2; bl[j]--;
+    }
+    // most frequent symbols get the shortest lengths
+    std::sort(leaves.begin(), leaves.end(), [](const std::pair<uint32_t, int> &a, const std::pair<uint32_t, int> &b) { return a.first > b.first || (a.first == b.first && a.second < b.second); });
+    size_t k = 0;
+    for (int l = 1; l <= limit; l++) for (int c = 0; c < bl[l]; c++) len[leaves[k++].second] = (uint8_t)l;
+}
+
+void canon_codes(const uint8_t *len, int n, uint16_t *code)
+{   // RFC 1951 3.2.2, stored bit-reversed for LSB-first output
+    int cnt[16] = {0}, next[16];
+    for (int i = 0; i < n; i++) cnt[len[i]]++;
+    cnt[0] = 0; int c = 0;
+    for (int l = 1; l <= 15; l++) { c = (c + cnt[l - 1]) << 1; next[l] = c; }
+    for (int i = 0; i < n; i++) if (len[i]) {
+        int v = next[len[i]]++, r = 0;
+        for (int b = 0; b < len[i]; b++) if (v & (1 << b)) r |= 1 << (len[i] - 1 - b);
+        code[i] = (uint16_t)r;
+    }
+}
+
+inline int len_sym(int len) { int s = 0; while (s < 28 && kLenBase[s + 1] <= len) s++; return s; }
+inline int dist_sym(int d) { int s = 0; while (s < 29 && kDistBase[s + 1] <= d) s++; return s; }
+} // namespace
+
+void deflate_tokens(const uint32_t *tok, size_t nt, uint32_t adler, std::vector<uint8_t> &out, size_t block_tokens)
+{
+    out.clear(); out.reserve(nt + 64);
+    out.push_back(0x78); out.push_back(0xDA);
+    BitOut bw(out);
+    static uint8_t lsym[259], dsym_small[513]; static bool init = false;
+    if (!init) { for (int l = 3; l <= 258; l++) lsym[l] = (uint8_t)len_sym(l); for (int d = 1; d <= 512; d++) dsym_small[d] = (uint8_t)dist_sym(d); init = true; }
+    auto dsym = [&](int d) { return d <= 512 ? (int)dsym_small[d] : dist_sym(d); };
+    size_t pos = 0;
+    if (nt == 0) { bw.put(1, 1); bw.put(1, 2); bw.put(0, 7); }
+    while (pos < nt) {
+        const size_t end = std::min(nt, pos + block_tokens);
+        uint32_t lf[286] = {0}, df[30] = {0};
+        for (size_t i = pos; i < end; i++) {
+            const uint32_t t = tok[i];
+            if (t & 0x80000000u) { lf[257 + lsym[((t >> 16) & 0xFF) + 3]]++; df[dsym((int)(t & 0xFFFF) + 1)]++; } else lf[t & 0xFF]++;
+        }
+        lf[256] = 1;
+        uint8_t ll[286], dl[30]; uint16_t lc[286], dc[30];
+        huff_lengths(lf, 286, 15, ll); huff_lengths(df, 30, 15, dl);
+        int ndist = 0; for (int i = 0; i < 30; i++) if (dl[i]) ndist++;
+        if (ndist == 0) dl[0] = 1;                          // at least one distance code must be described
+        canon_codes(ll, 286, lc); canon_codes(dl, 30, dc);
+        int hlit = 286; while (hlit > 257 && !ll[hlit - 1]) hlit--;
+        int hdist = 30; while (hdist > 1 && !dl[hdist - 1]) hdist--;
+        // run-length code the two length arrays (RFC 1951 3.2.7)
+        uint8_t seq[320]; int ns = 0;
+        for (int i = 0; i < hlit; i++) seq[ns++] = ll[i];
+        for (int i = 0; i < hdist; i++) seq[ns++] = dl[i];
+        struct Cl { uint8_t sym, extra; }; Cl cls[320]; int ncl = 0; uint32_t cf[19] = {0};
+        for (int i = 0; i < ns;) {
+            int v = seq[i], run = 1; while (i + run < ns && seq[i + run] == v) run++;
+            int left = run;
+            if (v == 0) {
+                while (left >= 11) { int r = std::min(left, 138); cls[ncl++] = {18, (uint8_t)(r - 11)}; cf[18]++; left -= r; }
+                if (left >= 3) { cls[ncl++] = {17, (uint8_t)(left - 3)}; cf[17]++; left = 0; }
+                while (left--) { cls[ncl++] = {0, 0}; cf[0]++; }
+            } else {
+                cls[ncl++] = {(uint8_t)v, 0}; cf[v]++; left--;
+                while (left >= 3) { int r = std::min(left, 6); cls[ncl++] = {16, (uint8_t)(r - 3)}; cf[16]++; left -= r; }
+                while (left-- > 0) { cls[ncl++] = {(uint8_t)v, 0}; cf[v]++; }
+            }
+            i += run;
+        }
+        uint8_t cll[19]; uint16_t clc[19];
+        huff_lengths(cf, 19, 7, cll); canon_codes(cll, 19, clc);
+        int hclen = 19; while (hclen > 4 && !cll[kClOrder[hclen - 1]]) hclen--;
+        bw.put(end == nt ? 1 : 0, 1); bw.put(2, 2);
+        bw.put((uint32_t)(hlit - 257), 5); bw.put((uint32_t)(hdist - 1), 5); bw.put((uint32_t)(hclen - 4), 4);
+        for (int i = 0; i < hclen; i++) bw.put(cll[kClOrder[i]], 3);
+        for (int i = 0; i < ncl; i++) {
+            bw.put(clc[cls[i].sym], cll[cls[i].sym]);
+            if (cls[i].sym == 16) bw.put(cls[i].extra, 2); else if (cls[i].sym == 17) bw.put(cls[i].extra, 3); else if (cls[i].sym == 18) bw.put(cls[i].extra, 7);
+        }
+        for (size_t i = pos; i < end; i++) {
+            const uint32_t t = tok[i];
+            if (t & 0x80000000u) {
+                const int len = (int)((t >> 16) & 0xFF) + 3, d = (int)(t & 0xFFFF) + 1, ls = lsym[len], ds = dsym(d);
+                bw.put(lc[257 + ls], ll[257 + ls]); if (kLenExtra[ls]) bw.put((uint32_t)(len - kLenBase[ls]), kLenExtra[ls]);
+                bw.put(dc[ds], dl[ds]); if (kDistExtra[ds]) bw.put((uint32_t)(d - kDistBase[ds]), kDistExtra[ds]);
+            } else bw.put(lc[t & 0xFF], ll[t & 0xFF]);
+        }
+        bw.put(lc[256], ll[256]);
+        pos = end;
+    }
+    bw.flush();
+    out.push_back(adler >> 24); out.push_back(adler >> 16); out.push_back(adler >> 8); out.push_back(adler);
+}
+
+} // namespace b200

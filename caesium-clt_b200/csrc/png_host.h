@@ -1,0 +1,41 @@
+// png_host.h -- host half of the lossless PNG path (libcaesium png::lossless -> oxipng, reached with png.optimize == true,
+// /root/reference/src/compressor.rs:428,436-437): container parsing, inflate + unfilter of the source IDAT, and the
+// DEFLATE bit-packer (dynamic Huffman blocks) + zlib/PNG framing around the LZ77 tokens the device produces.  Row-filter
+// selection (K6) and LZ77 match finding (K7) are CUDA kernels (png_kernels.cu); entropy coding stays here.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <string>
+#include <vector>
+
+namespace b200 {
+
+struct PngInfo {
+    uint32_t width = 0, height = 0;
+    int bit_depth = 8, color_type = 0, interlace = 0;
+    int channels = 1, bits_per_pixel = 8, bpp = 1;        // bpp = filter distance in bytes (>= 1)
+    size_t row_bytes = 0;                                  // without the filter byte
+    std::vector<uint8_t> plte, trns;                       // chunk payloads
+    std::vector<uint8_t> kept_before_idat, kept_after_idat;   // ancillary chunks carried over, serialised (len|type|data|crc)
+};
+
+// Parse + inflate + unfilter.  raw = height * row_bytes bytes of packed samples (no filter bytes).
+bool png_decode(const uint8_t *data, size_t len, bool keep_all_metadata, PngInfo &info, std::vector<uint8_t> &raw, std::string &err);
+
+// RFC 1951 inflate of a complete zlib stream (RFC 1950 wrapper checked, Adler-32 verified)
+bool zlib_inflate(const uint8_t *in, size_t n, std::vector<uint8_t> &out, size_t size_hint, std::string &err);
+
+// LZ77 token: literal = byte value (0..255); match = 0x80000000 | (length - 3) << 16 | (distance - 1)
+static inline uint32_t tok_match(int len, int dist) { return 0x80000000u | ((uint32_t)(len - 3) << 16) | (uint32_t)(dist - 1); }
+
+// DEFLATE-encode a token stream (dynamic Huffman, one block per `block_tokens` tokens) into a zlib stream.
+// adler = Adler-32 of the uncompressed bytes the tokens expand to.
+void deflate_tokens(const uint32_t *tokens, size_t ntokens, uint32_t adler, std::vector<uint8_t> &out, size_t block_tokens = 1 << 16);
+
+// Assemble the PNG file around one zlib stream.
+void png_write(const PngInfo &info, const std::vector<uint8_t> &zlib_stream, std::vector<uint8_t> &out);
+
+uint32_t crc32_update(uint32_t crc, const uint8_t *p, size_t n);
+uint32_t adler32(const uint8_t *p, size_t n);
+
+} // namespace b200

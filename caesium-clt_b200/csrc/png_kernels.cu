@@ -1,0 +1,249 @@
+// png_kernels.cu -- K6 (row-filter selection) and K7 (LZ77 match finding) for the lossless PNG path, SURVEY.md §8a row a8:
+// the device side of what oxipng 9.1.5 does behind libcaesium png::lossless (/root/reference/src/compressor.rs:428,
+// 436-437): for every filter strategy of the optimisation preset, filter all rows and run the compressor over them.
+// Filtering reads only RAW neighbours (left, up, up-left), so unlike un-filtering it is embarrassingly parallel: one CTA
+// per row scores the five candidate filters (MinSum / Entropy / Bigrams / BigEnt heuristics as histograms in shared
+// memory) and writes the winner.  Match finding is per position over a fixed candidate set that suits filtered image data
+// (pixel-multiple distances and the row above); parsing is sequential inside 4 KiB chunks, parallel across them.
+// All integer/byte work, HBM-bound; no tensor cores.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdint>
+#include "png_kernels.h"
+
+namespace b200 {
+
+void png_make_tlog(uint32_t *tlog, size_t n)
+{
+    tlog[0] = 0;
+    for (size_t c = 1; c <= n; c++) tlog[c] = (uint32_t)llround((double)c * std::log2((double)c) * 1024.0);
+}
+
+__device__ __forceinline__ int paeth_pred(int a, int b, int c)
+{
+    const int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+// the five PNG filters of byte x of a row (PNG 9.2), computed from raw neighbours
+__device__ __forceinline__ void five_filters(const uint8_t *__restrict__ row, const uint8_t *__restrict__ up, int x, int bpp, uint8_t v[5])
+{
+    const int cur = row[x], a = x >= bpp ? row[x - bpp] : 0, b = up ? up[x] : 0, c = (up && x >= bpp) ? up[x - bpp] : 0;
+    v[0] = (uint8_t)cur; v[1] = (uint8_t)(cur - a); v[2] = (uint8_t)(cur - b); v[3] = (uint8_t)(cur - ((a + b) >> 1)); v[4] = (uint8_t)(cur - paeth_pred(a, b, c));
+}
+
+__global__ void __launch_bounds__(256) k_png_filter(const uint8_t *__restrict__ raw, uint8_t *__restrict__ filt, int h, int rb, int bpp, int strategy, const uint32_t *__restrict__ tlog)
+{
+    extern __shared__ uint32_t sm[];
+    __shared__ unsigned long long score[5];
+    __shared__ int chosen;
+    const int y = blockIdx.x;
+    const uint8_t *row = raw + (size_t)y * rb, *up = y ? row - rb : nullptr;
+    uint8_t *out = filt + (size_t)y * (rb + 1);
+    int f = strategy;
+    if (strategy >= 5) {
+        if (threadIdx.x < 5) score[threadIdx.x] = 0;
+        const int words = strategy == PNGF_MINSUM ? 0 : (strategy == PNGF_BIGRAMS ? 5 * 2048 : (strategy == PNGF_BIGENT ? 5 * 4096 : 5 * 256));
+        for (int i = threadIdx.x; i < words; i += blockDim.x) sm[i] = 0;
+        __syncthreads();
+        if (strategy == PNGF_MINSUM) {
+            unsigned long long s[5] = {0, 0, 0, 0, 0};
+            for (int x = threadIdx.x; x < rb; x += blockDim.x) { uint8_t v[5]; five_filters(row, up, x, bpp, v); for (int k = 0; k < 5; k++) s[k] += (unsigned)abs((int)(int8_t)v[k]); }
+            for (int k = 0; k < 5; k++) atomicAdd(&score[k], s[k]);
+        } else if (strategy == PNGF_ENTROPY || strategy == PNGF_BRUTE) {
+            for (int x = threadIdx.x; x < rb; x += blockDim.x) { uint8_t v[5]; five_filters(row, up, x, bpp, v); for (int k = 0; k < 5; k++) atomicAdd(&sm[k * 256 + v[k]], 1u); }
+            __syncthreads();
+            for (int i = threadIdx.x; i < 5 * 256; i += blockDim.x) if (sm[i]) atomicAdd(&score[i >> 8], (unsigned long long)tlog[sm[i]]);
+        } else {
+            for (int x = threadIdx.x; x + 1 < rb; x += blockDim.x) {
+                uint8_t v[5], w[5]; five_filters(row, up, x, bpp, v); five_filters(row, up, x + 1, bpp, w);
+                for (int k = 0; k < 5; k++) {
+                    const unsigned bg = ((unsigned)v[k] << 8) | w[k];
+                    if (strategy == PNGF_BIGRAMS) atomicOr(&sm[k * 2048 + (bg >> 5)], 1u << (bg & 31));
+                    else atomicAdd(&sm[k * 4096 + (((bg * 2654435761u) >> 20) & 4095u)], 1u);
+                }
+            }
+            __syncthreads();
+            if (strategy == PNGF_BIGRAMS) { for (int i = threadIdx.x; i < 5 * 2048; i += blockDim.x) if (sm[i]) atomicAdd(&score[i >> 11], (unsigned long long)__popc(sm[i])); }
+            else for (int i = threadIdx.x; i < 5 * 4096; i += blockDim.x) if (sm[i]) atomicAdd(&score[i >> 12], (unsigned long long)tlog[min(sm[i], (uint32_t)rb)]);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const bool want_max = strategy == PNGF_ENTROPY || strategy == PNGF_BRUTE || strategy == PNGF_BIGENT;   // sum c*log2(c): larger = lower entropy
+            int best = 0;
+            for (int k = 1; k < 5; k++) if (want_max ? score[k] > score[best] : score[k] < score[best]) best = k;
+            chosen = best;
+        }
+        __syncthreads();
+        f = chosen;
+    }
+    if (threadIdx.x == 0) out[0] = (uint8_t)f;
+    for (int x = threadIdx.x; x < rb; x += blockDim.x) { uint8_t v[5]; five_filters(row, up, x, bpp, v); out[1 + x] = v[f]; }
+}
+
+// ---- K7 ---------------------------------------------------------------------------------------------------------------------
+constexpr int PARSE_CHUNK_MAX = 4096;
+
+__device__ __forceinline__ uint32_t load32u(const uint8_t *__restrict__ p)
+{   // unaligned 32-bit little-endian load from two aligned words
+    const uintptr_t a = (uintptr_t)p; const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    const int sh = (int)(a & 3) * 8;
+    return sh ? __funnelshift_r(w[0], w[1], sh) : w[0];
+}
+
+__device__ __forceinline__ int match_len(const uint8_t *__restrict__ s, size_t i, int d, int maxlen)
+{
+    int l = 0;
+    while (l + 4 <= maxlen) {
+        const uint32_t x = load32u(s + i + l) ^ load32u(s + i + l - d);
+        if (x) return l + ((__ffs((int)x) - 1) >> 3);
+        l += 4;
+    }
+    while (l < maxlen && s[i + l] == s[i + l - d]) l++;
+    return l;
+}
+
+__global__ void k_png_match(const uint8_t *__restrict__ s, uint32_t *__restrict__ best, size_t n, int bpp, int stride, int chunk)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t chunk_end = (i / chunk + 1) * (size_t)chunk;
+    const int maxlen = (int)min((size_t)258, min(n, chunk_end) - i);
+    int bl = 0, bd = 0;
+    if (maxlen >= 3) {
+        const int cand[10] = {bpp, 1, 2 * bpp, stride, stride - bpp, stride + bpp, 3 * bpp, 2, 3, 2 * stride};
+#pragma unroll
+        for (int c = 0; c < 10; c++) {
+            const int d = cand[c];
+            if (d < 1 || d > 32768 || (size_t)d > i) continue;
+            if (bl > 0 && s[i + bl] != s[i + bl - d]) continue;      // cannot beat the current best
+            const int l = match_len(s, i, d, maxlen);
+            if (l > bl || (l == bl && l >= 3 && d < bd)) { bl = l; bd = d; }
+            if (bl == maxlen) break;
+        }
+    }
+    best[i] = bl >= 3 ? ((uint32_t)bl << 16) | (uint32_t)bd : 0u;
+}
+
+__device__ __forceinline__ int len_symbol(int len)
+{   // RFC 1951 3.2.5 length code 257..285 (index 0..28)
+    if (len == 258) return 28;
+    if (len < 11) return len - 3;
+    const int l = len - 3, hb = 31 - __clz(l);              // l >= 8
+    return (hb - 1) * 4 + ((l >> (hb - 2)) & 3);
+}
+__device__ __forceinline__ int dist_symbol(int d)
+{
+    if (d <= 4) return d - 1;
+    const int v = d - 1, hb = 31 - __clz(v);
+    return hb * 2 + ((v >> (hb - 1)) & 1);
+}
+
+__global__ void __launch_bounds__(64) k_png_parse(const uint32_t *__restrict__ best, const uint8_t *__restrict__ s, size_t n, int chunk,
+                                                  uint32_t *__restrict__ tokens, uint32_t *__restrict__ counts, uint32_t *__restrict__ hist)
+{
+    __shared__ uint32_t h[316];
+    for (int k = threadIdx.x; k < 316; k += blockDim.x) h[k] = 0;
+    __syncthreads();
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t begin = c * (size_t)chunk;
+    if (begin < n) {
+        const size_t end = min(n, begin + (size_t)chunk);
+        uint32_t *out = tokens + begin;
+        uint32_t nt = 0;
+        size_t i = begin;
+        while (i < end) {
+            const uint32_t b = best[i];
+            int len = (int)(b >> 16), d = (int)(b & 0xFFFF);
+            if (len == 3 && d > 4096) len = 0;                                   // zlib's TOO_FAR rule
+            if (len >= 3 && i + 1 < end) { const uint32_t b1 = best[i + 1]; if ((int)(b1 >> 16) > len) len = 0; }   // one-step lazy matching
+            if (len >= 3) {
+                out[nt++] = 0x80000000u | ((uint32_t)(len - 3) << 16) | (uint32_t)(d - 1);
+                atomicAdd(&h[257 + len_symbol(len)], 1u); atomicAdd(&h[286 + dist_symbol(d)], 1u);
+                i += (size_t)len;
+            } else { const uint32_t v = s[i]; out[nt++] = v; atomicAdd(&h[v], 1u); i++; }
+        }
+        counts[c] = nt;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 316; k += blockDim.x) if (h[k]) atomicAdd(&hist[k], h[k]);
+}
+
+__global__ void k_png_compact(const uint32_t *__restrict__ tokens, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ offsets, int chunk, uint32_t *__restrict__ out)
+{
+    const size_t c = blockIdx.x;
+    const uint32_t n = counts[c], o = offsets[c];
+    const uint32_t *src = tokens + c * (size_t)chunk;
+    for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) out[o + t] = src[t];
+}
+
+__global__ void k_png_adler(const uint8_t *__restrict__ s, size_t n, unsigned long long *__restrict__ sums)
+{
+    const size_t piece = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t begin = piece * 4096;
+    if (begin >= n) return;
+    const size_t len = min((size_t)4096, n - begin);
+    unsigned long long a = 0, b = 0;
+    for (size_t k = 0; k < len; k++) { const unsigned v = s[begin + k]; a += v; b += (unsigned long long)(len - k) * v; }
+    sums[2 * piece] = a; sums[2 * piece + 1] = b;
+}
+
+__global__ void k_png_probe(const uint8_t *__restrict__ raw, size_t npix, int channels, uint32_t *__restrict__ flags)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const uint8_t *p = raw + i * channels;
+    if ((channels == 4 || channels == 2) && p[channels - 1] != 255) flags[0] = 1;
+    if (channels >= 3 && (p[0] != p[1] || p[1] != p[2])) flags[1] = 1;
+}
+__global__ void k_png_repack(const uint8_t *__restrict__ raw, uint8_t *__restrict__ out, size_t npix, int channels, int keep_mask, int kept)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const uint8_t *p = raw + i * channels; uint8_t *q = out + i * kept;
+    int o = 0;
+    for (int c = 0; c < channels; c++) if (keep_mask & (1 << c)) q[o++] = p[c];
+}
+
+static inline unsigned cdivu(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+int launch_png_filter(const uint8_t *d_raw, uint8_t *d_filt, int h, int rb, int bpp, int strategy, const uint32_t *d_tlog, void *stream)
+{
+    size_t smem = strategy == PNGF_BIGRAMS ? 5 * 2048 * 4 : (strategy == PNGF_BIGENT ? 5 * 4096 * 4 : (strategy >= 5 && strategy != PNGF_MINSUM ? 5 * 256 * 4 : 0));
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_png_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 4096 * 4);   // per device, cheap
+    k_png_filter<<<h, 256, smem, (cudaStream_t)stream>>>(d_raw, d_filt, h, rb, bpp, strategy, d_tlog);
+    return (int)cudaGetLastError();
+}
+int launch_png_match(const uint8_t *d_filt, uint32_t *d_best, size_t n, int bpp, int stride, void *stream)
+{
+    k_png_match<<<cdivu(n, 256), 256, 0, (cudaStream_t)stream>>>(d_filt, d_best, n, bpp, stride, PARSE_CHUNK_MAX);
+    return (int)cudaGetLastError();
+}
+int launch_png_parse(const uint32_t *d_best, const uint8_t *d_filt, size_t n, int chunk, uint32_t *d_tokens, uint32_t *d_counts, uint32_t *d_hist, void *stream)
+{
+    const size_t nchunks = (n + chunk - 1) / chunk;
+    k_png_parse<<<cdivu(nchunks, 64), 64, 0, (cudaStream_t)stream>>>(d_best, d_filt, n, chunk, d_tokens, d_counts, d_hist);
+    return (int)cudaGetLastError();
+}
+int launch_png_compact(const uint32_t *d_tokens, const uint32_t *d_counts, const uint32_t *d_offsets, size_t nchunks, int chunk, uint32_t *d_out, void *stream)
+{
+    k_png_compact<<<(unsigned)nchunks, 128, 0, (cudaStream_t)stream>>>(d_tokens, d_counts, d_offsets, chunk, d_out);
+    return (int)cudaGetLastError();
+}
+int launch_png_adler(const uint8_t *d_filt, size_t n, unsigned long long *d_sums, void *stream)
+{
+    k_png_adler<<<cdivu((n + 4095) / 4096, 64), 64, 0, (cudaStream_t)stream>>>(d_filt, n, d_sums);
+    return (int)cudaGetLastError();
+}
+int launch_png_probe(const uint8_t *d_raw, size_t npixels, int channels, uint32_t *d_flags, void *stream)
+{
+    k_png_probe<<<cdivu(npixels, 256), 256, 0, (cudaStream_t)stream>>>(d_raw, npixels, channels, d_flags);
+    return (int)cudaGetLastError();
+}
+int launch_png_repack(const uint8_t *d_raw, uint8_t *d_out, size_t npixels, int channels, int keep_mask, void *stream)
+{
+    int kept = 0; for (int c = 0; c < channels; c++) if (keep_mask & (1 << c)) kept++;
+    k_png_repack<<<cdivu(npixels, 256), 256, 0, (cudaStream_t)stream>>>(d_raw, d_out, npixels, channels, keep_mask, kept);
+    return (int)cudaGetLastError();
+}
+
+} // namespace b200

@@ -156,6 +156,22 @@ b200_status b200_jpeg_batch_download(b200_jpeg_batch *b, int index, int16_t *out
 b200_status b200_jpeg_batch_time(b200_jpeg_batch *b, int which, int iters, float *ms_per_run);
 void b200_jpeg_batch_destroy(b200_jpeg_batch *b);
 
+/* ---- PNG stage entry points (lossless path: libcaesium png::lossless -> oxipng, compressor.rs:428,436-437) ------- */
+/* Row-filter strategies (oxipng RowFilter order): 0 None 1 Sub 2 Up 3 Average 4 Paeth 5 MinSum 6 Entropy 7 Bigrams 8 BigEnt 9 Brute */
+/* host: parse + inflate + unfilter.  *raw (library-allocated) = height * row_bytes packed samples.  info: width, height,
+ * bit depth, colour type, bytes-per-pixel filter distance, row bytes. */
+typedef struct { uint32_t width, height; int32_t bit_depth, color_type, bpp; uint64_t row_bytes; } b200_png_info;
+b200_status b200_png_decode(const uint8_t *in, size_t in_len, b200_png_info *info, uint8_t **raw);
+/* device K6: filter raw[h][row_bytes] with `strategy` -> filtered[h][row_bytes + 1] (caller-allocated) */
+b200_status b200_png_filter(const uint8_t *raw, int h, int row_bytes, int bpp, int strategy, uint8_t *filtered);
+/* device K7: LZ77 tokens of a filtered stream (literal = byte; match = 0x80000000 | (len-3) << 16 | (dist-1)).
+ * *tokens library-allocated; hist[316] = litlen (286) + dist (30) symbol counts. */
+b200_status b200_png_lz77(const uint8_t *filtered, size_t n, int bpp, int stride, uint32_t **tokens, size_t *ntokens, uint32_t *hist);
+/* host: DEFLATE (dynamic Huffman) + zlib framing of a token stream; adler = Adler-32 of the bytes the tokens expand to */
+b200_status b200_png_deflate_tokens(const uint32_t *tokens, size_t ntokens, uint32_t adler, uint8_t **out, size_t *out_len);
+/* strategies tried for an optimisation level (returns the count; out[] holds up to 10) */
+int b200_png_level_strategies(int level, int *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -233,3 +233,45 @@ def jpeg_lossless(data, p):
     if lib().orc_jpeg_lossless(_buf(data), C.c_size_t(len(data)), C.byref(p), C.byref(outp), C.byref(outl), err):
         raise OracleError(err.value.decode())
     return _take(outp, outl)
+
+
+# ---- PNG lossless leg (oracle/png_oracle.c) -------------------------------------------------------------------
+PNG_STRATEGIES = {"none": 0, "sub": 1, "up": 2, "average": 3, "paeth": 4, "minsum": 5, "entropy": 6, "bigrams": 7, "bigent": 8, "brute": 9}
+
+
+def png_filter(raw, bpp, strategy):
+    """raw: uint8 [h, row_bytes] -> filtered uint8 [h, row_bytes + 1] (filter byte first)."""
+    raw = np.ascontiguousarray(raw, dtype=np.uint8)
+    h, rb = raw.shape
+    out = np.zeros((h, rb + 1), dtype=np.uint8)
+    lib().orc_png_filter(raw.ctypes.data_as(C.c_void_p), h, rb, bpp, int(strategy), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def png_unfilter(filt, bpp):
+    filt = np.ascontiguousarray(filt, dtype=np.uint8)
+    h, rb1 = filt.shape
+    out = np.zeros((h, rb1 - 1), dtype=np.uint8)
+    if lib().orc_png_unfilter(filt.ctypes.data_as(C.c_void_p), h, rb1 - 1, bpp, out.ctypes.data_as(C.c_void_p)):
+        raise OracleError("bad filter type")
+    return out
+
+
+def png_lz77(stream, bpp, stride):
+    """Filtered byte stream -> (tokens uint32[nt], hist uint32[316])."""
+    s = np.ascontiguousarray(stream, dtype=np.uint8).reshape(-1)
+    tok = np.zeros(s.size, dtype=np.uint32)
+    hist = np.zeros(316, dtype=np.uint32)
+    lib().orc_png_lz77.restype = C.c_size_t
+    nt = lib().orc_png_lz77(s.ctypes.data_as(C.c_void_p), C.c_size_t(s.size), bpp, stride, tok.ctypes.data_as(C.c_void_p), hist.ctypes.data_as(C.c_void_p))
+    return tok[:nt].copy(), hist
+
+
+def png_expand(tokens, n):
+    tokens = np.ascontiguousarray(tokens, dtype=np.uint32)
+    out = np.zeros(n, dtype=np.uint8)
+    lib().orc_png_expand.restype = C.c_size_t
+    got = lib().orc_png_expand(tokens.ctypes.data_as(C.c_void_p), C.c_size_t(tokens.size), out.ctypes.data_as(C.c_void_p), C.c_size_t(n))
+    if got != n:
+        raise OracleError("token stream does not expand to %d bytes" % n)
+    return out

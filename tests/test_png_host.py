@@ -1,0 +1,166 @@
+"""CPU tests of the PNG lossless leg: the oracle restatement (oracle/png_oracle.c) pinned against
+Pillow/libpng + zlib, and the product's HOST half (container parse, inflate, unfilter, DEFLATE writer) through the C-ABI.
+No device work is called here."""
+import zlib
+
+import numpy as np
+import pytest
+
+from pngutil import frame_png, idat_stream, pil_pixels, pil_png, synth
+
+CT = {1: 0, 2: 4, 3: 2, 4: 6}     # channels -> PNG colour type
+
+
+@pytest.mark.parametrize("channels", [1, 2, 3, 4])
+@pytest.mark.parametrize("strategy", range(10))
+def test_oracle_filter_is_lossless_and_libpng_agrees(O, channels, strategy):
+    img = synth(37, 53, channels, seed=strategy * 7 + channels, kind="photo" if strategy % 2 else "flat")
+    raw = img.reshape(37, 53 * channels)
+    filt = O.png_filter(raw, channels, strategy)
+    if strategy < 5:
+        assert (filt[:, 0] == strategy).all()
+    assert filt[:, 0].max() <= 4
+    assert np.array_equal(O.png_unfilter(filt, channels), raw)
+    # libpng (through Pillow) must reconstruct the same pixels from the oracle's filtered rows
+    png = frame_png(53, 37, 8, CT[channels], zlib.compress(filt.tobytes(), 6))
+    got = np.asarray(pil_pixels(png)).reshape(37, 53 * channels)
+    assert np.array_equal(got, raw)
+
+
+def test_oracle_heuristics_pick_the_expected_filter(O):
+    # a horizontal ramp is constant under Sub; a vertical ramp under Up
+    x = np.tile(np.arange(200, dtype=np.uint8) * 1, (20, 1))
+    y = np.tile((np.arange(20, dtype=np.uint8) * 3)[:, None], (1, 200))
+    for s in ("minsum", "entropy", "bigrams", "bigent", "brute"):
+        f = O.png_filter(x, 1, O.PNG_STRATEGIES[s])
+        assert (f[1:, 0] != 0).all(), s                # never None on a ramp (rows after the first may also pick Up/Paeth)
+    # constant rows: byte statistics cannot tell the filters apart except MinSum, which must leave None behind
+    assert (O.png_filter(y, 1, O.PNG_STRATEGIES["minsum"])[2:, 0] != 0).all()
+    # all-zero rows: every filter ties, the first (None) wins
+    z = np.zeros((5, 64), dtype=np.uint8)
+    for s in range(5, 10):
+        assert (O.png_filter(z, 1, s)[:, 0] == 0).all()
+
+
+@pytest.mark.parametrize("kind,channels", [("photo", 3), ("flat", 3), ("flat", 1), ("noise", 4), ("photo", 2)])
+def test_oracle_lz77_round_trips(O, kind, channels):
+    img = synth(64, 97, channels, seed=3, kind=kind)
+    filt = O.png_filter(img.reshape(64, -1), channels, O.PNG_STRATEGIES["paeth" if kind == "photo" else "none"])
+    stream = filt.reshape(-1)
+    tok, hist = O.png_lz77(stream, channels, filt.shape[1])
+    assert np.array_equal(O.png_expand(tok, stream.size), stream)
+    lits = tok[tok < 0x80000000]
+    assert hist[:256].sum() == lits.size and hist[257:286].sum() == (tok >= 0x80000000).sum() == hist[286:].sum()
+    if kind == "flat":
+        assert tok.size < stream.size // 4              # flat art must compress
+    if kind == "noise":
+        assert tok.size > stream.size * 0.9
+
+
+def test_host_deflate_writer_round_trips_through_zlib(L, O):
+    for kind, channels in (("photo", 3), ("flat", 4), ("noise", 1)):
+        img = synth(80, 120, channels, seed=11, kind=kind)
+        filt = O.png_filter(img.reshape(80, -1), channels, 4)
+        stream = filt.reshape(-1)
+        tok, _ = O.png_lz77(stream, channels, filt.shape[1])
+        z = L.png_deflate_tokens(tok, zlib.adler32(stream.tobytes()))
+        assert zlib.decompress(z) == stream.tobytes()
+        if kind != "noise":
+            assert len(z) < stream.size
+    # empty token stream is still a valid zlib stream
+    assert zlib.decompress(L.png_deflate_tokens(np.zeros(0, np.uint32), 1)) == b""
+
+
+def test_host_deflate_writer_many_blocks(L, O):
+    rng = np.random.default_rng(5)
+    stream = rng.integers(0, 7, 300000).astype(np.uint8)        # > 4 blocks of 65536 tokens
+    tok, _ = O.png_lz77(stream, 1, 1000)
+    z = L.png_deflate_tokens(tok, zlib.adler32(stream.tobytes()))
+    assert zlib.decompress(z) == stream.tobytes()
+
+
+@pytest.mark.parametrize("mode", ["L", "LA", "RGB", "RGBA", "P", "1", "I;16", "L2", "L4"])
+def test_host_png_decode_matches_pillow(L, mode):
+    from PIL import Image
+    rng = np.random.default_rng(9)
+    h, w = 45, 67
+    if mode in ("L", "LA", "RGB", "RGBA"):
+        ch = {"L": 1, "LA": 2, "RGB": 3, "RGBA": 4}[mode]
+        arr = synth(h, w, ch, seed=2)
+        png = pil_png(arr)
+        info, raw = L.png_decode(png)
+        assert (info.width, info.height, info.bit_depth, info.color_type, info.bpp, info.row_bytes) == (w, h, 8, CT[ch], ch, w * ch)
+        assert np.array_equal(raw, arr.reshape(h, w * ch))
+    elif mode == "P":
+        idx = rng.integers(0, 16, (h, w)).astype(np.uint8)
+        im = Image.fromarray(idx, mode="P"); im.putpalette([int(v) for v in rng.integers(0, 256, 48)])
+        info, raw = L.png_decode(pil_png(im))
+        assert info.color_type == 3
+        bits = info.bit_depth
+        # unpack and compare the indices
+        un = np.unpackbits(raw, axis=1).reshape(h, -1, bits)
+        vals = (un * (1 << np.arange(bits - 1, -1, -1))).sum(-1)[:, :w]
+        assert np.array_equal(vals, idx)
+    elif mode == "1":
+        b = rng.integers(0, 2, (h, w)).astype(bool)
+        info, raw = L.png_decode(pil_png(Image.fromarray(b)))
+        assert (info.bit_depth, info.color_type, info.row_bytes) == (1, 0, (w + 7) // 8)
+        assert np.array_equal(np.unpackbits(raw, axis=1)[:, :w].astype(bool), b)
+    elif mode == "I;16":
+        a = rng.integers(0, 65536, (h, w)).astype(np.uint16)
+        info, raw = L.png_decode(pil_png(Image.fromarray(a)))
+        assert (info.bit_depth, info.color_type, info.bpp, info.row_bytes) == (16, 0, 2, 2 * w)
+        assert np.array_equal(raw.reshape(h, w, 2)[:, :, 0].astype(np.uint16) * 256 + raw.reshape(h, w, 2)[:, :, 1], a)
+    else:
+        bits = int(mode[1])
+        vals = rng.integers(0, 1 << bits, (h, w)).astype(np.uint8)
+        packed = np.packbits(np.unpackbits(vals[:, :, None], axis=2)[:, :, 8 - bits:].reshape(h, -1), axis=1)
+        rows = np.concatenate([np.zeros((h, 1), np.uint8), packed], axis=1)
+        png = frame_png(w, h, bits, 0, zlib.compress(rows.tobytes()))
+        info, raw = L.png_decode(png)
+        assert (info.bit_depth, info.bpp, info.row_bytes) == (bits, 1, packed.shape[1])
+        assert np.array_equal(raw, packed)
+
+
+def test_host_png_decode_every_filter_type_and_split_idat(L, O):
+    import struct
+    from pngutil import chunk
+    img = synth(33, 41, 3, seed=4)
+    raw = img.reshape(33, -1)
+    # rows cycle through the five filter types; IDAT split into many small chunks; stored + fixed + dynamic blocks
+    rows = np.stack([O.png_filter(raw, 3, y % 5)[y] for y in range(33)])
+    for level in (0, 1, 9):
+        z = zlib.compress(rows.tobytes(), level)
+        parts = b"".join(chunk(b"IDAT", z[i:i + 100]) for i in range(0, len(z), 100))
+        png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 41, 33, 8, 2, 0, 0, 0)) + parts + chunk(b"IEND", b"")
+        _, got = L.png_decode(png)
+        assert np.array_equal(got, raw)
+
+
+def test_host_png_decode_rejects_bad_input(L):
+    good = pil_png(synth(16, 16, 3))
+    flipped = good[:60] + bytes([good[60] ^ 0x55]) + good[61:]
+    for bad, code in ((good[:40], 4), (flipped, 4), (b"\x89PNG\r\n\x1a\n" + b"\0" * 40, 4)):
+        with pytest.raises(L.B200Error) as e:
+            L.png_decode(bad)
+        assert e.value.code == code, e.value
+    # Adam7: hand-made header with the interlace byte set must be refused as unsupported (code 3), not mis-decoded
+    import struct
+    from pngutil import chunk
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 4, 4, 8, 0, 0, 0, 1)) + chunk(b"IDAT", zlib.compress(b"\0" * 64)) + chunk(b"IEND", b"")
+    with pytest.raises(L.B200Error) as e:
+        L.png_decode(png)
+    assert e.value.code == 3
+
+
+def test_png_level_strategy_sets(L):
+    assert L.png_level_strategies(0) == [0]
+    for lvl in range(1, 7):
+        s = L.png_level_strategies(lvl)
+        assert s[0] == 0 and len(set(s)) == len(s) and all(0 <= v <= 9 for v in s)
+    assert len(L.png_level_strategies(6)) > len(L.png_level_strategies(3)) > len(L.png_level_strategies(1))
+
+
+def test_idat_helper_on_pillow_file():
+    ihdr, idat, order = idat_stream(pil_png(synth(8, 8, 3)))
+    assert ihdr[:2] == (8, 8) and order[0] == b"IHDR" and order[-1] == b"IEND" and len(zlib.decompress(idat)) == 8 * 25
