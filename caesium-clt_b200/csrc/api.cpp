@@ -125,7 +125,28 @@ b200_status jpeg_compress(const uint8_t *in, size_t in_len, const b200_params *p
     const JpegGeom &gin = rd.geom();
     JpegWriteOptions wo; wo.progressive = p->jpeg_progressive != 0; wo.keep_metadata = p->keep_metadata != 0; wo.preserve_icc = p->jpeg_preserve_icc != 0;
     if (p->jpeg_optimize) {
-        // libcaesium jpeg::lossless: coefficient-domain transcode, nothing numeric to do on the device
+        // libcaesium jpeg::lossless: coefficient-domain transcode.  Baseline single-scan inputs are entropy-decoded and
+        // re-encoded (optimal tables, progressive script) by the device coders; the coefficients never leave HBM.
+        // Everything else (progressive input, no device) is transcoded on the calling thread -- there is no arithmetic
+        // on this path, only entropy coding.
+        std::string derr;
+        JpegReader::DeviceScan ds;
+        if (g_entropy_mode.load() < 0) {
+            const char *e = getenv("B200_ENTROPY");
+            g_entropy_mode.store(!e ? 3 : !strcmp(e, "host") ? 0 : !strcmp(e, "gpuenc") ? 1 : !strcmp(e, "gpudec") ? 2 : 3);
+        }
+        if (g_entropy_mode.load() == 3 && rd.device_decodable(ds) && ensure_runtime(derr)) {
+            if (Slot *s = slot_acquire(prefer_dev < 0 ? runtime_next_device() : prefer_dev, derr)) {
+                bool done = false;
+                wo.copy_jfif = true;
+                if (s->ensure((size_t)gin.total_coefs * 2, 0, 0, 1 << 14, derr) && slot_gpu_decode(s, rd, ds, derr) == 0 &&
+                    slot_gpu_encode(s, gin, wo.progressive, derr, true))
+                    done = jpeg_assemble(gin, wo, &rd.meta(), s->enc->results.data(), (int)s->enc->results.size(), out, derr);
+                slot_release(s);
+                if (done) return ok_status();
+                out.clear();
+            }
+        }
         std::vector<int16_t> coefs((size_t)gin.total_coefs);
         if (!rd.decode(coefs.data(), err)) return make_status(B200_ERR_CORRUPT_INPUT, err);
         jpeg_fill_dummy_blocks(gin, coefs.data());
@@ -229,8 +250,10 @@ void jpeg_compress_group(const uint8_t *const *in, const size_t *in_len, const s
     }
     if (members.size() < 2) return;
     const JpegGeom &gin0 = rd[members[0]]->geom();
+    const bool lossless = p->jpeg_optimize != 0;          // jpeg::lossless: decode -> encode, no transform, per-image tables kept
     JpegGeom gout;
-    if (!jpeg_output_geom(gin0, (int)p->jpeg_quality, (int)p->jpeg_chroma_subsampling, gout, err)) return;
+    if (lossless) gout = gin0;
+    else if (!jpeg_output_geom(gin0, (int)p->jpeg_quality, (int)p->jpeg_chroma_subsampling, gout, err)) return;
     Slot *s = slot_acquire(dev, err);
     if (!s) return;
     const int Kg = (int)members.size();
@@ -249,17 +272,18 @@ void jpeg_compress_group(const uint8_t *const *in, const size_t *in_len, const s
         tm.lap(0);
         if (!slot_decode_group(s, items, err)) break;
         tm.lap(1);
-        if (!slot_transform_group(s, gins.data(), gout, L, err)) break;
+        if (!lossless && !slot_transform_group(s, gins.data(), gout, L, err)) break;
         tm.lap(3);
         JpegWriteOptions wo; wo.progressive = p->jpeg_progressive != 0; wo.keep_metadata = p->keep_metadata != 0; wo.preserve_icc = p->jpeg_preserve_icc != 0;
-        if (!slot_encode_group(s, gout, wo.progressive, L, err)) break;
+        wo.copy_jfif = lossless;
+        if (!slot_encode_group(s, gout, wo.progressive, L, err, lossless)) break;
         tm.lap(4);
         const int spi = s->enc->plan.scans_per_image;
         for (int m = 0; m < Kg; m++) {
             const int k = members[m], i = idx[k];
             if (items[m].result != GpuDecoder::OK) continue;          // not converged: the per-image path decodes it on the host
             out[i] = nullptr; out_len[i] = 0;
-            if (!jpeg_assemble_malloc(gout, wo, &rd[k]->meta(), s->enc->results.data() + (size_t)m * spi, spi, &out[i], &out_len[i], err)) status[i] = make_status(B200_ERR_INVALID_ARGUMENT, err);
+            if (!jpeg_assemble_malloc(lossless ? rd[k]->geom() : gout, wo, &rd[k]->meta(), s->enc->results.data() + (size_t)m * spi, spi, &out[i], &out_len[i], err)) status[i] = make_status(B200_ERR_INVALID_ARGUMENT, err);
             else status[i] = ok_status();
             done[k] = 1;
         }
@@ -404,7 +428,7 @@ int b200_compress_batch(const uint8_t *const *in, const size_t *in_len, int n, c
     // sequence (decode rounds, transform, encode passes) for the whole group instead of one per image.  Images that do not
     // fit the group path (other formats, progressive input, resize, odd one out in shape) go through the per-image path.
     int K = 8; { const char *e = getenv("B200_MEGABATCH"); if (e) K = std::max(1, std::min(64, atoi(e))); }
-    const bool grouped = runtime_device_count() > 0 && g_entropy_mode.load() == 3 && K > 1 && !params->jpeg_optimize && !params->width && !params->height;
+    const bool grouped = runtime_device_count() > 0 && g_entropy_mode.load() == 3 && K > 1 && ((!params->width && !params->height) || params->jpeg_optimize);
     auto one = [&](int i, int dev) {
         out[i] = nullptr; out_len[i] = 0;
         try {

@@ -308,11 +308,12 @@ bool slot_decode_group(Slot *s, std::vector<GpuDecoder::Item> &items, std::strin
     return s->dec->decode(items, s->stream, err);
 }
 
-bool slot_encode_group(Slot *s, const JpegGeom &gout, bool progressive, const GroupLayout &L, std::string &err)
+bool slot_encode_group(Slot *s, const JpegGeom &gout, bool progressive, const GroupLayout &L, std::string &err, bool from_input)
 {
     if (!s->enc) s->enc = new GpuEncoder();
     std::vector<int16_t *> bases((size_t)L.K);
-    for (int k = 0; k < L.K; k++) bases[k] = reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(s->d_out) + L.out_stride * k);
+    for (int k = 0; k < L.K; k++) bases[k] = from_input ? reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(s->d_in) + L.in_stride * k)
+                                                        : reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(s->d_out) + L.out_stride * k);
     return s->enc->encode(gout, progressive, bases.data(), L.K, s->stream, true, err);
 }
 
@@ -340,10 +341,10 @@ bool slot_upload_out_coefs(Slot *s, size_t bytes, std::string &err)
     return true;
 }
 
-bool slot_gpu_encode(Slot *s, const JpegGeom &gout, bool progressive, std::string &err)
+bool slot_gpu_encode(Slot *s, const JpegGeom &gout, bool progressive, std::string &err, bool from_input)
 {
     if (!s->enc) s->enc = new GpuEncoder();
-    int16_t *base = s->d_out;
+    int16_t *base = from_input ? s->d_in : s->d_out;
     return s->enc->encode(gout, progressive, &base, 1, s->stream, true, err);
 }
 

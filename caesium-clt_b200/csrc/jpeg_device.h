@@ -73,11 +73,12 @@ struct GroupLayout { int K = 0; size_t in_stride = 0, out_stride = 0, scratch_st
 bool slot_group_layout(Slot *s, const JpegGeom &gin, const JpegGeom &gout, int K, GroupLayout &L, std::string &err);   // sizes + ensure()
 bool slot_decode_group(Slot *s, std::vector<GpuDecoder::Item> &items, std::string &err);      // items[k].d_coefs = d_in + k * in_stride
 bool slot_transform_group(Slot *s, const JpegGeom *const *gins, const JpegGeom &gout, const GroupLayout &L, std::string &err);
-bool slot_encode_group(Slot *s, const JpegGeom &gout, bool progressive, const GroupLayout &L, std::string &err);      // results in s->enc->results
+// results in s->enc->results; from_input = encode the coefficients in d_in (lossless transcode) instead of d_out
+bool slot_encode_group(Slot *s, const JpegGeom &gout, bool progressive, const GroupLayout &L, std::string &err, bool from_input = false);
 // H2D of s->h_out into s->d_out (entry point that encodes caller-supplied coefficients on the device)
 bool slot_upload_out_coefs(Slot *s, size_t bytes, std::string &err);
 // Entropy-code the output coefficients sitting in s->d_out on the device; result in s->enc->results
-bool slot_gpu_encode(Slot *s, const JpegGeom &gout, bool progressive, std::string &err);
+bool slot_gpu_encode(Slot *s, const JpegGeom &gout, bool progressive, std::string &err, bool from_input = false);
 // Resize path (CSParameters.width/height): gout carries the TARGET dimensions; decode -> RGB -> Lanczos3 -> YCbCr -> encode.
 bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err, bool download = true, bool upload = true);
 // Same front end, but stop after IDCT + upsample and copy planar full-res samples into `planes` (host).

@@ -117,7 +117,7 @@ __global__ void k_png_match(const uint8_t *__restrict__ s, uint32_t *__restrict_
             if (d < 1 || d > 32768 || (size_t)d > i) continue;
             if (bl > 0 && s[i + bl] != s[i + bl - d]) continue;      // cannot beat the current best
             const int l = match_len(s, i, d, maxlen);
-            if (l > bl || (l == bl && l >= 3 && d < bd)) { bl = l; bd = d; }
+            if (l > bl) { bl = l; bd = d; }                           // earlier candidate wins ties
             if (bl == maxlen) break;
         }
     }

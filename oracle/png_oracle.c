@@ -124,8 +124,8 @@ static int dist_symbol(int d)
     return s;
 }
 
-/* longest match at position i among the candidate distances, confined to i's 4 KiB chunk; ties -> smaller distance,
- * except that candidates are visited in a fixed order and a later one must be strictly longer or equal-and-nearer */
+/* longest match at position i among the candidate distances, confined to i's 4 KiB chunk; candidates are visited in a
+ * fixed order and a later one must be strictly longer to replace an earlier one */
 static uint32_t best_match(const uint8_t *s, size_t n, size_t i, int bpp, int stride)
 {
     size_t chunk_end = (i / CHUNK + 1) * (size_t)CHUNK; if (chunk_end > n) chunk_end = n;
@@ -137,7 +137,7 @@ static uint32_t best_match(const uint8_t *s, size_t n, size_t i, int bpp, int st
         int d = cand[c], l = 0;
         if (d < 1 || d > 32768 || (size_t)d > i) continue;
         while (l < maxlen && s[i + l] == s[i + l - d]) l++;
-        if (l > bl || (l == bl && l >= 3 && d < bd)) { bl = l; bd = d; }
+        if (l > bl) { bl = l; bd = d; }
         if (bl == maxlen) break;
     }
     return bl >= 3 ? ((uint32_t)bl << 16) | (uint32_t)bd : 0;

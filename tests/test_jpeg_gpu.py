@@ -189,6 +189,21 @@ def test_batch_matches_single(L, O, golden):
         assert out == O.jpeg_lossy(d, O.params(80, 420, True))
 
 
+@pytest.mark.parametrize("prog", [True, False])
+def test_lossless_transcode_on_device_matches_oracle(L, O, golden, prog):
+    """jpeg::lossless (BASELINE configs[2]): device entropy decode -> device entropy encode, bytes == oracle transcode;
+    single calls and the megabatch path, mixed with inputs that take the host route (progressive)."""
+    p = _params(L, 80, 0, prog)
+    p.jpeg_optimize = 1
+    p.keep_metadata = 1
+    for name in INPUTS:
+        assert L.compress_in_memory(golden(name), p) == O.jpeg_lossless(golden(name), O.params(80, 0, prog, keep_metadata=True)), name
+    datas = [golden("in_420_base_355x237.jpg")] * 5 + [golden("in_420_prog_355x237.jpg")] + [golden("in_420_base_640x480.jpg")] * 4
+    for d, (out, code, msg) in zip(datas, L.compress_batch(datas, p, n_threads=4)):
+        assert code == 0, msg
+        assert out == O.jpeg_lossless(d, O.params(80, 0, prog, keep_metadata=True))
+
+
 def test_megabatch_device_resident(L, O, golden):
     data = golden("in_420_base_640x480.jpg")
     lay, co = L.jpeg_decode_coefficients(data)
