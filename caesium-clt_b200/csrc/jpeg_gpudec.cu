@@ -71,10 +71,14 @@ __global__ void __launch_bounds__(64) k_gd_round0(const DecImage *__restrict__ i
 // thread i restarts from exit i-1 of the previous round; if that exit did not change last round, neither can ours
 __global__ void __launch_bounds__(64) k_gd_round(const DecImage *__restrict__ imgs, const uint8_t *__restrict__ stream_all, const DecTable *__restrict__ tabs_all,
                                                  const DecState *__restrict__ A, DecState *__restrict__ B, const uint8_t *__restrict__ chg_in, uint8_t *__restrict__ chg_out,
-                                                 uint32_t *__restrict__ nblk, uint32_t *__restrict__ any_changed /*[image]*/)
+                                                 uint32_t *__restrict__ nblk, uint32_t *__restrict__ any_changed /*[image]*/,
+                                                 const uint32_t *__restrict__ prev_changed /*[image] of the round before, or null*/)
 {
     __shared__ DecShared sh;
     __shared__ int work;
+    // An image whose previous round changed nothing has settled: both state buffers are identical from then on, so the
+    // remaining rounds of the launch group are empty for it (the host only looks at the flags after the whole group).
+    if (prev_changed && prev_changed[blockIdx.y] == 0) return;
     const DecImage &im = imgs[blockIdx.y];
     const uint32_t nsub = im.g.nsub;
     if (blockIdx.x * blockDim.x >= nsub) return;
@@ -255,7 +259,7 @@ bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &er
     while (nconv < N && rounds < MAX_ROUNDS) {
         const int first_round = rounds;
         for (int r = 0; r < ROUNDS_PER_GROUP && rounds < MAX_ROUNDS; r++, rounds++) {
-            k_gd_round<<<gs, 64, 0, st>>>(dI, d_stream, dT, A, B, cA, cB, d_nblk, dF + (size_t)rounds * N);
+            k_gd_round<<<gs, 64, 0, st>>>(dI, d_stream, dT, A, B, cA, cB, d_nblk, dF + (size_t)rounds * N, rounds ? dF + (size_t)(rounds - 1) * N : nullptr);
             std::swap(A, B); std::swap(cA, cB);
         }
         CUD(cudaMemcpyAsync(hF + (size_t)first_round * N, dF + (size_t)first_round * N, (size_t)4 * N * (rounds - first_round), cudaMemcpyDeviceToHost, st));
