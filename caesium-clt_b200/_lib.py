@@ -67,6 +67,7 @@ _SYMBOLS = [
     "b200_jpeg_batch_create", "b200_jpeg_batch_upload", "b200_jpeg_batch_run", "b200_jpeg_batch_download",
     "b200_jpeg_batch_time", "b200_jpeg_batch_destroy", "b200_jpeg_encode_coefficients_device",
     "b200_png_decode", "b200_png_filter", "b200_png_lz77", "b200_png_deflate_tokens", "b200_png_level_strategies",
+    "b200_webp_encode_rgb", "b200_webp_write_levels", "b200_webp_qindex",
 ]
 
 
@@ -82,7 +83,8 @@ def lib():
                   "b200_jpeg_decode_coefficients", "b200_jpeg_output_layout", "b200_jpeg_requantize",
                   "b200_jpeg_encode_coefficients", "b200_jpeg_decode_planes", "b200_jpeg_batch_create",
                   "b200_jpeg_batch_upload", "b200_jpeg_batch_run", "b200_jpeg_batch_download", "b200_jpeg_batch_time",
-                  "b200_png_decode", "b200_png_filter", "b200_png_lz77", "b200_png_deflate_tokens"):
+                  "b200_png_decode", "b200_png_filter", "b200_png_lz77", "b200_png_deflate_tokens",
+                  "b200_webp_encode_rgb", "b200_webp_write_levels", "b200_jpeg_encode_coefficients_device"):
             getattr(L, f).restype = Status
         L.b200_version.restype = C.c_char_p
         L.b200_sniff_format.restype = C.c_uint32
@@ -267,6 +269,35 @@ def png_level_strategies(level):
     out = (C.c_int * 10)()
     n = lib().b200_png_level_strategies(int(level), out)
     return list(out[:n])
+
+
+# ---- WebP stage entry points (lossy VP8) ---------------------------------------------------------------------
+def webp_encode_rgb(rgb, quality, want_stage=False):
+    """Device K8 + host writer: planar uint8 [3, h, w] -> .webp bytes (and, if asked, (levels [nmb,25,16], modes [nmb,4]))."""
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    _, h, w = rgb.shape
+    nmb = ((w + 15) // 16) * ((h + 15) // 16)
+    levels = np.zeros((nmb, 25, 16), np.int16) if want_stage else None
+    modes = np.zeros((nmb, 4), np.uint8) if want_stage else None
+    outp, outl = C.POINTER(C.c_uint8)(), C.c_size_t()
+    _check(lib().b200_webp_encode_rgb(rgb.ctypes.data_as(C.c_void_p), w, h, int(quality), C.byref(outp), C.byref(outl),
+                                      levels.ctypes.data_as(C.c_void_p) if want_stage else None, modes.ctypes.data_as(C.c_void_p) if want_stage else None))
+    data = _take(outp, outl)
+    return (data, levels, modes) if want_stage else data
+
+
+def webp_write_levels(w, h, quality, levels, modes):
+    """Host only: boolean-code a stage view (layout of webp_encode_rgb) into a .webp file."""
+    levels = np.ascontiguousarray(levels, dtype=np.int16); modes = np.ascontiguousarray(modes, dtype=np.uint8)
+    outp, outl = C.POINTER(C.c_uint8)(), C.c_size_t()
+    _check(lib().b200_webp_write_levels(int(w), int(h), int(quality), levels.ctypes.data_as(C.c_void_p), modes.ctypes.data_as(C.c_void_p), C.byref(outp), C.byref(outl)))
+    return _take(outp, outl)
+
+
+def webp_qindex(quality):
+    f = (C.c_int * 6)()
+    q = lib().b200_webp_qindex(int(quality), f)
+    return q, list(f)
 
 
 def component_view(layout, coefs, c):

@@ -20,6 +20,8 @@
 #include "resize_kernels.h"
 #include "png_host.h"
 #include "png_device.h"
+#include "vp8_host.h"
+#include "webp_device.h"
 
 using namespace b200;
 
@@ -318,6 +320,81 @@ b200_status png_compress(const uint8_t *in, size_t in_len, const b200_params *p,
     return ok_status();
 }
 
+// ---- conversion to WebP (lossy VP8) ----------------------------------------------------------------------------------
+// libcaesium convert: decode -> (resize) -> webp::compress at parameters.webp.quality.  JPEG sources are decoded on the
+// device (entropy decode, IDCT, upsample, YCbCr -> RGB, Lanczos3 when width/height are set) and never leave HBM before K8.
+b200_status jpeg_to_webp(const uint8_t *in, size_t in_len, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
+{
+    std::string err;
+    JpegReader rd(in, in_len);
+    if (!rd.read_header(err)) return make_status(B200_ERR_CORRUPT_INPUT, err);
+    const JpegGeom &gin = rd.geom();
+    if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
+    uint32_t nw = (uint32_t)gin.width, nh = (uint32_t)gin.height;
+    if (p->width || p->height) compute_resize_dimensions((uint32_t)gin.width, (uint32_t)gin.height, p->width, p->height, nw, nh);
+    if (nw == 0 || nh == 0 || nw > 16383 || nh > 16383) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid target dimensions for WebP");
+    JpegGeom gout = gin; gout.width = (int)nw; gout.height = (int)nh; gout.finalize();
+    if (g_entropy_mode.load() < 0) {
+        const char *e = getenv("B200_ENTROPY");
+        g_entropy_mode.store(!e ? 3 : !strcmp(e, "host") ? 0 : !strcmp(e, "gpuenc") ? 1 : !strcmp(e, "gpudec") ? 2 : 3);
+    }
+    Slot *s = slot_acquire(prefer_dev < 0 ? runtime_next_device() : prefer_dev, err);
+    if (!s) return make_status(B200_ERR_CUDA, err);
+    b200_status st = ok_status();
+    do {
+        if (!s->ensure((size_t)gin.total_coefs * 2, (size_t)gout.total_coefs * 2, 0, 1 << 14, err)) { st = make_status(B200_ERR_OUT_OF_MEMORY, err); break; }
+        bool on_device = false;
+        JpegReader::DeviceScan ds;
+        if ((g_entropy_mode.load() & 2) && rd.device_decodable(ds)) {
+            const int r = slot_gpu_decode(s, rd, ds, err);
+            if (r == 0) on_device = true; else if (r != 1) { st = make_status(B200_ERR_CUDA, err); break; }
+        }
+        if (!on_device && !rd.decode(s->h_in, err)) { st = make_status(B200_ERR_CORRUPT_INPUT, err); break; }
+        uint8_t *rgb[3] = {nullptr, nullptr, nullptr};
+        if (!slot_transform_resized(s, gin, gout, err, false, !on_device, rgb)) { st = make_status(B200_ERR_CUDA, err); break; }
+        if (!s->webp) s->webp = new WebpDevice();
+        if (!s->webp->encode_planes(rgb[0], rgb[1], rgb[2], (int)nw, (int)nh, (int)p->webp_quality, s->stream, out, err)) { st = make_status(B200_ERR_CUDA, err); break; }
+    } while (0);
+    slot_release(s);
+    return st;
+}
+
+// PNG source: samples are expanded to 8-bit RGB on the host (palette, grey, 16-bit -> high byte; alpha is dropped: the VP8X
+// alpha plane is outside this path) and go through the same K8.
+b200_status png_to_webp(const uint8_t *in, size_t in_len, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
+{
+    if (p->width || p->height) return make_status(B200_ERR_UNSUPPORTED, "PNG resize is outside the GPU path (route to caesium::convert_in_memory)");
+    std::string err;
+    PngInfo info; std::vector<uint8_t> raw;
+    if (!png_decode(in, in_len, false, info, raw, err)) return make_status(err.find("interlace") != std::string::npos ? B200_ERR_UNSUPPORTED : B200_ERR_CORRUPT_INPUT, err);
+    const size_t w = info.width, h = info.height, n = w * h;
+    if (w > 16383 || h > 16383) return make_status(B200_ERR_INVALID_ARGUMENT, "image too large for WebP");
+    std::vector<uint8_t> rgb(3 * n);
+    const int bd = info.bit_depth, ct = info.color_type;
+    for (size_t y = 0; y < h; y++) {
+        const uint8_t *row = raw.data() + y * info.row_bytes;
+        for (size_t x = 0; x < w; x++) {
+            uint8_t r, g, b;
+            if (ct == 2 || ct == 6) { const size_t o = x * info.channels * (bd / 8); r = row[o]; g = row[o + bd / 8]; b = row[o + 2 * (bd / 8)]; }
+            else {
+                unsigned v;
+                if (bd >= 8) v = row[x * info.channels * (bd / 8)];
+                else v = (row[(x * bd) >> 3] >> (8 - bd - ((x * bd) & 7))) & ((1u << bd) - 1);
+                if (ct == 3) { if (3 * v + 2 < info.plte.size()) { r = info.plte[3 * v]; g = info.plte[3 * v + 1]; b = info.plte[3 * v + 2]; } else r = g = b = 0; }
+                else { if (bd < 8) v = v * 255 / ((1u << bd) - 1); r = g = b = (uint8_t)v; }
+            }
+            rgb[y * w + x] = r; rgb[n + y * w + x] = g; rgb[2 * n + y * w + x] = b;
+        }
+    }
+    if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
+    Slot *s = slot_acquire(prefer_dev < 0 ? runtime_next_device() : prefer_dev, err);
+    if (!s) return make_status(B200_ERR_CUDA, err);
+    if (!s->webp) s->webp = new WebpDevice();
+    const bool ok = s->webp->encode_host_rgb(rgb.data(), (int)w, (int)h, (int)p->webp_quality, s->stream, out, err);
+    slot_release(s);
+    return ok ? ok_status() : make_status(B200_ERR_CUDA, err);
+}
+
 b200_status compress_dispatch(const uint8_t *in, size_t in_len, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
 {
     switch (b200_sniff_format(in, in_len)) {
@@ -379,7 +456,16 @@ b200_status b200_convert_in_memory(const uint8_t *in, size_t in_len, const b200_
     uint32_t src = b200_sniff_format(in, in_len);
     if (src == B200_FMT_UNKNOWN) return make_status(B200_ERR_UNKNOWN_FORMAT, "Unknown file type");
     if (src == fmt) return make_status(B200_ERR_SAME_FORMAT, "Cannot convert to the same format");
-    return make_status(B200_ERR_UNSUPPORTED, "format conversion is not implemented on the GPU path yet");
+    if (fmt != B200_FMT_WEBP) return make_status(B200_ERR_UNSUPPORTED, "only conversion to WebP is implemented on the GPU path (route to caesium::convert_in_memory)");
+    if (params->webp_lossless) return make_status(B200_ERR_UNSUPPORTED, "lossless WebP (VP8L) is outside the GPU path (route to caesium::convert_in_memory)");
+    try {
+        std::vector<uint8_t> v;
+        b200_status s = src == B200_FMT_JPEG ? jpeg_to_webp(in, in_len, params, -1, v)
+                      : src == B200_FMT_PNG ? png_to_webp(in, in_len, params, -1, v)
+                      : make_status(B200_ERR_UNSUPPORTED, "conversion from this format is outside the GPU path (route to caesium::convert_in_memory)");
+        if (s.code) return s;
+        return give(v, out, out_len);
+    } catch (const std::exception &e) { return make_status(B200_ERR_OUT_OF_MEMORY, e.what()); }
 }
 
 b200_status b200_compress_to_size_in_memory(const uint8_t *in, size_t in_len, b200_params *params, size_t max_output_size, uint8_t return_smallest,
@@ -648,6 +734,35 @@ b200_status b200_png_deflate_tokens(const uint32_t *tokens, size_t ntokens, uint
     memcpy(*out, z.data(), z.size()); *out_len = z.size();
     return ok_status();
 }
+// ---- WebP stage entry points -----------------------------------------------------------------------------------------
+b200_status b200_webp_encode_rgb(const uint8_t *rgb, int w, int h, int quality, uint8_t **out, size_t *out_len, int16_t *levels, uint8_t *modes)
+{
+    if (!rgb || !out || !out_len || w < 1 || h < 1 || w > 16383 || h > 16383) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid argument");
+    *out = nullptr; *out_len = 0;
+    std::string err;
+    if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
+    Slot *s = slot_acquire(runtime_next_device(), err);
+    if (!s) return make_status(B200_ERR_CUDA, err);
+    if (!s->webp) s->webp = new WebpDevice();
+    std::vector<uint8_t> v;
+    const bool ok = s->webp->encode_host_rgb(rgb, w, h, quality, s->stream, v, err, levels, modes);
+    slot_release(s);
+    return ok ? give(v, out, out_len) : make_status(B200_ERR_CUDA, err);
+}
+b200_status b200_webp_write_levels(int w, int h, int quality, const int16_t *levels, const uint8_t *modes, uint8_t **out, size_t *out_len)
+{
+    if (!levels || !modes || !out || !out_len) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    std::vector<uint8_t> v;
+    if (!vp8_write_file(w, h, vp8_qindex(quality < 0 ? 0 : quality > 100 ? 100 : quality), levels, modes, v)) return make_status(B200_ERR_INVALID_ARGUMENT, "frame cannot be written as VP8");
+    return give(v, out, out_len);
+}
+int b200_webp_qindex(int quality, int factors[6])
+{
+    const int q = vp8_qindex(quality < 0 ? 0 : quality > 100 ? 100 : quality);
+    if (factors) vp8_quant_factors(q, factors);
+    return q;
+}
+
 int b200_png_level_strategies(int level, int *out)
 {
     const std::vector<int> v = png_level_strategies(level < 0 ? 0 : level > 6 ? 6 : level);

@@ -14,6 +14,7 @@
 #include "jpeg_gpuenc.h"
 #include "jpeg_gpudec.h"
 #include "png_device.h"
+#include "webp_device.h"
 
 namespace b200 {
 
@@ -153,7 +154,7 @@ void runtime_shutdown()
         cudaSetDevice(d->ordinal);
         for (Slot *s : d->free_slots) {
             if (s->stream) cudaStreamDestroy((cudaStream_t)s->stream);
-            cudaFreeHost(s->h_in); cudaFreeHost(s->h_out); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_scratch); cudaFreeHost(s->h_par); cudaFree(s->d_par); delete s->enc; delete s->dec; delete s->png;
+            cudaFreeHost(s->h_in); cudaFreeHost(s->h_out); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_scratch); cudaFreeHost(s->h_par); cudaFree(s->d_par); delete s->enc; delete s->dec; delete s->png; delete s->webp;
             delete s;
         }
         delete d;
@@ -386,7 +387,7 @@ bool slot_decode_planes(Slot *s, const JpegGeom &gin, uint8_t *planes, std::stri
 }
 
 // ---- resize path: decode -> (YCbCr->RGB) -> Lanczos3 -> (RGB->YCbCr) -> encode side --------------------------------
-bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err, bool download, bool upload)
+bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err, bool download, bool upload, uint8_t **rgb_out)
 {
     const int W = gin.width, H = gin.height, NW = gout.width, NH = gout.height, nc = gin.ncomp;
     if (gout.ncomp != nc) { err = "component count mismatch"; return false; }
@@ -460,6 +461,7 @@ bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, 
         if (!chk(launch_resize_h(tmp, W, rz[c], NW, NH, NW, reinterpret_cast<const int *>(s->d_par + lh), reinterpret_cast<const int *>(s->d_par + chh),
                                  reinterpret_cast<const float *>(s->d_par + wh), ah.cap, st), "resize_h")) return false;
     }
+    if (rgb_out) { rgb_out[0] = rz[0]; rgb_out[1] = nc == 3 ? rz[1] : rz[0]; rgb_out[2] = nc == 3 ? rz[2] : rz[0]; return true; }
     if (nc == 3 && !chk(launch_rgb_to_ycc(rz[0], rz[1], rz[2], (size_t)NW * NH, st), "rgb_to_ycc")) return false;
     if (!chk(launch_downsample(p_down, nc, wl.max_dn_w, wl.max_dn_h, st), "downsample")) return false;
     if (!chk(launch_fdct_plane(p_fdct, nc, wl.max_fdct, st), "fdct")) return false;

@@ -51,6 +51,7 @@ struct Slot {
     class GpuEncoder *enc = nullptr;                                                     // device entropy encoder (lazy)
     class GpuDecoder *dec = nullptr;                                                     // device entropy decoder (lazy)
     struct PngDevice *png = nullptr;                                                     // lossless PNG state (lazy, png_device.cu)
+    struct WebpDevice *webp = nullptr;                                                   // WebP / VP8 state (lazy, webp_device.cu)
     bool ensure(size_t in_bytes, size_t out_bytes, size_t scratch_bytes, size_t par_bytes, std::string &err);
     bool ensure_device(size_t in_bytes, size_t out_bytes, size_t scratch_bytes, size_t par_bytes, std::string &err);
 };
@@ -80,7 +81,10 @@ bool slot_upload_out_coefs(Slot *s, size_t bytes, std::string &err);
 // Entropy-code the output coefficients sitting in s->d_out on the device; result in s->enc->results
 bool slot_gpu_encode(Slot *s, const JpegGeom &gout, bool progressive, std::string &err, bool from_input = false);
 // Resize path (CSParameters.width/height): gout carries the TARGET dimensions; decode -> RGB -> Lanczos3 -> YCbCr -> encode.
-bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err, bool download = true, bool upload = true);
+// rgb_out != nullptr: stop after the resize and hand back the three device planes (R, G, B of the TARGET size, pitch = target
+// width; a greyscale source returns its single plane three times) -- the front end of the format-conversion paths.
+bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err, bool download = true, bool upload = true,
+                            uint8_t **rgb_out = nullptr);
 // Same front end, but stop after IDCT + upsample and copy planar full-res samples into `planes` (host).
 bool slot_decode_planes(Slot *s, const JpegGeom &gin, uint8_t *planes, std::string &err);
 

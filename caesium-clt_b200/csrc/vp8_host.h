@@ -1,0 +1,19 @@
+// vp8_host.h -- host half of the WebP (lossy VP8) leg: quality -> quantiser mapping, the boolean entropy coder, header / mode /
+// token partitions (RFC 6386 sections 7, 9, 13, 19) and the RIFF container, around the levels and modes K8 leaves in HBM.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <vector>
+
+namespace b200 {
+
+// libwebp's quality (0..100) -> base quantiser index curve (one segment)
+int vp8_qindex(int quality);
+// dequantisation factors of an index: y1 dc, y1 ac, y2 dc, y2 ac, uv dc, uv ac (RFC 6386 9.6 / 14.1)
+void vp8_quant_factors(int qindex, int f[6]);
+
+// levels: [mbh*mbw][25][16] int16 in zigzag order (Y2, 16 Y, 4 U, 4 V); modes: [mbh*mbw][4] = ymode, uvmode, skip, 0
+// (prediction modes 0 DC, 1 TM, 2 V, 3 H).  Writes a complete simple-format .webp file.  false if the frame cannot be framed.
+bool vp8_write_file(int width, int height, int qindex, const int16_t *levels, const uint8_t *modes, std::vector<uint8_t> &out);
+
+} // namespace b200

@@ -1,0 +1,28 @@
+// vp8_kernels.h -- K8: the device half of the WebP (lossy VP8 key frame) leg, SURVEY.md §8a row a10:
+// caesium::convert_in_memory(.., WebP) (/root/reference/src/compressor.rs:288-292 -> libcaesium webp::compress -> libwebp).
+// RGB -> Y'CbCr 4:2:0, then per macroblock: intra mode choice, forward DCT/WHT, quantisation, and the decoder-exact
+// reconstruction the next macroblocks predict from.  The boolean entropy coder stays on the host (vp8_host.cpp).
+#pragma once
+#include <cstdint>
+#include <cstddef>
+
+namespace b200 {
+
+constexpr int VP8_MB_COEFS = 25 * 16;        // int16 levels per macroblock: Y2, 16 Y, 4 U, 4 V, each 16 in zigzag order
+
+struct Vp8Frame {
+    int w = 0, h = 0, mbw = 0, mbh = 0;
+    int q[6] = {0, 0, 0, 0, 0, 0};           // y1 dc, y1 ac, y2 dc, y2 ac, uv dc, uv ac
+    const uint8_t *Y = nullptr, *U = nullptr, *V = nullptr;     // source planes, macroblock-padded (pitch mbw*16 / mbw*8)
+    uint8_t *RY = nullptr, *RU = nullptr, *RV = nullptr;        // reconstruction, same geometry
+    int16_t *levels = nullptr;               // [mbh*mbw][VP8_MB_COEFS]
+    uint8_t *modes = nullptr;                // [mbh*mbw][4]: ymode, uvmode, skip, 0   (modes: 0 DC, 1 TM, 2 V, 3 H)
+    int *progress = nullptr;                 // [mbh + 1]: macroblocks finished per row; [mbh] = row ticket.  Zeroed by the launcher.
+};
+
+// planar RGB (pitch w) -> macroblock-padded Y, U, V (libwebp fixed-point weights, 2x2 box chroma, edges replicated)
+int launch_vp8_rgb_to_yuv(const uint8_t *r, const uint8_t *g, const uint8_t *b, int w, int h, uint8_t *Y, uint8_t *U, uint8_t *V, void *stream);
+// wavefront over macroblocks: one warp per macroblock row, rows released in ticket order
+int launch_vp8_encode(const Vp8Frame &f, void *stream);
+
+} // namespace b200

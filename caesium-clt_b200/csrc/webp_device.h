@@ -1,0 +1,27 @@
+// webp_device.h -- per-worker device state of the WebP (lossy VP8) leg: planar RGB in HBM -> K8 -> levels/modes -> host writer.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <string>
+#include <vector>
+
+namespace b200 {
+
+struct WebpDevice {
+    uint8_t *d_planes = nullptr; size_t cap_planes = 0;        // Y,U,V source + RY,RU,RV reconstruction, macroblock-padded
+    uint8_t *d_rgb = nullptr; size_t cap_rgb = 0;              // staging for callers whose RGB starts on the host
+    int16_t *d_levels = nullptr; size_t cap_levels = 0;
+    uint8_t *d_modes = nullptr; size_t cap_modes = 0;
+    int *d_progress = nullptr; size_t cap_progress = 0;
+    uint8_t *h_out = nullptr; size_t cap_hout = 0;             // pinned: levels | modes
+    uint8_t *h_rgb = nullptr; size_t cap_hrgb = 0;             // pinned staging for host RGB
+    ~WebpDevice();
+    // d_r/d_g/d_b: device planes (pitch w).  Produces the .webp file; optionally also hands back the levels/modes (tests).
+    bool encode_planes(const uint8_t *d_r, const uint8_t *d_g, const uint8_t *d_b, int w, int h, int quality, void *stream,
+                       std::vector<uint8_t> &out, std::string &err, int16_t *levels_out = nullptr, uint8_t *modes_out = nullptr);
+    // rgb: host, planar [3][h][w]
+    bool encode_host_rgb(const uint8_t *rgb, int w, int h, int quality, void *stream, std::vector<uint8_t> &out, std::string &err,
+                         int16_t *levels_out = nullptr, uint8_t *modes_out = nullptr);
+};
+
+} // namespace b200

@@ -172,6 +172,17 @@ b200_status b200_png_deflate_tokens(const uint32_t *tokens, size_t ntokens, uint
 /* strategies tried for an optimisation level (returns the count; out[] holds up to 10) */
 int b200_png_level_strategies(int level, int *out);
 
+/* ---- WebP stage entry points (lossy VP8 key frame: caesium::convert_in_memory(.., WebP), compressor.rs:288-292) ---- */
+/* device K8 + host writer: planar RGB [3][h][w] (host) -> a complete .webp file at `quality` (0..100).  levels / modes may
+ * be NULL; otherwise they receive the per-macroblock stage output: levels [mbh*mbw][25][16] int16 (Y2, 16 Y, 4 U, 4 V in
+ * zigzag order), modes [mbh*mbw][4] = {ymode, uvmode, skip, 0} with modes 0 DC, 1 TM, 2 V, 3 H; mbw = ceil(w/16). */
+b200_status b200_webp_encode_rgb(const uint8_t *rgb, int w, int h, int quality, uint8_t **out, size_t *out_len,
+                                 int16_t *levels, uint8_t *modes);
+/* host only: boolean-code levels + modes (layout above) into a .webp file -- the entropy-coding half on its own */
+b200_status b200_webp_write_levels(int w, int h, int quality, const int16_t *levels, const uint8_t *modes, uint8_t **out, size_t *out_len);
+/* libwebp's quality -> quantiser index curve and the six dequantisation factors (y1 dc/ac, y2 dc/ac, uv dc/ac) it selects */
+int b200_webp_qindex(int quality, int factors[6]);
+
 #ifdef __cplusplus
 }
 #endif

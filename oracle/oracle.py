@@ -267,6 +267,55 @@ def png_lz77(stream, bpp, stride):
     return tok[:nt].copy(), hist
 
 
+# ---- WebP (lossy VP8) leg (oracle/webp_oracle.c) ----------------------------------------------------------------
+def vp8_qindex(quality):
+    return lib().orc_vp8_qindex(int(quality))
+
+
+def webp_rgb_to_yuv(rgb):
+    """rgb: uint8 [3, h, w] planar -> (Y [mbh*16, mbw*16], U, V [mbh*8, mbw*8]) macroblock-padded."""
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    _, h, w = rgb.shape
+    mbw, mbh = (w + 15) // 16, (h + 15) // 16
+    Y = np.zeros((mbh * 16, mbw * 16), np.uint8); U = np.zeros((mbh * 8, mbw * 8), np.uint8); V = np.zeros_like(U)
+    lib().orc_webp_rgb_to_yuv(rgb[0].ctypes.data_as(C.c_void_p), rgb[1].ctypes.data_as(C.c_void_p), rgb[2].ctypes.data_as(C.c_void_p), w, h,
+                              Y.ctypes.data_as(C.c_void_p), U.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p))
+    return Y, U, V
+
+
+def webp_analyze(rgb, quality):
+    """Stage view: (levels int16 [nmb, 25, 16] zigzag, modes uint8 [nmb, 4] = ymode, uvmode, skip, 0)."""
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    _, h, w = rgb.shape
+    nmb = ((w + 15) // 16) * ((h + 15) // 16)
+    levels = np.zeros((nmb, 25, 16), np.int16); modes = np.zeros((nmb, 4), np.uint8)
+    rc = lib().orc_webp_analyze(rgb[0].ctypes.data_as(C.c_void_p), rgb[1].ctypes.data_as(C.c_void_p), rgb[2].ctypes.data_as(C.c_void_p), w, h, int(quality),
+                                levels.ctypes.data_as(C.c_void_p), modes.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise OracleError("webp analyze failed (%d)" % rc)
+    return levels, modes
+
+
+def vp8_quant_factors(qindex):
+    f = (C.c_int * 6)()
+    lib().orc_vp8_quant_factors(int(qindex), f)
+    return list(f)
+
+
+def webp_encode(rgb, quality):
+    """rgb: uint8 [3, h, w] planar -> (file bytes, (Y, U, V) reconstruction at macroblock-padded size)."""
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    _, h, w = rgb.shape
+    mbw, mbh = (w + 15) // 16, (h + 15) // 16
+    Y = np.zeros((mbh * 16, mbw * 16), np.uint8); U = np.zeros((mbh * 8, mbw * 8), np.uint8); V = np.zeros_like(U)
+    outp, outl = C.POINTER(C.c_uint8)(), C.c_size_t()
+    rc = lib().orc_webp_encode(rgb[0].ctypes.data_as(C.c_void_p), rgb[1].ctypes.data_as(C.c_void_p), rgb[2].ctypes.data_as(C.c_void_p), w, h, int(quality),
+                               C.byref(outp), C.byref(outl), Y.ctypes.data_as(C.c_void_p), U.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise OracleError("webp encode failed (%d)" % rc)
+    return _take(outp, outl), (Y, U, V)
+
+
 def png_expand(tokens, n):
     tokens = np.ascontiguousarray(tokens, dtype=np.uint32)
     out = np.zeros(n, dtype=np.uint8)

@@ -1,0 +1,126 @@
+"""GPU parity tests of the WebP (lossy VP8) leg, SURVEY.md §8 row a10: K8 (RGB -> YUV, intra prediction, forward DCT/WHT,
+quantisation, reconstruction wavefront) + the host boolean coder, through the C-ABI, against the oracle.
+Bar: bit-exact stage output (levels, modes) and byte-identical files; and independently of the oracle, libwebp must decode
+the product's files to the reconstruction the stage output implies."""
+import numpy as np
+import pytest
+
+from pngutil import pil_png, synth
+from webputil import pil_decode
+
+pytestmark = pytest.mark.gpu
+
+FMT_JPEG, FMT_PNG, FMT_GIF, FMT_WEBP = 0, 1, 2, 3
+
+
+def planar(img):
+    return np.ascontiguousarray(img.transpose(2, 0, 1))
+
+
+@pytest.mark.parametrize("h,w", [(64, 64), (37, 53), (1, 1), (16, 16), (17, 16), (16, 17), (15, 300), (300, 15), (129, 65), (240, 320)])
+@pytest.mark.parametrize("q,kind", [(75, "photo"), (30, "flat"), (95, "noise"), (0, "photo"), (100, "flat")])
+def test_k8_stage_and_file_match_oracle(L, O, h, w, q, kind):
+    img = planar(synth(h, w, 3, seed=h * 7 + w + q, kind=kind))
+    data, levels, modes = L.webp_encode_rgb(img, q, want_stage=True)
+    wl, wm = O.webp_analyze(img, q)
+    assert np.array_equal(modes, wm), "prediction modes / skip flags"
+    assert np.array_equal(levels, wl), "quantised levels"
+    want, _ = O.webp_encode(img, q)
+    assert data == want
+
+
+def test_k8_many_rows_wavefront(L, O):
+    # tall and wide frames: hundreds of macroblock rows in flight, every row waits on the one above
+    for h, w in ((2000, 48), (48, 2000), (1080, 1920)):
+        img = planar(synth(h, w, 3, seed=h, kind="photo"))
+        data = L.webp_encode_rgb(img, 80)
+        want, _ = O.webp_encode(img, 80)
+        assert data == want
+        dec = pil_decode(data)
+        assert dec.shape == (h, w, 3)
+        assert np.abs(dec.astype(int) - img.transpose(1, 2, 0).astype(int)).mean() < 4.0
+
+
+def test_k8_repeatable(L):
+    img = planar(synth(333, 517, 3, seed=9, kind="photo"))
+    a = L.webp_encode_rgb(img, 60)
+    for _ in range(5):
+        assert L.webp_encode_rgb(img, 60) == a
+
+
+def _jpeg_rgb(O, data, nw=None, nh=None):
+    """Oracle restatement of the convert front end: decode -> RGB -> (Lanczos3) ; planar [3, h, w]."""
+    ycc = O.Jpeg(data).decode_native()
+    rgb = O.ycc_to_rgb(ycc) if ycc.shape[0] == 3 else np.repeat(ycc, 3, axis=0)
+    if nw is not None and (nw, nh) != (rgb.shape[2], rgb.shape[1]):
+        rgb = np.stack([O.resize_plane(rgb[c], nw, nh) for c in range(3)])
+    return rgb
+
+
+@pytest.mark.parametrize("name", ["in_420_base_355x237.jpg", "in_420_prog_355x237.jpg", "in_444_base_355x237.jpg", "in_422_base_355x237.jpg",
+                                  "in_gray_base_355x237.jpg", "in_420_base_640x480.jpg", "in_420_tiny_17x9.jpg", "in_420_tiny_3x3.jpg"])
+def test_convert_jpeg_to_webp_matches_oracle(L, O, golden, name):
+    data = golden(name)
+    p = L.default_params(); p.webp_quality = 85
+    out = L.convert_in_memory(data, p, FMT_WEBP)
+    want, _ = O.webp_encode(_jpeg_rgb(O, data), 85)
+    assert out == want
+    assert pil_decode(out).shape[:2] == _jpeg_rgb(O, data).shape[1:]
+
+
+@pytest.mark.parametrize("tw,th", [(200, 0), (0, 100), (177, 99), (640, 480)])
+def test_convert_jpeg_to_webp_with_resize_matches_oracle(L, O, golden, tw, th):
+    data = golden("in_420_base_640x480.jpg")
+    p = L.default_params(); p.webp_quality = 70; p.width, p.height = tw, th
+    out = L.convert_in_memory(data, p, FMT_WEBP)
+    nw, nh = O.compute_dimensions(640, 480, tw, th)
+    want, _ = O.webp_encode(_jpeg_rgb(O, data, nw, nh), 70)
+    assert out == want
+
+
+def test_convert_png_to_webp_matches_oracle(L, O):
+    from PIL import Image
+    rng = np.random.default_rng(2)
+    rgb = synth(90, 120, 3, seed=4)
+    p = L.default_params(); p.webp_quality = 80
+    assert L.convert_in_memory(pil_png(rgb), p, FMT_WEBP) == O.webp_encode(planar(rgb), 80)[0]
+    rgba = np.concatenate([rgb, synth(90, 120, 1, seed=5)], axis=2)                   # alpha is dropped on this path
+    assert L.convert_in_memory(pil_png(rgba), p, FMT_WEBP) == O.webp_encode(planar(rgb), 80)[0]
+    grey = synth(50, 70, 1, seed=6)
+    assert L.convert_in_memory(pil_png(grey), p, FMT_WEBP) == O.webp_encode(planar(np.repeat(grey, 3, axis=2)), 80)[0]
+    idx = rng.integers(0, 16, (40, 60)).astype(np.uint8)
+    im = Image.fromarray(idx, mode="P"); im.putpalette([int(v) for v in rng.integers(0, 256, 48)])
+    want = O.webp_encode(planar(np.asarray(im.convert("RGB"))), 80)[0]
+    assert L.convert_in_memory(pil_png(im), p, FMT_WEBP) == want
+
+
+def test_convert_refusals(L, golden):
+    data = golden("in_420_base_355x237.jpg")
+    p = L.default_params()
+    for fmt, code in ((FMT_JPEG, 8), (FMT_PNG, 3), (FMT_GIF, 3)):
+        with pytest.raises(L.B200Error) as e:
+            L.convert_in_memory(data, p, fmt)
+        assert e.value.code == code
+    p.webp_lossless = 1
+    with pytest.raises(L.B200Error) as e:
+        L.convert_in_memory(data, p, FMT_WEBP)
+    assert e.value.code == 3
+    with pytest.raises(L.B200Error) as e:
+        L.convert_in_memory(b"garbage", L.default_params(), FMT_WEBP)
+    assert e.value.code == 2
+
+
+def test_convert_full_size_config5_shape(L, O):
+    """BASELINE configs[4] in miniature: a large JPEG, --width 1920 --format webp -q 85; file == oracle, decodes close to the
+    Lanczos-resized source."""
+    import io
+    from PIL import Image
+    img = synth(2000, 3000, 3, seed=3, kind="photo")
+    b = io.BytesIO(); Image.fromarray(img).save(b, format="JPEG", quality=92, subsampling=2)
+    p = L.default_params(); p.webp_quality = 85; p.width = 1920
+    out = L.convert_in_memory(b.getvalue(), p, FMT_WEBP)
+    nw, nh = O.compute_dimensions(3000, 2000, 1920, 0)
+    rgb = _jpeg_rgb(O, b.getvalue(), nw, nh)
+    assert out == O.webp_encode(rgb, 85)[0]
+    dec = pil_decode(out)
+    assert dec.shape == (nh, nw, 3) and np.abs(dec.astype(int) - rgb.transpose(1, 2, 0).astype(int)).mean() < 3.0
