@@ -135,18 +135,32 @@ def compress_to_size_in_memory(data, params, max_size, return_smallest=True):
     return _take(outp, outl)
 
 
-def compress_batch(datas, params, n_threads=0):
-    """Batch form of start_compression's par_iter (compressor.rs:74-101): returns [(bytes | None, code, message)]."""
-    n = len(datas)
-    ins = (C.c_char_p * n)(*datas)
-    lens = (C.c_size_t * n)(*[len(d) for d in datas])
+class BatchInputs:
+    """Inputs of compress_batch marshalled once (pointer / length arrays), for callers that time the C-ABI call itself."""
+
+    def __init__(self, datas):
+        self.n = len(datas)
+        self.datas = datas                              # keeps the bytes objects alive
+        self.ins = (C.c_char_p * self.n)(*datas)
+        self.lens = (C.c_size_t * self.n)(*[len(d) for d in datas])
+
+
+def compress_batch(datas, params, n_threads=0, copy=True):
+    """Batch form of start_compression's par_iter (compressor.rs:74-101): returns [(bytes | None, code, message)].
+    copy=False: the library's malloc'ed outputs are inspected in place (length, first two bytes) and freed without being
+    duplicated into Python bytes objects -- entries are (length, code, message, head)."""
+    bi = datas if isinstance(datas, BatchInputs) else BatchInputs(datas)
+    n = bi.n
     outs = (C.c_void_p * n)()
     outl = (C.c_size_t * n)()
     sts = (Status * n)()
-    lib().b200_compress_batch(ins, lens, n, C.byref(params), int(n_threads), outs, outl, sts)
+    lib().b200_compress_batch(bi.ins, bi.lens, n, C.byref(params), int(n_threads), outs, outl, sts)
     res = []
     for i in range(n):
-        if sts[i].code == 0:
+        if sts[i].code == 0 and not copy:
+            res.append((outl[i], 0, "", C.string_at(outs[i], 2)))
+            lib().b200_free(outs[i])
+        elif sts[i].code == 0:
             res.append((C.string_at(outs[i], outl[i]), 0, ""))
             lib().b200_free(outs[i])
         else:

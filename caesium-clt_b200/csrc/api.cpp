@@ -536,7 +536,8 @@ int b200_compress_batch(const uint8_t *const *in, const size_t *in_len, int n, c
             for (size_t k = 0; k < idx.size(); k++) { if (!done[k]) one(idx[k], dev); else if (status[idx[k]].code) failed++; }
         }
     };
-    if (grouped) n_threads = std::max(1, std::min(n_threads, std::min(8, (n + K - 1) / K)));
+    int max_workers = 8; { const char *e = getenv("B200_GROUP_WORKERS"); if (e) max_workers = std::max(1, std::min(32, atoi(e))); }
+    if (grouped) n_threads = std::max(1, std::min(n_threads, std::min(max_workers, (n + K - 1) / K)));
     std::vector<std::thread> th;
     for (int t = 1; t < n_threads; t++) th.emplace_back(worker);
     worker();

@@ -110,6 +110,27 @@ def test_convert_refusals(L, golden):
     assert e.value.code == 2
 
 
+def test_cli_format_webp_and_png_lossless(L, O, golden, tmp_path):
+    """The b200clt mirror of caesiumclt drives the same entry points: --format webp (+ --width) and --lossless on a PNG."""
+    import json
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "caesium-clt_b200", "b200clt")
+    src = tmp_path / "in"; src.mkdir()
+    (src / "a.jpg").write_bytes(golden("in_420_base_640x480.jpg"))
+    (src / "b.png").write_bytes(pil_png(synth(64, 96, 3, seed=1)))
+    out = tmp_path / "out"
+    r = subprocess.run([exe, "-q", "85", "--width", "320", "--format", "webp", "-o", str(out), "--json", str(src / "a.jpg")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    p = L.default_params(); p.webp_quality = 85; p.jpeg_quality = 85; p.png_quality = 85; p.width = 320
+    assert (out / "a.webp").read_bytes() == L.convert_in_memory(golden("in_420_base_640x480.jpg"), p, FMT_WEBP)
+    json.loads(r.stdout)                                     # --json prints one valid document
+    r = subprocess.run([exe, "--lossless", "-o", str(out), str(src / "b.png")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    from pngutil import pil_pixels
+    assert np.array_equal(np.asarray(pil_pixels((out / "b.png").read_bytes())), np.asarray(pil_pixels((src / "b.png").read_bytes())))
+
+
 def test_convert_full_size_config5_shape(L, O):
     """BASELINE configs[4] in miniature: a large JPEG, --width 1920 --format webp -q 85; file == oracle, decodes close to the
     Lanczos-resized source."""

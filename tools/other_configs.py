@@ -77,4 +77,33 @@ if __name__ == "__main__":
     mp = w * h / 1e6
     print(json.dumps({"config": "configs[3] %dx%d RGBA PNG --lossless --png-opt-level 3" % (w, h), "images": n, "images_per_s": round(n / dt, 2), "mp_per_s": round(n * mp / dt, 1),
                       "cpu_oracle_mp_per_s": round(len(imgs) * mp / cdt, 1), "cpu_cores": cores, "out_over_in_bytes": round(out_bytes / in_bytes, 3)}), flush=True)
+    # ---- configs[4]: 6000x4000 JPEG -> --width 1920 --format webp -q 85
+    import io
+    from PIL import Image
+    big = []
+    for s in range(4):
+        b = io.BytesIO(); Image.fromarray(synth(4000, 6000, 3, seed=s, kind="photo")).save(b, format="JPEG", quality=90, subsampling=2)
+        big.append(b.getvalue())
+    n = 64
+    work = [big[i % len(big)] for i in range(n)]
+    p = L.default_params(); p.webp_quality = 85; p.width = 1920
+
+    def conv(d):
+        return L.convert_in_memory(d, p, 3)
+    with ThreadPoolExecutor(16) as ex:
+        list(ex.map(conv, work[:32]))
+        dt, res = timed(lambda: list(ex.map(conv, work)))
+
+    def oracle_conv(d):
+        ycc = O.Jpeg(d).decode_native()
+        rgb = O.ycc_to_rgb(ycc)
+        nw, nh = O.compute_dimensions(6000, 4000, 1920, 0)
+        rgb = np.stack([O.resize_plane(rgb[c], nw, nh) for c in range(3)])
+        return O.webp_encode(rgb, 85)[0]
+    with ThreadPoolExecutor(cores) as ex:
+        cdt, cres = timed(lambda: list(ex.map(oracle_conv, big)))
+    assert res[0] == cres[0], "device WebP conversion differs from the oracle"
+    mp = 24.0
+    print(json.dumps({"config": "configs[4] 6000x4000 JPEG -q 85 --width 1920 --format webp", "images": n, "images_per_s": round(n / dt, 1), "input_mp_per_s": round(n * mp / dt, 1),
+                      "cpu_oracle_input_mp_per_s": round(len(big) * mp / cdt, 1), "cpu_cores": cores, "bytes_identical_to_oracle": True, "out_bytes": len(res[0])}), flush=True)
     L.lib().b200_shutdown()
