@@ -3,6 +3,7 @@
 // callers of the reference's rayon map (compressor.rs:81-83) each get a private stream, pinned staging buffers and
 // HBM buffers; images are sharded round-robin over the initialised GPUs (no cross-GPU traffic on this path).
 #include <cuda_runtime.h>
+#include <malloc.h>
 #include <algorithm>
 #include <condition_variable>
 #include <cstring>
@@ -15,6 +16,7 @@
 #include "jpeg_gpudec.h"
 #include "png_device.h"
 #include "webp_device.h"
+#include "stream_wait.h"
 
 namespace b200 {
 
@@ -123,14 +125,20 @@ int runtime_init(int n_gpus, int only_device, std::string &err)
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_inited) return (int)g_devs.size();
     int count = 0;
-    // Callers block in cudaStreamSynchronize a few times per image; with the default spin-wait, N caller threads burn N
-    // cores doing nothing (and trip cgroup CPU quotas).  Blocking waits leave the cores to the threads that have work.
-    // B200_SYNC=spin restores the driver default.  Harmless no-op if a context already exists (e.g. created by torch).
+    // How callers wait for their stream is decided in stream_wait.h (hybrid poll-then-sleep by default); B200_SYNC=block
+    // additionally asks the driver for blocking synchronisation (no-op if a context already exists, e.g. torch's).
     // One stream per in-flight image, dozens in flight: with the default 8 hardware work queues, streams alias onto the
     // same queue and serialise behind each other.  32 is the maximum; only effective if set before the context exists.
     setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
-    const char *sy = getenv("B200_SYNC");
-    const bool blocking = !(sy && !strcmp(sy, "spin"));
+    const bool blocking = stream_wait_mode() == 1;
+    // Every image hands a freshly malloc'ed file (~1 MB) to the caller, thousands per second from several threads.  With
+    // glibc's defaults each of those is an mmap + page faults + munmap (or a heap that is trimmed back to the OS as soon as
+    // the caller frees), all serialised on the process's mmap lock: measured, that alone cost 45 % of the end-to-end rate.
+    // Keep freed memory in the allocator instead.  B200_MALLOPT=0 leaves the process's malloc settings untouched.
+    {
+        const char *mo = getenv("B200_MALLOPT");
+        if (!(mo && !strcmp(mo, "0"))) { mallopt(M_MMAP_THRESHOLD, 32 << 20); mallopt(M_TRIM_THRESHOLD, 2000000000); mallopt(M_TOP_PAD, 64 << 20); }
+    }
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count <= 0) { err = std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") + "); this build has no CPU fallback"; return 0; }
     std::vector<int> ords;
@@ -261,7 +269,7 @@ bool slot_transform(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::str
     if (rc) { err = std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)rc); return false; }
     if (!download) return true;          // the coefficients stay in HBM for the device entropy encoder
     CU(cudaMemcpyAsync(s->h_out, s->d_out, plan.out_bytes, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(stream_wait(st));
     return true;
 }
 
@@ -322,7 +330,7 @@ bool slot_download_coefs(Slot *s, size_t out_bytes, std::string &err)
 {
     cudaStream_t st = (cudaStream_t)s->stream;
     CU(cudaMemcpyAsync(s->h_out, s->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(stream_wait(st));
     return true;
 }
 
@@ -381,7 +389,7 @@ bool slot_decode_planes(Slot *s, const JpegGeom &gin, uint8_t *planes, std::stri
     uint8_t *h = reinterpret_cast<uint8_t *>(s->h_out);
     for (int c = 0; c < gin.ncomp; c++)
         CU(cudaMemcpyAsync(h + (size_t)c * gin.width * gin.height, s->d_scratch + plan.plane_bytes + plan.full_off[c], (size_t)gin.width * gin.height, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(stream_wait(st));
     memcpy(planes, h, (size_t)gin.ncomp * gin.width * gin.height);
     return true;
 }
@@ -467,7 +475,7 @@ bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, 
     if (!chk(launch_fdct_plane(p_fdct, nc, wl.max_fdct, st), "fdct")) return false;
     if (!download) return true;
     CU(cudaMemcpyAsync(s->h_out, s->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(stream_wait(st));
     return true;
 }
 
@@ -527,7 +535,7 @@ bool batch_download(JpegBatch *b, int idx, int16_t *coefs, std::string &err)
 {
     if (!b || idx < 0 || idx >= b->n) { err = "bad batch index"; return false; }
     cudaSetDevice(g_devs[0]->ordinal);
-    CU(cudaStreamSynchronize((cudaStream_t)b->stream));
+    CU(stream_wait((cudaStream_t)b->stream));
     CU(cudaDeviceSynchronize());
     const size_t out_b = align_up(b->plan.out_bytes, 256);
     CU(cudaMemcpy(coefs, (uint8_t *)b->d_out + out_b * idx, b->plan.out_bytes, cudaMemcpyDeviceToHost));
@@ -539,7 +547,7 @@ bool batch_time(JpegBatch *b, int which, int iters, float *ms, std::string &err)
     if (!b || iters <= 0) { err = "bad arguments"; return false; }
     cudaSetDevice(g_devs[0]->ordinal);
     cudaStream_t st = (cudaStream_t)b->stream;
-    CU(cudaStreamSynchronize(st));
+    CU(stream_wait(st));
     CU(cudaEventRecord((cudaEvent_t)b->ev0, st));
     for (int i = 0; i < iters; i++) {
         int rc = launch_work(b->wl, b->d_work, st, which, nullptr);

@@ -11,6 +11,7 @@
 #include <cstring>
 #include "jpeg_gpudec.h"
 #include "jpeg_gpuenc_plan.h"
+#include "stream_wait.h"
 
 namespace b200 {
 
@@ -263,7 +264,7 @@ bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &er
             std::swap(A, B); std::swap(cA, cB);
         }
         CUD(cudaMemcpyAsync(hF + (size_t)first_round * N, dF + (size_t)first_round * N, (size_t)4 * N * (rounds - first_round), cudaMemcpyDeviceToHost, st));
-        CUD(cudaStreamSynchronize(st));
+        CUD(stream_wait(st));
         for (int n = 0; n < N; n++) if (!conv[n]) for (int r = first_round; r < rounds; r++) if (hF[(size_t)r * N + n] == 0) { conv[n] = 1; nconv++; break; }
     }
     rounds_used = rounds;

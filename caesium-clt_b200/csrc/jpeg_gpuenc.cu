@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstring>
 #include "jpeg_gpuenc.h"
+#include "stream_wait.h"
 
 namespace b200 {
 
@@ -431,7 +432,7 @@ bool GpuEncoder::encode(const JpegGeom &g, bool progressive, int16_t *const *d_c
     k_ge_totals<<<cdiv(NS, 128), 128, 0, st>>>(d_scans, NS, d_bitlen, d_bitoff, d_total);
     CU(cudaMemcpyAsync(h_total, d_total, (size_t)NS * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(st));
+    CU(stream_wait(st));
     // ---- sizes are known: lay out the stuffing stage
     uint32_t groups = 0; size_t img_bytes_max = 0, img_bytes = 0; uint32_t max_groups = 0; long long max_words = 0;
     for (int si = 0; si < NS; si++) {
@@ -468,7 +469,7 @@ bool GpuEncoder::encode(const JpegGeom &g, bool progressive, int16_t *const *d_c
     CU(cudaMemcpyAsync(h_dht, d_dht, (size_t)NS * 4 * sizeof(DhtOut), cudaMemcpyDeviceToHost, st));
     for (int im = 0; im < nimages; im++) CU(cudaMemcpyAsync(h_out + (size_t)im * copy_bytes, d_out + (size_t)im * out_stride, copy_bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(st));
+    CU(stream_wait(st));
     // rare: an image stuffed more than the copied margin -> fetch the rest
     for (int im = 0; im < nimages; im++) {
         size_t tot = 0; for (int k = 0; k < plan.scans_per_image; k++) tot += h_outlen[im * plan.scans_per_image + k];
@@ -478,7 +479,7 @@ bool GpuEncoder::encode(const JpegGeom &g, bool progressive, int16_t *const *d_c
             if (!grow(h_out, c, out_stride * nimages, true, err)) return false; cap_hout = c;
             copy_bytes = out_stride;
             for (int j = 0; j < nimages; j++) CU(cudaMemcpyAsync(h_out + (size_t)j * copy_bytes, d_out + (size_t)j * out_stride, copy_bytes, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
+            CU(stream_wait(st));
             break;
         }
     }

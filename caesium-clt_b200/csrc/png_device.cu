@@ -9,6 +9,7 @@
 #include <cstring>
 #include "png_device.h"
 #include "png_kernels.h"
+#include "stream_wait.h"
 
 namespace b200 {
 
@@ -87,7 +88,7 @@ bool PngDevice::compress(PngInfo &info, const std::vector<uint8_t> &raw_in, int 
         !growp(d_tlog, cap_tlog, (rb + 8) * 4, false, err) || !growp(h_small, cap_small, 1 << 16, true, err)) return false;
     size_t tb = 0; cub::DeviceScan::ExclusiveSum((void *)nullptr, tb, d_counts, d_offsets, (int)nchunks_max, st);
     if (!growp(d_temp, cap_temp, tb + 256, false, err)) return false;
-    if (tlog_n < rb + 2) { std::vector<uint32_t> t(rb + 2); png_make_tlog(t.data(), rb + 1); CUP(cudaMemcpyAsync(d_tlog, t.data(), (rb + 2) * 4, cudaMemcpyHostToDevice, st)); CUP(cudaStreamSynchronize(st)); tlog_n = rb + 2; }
+    if (tlog_n < rb + 2) { std::vector<uint32_t> t(rb + 2); png_make_tlog(t.data(), rb + 1); CUP(cudaMemcpyAsync(d_tlog, t.data(), (rb + 2) * 4, cudaMemcpyHostToDevice, st)); CUP(stream_wait(st)); tlog_n = rb + 2; }
     memcpy(h_raw, raw_in.data(), nraw);
     CUP(cudaMemcpyAsync(d_raw, h_raw, nraw, cudaMemcpyHostToDevice, st));
     // ---- lossless reductions (oxipng reduction::*): 8-bit samples without tRNS only
@@ -99,7 +100,7 @@ bool PngDevice::compress(PngInfo &info, const std::vector<uint8_t> &raw_in, int 
         int rc = launch_png_probe(d_raw, npix, info.channels, d_flags, st);
         if (rc) { err = "png probe launch failed"; return false; }
         CUP(cudaMemcpyAsync(h_flags, d_flags, 8, cudaMemcpyDeviceToHost, st));
-        CUP(cudaStreamSynchronize(st));
+        CUP(stream_wait(st));
         const bool has_alpha = info.color_type == 4 || info.color_type == 6, is_rgb = info.color_type == 2 || info.color_type == 6;
         const bool drop_alpha = has_alpha && h_flags[0] == 0, to_grey = is_rgb && h_flags[1] == 0;
         if (drop_alpha || to_grey) {
@@ -127,7 +128,7 @@ bool PngDevice::compress(PngInfo &info, const std::vector<uint8_t> &raw_in, int 
             if (!run_strategy(strategies[k], h, (int)rb, bpp, st, err)) return false;
             CUP(cudaMemcpyAsync(h_small + 1024 + k * 316 * 4, d_hist, 316 * 4, cudaMemcpyDeviceToHost, st));
         }
-        CUP(cudaStreamSynchronize(st));
+        CUP(stream_wait(st));
         for (size_t k = 0; k < strategies.size(); k++) {
             const double bits = estimate_bits(reinterpret_cast<const uint32_t *>(h_small + 1024 + k * 316 * 4));
             if (best_bits < 0 || bits < best_bits) { best_bits = bits; best_s = strategies[k]; }
@@ -144,14 +145,14 @@ bool PngDevice::compress(PngInfo &info, const std::vector<uint8_t> &raw_in, int 
     uint32_t *h_last = reinterpret_cast<uint32_t *>(h_small + 64);
     CUP(cudaMemcpyAsync(h_last, d_offsets + (nchunks - 1), 4, cudaMemcpyDeviceToHost, st));
     CUP(cudaMemcpyAsync(h_last + 1, d_counts + (nchunks - 1), 4, cudaMemcpyDeviceToHost, st));
-    CUP(cudaStreamSynchronize(st));
+    CUP(stream_wait(st));
     const size_t ntok = (size_t)h_last[0] + h_last[1];
     const size_t npieces = (n + 4095) / 4096;
     if (!growp(h_tok, cap_htok, ntok * 4 + npieces * 16 + 64, true, err)) return false;
     CUP(cudaMemcpyAsync(h_tok, d_out, ntok * 4, cudaMemcpyDeviceToHost, st));
     unsigned long long *h_sums = reinterpret_cast<unsigned long long *>(h_tok + ((ntok * 4 + 15) / 16 * 16) / 4);
     CUP(cudaMemcpyAsync(h_sums, d_sums, npieces * 16, cudaMemcpyDeviceToHost, st));
-    CUP(cudaStreamSynchronize(st));
+    CUP(stream_wait(st));
     // Adler-32 of the filtered stream from the per-piece sums: a' = a + S, b' = b + len * a + T   (mod 65521)
     unsigned long long a = 1, b = 0;
     for (size_t p = 0; p < npieces; p++) {

@@ -4,6 +4,7 @@
 #include "webp_device.h"
 #include "vp8_kernels.h"
 #include "vp8_host.h"
+#include "stream_wait.h"
 
 namespace b200 {
 
@@ -48,7 +49,7 @@ bool WebpDevice::encode_planes(const uint8_t *d_r, const uint8_t *d_g, const uin
     if (rc) { err = std::string("vp8 kernels: ") + cudaGetErrorString((cudaError_t)rc); return false; }
     CUW(cudaMemcpyAsync(h_out, d_levels, lv_bytes, cudaMemcpyDeviceToHost, st));
     CUW(cudaMemcpyAsync(h_out + lv_bytes, d_modes, md_bytes, cudaMemcpyDeviceToHost, st));
-    CUW(cudaStreamSynchronize(st));
+    CUW(stream_wait(st));
     if (levels_out) memcpy(levels_out, h_out, lv_bytes);
     if (modes_out) memcpy(modes_out, h_out + lv_bytes, md_bytes);
     if (!vp8_write_file(w, h, qi, reinterpret_cast<const int16_t *>(h_out), h_out + lv_bytes, out)) { err = "VP8 frame cannot be framed (first partition too large)"; return false; }
