@@ -306,17 +306,28 @@ b200_status png_compress(const uint8_t *in, size_t in_len, const b200_params *p,
     if (p->width || p->height) return make_status(B200_ERR_UNSUPPORTED, "PNG resize is outside the GPU path (route to caesium::compress_in_memory)");
     std::string err;
     PngInfo info; std::vector<uint8_t> raw;
+    static const bool verbose = getenv("B200_TRACE") && atoi(getenv("B200_TRACE")) >= 2;
+    const auto t0 = std::chrono::steady_clock::now();
     if (!png_decode(in, in_len, p->keep_metadata != 0, info, raw, err)) return make_status(err.find("interlace") != std::string::npos ? B200_ERR_UNSUPPORTED : B200_ERR_CORRUPT_INPUT, err);
+    const auto t1 = std::chrono::steady_clock::now();
     if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
     Slot *s = slot_acquire(prefer_dev < 0 ? runtime_next_device() : prefer_dev, err);
     if (!s) return make_status(B200_ERR_CUDA, err);
     if (!s->png) s->png = new PngDevice();
     std::vector<uint8_t> z;
     int level = (int)p->png_optimization_level; if (level > 6) level = 6;
+    const auto t2 = std::chrono::steady_clock::now();
     const bool ok = s->png->compress(info, raw, level, s->stream, z, nullptr, err);
+    const double deflate_ms = s->png->last_deflate_ms;
     slot_release(s);
     if (!ok) return make_status(B200_ERR_CUDA, err);
+    const auto t3 = std::chrono::steady_clock::now();
     png_write(info, z, out);
+    if (verbose) {
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[b200 trace] png %ux%u: host inflate+unfilter %.1f ms, slot wait %.1f ms, device filter/LZ77 + host Huffman %.1f ms (Huffman %.1f), container %.1f ms\n",
+                info.width, info.height, ms(t0, t1), ms(t1, t2), ms(t2, t3), deflate_ms, ms(t3, std::chrono::steady_clock::now()));
+    }
     return ok_status();
 }
 

@@ -66,40 +66,46 @@ __global__ void __launch_bounds__(64) k_gd_round0(const DecImage *__restrict__ i
     if (i >= sh.g.nsub) return;
     NullSink sk; DecState st; st.p = i * sh.g.subseq_bits; st.k = 0; st.b = 0;
     A[im.sub_off + i] = decode_subsequence(stream_all + im.stream_off, sh.g, sh.tabs, i, st, sk);
-    nblk[im.sub_off + i] = sk.nblk; chg[im.sub_off + i] = 1;
+    nblk[im.sub_off + i] = sk.nblk; chg[im.sub_off + i] = 0;       // epoch 0: "changed in round 0"
 }
 
-// thread i restarts from exit i-1 of the previous round; if that exit did not change last round, neither can ours
+__device__ __forceinline__ DecState load_state(const DecState *p) { const unsigned long long v = *reinterpret_cast<const volatile unsigned long long *>(p); DecState s; memcpy(&s, &v, 8); return s; }
+__device__ __forceinline__ void store_state(DecState *p, const DecState &s) { unsigned long long v; memcpy(&v, &s, 8); *reinterpret_cast<volatile unsigned long long *>(p) = v; }
+
+// Round r (1, 2, ...): subsequence i is decoded again iff the exit state of i-1 changed in round r-1 (epoch[i-1] == r-1).
+// States are updated in place with single 64-bit accesses: a reader sees the old or the new exit of its predecessor, and
+// if it was the old one the predecessor's epoch makes it run again next round.  A CTA whose 64 predecessors all kept their
+// exits is "clean": it leaves after one byte read (dirty flags double-buffered by round parity), and an image whose
+// previous round changed nothing leaves at once, so the tail rounds of a launch group cost almost nothing.
 __global__ void __launch_bounds__(64) k_gd_round(const DecImage *__restrict__ imgs, const uint8_t *__restrict__ stream_all, const DecTable *__restrict__ tabs_all,
-                                                 const DecState *__restrict__ A, DecState *__restrict__ B, const uint8_t *__restrict__ chg_in, uint8_t *__restrict__ chg_out,
+                                                 DecState *__restrict__ S, uint8_t *__restrict__ epoch, uint8_t *__restrict__ dirty_in, uint8_t *__restrict__ dirty_out,
                                                  uint32_t *__restrict__ nblk, uint32_t *__restrict__ any_changed /*[image]*/,
-                                                 const uint32_t *__restrict__ prev_changed /*[image] of the round before, or null*/)
+                                                 const uint32_t *__restrict__ prev_changed /*[image] of the round before, or null*/, int r)
 {
     __shared__ DecShared sh;
-    __shared__ int work;
-    // An image whose previous round changed nothing has settled: both state buffers are identical from then on, so the
-    // remaining rounds of the launch group are empty for it (the host only looks at the flags after the whole group).
+    __shared__ int go;
     if (prev_changed && prev_changed[blockIdx.y] == 0) return;
     const DecImage &im = imgs[blockIdx.y];
     const uint32_t nsub = im.g.nsub;
     if (blockIdx.x * blockDim.x >= nsub) return;
-    if (threadIdx.x == 0) work = 0;
+    const size_t cta = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    if (threadIdx.x == 0) { go = r == 1 || dirty_in[cta]; if (r > 1 && go) dirty_in[cta] = 0; }
     __syncthreads();
+    if (!go) return;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, gi = im.sub_off + i;
-    const bool mine = i < nsub && (i == 0 || chg_in[gi - 1]);
-    if (i < nsub && !mine) { B[gi] = A[gi]; chg_out[gi] = 0; }
-    if (mine) work = 1;
-    __syncthreads();
-    if (!work) return;                              // nobody in this CTA has to re-decode: skip the table staging too
+    const bool mine = i > 0 && i < nsub && epoch[gi - 1] == (uint8_t)(r - 1);
+    if (!__syncthreads_or(mine)) return;             // nobody in this CTA has to re-decode: skip the table staging too
     stage_shared(sh, im, tabs_all + 8 * blockIdx.y);
     if (!mine) return;
-    NullSink sk; DecState st;
-    if (i == 0) { st.p = 0; st.k = 0; st.b = 0; } else st = A[gi - 1];
+    NullSink sk;
+    const DecState st = load_state(S + gi - 1), old = load_state(S + gi);
     const DecState o = decode_subsequence(stream_all + im.stream_off, sh.g, sh.tabs, i, st, sk);
-    B[gi] = o; nblk[gi] = sk.nblk;
-    const bool c = !same_state(o, A[gi]);
-    chg_out[gi] = c ? 1 : 0;
-    if (c) atomicOr(&any_changed[blockIdx.y], 1u);
+    nblk[gi] = sk.nblk;
+    if (!same_state(o, old)) {
+        store_state(S + gi, o); epoch[gi] = (uint8_t)r;
+        if (i + 1 < nsub) dirty_out[threadIdx.x == blockDim.x - 1 ? cta + 1 : cta] = 1;
+        atomicOr(&any_changed[blockIdx.y], 1u);
+    }
 }
 
 struct DevWriteSink {
@@ -219,8 +225,8 @@ bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &er
     const size_t par_bytes = o_flag + align_up((size_t)4 * N * (MAX_ROUNDS + 2), 256);
     if (!growd(h_raw, cap_hraw, raw_total + 64, true, err) || !growd(d_raw, cap_raw, raw_total + 64, false, err) || !growd(d_stream, cap_stream, stream_total + 64, false, err) ||
         !growd(d_cnt, cap_cnt, (size_t)grp_total * 4 + 4, false, err) || !growd(d_off, cap_off, (size_t)grp_total * 4 + 4, false, err) ||
-        !growd(d_A, cap_A, (size_t)sub_total * sizeof(DecState), false, err) || !growd(d_B, cap_B, (size_t)sub_total * sizeof(DecState), false, err) ||
-        !growd(d_chgA, cap_chgA, sub_total, false, err) || !growd(d_chgB, cap_chgB, sub_total, false, err) ||
+        !growd(d_A, cap_A, (size_t)sub_total * sizeof(DecState), false, err) ||
+        !growd(d_chgA, cap_chgA, sub_total, false, err) || !growd(d_chgB, cap_chgB, (size_t)2 * N * cdiv(max_sub, 64) + 64, false, err) ||
         !growd(d_nblk, cap_nblk, (size_t)sub_total * 4, false, err) || !growd(d_first, cap_first, (size_t)sub_total * 4, false, err) ||
         !growd(d_dc, cap_dc, (size_t)blk_total * 4, false, err) || !growd(d_dcs, cap_dcs, (size_t)blk_total * 4, false, err) ||
         !growd(d_par, cap_par, par_bytes, false, err) || !growd(h_par, cap_hpar, par_bytes, true, err)) return false;
@@ -254,14 +260,17 @@ bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &er
     for (int n = 0; n < N; n++) CUD(cudaMemsetAsync(items[n].d_coefs, 0, (size_t)items[n].rd->geom().total_coefs * 2, st));
     // ---- rounds
     const dim3 gs(cdiv(max_sub, 64), N);
+    const size_t ncta = (size_t)N * gs.x;                    // dirty flags: two buffers of one byte per CTA, by round parity
+    CUD(cudaMemsetAsync(d_chgB, 0, 2 * ncta, st));
     k_gd_round0<<<gs, 64, 0, st>>>(dI, d_stream, dT, d_A, d_chgA, d_nblk);
-    DecState *A = d_A, *B = d_B; uint8_t *cA = d_chgA, *cB = d_chgB;
+    DecState *A = d_A;
     int rounds = 0; std::vector<char> conv((size_t)N, 0); int nconv = 0;
     while (nconv < N && rounds < MAX_ROUNDS) {
         const int first_round = rounds;
         for (int r = 0; r < ROUNDS_PER_GROUP && rounds < MAX_ROUNDS; r++, rounds++) {
-            k_gd_round<<<gs, 64, 0, st>>>(dI, d_stream, dT, A, B, cA, cB, d_nblk, dF + (size_t)rounds * N, rounds ? dF + (size_t)(rounds - 1) * N : nullptr);
-            std::swap(A, B); std::swap(cA, cB);
+            const int rn = rounds + 1;                        // round number: reads dirty[rn & 1], writes dirty[(rn + 1) & 1]
+            k_gd_round<<<gs, 64, 0, st>>>(dI, d_stream, dT, d_A, d_chgA, d_chgB + (size_t)(rn & 1) * ncta, d_chgB + (size_t)((rn + 1) & 1) * ncta, d_nblk,
+                                          dF + (size_t)rounds * N, rounds ? dF + (size_t)(rounds - 1) * N : nullptr, rn);
         }
         CUD(cudaMemcpyAsync(hF + (size_t)first_round * N, dF + (size_t)first_round * N, (size_t)4 * N * (rounds - first_round), cudaMemcpyDeviceToHost, st));
         CUD(stream_wait(st));

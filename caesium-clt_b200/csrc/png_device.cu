@@ -148,7 +148,9 @@ bool PngDevice::compress(PngInfo &info, const std::vector<uint8_t> &raw_in, int 
     CUP(stream_wait(st));
     const size_t ntok = (size_t)h_last[0] + h_last[1];
     const size_t npieces = (n + 4095) / 4096;
-    if (!growp(h_tok, cap_htok, ntok * 4 + npieces * 16 + 64, true, err)) return false;
+    // sized for the worst case (one token per byte) so that images of one size never regrow it: cudaFreeHost / cudaHostAlloc
+    // synchronise the whole device and stall every other worker
+    if (!growp(h_tok, cap_htok, nmax * 4 + ((nmax + 4095) / 4096) * 16 + 64, true, err)) return false;
     CUP(cudaMemcpyAsync(h_tok, d_out, ntok * 4, cudaMemcpyDeviceToHost, st));
     unsigned long long *h_sums = reinterpret_cast<unsigned long long *>(h_tok + ((ntok * 4 + 15) / 16 * 16) / 4);
     CUP(cudaMemcpyAsync(h_sums, d_sums, npieces * 16, cudaMemcpyDeviceToHost, st));
@@ -159,7 +161,9 @@ bool PngDevice::compress(PngInfo &info, const std::vector<uint8_t> &raw_in, int 
         const unsigned long long len = std::min<size_t>(4096, n - p * 4096);
         b = (b + len * a + h_sums[2 * p + 1]) % 65521; a = (a + h_sums[2 * p]) % 65521;
     }
+    const auto td = std::chrono::steady_clock::now();
     deflate_tokens(h_tok, ntok, (uint32_t)((b << 16) | a), zlib_stream);
+    last_deflate_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - td).count();
     return true;
 }
 

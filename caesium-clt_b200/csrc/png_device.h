@@ -21,6 +21,7 @@ struct PngDevice {
     size_t cap_raw = 0, cap_raw2 = 0, cap_filt = 0, cap_best = 0, cap_tok = 0, cap_out = 0, cap_counts = 0, cap_offsets = 0, cap_hist = 0, cap_sums = 0,
            cap_tlog = 0, cap_temp = 0, cap_small = 0, cap_htok = 0, cap_hraw = 0;
     size_t tlog_n = 0;
+    double last_deflate_ms = 0;                          // host Huffman/bit-packing time of the last compress() (tracing)
     ~PngDevice();
 
     // info/raw from png_decode; may rewrite info (colour-type reductions).  Produces the zlib stream of the re-filtered image.

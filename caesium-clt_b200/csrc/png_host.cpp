@@ -2,6 +2,7 @@
 // duties of oxipng 9.1.5 + libdeflate (Cargo.lock:1161, :917) behind libcaesium png::lossless: decode the source, keep
 // the chunks StripChunks::Safe keeps, and wrap the re-compressed image data.
 #include "png_host.h"
+#include <emmintrin.h>
 #include <algorithm>
 #include <cstring>
 
@@ -33,6 +34,12 @@ uint32_t adler32(const uint8_t *p, size_t n)
     uint32_t a = 1, b = 0;
     while (n) {
         size_t k = n < 5552 ? n : 5552; n -= k;
+        // 16 bytes at a time: b += 16 a + 16 p0 + 15 p1 + ... + p15, a += sum -- no dependency between the byte terms
+        for (; k >= 16; k -= 16, p += 16) {
+            uint32_t s = 0, w = 0;
+            for (int i = 0; i < 16; i++) { s += p[i]; w += (uint32_t)(16 - i) * p[i]; }
+            b += 16 * a + w; a += s;
+        }
         while (k--) { a += *p++; b += a; }
         a %= 65521; b %= 65521;
     }
@@ -41,7 +48,7 @@ uint32_t adler32(const uint8_t *p, size_t n)
 
 // ---- inflate -----------------------------------------------------------------------------------------------------------
 namespace {
-struct InfTable { uint16_t fast[1 << 10]; uint16_t count[16]; uint16_t symbol[320]; int maxlen; };   // fast: (len << 12) | sym, 0 = slow path
+struct InfTable { uint16_t fast[1 << 12]; uint16_t count[16]; uint16_t symbol[320]; int maxlen; };   // fast: (len << 12) | sym, 0 = slow path
 
 bool build_inf(InfTable &t, const uint8_t *lens, int n)
 {
@@ -59,9 +66,9 @@ bool build_inf(InfTable &t, const uint8_t *lens, int n)
     for (int l = 1; l <= 15; l++) {
         for (int k = 0; k < t.count[l]; k++, idx++, code++) {
             t.maxlen = l;
-            if (l <= 10) {
+            if (l <= 12) {
                 int rev = 0; for (int b = 0; b < l; b++) if (code & (1 << b)) rev |= 1 << (l - 1 - b);
-                for (int f = rev; f < 1024; f += 1 << l) t.fast[f] = (uint16_t)((l << 12) | t.symbol[idx]);
+                for (int f = rev; f < 4096; f += 1 << l) t.fast[f] = (uint16_t)((l << 12) | t.symbol[idx]);
             }
         }
         code <<= 1;
@@ -71,7 +78,17 @@ bool build_inf(InfTable &t, const uint8_t *lens, int n)
 
 struct InfBits {
     const uint8_t *p, *end; uint64_t acc = 0; int n = 0;
-    inline void fill() { while (n <= 56 && p < end) { acc |= (uint64_t)*p++ << n; n += 8; } }
+    inline void fill()
+    {
+        if (end - p >= 8) {                              // one unaligned 64-bit load tops the accumulator up to >= 56 bits
+            uint64_t v; memcpy(&v, p, 8);
+            acc |= v << n;
+            const int adv = (63 - n) >> 3;
+            p += adv; n += adv * 8;
+            return;
+        }
+        while (n <= 56 && p < end) { acc |= (uint64_t)*p++ << n; n += 8; }
+    }
     inline uint32_t peek(int k) { return (uint32_t)(acc & ((1ull << k) - 1)); }
     inline void drop(int k) { acc >>= k; n -= k; }
     inline uint32_t get(int k) { if (n < k) fill(); uint32_t v = peek(k); drop(k); return v; }
@@ -80,7 +97,7 @@ struct InfBits {
 inline int inf_decode(InfBits &b, const InfTable &t)
 {
     if (b.n < 15) b.fill();
-    uint32_t e = t.fast[b.peek(10)];
+    uint32_t e = t.fast[b.peek(12)];
     if (e) { b.drop(e >> 12); return e & 0xFFF; }
     int code = 0, first = 0, index = 0;
     for (int l = 1; l <= 15; l++) {
@@ -104,7 +121,8 @@ bool zlib_inflate(const uint8_t *in, size_t n, std::vector<uint8_t> &out, size_t
     if (n < 6) { err = "zlib stream too short"; return false; }
     if ((in[0] & 0x0F) != 8 || ((in[0] << 8) | in[1]) % 31 != 0 || (in[1] & 0x20)) { err = "bad zlib header"; return false; }
     InfBits b; b.p = in + 2; b.end = in + n;
-    out.clear(); out.reserve(size_hint ? size_hint : n * 4);
+    size_t cap = (size_hint ? size_hint : n * 4) + 4096, pos = 0;     // bytes are written through a raw pointer; the vector is trimmed at the end
+    out.resize(cap + 16);
     static thread_local InfTable lit, dist;
     for (;;) {
         const uint32_t final = b.get(1), type = b.get(2);
@@ -115,7 +133,8 @@ bool zlib_inflate(const uint8_t *in, size_t n, std::vector<uint8_t> &out, size_t
             if (b.end - b.p < 4) { err = "truncated stored block"; return false; }
             const uint32_t len = b.p[0] | (b.p[1] << 8), nlen = b.p[2] | (b.p[3] << 8);
             if ((len ^ 0xFFFF) != nlen || (size_t)(b.end - b.p - 4) < len) { err = "bad stored block"; return false; }
-            out.insert(out.end(), b.p + 4, b.p + 4 + len); b.p += 4 + len;
+            if (cap - pos < len + 320) { cap = cap * 2 + len + 4096; out.resize(cap + 16); }
+            memcpy(out.data() + pos, b.p + 4, len); pos += len; b.p += 4 + len;
         } else if (type == 1 || type == 2) {
             uint8_t lens[320];
             if (type == 1) {
@@ -145,25 +164,31 @@ bool zlib_inflate(const uint8_t *in, size_t n, std::vector<uint8_t> &out, size_t
                 if (!build_inf(lit, lens, hlit) || !build_inf(dist, lens + hlit, hdist)) { err = "bad Huffman code"; return false; }
             }
             for (;;) {
+                if (cap - pos < 320) { cap = cap * 2 + 4096; out.resize(cap + 16); }     // room for one match + 8-byte copy slack
+                uint8_t *o = out.data();
                 int s = inf_decode(b, lit);
                 if (s < 0) { err = "bad literal/length code"; return false; }
-                if (s < 256) out.push_back((uint8_t)s);
+                if (s < 256) o[pos++] = (uint8_t)s;
                 else if (s == 256) break;
                 else {
                     s -= 257; if (s >= 29) { err = "bad length symbol"; return false; }
-                    const int len = kLenBase[s] + (int)b.get(kLenExtra[s]);
+                    const size_t len = kLenBase[s] + b.get(kLenExtra[s]);
                     const int ds = inf_decode(b, dist);
                     if (ds < 0 || ds >= 30) { err = "bad distance code"; return false; }
                     const size_t d = kDistBase[ds] + b.get(kDistExtra[ds]);
-                    if (d > out.size()) { err = "distance too far back"; return false; }
-                    const size_t start = out.size() - d;
-                    for (int k = 0; k < len; k++) out.push_back(out[start + k]);
+                    if (d > pos) { err = "distance too far back"; return false; }
+                    uint8_t *dst = o + pos; const uint8_t *src = dst - d;
+                    if (d >= 8) { for (size_t k = 0; k < len; k += 8) memcpy(dst + k, src + k, 8); }      // chunks never overlap their own source
+                    else if (d == 1) memset(dst, src[0], len);
+                    else for (size_t k = 0; k < len; k++) dst[k] = src[k];
+                    pos += len;
                 }
                 if (b.p >= b.end && b.n <= 0) { err = "truncated deflate stream"; return false; }
             }
         } else { err = "bad block type"; return false; }
         if (final) break;
     }
+    out.resize(pos);
     b.drop(b.n & 7);
     uint8_t tail[4]; for (int i = 0; i < 4; i++) tail[i] = (uint8_t)b.get(8);
     const uint32_t want = ((uint32_t)tail[0] << 24) | (tail[1] << 16) | (tail[2] << 8) | tail[3];
@@ -183,6 +208,29 @@ static void put_chunk(std::vector<uint8_t> &o, const char *type, const uint8_t *
 }
 
 static inline int paeth(int a, int b, int c) { int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c); return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); }
+
+// Paeth reconstruction for 3- and 4-byte pixels: the channels of one pixel are independent, so they ride in four 16-bit
+// lanes; the serial dependency is only pixel to pixel.  Loads/stores are 4 bytes wide (callers keep slack after the rows).
+static void unfilter_paeth_sse2(const uint8_t *f, const uint8_t *up, uint8_t *r, size_t rb, size_t bpp)
+{
+    const __m128i zero = _mm_setzero_si128();
+    __m128i a = zero, c = zero;                       // left and upper-left pixels (zero before the first pixel)
+    for (size_t x = 0; x < rb; x += bpp) {
+        uint32_t ub, fx; memcpy(&ub, up + x, 4); memcpy(&fx, f + x, 4);
+        const __m128i b = _mm_unpacklo_epi8(_mm_cvtsi32_si128((int)ub), zero), v = _mm_unpacklo_epi8(_mm_cvtsi32_si128((int)fx), zero);
+        __m128i pa = _mm_sub_epi16(b, c), pb = _mm_sub_epi16(a, c);              // p - a = b - c, p - b = a - c
+        __m128i pc = _mm_add_epi16(pa, pb);                                      // p - c
+        pa = _mm_max_epi16(pa, _mm_sub_epi16(zero, pa)); pb = _mm_max_epi16(pb, _mm_sub_epi16(zero, pb)); pc = _mm_max_epi16(pc, _mm_sub_epi16(zero, pc));
+        const __m128i smallest = _mm_min_epi16(pc, _mm_min_epi16(pa, pb));
+        const __m128i ma = _mm_cmpeq_epi16(smallest, pa), mb = _mm_cmpeq_epi16(smallest, pb);
+        const __m128i bc = _mm_or_si128(_mm_and_si128(mb, b), _mm_andnot_si128(mb, c));
+        const __m128i pred = _mm_or_si128(_mm_and_si128(ma, a), _mm_andnot_si128(ma, bc));
+        const __m128i d = _mm_and_si128(_mm_add_epi16(v, pred), _mm_set1_epi16(0xFF));
+        c = b; a = d;
+        const uint32_t o = (uint32_t)_mm_cvtsi128_si32(_mm_packus_epi16(d, d));
+        if (bpp == 4 || x + 4 <= rb) memcpy(r + x, &o, 4); else memcpy(r + x, &o, 3);
+    }
+}
 
 bool png_decode(const uint8_t *d, size_t n, bool keep_all, PngInfo &info, std::vector<uint8_t> &raw, std::string &err)
 {
@@ -225,20 +273,36 @@ bool png_decode(const uint8_t *d, size_t n, bool keep_all, PngInfo &info, std::v
     const size_t stride = info.row_bytes + 1;
     if (!zlib_inflate(idat.data(), idat.size(), filt, stride * info.height, err)) return false;
     if (filt.size() < stride * info.height) { err = "IDAT too short"; return false; }
-    raw.resize(info.row_bytes * info.height);
-    const int bpp = info.bpp; const size_t rb = info.row_bytes;
+    const size_t nraw = info.row_bytes * info.height;
+    raw.resize(nraw + 16);                          // slack: the 4-byte-wide Paeth path stores one byte past a 3-byte pixel
+    filt.resize(filt.size() + 16);
+    const size_t bpp = (size_t)info.bpp, rb = info.row_bytes;
+    const std::vector<uint8_t> zero_row(rb + 16, 0);
     for (uint32_t y = 0; y < info.height; y++) {   // PNG 9.2 reconstruction
         const uint8_t *f = filt.data() + (size_t)y * stride; const int ft = f[0]; f++;
-        uint8_t *r = raw.data() + (size_t)y * rb; const uint8_t *up = y ? r - rb : nullptr;
+        uint8_t *r = raw.data() + (size_t)y * rb; const uint8_t *up = y ? r - rb : zero_row.data();
         switch (ft) {
             case 0: memcpy(r, f, rb); break;
-            case 1: for (size_t x = 0; x < rb; x++) r[x] = (uint8_t)(f[x] + (x >= (size_t)bpp ? r[x - bpp] : 0)); break;
-            case 2: for (size_t x = 0; x < rb; x++) r[x] = (uint8_t)(f[x] + (up ? up[x] : 0)); break;
-            case 3: for (size_t x = 0; x < rb; x++) r[x] = (uint8_t)(f[x] + (((x >= (size_t)bpp ? r[x - bpp] : 0) + (up ? up[x] : 0)) >> 1)); break;
-            case 4: for (size_t x = 0; x < rb; x++) { int a = x >= (size_t)bpp ? r[x - bpp] : 0, b = up ? up[x] : 0, c = (up && x >= (size_t)bpp) ? up[x - bpp] : 0; r[x] = (uint8_t)(f[x] + paeth(a, b, c)); } break;
+            case 1:
+                for (size_t x = 0; x < bpp && x < rb; x++) r[x] = f[x];
+                for (size_t x = bpp; x < rb; x++) r[x] = (uint8_t)(f[x] + r[x - bpp]);
+                break;
+            case 2: for (size_t x = 0; x < rb; x++) r[x] = (uint8_t)(f[x] + up[x]); break;
+            case 3:
+                for (size_t x = 0; x < bpp && x < rb; x++) r[x] = (uint8_t)(f[x] + (up[x] >> 1));
+                for (size_t x = bpp; x < rb; x++) r[x] = (uint8_t)(f[x] + ((r[x - bpp] + up[x]) >> 1));
+                break;
+            case 4:
+                if ((bpp == 3 || bpp == 4) && rb >= bpp) unfilter_paeth_sse2(f, up, r, rb, bpp);
+                else {
+                    for (size_t x = 0; x < bpp && x < rb; x++) r[x] = (uint8_t)(f[x] + up[x]);          // a = c = 0: the predictor is b
+                    for (size_t x = bpp; x < rb; x++) r[x] = (uint8_t)(f[x] + paeth(r[x - bpp], up[x], up[x - bpp]));
+                }
+                break;
             default: err = "bad filter type"; return false;
         }
     }
+    raw.resize(nraw);
     return true;
 }
 
