@@ -370,18 +370,14 @@ b200_status jpeg_to_webp(const uint8_t *in, size_t in_len, const b200_params *p,
     return st;
 }
 
-// PNG source: samples are expanded to 8-bit RGB on the host (palette, grey, 16-bit -> high byte; alpha is dropped: the VP8X
-// alpha plane is outside this path) and go through the same K8.
-b200_status png_to_webp(const uint8_t *in, size_t in_len, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
+// Decoded PNG samples -> 8-bit planar samples on the host: palette looked up, sub-byte greys scaled, 16-bit -> high byte,
+// alpha dropped (like the image crate's to_rgb8 / to_luma8).  allow_grey: grey colour types stay one plane (JPEG target).
+void png_expand_planar(const PngInfo &info, const std::vector<uint8_t> &raw, bool allow_grey, std::vector<uint8_t> &planes, int &nc)
 {
-    if (p->width || p->height) return make_status(B200_ERR_UNSUPPORTED, "PNG resize is outside the GPU path (route to caesium::convert_in_memory)");
-    std::string err;
-    PngInfo info; std::vector<uint8_t> raw;
-    if (!png_decode(in, in_len, false, info, raw, err)) return make_status(err.find("interlace") != std::string::npos ? B200_ERR_UNSUPPORTED : B200_ERR_CORRUPT_INPUT, err);
     const size_t w = info.width, h = info.height, n = w * h;
-    if (w > 16383 || h > 16383) return make_status(B200_ERR_INVALID_ARGUMENT, "image too large for WebP");
-    std::vector<uint8_t> rgb(3 * n);
     const int bd = info.bit_depth, ct = info.color_type;
+    nc = (allow_grey && (ct == 0 || ct == 4)) ? 1 : 3;
+    planes.resize((size_t)nc * n);
     for (size_t y = 0; y < h; y++) {
         const uint8_t *row = raw.data() + y * info.row_bytes;
         for (size_t x = 0; x < w; x++) {
@@ -394,14 +390,80 @@ b200_status png_to_webp(const uint8_t *in, size_t in_len, const b200_params *p, 
                 if (ct == 3) { if (3 * v + 2 < info.plte.size()) { r = info.plte[3 * v]; g = info.plte[3 * v + 1]; b = info.plte[3 * v + 2]; } else r = g = b = 0; }
                 else { if (bd < 8) v = v * 255 / ((1u << bd) - 1); r = g = b = (uint8_t)v; }
             }
-            rgb[y * w + x] = r; rgb[n + y * w + x] = g; rgb[2 * n + y * w + x] = b;
+            planes[y * w + x] = r;
+            if (nc == 3) { planes[n + y * w + x] = g; planes[2 * n + y * w + x] = b; }
         }
+    }
+}
+
+// PNG -> JPEG: the expanded samples are uploaded in place of the JPEG decode front end and take the resize path's back end
+// (K3 Lanczos3 when width/height are set, RGB -> YCbCr, K4 box downsample, K5 FDCT + quantise) and the device Huffman encoder.
+b200_status png_to_jpeg(const uint8_t *in, size_t in_len, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
+{
+    std::string err;
+    PngInfo info; std::vector<uint8_t> raw;
+    if (!png_decode(in, in_len, false, info, raw, err)) return make_status(err.find("interlace") != std::string::npos ? B200_ERR_UNSUPPORTED : B200_ERR_CORRUPT_INPUT, err);
+    if (info.width > 65535 || info.height > 65535) return make_status(B200_ERR_INVALID_ARGUMENT, "image too large for JPEG");
+    std::vector<uint8_t> planes; int nc = 3;
+    png_expand_planar(info, raw, true, planes, nc);
+    JpegGeom gin; gin.width = (int)info.width; gin.height = (int)info.height; gin.ncomp = nc;
+    for (int c = 0; c < nc; c++) { gin.cid[c] = c + 1; gin.hs[c] = gin.vs[c] = 1; gin.tq[c] = 0; }
+    gin.finalize();
+    JpegGeom gout;
+    if (!jpeg_output_geom(gin, (int)p->jpeg_quality, (int)p->jpeg_chroma_subsampling, gout, err)) return make_status(B200_ERR_INVALID_ARGUMENT, err);
+    if (p->width || p->height) {
+        uint32_t nw = 0, nh = 0;
+        compute_resize_dimensions(info.width, info.height, p->width, p->height, nw, nh);
+        if (nw == 0 || nh == 0 || nw > 65535 || nh > 65535) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid target dimensions");
+        gout.width = (int)nw; gout.height = (int)nh; gout.finalize();
     }
     if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
     Slot *s = slot_acquire(prefer_dev < 0 ? runtime_next_device() : prefer_dev, err);
     if (!s) return make_status(B200_ERR_CUDA, err);
+    b200_status st = ok_status();
+    JpegWriteOptions wo; wo.progressive = p->jpeg_progressive != 0;
+    do {
+        if (!slot_transform_resized(s, gin, gout, err, false, false, nullptr, planes.data())) { st = make_status(B200_ERR_CUDA, err); break; }
+        if (slot_gpu_encode(s, gout, wo.progressive, err)) {
+            if (!jpeg_assemble(gout, wo, nullptr, s->enc->results.data(), (int)s->enc->results.size(), out, err)) st = make_status(B200_ERR_INVALID_ARGUMENT, err);
+            break;
+        }
+        if (!s->enc || !s->enc->overflow) { st = make_status(B200_ERR_CUDA, err); break; }
+        if (!slot_download_coefs(s, (size_t)gout.total_coefs * 2, err)) { st = make_status(B200_ERR_CUDA, err); break; }
+        jpeg_fill_dummy_blocks(gout, s->h_out);
+        if (!jpeg_write(gout, s->h_out, wo, nullptr, out, err)) st = make_status(B200_ERR_INVALID_ARGUMENT, err);
+    } while (0);
+    slot_release(s);
+    return st;
+}
+
+// PNG source: samples are expanded to 8-bit RGB on the host (palette, grey, 16-bit -> high byte; alpha is dropped: the VP8X
+// alpha plane is outside this path) and go through the same K8.
+b200_status png_to_webp(const uint8_t *in, size_t in_len, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
+{
+    std::string err;
+    PngInfo info; std::vector<uint8_t> raw;
+    if (!png_decode(in, in_len, false, info, raw, err)) return make_status(err.find("interlace") != std::string::npos ? B200_ERR_UNSUPPORTED : B200_ERR_CORRUPT_INPUT, err);
+    uint32_t nw = info.width, nh = info.height;
+    if (p->width || p->height) compute_resize_dimensions(info.width, info.height, p->width, p->height, nw, nh);
+    if (nw == 0 || nh == 0 || nw > 16383 || nh > 16383 || info.width > 65535 || info.height > 65535) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid dimensions for WebP");
+    std::vector<uint8_t> rgb; int nc = 3;
+    png_expand_planar(info, raw, false, rgb, nc);
+    if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
+    Slot *s = slot_acquire(prefer_dev < 0 ? runtime_next_device() : prefer_dev, err);
+    if (!s) return make_status(B200_ERR_CUDA, err);
     if (!s->webp) s->webp = new WebpDevice();
-    const bool ok = s->webp->encode_host_rgb(rgb.data(), (int)w, (int)h, (int)p->webp_quality, s->stream, out, err);
+    bool ok;
+    if (nw == info.width && nh == info.height) ok = s->webp->encode_host_rgb(rgb.data(), (int)nw, (int)nh, (int)p->webp_quality, s->stream, out, err);
+    else {   // through the resize leg (K3 Lanczos3) first
+        JpegGeom gin; gin.width = (int)info.width; gin.height = (int)info.height; gin.ncomp = 3;
+        for (int c = 0; c < 3; c++) { gin.cid[c] = c + 1; gin.hs[c] = gin.vs[c] = 1; gin.tq[c] = 0; }
+        gin.finalize();
+        JpegGeom gout = gin; gout.width = (int)nw; gout.height = (int)nh; gout.finalize();
+        uint8_t *planes[3] = {nullptr, nullptr, nullptr};
+        ok = slot_transform_resized(s, gin, gout, err, false, false, planes, rgb.data()) &&
+             s->webp->encode_planes(planes[0], planes[1], planes[2], (int)nw, (int)nh, (int)p->webp_quality, s->stream, out, err);
+    }
     slot_release(s);
     return ok ? ok_status() : make_status(B200_ERR_CUDA, err);
 }
@@ -467,11 +529,14 @@ b200_status b200_convert_in_memory(const uint8_t *in, size_t in_len, const b200_
     uint32_t src = b200_sniff_format(in, in_len);
     if (src == B200_FMT_UNKNOWN) return make_status(B200_ERR_UNKNOWN_FORMAT, "Unknown file type");
     if (src == fmt) return make_status(B200_ERR_SAME_FORMAT, "Cannot convert to the same format");
-    if (fmt != B200_FMT_WEBP) return make_status(B200_ERR_UNSUPPORTED, "only conversion to WebP is implemented on the GPU path (route to caesium::convert_in_memory)");
-    if (params->webp_lossless) return make_status(B200_ERR_UNSUPPORTED, "lossless WebP (VP8L) is outside the GPU path (route to caesium::convert_in_memory)");
+    const bool to_webp = fmt == B200_FMT_WEBP, png_to_jpg = fmt == B200_FMT_JPEG && src == B200_FMT_PNG;
+    if (!to_webp && !png_to_jpg) return make_status(B200_ERR_UNSUPPORTED, "this conversion is outside the GPU path (route to caesium::convert_in_memory)");
+    if (to_webp && params->webp_lossless) return make_status(B200_ERR_UNSUPPORTED, "lossless WebP (VP8L) is outside the GPU path (route to caesium::convert_in_memory)");
+    if (png_to_jpg && params->jpeg_optimize) return make_status(B200_ERR_UNSUPPORTED, "lossless conversion to JPEG is outside the GPU path (route to caesium::convert_in_memory)");
     try {
         std::vector<uint8_t> v;
-        b200_status s = src == B200_FMT_JPEG ? jpeg_to_webp(in, in_len, params, -1, v)
+        b200_status s = png_to_jpg ? png_to_jpeg(in, in_len, params, -1, v)
+                      : src == B200_FMT_JPEG ? jpeg_to_webp(in, in_len, params, -1, v)
                       : src == B200_FMT_PNG ? png_to_webp(in, in_len, params, -1, v)
                       : make_status(B200_ERR_UNSUPPORTED, "conversion from this format is outside the GPU path (route to caesium::convert_in_memory)");
         if (s.code) return s;

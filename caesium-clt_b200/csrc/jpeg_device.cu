@@ -395,7 +395,8 @@ bool slot_decode_planes(Slot *s, const JpegGeom &gin, uint8_t *planes, std::stri
 }
 
 // ---- resize path: decode -> (YCbCr->RGB) -> Lanczos3 -> (RGB->YCbCr) -> encode side --------------------------------
-bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err, bool download, bool upload, uint8_t **rgb_out)
+bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err, bool download, bool upload, uint8_t **rgb_out,
+                            const uint8_t *host_rgb)
 {
     const int W = gin.width, H = gin.height, NW = gout.width, NH = gout.height, nc = gin.ncomp;
     if (gout.ncomp != nc) { err = "component count mismatch"; return false; }
@@ -449,15 +450,19 @@ bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, 
     size_t nw_ = flatten_work(wl, reinterpret_cast<CompWork *>(s->h_par + PAR_WORK));
     (void)nw_;
     CU(cudaMemcpyAsync(s->d_par, s->h_par, pbytes, cudaMemcpyHostToDevice, st));
-    if (upload) CU(cudaMemcpyAsync(s->d_in, s->h_in, in_bytes, cudaMemcpyHostToDevice, st));
+    if (upload && !host_rgb) CU(cudaMemcpyAsync(s->d_in, s->h_in, in_bytes, cudaMemcpyHostToDevice, st));
     const CompWork *dw = reinterpret_cast<const CompWork *>(s->d_par + PAR_WORK);
     const CompWork *p_idct = dw, *p_up = p_idct + wl.idct.size(), *p_down = p_up + wl.up.size(), *p_fdct = p_down + wl.down.size();
     auto chk = [&](int rc, const char *what) { if (rc) { err = std::string(what) + ": " + cudaGetErrorString((cudaError_t)rc); return false; } return true; };
-    if (!chk(launch_idct_plane(p_idct, nc, wl.max_idct, st), "idct")) return false;
-    if (!chk(launch_upsample(p_up, nc, W, H, st), "upsample")) return false;
     uint8_t *full[3] = {s->d_scratch + full_off[0], nc == 3 ? s->d_scratch + full_off[1] : nullptr, nc == 3 ? s->d_scratch + full_off[2] : nullptr};
     uint8_t *rz[3] = {s->d_scratch + rz_off[0], nc == 3 ? s->d_scratch + rz_off[1] : nullptr, nc == 3 ? s->d_scratch + rz_off[2] : nullptr};
-    if (nc == 3 && !chk(launch_ycc_to_rgb(full[0], full[1], full[2], (size_t)W * H, st), "ycc_to_rgb")) return false;
+    if (host_rgb) {   // samples that never were a JPEG (PNG source): planar RGB (or one grey plane) straight into the full-resolution planes
+        for (int c = 0; c < nc; c++) CU(cudaMemcpyAsync(full[c], host_rgb + (size_t)c * W * H, (size_t)W * H, cudaMemcpyHostToDevice, st));
+    } else {
+        if (!chk(launch_idct_plane(p_idct, nc, wl.max_idct, st), "idct")) return false;
+        if (!chk(launch_upsample(p_up, nc, W, H, st), "upsample")) return false;
+        if (nc == 3 && !chk(launch_ycc_to_rgb(full[0], full[1], full[2], (size_t)W * H, st), "ycc_to_rgb")) return false;
+    }
     float *tmp = reinterpret_cast<float *>(s->d_scratch + tmp_off);
     for (int c = 0; c < nc; c++) {
         if (NW == W && NH == H) {   // imageops::resize copies when the dimensions are unchanged

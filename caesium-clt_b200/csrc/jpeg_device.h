@@ -83,8 +83,10 @@ bool slot_gpu_encode(Slot *s, const JpegGeom &gout, bool progressive, std::strin
 // Resize path (CSParameters.width/height): gout carries the TARGET dimensions; decode -> RGB -> Lanczos3 -> YCbCr -> encode.
 // rgb_out != nullptr: stop after the resize and hand back the three device planes (R, G, B of the TARGET size, pitch = target
 // width; a greyscale source returns its single plane three times) -- the front end of the format-conversion paths.
+// host_rgb != nullptr: the source is not a JPEG -- planar samples [ncomp][H][W] (RGB, or one grey plane) replace the decode
+// front end; gin then only carries width / height / ncomp with 1x1 sampling.
 bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err, bool download = true, bool upload = true,
-                            uint8_t **rgb_out = nullptr);
+                            uint8_t **rgb_out = nullptr, const uint8_t *host_rgb = nullptr);
 // Same front end, but stop after IDCT + upsample and copy planar full-res samples into `planes` (host).
 bool slot_decode_planes(Slot *s, const JpegGeom &gin, uint8_t *planes, std::string &err);
 

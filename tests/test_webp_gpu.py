@@ -94,6 +94,32 @@ def test_convert_png_to_webp_matches_oracle(L, O):
     assert L.convert_in_memory(pil_png(im), p, FMT_WEBP) == want
 
 
+def test_convert_png_to_webp_with_resize_matches_oracle(L, O):
+    rgb = synth(120, 200, 3, seed=8)
+    p = L.default_params(); p.webp_quality = 75; p.width = 77
+    nw, nh = O.compute_dimensions(200, 120, 77, 0)
+    want = O.webp_encode(np.stack([O.resize_plane(np.ascontiguousarray(rgb[:, :, c]), nw, nh) for c in range(3)]), 75)[0]
+    assert L.convert_in_memory(pil_png(rgb), p, FMT_WEBP) == want
+
+
+@pytest.mark.parametrize("q,ss,prog", [(80, 0, True), (90, 444, False), (60, 422, True)])
+def test_convert_png_to_jpeg_matches_oracle(L, O, q, ss, prog):
+    """PNG -> JPEG: RGB -> YCbCr (jccolor tables) -> box downsample -> FDCT/quantise -> Huffman, all against the oracle's
+    forward path (itself bit-exact with libjpeg-turbo, tests/test_oracle_jpeg.py)."""
+    rgb = synth(93, 141, 3, seed=q)
+    p = L.default_params(); p.jpeg_quality, p.jpeg_chroma_subsampling, p.jpeg_progressive = q, ss, int(prog)
+    op = O.params(q, ss, prog)
+    want = O.write(O.forward(O.rgb_to_ycc(planar(rgb)), op), op)
+    assert L.convert_in_memory(pil_png(rgb), p, FMT_JPEG) == want
+    grey = synth(50, 70, 1, seed=q)                                   # grey PNG -> single-component JPEG
+    want = O.write(O.forward(planar(grey), op), op)
+    assert L.convert_in_memory(pil_png(grey), p, FMT_JPEG) == want
+    p.width = 64                                                      # with Lanczos3 resize
+    nw, nh = O.compute_dimensions(141, 93, 64, 0)
+    rz = np.stack([O.resize_plane(np.ascontiguousarray(rgb[:, :, c]), nw, nh) for c in range(3)])
+    assert L.convert_in_memory(pil_png(rgb), p, FMT_JPEG) == O.write(O.forward(O.rgb_to_ycc(rz), op), op)
+
+
 def test_convert_refusals(L, golden):
     data = golden("in_420_base_355x237.jpg")
     p = L.default_params()
