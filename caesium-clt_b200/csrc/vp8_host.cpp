@@ -54,49 +54,86 @@ private:
 };
 
 const uint8_t kBands[17] = {0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 0};
-inline const uint8_t *probs(int type, int band, int ctx) { return VP8_COEF_PROBS + ((type * 8 + band) * 3 + ctx) * 11; }
+constexpr int kNumProbs = 4 * 8 * 3 * 11;
+inline int slot(int type, int band, int ctx) { return ((type * 8 + band) * 3 + ctx) * 11; }
+
+// Two consumers of the token walk: the writer codes each tree decision with the slot's probability; the counter only tallies
+// zeros and ones per slot (the statistics the probability update is chosen from).
+struct TokenWriter {
+    BoolWriter &w; const uint8_t *probs;
+    void node(int s, bool bit) { w.put(bit, probs[s]); }
+    void fixed(bool bit, int prob) { w.put(bit, prob); }
+};
+struct TokenCounter {
+    uint32_t (*count)[2];
+    void node(int s, bool bit) { count[s][bit ? 1 : 0]++; }
+    void fixed(bool, int) {}
+};
 
 // RFC 6386 13.2: one block's tokens; `lv` = 16 levels in zigzag order.  Returns the "has coded coefficients" context flag.
-int put_block(BoolWriter &w, const int16_t *lv, int type, int first, int ctx)
+template <class Sink> int put_block(Sink &w, const int16_t *lv, int type, int first, int ctx)
 {
     static const uint8_t kCat3[] = {173, 148, 140}, kCat4[] = {176, 155, 140, 135}, kCat5[] = {180, 157, 141, 134, 130},
                          kCat6[] = {254, 254, 243, 230, 196, 177, 153, 140, 133, 130, 129};
     int last = -1;
     for (int i = 15; i >= first; i--) if (lv[i]) { last = i; break; }
-    const uint8_t *p = probs(type, kBands[first], ctx);
-    w.put(last >= 0, p[0]);
+    int p = slot(type, kBands[first], ctx);
+    w.node(p, last >= 0);
     if (last < 0) return 0;
     for (int n = first; n < 16;) {
         const int c = lv[n++], v = c < 0 ? -c : c;
-        w.put(v != 0, p[1]);
-        if (!v) { p = probs(type, kBands[n], 0); continue; }          // a zero is never followed by an end-of-block check
-        w.put(v > 1, p[2]);
-        if (v == 1) p = probs(type, kBands[n], 1);
+        w.node(p + 1, v != 0);
+        if (!v) { p = slot(type, kBands[n], 0); continue; }           // a zero is never followed by an end-of-block check
+        w.node(p + 2, v > 1);
+        if (v == 1) p = slot(type, kBands[n], 1);
         else {
-            w.put(v > 4, p[3]);
-            if (v <= 4) { w.put(v != 2, p[4]); if (v != 2) w.put(v == 4, p[5]); }
+            w.node(p + 3, v > 4);
+            if (v <= 4) { w.node(p + 4, v != 2); if (v != 2) w.node(p + 5, v == 4); }
             else {
-                w.put(v > 10, p[6]);
+                w.node(p + 6, v > 10);
                 if (v <= 10) {
-                    w.put(v > 6, p[7]);
-                    if (v <= 6) w.put(v == 6, 159); else { w.put(v >= 9, 165); w.put(!(v & 1), 145); }
+                    w.node(p + 7, v > 6);
+                    if (v <= 6) w.fixed(v == 6, 159); else { w.fixed(v >= 9, 165); w.fixed(!(v & 1), 145); }
                 } else {
                     const int cat = v < 19 ? 0 : v < 35 ? 1 : v < 67 ? 2 : 3;       // DCT_CAT3..6: bases 11, 19, 35, 67
                     static const uint8_t *const tabs[4] = {kCat3, kCat4, kCat5, kCat6};
                     static const int nbits[4] = {3, 4, 5, 11}, base[4] = {11, 19, 35, 67};
-                    w.put(cat >> 1, p[8]); w.put(cat & 1, p[9 + (cat >> 1)]);
-                    for (int i = nbits[cat] - 1, t = 0; i >= 0; i--, t++) w.put(((v - base[cat]) >> i) & 1, tabs[cat][t]);
+                    w.node(p + 8, cat >> 1); w.node(p + 9 + (cat >> 1), cat & 1);
+                    for (int i = nbits[cat] - 1, t = 0; i >= 0; i--, t++) w.fixed(((v - base[cat]) >> i) & 1, tabs[cat][t]);
                 }
             }
-            p = probs(type, kBands[n], 2);
+            p = slot(type, kBands[n], 2);
         }
-        w.put(c < 0, 128);
+        w.fixed(c < 0, 128);
         if (n == 16) break;
-        w.put(n <= last, p[0]);
+        w.node(p, n <= last);
         if (n > last) break;
     }
     return 1;
 }
+
+// every residual block of the frame in coding order (13): contexts are the "has coefficients" flags of the blocks above and
+// to the left; a skipped macroblock clears them
+template <class Sink> void walk_tokens(Sink &sk, int mbw, int mbh, bool use_skip, const int16_t *levels, const uint8_t *modes)
+{
+    std::vector<uint8_t> top((size_t)mbw * 9, 0);
+    for (int my = 0; my < mbh; my++) {
+        uint8_t left[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int mx = 0; mx < mbw; mx++) {
+            const size_t mb = (size_t)my * mbw + mx;
+            uint8_t *t = &top[(size_t)mx * 9];
+            if (use_skip && modes[4 * mb + 2]) { memset(t, 0, 9); memset(left, 0, 9); continue; }
+            const int16_t *lv = levels + mb * 400;
+            t[8] = left[8] = (uint8_t)put_block(sk, lv, 1, 0, t[8] + left[8]);
+            for (int b = 0; b < 16; b++) { const int x = b & 3, y = b >> 2; t[x] = left[y] = (uint8_t)put_block(sk, lv + 16 * (1 + b), 0, 1, t[x] + left[y]); }
+            for (int c = 0; c < 2; c++)
+                for (int b = 0; b < 4; b++) { const int x = 4 + 2 * c + (b & 1), y = 4 + 2 * c + (b >> 1); t[x] = left[y] = (uint8_t)put_block(sk, lv + 16 * (17 + 4 * c + b), 2, 0, t[x] + left[y]); }
+        }
+    }
+}
+
+// price of one decision coded with probability-of-zero p/256, in 1/256 bit
+inline int bit_cost(int p) { return p <= 0 ? 1 << 20 : (int)(-std::log2(p / 256.0) * 256.0 + 0.5); }
 
 void put_le(std::vector<uint8_t> &o, uint32_t v, int nbytes) { for (int i = 0; i < nbytes; i++) o.push_back((uint8_t)(v >> (8 * i))); }
 
@@ -110,6 +147,23 @@ bool vp8_write_file(int width, int height, int qindex, const int16_t *levels, co
     for (int i = 0; i < nmb; i++) nskip += modes[4 * i + 2];
     const bool use_skip = nskip > 0;
     int skip_p = (int)(((long long)(nmb - nskip) * 255) / nmb); if (skip_p < 1) skip_p = 1; if (skip_p > 255) skip_p = 255;
+    // ---- token probabilities (13.4): count the tree decisions of this frame, then replace a default wherever the frame's
+    //      own estimate (libwebp's 255 - ones * 255 / total) saves more than the flag + 8-bit update costs
+    std::vector<uint8_t> probs(VP8_COEF_PROBS, VP8_COEF_PROBS + kNumProbs), updated(kNumProbs, 0);
+    {
+        std::vector<uint32_t> cnt((size_t)kNumProbs * 2, 0);
+        TokenCounter tc{reinterpret_cast<uint32_t (*)[2]>(cnt.data())};
+        walk_tokens(tc, mbw, mbh, use_skip, levels, modes);
+        for (int i = 0; i < kNumProbs; i++) {
+            const uint64_t c0 = cnt[2 * i], c1 = cnt[2 * i + 1], total = c0 + c1;
+            if (!total) continue;
+            const int oldp = probs[i], u = VP8_COEF_UPDATE_PROBS[i];
+            int newp = 255 - (int)(c1 * 255 / total); if (newp < 1) newp = 1;
+            const uint64_t keep = c0 * bit_cost(oldp) + c1 * bit_cost(256 - oldp) + bit_cost(u);
+            const uint64_t change = c0 * bit_cost(newp) + c1 * bit_cost(256 - newp) + bit_cost(256 - u) + 8 * 256;
+            if (newp != oldp && change < keep) { probs[i] = (uint8_t)newp; updated[i] = 1; }
+        }
+    }
     // ---- first partition: frame header (RFC 6386 9.2-9.11, 19.2) and the per-macroblock modes (19.3)
     BoolWriter hd;
     hd.literal(0, 1);                   // color_space
@@ -123,7 +177,7 @@ bool vp8_write_file(int width, int height, int qindex, const int16_t *levels, co
     hd.literal(qindex, 7);              // y_ac_qi
     hd.literal(0, 5);                   // five delta-present flags, all clear
     hd.literal(0, 1);                   // refresh_entropy_probs
-    for (int i = 0; i < 4 * 8 * 3 * 11; i++) hd.put(0, VP8_COEF_UPDATE_PROBS[i]);      // default token probabilities kept
+    for (int i = 0; i < kNumProbs; i++) { hd.put(updated[i], VP8_COEF_UPDATE_PROBS[i]); if (updated[i]) hd.literal(probs[i], 8); }
     hd.literal(use_skip, 1);            // mb_no_coeff_skip
     if (use_skip) hd.literal(skip_p, 8);
     for (int i = 0; i < nmb; i++) {
@@ -138,22 +192,9 @@ bool vp8_write_file(int width, int height, int qindex, const int16_t *levels, co
     }
     hd.finish();
     if (hd.bytes.size() >= (1u << 19)) return false;
-    // ---- token partition (13): contexts are the "has coefficients" flags of the blocks above and to the left
+    // ---- token partition, coded with the table chosen above
     BoolWriter tk;
-    std::vector<uint8_t> top((size_t)mbw * 9, 0);
-    for (int my = 0; my < mbh; my++) {
-        uint8_t left[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        for (int mx = 0; mx < mbw; mx++) {
-            const size_t mb = (size_t)my * mbw + mx;
-            uint8_t *t = &top[(size_t)mx * 9];
-            if (use_skip && modes[4 * mb + 2]) { memset(t, 0, 9); memset(left, 0, 9); continue; }
-            const int16_t *lv = levels + mb * 400;
-            t[8] = left[8] = (uint8_t)put_block(tk, lv, 1, 0, t[8] + left[8]);
-            for (int b = 0; b < 16; b++) { const int x = b & 3, y = b >> 2; t[x] = left[y] = (uint8_t)put_block(tk, lv + 16 * (1 + b), 0, 1, t[x] + left[y]); }
-            for (int c = 0; c < 2; c++)
-                for (int b = 0; b < 4; b++) { const int x = 4 + 2 * c + (b & 1), y = 4 + 2 * c + (b >> 1); t[x] = left[y] = (uint8_t)put_block(tk, lv + 16 * (17 + 4 * c + b), 2, 0, t[x] + left[y]); }
-        }
-    }
+    { TokenWriter tw{tk, probs.data()}; walk_tokens(tw, mbw, mbh, use_skip, levels, modes); }
     tk.finish();
     // ---- RIFF container (WebP simple lossy format)
     const size_t vp8_size = 10 + hd.bytes.size() + tk.bytes.size(), riff_payload = 4 + 8 + vp8_size + (vp8_size & 1);

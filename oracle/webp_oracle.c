@@ -5,11 +5,12 @@
  * `parameters.webp.quality`).  libwebp is a Cargo/C dependency that is NOT vendored under /root/reference; the VP8
  * bitstream, its arithmetic ("bool") coder, token tree, transforms and intra predictors are normative (RFC 6386), so the
  * decoder side of every function below is fixed by the standard.  The ENCODER decisions are this project's profile:
- * 16x16 luma prediction only (DC / TM / V / H by least squared error), one segment, default token probabilities, loop
- * filter level 0, libwebp's forward transforms and quality -> quantiser-index curve, quantiser bias 3/8.  Documented
+ * 16x16 luma prediction only (DC / TM / V / H by least squared error), one segment, token probabilities re-estimated per
+ * frame where the update pays for itself, loop filter level 0, libwebp's forward transforms and quality -> quantiser-index
+ * curve, quantiser bias 3/8.  Documented
  * deviation: no 4x4 intra modes, no RD optimisation, no segmentation, no deblocking, no alpha plane.
  * Parity status: "pinned by decode" -- files made here must decode in libwebp (through Pillow) to exactly this encoder's
- * own reconstruction (tests/test_oracle_webp.py); byte-identity with libwebp's encoder output is not claimed.
+ * own reconstruction (tests/test_webp_host.py); byte-identity with libwebp's encoder output is not claimed.
  * Plain scalar C, macroblock by macroblock in raster order.
  */
 #include <math.h>
@@ -254,38 +255,87 @@ static void bool_flush(Bool *e)
     for (c = 0; c < 4; c++) { bool_byte(e, (uint8_t)(v >> 24)); v <<= 8; }
 }
 
-/* ---- RFC 6386 13: token coding of one block; returns 1 if anything but an immediate end-of-block was written ------------------ */
-static int put_coeffs(Bool *e, const int16_t lv[16], int type, int first, int ctx)
+/* ---- RFC 6386 13: token coding of one block; returns 1 if anything but an immediate end-of-block was coded.
+ *      The same walk either writes bits (k->e set) or only counts the 0/1 decisions per probability slot (k->stats set):
+ *      the counting pass feeds the probability update below. */
+typedef struct { Bool *e; uint32_t *stats /* [1056][2] */; const uint8_t *probs /* [1056] */; } Coder;
+static int node(Coder *k, int slot, int bit)
+{
+    if (k->stats) k->stats[2 * slot + (bit ? 1 : 0)]++;
+    else bool_put(k->e, bit, k->probs[slot]);
+    return bit;
+}
+static void fixed(Coder *k, int bit, int prob) { if (!k->stats) bool_put(k->e, bit, prob); }
+
+static int put_coeffs(Coder *k, const int16_t lv[16], int type, int first, int ctx)
 {
     static const uint8_t cat3[] = {173, 148, 140}, cat4[] = {176, 155, 140, 135}, cat5[] = {180, 157, 141, 134, 130}, cat6[] = {254, 254, 243, 230, 196, 177, 153, 140, 133, 130, 129};
     int last = -1, n = first;
     for (int i = first; i < 16; i++) if (lv[i]) last = i;
-    const uint8_t *p = ORC_VP8_COEF_PROBS + ((type * 8 + kBand[n]) * 3 + ctx) * 11;
-    if (!bool_put(e, last >= 0, p[0])) return 0;
+    int p = ((type * 8 + kBand[n]) * 3 + ctx) * 11;                 /* slot of node 0 for the current (band, context) */
+    if (!node(k, p + 0, last >= 0)) return 0;
     while (n < 16) {
         int c = lv[n++], sign = c < 0, v = sign ? -c : c;
-        const uint8_t *base = ORC_VP8_COEF_PROBS + (type * 8 + kBand[n]) * 3 * 11;
-        if (!bool_put(e, v != 0, p[1])) { p = base; continue; }
-        if (!bool_put(e, v > 1, p[2])) p = base + 11;
+        const int base = (type * 8 + kBand[n]) * 3 * 11;
+        if (!node(k, p + 1, v != 0)) { p = base; continue; }
+        if (!node(k, p + 2, v > 1)) p = base + 11;
         else {
-            if (!bool_put(e, v > 4, p[3])) { if (bool_put(e, v != 2, p[4])) bool_put(e, v == 4, p[5]); }
-            else if (!bool_put(e, v > 10, p[6])) {
-                if (!bool_put(e, v > 6, p[7])) bool_put(e, v == 6, 159);
-                else { bool_put(e, v >= 9, 165); bool_put(e, !(v & 1), 145); }
+            if (!node(k, p + 3, v > 4)) { if (node(k, p + 4, v != 2)) node(k, p + 5, v == 4); }
+            else if (!node(k, p + 6, v > 10)) {
+                if (!node(k, p + 7, v > 6)) fixed(k, v == 6, 159);
+                else { fixed(k, v >= 9, 165); fixed(k, !(v & 1), 145); }
             } else {
                 const uint8_t *tab; int nb, residue;
-                if (v < 19) { bool_put(e, 0, p[8]); bool_put(e, 0, p[9]); residue = v - 11; nb = 3; tab = cat3; }
-                else if (v < 35) { bool_put(e, 0, p[8]); bool_put(e, 1, p[9]); residue = v - 19; nb = 4; tab = cat4; }
-                else if (v < 67) { bool_put(e, 1, p[8]); bool_put(e, 0, p[10]); residue = v - 35; nb = 5; tab = cat5; }
-                else { bool_put(e, 1, p[8]); bool_put(e, 1, p[10]); residue = v - 67; nb = 11; tab = cat6; }
-                for (int i = nb - 1; i >= 0; i--) bool_put(e, (residue >> i) & 1, *tab++);
+                if (v < 19) { node(k, p + 8, 0); node(k, p + 9, 0); residue = v - 11; nb = 3; tab = cat3; }
+                else if (v < 35) { node(k, p + 8, 0); node(k, p + 9, 1); residue = v - 19; nb = 4; tab = cat4; }
+                else if (v < 67) { node(k, p + 8, 1); node(k, p + 10, 0); residue = v - 35; nb = 5; tab = cat5; }
+                else { node(k, p + 8, 1); node(k, p + 10, 1); residue = v - 67; nb = 11; tab = cat6; }
+                for (int i = nb - 1; i >= 0; i--) fixed(k, (residue >> i) & 1, *tab++);
             }
             p = base + 22;
         }
-        bool_put(e, sign, 128);
-        if (n == 16 || !bool_put(e, n <= last, p[0])) return 1;
+        fixed(k, sign, 128);
+        if (n == 16 || !node(k, p + 0, n <= last)) return 1;
     }
     return 1;
+}
+
+/* all residual tokens of the frame in coding order, through `k` */
+static void code_frame_tokens(Coder *k, const MbCoded *mbs, int mbw, int mbh, int use_skip)
+{
+    uint8_t *top_nz = (uint8_t *)calloc((size_t)mbw, 9), left_nz[9];
+    for (int mby = 0; mby < mbh; mby++) {
+        memset(left_nz, 0, 9);
+        for (int mbx = 0; mbx < mbw; mbx++) {
+            const MbCoded *m = &mbs[mby * mbw + mbx];
+            uint8_t *t = top_nz + (size_t)mbx * 9, *l = left_nz;
+            if (use_skip && m->skip) { memset(t, 0, 9); memset(l, 0, 9); continue; }
+            t[8] = l[8] = (uint8_t)put_coeffs(k, m->y2, 1, 0, t[8] + l[8]);
+            for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) t[x] = l[y] = (uint8_t)put_coeffs(k, m->y[y * 4 + x], 0, 1, t[x] + l[y]);
+            for (int y = 0; y < 2; y++) for (int x = 0; x < 2; x++) t[4 + x] = l[4 + y] = (uint8_t)put_coeffs(k, m->u[y * 2 + x], 2, 0, t[4 + x] + l[4 + y]);
+            for (int y = 0; y < 2; y++) for (int x = 0; x < 2; x++) t[6 + x] = l[6 + y] = (uint8_t)put_coeffs(k, m->v[y * 2 + x], 2, 0, t[6 + x] + l[6 + y]);
+        }
+    }
+    free(top_nz);
+}
+
+/* cost of coding one decision with probability-of-zero p/256, in 1/256 bit */
+static int bit_cost(int p) { return p <= 0 ? 1 << 20 : (int)(-log2(p / 256.0) * 256.0 + 0.5); }
+
+/* RFC 6386 13.4: per slot, replace the default probability by the frame's own estimate when that pays for the 8-bit update
+ * (libwebp's estimate: 255 - ones * 255 / total).  probs[] in: defaults, out: the table the tokens are coded with. */
+static void choose_probs(const uint32_t *stats, uint8_t *probs, uint8_t *updated)
+{
+    for (int i = 0; i < 4 * 8 * 3 * 11; i++) {
+        const uint64_t c0 = stats[2 * i], c1 = stats[2 * i + 1], total = c0 + c1;
+        const int oldp = probs[i], u = ORC_VP8_COEF_UPDATE_PROBS[i];
+        updated[i] = 0;
+        if (!total) continue;
+        int newp = 255 - (int)(c1 * 255 / total); if (newp < 1) newp = 1;
+        const uint64_t old_cost = c0 * bit_cost(oldp) + c1 * bit_cost(256 - oldp) + bit_cost(u);
+        const uint64_t new_cost = c0 * bit_cost(newp) + c1 * bit_cost(256 - newp) + bit_cost(256 - u) + 8 * 256;
+        if (newp != oldp && new_cost < old_cost) { probs[i] = (uint8_t)newp; updated[i] = 1; }
+    }
 }
 
 /* Stage view for the parity tests: per macroblock the 25 x 16 quantised levels (Y2, 16 Y, 4 U, 4 V; zigzag order) and
@@ -331,6 +381,16 @@ int orc_webp_encode(const uint8_t *r, const uint8_t *g, const uint8_t *b, int w,
     /* ---- first partition: frame header + per-macroblock modes */
     Bool h0, tk; bool_init(&h0); bool_init(&tk);
     const int use_skip = nskip > 0;
+    /* counting pass over the tokens -> which default probabilities are worth replacing */
+    uint8_t probs[4 * 8 * 3 * 11], updated[4 * 8 * 3 * 11];
+    memcpy(probs, ORC_VP8_COEF_PROBS, sizeof(probs));
+    {
+        uint32_t *stats = (uint32_t *)calloc(4 * 8 * 3 * 11 * 2, sizeof(uint32_t));
+        Coder k = {NULL, stats, probs};
+        code_frame_tokens(&k, mbs, mbw, mbh, use_skip);
+        choose_probs(stats, probs, updated);
+        free(stats);
+    }
     int skip_p = (int)(((long)(nmb - nskip) * 255) / nmb); if (skip_p < 1) skip_p = 1; if (skip_p > 255) skip_p = 255;
     bool_bits(&h0, 0, 1);             /* color_space */
     bool_bits(&h0, 0, 1);             /* clamping_type: clamping needed */
@@ -343,7 +403,9 @@ int orc_webp_encode(const uint8_t *r, const uint8_t *g, const uint8_t *b, int w,
     bool_bits(&h0, q, 7);             /* y_ac_qi */
     for (int i = 0; i < 5; i++) bool_bits(&h0, 0, 1);   /* y_dc, y2_dc, y2_ac, uv_dc, uv_ac deltas absent */
     bool_bits(&h0, 0, 1);             /* refresh_entropy_probs */
-    for (int i = 0; i < 4 * 8 * 3 * 11; i++) bool_put(&h0, 0, ORC_VP8_COEF_UPDATE_PROBS[i]);   /* keep the default token probabilities */
+    for (int i = 0; i < 4 * 8 * 3 * 11; i++) {                                                /* token probability updates */
+        if (bool_put(&h0, updated[i], ORC_VP8_COEF_UPDATE_PROBS[i])) bool_bits(&h0, probs[i], 8);
+    }
     bool_bits(&h0, use_skip, 1);      /* mb_no_coeff_skip */
     if (use_skip) bool_bits(&h0, skip_p, 8);
     for (int i = 0; i < nmb; i++) {
@@ -356,19 +418,7 @@ int orc_webp_encode(const uint8_t *r, const uint8_t *g, const uint8_t *b, int w,
     }
     bool_flush(&h0);
     /* ---- token partition */
-    uint8_t *top_nz = (uint8_t *)calloc((size_t)mbw, 9), left_nz[9];
-    for (int mby = 0; mby < mbh; mby++) {
-        memset(left_nz, 0, 9);
-        for (int mbx = 0; mbx < mbw; mbx++) {
-            const MbCoded *m = &mbs[mby * mbw + mbx];
-            uint8_t *t = top_nz + (size_t)mbx * 9, *l = left_nz;
-            if (use_skip && m->skip) { memset(t, 0, 9); memset(l, 0, 9); continue; }
-            t[8] = l[8] = (uint8_t)put_coeffs(&tk, m->y2, 1, 0, t[8] + l[8]);
-            for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) t[x] = l[y] = (uint8_t)put_coeffs(&tk, m->y[y * 4 + x], 0, 1, t[x] + l[y]);
-            for (int y = 0; y < 2; y++) for (int x = 0; x < 2; x++) t[4 + x] = l[4 + y] = (uint8_t)put_coeffs(&tk, m->u[y * 2 + x], 2, 0, t[4 + x] + l[4 + y]);
-            for (int y = 0; y < 2; y++) for (int x = 0; x < 2; x++) t[6 + x] = l[6 + y] = (uint8_t)put_coeffs(&tk, m->v[y * 2 + x], 2, 0, t[6 + x] + l[6 + y]);
-        }
-    }
+    { Coder k = {&tk, NULL, probs}; code_frame_tokens(&k, mbs, mbw, mbh, use_skip); }
     bool_flush(&tk);
     /* ---- container */
     const size_t vp8_size = 10 + h0.n + tk.n, riff_payload = 4 + 8 + vp8_size + (vp8_size & 1);
@@ -387,6 +437,6 @@ int orc_webp_encode(const uint8_t *r, const uint8_t *g, const uint8_t *b, int w,
     if (recon_y) memcpy(recon_y, RY, ny);
     if (recon_u) memcpy(recon_u, RU, nc);
     if (recon_v) memcpy(recon_v, RV, nc);
-    free(Y); free(U); free(V); free(RY); free(RU); free(RV); free(mbs); free(top_nz); free(h0.buf); free(tk.buf);
+    free(Y); free(U); free(V); free(RY); free(RU); free(RV); free(mbs); free(h0.buf); free(tk.buf);
     return h0.n >= (1u << 19) ? -2 : 0;
 }
