@@ -183,7 +183,7 @@ template <typename T> static bool growd(T *&p, size_t &cap, size_t need, bool ho
 
 GpuDecoder::~GpuDecoder()
 {
-    cudaFreeHost(h_raw); cudaFree(d_raw); cudaFree(d_stream); cudaFree(d_cnt); cudaFree(d_off); cudaFree(d_A); cudaFree(d_B); cudaFree(d_chgA); cudaFree(d_chgB);
+    cudaFreeHost(h_raw); cudaFree(d_raw); cudaFree(d_stream); cudaFree(d_cnt); cudaFree(d_off); cudaFree(d_A); cudaFree(d_chgA); cudaFree(d_chgB);
     cudaFree(d_nblk); cudaFree(d_first); cudaFree(d_dc); cudaFree(d_dcs); cudaFree(d_par); cudaFreeHost(h_par); cudaFree(d_temp);
 }
 
