@@ -108,11 +108,25 @@ __global__ void __launch_bounds__(64) k_gd_round(const DecImage *__restrict__ im
     }
 }
 
+// Write pass sink.  A block's 64 coefficients are staged in the thread's local memory and leave as eight 16-byte stores when
+// the block ends, zeros included -- so the coefficient buffer needs no memset and HBM sees whole 128-byte blocks instead of
+// scattered 2-byte stores.  A block that straddles subsequences is shared by position: each thread writes exactly the zigzag
+// range [lo, hi) it decoded (ranges of neighbouring threads are disjoint and contiguous in the zigzag layout).
 struct DevWriteSink {
-    const ge::Scan *scan; uint32_t cur, total; int16_t *ptr;
+    const ge::Scan *scan; uint32_t cur, total; int16_t *ptr; int lo;
+    uint4 buf[8];
     __device__ __forceinline__ void seek() { ptr = cur < total ? const_cast<int16_t *>(ge::locate(*scan, (int)cur).blk) : nullptr; }
-    __device__ __forceinline__ void coef(int k, int v) { if (ptr) ptr[k] = (int16_t)v; }
-    __device__ __forceinline__ void block_done() { cur++; seek(); }
+    __device__ __forceinline__ void clear() { for (int i = 0; i < 8; i++) buf[i] = make_uint4(0u, 0u, 0u, 0u); }
+    __device__ __forceinline__ void coef(int k, int v) { reinterpret_cast<int16_t *>(buf)[k] = (int16_t)v; }
+    __device__ __forceinline__ void flush(int hi)
+    {
+        if (ptr) {
+            if (lo == 0 && hi == 64) { uint4 *d = reinterpret_cast<uint4 *>(ptr); for (int i = 0; i < 8; i++) d[i] = buf[i]; }
+            else { const int16_t *s = reinterpret_cast<const int16_t *>(buf); for (int k = lo; k < hi; k++) ptr[k] = s[k]; }
+        }
+        clear();
+    }
+    __device__ __forceinline__ void block_done() { flush(64); lo = 0; cur++; seek(); }
 };
 
 __global__ void __launch_bounds__(64) k_gd_write(const DecImage *__restrict__ imgs, const uint8_t *__restrict__ stream_all, const DecTable *__restrict__ tabs_all,
@@ -127,11 +141,13 @@ __global__ void __launch_bounds__(64) k_gd_write(const DecImage *__restrict__ im
     __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= sh.g.nsub) return;
-    DevWriteSink sk{&ssc, first[im.sub_off + i] - first[im.sub_off], sh.g.total_blocks, nullptr};
-    sk.seek();
     DecState st;
     if (i == 0) { st.p = 0; st.k = 0; st.b = 0; } else st = A[im.sub_off + i - 1];
-    decode_subsequence(stream_all + im.stream_off, sh.g, sh.tabs, i, st, sk);
+    DevWriteSink sk;
+    sk.scan = &ssc; sk.cur = first[im.sub_off + i] - first[im.sub_off]; sk.total = sh.g.total_blocks; sk.ptr = nullptr; sk.lo = st.k;
+    sk.clear(); sk.seek();
+    const DecState o = decode_subsequence(stream_all + im.stream_off, sh.g, sh.tabs, i, st, sk);
+    if (o.k > sk.lo) sk.flush(o.k);                 // the block this subsequence ends inside: our part of it
 }
 
 // ---- DC: gather differences component-major, inclusive scan, subtract the component's base, scatter ------------------
@@ -144,13 +160,20 @@ __device__ __forceinline__ uint32_t dc_slot_index(const ge::Scan &s, uint32_t u,
     *comp_start = start;
     return start + m * s.hs[i] * s.vs[i] + q;
 }
-__global__ void k_gd_dc_gather(const DecImage *__restrict__ imgs, int32_t *__restrict__ d)
+// Also finishes what the write pass could not: a stream that ends early (truncated file) leaves its last block half written
+// and the following blocks untouched; they are zero-filled here (libjpeg's premature-end behaviour), the buffer is not memset.
+__global__ void k_gd_dc_gather(const DecImage *__restrict__ imgs, int32_t *__restrict__ d, const DecState *__restrict__ A,
+                               const uint32_t *__restrict__ first, const uint32_t *__restrict__ nblk)
 {
     const DecImage &im = imgs[blockIdx.y];
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= im.g.total_blocks) return;
+    int16_t *blk = const_cast<int16_t *>(ge::locate(im.scan, (int)u).blk);
+    const uint32_t last = im.sub_off + im.g.nsub - 1;
+    const uint32_t done = first[last] - first[im.sub_off] + nblk[last];          // blocks the stream completed
+    if (u >= done) { for (int k = u == done ? (int)A[last].k : 0; k < 64; k++) blk[k] = 0; }
     uint32_t cs;
-    d[im.blk_off + dc_slot_index(im.scan, u, &cs)] = ge::locate(im.scan, (int)u).blk[0];
+    d[im.blk_off + dc_slot_index(im.scan, u, &cs)] = blk[0];
 }
 __global__ void k_gd_dc_scatter(const DecImage *__restrict__ imgs, const int32_t *__restrict__ sum)
 {
@@ -257,7 +280,6 @@ bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &er
     size_t tb = cap_temp;
     cub::DeviceScan::ExclusiveSum(d_temp, tb, d_cnt, d_off, (int)grp_total, st);
     k_gd_unstuff_scatter<<<gg, 128, 0, st>>>(dI, d_raw, d_off, d_stream);
-    for (int n = 0; n < N; n++) CUD(cudaMemsetAsync(items[n].d_coefs, 0, (size_t)items[n].rd->geom().total_coefs * 2, st));
     // ---- rounds
     const dim3 gs(cdiv(max_sub, 64), N);
     const size_t ncta = (size_t)N * gs.x;                    // dirty flags: two buffers of one byte per CTA, by round parity
@@ -285,7 +307,7 @@ bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &er
     cub::DeviceScan::ExclusiveSum(d_temp, tb, d_nblk, d_first, (int)sub_total, st);
     k_gd_write<<<gs, 64, 0, st>>>(dI, d_stream, dT, A, d_first);
     const dim3 gb(cdiv(max_blk, 128), N);
-    k_gd_dc_gather<<<gb, 128, 0, st>>>(dI, d_dc);
+    k_gd_dc_gather<<<gb, 128, 0, st>>>(dI, d_dc, d_A, d_first, d_nblk);
     tb = cap_temp;
     cub::DeviceScan::InclusiveSum(d_temp, tb, d_dc, d_dcs, (int)blk_total, st);
     k_gd_dc_scatter<<<gb, 128, 0, st>>>(dI, d_dcs);
