@@ -84,6 +84,28 @@ def test_lossless_transcode_bytes_match_oracle(L, O, golden, name, prog):
         assert np.array_equal(L.component_view(l0, c0, c)[:l0.rbh[c], :l0.rbw[c]], L.component_view(l1, c1, c)[:l0.rbh[c], :l0.rbw[c]])
 
 
+def _pillow_jpeg(**kw):
+    import io
+    from PIL import Image
+    yy, xx = np.mgrid[0:237, 0:355]
+    rgb = np.stack([(xx * 3 + yy) % 256, (xx + yy * 2) % 256, (xx * yy // 64) % 256], -1).astype(np.uint8)
+    b = io.BytesIO()
+    Image.fromarray(rgb).save(b, format="JPEG", **kw)
+    return b.getvalue()
+
+
+@pytest.mark.parametrize("kw", [dict(quality=85, restart_marker_blocks=7), dict(quality=85, restart_marker_rows=1),
+                                dict(quality=85, progressive=True, restart_marker_rows=2), dict(quality=85, optimize=True)])
+def test_restart_intervals_and_custom_tables_decode_like_the_oracle(L, O, kw):
+    """Inputs with DRI / RSTn markers (baseline and progressive) and optimised Huffman tables: the host decoder (the route
+    such files take, they are not device-decodable) must carry the coefficients exactly; checked through the transcode."""
+    data = _pillow_jpeg(**kw)
+    assert (b"\xff\xdd" in data) == any(k.startswith("restart") for k in kw)
+    p = L.default_params()
+    p.jpeg_optimize = 1
+    assert L.compress_in_memory(data, p) == O.jpeg_lossless(data, O.params(80, 0, True))
+
+
 @pytest.mark.parametrize("prog", [0, 1])
 def test_host_huffman_encode_matches_oracle_writer(L, O, golden, prog):
     """Entropy-code the ORACLE's forward coefficients with the product's encoder: files must be identical."""

@@ -204,6 +204,27 @@ def test_lossless_transcode_on_device_matches_oracle(L, O, golden, prog):
         assert out == O.jpeg_lossless(d, O.params(80, 0, prog, keep_metadata=True))
 
 
+@pytest.mark.parametrize("kw", [dict(quality=85, restart_marker_blocks=7), dict(quality=85, restart_marker_rows=1),
+                                dict(quality=85, progressive=True, restart_marker_rows=2), dict(quality=92, optimize=True, subsampling=0)])
+def test_inputs_that_take_the_host_decoder(L, O, kw):
+    """DRI / progressive / multi-table inputs are not device-decodable: host Huffman decode, then the same CUDA transform and
+    device encoder -- single calls, and inside a batch next to device-decodable files."""
+    import io
+    from PIL import Image
+    yy, xx = np.mgrid[0:237, 0:355]
+    rgb = np.stack([(xx * 3 + yy) % 256, (xx + yy * 2) % 256, (xx * yy // 64) % 256], -1).astype(np.uint8)
+    b = io.BytesIO(); Image.fromarray(rgb).save(b, format="JPEG", **kw)
+    data = b.getvalue()
+    p = _params(L, 80, 420, True)
+    want = O.jpeg_lossy(data, O.params(80, 420, True))
+    assert L.compress_in_memory(data, p) == want
+    plain = io.BytesIO(); Image.fromarray(rgb).save(plain, format="JPEG", quality=85)
+    datas = [plain.getvalue()] * 3 + [data] + [plain.getvalue()] * 4
+    for d, (out, code, msg) in zip(datas, L.compress_batch(datas, p, n_threads=4)):
+        assert code == 0, msg
+        assert out == O.jpeg_lossy(d, O.params(80, 420, True))
+
+
 def test_megabatch_device_resident(L, O, golden):
     data = golden("in_420_base_640x480.jpg")
     lay, co = L.jpeg_decode_coefficients(data)
