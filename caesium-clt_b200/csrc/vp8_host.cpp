@@ -13,6 +13,8 @@ int vp8_qindex(int quality)
     return q < 0 ? 0 : q > 127 ? 127 : q;
 }
 
+int vp8_filter_level(int qindex) { const int l = qindex / 2; return l > 63 ? 63 : l; }
+
 void vp8_quant_factors(int q, int f[6])
 {
     f[0] = VP8_DC_Q[q]; f[1] = VP8_AC_Q[q];
@@ -169,8 +171,8 @@ bool vp8_write_file(int width, int height, int qindex, const int16_t *levels, co
     hd.literal(0, 1);                   // color_space
     hd.literal(0, 1);                   // clamping_type
     hd.literal(0, 1);                   // segmentation_enabled
-    hd.literal(0, 1);                   // filter_type
-    hd.literal(0, 6);                   // loop_filter_level: none, so the decoder's output is exactly the reconstruction of K8
+    hd.literal(1, 1);                   // filter_type: simple (luma edges only)
+    hd.literal(vp8_filter_level(qindex), 6);   // loop_filter_level: a decoder-side post-filter; prediction in K8 uses unfiltered samples, as the format defines
     hd.literal(0, 3);                   // sharpness_level
     hd.literal(0, 1);                   // loop_filter_adj_enable
     hd.literal(0, 2);                   // log2_nbr_of_dct_partitions

@@ -9,6 +9,9 @@ namespace b200 {
 
 // libwebp's quality (0..100) -> base quantiser index curve (one segment)
 int vp8_qindex(int quality);
+// strength of the decoder-side simple loop filter requested in the frame header: none at the finest quantisers, rising with
+// the step size (+0.5..0.9 dB on photographic content at -q 10..75)
+int vp8_filter_level(int qindex);
 // dequantisation factors of an index: y1 dc, y1 ac, y2 dc, y2 ac, uv dc, uv ac (RFC 6386 9.6 / 14.1)
 void vp8_quant_factors(int qindex, int f[6]);
 

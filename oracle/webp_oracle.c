@@ -6,9 +6,9 @@
  * bitstream, its arithmetic ("bool") coder, token tree, transforms and intra predictors are normative (RFC 6386), so the
  * decoder side of every function below is fixed by the standard.  The ENCODER decisions are this project's profile:
  * 16x16 luma prediction only (DC / TM / V / H by least squared error), one segment, token probabilities re-estimated per
- * frame where the update pays for itself, loop filter level 0, libwebp's forward transforms and quality -> quantiser-index
- * curve, quantiser bias 3/8.  Documented
- * deviation: no 4x4 intra modes, no RD optimisation, no segmentation, no deblocking, no alpha plane.
+ * frame where the update pays for itself, the simple loop filter at level qindex/2, libwebp's forward transforms and
+ * quality -> quantiser-index curve, quantiser bias 3/8.  Documented deviation: no 4x4 intra modes, no RD
+ * optimisation, no segmentation, simple instead of normal deblocking filter, no alpha plane.
  * Parity status: "pinned by decode" -- files made here must decode in libwebp (through Pillow) to exactly this encoder's
  * own reconstruction (tests/test_webp_host.py); byte-identity with libwebp's encoder output is not claimed.
  * Plain scalar C, macroblock by macroblock in raster order.
@@ -172,7 +172,7 @@ static long sse(const uint8_t *src, int ss, const uint8_t *pred, int n)
 }
 
 /* ---- macroblock analysis + reconstruction ------------------------------------------------------------------------------ */
-typedef struct { uint8_t ymode, uvmode, skip; int16_t y2[16], y[16][16], u[4][16], v[4][16]; /* levels, ZIGZAG order */ } MbCoded;
+typedef struct { uint8_t ymode, uvmode, skip, inner /* decoder filters the inner 4x4 edges */; int16_t y2[16], y[16][16], u[4][16], v[4][16]; /* levels, ZIGZAG order */ } MbCoded;
 
 static void code_block(const int16_t coef[16], int first, int qdc, int qac, int16_t levels_zz[16], int16_t deq[16])
 {
@@ -195,12 +195,13 @@ static void encode_mb(const uint8_t *Y, const uint8_t *U, const uint8_t *V, uint
     fwht(dcs, wht);
     code_block(wht, 0, f[2], f[3], mb->y2, y2deq);
     iwht(y2deq, dcrec);
-    int nz = 0;
+    int nz = 0, inner = 0;      /* inner: some block carries a non-zero coefficient AFTER the inverse WHT (what the decoder's filter looks at) */
     for (int n = 0; n < 16; n++) nz |= mb->y2[n];
     uint8_t *ry = RY + (size_t)mby * 16 * ys + mbx * 16;
     for (int k = 0; k < 16; k++) {
         code_block(coef[k], 1, f[0], f[1], mb->y[k], deq);
         deq[0] = dcrec[k];
+        inner |= dcrec[k] != 0;
         for (int n = 1; n < 16; n++) nz |= mb->y[k][n];
         idct4_add(deq, pred[bm] + (k >> 2) * 64 + (k & 3) * 4, 16, ry + (k >> 2) * 4 * ys + (k & 3) * 4, ys);
     }
@@ -225,7 +226,42 @@ static void encode_mb(const uint8_t *Y, const uint8_t *U, const uint8_t *V, uint
         idct4_add(deq, pv[bm] + po, 8, rv + o, cs);
     }
     mb->skip = nz == 0;
+    {   /* Y2 levels alone do not make an inner edge: only what reaches the 4x4 blocks counts */
+        int ac_or_uv = 0;
+        for (int k = 0; k < 16; k++) for (int n = 1; n < 16; n++) ac_or_uv |= mb->y[k][n];
+        for (int k = 0; k < 4; k++) for (int n = 0; n < 16; n++) ac_or_uv |= mb->u[k][n] | mb->v[k][n];
+        mb->inner = (uint8_t)(inner || ac_or_uv);
+    }
 }
+
+/* ---- RFC 6386 15.2: the decoder's SIMPLE loop filter (luma only), macroblocks in raster order, in place.  The encoder never
+ *      looks at filtered samples (intra prediction uses the unfiltered reconstruction); this is here so that the tests know what
+ *      a decoder must output. */
+static int sclip(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
+static void simple_edge(uint8_t *p, int step, int thresh)
+{
+    const int p1 = p[-2 * step], p0 = p[-step], q0 = p[0], q1 = p[step];
+    if (4 * abs(p0 - q0) + abs(p1 - q1) > 2 * thresh + 1) return;
+    const int a = 3 * (q0 - p0) + sclip(p1 - q1, -128, 127);
+    const int a1 = sclip((a + 4) >> 3, -16, 15), a2 = sclip((a + 3) >> 3, -16, 15);
+    p[-step] = (uint8_t)clip8(p0 + a2); p[0] = (uint8_t)clip8(q0 - a1);
+}
+static void loop_filter_simple(uint8_t *Yp, int mbw, int mbh, int level, const MbCoded *mbs)
+{
+    if (level <= 0) return;
+    const int ys = mbw * 16, limit = 2 * level + (level < 1 ? 1 : level);      /* sharpness 0: interior level = level */
+    for (int my = 0; my < mbh; my++) for (int mx = 0; mx < mbw; mx++) {
+        uint8_t *p = Yp + (size_t)my * 16 * ys + mx * 16;
+        const int inner = mbs[my * mbw + mx].inner;
+        if (mx > 0) for (int i = 0; i < 16; i++) simple_edge(p + i * ys, 1, limit + 4);
+        if (inner) for (int e = 4; e < 16; e += 4) for (int i = 0; i < 16; i++) simple_edge(p + i * ys + e, 1, limit);
+        if (my > 0) for (int i = 0; i < 16; i++) simple_edge(p + i, ys, limit + 4);
+        if (inner) for (int e = 4; e < 16; e += 4) for (int i = 0; i < 16; i++) simple_edge(p + e * ys + i, ys, limit);
+    }
+}
+
+/* loop filter strength this encoder asks the decoder for: none at the finest quantisers, rising with the step size */
+int orc_vp8_filter_level(int qindex) { int l = qindex / 2; return l > 63 ? 63 : l; }
 
 /* ---- RFC 6386 section 7: the boolean entropy encoder ---------------------------------------------------------------------- */
 typedef struct { uint8_t *buf; size_t n, cap; uint32_t range, bottom; int bit_count; } Bool;
@@ -375,6 +411,7 @@ int orc_webp_encode(const uint8_t *r, const uint8_t *g, const uint8_t *b, int w,
     MbCoded *mbs = (MbCoded *)malloc(sizeof(MbCoded) * (size_t)nmb);
     orc_webp_rgb_to_yuv(r, g, b, w, h, Y, U, V);
     const int q = orc_vp8_qindex(quality);
+    const int flevel = orc_vp8_filter_level(q);
     int f[6]; orc_vp8_quant_factors(q, f);
     int nskip = 0;
     for (int mby = 0; mby < mbh; mby++) for (int mbx = 0; mbx < mbw; mbx++) { encode_mb(Y, U, V, RY, RU, RV, mbw, mbx, mby, f, &mbs[mby * mbw + mbx]); nskip += mbs[mby * mbw + mbx].skip; }
@@ -395,8 +432,8 @@ int orc_webp_encode(const uint8_t *r, const uint8_t *g, const uint8_t *b, int w,
     bool_bits(&h0, 0, 1);             /* color_space */
     bool_bits(&h0, 0, 1);             /* clamping_type: clamping needed */
     bool_bits(&h0, 0, 1);             /* segmentation_enabled */
-    bool_bits(&h0, 0, 1);             /* filter_type */
-    bool_bits(&h0, 0, 6);             /* loop_filter_level */
+    bool_bits(&h0, 1, 1);             /* filter_type: simple */
+    bool_bits(&h0, flevel, 6);        /* loop_filter_level */
     bool_bits(&h0, 0, 3);             /* sharpness_level */
     bool_bits(&h0, 0, 1);             /* loop_filter_adj_enable */
     bool_bits(&h0, 0, 2);             /* log2_nbr_of_dct_partitions */
@@ -434,7 +471,7 @@ int orc_webp_encode(const uint8_t *r, const uint8_t *g, const uint8_t *b, int w,
     memcpy(p, h0.buf, h0.n); p += h0.n; memcpy(p, tk.buf, tk.n); p += tk.n;
     if (vp8_size & 1) *p++ = 0;
     *out = o; *out_len = (size_t)(p - o);
-    if (recon_y) memcpy(recon_y, RY, ny);
+    if (recon_y) { loop_filter_simple(RY, mbw, mbh, flevel, mbs); memcpy(recon_y, RY, ny); }      /* what a decoder shows */
     if (recon_u) memcpy(recon_u, RU, nc);
     if (recon_v) memcpy(recon_v, RV, nc);
     free(Y); free(U); free(V); free(RY); free(RU); free(RV); free(mbs); free(h0.buf); free(tk.buf);
