@@ -370,6 +370,57 @@ b200_status jpeg_to_webp(const uint8_t *in, size_t in_len, const b200_params *p,
     return st;
 }
 
+// JPEG -> PNG (lossless PNG only: png.optimize): device decode (+ K3 resize) to RGB, samples back to the host as PNG rows, then
+// the lossless PNG leg (K6 filter selection, K7 LZ77).  A greyscale JPEG becomes a greyscale PNG.
+b200_status jpeg_to_png(const uint8_t *in, size_t in_len, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
+{
+    if (!p->png_optimize) return make_status(B200_ERR_UNSUPPORTED, "lossy PNG (imagequant) is outside the GPU path (route to caesium::convert_in_memory)");
+    std::string err;
+    JpegReader rd(in, in_len);
+    if (!rd.read_header(err)) return make_status(B200_ERR_CORRUPT_INPUT, err);
+    const JpegGeom &gin = rd.geom();
+    if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
+    uint32_t nw = (uint32_t)gin.width, nh = (uint32_t)gin.height;
+    if (p->width || p->height) compute_resize_dimensions((uint32_t)gin.width, (uint32_t)gin.height, p->width, p->height, nw, nh);
+    if (nw == 0 || nh == 0 || nw > 65535 || nh > 65535) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid target dimensions");
+    JpegGeom gout = gin; gout.width = (int)nw; gout.height = (int)nh; gout.finalize();
+    if (g_entropy_mode.load() < 0) {
+        const char *e = getenv("B200_ENTROPY");
+        g_entropy_mode.store(!e ? 3 : !strcmp(e, "host") ? 0 : !strcmp(e, "gpuenc") ? 1 : !strcmp(e, "gpudec") ? 2 : 3);
+    }
+    Slot *s = slot_acquire(prefer_dev < 0 ? runtime_next_device() : prefer_dev, err);
+    if (!s) return make_status(B200_ERR_CUDA, err);
+    b200_status st = ok_status();
+    const int nc = gin.ncomp == 1 ? 1 : 3;
+    const size_t n = (size_t)nw * nh;
+    std::vector<uint8_t> planes((size_t)nc * n), raw;
+    do {
+        if (!s->ensure((size_t)gin.total_coefs * 2, (size_t)gout.total_coefs * 2, 0, 1 << 14, err)) { st = make_status(B200_ERR_OUT_OF_MEMORY, err); break; }
+        bool on_device = false;
+        JpegReader::DeviceScan ds;
+        if ((g_entropy_mode.load() & 2) && rd.device_decodable(ds)) {
+            const int r = slot_gpu_decode(s, rd, ds, err);
+            if (r == 0) on_device = true; else if (r != 1) { st = make_status(B200_ERR_CUDA, err); break; }
+        }
+        if (!on_device && !rd.decode(s->h_in, err)) { st = make_status(B200_ERR_CORRUPT_INPUT, err); break; }
+        uint8_t *rgb[3] = {nullptr, nullptr, nullptr};
+        if (!slot_transform_resized(s, gin, gout, err, false, !on_device, rgb)) { st = make_status(B200_ERR_CUDA, err); break; }
+        if (!slot_fetch_planes(s, rgb, nc, n, planes.data(), err)) { st = make_status(B200_ERR_CUDA, err); break; }
+        raw.resize((size_t)nc * n);
+        if (nc == 1) raw = planes;
+        else for (size_t i = 0; i < n; i++) { raw[3 * i] = planes[i]; raw[3 * i + 1] = planes[n + i]; raw[3 * i + 2] = planes[2 * n + i]; }
+        PngInfo info; info.width = nw; info.height = nh; info.bit_depth = 8; info.color_type = nc == 1 ? 0 : 2; info.channels = nc;
+        info.bits_per_pixel = 8 * nc; info.bpp = nc; info.row_bytes = (size_t)nw * nc;
+        if (!s->png) s->png = new PngDevice();
+        std::vector<uint8_t> z;
+        int level = (int)p->png_optimization_level; if (level > 6) level = 6;
+        if (!s->png->compress(info, raw, level, s->stream, z, nullptr, err)) { st = make_status(B200_ERR_CUDA, err); break; }
+        png_write(info, z, out);
+    } while (0);
+    slot_release(s);
+    return st;
+}
+
 // Decoded PNG samples -> 8-bit planar samples on the host: palette looked up, sub-byte greys scaled, 16-bit -> high byte,
 // alpha dropped (like the image crate's to_rgb8 / to_luma8).  allow_grey: grey colour types stay one plane (JPEG target).
 void png_expand_planar(const PngInfo &info, const std::vector<uint8_t> &raw, bool allow_grey, std::vector<uint8_t> &planes, int &nc)
@@ -529,7 +580,11 @@ b200_status b200_convert_in_memory(const uint8_t *in, size_t in_len, const b200_
     uint32_t src = b200_sniff_format(in, in_len);
     if (src == B200_FMT_UNKNOWN) return make_status(B200_ERR_UNKNOWN_FORMAT, "Unknown file type");
     if (src == fmt) return make_status(B200_ERR_SAME_FORMAT, "Cannot convert to the same format");
-    const bool to_webp = fmt == B200_FMT_WEBP, png_to_jpg = fmt == B200_FMT_JPEG && src == B200_FMT_PNG;
+    const bool to_webp = fmt == B200_FMT_WEBP, png_to_jpg = fmt == B200_FMT_JPEG && src == B200_FMT_PNG, jpg_to_png = fmt == B200_FMT_PNG && src == B200_FMT_JPEG;
+    if (jpg_to_png) {
+        try { std::vector<uint8_t> v; b200_status s = jpeg_to_png(in, in_len, params, -1, v); if (s.code) return s; return give(v, out, out_len); }
+        catch (const std::exception &e) { return make_status(B200_ERR_OUT_OF_MEMORY, e.what()); }
+    }
     if (!to_webp && !png_to_jpg) return make_status(B200_ERR_UNSUPPORTED, "this conversion is outside the GPU path (route to caesium::convert_in_memory)");
     if (to_webp && params->webp_lossless) return make_status(B200_ERR_UNSUPPORTED, "lossless WebP (VP8L) is outside the GPU path (route to caesium::convert_in_memory)");
     if (png_to_jpg && params->jpeg_optimize) return make_status(B200_ERR_UNSUPPORTED, "lossless conversion to JPEG is outside the GPU path (route to caesium::convert_in_memory)");

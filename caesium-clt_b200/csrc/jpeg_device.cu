@@ -357,6 +357,14 @@ bool slot_gpu_encode(Slot *s, const JpegGeom &gout, bool progressive, std::strin
     return s->enc->encode(gout, progressive, &base, 1, s->stream, true, err);
 }
 
+bool slot_fetch_planes(Slot *s, uint8_t *const *d_planes, int nplanes, size_t n, uint8_t *host, std::string &err)
+{
+    cudaStream_t st = (cudaStream_t)s->stream;
+    for (int c = 0; c < nplanes; c++) CU(cudaMemcpyAsync(host + (size_t)c * n, d_planes[c], n, cudaMemcpyDeviceToHost, st));
+    CU(stream_wait(st));
+    return true;
+}
+
 bool slot_decode_planes(Slot *s, const JpegGeom &gin, uint8_t *planes, std::string &err)
 {
     // route every component through idct (+ upsample) by planning against a 4:4:4 output of the same size

@@ -87,6 +87,8 @@ bool slot_gpu_encode(Slot *s, const JpegGeom &gout, bool progressive, std::strin
 // front end; gin then only carries width / height / ncomp with 1x1 sampling.
 bool slot_transform_resized(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err, bool download = true, bool upload = true,
                             uint8_t **rgb_out = nullptr, const uint8_t *host_rgb = nullptr);
+// D2H of nplanes device planes of n bytes each (rgb_out of slot_transform_resized) into one host buffer, synchronised
+bool slot_fetch_planes(Slot *s, uint8_t *const *d_planes, int nplanes, size_t n, uint8_t *host, std::string &err);
 // Same front end, but stop after IDCT + upsample and copy planar full-res samples into `planes` (host).
 bool slot_decode_planes(Slot *s, const JpegGeom &gin, uint8_t *planes, std::string &err);
 

@@ -120,6 +120,23 @@ def test_convert_png_to_jpeg_matches_oracle(L, O, q, ss, prog):
     assert L.convert_in_memory(pil_png(rgb), p, FMT_JPEG) == O.write(O.forward(O.rgb_to_ycc(rz), op), op)
 
 
+@pytest.mark.parametrize("name", ["in_420_base_355x237.jpg", "in_444_base_355x237.jpg", "in_gray_base_355x237.jpg", "in_420_prog_355x237.jpg"])
+def test_convert_jpeg_to_lossless_png_matches_oracle_decode(L, O, golden, name):
+    """JPEG -> PNG with png.optimize: the PNG must hold exactly the oracle's RGB decode of the JPEG (libjpeg-turbo-exact IDCT,
+    fancy upsampling and colour conversion), also after a Lanczos3 resize."""
+    from pngutil import pil_pixels
+    data = golden(name)
+    p = L.default_params(); p.png_optimize = 1; p.png_optimization_level = 2
+    out = L.convert_in_memory(data, p, FMT_PNG)
+    want = _jpeg_rgb(O, data)
+    got = np.asarray(pil_pixels(out).convert("RGB")).transpose(2, 0, 1)
+    assert np.array_equal(got, want)
+    p.width = 120
+    nw, nh = O.compute_dimensions(355, 237, 120, 0)
+    got = np.asarray(pil_pixels(L.convert_in_memory(data, p, FMT_PNG)).convert("RGB")).transpose(2, 0, 1)
+    assert np.array_equal(got, _jpeg_rgb(O, data, nw, nh))
+
+
 def test_convert_refusals(L, golden):
     data = golden("in_420_base_355x237.jpg")
     p = L.default_params()
