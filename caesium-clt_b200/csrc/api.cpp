@@ -7,8 +7,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <exception>
 #include <fstream>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -655,24 +657,47 @@ int b200_compress_batch(const uint8_t *const *in, const size_t *in_len, int n, c
         } catch (const std::exception &e) { status[i] = make_status(B200_ERR_OUT_OF_MEMORY, e.what()); } catch (...) { status[i] = make_status(B200_ERR_INVALID_ARGUMENT, "unexpected failure"); }
         if (status[i].code) failed++;
     };
-    auto worker = [&]() {
-        if (!grouped) { for (;;) { int i = next.fetch_add(1); if (i >= n) break; one(i, i % ndev); } return; }
-        for (;;) {
-            const int i0 = next.fetch_add(K);
-            if (i0 >= n) break;
-            const int i1 = std::min(n, i0 + K), dev = chunk_id.fetch_add(1) % ndev;
-            std::vector<int> idx; for (int i = i0; i < i1; i++) idx.push_back(i);
-            std::vector<char> done(idx.size(), 0);
-            try { jpeg_compress_group(in, in_len, idx, params, dev, out, out_len, status, done); } catch (...) {}
-            for (size_t k = 0; k < idx.size(); k++) { if (!done[k]) one(idx[k], dev); else if (status[idx[k]].code) failed++; }
-        }
+    auto run_threads = [](int nt, const std::function<void()> &fn) {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back(fn);
+        fn();
+        for (auto &t : th) t.join();
     };
-    int max_workers = 8; { const char *e = getenv("B200_GROUP_WORKERS"); if (e) max_workers = std::max(1, std::min(32, atoi(e))); }
-    if (grouped) n_threads = std::max(1, std::min(n_threads, std::min(max_workers, (n + K - 1) / K)));
-    std::vector<std::thread> th;
-    for (int t = 1; t < n_threads; t++) th.emplace_back(worker);
-    worker();
-    for (auto &t : th) t.join();
+    // phase 1: JPEGs, K at a time, on a few group workers (each group is one long launch sequence; more workers than this only
+    // queue behind each other on the GPU).  Whatever a group could not take is left for phase 2.
+    std::vector<int> rest;
+    if (grouped) {
+        std::vector<int> jpegs;
+        for (int i = 0; i < n; i++) (b200_sniff_format(in[i], in_len[i]) == B200_FMT_JPEG ? jpegs : rest).push_back(i);
+        if (jpegs.size() < 2) { rest.insert(rest.end(), jpegs.begin(), jpegs.end()); jpegs.clear(); }
+        const int nj = (int)jpegs.size();
+        if (nj) {
+            std::mutex rest_mu;
+            int max_workers = 8; { const char *e = getenv("B200_GROUP_WORKERS"); if (e) max_workers = std::max(1, std::min(32, atoi(e))); }
+            auto group_worker = [&]() {
+                for (;;) {
+                    const int j0 = next.fetch_add(K);
+                    if (j0 >= nj) break;
+                    const int j1 = std::min(nj, j0 + K), dev = chunk_id.fetch_add(1) % ndev;
+                    std::vector<int> idx(jpegs.begin() + j0, jpegs.begin() + j1);
+                    std::vector<char> done(idx.size(), 0);
+                    try { jpeg_compress_group(in, in_len, idx, params, dev, out, out_len, status, done); } catch (...) {}
+                    for (size_t k = 0; k < idx.size(); k++) {
+                        if (done[k]) { if (status[idx[k]].code) failed++; }
+                        else { std::lock_guard<std::mutex> lk(rest_mu); rest.push_back(idx[k]); }
+                    }
+                }
+            };
+            run_threads(std::max(1, std::min(n_threads, std::min(max_workers, (nj + K - 1) / K))), group_worker);
+        }
+    } else for (int i = 0; i < n; i++) rest.push_back(i);
+    // phase 2: one image per call on every thread the caller allows (PNG, conversions' sources, progressive JPEGs, ...)
+    if (!rest.empty()) {
+        std::sort(rest.begin(), rest.end());
+        std::atomic<int> nr{0};
+        const int total = (int)rest.size();
+        run_threads(std::min(n_threads, total), [&]() { for (;;) { const int r = nr.fetch_add(1); if (r >= total) break; one(rest[r], rest[r] % ndev); } });
+    }
     return failed.load();
 }
 

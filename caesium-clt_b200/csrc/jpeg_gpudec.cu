@@ -128,7 +128,17 @@ struct DevWriteSink {
     }
     __device__ __forceinline__ void block_done() { flush(64); lo = 0; cur++; seek(); }
 };
+// The alternative (B200_DEC_WRITE=sparse): every non-zero coefficient is stored on its own into a buffer that was memset.
+struct SparseWriteSink {
+    const ge::Scan *scan; uint32_t cur, total; int16_t *ptr; int lo;
+    __device__ __forceinline__ void seek() { ptr = cur < total ? const_cast<int16_t *>(ge::locate(*scan, (int)cur).blk) : nullptr; }
+    __device__ __forceinline__ void clear() {}
+    __device__ __forceinline__ void coef(int k, int v) { if (ptr) ptr[k] = (int16_t)v; }
+    __device__ __forceinline__ void flush(int) {}
+    __device__ __forceinline__ void block_done() { cur++; seek(); }
+};
 
+template <class WriteSink>
 __global__ void __launch_bounds__(64) k_gd_write(const DecImage *__restrict__ imgs, const uint8_t *__restrict__ stream_all, const DecTable *__restrict__ tabs_all,
                                                  const DecState *__restrict__ A, const uint32_t *__restrict__ first)
 {
@@ -143,7 +153,7 @@ __global__ void __launch_bounds__(64) k_gd_write(const DecImage *__restrict__ im
     if (i >= sh.g.nsub) return;
     DecState st;
     if (i == 0) { st.p = 0; st.k = 0; st.b = 0; } else st = A[im.sub_off + i - 1];
-    DevWriteSink sk;
+    WriteSink sk;
     sk.scan = &ssc; sk.cur = first[im.sub_off + i] - first[im.sub_off]; sk.total = sh.g.total_blocks; sk.ptr = nullptr; sk.lo = st.k;
     sk.clear(); sk.seek();
     const DecState o = decode_subsequence(stream_all + im.stream_off, sh.g, sh.tabs, i, st, sk);
@@ -280,6 +290,8 @@ bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &er
     size_t tb = cap_temp;
     cub::DeviceScan::ExclusiveSum(d_temp, tb, d_cnt, d_off, (int)grp_total, st);
     k_gd_unstuff_scatter<<<gg, 128, 0, st>>>(dI, d_raw, d_off, d_stream);
+    static const bool sparse_write = [] { const char *e = getenv("B200_DEC_WRITE"); return e && !strcmp(e, "sparse"); }();
+    if (sparse_write) for (int n = 0; n < N; n++) CUD(cudaMemsetAsync(items[n].d_coefs, 0, (size_t)items[n].rd->geom().total_coefs * 2, st));
     // ---- rounds
     const dim3 gs(cdiv(max_sub, 64), N);
     const size_t ncta = (size_t)N * gs.x;                    // dirty flags: two buffers of one byte per CTA, by round parity
@@ -305,7 +317,8 @@ bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &er
     //      that their caller discards)
     tb = cap_temp;
     cub::DeviceScan::ExclusiveSum(d_temp, tb, d_nblk, d_first, (int)sub_total, st);
-    k_gd_write<<<gs, 64, 0, st>>>(dI, d_stream, dT, A, d_first);
+    if (sparse_write) k_gd_write<SparseWriteSink><<<gs, 64, 0, st>>>(dI, d_stream, dT, A, d_first);
+    else k_gd_write<DevWriteSink><<<gs, 64, 0, st>>>(dI, d_stream, dT, A, d_first);
     const dim3 gb(cdiv(max_blk, 128), N);
     k_gd_dc_gather<<<gb, 128, 0, st>>>(dI, d_dc, d_A, d_first, d_nblk);
     tb = cap_temp;
