@@ -108,9 +108,9 @@ __global__ void __launch_bounds__(64) k_gd_round(const DecImage *__restrict__ im
     }
 }
 
-// Write pass sink.  A block's 64 coefficients are staged in the thread's local memory and leave as eight 16-byte stores when
-// the block ends, zeros included -- so the coefficient buffer needs no memset and HBM sees whole 128-byte blocks instead of
-// scattered 2-byte stores.  A block that straddles subsequences is shared by position: each thread writes exactly the zigzag
+// Write pass sink, variant B200_DEC_WRITE=staged (NOT the default: it measured slower, see GpuDecoder::decode).  A block's 64
+// coefficients are staged in the thread's local memory and leave as eight 16-byte stores when the block ends, zeros included
+// -- so the coefficient buffer needs no memset and HBM sees whole 128-byte blocks instead of scattered 2-byte stores.  A block that straddles subsequences is shared by position: each thread writes exactly the zigzag
 // range [lo, hi) it decoded (ranges of neighbouring threads are disjoint and contiguous in the zigzag layout).
 struct DevWriteSink {
     const ge::Scan *scan; uint32_t cur, total; int16_t *ptr; int lo;
@@ -128,7 +128,7 @@ struct DevWriteSink {
     }
     __device__ __forceinline__ void block_done() { flush(64); lo = 0; cur++; seek(); }
 };
-// The alternative (B200_DEC_WRITE=sparse): every non-zero coefficient is stored on its own into a buffer that was memset.
+// The default: every non-zero coefficient is stored on its own into a buffer that was memset.
 struct SparseWriteSink {
     const ge::Scan *scan; uint32_t cur, total; int16_t *ptr; int lo;
     __device__ __forceinline__ void seek() { ptr = cur < total ? const_cast<int16_t *>(ge::locate(*scan, (int)cur).blk) : nullptr; }
@@ -290,7 +290,9 @@ bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &er
     size_t tb = cap_temp;
     cub::DeviceScan::ExclusiveSum(d_temp, tb, d_cnt, d_off, (int)grp_total, st);
     k_gd_unstuff_scatter<<<gg, 128, 0, st>>>(dI, d_raw, d_off, d_stream);
-    static const bool sparse_write = [] { const char *e = getenv("B200_DEC_WRITE"); return e && !strcmp(e, "sparse"); }();
+    // measured on the 4K bench set (tools/throughput.py, same box, alternating): sparse 3,750 images/s, staged 3,220 -- the
+    // local-memory round trip of the staged sink costs more than the memset and the partial-sector stores it avoids
+    static const bool sparse_write = [] { const char *e = getenv("B200_DEC_WRITE"); return !(e && !strcmp(e, "staged")); }();
     if (sparse_write) for (int n = 0; n < N; n++) CUD(cudaMemsetAsync(items[n].d_coefs, 0, (size_t)items[n].rd->geom().total_coefs * 2, st));
     // ---- rounds
     const dim3 gs(cdiv(max_sub, 64), N);
