@@ -490,8 +490,8 @@ b200_status png_to_jpeg(const uint8_t *in, size_t in_len, const b200_params *p, 
     return st;
 }
 
-// PNG source: samples are expanded to 8-bit RGB on the host (palette, grey, 16-bit -> high byte; alpha is dropped: the VP8X
-// alpha plane is outside this path) and go through the same K8.
+// PNG source: samples are expanded to 8-bit RGB on the host (palette, grey, 16-bit -> high byte; an opaque alpha channel is
+// discarded, a transparent one is refused below) and go through the same K8.
 b200_status png_to_webp(const uint8_t *in, size_t in_len, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
 {
     std::string err;
@@ -500,6 +500,18 @@ b200_status png_to_webp(const uint8_t *in, size_t in_len, const b200_params *p, 
     uint32_t nw = info.width, nh = info.height;
     if (p->width || p->height) compute_resize_dimensions(info.width, info.height, p->width, p->height, nw, nh);
     if (nw == 0 || nh == 0 || nw > 16383 || nh > 16383 || info.width > 65535 || info.height > 65535) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid dimensions for WebP");
+    // Transparency would need the VP8X container with an ALPH chunk (VP8L-coded alpha), which this path does not write: a PNG
+    // whose alpha is not fully opaque goes back to the host with code 3 rather than silently losing its transparency.
+    if (!info.trns.empty()) return make_status(B200_ERR_UNSUPPORTED, "PNG transparency needs the WebP alpha plane, outside the GPU path (route to caesium::convert_in_memory)");
+    if (info.color_type == 4 || info.color_type == 6) {
+        const size_t bps = (size_t)info.bit_depth / 8, px = (size_t)info.channels * bps;
+        bool opaque = true;
+        for (size_t y = 0; y < info.height && opaque; y++) {
+            const uint8_t *a = raw.data() + y * info.row_bytes + px - bps;
+            for (size_t x = 0; x < info.width; x++, a += px) if (a[0] != 0xFF || (bps == 2 && a[1] != 0xFF)) { opaque = false; break; }
+        }
+        if (!opaque) return make_status(B200_ERR_UNSUPPORTED, "PNG transparency needs the WebP alpha plane, outside the GPU path (route to caesium::convert_in_memory)");
+    }
     std::vector<uint8_t> rgb; int nc = 3;
     png_expand_planar(info, raw, false, rgb, nc);
     if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);

@@ -84,8 +84,12 @@ def test_convert_png_to_webp_matches_oracle(L, O):
     rgb = synth(90, 120, 3, seed=4)
     p = L.default_params(); p.webp_quality = 80
     assert L.convert_in_memory(pil_png(rgb), p, FMT_WEBP) == O.webp_encode(planar(rgb), 80)[0]
-    rgba = np.concatenate([rgb, synth(90, 120, 1, seed=5)], axis=2)                   # alpha is dropped on this path
-    assert L.convert_in_memory(pil_png(rgba), p, FMT_WEBP) == O.webp_encode(planar(rgb), 80)[0]
+    opaque = np.concatenate([rgb, np.full((90, 120, 1), 255, np.uint8)], axis=2)        # fully opaque alpha carries nothing
+    assert L.convert_in_memory(pil_png(opaque), p, FMT_WEBP) == O.webp_encode(planar(rgb), 80)[0]
+    rgba = np.concatenate([rgb, synth(90, 120, 1, seed=5)], axis=2)                   # real transparency: not this path's to drop
+    with pytest.raises(L.B200Error) as e:
+        L.convert_in_memory(pil_png(rgba), p, FMT_WEBP)
+    assert e.value.code == 3
     grey = synth(50, 70, 1, seed=6)
     assert L.convert_in_memory(pil_png(grey), p, FMT_WEBP) == O.webp_encode(planar(np.repeat(grey, 3, axis=2)), 80)[0]
     idx = rng.integers(0, 16, (40, 60)).astype(np.uint8)

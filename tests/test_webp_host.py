@@ -70,6 +70,21 @@ def test_host_writer_reproduces_oracle_file_from_oracle_stage_output(L, O, h, w,
     assert L.webp_write_levels(w, h, q, levels, modes) == want
 
 
+def test_transparent_png_is_not_silently_flattened(L):
+    """A PNG with real transparency cannot become a simple-format WebP without losing it: the call hands it back (code 3)
+    before touching the device; the same goes for lossless WebP."""
+    from pngutil import pil_png
+    rgba = np.concatenate([synth(20, 30, 3, seed=1), synth(20, 30, 1, seed=2)], axis=2)
+    p = L.default_params()
+    with pytest.raises(L.B200Error) as e:
+        L.convert_in_memory(pil_png(rgba), p, 3)
+    assert e.value.code == 3 and "alpha" in str(e.value)
+    p.webp_lossless = 1
+    with pytest.raises(L.B200Error) as e:
+        L.convert_in_memory(pil_png(rgba[:, :, :3].copy()), p, 3)
+    assert e.value.code == 3
+
+
 def test_host_writer_extreme_levels(L):
     # every token class incl. DCT_CAT6 (|v| up to 2047), random signs, all four modes, some skipped macroblocks
     rng = np.random.default_rng(3)
