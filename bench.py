@@ -144,7 +144,7 @@ def run_reference(args, rank, world):
         t_total += dt; imgs += n
     v = imgs * MP_PER_IMAGE / t_total
     sample = f"{n} images/step of the 3840x2160 q90 4:2:0 synthetic set, {cores} threads, oracle jpeg_lossy (progressive, optimised Huffman; no trellis / scan search)"
-    print(json.dumps({
+    _emit(({
         "impl": "reference", "metric": "megapixels/sec JPEG q=80 4K re-encode", "value": round(v, 2), "unit": "MP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t_total / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
@@ -156,7 +156,27 @@ def run_reference(args, rank, world):
     }))
 
 
+_RESULT_OUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too at the C level (NCCL's version banner under
+    torchrun), so file descriptor 1 is pointed at stderr for the whole run and the result line goes to a private duplicate
+    of the original stdout."""
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def _emit(obj):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -308,7 +328,7 @@ def main():
                "sample": f"{n} of the same 4K inputs, {cores} threads, oracle jpeg_lossy (restated reference: progressive + optimised Huffman, no trellis/scan search), {cdt:.1f} s"}
 
     if rank == 0:
-        print(json.dumps({
+        _emit(({
             "metric": "megapixels/sec JPEG q=80 4K re-encode", "value": round(value, 1), "unit": "MP/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",

@@ -240,7 +240,8 @@ bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &er
         for (int c = 0; c < g.ncomp; c++) for (int k = 0; k < (g.ncomp == 1 ? 1 : g.hs[c] * g.vs[c]); k++) { if (q >= 10) { err = "MCU too large"; return false; } G.dc_tbl[q] = ds.td[c]; G.ac_tbl[q] = ds.ta[c]; q++; }
         G.blocks_per_mcu = q;
         G.total_blocks = g.ncomp == 1 ? (uint32_t)(g.rbw[0] * g.rbh[0]) : (uint32_t)(g.mcux * g.mcuy * q);
-        G.nbits = nstream * 8; G.subseq_bits = SUBSEQ_BITS; G.nsub = (G.nbits + G.subseq_bits - 1) / G.subseq_bits;
+        static const int subseq_bits = [] { const char *e = getenv("B200_DEC_SUBSEQ"); const int v = e ? atoi(e) : 0; return v >= 128 && v <= 8192 && v % 32 == 0 ? v : (int)SUBSEQ_BITS; }();
+        G.nbits = nstream * 8; G.subseq_bits = subseq_bits; G.nsub = (G.nbits + G.subseq_bits - 1) / G.subseq_bits;
         if (G.nsub == 0) { err = "empty scan"; return false; }
         GpuEncPlan plan; const int16_t *base = items[n].d_coefs;
         gpuenc_plan(g, false, &base, 1, plan);
