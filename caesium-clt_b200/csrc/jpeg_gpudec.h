@@ -34,7 +34,9 @@ public:
     // short host sync per group of rounds.
     bool decode(std::vector<Item> &items, void *stream, std::string &err);
     int rounds_used = 0;
-    static constexpr int SUBSEQ_BITS = 1024, ROUNDS_PER_GROUP = 16, MAX_ROUNDS = 64;
+    // subsequence size: swept 512 .. 8192 on the 4K bench set under full batch load (tools/throughput.py): 512 -> 3,400
+    // images/s, 1024 -> 3,750, 2048 -> 3,970, 4096 -> 3,865, 8192 -> 3,560 (B200_DEC_SUBSEQ overrides)
+    static constexpr int SUBSEQ_BITS = 2048, ROUNDS_PER_GROUP = 16, MAX_ROUNDS = 64;
 private:
     uint8_t *h_raw = nullptr; size_t cap_hraw = 0;          // pinned staging of the entropy-coded segments
     uint8_t *d_raw = nullptr, *d_stream = nullptr; size_t cap_raw = 0, cap_stream = 0;
