@@ -44,28 +44,34 @@ __global__ void k_gd_unstuff_scatter(const DecImage *__restrict__ imgs, const ui
 
 // ---- synchronisation rounds ------------------------------------------------------------------------------------------------
 // Geometry and the Huffman tables are staged in shared memory: the decode loop indexes both dynamically.
-struct DecShared { Geometry g; DecTable tabs[8]; };
-__device__ __forceinline__ void stage_shared(DecShared &sh, const DecImage &im, const DecTable *__restrict__ tabs)
+struct DecShared { Geometry g; DecTables T; };
+__device__ __forceinline__ void stage_shared(DecShared &sh, const DecImage &im, const DecTables *__restrict__ tabs)
 {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(&im.g);
     uint32_t *dst = reinterpret_cast<uint32_t *>(&sh.g);
     for (int i = threadIdx.x; i < (int)(sizeof(Geometry) / 4); i += blockDim.x) dst[i] = src[i];
-    src = reinterpret_cast<const uint32_t *>(tabs); dst = reinterpret_cast<uint32_t *>(sh.tabs);
-    for (int i = threadIdx.x; i < (int)(sizeof(DecTable) * 8 / 4); i += blockDim.x) dst[i] = src[i];
+    // only what the image uses: its first-level tables, the used part of the second-level pool, the selector / header words
+    const int nlook = tabs->nlook * (LOOK_N / 2), next = (tabs->next + 1) / 2;
+    src = reinterpret_cast<const uint32_t *>(tabs->look); dst = reinterpret_cast<uint32_t *>(sh.T.look);
+    for (int i = threadIdx.x; i < nlook; i += blockDim.x) dst[i] = src[i];
+    src = reinterpret_cast<const uint32_t *>(tabs->ext); dst = reinterpret_cast<uint32_t *>(sh.T.ext);
+    for (int i = threadIdx.x; i < next; i += blockDim.x) dst[i] = src[i];
+    src = reinterpret_cast<const uint32_t *>(tabs->sel); dst = reinterpret_cast<uint32_t *>(sh.T.sel);
+    for (int i = threadIdx.x; i < 12; i += blockDim.x) dst[i] = src[i];          // sel[20] + nlook, next, ok, pad
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(64) k_gd_round0(const DecImage *__restrict__ imgs, const uint8_t *__restrict__ stream_all, const DecTable *__restrict__ tabs_all,
+__global__ void __launch_bounds__(64) k_gd_round0(const DecImage *__restrict__ imgs, const uint8_t *__restrict__ stream_all, const DecTables *__restrict__ tabs_all,
                                                   DecState *__restrict__ A, uint8_t *__restrict__ chg, uint32_t *__restrict__ nblk)
 {
     __shared__ DecShared sh;
     const DecImage &im = imgs[blockIdx.y];
     if (blockIdx.x * blockDim.x >= im.g.nsub) return;
-    stage_shared(sh, im, tabs_all + 8 * blockIdx.y);
+    stage_shared(sh, im, tabs_all + blockIdx.y);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= sh.g.nsub) return;
     NullSink sk; DecState st; st.p = i * sh.g.subseq_bits; st.k = 0; st.b = 0;
-    A[im.sub_off + i] = decode_subsequence(stream_all + im.stream_off, sh.g, sh.tabs, i, st, sk);
+    A[im.sub_off + i] = decode_subsequence(stream_all + im.stream_off, sh.g, sh.T, i, st, sk);
     nblk[im.sub_off + i] = sk.nblk; chg[im.sub_off + i] = 0;       // epoch 0: "changed in round 0"
 }
 
@@ -77,7 +83,7 @@ __device__ __forceinline__ void store_state(DecState *p, const DecState &s) { un
 // if it was the old one the predecessor's epoch makes it run again next round.  A CTA whose 64 predecessors all kept their
 // exits is "clean": it leaves after one byte read (dirty flags double-buffered by round parity), and an image whose
 // previous round changed nothing leaves at once, so the tail rounds of a launch group cost almost nothing.
-__global__ void __launch_bounds__(64) k_gd_round(const DecImage *__restrict__ imgs, const uint8_t *__restrict__ stream_all, const DecTable *__restrict__ tabs_all,
+__global__ void __launch_bounds__(64) k_gd_round(const DecImage *__restrict__ imgs, const uint8_t *__restrict__ stream_all, const DecTables *__restrict__ tabs_all,
                                                  DecState *__restrict__ S, uint8_t *__restrict__ epoch, uint8_t *__restrict__ dirty_in, uint8_t *__restrict__ dirty_out,
                                                  uint32_t *__restrict__ nblk, uint32_t *__restrict__ any_changed /*[image]*/,
                                                  const uint32_t *__restrict__ prev_changed /*[image] of the round before, or null*/, int r)
@@ -95,11 +101,11 @@ __global__ void __launch_bounds__(64) k_gd_round(const DecImage *__restrict__ im
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, gi = im.sub_off + i;
     const bool mine = i > 0 && i < nsub && epoch[gi - 1] == (uint8_t)(r - 1);
     if (!__syncthreads_or(mine)) return;             // nobody in this CTA has to re-decode: skip the table staging too
-    stage_shared(sh, im, tabs_all + 8 * blockIdx.y);
+    stage_shared(sh, im, tabs_all + blockIdx.y);
     if (!mine) return;
     NullSink sk;
     const DecState st = load_state(S + gi - 1), old = load_state(S + gi);
-    const DecState o = decode_subsequence(stream_all + im.stream_off, sh.g, sh.tabs, i, st, sk);
+    const DecState o = decode_subsequence(stream_all + im.stream_off, sh.g, sh.T, i, st, sk);
     nblk[gi] = sk.nblk;
     if (!same_state(o, old)) {
         store_state(S + gi, o); epoch[gi] = (uint8_t)r;
@@ -108,56 +114,33 @@ __global__ void __launch_bounds__(64) k_gd_round(const DecImage *__restrict__ im
     }
 }
 
-// Write pass sink, variant B200_DEC_WRITE=staged (NOT the default: it measured slower, see GpuDecoder::decode).  A block's 64
-// coefficients are staged in the thread's local memory and leave as eight 16-byte stores when the block ends, zeros included
-// -- so the coefficient buffer needs no memset and HBM sees whole 128-byte blocks instead of scattered 2-byte stores.  A block that straddles subsequences is shared by position: each thread writes exactly the zigzag
-// range [lo, hi) it decoded (ranges of neighbouring threads are disjoint and contiguous in the zigzag layout).
-struct DevWriteSink {
-    const ge::Scan *scan; uint32_t cur, total; int16_t *ptr; int lo;
-    uint4 buf[8];
-    __device__ __forceinline__ void seek() { ptr = cur < total ? const_cast<int16_t *>(ge::locate(*scan, (int)cur).blk) : nullptr; }
-    __device__ __forceinline__ void clear() { for (int i = 0; i < 8; i++) buf[i] = make_uint4(0u, 0u, 0u, 0u); }
-    __device__ __forceinline__ void coef(int k, int v) { reinterpret_cast<int16_t *>(buf)[k] = (int16_t)v; }
-    __device__ __forceinline__ void flush(int hi)
-    {
-        if (ptr) {
-            if (lo == 0 && hi == 64) { uint4 *d = reinterpret_cast<uint4 *>(ptr); for (int i = 0; i < 8; i++) d[i] = buf[i]; }
-            else { const int16_t *s = reinterpret_cast<const int16_t *>(buf); for (int k = lo; k < hi; k++) ptr[k] = s[k]; }
-        }
-        clear();
-    }
-    __device__ __forceinline__ void block_done() { flush(64); lo = 0; cur++; seek(); }
-};
-// The default: every non-zero coefficient is stored on its own into a buffer that was memset.
+// Write pass sink: every non-zero coefficient is stored on its own into a buffer that was memset.  (A variant that staged whole
+// blocks in local memory and stored them with 16-byte writes, without the memset, measured slower -- 3,220 vs 3,750 images/s --
+// and was removed.)  The block address moves with a gd::Cursor: no divisions inside the decode loop.
 struct SparseWriteSink {
-    const ge::Scan *scan; uint32_t cur, total; int16_t *ptr; int lo;
-    __device__ __forceinline__ void seek() { ptr = cur < total ? const_cast<int16_t *>(ge::locate(*scan, (int)cur).blk) : nullptr; }
-    __device__ __forceinline__ void clear() {}
+    const Walk *walk; int16_t *coefs; uint32_t cur, total; Cursor c; int16_t *ptr;
+    __device__ __forceinline__ void seek() { c.seek(*walk, cur); ptr = cur < total ? coefs + c.offset(*walk) : nullptr; }
     __device__ __forceinline__ void coef(int k, int v) { if (ptr) ptr[k] = (int16_t)v; }
-    __device__ __forceinline__ void flush(int) {}
-    __device__ __forceinline__ void block_done() { cur++; seek(); }
+    __device__ __forceinline__ void block_done() { cur++; c.next(*walk); ptr = cur < total ? coefs + c.offset(*walk) : nullptr; }
 };
 
-template <class WriteSink>
-__global__ void __launch_bounds__(64) k_gd_write(const DecImage *__restrict__ imgs, const uint8_t *__restrict__ stream_all, const DecTable *__restrict__ tabs_all,
+__global__ void __launch_bounds__(64) k_gd_write(const DecImage *__restrict__ imgs, const uint8_t *__restrict__ stream_all, const DecTables *__restrict__ tabs_all,
                                                  const DecState *__restrict__ A, const uint32_t *__restrict__ first)
 {
     __shared__ DecShared sh;
-    __shared__ ge::Scan ssc;
+    __shared__ Walk walk;
     const DecImage &im = imgs[blockIdx.y];
     if (blockIdx.x * blockDim.x >= im.g.nsub) return;
-    stage_shared(sh, im, tabs_all + 8 * blockIdx.y);
-    if (threadIdx.x == 0) ssc = im.scan;
-    __syncthreads();
+    if (threadIdx.x < sizeof(Walk) / 4) reinterpret_cast<uint32_t *>(&walk)[threadIdx.x] = reinterpret_cast<const uint32_t *>(&im.walk)[threadIdx.x];
+    stage_shared(sh, im, tabs_all + blockIdx.y);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= sh.g.nsub) return;
     DecState st;
     if (i == 0) { st.p = 0; st.k = 0; st.b = 0; } else st = A[im.sub_off + i - 1];
-    WriteSink sk;
-    sk.scan = &ssc; sk.cur = first[im.sub_off + i] - first[im.sub_off]; sk.total = sh.g.total_blocks; sk.ptr = nullptr; sk.lo = st.k;
-    sk.clear(); sk.seek();
-    const DecState o = decode_subsequence(stream_all + im.stream_off, sh.g, sh.tabs, i, st, sk);
-    if (o.k > sk.lo) sk.flush(o.k);                 // the block this subsequence ends inside: our part of it
+    SparseWriteSink sk;
+    sk.walk = &walk; sk.coefs = const_cast<int16_t *>(im.scan.coef); sk.cur = first[im.sub_off + i] - first[im.sub_off]; sk.total = sh.g.total_blocks;
+    sk.seek();
+    decode_subsequence(stream_all + im.stream_off, sh.g, sh.T, i, st, sk);
 }
 
 // ---- DC: gather differences component-major, inclusive scan, subtract the component's base, scatter ------------------
@@ -246,6 +229,7 @@ bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &er
         GpuEncPlan plan; const int16_t *base = items[n].d_coefs;
         gpuenc_plan(g, false, &base, 1, plan);
         im.scan = plan.scans[0];
+        im.walk = make_walk(im.scan);
         im.raw_off = (uint32_t)raw_total; im.nraw = (uint32_t)nraw; raw_total += align_up(nraw + 16, 16);
         im.stream_off = (uint32_t)stream_total; stream_total += align_up((size_t)nstream + 32, 16);
         im.grp_off = grp_total; im.ngrp = (uint32_t)((nraw + 15) / 16); grp_total += im.ngrp;
@@ -255,7 +239,7 @@ bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &er
     }
     if (raw_total >= (1ull << 31) || stream_total >= (1ull << 31)) { err = "decode batch too large"; return false; }
     // ---- buffers
-    const size_t o_img = 0, o_tab = align_up(sizeof(DecImage) * N, 256), o_flag = o_tab + align_up(sizeof(DecTable) * 8 * N, 256);
+    const size_t o_img = 0, o_tab = align_up(sizeof(DecImage) * N, 256), o_flag = o_tab + align_up(sizeof(DecTables) * N, 256);
     const size_t par_bytes = o_flag + align_up((size_t)4 * N * (MAX_ROUNDS + 2), 256);
     if (!growd(h_raw, cap_hraw, raw_total + 64, true, err) || !growd(d_raw, cap_raw, raw_total + 64, false, err) || !growd(d_stream, cap_stream, stream_total + 64, false, err) ||
         !growd(d_cnt, cap_cnt, (size_t)grp_total * 4 + 4, false, err) || !growd(d_off, cap_off, (size_t)grp_total * 4 + 4, false, err) ||
@@ -270,19 +254,23 @@ bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &er
     cub::DeviceScan::InclusiveSum((void *)nullptr, t3, d_dc, d_dcs, (int)blk_total, st);
     if (!growd(d_temp, cap_temp, std::max(t1, std::max(t2, t3)) + 256, false, err)) return false;
     // ---- parameters + raw bytes
-    memcpy(h_par + o_img, imgs.data(), sizeof(DecImage) * N);
-    DecTable *ht = reinterpret_cast<DecTable *>(h_par + o_tab);
-    memset(ht, 0, sizeof(DecTable) * 8 * N);
+    DecTables *ht = reinterpret_cast<DecTables *>(h_par + o_tab);
+    std::vector<char> tables_ok((size_t)N, 1);
     for (int n = 0; n < N; n++) {
         const JpegReader &rd = *items[n].rd;
-        for (int id = 0; id < 4; id++) for (int kind = 0; kind < 2; kind++) if (rd.dht_present(kind, id)) build_dec_table(rd.dht_bits(kind, id), rd.dht_vals(kind, id), ht[8 * n + kind * 4 + id]);
+        const uint8_t *db[8], *dv[8];
+        for (int id = 0; id < 4; id++) for (int kind = 0; kind < 2; kind++) { const bool pr = rd.dht_present(kind, id); db[kind * 4 + id] = pr ? rd.dht_bits(kind, id) : nullptr; dv[kind * 4 + id] = pr ? rd.dht_vals(kind, id) : nullptr; }
+        // tables that do not fit the second-level pool: the kernels run on an all-invalid table set and the image is reported
+        // NOT_CONVERGED, which sends it to the host decoder
+        tables_ok[n] = build_dec_tables(db, dv, imgs[n].g, ht[n]) ? 1 : 0;
         memcpy(h_raw + imgs[n].raw_off, rd.data() + items[n].ds->ecs_begin, imgs[n].nraw);
     }
+    memcpy(h_par + o_img, imgs.data(), sizeof(DecImage) * N);
     memset(h_par + o_flag, 0, (size_t)4 * N * (MAX_ROUNDS + 2));
     CUD(cudaMemcpyAsync(d_par, h_par, par_bytes, cudaMemcpyHostToDevice, st));
     CUD(cudaMemcpyAsync(d_raw, h_raw, raw_total, cudaMemcpyHostToDevice, st));
     const DecImage *dI = reinterpret_cast<const DecImage *>(d_par + o_img);
-    const DecTable *dT = reinterpret_cast<const DecTable *>(d_par + o_tab);
+    const DecTables *dT = reinterpret_cast<const DecTables *>(d_par + o_tab);
     uint32_t *dF = reinterpret_cast<uint32_t *>(d_par + o_flag);
     uint32_t *hF = reinterpret_cast<uint32_t *>(h_par + o_flag);
     // ---- unstuff
@@ -291,10 +279,7 @@ bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &er
     size_t tb = cap_temp;
     cub::DeviceScan::ExclusiveSum(d_temp, tb, d_cnt, d_off, (int)grp_total, st);
     k_gd_unstuff_scatter<<<gg, 128, 0, st>>>(dI, d_raw, d_off, d_stream);
-    // measured on the 4K bench set (tools/throughput.py, same box, alternating): sparse 3,750 images/s, staged 3,220 -- the
-    // local-memory round trip of the staged sink costs more than the memset and the partial-sector stores it avoids
-    static const bool sparse_write = [] { const char *e = getenv("B200_DEC_WRITE"); return !(e && !strcmp(e, "staged")); }();
-    if (sparse_write) for (int n = 0; n < N; n++) CUD(cudaMemsetAsync(items[n].d_coefs, 0, (size_t)items[n].rd->geom().total_coefs * 2, st));
+    for (int n = 0; n < N; n++) CUD(cudaMemsetAsync(items[n].d_coefs, 0, (size_t)items[n].rd->geom().total_coefs * 2, st));
     // ---- rounds
     const dim3 gs(cdiv(max_sub, 64), N);
     const size_t ncta = (size_t)N * gs.x;                    // dirty flags: two buffers of one byte per CTA, by round parity
@@ -314,14 +299,13 @@ bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &er
         for (int n = 0; n < N; n++) if (!conv[n]) for (int r = first_round; r < rounds; r++) if (hF[(size_t)r * N + n] == 0) { conv[n] = 1; nconv++; break; }
     }
     rounds_used = rounds;
-    for (int n = 0; n < N; n++) items[n].result = conv[n] ? OK : NOT_CONVERGED;
+    for (int n = 0; n < N; n++) items[n].result = conv[n] && tables_ok[n] ? OK : NOT_CONVERGED;
     if (nconv == 0) return true;
     // ---- block counts -> first block of each subsequence -> write -> DC (images that did not converge produce garbage
     //      that their caller discards)
     tb = cap_temp;
     cub::DeviceScan::ExclusiveSum(d_temp, tb, d_nblk, d_first, (int)sub_total, st);
-    if (sparse_write) k_gd_write<SparseWriteSink><<<gs, 64, 0, st>>>(dI, d_stream, dT, A, d_first);
-    else k_gd_write<DevWriteSink><<<gs, 64, 0, st>>>(dI, d_stream, dT, A, d_first);
+    k_gd_write<<<gs, 64, 0, st>>>(dI, d_stream, dT, A, d_first);
     const dim3 gb(cdiv(max_blk, 128), N);
     k_gd_dc_gather<<<gb, 128, 0, st>>>(dI, d_dc, d_A, d_first, d_nblk);
     tb = cap_temp;

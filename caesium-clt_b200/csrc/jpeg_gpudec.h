@@ -18,6 +18,7 @@ struct DecImage {               // one image of a decode batch (device-visible)
     uint32_t blk_off;           // first block of this image in the DC arrays
     gd::Geometry g;
     ge::Scan scan;              // output addressing (scan.coef = this image's coefficient buffer)
+    gd::Walk walk;              // the same, in the division-free form the write pass steps through
 };
 
 class GpuDecoder {
@@ -45,7 +46,7 @@ private:
     uint8_t *d_chgA = nullptr, *d_chgB = nullptr; size_t cap_chgA = 0, cap_chgB = 0;   // epoch of the last change per subsequence; dirty flags per CTA (x2)
     uint32_t *d_nblk = nullptr, *d_first = nullptr; size_t cap_nblk = 0, cap_first = 0;
     int32_t *d_dc = nullptr, *d_dcs = nullptr; size_t cap_dc = 0, cap_dcs = 0;
-    uint8_t *d_par = nullptr, *h_par = nullptr; size_t cap_par = 0, cap_hpar = 0;   // DecImage[] | DecTable[8][] | round flags
+    uint8_t *d_par = nullptr, *h_par = nullptr; size_t cap_par = 0, cap_hpar = 0;   // DecImage[] | DecTables[] | round flags
     uint8_t *d_temp = nullptr; size_t cap_temp = 0;
 };
 

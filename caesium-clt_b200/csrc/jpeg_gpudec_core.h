@@ -22,7 +22,7 @@
 namespace b200 {
 namespace gd {
 
-struct DecTable {               // one Huffman table, decode form (jdhuff.c jpeg_make_d_derived_tbl)
+struct DecTable {               // one Huffman table, jdhuff.c form (jpeg_make_d_derived_tbl): the REFERENCE the kernel form is checked against
     uint16_t look[512];         // 9-bit lookahead: (len << 8) | symbol, 0 = code longer than 9 bits (or invalid)
     int32_t maxcode[18];        // maxcode[l] = largest code of length l (-1 if none); maxcode[17] = sentinel
     int32_t valoff[17];         // vals index = valoff[l] + code
@@ -75,30 +75,146 @@ struct Geometry {               // what the decoder needs to know about the scan
     uint32_t nsub;              // number of subsequences
 };
 
+// ---- decode tables, kernel form --------------------------------------------------------------------------------------------
+// All Huffman tables of one image, laid out for a loop-free symbol decode: a 9-bit first-level table per Huffman table
+// that resolves every code of up to 9 bits in one read, and for each 9-bit prefix under which longer codes live a
+// second-level table of 2^(Lmax - 9) entries (Lmax = longest code under that prefix) drawn from one shared pool.  Canonical
+// codes put the long codes at the top of the code space, so only a handful of prefixes need a second level (Annex K luminance
+// AC: 5 prefixes, < 300 entries).  Entry format, both levels: (code length << 8) | symbol; first level only: bit 15 set =
+// "second level": bits 11..13 = index bits - 1, bits 0..10 = pool offset.  A bit pattern that is no code at all decodes as
+// (16, 0) -- "skip 16 bits" -- exactly what the canonical jdhuff.c search (decode_symbol above) answers for it.
+constexpr int LOOK_BITS = 9, LOOK_N = 1 << LOOK_BITS, MAX_TABLES = 8, EXT_N = 1536;
+struct DecTables {
+    uint16_t look[MAX_TABLES * LOOK_N];     // first level of table slot t at look[t * LOOK_N]
+    uint16_t ext[EXT_N];                    // second-level pool
+    uint16_t sel[20];                       // [2 * q + (AC ? 1 : 0)] -> first-level offset of block q's DC / AC table
+    uint16_t nlook, next;                   // slots / pool entries in use (what has to be staged)
+    uint16_t ok, pad_;                      // 0: the tables did not fit the pool (the image is decoded on the host instead)
+};
+
+// Build the kernel form from DHT payloads.  dht_bits[kind*4+id] / dht_vals[...] = BITS[17] / HUFFVAL of table (kind, id), null if
+// absent; the scan's table use comes from g.dc_tbl / g.ac_tbl.  Returns false (and leaves a harmless all-invalid table set) when
+// the second-level pool would overflow or a DHT is over-subscribed.
+inline bool build_dec_tables(const uint8_t *const dht_bits[8], const uint8_t *const dht_vals[8], const Geometry &g, DecTables &T)
+{
+    const uint16_t INVALID = (uint16_t)(16 << 8);
+    for (int i = 0; i < MAX_TABLES * LOOK_N; i++) T.look[i] = INVALID;
+    for (int i = 0; i < EXT_N; i++) T.ext[i] = INVALID;
+    for (int i = 0; i < 20; i++) T.sel[i] = 0;
+    T.nlook = 1; T.next = 0; T.ok = 0; T.pad_ = 0;
+    int slot_of[8]; for (int i = 0; i < 8; i++) slot_of[i] = -1;
+    int nslot = 0; bool ok = true;
+    for (int q = 0; q < g.blocks_per_mcu && q < 10; q++) for (int ac = 0; ac < 2; ac++) {
+        const int t = ac * 4 + ((ac ? g.ac_tbl[q] : g.dc_tbl[q]) & 3);
+        if (slot_of[t] < 0) slot_of[t] = nslot++;
+        T.sel[2 * q + ac] = (uint16_t)(slot_of[t] * LOOK_N);
+    }
+    uint32_t next = 0;
+    for (int t = 0; t < 8 && ok; t++) {
+        if (slot_of[t] < 0) continue;
+        if (!dht_bits[t]) { ok = false; break; }
+        uint16_t *look = T.look + slot_of[t] * LOOK_N;
+        const uint8_t *bits = dht_bits[t], *vals = dht_vals[t];
+        // pass 1: canonical codes; short ones fill the first level, long ones record the longest length per prefix
+        uint8_t lmax[LOOK_N]; for (int i = 0; i < LOOK_N; i++) lmax[i] = 0;
+        uint32_t code = 0; int p = 0;
+        for (int l = 1; l <= 16 && ok; l++) {
+            for (int i = 0; i < bits[l]; i++, p++, code++) {
+                if (p >= 256 || code >= (1u << l)) { ok = false; break; }
+                if (l <= LOOK_BITS) { const uint32_t first = code << (LOOK_BITS - l); for (uint32_t k = 0; k < (1u << (LOOK_BITS - l)); k++) look[first + k] = (uint16_t)((l << 8) | vals[p]); }
+                else { const uint32_t pre = code >> (l - LOOK_BITS); if (lmax[pre] < l) lmax[pre] = (uint8_t)l; }
+            }
+            code <<= 1;
+        }
+        if (!ok) break;
+        // pass 2: second-level tables
+        for (int pre = 0; pre < LOOK_N; pre++) if (lmax[pre]) {
+            const uint32_t nb = lmax[pre] - LOOK_BITS;
+            if (next + (1u << nb) > (uint32_t)EXT_N || next > 0x7FFu) { ok = false; break; }
+            look[pre] = (uint16_t)(0x8000u | ((nb - 1) << 11) | next);
+            next += 1u << nb;
+        }
+        if (!ok) break;
+        code = 0; p = 0;
+        for (int l = 1; l <= 16; l++) {
+            for (int i = 0; i < bits[l]; i++, p++, code++) if (l > LOOK_BITS) {
+                const uint32_t pre = code >> (l - LOOK_BITS), e = look[pre], nb = ((e >> 11) & 7) + 1, off = e & 0x7FF;
+                const uint32_t low = code & ((1u << (l - LOOK_BITS)) - 1), first = low << (LOOK_BITS + nb - l);
+                for (uint32_t k = 0; k < (1u << (LOOK_BITS + nb - l)); k++) T.ext[off + first + k] = (uint16_t)((l << 8) | vals[p]);
+            }
+            code <<= 1;
+        }
+    }
+    if (!ok) {
+        for (int i = 0; i < MAX_TABLES * LOOK_N; i++) T.look[i] = INVALID;
+        for (int i = 0; i < EXT_N; i++) T.ext[i] = INVALID;
+        T.nlook = 1; T.next = 0; T.ok = 0;
+        return false;
+    }
+    T.nlook = (uint16_t)(nslot ? nslot : 1); T.next = (uint16_t)next; T.ok = 1;
+    return true;
+}
+
+// one symbol from the top bits of `bits` (32 valid bits) with the table at first-level offset `base`: (length << 8) | symbol
+GE_HD uint32_t lookup_symbol(const DecTables &T, uint32_t base, uint32_t bits)
+{
+    uint32_t e = T.look[base + (bits >> (32 - LOOK_BITS))];
+    if (e & 0x8000u) { const uint32_t nb = ((e >> 11) & 7u) + 1u; e = T.ext[(e & 0x7FFu) + ((bits << LOOK_BITS) >> (32 - nb))]; }
+    return e;
+}
+
+// ---- output addressing without divisions -------------------------------------------------------------------------------------
+// Scan-order unit -> coefficient offset, walked incrementally: the write pass finishes a block every dozen symbols, and
+// ge::locate()'s divisions were half of its instructions.  A non-interleaved scan is the special case "one block per MCU".
+struct Walk {
+    int bpm, mcux;              // blocks per MCU, MCUs per row (single-component scan: 1, real blocks per row)
+    long long base[10];         // int16 offset of block q of MCU (0, 0)
+    int colstep[10], rowstep[10];   // offset step to the next MCU in the row / to the next MCU row
+};
+inline Walk make_walk(const ge::Scan &s)
+{
+    Walk w{};
+    if (s.ns == 1) { w.bpm = 1; w.mcux = s.rbw; w.base[0] = s.comp_off[0]; w.colstep[0] = 64; w.rowstep[0] = s.bw[0] * 64; return w; }
+    w.bpm = s.blocks_per_mcu; w.mcux = s.mcux;
+    int q = 0;
+    for (int i = 0; i < s.ns; i++) for (int by = 0; by < s.vs[i]; by++) for (int bx = 0; bx < s.hs[i]; bx++, q++) if (q < 10) {
+        w.base[q] = s.comp_off[i] + ((long long)by * s.bw[i] + bx) * 64;
+        w.colstep[q] = s.hs[i] * 64; w.rowstep[q] = s.vs[i] * s.bw[i] * 64;
+    }
+    return w;
+}
+struct Cursor {                 // position of one scan-order unit
+    int q, mx, my;
+    GE_HD void seek(const Walk &w, uint32_t u) { const uint32_t m = u / (uint32_t)w.bpm; q = (int)(u - m * (uint32_t)w.bpm); my = (int)(m / (uint32_t)w.mcux); mx = (int)(m - (uint32_t)my * (uint32_t)w.mcux); }
+    GE_HD void next(const Walk &w) { if (++q == w.bpm) { q = 0; if (++mx == w.mcux) { mx = 0; my++; } } }
+    GE_HD long long offset(const Walk &w) const { return w.base[q] + (long long)my * w.rowstep[q] + (long long)mx * w.colstep[q]; }
+};
+
 // Decode from state `st` until the position leaves subsequence `i` (p >= (i+1)*S) or the stream ends.  Sink receives
-// coef(block_ordinal_since_start, k, value) for every coefficient (DC as raw difference) and block_done().
+// coef(k, value) for every coefficient (DC as raw difference) and block_done().
 template <class Sink>
-GE_HD DecState decode_subsequence(const uint8_t *__restrict__ stream, const Geometry &g, const DecTable *__restrict__ tabs /*[0..3] DC ids, [4..7] AC ids*/,
-                                  uint32_t i, DecState st, Sink &sk)
+GE_HD DecState decode_subsequence(const uint8_t *__restrict__ stream, const Geometry &g, const DecTables &T, uint32_t i, DecState st, Sink &sk)
 {
     const uint32_t end = (i + 1) * g.subseq_bits < g.nbits ? (i + 1) * g.subseq_bits : g.nbits;
     uint32_t p = st.p; int k = st.k, b = st.b;
-    // 64-bit bit buffer in registers, left aligned at position p, refilled one aligned word at a time: the stream load is
-    // off the critical path except once every 32 consumed bits (a symbol consumes at most 16 + 15 bits, so >= 32 buffered
-    // bits always suffice)
-    uint32_t nextw = (p >> 5) + 2;
-    unsigned long long buf = (((unsigned long long)load_be32(stream, p >> 5) << 32) | load_be32(stream, (p >> 5) + 1)) << (p & 31);
-    int have = 64 - (int)(p & 31);
-    uint32_t pbuf = p;                              // position the buffer is aligned to
+    // Three-word window over the stream: w0 / w1 hold the words the next 32 bits come from, w2 is fetched one word ahead so
+    // the load is off the critical path.  A symbol consumes at most 16 + 15 bits, so the window moves by at most one word.
+    uint32_t wi = p >> 5;
+    uint32_t w0 = load_be32(stream, wi), w1 = load_be32(stream, wi + 1), w2 = load_be32(stream, wi + 2);
+    const int bpm = g.blocks_per_mcu;
     while (p < end) {
-        { const int used = (int)(p - pbuf); if (used) { buf <<= used; have -= used; pbuf = p; } }
-        if (have < 32) { buf |= (unsigned long long)load_be32(stream, nextw++) << (32 - have); have += 32; }
-        const uint32_t bits = (uint32_t)(buf >> 32);
+        if ((p >> 5) != wi) { wi = p >> 5; w0 = w1; w1 = w2; w2 = load_be32(stream, wi + 2); }
+        const uint32_t sh = p & 31;
+#if defined(__CUDA_ARCH__)
+        const uint32_t bits = __funnelshift_l(w1, w0, sh);
+#else
+        const uint32_t bits = sh ? (w0 << sh) | (w1 >> (32 - sh)) : w0;
+#endif
         // One uniform body for DC and AC symbols (a DC symbol is "run 0, category s at index 0"), selects instead of
         // branches: the lanes of a warp sit at unrelated points of their blocks, so divergent paths would serialise.
         const bool dc = k == 0;
-        int len;
-        const int sym = decode_symbol(tabs[dc ? g.dc_tbl[b] : 4 + g.ac_tbl[b]], bits, &len);
+        const uint32_t e = lookup_symbol(T, T.sel[2 * b + (dc ? 0 : 1)], bits);
+        const int len = (int)(e >> 8), sym = (int)(e & 0xFF);
         const int r = dc ? 0 : (sym >> 4), s = sym & 15;
         const uint32_t ext = s ? (bits << len) >> (32 - s) : 0u;
         const int v = s ? ((int)ext < (1 << (s - 1)) ? (int)ext - (1 << s) + 1 : (int)ext) : 0;
@@ -107,7 +223,7 @@ GE_HD DecState decode_subsequence(const uint8_t *__restrict__ stream, const Geom
         if (!eob_or_zrl) sk.coef(kw, v);
         k = eob_or_zrl ? (r == 15 ? k + 16 : 64) : kw + 1;
         p += (uint32_t)(len + s);
-        if (k >= 64) { k = 0; b++; if (b == g.blocks_per_mcu) b = 0; sk.block_done(); }
+        if (k >= 64) { k = 0; b++; if (b == bpm) b = 0; sk.block_done(); }
     }
     DecState o; o.p = p; o.k = (uint16_t)k; o.b = (uint16_t)b;
     return o;

@@ -21,19 +21,6 @@ using namespace ge;
 #define CU(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(e_); return false; } } while (0)
 
 // ---- kernels ------------------------------------------------------------------------------------------------------
-__global__ void k_ge_classify(const Scan *__restrict__ scans, uint32_t *__restrict__ meta, int *__restrict__ evkey, uint32_t *__restrict__ tail)
-{
-    const Scan s = scans[blockIdx.y];
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= s.nblocks) return;
-    const BlockRef b = locate(s, u);
-    const uint32_t m = classify(s, b.blk);
-    const long long g = s.unit_base + u;
-    meta[g] = m;
-    evkey[g] = meta_event(m) ? (int)g : -1;
-    tail[g] = (uint32_t)meta_tail(m);
-}
-
 __global__ void k_ge_groups(const Scan *__restrict__ scans, const uint32_t *__restrict__ meta, const int *__restrict__ evkey,
                             const int *__restrict__ prev, const uint32_t *__restrict__ tsum, uint32_t *__restrict__ gcount)
 {
@@ -46,23 +33,6 @@ __global__ void k_ge_groups(const Scan *__restrict__ scans, const uint32_t *__re
     else { const long long last = s.unit_base + s.nblocks - 1; pg = max(prev[last], evkey[last]); }
     const int pl = pg >= s.unit_base ? (int)(pg - s.unit_base) : -1;
     assign_groups(meta + s.unit_base, tsum + s.unit_base, s.nblocks, pl, b, gcount + s.unit_base);
-}
-
-__global__ void k_ge_hist(const Scan *__restrict__ scans, const uint32_t *__restrict__ gcount, uint32_t *__restrict__ hist)
-{
-    __shared__ uint32_t h[4 * 256];
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) h[i] = 0;
-    __syncthreads();
-    const Scan s = scans[blockIdx.y];
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u < s.nblocks) {
-        auto add = [&](int idx) { atomicAdd(&h[idx], 1u); };
-        HistSink<decltype(add)> sk(add);
-        gen_block(s, locate(s, u), gcount[s.unit_base + u], sk);
-    }
-    __syncthreads();
-    uint32_t *g = hist + (size_t)s.tab_base * 256;
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) if (h[i]) atomicAdd(&g[i], h[i]);
 }
 
 // jchuff.c jpeg_gen_optimal_table with the two minimum searches spread over a warp (ties resolve to the LARGEST index,
@@ -129,16 +99,6 @@ __global__ void k_ge_tables(const uint32_t *__restrict__ hist, Table *__restrict
     }
 }
 
-__global__ void k_ge_len(const Scan *__restrict__ scans, const uint32_t *__restrict__ gcount, const Table *__restrict__ tabs, uint32_t *__restrict__ bitlen)
-{
-    const Scan s = scans[blockIdx.y];
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= s.nblocks) return;
-    LenSink sk; sk.tabs = tabs + s.tab_base;
-    gen_block(s, locate(s, u), gcount[s.unit_base + u], sk);
-    bitlen[s.unit_base + u] = (uint32_t)sk.bits;
-}
-
 __global__ void k_ge_totals(const Scan *__restrict__ scans, int nscans, const uint32_t *__restrict__ bitlen, const uint32_t *__restrict__ bitoff, uint32_t *__restrict__ total)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -155,18 +115,6 @@ __global__ void k_ge_zero(const Scan *__restrict__ scans, const ScanOut *__restr
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n && i < s.word_cap; i += (long long)gridDim.x * blockDim.x) words[s.word_base + i] = 0;
 }
 
-__global__ void k_ge_emit(const Scan *__restrict__ scans, const uint32_t *__restrict__ gcount, const Table *__restrict__ tabs,
-                          const uint32_t *__restrict__ bitoff, uint32_t *__restrict__ words)
-{
-    const Scan s = scans[blockIdx.y];
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= s.nblocks) return;
-    auto orw = [&](long long i, uint32_t v) { if (v) atomicOr(&words[i], v); };
-    EmitSink<decltype(orw)> sk(tabs + s.tab_base, orw, s.word_base, (unsigned long long)(bitoff[s.unit_base + u] - bitoff[s.unit_base]));
-    gen_block(s, locate(s, u), gcount[s.unit_base + u], sk);
-    sk.finish();
-}
-
 // ---- block-major passes: one thread per block; the block is read (and its threshold masks built) once per pass and
 // serves every scan that visits it ------------------------------------------------------------------------------------
 __device__ __forceinline__ int unit_of(const Scan &s, const BlockComp &bc, int row, int col)
@@ -181,7 +129,19 @@ __device__ __forceinline__ BlockRef ref_of(const Scan &s, int u, const int16_t *
     BlockRef r; r.blk = blk; r.prev = nullptr; r.slot = 0; return r;
 }
 
-__global__ void k_geb_classify(const BlockComp *__restrict__ comps, const Scan *__restrict__ scans, uint32_t *__restrict__ meta, int *__restrict__ evkey, uint32_t *__restrict__ tail)
+// The classify pass builds each block's threshold masks once and leaves them in `masks` (24 bytes per block, indexed
+// comp.mask_base + block); the histogram, length and emit passes read them back instead of re-deriving them from the 128-byte
+// block (the mask construction was a quarter to a third of those passes' instructions).
+__device__ __forceinline__ Masks3 load_masks(const Masks3 *__restrict__ masks, const BlockComp &bc, int i)
+{
+    const unsigned long long *q = reinterpret_cast<const unsigned long long *>(masks + bc.mask_base + i);   // 24-byte records
+    Masks3 M;
+    M.m[0] = __ldg(q); M.m[1] = __ldg(q + 1); M.m[2] = __ldg(q + 2);
+    return M;
+}
+
+__global__ void k_geb_classify(const BlockComp *__restrict__ comps, const Scan *__restrict__ scans, uint32_t *__restrict__ meta, int *__restrict__ evkey, uint32_t *__restrict__ tail,
+                               Masks3 *__restrict__ masks)
 {
     const BlockComp bc = comps[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -189,6 +149,7 @@ __global__ void k_geb_classify(const BlockComp *__restrict__ comps, const Scan *
     const int row = i / bc.bw, col = i - row * bc.bw;
     const int16_t *blk = bc.coef + bc.comp_off + ((long long)row * bc.bw + col) * 64;
     const Masks3 M = make_masks3(blk);
+    masks[bc.mask_base + i] = M;
     for (int j = 0; j < bc.nscan; j++) {
         const Scan &s = scans[bc.scan_idx[j]];
         const int u = unit_of(s, bc, row, col);
@@ -199,7 +160,9 @@ __global__ void k_geb_classify(const BlockComp *__restrict__ comps, const Scan *
     }
 }
 
-__global__ void k_geb_hist(const BlockComp *__restrict__ comps, const Scan *__restrict__ scans, const uint32_t *__restrict__ gcount, uint32_t *__restrict__ hist)
+// 512 blocks per CTA: the 16 KB shared histogram is zeroed and flushed once per CTA (a fifth of the pass at 128)
+constexpr int HIST_THREADS = 512;
+__global__ void __launch_bounds__(HIST_THREADS) k_geb_hist(const BlockComp *__restrict__ comps, const Scan *__restrict__ scans, const uint32_t *__restrict__ gcount, uint32_t *__restrict__ hist, const Masks3 *__restrict__ masks)
 {
     __shared__ uint32_t h[4][1024];
     for (int i = threadIdx.x; i < 4096; i += blockDim.x) (&h[0][0])[i] = 0;
@@ -209,7 +172,7 @@ __global__ void k_geb_hist(const BlockComp *__restrict__ comps, const Scan *__re
     if (i < bc.bw * bc.bh) {
         const int row = i / bc.bw, col = i - row * bc.bw;
         const int16_t *blk = bc.coef + bc.comp_off + ((long long)row * bc.bw + col) * 64;
-        const Masks3 M = make_masks3(blk);
+        const Masks3 M = load_masks(masks, bc, i);
         for (int j = 0; j < bc.nscan; j++) {
             const Scan &s = scans[bc.scan_idx[j]];
             const int u = unit_of(s, bc, row, col);
@@ -227,14 +190,14 @@ __global__ void k_geb_hist(const BlockComp *__restrict__ comps, const Scan *__re
     }
 }
 
-__global__ void k_geb_len(const BlockComp *__restrict__ comps, const Scan *__restrict__ scans, const uint32_t *__restrict__ gcount, const Table *__restrict__ tabs, uint32_t *__restrict__ bitlen)
+__global__ void k_geb_len(const BlockComp *__restrict__ comps, const Scan *__restrict__ scans, const uint32_t *__restrict__ gcount, const Table *__restrict__ tabs, uint32_t *__restrict__ bitlen, const Masks3 *__restrict__ masks)
 {
     const BlockComp bc = comps[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= bc.bw * bc.bh) return;
     const int row = i / bc.bw, col = i - row * bc.bw;
     const int16_t *blk = bc.coef + bc.comp_off + ((long long)row * bc.bw + col) * 64;
-    const Masks3 M = make_masks3(blk);
+    const Masks3 M = load_masks(masks, bc, i);
     for (int j = 0; j < bc.nscan; j++) {
         const Scan &s = scans[bc.scan_idx[j]];
         const int u = unit_of(s, bc, row, col);
@@ -246,14 +209,14 @@ __global__ void k_geb_len(const BlockComp *__restrict__ comps, const Scan *__res
 }
 
 __global__ void k_geb_emit(const BlockComp *__restrict__ comps, const Scan *__restrict__ scans, const uint32_t *__restrict__ gcount, const Table *__restrict__ tabs,
-                           const uint32_t *__restrict__ bitoff, uint32_t *__restrict__ words)
+                           const uint32_t *__restrict__ bitoff, uint32_t *__restrict__ words, const Masks3 *__restrict__ masks)
 {
     const BlockComp bc = comps[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= bc.bw * bc.bh) return;
     const int row = i / bc.bw, col = i - row * bc.bw;
     const int16_t *blk = bc.coef + bc.comp_off + ((long long)row * bc.bw + col) * 64;
-    const Masks3 M = make_masks3(blk);
+    const Masks3 M = load_masks(masks, bc, i);
     auto orw = [&](long long w, uint32_t v) { if (v) atomicOr(&words[w], v); };
     for (int j = 0; j < bc.nscan; j++) {
         const Scan &s = scans[bc.scan_idx[j]];
@@ -354,7 +317,7 @@ GpuEncoder::~GpuEncoder()
 {
     cudaFree(d_scans); cudaFree(d_comps); cudaFree(d_meta); cudaFree(d_evkey); cudaFree(d_prev); cudaFree(d_tail); cudaFree(d_tsum); cudaFree(d_gcount);
     cudaFree(d_bitlen); cudaFree(d_bitoff); cudaFree(d_hist); cudaFree(d_tabs); cudaFree(d_dht); cudaFree(d_total); cudaFree(d_so);
-    cudaFree(d_words); cudaFree(d_ffcount); cudaFree(d_ffoff); cudaFree(d_outoff); cudaFree(d_outlen); cudaFree(d_out); cudaFree(d_temp);
+    cudaFree(d_words); cudaFree(d_masks); cudaFree(d_ffcount); cudaFree(d_ffoff); cudaFree(d_outoff); cudaFree(d_outlen); cudaFree(d_out); cudaFree(d_temp);
     cudaFreeHost(h_small); cudaFreeHost(h_out);
 }
 
@@ -390,6 +353,7 @@ bool GpuEncoder::encode(const JpegGeom &g, bool progressive, int16_t *const *d_c
     c = cap_oo; if (!grow(d_outoff, c, (size_t)NS * 4, false, err)) return false; cap_oo = c;
     c = cap_ol; if (!grow(d_outlen, c, (size_t)NS * 4, false, err)) return false; cap_ol = c;
     c = cap_words; if (!grow(d_words, c, (size_t)plan.total_words * 4, false, err)) return false; cap_words = c;
+    c = cap_masks; if (!grow(d_masks, c, (size_t)plan.total_comp_blocks * sizeof(Masks3), false, err)) return false; cap_masks = c;
     const size_t small_bytes = align_up((size_t)NS * sizeof(Scan), 256) + align_up((size_t)NS * sizeof(ScanOut), 256) + align_up((size_t)NS * 4, 256) * 2 + align_up((size_t)NS * 4 * sizeof(DhtOut), 256) +
                                align_up((size_t)NC * sizeof(BlockComp), 256);
     c = cap_small; if (!grow(h_small, c, small_bytes, true, err)) return false; cap_small = c;
@@ -416,7 +380,7 @@ bool GpuEncoder::encode(const JpegGeom &g, bool progressive, int16_t *const *d_c
         }
     }
     const dim3 gu(cdiv(max_units, 128), NS), gu1(cdiv(max_units + 1, 128), NS);
-    k_geb_classify<<<gb, 128, 0, st>>>(d_comps, d_scans, d_meta, d_evkey, d_tail);
+    k_geb_classify<<<gb, 128, 0, st>>>(d_comps, d_scans, d_meta, d_evkey, d_tail, d_masks);
     size_t tb = cap_temp;
     cub::DeviceScan::ExclusiveScan(d_temp, tb, d_evkey, d_prev, cub::Max(), -1, (int)U, st);
     tb = cap_temp;
@@ -424,9 +388,9 @@ bool GpuEncoder::encode(const JpegGeom &g, bool progressive, int16_t *const *d_c
     CU(cudaMemsetAsync(d_gcount, 0, U * 4, st));
     k_ge_groups<<<gu1, 128, 0, st>>>(d_scans, d_meta, d_evkey, d_prev, d_tsum, d_gcount);
     CU(cudaMemsetAsync(d_hist, 0, (size_t)NS * 4 * 256 * 4, st));
-    k_geb_hist<<<gb, 128, 0, st>>>(d_comps, d_scans, d_gcount, d_hist);
+    k_geb_hist<<<dim3(cdiv(plan.max_comp_blocks, HIST_THREADS), NC), HIST_THREADS, 0, st>>>(d_comps, d_scans, d_gcount, d_hist, d_masks);
     k_ge_tables<<<NS * 4, 32, 0, st>>>(d_hist, d_tabs, d_dht);
-    k_geb_len<<<gb, 128, 0, st>>>(d_comps, d_scans, d_gcount, d_tabs, d_bitlen);
+    k_geb_len<<<gb, 128, 0, st>>>(d_comps, d_scans, d_gcount, d_tabs, d_bitlen, d_masks);
     tb = cap_temp;
     cub::DeviceScan::ExclusiveSum(d_temp, tb, d_bitlen, d_bitoff, (int)U, st);
     k_ge_totals<<<cdiv(NS, 128), 128, 0, st>>>(d_scans, NS, d_bitlen, d_bitoff, d_total);
@@ -454,7 +418,7 @@ bool GpuEncoder::encode(const JpegGeom &g, bool progressive, int16_t *const *d_c
     c = cap_temp; if (!grow(d_temp, c, tb3 + 256, false, err)) return false; cap_temp = c;
     CU(cudaMemcpyAsync(d_so, h_so, (size_t)NS * sizeof(ScanOut), cudaMemcpyHostToDevice, st));
     k_ge_zero<<<dim3(std::max(1, std::min(cdiv(max_words, 256), 256)), NS), 256, 0, st>>>(d_scans, d_so, d_words);
-    k_geb_emit<<<gb, 128, 0, st>>>(d_comps, d_scans, d_gcount, d_tabs, d_bitoff, d_words);
+    k_geb_emit<<<gb, 128, 0, st>>>(d_comps, d_scans, d_gcount, d_tabs, d_bitoff, d_words, d_masks);
     if (groups) {
         const dim3 gg(cdiv(max_groups, 128), NS);
         k_ge_ffcount<<<gg, 128, 0, st>>>(d_scans, d_so, d_words, d_ffcount);

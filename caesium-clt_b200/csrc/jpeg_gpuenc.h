@@ -39,6 +39,7 @@ private:
     uint32_t *d_total = nullptr; size_t cap_total = 0;
     ScanOut *d_so = nullptr; size_t cap_so = 0;
     uint32_t *d_words = nullptr; size_t cap_words = 0;
+    ge::Masks3 *d_masks = nullptr; size_t cap_masks = 0;       // threshold masks per block, written by the classify pass
     uint32_t *d_ffcount = nullptr, *d_ffoff = nullptr; size_t cap_ff[2] = {0, 0};
     uint32_t *d_outoff = nullptr, *d_outlen = nullptr; size_t cap_oo = 0, cap_ol = 0;
     uint8_t *d_out = nullptr; size_t cap_out = 0;

@@ -136,34 +136,54 @@ GE_HD unsigned long long band_mask(int Ss, int Se) { return (Se >= 63 ? ~0ull : 
 struct Masks3 { unsigned long long m[3]; };
 GE_HD bool masks_cover(int mode, int Al) { return mode == MODE_AC_REFINE ? Al <= 1 : Al <= 2; }
 
+// SWAR over the 32 coefficient pairs of a block (two int16 per 32-bit word, little endian): per word |c| of both halves,
+// then for each threshold one add turns "half >= T" into bit 15 / bit 31, which is shifted onto the word's position in a
+// 32-bit accumulator (even coefficients in the low half, odd ones in the high half); the two halves are interleaved once at
+// the end.  ~600 integer operations per block instead of a compare-and-insert per coefficient and threshold.  The same code
+// runs in the CPU emulation (tests/emul), so the bit tricks are covered without a GPU.
+GE_HD uint32_t interleave16(uint32_t acc)       // bits 0..15 -> even positions, bits 16..31 -> odd positions
+{
+    uint32_t x = acc & 0xFFFFu, y = acc >> 16;
+    x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu; x = (x | (x << 2)) & 0x33333333u; x = (x | (x << 1)) & 0x55555555u;
+    y = (y | (y << 8)) & 0x00FF00FFu; y = (y | (y << 4)) & 0x0F0F0F0Fu; y = (y | (y << 2)) & 0x33333333u; y = (y | (y << 1)) & 0x55555555u;
+    return x | (y << 1);
+}
+GE_HD void masks_word(uint32_t w, int jj /*0..15: word inside its half*/, uint32_t (&acc)[3])
+{
+    const uint32_t sb = (w >> 15) & 0x00010001u;
+    const uint32_t a = (w ^ (sb * 0xFFFFu)) + sb;                   // |lo| , |hi| (32768 for -32768): no carry between the halves
+    const uint32_t pos = 0x00010001u << jj;
+    acc[0] |= ((a + 0x7FFF7FFFu) >> (15 - jj)) & pos;              // half >= 1
+    acc[1] |= (((a & 0xFFFEFFFEu) + 0x7FFF7FFFu) >> (15 - jj)) & pos;   // half >= 2
+    acc[2] |= (((a & 0xFFFCFFFCu) + 0x7FFF7FFFu) >> (15 - jj)) & pos;   // half >= 4
+}
 GE_HD Masks3 make_masks3(const int16_t *__restrict__ blk)
 {
     Masks3 M;
+    uint32_t lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
 #if defined(__CUDA_ARCH__)
-    const uint4 *v = reinterpret_cast<const uint4 *>(blk);          // 8 x 128-bit loads, two coefficients per 32-bit word
-    unsigned lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    const uint4 *v = reinterpret_cast<const uint4 *>(blk);          // 8 x 128-bit loads
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         const uint4 q = v[j];
-        const unsigned w[4] = {q.x, q.y, q.z, q.w};
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const unsigned a = __vabsss2(w[i]);
-            const int sh = 2 * ((4 * j + i) & 15);
-#pragma unroll
-            for (int t = 0; t < 3; t++) {
-                const unsigned c = __vcmpgeu2(a, 0x00010001u << t);
-                const unsigned b = (c & 1u) | ((c >> 15) & 2u);
-                if (j < 4) lo[t] |= b << sh; else hi[t] |= b << sh;
-            }
-        }
+        for (int i = 0; i < 4; i++) { if (j < 4) masks_word(w[i], (4 * j + i) & 15, lo); else masks_word(w[i], (4 * j + i) & 15, hi); }
     }
-#pragma unroll
-    for (int t = 0; t < 3; t++) M.m[t] = ((unsigned long long)hi[t] << 32) | lo[t];
 #else
-    M.m[0] = M.m[1] = M.m[2] = 0;
-    for (int k = 0; k < 64; k++) { int a = blk[k]; if (a < 0) a = -a; for (int t = 0; t < 3; t++) if (a >= (1 << t)) M.m[t] |= 1ull << k; }
+    for (int j = 0; j < 32; j++) {
+        const uint32_t w = (uint32_t)(uint16_t)blk[2 * j] | ((uint32_t)(uint16_t)blk[2 * j + 1] << 16);
+        if (j < 16) masks_word(w, j, lo); else masks_word(w, j - 16, hi);
+    }
 #endif
+    for (int t = 0; t < 3; t++) M.m[t] = ((unsigned long long)interleave16(hi[t]) << 32) | interleave16(lo[t]);
+    return M;
+}
+// the definition the SWAR form is checked against in tests/emul: bit k of m[t] <=> |blk[k]| >= 2^t
+inline Masks3 make_masks3_reference(const int16_t *blk)
+{
+    Masks3 M; M.m[0] = M.m[1] = M.m[2] = 0;
+    for (int k = 0; k < 64; k++) { int a = blk[k]; if (a < 0) a = -a; for (int t = 0; t < 3; t++) if (a >= (1 << t)) M.m[t] |= 1ull << k; }
     return M;
 }
 
@@ -312,9 +332,9 @@ struct EmitSink {
     }
     GE_HD void sym(int kind, int tbl, int symbol, int nb, unsigned extra)
     {
+        // code and value bits leave as one piece: at most 16 + 16 bits
         const Table &t = tabs[kind * 2 + tbl];
-        put(t.code[symbol], t.size[symbol]);
-        put(extra, nb);
+        put((t.code[symbol] << nb) | (extra & ((1u << nb) - 1u)), t.size[symbol] + nb);
     }
     GE_HD void raw64(int nb, unsigned long long v)
     {

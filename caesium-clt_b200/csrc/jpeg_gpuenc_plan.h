@@ -16,6 +16,7 @@ struct BlockComp {
     int bw, bh, rbw, rbh, hs, vs;
     int q_base, blocks_per_mcu, mcux;   // position of the component's first block inside an MCU (interleaved scans)
     int nscan, scan_idx[6];             // indices into GpuEncPlan::scans
+    long long mask_base;                // first block of this component in the batch-wide per-block mask array
 };
 
 struct GpuEncPlan {
@@ -25,7 +26,7 @@ struct GpuEncPlan {
     std::vector<ScanDef> defs;          // one script (shared by all images of the batch)
     int scans_per_image = 0;
     long long units_per_image = 0, words_per_image = 0;
-    long long total_units = 0, total_words = 0;
+    long long total_units = 0, total_words = 0, total_comp_blocks = 0;
 };
 
 // coef_base[i] = device (or host) pointer to image i's coefficient buffer (geometry g, zigzag)
@@ -63,7 +64,7 @@ inline void gpuenc_plan(const JpegGeom &g, bool progressive, const int16_t *cons
         if (im == 0) { p.units_per_image = unit; p.words_per_image = word; }
     }
     p.total_units = unit; p.total_words = word;
-    p.comps.clear(); p.max_comp_blocks = 0;
+    p.comps.clear(); p.max_comp_blocks = 0; p.total_comp_blocks = 0;
     for (int im = 0; im < nimages; im++) {
         int qb = 0;
         for (int c = 0; c < g.ncomp; c++) {
@@ -75,6 +76,7 @@ inline void gpuenc_plan(const JpegGeom &g, bool progressive, const int16_t *cons
             qb += g.hs[c] * g.vs[c];
             bc.nscan = 0;
             for (int si = 0; si < ns; si++) for (int i = 0; i < sc[si].ns; i++) if (sc[si].ci[i] == c && bc.nscan < 6) bc.scan_idx[bc.nscan++] = im * ns + si;
+            bc.mask_base = p.total_comp_blocks; p.total_comp_blocks += (long long)bc.bw * bc.bh;
             p.comps.push_back(bc);
             p.max_comp_blocks = std::max(p.max_comp_blocks, bc.bw * bc.bh);
         }

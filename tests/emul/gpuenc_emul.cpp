@@ -117,3 +117,26 @@ extern "C" int emul_gpu_transcode(const uint8_t *jpeg, size_t len, int progressi
     *out = (uint8_t *)malloc(file.size()); memcpy(*out, file.data(), file.size()); *out_len = file.size();
     return 0;
 }
+
+// SWAR threshold masks (what the kernels compute) against the per-coefficient definition, on random blocks that mix small values,
+// zeros and the extremes; returns the number of blocks that differ.
+extern "C" int emul_masks_check(int nblocks, unsigned seed)
+{
+    int bad = 0;
+    unsigned x = seed * 2654435761u + 1u;
+    auto rnd = [&x]() { x ^= x << 13; x ^= x >> 17; x ^= x << 5; return x; };
+    static const int16_t special[] = {0, 1, -1, 2, -2, 3, -3, 4, -4, 5, -5, 7, -8, 255, -256, 32767, -32767, -32768, 16384, -16384};
+    for (int n = 0; n < nblocks; n++) {
+        alignas(16) int16_t blk[64];
+        const unsigned density = rnd() % 5;
+        for (int k = 0; k < 64; k++) {
+            const unsigned r = rnd();
+            if (density < 4 && (r & 7u) > density * 2u) blk[k] = 0;
+            else if (r & 0x100u) blk[k] = special[(r >> 9) % (sizeof(special) / sizeof(special[0]))];
+            else blk[k] = (int16_t)(r >> 16);
+        }
+        const ge::Masks3 a = ge::make_masks3(blk), b = ge::make_masks3_reference(blk);
+        if (a.m[0] != b.m[0] || a.m[1] != b.m[1] || a.m[2] != b.m[2]) bad++;
+    }
+    return bad;
+}

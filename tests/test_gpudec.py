@@ -70,6 +70,23 @@ def test_optimised_tables_and_high_quality(L, emul):
         assert rc == 0 and np.array_equal(out, ref)
 
 
+def test_kernel_form_tables_equal_the_jdhuff_search(emul, golden):
+    """Two-level lookup tables (what the kernels read) against the canonical maxcode search, for every 16-bit pattern and
+    every table of the scan -- Annex K tables, per-image optimised tables, q=100 tables with 16-bit codes in use."""
+    from tools.synth import synth_rgb
+    files = [golden(n) for n in BASELINE_INPUTS[:5]]
+    for q, kw in [(100, {}), (30, {"optimize": True}), (95, {"optimize": True, "subsampling": "4:4:4"}), (5, {"optimize": True})]:
+        b = io.BytesIO()
+        Image.fromarray(synth_rgb(333, 211, 40 + q), "RGB").save(b, "JPEG", quality=q, **kw)
+        files.append(b.getvalue())
+    emul.emul_gpu_dec_table_check.restype = C.c_longlong
+    for data in files:
+        used = C.c_int(-1)
+        bad = emul.emul_gpu_dec_table_check(data, C.c_size_t(len(data)), C.byref(used))
+        assert bad == 0, bad
+        assert 0 <= used.value <= 1536
+
+
 def test_flat_image_reports_non_convergence_or_matches(L, emul):
     """A constant image is a periodic bit stream: a wrong phase can persist, so the round budget may run out.  Whatever
     the outcome, a 0 return code must mean identical coefficients."""

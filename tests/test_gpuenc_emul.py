@@ -47,6 +47,12 @@ def test_block_parallel_encoder_matches_sequential_writer(L, O, emul, golden, na
     assert got == O.jpeg_lossless(data, O.params(80, 0, bool(prog)))
 
 
+def test_swar_threshold_masks_equal_the_definition(emul):
+    """make_masks3 (the word-parallel form the kernels run) against |c| >= 1 / 2 / 4 per coefficient: 200k random blocks with
+    zeros, small values and the int16 extremes."""
+    assert emul.emul_masks_check(200000, 12345) == 0
+
+
 def _layout(L, w, h, ncomp=1):
     lay = L.JpegLayout()
     lay.width, lay.height, lay.ncomp = w, h, ncomp
