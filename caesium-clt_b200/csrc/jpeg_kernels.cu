@@ -47,13 +47,21 @@ constexpr int STAGE_INT4_PER_WARP = 32 * 9;   // 32 blocks x (8 + 1 pad) int4 ->
 template <int N> __device__ __forceinline__ int descale(int x) { return (x + (1 << (N - 1))) >> N; }
 
 // 1-D inverse butterfly of jidctint.c; SHIFT = CONST_BITS - PASS1_BITS (11) in pass 1, CONST_BITS + PASS1_BITS + 3 (18) in pass 2
-template <int SHIFT>
+// IDCT_range_limit[(x >> SHIFT) & 1023] as an UNCENTRED sample 0..255; x already carries the rounding constant
+template <int SHIFT> __device__ __forceinline__ int sample_of(int x)
+{
+    const int w = (int)((unsigned)x << (22 - SHIFT)) >> 22;          // the descaled value, wrapped to 10 signed bits
+    return __viaddmin_s32_relu(w, 128, 255);                         // max(min(w + 128, 255), 0)
+}
+
+template <int SHIFT, bool SAMPLES = false>
 __device__ __forceinline__ void idct8(int &d0, int &d1, int &d2, int &d3, int &d4, int &d5, int &d6, int &d7)
 {
+    constexpr int R = 1 << (SHIFT - 1);         // the descale's rounding constant rides in on the even part (one multiply-add)
     int z1 = (d2 + d6) * FIX_0_541196100;
     int t2 = z1 + d6 * (-FIX_1_847759065);
     int t3 = z1 + d2 * FIX_0_765366865;
-    int t0 = (d0 + d4) * 8192, t1 = (d0 - d4) * 8192;
+    int t0 = (d0 + d4) * 8192 + R, t1 = (d0 - d4) * 8192 + R;
     int t10 = t0 + t3, t13 = t0 - t3, t11 = t1 + t2, t12 = t1 - t2;
     int o0 = d7, o1 = d5, o2 = d3, o3 = d1;
     z1 = o0 + o3; int z2 = o1 + o2, z3 = o0 + o2, z4 = o1 + o3;
@@ -62,45 +70,49 @@ __device__ __forceinline__ void idct8(int &d0, int &d1, int &d2, int &d3, int &d
     z1 *= -FIX_0_899976223; z2 *= -FIX_2_562915447; z3 *= -FIX_1_961570560; z4 *= -FIX_0_390180644;
     z3 += z5; z4 += z5;
     o0 += z1 + z3; o1 += z2 + z4; o2 += z2 + z3; o3 += z1 + z4;
-    d0 = descale<SHIFT>(t10 + o3); d7 = descale<SHIFT>(t10 - o3);
-    d1 = descale<SHIFT>(t11 + o2); d6 = descale<SHIFT>(t11 - o2);
-    d2 = descale<SHIFT>(t12 + o1); d5 = descale<SHIFT>(t12 - o1);
-    d3 = descale<SHIFT>(t13 + o0); d4 = descale<SHIFT>(t13 - o0);
+    if (!SAMPLES) {
+        d0 = (t10 + o3) >> SHIFT; d7 = (t10 - o3) >> SHIFT;
+        d1 = (t11 + o2) >> SHIFT; d6 = (t11 - o2) >> SHIFT;
+        d2 = (t12 + o1) >> SHIFT; d5 = (t12 - o1) >> SHIFT;
+        d3 = (t13 + o0) >> SHIFT; d4 = (t13 - o0) >> SHIFT;
+    } else {
+        // pass 2 ends in IDCT_range_limit[(x >> SHIFT) & RANGE_MASK]: the descale, the 10-bit wrap and the clamp as
+        // (x + round) << (22 - SHIFT) >> 22 (sign-extends bit 9 of the descaled value) and one add-min-relu to [0, 255]
+        d0 = sample_of<SHIFT>(t10 + o3); d7 = sample_of<SHIFT>(t10 - o3);
+        d1 = sample_of<SHIFT>(t11 + o2); d6 = sample_of<SHIFT>(t11 - o2);
+        d2 = sample_of<SHIFT>(t12 + o1); d5 = sample_of<SHIFT>(t12 - o1);
+        d3 = sample_of<SHIFT>(t13 + o0); d4 = sample_of<SHIFT>(t13 - o0);
+    }
 }
 
 // 1-D forward butterfly of jfdctint.c.  PASS 1: outputs scaled up by PASS1_BITS; PASS 2: scaled back down.
 template <int PASS>
 __device__ __forceinline__ void fdct8(int &d0, int &d1, int &d2, int &d3, int &d4, int &d5, int &d6, int &d7)
 {
-    constexpr int SH = PASS == 1 ? 11 : 15;
+    constexpr int SH = PASS == 1 ? 11 : 15, R = 1 << (SH - 1);       // rounding constants folded into the multiply-adds
     int t0 = d0 + d7, t7 = d0 - d7, t1 = d1 + d6, t6 = d1 - d6;
     int t2 = d2 + d5, t5 = d2 - d5, t3 = d3 + d4, t4 = d3 - d4;
     int t10 = t0 + t3, t13 = t0 - t3, t11 = t1 + t2, t12 = t1 - t2;
     if (PASS == 1) { d0 = (t10 + t11) * 4; d4 = (t10 - t11) * 4; }
-    else           { d0 = descale<2>(t10 + t11); d4 = descale<2>(t10 - t11); }
-    int z1 = (t12 + t13) * FIX_0_541196100;
-    d2 = descale<SH>(z1 + t13 * FIX_0_765366865);
-    d6 = descale<SH>(z1 + t12 * (-FIX_1_847759065));
+    else           { d0 = (t10 + t11 + 2) >> 2; d4 = (t10 - t11 + 2) >> 2; }
+    int z1 = (t12 + t13) * FIX_0_541196100 + R;
+    d2 = (z1 + t13 * FIX_0_765366865) >> SH;
+    d6 = (z1 + t12 * (-FIX_1_847759065)) >> SH;
     z1 = t4 + t7; int z2 = t5 + t6, z3 = t4 + t6, z4 = t5 + t7;
-    int z5 = (z3 + z4) * FIX_1_175875602;
+    int z5 = (z3 + z4) * FIX_1_175875602 + R;
     t4 *= FIX_0_298631336; t5 *= FIX_2_053119869; t6 *= FIX_3_072711026; t7 *= FIX_1_501321110;
     z1 *= -FIX_0_899976223; z2 *= -FIX_2_562915447; z3 *= -FIX_1_961570560; z4 *= -FIX_0_390180644;
     z3 += z5; z4 += z5;
-    d7 = descale<SH>(t4 + z1 + z3); d5 = descale<SH>(t5 + z2 + z4);
-    d3 = descale<SH>(t6 + z2 + z3); d1 = descale<SH>(t7 + z1 + z4);
-}
-
-// IDCT_range_limit[x & RANGE_MASK] - CENTERJSAMPLE: the centred sample in [-128, 127] with the IJG 10-bit wrap
-__device__ __forceinline__ int range_limit_centered(int x)
-{
-    x = (x << 22) >> 22;
-    return max(-128, min(127, x));
+    d7 = (t4 + z1 + z3) >> SH; d5 = (t5 + z2 + z4) >> SH;
+    d3 = (t6 + z2 + z3) >> SH; d1 = (t7 + z1 + z4) >> SH;
 }
 
 struct Tables {
     uint16_t dq[64];
-    uint32_t m[64];
-    uint32_t half_sh[64];
+    uint2 mc[64];           // (m, c) of QuantDev, one 8-byte shared-memory read per coefficient
+    uint32_t kpair[32];
+    uint8_t sh[64];
+    uint32_t any_shift;
 };
 
 __device__ __forceinline__ void load_tables(Tables &t, const CompWork &w, bool need_dq, bool need_q)
@@ -108,7 +120,7 @@ __device__ __forceinline__ void load_tables(Tables &t, const CompWork &w, bool n
     int i = threadIdx.x;
     if (i < 64) {
         if (need_dq) t.dq[i] = w.dq[i];
-        if (need_q) { t.m[i] = w.q->m[i]; t.half_sh[i] = w.q->half_sh[i]; }
+        if (need_q) { t.mc[i] = make_uint2(w.q->m[i], w.q->c[i]); t.sh[i] = w.q->sh[i]; if (i < 32) t.kpair[i] = w.q->kpair[i]; if (i == 0) t.any_shift = w.q->any_shift; }
     }
     __syncthreads();
 }
@@ -173,44 +185,42 @@ __device__ __forceinline__ void dequant_dezigzag(const int4 (&r)[8], const Table
 #undef X
 }
 
-// v: dequantised coefficients (natural order) -> centred samples (sample - 128) in place
+// v: dequantised coefficients (natural order) -> samples 0..255 in place
 __device__ __forceinline__ void idct_block(int (&v)[64])
 {
 #pragma unroll
     for (int c = 0; c < 8; c++) idct8<11>(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-        idct8<18>(v[8 * r], v[8 * r + 1], v[8 * r + 2], v[8 * r + 3], v[8 * r + 4], v[8 * r + 5], v[8 * r + 6], v[8 * r + 7]);
-#pragma unroll
-        for (int c = 0; c < 8; c++) v[8 * r + c] = range_limit_centered(v[8 * r + c]);
-    }
+    for (int r = 0; r < 8; r++) idct8<18, true>(v[8 * r], v[8 * r + 1], v[8 * r + 2], v[8 * r + 3], v[8 * r + 4], v[8 * r + 5], v[8 * r + 6], v[8 * r + 7]);
 }
 
-// v: centred samples -> forward DCT (scaled by 8) in place
+// v: samples 0..255 -> forward DCT (scaled by 8) of the CENTRED samples, in place.  jcdctmgr.c subtracts CENTERJSAMPLE first;
+// the butterflies are linear and every output but DC is built from differences, so running them on the uncentred samples adds
+// exactly 8 * 128 * 8 = 8192 to v[0] (row pass: +4096 in column 0 only; column pass: (x + 32768 + 2) >> 2) and nothing else.
 __device__ __forceinline__ void fdct_block(int (&v)[64])
 {
 #pragma unroll
     for (int r = 0; r < 8; r++) fdct8<1>(v[8 * r], v[8 * r + 1], v[8 * r + 2], v[8 * r + 3], v[8 * r + 4], v[8 * r + 5], v[8 * r + 6], v[8 * r + 7]);
 #pragma unroll
     for (int c = 0; c < 8; c++) fdct8<2>(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
+    v[0] -= 8192;
 }
 
-__device__ __forceinline__ int quant1(int x, uint32_t m, uint32_t half_sh)
+// DCT output (natural order) -> quantised zigzag int16 block packed into 8 x int4 (QuantDev: biased sign-free division)
+template <bool SHIFT>
+__device__ __forceinline__ void quant_zigzag_t(const int (&v)[64], const Tables &t, int4 (&r)[8])
 {
-    uint32_t a = (uint32_t)abs(x) + (half_sh & 0xFFFFFFu);
-    int q = (int)(__umulhi(a, m) >> (half_sh >> 24));
-    return x < 0 ? -q : q;
-}
-
-// DCT output (natural order) -> quantised zigzag int16 block packed into 8 x int4
-__device__ __forceinline__ void quant_zigzag(const int (&v)[64], const Tables &t, int4 (&r)[8])
-{
-    int ow[32];
-#define X(k, n) { int qv = quant1(v[n], t.m[k], t.half_sh[k]); if ((k) & 1) ow[(k) >> 1] |= (qv << 16); else ow[(k) >> 1] = qv & 0xFFFF; }
+    uint32_t ow[32];
+#define X(k, n) { const uint2 mc = t.mc[k]; const uint32_t qb = quant_biased(v[n], mc.x, mc.y, SHIFT ? (uint32_t)t.sh[k] : 0u); \
+                  if ((k) & 1) ow[(k) >> 1] = quant_pack(ow[(k) >> 1], qb, t.kpair[(k) >> 1]); else ow[(k) >> 1] = qb; }
     ZZ_LIST(X)
 #undef X
 #pragma unroll
-    for (int j = 0; j < 8; j++) r[j] = make_int4(ow[4 * j], ow[4 * j + 1], ow[4 * j + 2], ow[4 * j + 3]);
+    for (int j = 0; j < 8; j++) r[j] = make_int4((int)ow[4 * j], (int)ow[4 * j + 1], (int)ow[4 * j + 2], (int)ow[4 * j + 3]);
+}
+__device__ __forceinline__ void quant_zigzag(const int (&v)[64], const Tables &t, int4 (&r)[8])
+{
+    if (t.any_shift) quant_zigzag_t<true>(v, t, r); else quant_zigzag_t<false>(v, t, r);     // block-uniform branch
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -273,8 +283,8 @@ __global__ void __launch_bounds__(THREADS) k_idct_plane(const CompWork *__restri
     uint8_t *p = w.plane + (size_t)(t.by * 8) * w.pstride + (t.bx0 + lane) * 8;
 #pragma unroll
     for (int y = 0; y < 8; y++) {
-        uint32_t lo = (uint32_t)(v[8 * y] + 128) | ((uint32_t)(v[8 * y + 1] + 128) << 8) | ((uint32_t)(v[8 * y + 2] + 128) << 16) | ((uint32_t)(v[8 * y + 3] + 128) << 24);
-        uint32_t hi = (uint32_t)(v[8 * y + 4] + 128) | ((uint32_t)(v[8 * y + 5] + 128) << 8) | ((uint32_t)(v[8 * y + 6] + 128) << 16) | ((uint32_t)(v[8 * y + 7] + 128) << 24);
+        uint32_t lo = (uint32_t)v[8 * y] | ((uint32_t)v[8 * y + 1] << 8) | ((uint32_t)v[8 * y + 2] << 16) | ((uint32_t)v[8 * y + 3] << 24);
+        uint32_t hi = (uint32_t)v[8 * y + 4] | ((uint32_t)v[8 * y + 5] << 8) | ((uint32_t)v[8 * y + 6] << 16) | ((uint32_t)v[8 * y + 7] << 24);
         *reinterpret_cast<uint2 *>(p + (size_t)y * w.pstride) = make_uint2(lo, hi);   // lanes -> consecutive 8 B: coalesced
     }
 }
@@ -366,7 +376,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_chroma420_refdct(const CompWork 
                 const int tu = 3 * su[X + 1], tl = 3 * sl[X + 1];
                 const int u00 = (tu + su[X] + 8) >> 4, u01 = (tu + su[X + 2] + 7) >> 4;
                 const int u10 = (tl + sl[X] + 8) >> 4, u11 = (tl + sl[X + 2] + 7) >> 4;
-                v[8 * Y + X] = ((u00 + u01 + u10 + u11 + 1 + (X & 1)) >> 2) - 128;   // bias 1,2,1,2 across output columns
+                v[8 * Y + X] = (u00 + u01 + u10 + u11 + 1 + (X & 1)) >> 2;   // bias 1,2,1,2 across output columns
             }
         }
         pL = cL; pM0 = cM0; pM1 = cM1; pR = cR;
@@ -379,7 +389,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_chroma420_refdct(const CompWork 
         for (int j = 0; j < 16; j++) {
             uint32_t m4 = *reinterpret_cast<const uint32_t *>(mine + 4 * j);
 #pragma unroll
-            for (int k = 0; k < 4; k++) v[4 * j + k] = (int)((m4 >> (8 * k)) & 0xFF) - 128;
+            for (int k = 0; k < 4; k++) v[4 * j + k] = (int)((m4 >> (8 * k)) & 0xFF);
         }
     }
     __syncwarp();
@@ -450,7 +460,7 @@ __global__ void __launch_bounds__(THREADS) k_fdct_plane(const CompWork *__restri
     for (int y = 0; y < 8; y++) {
         uint2 m = __ldg(reinterpret_cast<const uint2 *>(w.dplane + (size_t)(by * 8 + y) * pw + bx * 8));
 #pragma unroll
-        for (int k = 0; k < 4; k++) { v[8 * y + k] = (int)((m.x >> (8 * k)) & 0xFF) - 128; v[8 * y + 4 + k] = (int)((m.y >> (8 * k)) & 0xFF) - 128; }
+        for (int k = 0; k < 4; k++) { v[8 * y + k] = (int)((m.x >> (8 * k)) & 0xFF); v[8 * y + 4 + k] = (int)((m.y >> (8 * k)) & 0xFF); }
     }
     fdct_block(v);
     int4 r[8];
@@ -461,22 +471,6 @@ __global__ void __launch_bounds__(THREADS) k_fdct_plane(const CompWork *__restri
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
-void make_quant_dev(const uint16_t qt_zigzag[64], QuantDev *out)
-{
-    for (int k = 0; k < 64; k++) {
-        uint32_t d = (uint32_t)qt_zigzag[k] << 3;       // jcdctmgr.c: ISLOW divisor = quantval << 3
-        if (d == 0) d = 8;
-        int l = 0; while ((1u << l) < d) l++;            // ceil(log2 d)
-        int s = 19 + l;
-        uint64_t mfull = ((1ull << s) + d - 1) / d;      // ceil(2^s / d) <= 2^20
-        uint32_t m, sh;
-        if (s <= 32) { m = (uint32_t)(mfull << (32 - s)); sh = 0; }
-        else         { m = (uint32_t)mfull; sh = (uint32_t)(s - 32); }
-        out->m[k] = m;
-        out->half_sh[k] = (d >> 1) | (sh << 24);
-    }
-}
-
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 int launch_fused_same(const CompWork *work, int n, int max_tiles, void *stream)
