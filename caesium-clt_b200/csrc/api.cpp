@@ -685,7 +685,7 @@ int b200_compress_batch(const uint8_t *const *in, const size_t *in_len, int n, c
         const int nj = (int)jpegs.size();
         if (nj) {
             std::mutex rest_mu;
-            int max_workers = 8; { const char *e = getenv("B200_GROUP_WORKERS"); if (e) max_workers = std::max(1, std::min(32, atoi(e))); }
+            int max_workers = 16; { const char *e = getenv("B200_GROUP_WORKERS"); if (e) max_workers = std::max(1, std::min(32, atoi(e))); }
             auto group_worker = [&]() {
                 for (;;) {
                     const int j0 = next.fetch_add(K);

@@ -44,8 +44,6 @@ int launch_work(const WorkLists &wl, const CompWork *d_work, void *stream, int w
 struct Slot {
     int dev = 0;
     void *stream = nullptr;
-    void *stream_hi = nullptr;  // highest-priority stream for the entropy DECODE passes (small, latency-bound grids), see slot_decode_group
-    void *ev_order = nullptr;   // orders work between the two streams
     int16_t *h_in = nullptr, *h_out = nullptr; size_t h_in_cap = 0, h_out_cap = 0;       // pinned
     int16_t *d_in = nullptr, *d_out = nullptr; size_t d_in_cap = 0, d_out_cap = 0;
     uint8_t *d_scratch = nullptr; size_t d_scratch_cap = 0;

@@ -47,20 +47,20 @@ __global__ void k_ge_tables(const uint32_t *__restrict__ hist, Table *__restrict
     for (int i = lane; i < 257; i += 32) { freq[i] = i < 256 ? (long long)f[i] : 1; codesize[i] = 0; others[i] = -1; }
     if (lane == 0) for (int i = 0; i < 33; i++) bits[i] = 0;
     __syncwarp();
+    // argmin over the live entries (freq > 0), ties to the LARGEST index, entries above 10^9 never chosen (jchuff.c's `v = 1000000000L`
+    // start value): each lane scans its 9 entries in ascending order, then three warp reductions (REDUX) pick the winner --
+    // high word, low word, index -- instead of a five-step shuffle butterfly on (value, index) pairs.
+    auto warp_argmin = [&](int exclude) {
+        unsigned long long v = 1000000000ULL; int c = -1;
+        for (int i = lane; i < 257; i += 32) { const unsigned long long fi = (unsigned long long)freq[i]; if (fi && fi <= v && i != exclude) { v = fi; c = i; } }
+        const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+        const unsigned mhi = __reduce_min_sync(0xFFFFFFFFu, hi);
+        const unsigned mlo = __reduce_min_sync(0xFFFFFFFFu, hi == mhi ? lo : 0xFFFFFFFFu);
+        return __reduce_max_sync(0xFFFFFFFFu, (hi == mhi && lo == mlo) ? c : -1);
+    };
     for (;;) {
-        // c1 = argmin over freq > 0, largest index among ties
-        long long v1 = 1000000000LL; int c1 = -1;
-        for (int i = lane; i < 257; i += 32) { const long long fi = freq[i]; if (fi && fi <= v1) { v1 = fi; c1 = i; } }
-        for (int o = 16; o; o >>= 1) {
-            const long long ov = __shfl_xor_sync(0xFFFFFFFFu, v1, o); const int oc = __shfl_xor_sync(0xFFFFFFFFu, c1, o);
-            if (oc >= 0 && (c1 < 0 || ov < v1 || (ov == v1 && oc > c1))) { v1 = ov; c1 = oc; }
-        }
-        long long v2 = 1000000000LL; int c2 = -1;
-        for (int i = lane; i < 257; i += 32) { const long long fi = freq[i]; if (fi && fi <= v2 && i != c1) { v2 = fi; c2 = i; } }
-        for (int o = 16; o; o >>= 1) {
-            const long long ov = __shfl_xor_sync(0xFFFFFFFFu, v2, o); const int oc = __shfl_xor_sync(0xFFFFFFFFu, c2, o);
-            if (oc >= 0 && (c2 < 0 || ov < v2 || (ov == v2 && oc > c2))) { v2 = ov; c2 = oc; }
-        }
+        const int c1 = warp_argmin(-1);
+        const int c2 = c1 < 0 ? -1 : warp_argmin(c1);
         if (c2 < 0) break;
         if (lane == 0) {
             int a = c1, b = c2;
