@@ -224,8 +224,6 @@ bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &er
         G.blocks_per_mcu = q;
         G.total_blocks = g.ncomp == 1 ? (uint32_t)(g.rbw[0] * g.rbh[0]) : (uint32_t)(g.mcux * g.mcuy * q);
         static const int subseq_bits = [] { const char *e = getenv("B200_DEC_SUBSEQ"); const int v = e ? atoi(e) : 0; return v >= 128 && v <= 8192 && v % 32 == 0 ? v : (int)SUBSEQ_BITS; }();
-        static const uint32_t prefetch = [] { const char *e = getenv("B200_DEC_PREFETCH"); return (uint32_t)!(e && atoi(e) == 0); }();
-        G.prefetch = prefetch;
         G.nbits = nstream * 8; G.subseq_bits = subseq_bits; G.nsub = (G.nbits + G.subseq_bits - 1) / G.subseq_bits;
         if (G.nsub == 0) { err = "empty scan"; return false; }
         GpuEncPlan plan; const int16_t *base = items[n].d_coefs;

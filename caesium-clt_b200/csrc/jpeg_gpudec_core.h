@@ -34,18 +34,17 @@ struct DecState { uint32_t p; uint16_t k; uint16_t b; };   // 8 bytes
 GE_HD bool same_state(const DecState &a, const DecState &b) { return a.p == b.p && a.k == b.k && a.b == b.b; }
 
 // 32 bits of the unstuffed stream starting at bit position p (big-endian bit order).  The stream buffer is 4-byte
-// aligned and followed by at least 16 bytes of 0xFF padding, so bits past the end read as 1s (like jdhuff.c's padding)
-// and the decoder may read up to three words past the one that holds the last bit.
-GE_HD uint32_t load_raw32(const uint8_t *__restrict__ s, uint32_t word) { return reinterpret_cast<const uint32_t *>(s)[word]; }
-GE_HD uint32_t swap_be32(uint32_t w)
+// aligned and followed by at least 8 bytes of 0xFF padding, so bits past the end read as 1s (like jdhuff.c's padding)
+// and two aligned word loads always suffice.
+GE_HD uint32_t load_be32(const uint8_t *__restrict__ s, uint32_t word)
 {
+    const uint32_t w = reinterpret_cast<const uint32_t *>(s)[word];
 #if defined(__CUDA_ARCH__)
     return __byte_perm(w, 0, 0x0123);
 #else
     return __builtin_bswap32(w);
 #endif
 }
-GE_HD uint32_t load_be32(const uint8_t *__restrict__ s, uint32_t word) { return swap_be32(load_raw32(s, word)); }
 GE_HD uint32_t peek32(const uint8_t *__restrict__ s, uint32_t /*nbits_total*/, uint32_t p)
 {
     const uint32_t wi = p >> 5, sh = p & 31;
@@ -74,7 +73,6 @@ struct Geometry {               // what the decoder needs to know about the scan
     uint32_t nbits;             // length of the unstuffed stream in bits
     uint32_t subseq_bits;
     uint32_t nsub;              // number of subsequences
-    uint32_t prefetch;          // device only: pull the stream two sectors ahead into L1 (B200_DEC_PREFETCH=0 turns it off)
 };
 
 // ---- decode tables, kernel form --------------------------------------------------------------------------------------------
@@ -89,7 +87,7 @@ constexpr int LOOK_BITS = 9, LOOK_N = 1 << LOOK_BITS, MAX_TABLES = 8, EXT_N = 15
 struct DecTables {
     uint16_t look[MAX_TABLES * LOOK_N];     // first level of table slot t at look[t * LOOK_N]
     uint16_t ext[EXT_N];                    // second-level pool
-    alignas(4) uint16_t sel[20];            // [2 * q + (AC ? 1 : 0)] -> first-level offset of block q's DC / AC table (read as one 32-bit pair per q)
+    uint16_t sel[20];                       // [2 * q + (AC ? 1 : 0)] -> first-level offset of block q's DC / AC table
     uint16_t nlook, next;                   // slots / pool entries in use (what has to be staged)
     uint16_t ok, pad_;                      // 0: the tables did not fit the pool (the image is decoded on the host instead)
 };
@@ -199,29 +197,13 @@ GE_HD DecState decode_subsequence(const uint8_t *__restrict__ stream, const Geom
 {
     const uint32_t end = (i + 1) * g.subseq_bits < g.nbits ? (i + 1) * g.subseq_bits : g.nbits;
     uint32_t p = st.p; int k = st.k, b = st.b;
-    // Window over the stream: w0 / w1 hold the (byte-swapped) words the next 32 bits come from; r2 / r3 are the next two words
-    // exactly as loaded.  A symbol consumes at most 16 + 15 bits, so the window moves by at most one word per symbol, and a
-    // word is first touched (swapped into w1) two window moves -- about ten symbols -- after its load was issued: the stream
-    // read stays off the critical path (with the swap right behind the load it was 40 % of the write pass's stall samples).
+    // Three-word window over the stream: w0 / w1 hold the words the next 32 bits come from, w2 is fetched one word ahead so
+    // the load is off the critical path.  A symbol consumes at most 16 + 15 bits, so the window moves by at most one word.
     uint32_t wi = p >> 5;
-    uint32_t w0 = load_be32(stream, wi), w1 = load_be32(stream, wi + 1);
-    uint32_t r2 = load_raw32(stream, wi + 2), r3 = load_raw32(stream, wi + 3);
+    uint32_t w0 = load_be32(stream, wi), w1 = load_be32(stream, wi + 1), w2 = load_be32(stream, wi + 2);
     const int bpm = g.blocks_per_mcu;
-    // first-level offsets of the current block's DC (low half) and AC (high half) tables: re-read once per block, so the
-    // per-symbol table choice is a select, not a shared-memory read on the critical path
-    uint32_t selp = reinterpret_cast<const uint32_t *>(T.sel)[b];
-#if defined(__CUDA_ARCH__)
-    const uint32_t last_word = (g.nbits >> 5) + 3;      // inside the 0xFF padding
-    if (g.prefetch) asm volatile("prefetch.global.L1 [%0];" :: "l"(reinterpret_cast<const uint32_t *>(stream) + ((wi + 8 < last_word ? wi + 8 : last_word))));
-#endif
     while (p < end) {
-        if ((p >> 5) != wi) {
-            wi = p >> 5; w0 = w1; w1 = swap_be32(r2); r2 = r3; r3 = load_raw32(stream, wi + 3);
-#if defined(__CUDA_ARCH__)
-            // entering a new 32-byte sector: ask for the sector two ahead, so that the register load above finds its word in L1
-            if (g.prefetch && (wi & 7u) == 0) { const uint32_t pw = wi + 16 < last_word ? wi + 16 : last_word; asm volatile("prefetch.global.L1 [%0];" :: "l"(reinterpret_cast<const uint32_t *>(stream) + pw)); }
-#endif
-        }
+        if ((p >> 5) != wi) { wi = p >> 5; w0 = w1; w1 = w2; w2 = load_be32(stream, wi + 2); }
         const uint32_t sh = p & 31;
 #if defined(__CUDA_ARCH__)
         const uint32_t bits = __funnelshift_l(w1, w0, sh);
@@ -231,7 +213,7 @@ GE_HD DecState decode_subsequence(const uint8_t *__restrict__ stream, const Geom
         // One uniform body for DC and AC symbols (a DC symbol is "run 0, category s at index 0"), selects instead of
         // branches: the lanes of a warp sit at unrelated points of their blocks, so divergent paths would serialise.
         const bool dc = k == 0;
-        const uint32_t e = lookup_symbol(T, dc ? (selp & 0xFFFFu) : (selp >> 16), bits);
+        const uint32_t e = lookup_symbol(T, T.sel[2 * b + (dc ? 0 : 1)], bits);
         const int len = (int)(e >> 8), sym = (int)(e & 0xFF);
         const int r = dc ? 0 : (sym >> 4), s = sym & 15;
         const uint32_t ext = s ? (bits << len) >> (32 - s) : 0u;
@@ -241,7 +223,7 @@ GE_HD DecState decode_subsequence(const uint8_t *__restrict__ stream, const Geom
         if (!eob_or_zrl) sk.coef(kw, v);
         k = eob_or_zrl ? (r == 15 ? k + 16 : 64) : kw + 1;
         p += (uint32_t)(len + s);
-        if (k >= 64) { k = 0; b++; if (b == bpm) b = 0; selp = reinterpret_cast<const uint32_t *>(T.sel)[b]; sk.block_done(); }
+        if (k >= 64) { k = 0; b++; if (b == bpm) b = 0; sk.block_done(); }
     }
     DecState o; o.p = p; o.k = (uint16_t)k; o.b = (uint16_t)b;
     return o;
