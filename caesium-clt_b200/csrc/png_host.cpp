@@ -48,7 +48,14 @@ uint32_t adler32(const uint8_t *p, size_t n)
 
 // ---- inflate -----------------------------------------------------------------------------------------------------------
 namespace {
-struct InfTable { uint16_t fast[1 << 12]; uint16_t count[16]; uint16_t symbol[320]; int maxlen; };   // fast: (len << 12) | sym, 0 = slow path
+struct InfTable {
+    uint16_t fast[1 << 12]; uint16_t count[16]; uint16_t symbol[320]; int maxlen;   // fast: (len << 12) | sym, 0 = slow path
+    // the same 12-bit lookup with the symbol already interpreted, for the unchecked inner loop of zlib_inflate (build_rich):
+    // bits 0..3 code length (0 = leave the fast loop), bit 4 literal, bit 5 end of block, bits 8..11 extra-bit count,
+    // bits 16..31 literal value / length base / distance base
+    uint32_t rich[1 << 11];     // literal/length codes use all 11 index bits, distance codes the low 9 (longer codes: checked path)
+};
+enum { RICH_LIT = 1 << 4, RICH_EOB = 1 << 5 };
 
 bool build_inf(InfTable &t, const uint8_t *lens, int n)
 {
@@ -114,6 +121,23 @@ const uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3
 const uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
 const uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 const uint8_t kClOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+constexpr int RICH_LIT_BITS = 11, RICH_DIST_BITS = 9;
+void build_rich(InfTable &t, bool dist)
+{
+    const int bits = dist ? RICH_DIST_BITS : RICH_LIT_BITS;
+    for (int f = 0; f < (1 << bits); f++) {
+        const uint32_t e = t.fast[f]; uint32_t r = 0;
+        if (e && (int)(e >> 12) <= bits) {
+            const uint32_t len = e >> 12, s = e & 0xFFF;
+            if (dist) { if (s < 30) r = len | ((uint32_t)kDistExtra[s] << 8) | ((uint32_t)kDistBase[s] << 16); }
+            else if (s < 256) r = len | RICH_LIT | (s << 16);
+            else if (s == 256) r = len | RICH_EOB;
+            else if (s < 286) r = len | ((uint32_t)kLenExtra[s - 257] << 8) | ((uint32_t)kLenBase[s - 257] << 16);
+        }
+        t.rich[f] = r;             // 0: long code or invalid symbol -> the checked path deals with it
+    }
+}
 } // namespace
 
 bool zlib_inflate(const uint8_t *in, size_t n, std::vector<uint8_t> &out, size_t size_hint, std::string &err)
@@ -142,6 +166,7 @@ bool zlib_inflate(const uint8_t *in, size_t n, std::vector<uint8_t> &out, size_t
                 build_inf(lit, lens, 288);
                 for (int i = 0; i < 30; i++) lens[i] = 5;
                 build_inf(dist, lens, 30);
+                build_rich(lit, false); build_rich(dist, true);
             } else {
                 const int hlit = (int)b.get(5) + 257, hdist = (int)b.get(5) + 1, hclen = (int)b.get(4) + 4;
                 uint8_t cl[19] = {0};
@@ -162,10 +187,54 @@ bool zlib_inflate(const uint8_t *in, size_t n, std::vector<uint8_t> &out, size_t
                     }
                 }
                 if (!build_inf(lit, lens, hlit) || !build_inf(dist, lens + hlit, hdist)) { err = "bad Huffman code"; return false; }
+                build_rich(lit, false); build_rich(dist, true);
             }
             for (;;) {
-                if (cap - pos < 320) { cap = cap * 2 + 4096; out.resize(cap + 16); }     // room for one match + 8-byte copy slack
+                if (cap - pos < 640) { cap = cap * 2 + 4096; out.resize(cap + 16); }     // room for the fast loop's unchecked stretch
                 uint8_t *o = out.data();
+                // ---- unchecked inner loop: one 64-bit refill per iteration covers a whole match (15 + 5 + 15 + 13 bits) or up
+                // to three literals; it runs while >= 16 input bytes and >= 320 output bytes remain and hands anything unusual
+                // (codes longer than 12 bits, invalid symbols, distances past the start) to the checked code below, untouched
+                {
+                    const uint8_t *ip = b.p; uint64_t acc = b.acc; int nb = b.n;
+                    uint8_t *op = o + pos, *const olimit = o + cap - 320;
+                    const uint8_t *const ilimit = b.end - 16;
+                    bool eob = false;
+                    while (ip <= ilimit && op <= olimit) {
+                        { uint64_t v; memcpy(&v, ip, 8); acc |= v << nb; ip += (63 - nb) >> 3; nb |= 56; }
+                        uint32_t e = lit.rich[acc & ((1u << RICH_LIT_BITS) - 1)];
+                        if (e & RICH_LIT) {
+                            *op++ = (uint8_t)(e >> 16); acc >>= (e & 15); nb -= (int)(e & 15);
+                            e = lit.rich[acc & ((1u << RICH_LIT_BITS) - 1)];
+                            if (e & RICH_LIT) {
+                                *op++ = (uint8_t)(e >> 16); acc >>= (e & 15); nb -= (int)(e & 15);
+                                e = lit.rich[acc & ((1u << RICH_LIT_BITS) - 1)];
+                                if (e & RICH_LIT) { *op++ = (uint8_t)(e >> 16); acc >>= (e & 15); nb -= (int)(e & 15); }
+                            }
+                            continue;
+                        }
+                        if (!(e & 15)) break;
+                        if (e & RICH_EOB) { acc >>= (e & 15); nb -= (int)(e & 15); eob = true; break; }
+                        // a match: decode everything on copies, commit only when it is sound
+                        uint64_t a2 = acc >> (e & 15); int n2 = nb - (int)(e & 15);
+                        const uint32_t lx = (e >> 8) & 15;
+                        const size_t len = (e >> 16) + (size_t)(a2 & ((1u << lx) - 1)); a2 >>= lx; n2 -= (int)lx;
+                        const uint32_t de = dist.rich[a2 & ((1u << RICH_DIST_BITS) - 1)];
+                        if (!(de & 15)) break;
+                        a2 >>= (de & 15); n2 -= (int)(de & 15);
+                        const uint32_t dx = (de >> 8) & 15;
+                        const size_t d = (de >> 16) + (size_t)(a2 & ((1u << dx) - 1)); a2 >>= dx; n2 -= (int)dx;
+                        if (d > (size_t)(op - o)) break;
+                        acc = a2; nb = n2;
+                        const uint8_t *src = op - d;
+                        if (d >= 8) { for (size_t k = 0; k < len; k += 8) memcpy(op + k, src + k, 8); }
+                        else if (d == 1) memset(op, src[0], len);
+                        else for (size_t k = 0; k < len; k++) op[k] = src[k];
+                        op += len;
+                    }
+                    b.p = ip; b.acc = acc; b.n = nb; pos = (size_t)(op - o);
+                    if (eob) break;
+                }
                 int s = inf_decode(b, lit);
                 if (s < 0) { err = "bad literal/length code"; return false; }
                 if (s < 256) o[pos++] = (uint8_t)s;
@@ -325,11 +394,19 @@ void png_write(const PngInfo &info, const std::vector<uint8_t> &z, std::vector<u
 
 // ---- DEFLATE encoder over device-made LZ77 tokens --------------------------------------------------------------------------
 namespace {
-struct BitOut {
-    std::vector<uint8_t> &o; uint64_t acc = 0; int n = 0;
-    explicit BitOut(std::vector<uint8_t> &out) : o(out) {}
-    inline void put(uint32_t v, int k) { acc |= (uint64_t)v << n; n += k; while (n >= 8) { o.push_back((uint8_t)acc); acc >>= 8; n -= 8; } }
-    inline void flush() { if (n) { o.push_back((uint8_t)acc); acc = 0; n = 0; } }
+struct BitOut {                 // LSB-first bit writer over a vector grown in big steps; branch-free: every put stores the 8-byte
+                                // accumulator at the write position and advances by the whole bytes it holds
+    std::vector<uint8_t> &o; size_t pos; uint64_t acc = 0; int n = 0;          // n < 8 between puts
+    explicit BitOut(std::vector<uint8_t> &out) : o(out), pos(out.size()) {}
+    inline void reserve(size_t more) { if (o.size() < pos + more + 16) o.resize(std::max(o.size() * 2, pos + more + 16)); }
+    inline void put(uint64_t v, int k)              // k <= 56; the caller has reserved the room
+    {
+        acc |= v << n; n += k;
+        memcpy(o.data() + pos, &acc, 8);
+        const int adv = n >> 3;
+        pos += (size_t)adv; acc = adv >= 8 ? 0 : acc >> (adv * 8); n &= 7;
+    }
+    inline void flush() { if (n > 0) { o[pos++] = (uint8_t)acc; } acc = 0; n = 0; o.resize(pos); }
 };
 
 // length-limited Huffman code lengths: plain Huffman, then the IJG/zlib style overflow repair, then lengths handed out by rank
@@ -382,18 +459,25 @@ void canon_codes(const uint8_t *len, int n, uint16_t *code)
 }
 
 inline int len_sym(int len) { int s = 0; while (s < 28 && kLenBase[s + 1] <= len) s++; return s; }
-inline int dist_sym(int d) { int s = 0; while (s < 29 && kDistBase[s + 1] <= d) s++; return s; }
+inline int dist_sym(int d)      // RFC 1951 distance code of d = 1..32768 in closed form: two codes per power of two above 4
+{
+    const unsigned x = (unsigned)d - 1u;
+    if (x < 4u) return (int)x;
+    const int nb = 31 - __builtin_clz(x);
+    return 2 * nb + (int)((x >> (nb - 1)) & 1u);
+}
 } // namespace
 
 void deflate_tokens(const uint32_t *tok, size_t nt, uint32_t adler, std::vector<uint8_t> &out, size_t block_tokens)
 {
-    out.clear(); out.reserve(nt + 64);
+    out.clear(); out.reserve(nt + nt / 4 + 1024);
     out.push_back(0x78); out.push_back(0xDA);
     BitOut bw(out);
-    static uint8_t lsym[259], dsym_small[513]; static bool init = false;
-    if (!init) { for (int l = 3; l <= 258; l++) lsym[l] = (uint8_t)len_sym(l); for (int d = 1; d <= 512; d++) dsym_small[d] = (uint8_t)dist_sym(d); init = true; }
-    auto dsym = [&](int d) { return d <= 512 ? (int)dsym_small[d] : dist_sym(d); };
+    static uint8_t lsym[259]; static bool init = false;
+    if (!init) { for (int l = 3; l <= 258; l++) lsym[l] = (uint8_t)len_sym(l); init = true; }
+    auto dsym = [&](int d) { return dist_sym(d); };
     size_t pos = 0;
+    bw.reserve(64);
     if (nt == 0) { bw.put(1, 1); bw.put(1, 2); bw.put(0, 7); }
     while (pos < nt) {
         const size_t end = std::min(nt, pos + block_tokens);
@@ -432,6 +516,7 @@ void deflate_tokens(const uint32_t *tok, size_t nt, uint32_t adler, std::vector<
         uint8_t cll[19]; uint16_t clc[19];
         huff_lengths(cf, 19, 7, cll); canon_codes(cll, 19, clc);
         int hclen = 19; while (hclen > 4 && !cll[kClOrder[hclen - 1]]) hclen--;
+        bw.reserve(512 + (end - pos) * 6);                  // header < 400 bytes; a token is at most 15 + 5 + 15 + 13 bits
         bw.put(end == nt ? 1 : 0, 1); bw.put(2, 2);
         bw.put((uint32_t)(hlit - 257), 5); bw.put((uint32_t)(hdist - 1), 5); bw.put((uint32_t)(hclen - 4), 4);
         for (int i = 0; i < hclen; i++) bw.put(cll[kClOrder[i]], 3);
@@ -439,17 +524,25 @@ void deflate_tokens(const uint32_t *tok, size_t nt, uint32_t adler, std::vector<
             bw.put(clc[cls[i].sym], cll[cls[i].sym]);
             if (cls[i].sym == 16) bw.put(cls[i].extra, 2); else if (cls[i].sym == 17) bw.put(cls[i].extra, 3); else if (cls[i].sym == 18) bw.put(cls[i].extra, 7);
         }
+        // per-block emit tables: literal -> (code, bits); match length 3..258 -> code and extra bits as one piece (<= 20 bits)
+        uint32_t lit_cb[256], len_cb[256]; uint8_t lit_nb[256], len_nb[256];
+        for (int c = 0; c < 256; c++) { lit_cb[c] = lc[c]; lit_nb[c] = ll[c]; }
+        for (int l = 3; l <= 258; l++) {
+            const int ls = lsym[l], sym = 257 + ls;
+            len_cb[l - 3] = (uint32_t)lc[sym] | ((uint32_t)(l - kLenBase[ls]) << ll[sym]); len_nb[l - 3] = (uint8_t)(ll[sym] + kLenExtra[ls]);
+        }
         for (size_t i = pos; i < end; i++) {
             const uint32_t t = tok[i];
             if (t & 0x80000000u) {
-                const int len = (int)((t >> 16) & 0xFF) + 3, d = (int)(t & 0xFFFF) + 1, ls = lsym[len], ds = dsym(d);
-                bw.put(lc[257 + ls], ll[257 + ls]); if (kLenExtra[ls]) bw.put((uint32_t)(len - kLenBase[ls]), kLenExtra[ls]);
-                bw.put(dc[ds], dl[ds]); if (kDistExtra[ds]) bw.put((uint32_t)(d - kDistBase[ds]), kDistExtra[ds]);
-            } else bw.put(lc[t & 0xFF], ll[t & 0xFF]);
+                const int li = (int)((t >> 16) & 0xFF), d = (int)(t & 0xFFFF) + 1, ds = dsym(d);
+                const uint64_t dpiece = (uint64_t)dc[ds] | ((uint64_t)(d - kDistBase[ds]) << dl[ds]);                  // <= 15 + 13 bits
+                bw.put((uint64_t)len_cb[li] | (dpiece << len_nb[li]), len_nb[li] + dl[ds] + kDistExtra[ds]);           // <= 20 + 28 bits
+            } else bw.put(lit_cb[t & 0xFF], lit_nb[t & 0xFF]);
         }
         bw.put(lc[256], ll[256]);
         pos = end;
     }
+    bw.reserve(16);
     bw.flush();
     out.push_back(adler >> 24); out.push_back(adler >> 16); out.push_back(adler >> 8); out.push_back(adler);
 }

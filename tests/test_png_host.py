@@ -79,6 +79,28 @@ def test_host_deflate_writer_many_blocks(L, O):
     assert zlib.decompress(z) == stream.tobytes()
 
 
+def test_host_deflate_writer_every_distance_and_length(L):
+    """every match distance 1..32768 and every length 3..258 through the writer (closed-form distance codes, merged code + extra-bit
+    pieces, branch-free bit packing): the stream must inflate to what the tokens say"""
+    rng = np.random.default_rng(17)
+    head = rng.integers(0, 256, 32768).astype(np.uint8)
+    tok = list(head.astype(np.uint32))
+    out = bytearray(head.tobytes())
+    for d in range(1, 32769):
+        ln = 3 + (d * 7) % 256
+        tok.append(0x80000000 | ((ln - 3) << 16) | (d - 1))
+        for _ in range(ln):
+            out.append(out[-d])
+        if d % 5 == 0:
+            tok.append(int(d & 255)); out.append(d & 255)
+    for ln in range(3, 259):
+        tok.append(0x80000000 | ((ln - 3) << 16) | (4 - 1))
+        for _ in range(ln):
+            out.append(out[-4])
+    z = L.png_deflate_tokens(np.array(tok, dtype=np.uint32), zlib.adler32(bytes(out)))
+    assert zlib.decompress(z) == bytes(out)
+
+
 @pytest.mark.parametrize("mode", ["L", "LA", "RGB", "RGBA", "P", "1", "I;16", "L2", "L4"])
 def test_host_png_decode_matches_pillow(L, mode):
     from PIL import Image
