@@ -279,6 +279,10 @@ def main():
         try:
             tr = json.load(open(traffic_file))
             roofline["traffic"] = tr.get("k_fused_same_bytes_per_image", 0) * B or None
+            # what actually bounds the kernel (ncu --set full, profiles/): exact ISLOW butterflies are integer multiply-adds, which
+            # issue on the fmaheavy half of the FMA pipe only; reported next to the HBM fraction so the two are not confused
+            if "k_fused_same_pipes" in tr:
+                roofline["pipes"] = dict(tr["k_fused_same_pipes"], source=tr.get("source", "profiles/traffic.json"))
         except Exception:
             pass
     batch.close()
@@ -316,7 +320,7 @@ def main():
     d2h = out_bytes if ent in ("gpu", "gpuenc") else Be * int(olay.total_coefs) * 2
     e2e = {"value": round(e2e_val, 2), "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "images_per_sec": round(e2e_val / MP_PER_IMAGE, 2), "host_threads": threads, "in_bytes_per_step": in_bytes, "out_bytes_per_step": out_bytes,
-           "entropy": ent, "megabatch": int(os.environ.get("B200_MEGABATCH", "8")),
+           "entropy": ent, "megabatch": int(os.environ.get("B200_MEGABATCH", "8")), "group_workers": min(threads, int(os.environ.get("B200_GROUP_WORKERS", "16"))),
            "note": "JPEG bytes in host memory -> JPEG bytes in host memory via b200_compress_batch (the batch form of start_compression's par_iter), all inside the timed region: marker parsing, pinned H2D of the entropy-coded scans, device Huffman decode, transform kernels, device Huffman encode (statistics, optimal tables, bit packing, stuffing), D2H of the scans, file assembly. Output bytes are identical to the oracle's. B200_ENTROPY=host keeps both entropy stages on host threads."}
 
     cpu = None

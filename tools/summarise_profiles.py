@@ -8,7 +8,8 @@ WANT = ["Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.s
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio", "lts__t_sector_hit_rate.pct"]
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "lts__t_sector_hit_rate.pct"]
 
 
 def raw(rep):
@@ -47,8 +48,13 @@ t = summarise(os.path.join(G, f"{tag}_transform.ncu-rep"), f"{tag} -- transform 
 summarise(os.path.join(G, f"{tag}_entropy.ncu-rep"), f"{tag} -- entropy kernels of one megabatch (8 images of 3840x2160) through b200_compress_batch (tools/profile_group.py 8)", os.path.join(P, f"{tag}_ncu_entropy_full.txt"))
 k = next(v for n, v in t.items() if "k_fused_same" in n)
 traffic = to_bytes(k["dram__bytes_read.sum"], k["units"]["dram__bytes_read.sum"]) + to_bytes(k["dram__bytes_write.sum"], k["units"]["dram__bytes_write.sum"])
+fl = lambda key: float(k[key].replace(",", ""))
 json.dump({"source": f"profiles/{tag}_ncu_transform_full.txt (ncu --set full, one k_fused_same launch over 64 images)", "k_fused_same_bytes_per_launch": traffic, "images_per_launch": 64,
-           "k_fused_same_bytes_per_image": traffic / 64}, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+           "k_fused_same_bytes_per_image": traffic / 64,
+           "k_fused_same_pipes": {"warp_instructions_per_launch": fl("smsp__inst_executed.sum"), "issue_active_pct": fl("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                                  "alu_pct": fl("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"), "fma_pct": fl("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                                  "fmaheavy_cycles_pct": fl("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"), "registers": fl("launch__registers_per_thread")}},
+          open(os.path.join(P, "traffic.json"), "w"), indent=1)
 for f in (f"{tag}_launches_bench.csv", f"{tag}_launches_group.csv", f"{tag}_bench.json", f"{tag}_bench_reference.json"):
     shutil.copy(os.path.join(G, f), os.path.join(P, f))
 # per-kernel table of one megabatch
