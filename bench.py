@@ -337,6 +337,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
             "config": {"workload": "configs[1]: 3840x2160 RGB JPEG q90 4:2:0 -> -q 80 --jpeg-chroma-subsampling 4:2:0 (progressive, optimised Huffman)",
+                       "value_scope": "north_star's named transform kernels (K1-K5) over HBM-resident coefficients; the device Huffman decode / encode passes run inside e2e, which is GPU-bound (profiles/r1c_group_kernels.txt)",
                        "images_per_step_per_gpu": B, "unique_sources_per_gpu": len(datas), "parallelism": f"dp{world} (images sharded, no collective on the path)",
                        "l2": f"inputs larger than L2 ({B * coef_bytes / 1e6:.0f} MB of coefficients per step per GPU vs 126 MB)"},
             "images_per_sec": round(value / MP_PER_IMAGE, 1),
