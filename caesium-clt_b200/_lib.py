@@ -66,7 +66,7 @@ _SYMBOLS = [
     "b200_jpeg_encode_coefficients", "b200_jpeg_decode_planes", "b200_jpeg_quant_table",
     "b200_jpeg_batch_create", "b200_jpeg_batch_upload", "b200_jpeg_batch_run", "b200_jpeg_batch_download",
     "b200_jpeg_batch_time", "b200_jpeg_batch_destroy", "b200_jpeg_encode_coefficients_device",
-    "b200_png_decode", "b200_png_filter", "b200_png_lz77", "b200_png_deflate_tokens", "b200_png_level_strategies",
+    "b200_png_decode", "b200_png_decode_reduced", "b200_png_filter", "b200_png_lz77", "b200_png_deflate_tokens", "b200_png_level_strategies",
     "b200_webp_encode_rgb", "b200_webp_write_levels", "b200_webp_qindex",
 ]
 
@@ -83,7 +83,7 @@ def lib():
                   "b200_jpeg_decode_coefficients", "b200_jpeg_output_layout", "b200_jpeg_requantize",
                   "b200_jpeg_encode_coefficients", "b200_jpeg_decode_planes", "b200_jpeg_batch_create",
                   "b200_jpeg_batch_upload", "b200_jpeg_batch_run", "b200_jpeg_batch_download", "b200_jpeg_batch_time",
-                  "b200_png_decode", "b200_png_filter", "b200_png_lz77", "b200_png_deflate_tokens",
+                  "b200_png_decode", "b200_png_decode_reduced", "b200_png_filter", "b200_png_lz77", "b200_png_deflate_tokens",
                   "b200_webp_encode_rgb", "b200_webp_write_levels", "b200_jpeg_encode_coefficients_device"):
             getattr(L, f).restype = Status
         L.b200_version.restype = C.c_char_p
@@ -249,6 +249,19 @@ def png_decode(data):
     arr = np.frombuffer(C.string_at(raw, n), dtype=np.uint8).reshape(info.height, info.row_bytes).copy()
     lib().b200_free(raw)
     return info, arr
+
+
+def png_decode_reduced(data):
+    """Host: png_decode + the palette reduction of the lossless path -> (PngInfo, raw, palette [n, 4] RGBA or None)."""
+    info, raw = PngInfo(), C.POINTER(C.c_uint8)()
+    pal, npal = (C.c_uint8 * 1024)(), C.c_int(0)
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    _check(lib().b200_png_decode_reduced(buf, C.c_size_t(len(data)), C.byref(info), C.byref(raw), pal, C.byref(npal)))
+    n = info.height * info.row_bytes
+    arr = np.frombuffer(C.string_at(raw, n), dtype=np.uint8).reshape(info.height, info.row_bytes).copy()
+    lib().b200_free(raw)
+    palette = np.frombuffer(bytes(pal), dtype=np.uint8)[:4 * npal.value].reshape(-1, 4).copy() if npal.value else None
+    return info, arr, palette
 
 
 def png_filter(raw, bpp, strategy):

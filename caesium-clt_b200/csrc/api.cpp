@@ -313,6 +313,7 @@ b200_status png_compress(const uint8_t *in, size_t in_len, const b200_params *p,
     if (!png_decode(in, in_len, p->keep_metadata != 0, info, raw, err)) return make_status(err.find("interlace") != std::string::npos ? B200_ERR_UNSUPPORTED : B200_ERR_CORRUPT_INPUT, err);
     const auto t1 = std::chrono::steady_clock::now();
     if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
+    png_reduce_palette(info, raw);                   // <= 256 colours: indexed samples go to the device (oxipng reduction::palette)
     Slot *s = slot_acquire(prefer_dev < 0 ? runtime_next_device() : prefer_dev, err);
     if (!s) return make_status(B200_ERR_CUDA, err);
     if (!s->png) s->png = new PngDevice();
@@ -861,6 +862,25 @@ b200_status b200_png_decode(const uint8_t *in, size_t in_len, b200_png_info *inf
     if (!in || !info || !raw) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
     std::string err; PngInfo pi; std::vector<uint8_t> r;
     if (!png_decode(in, in_len, false, pi, r, err)) return make_status(err.find("interlace") != std::string::npos ? B200_ERR_UNSUPPORTED : B200_ERR_CORRUPT_INPUT, err);
+    info->width = pi.width; info->height = pi.height; info->bit_depth = pi.bit_depth; info->color_type = pi.color_type; info->bpp = pi.bpp; info->row_bytes = pi.row_bytes;
+    *raw = (uint8_t *)malloc(r.size() ? r.size() : 1);
+    if (!*raw) return make_status(B200_ERR_OUT_OF_MEMORY, "malloc failed");
+    memcpy(*raw, r.data(), r.size());
+    return ok_status();
+}
+b200_status b200_png_decode_reduced(const uint8_t *in, size_t in_len, b200_png_info *info, uint8_t **raw, uint8_t *palette_rgba, int *npalette)
+{
+    if (!in || !info || !raw || !palette_rgba || !npalette) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    std::string err; PngInfo pi; std::vector<uint8_t> r;
+    if (!png_decode(in, in_len, false, pi, r, err)) return make_status(err.find("interlace") != std::string::npos ? B200_ERR_UNSUPPORTED : B200_ERR_CORRUPT_INPUT, err);
+    *npalette = 0;
+    if (png_reduce_palette(pi, r)) {
+        *npalette = (int)(pi.plte.size() / 3);
+        for (int k = 0; k < *npalette; k++) {
+            palette_rgba[4 * k] = pi.plte[3 * k]; palette_rgba[4 * k + 1] = pi.plte[3 * k + 1]; palette_rgba[4 * k + 2] = pi.plte[3 * k + 2];
+            palette_rgba[4 * k + 3] = (size_t)k < pi.trns.size() ? pi.trns[k] : 255;
+        }
+    }
     info->width = pi.width; info->height = pi.height; info->bit_depth = pi.bit_depth; info->color_type = pi.color_type; info->bpp = pi.bpp; info->row_bytes = pi.row_bytes;
     *raw = (uint8_t *)malloc(r.size() ? r.size() : 1);
     if (!*raw) return make_status(B200_ERR_OUT_OF_MEMORY, "malloc failed");

@@ -375,6 +375,76 @@ bool png_decode(const uint8_t *d, size_t n, bool keep_all, PngInfo &info, std::v
     return true;
 }
 
+static bool kept_has(const std::vector<uint8_t> &kept, const char *type)
+{   // kept = serialised chunks: length (4, big endian) | type (4) | data | crc (4)
+    size_t i = 0;
+    while (i + 12 <= kept.size()) {
+        const uint32_t L = be32(kept.data() + i);
+        if (!memcmp(kept.data() + i + 4, type, 4)) return true;
+        if (L > kept.size() - i - 12) break;
+        i += 12 + (size_t)L;
+    }
+    return false;
+}
+
+bool png_reduce_palette(PngInfo &info, std::vector<uint8_t> &raw)
+{
+    if (info.bit_depth != 8 || (info.color_type != 2 && info.color_type != 6) || !info.trns.empty() || !info.plte.empty()) return false;
+    for (const char *t : {"sBIT", "bKGD", "hIST", "acTL"}) if (kept_has(info.kept_before_idat, t) || kept_has(info.kept_after_idat, t)) return false;
+    const size_t npix = (size_t)info.width * info.height; const int ch = info.channels;
+    if (raw.size() < npix * (size_t)ch || npix == 0) return false;
+    // distinct pixel values, first-appearance order; open addressing over 1024 slots; bail out at the 257th colour
+    uint32_t key[1024]; int16_t slot_idx[1024]; memset(slot_idx, 0xFF, sizeof(slot_idx));
+    uint32_t colours[256]; int ncol = 0; bool grey = true;
+    {   // photographs leave here without touching memory: more than 256 values among the first few thousand pixels
+        const size_t probe = std::min<size_t>(npix, 8192);
+        const uint8_t *q = raw.data(); uint32_t seen[512]; uint8_t used[512]; memset(used, 0, sizeof(used)); int nseen = 0;
+        for (size_t i = 0; i < probe; i++, q += ch) {
+            const uint32_t v = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)(ch == 4 ? q[3] : 255) << 24);
+            uint32_t h = (v * 2654435761u) >> 23;
+            while (used[h] && seen[h] != v) h = (h + 1) & 511;
+            if (!used[h]) { if (++nseen > 256) return false; used[h] = 1; seen[h] = v; }
+        }
+    }
+    std::vector<uint8_t> idx(npix);
+    const uint8_t *p = raw.data();
+    uint32_t last = 0; int last_i = -1;
+    for (size_t i = 0; i < npix; i++, p += ch) {
+        const uint32_t v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)(ch == 4 ? p[3] : 255) << 24);
+        if (last_i >= 0 && v == last) { idx[i] = (uint8_t)last_i; continue; }      // runs: flat art is mostly this
+        uint32_t h = (v * 2654435761u) >> 22;
+        for (;;) {
+            const int s = slot_idx[h];
+            if (s < 0) {
+                if (ncol == 256) return false;
+                key[h] = v; slot_idx[h] = (int16_t)ncol; colours[ncol] = v;
+                if (p[0] != p[1] || p[1] != p[2]) grey = false;
+                last_i = ncol++; break;
+            }
+            if (key[h] == v) { last_i = s; break; }
+            h = (h + 1) & 1023;
+        }
+        last = v; idx[i] = (uint8_t)last_i;
+    }
+    if (grey) return false;
+    // entries that are not opaque go first (stable), so tRNS can stop at the last of them
+    uint8_t remap[256]; int order[256], n = 0, ntrans = 0;
+    for (int c = 0; c < ncol; c++) if ((colours[c] >> 24) != 255) order[n++] = c;
+    ntrans = n;
+    for (int c = 0; c < ncol; c++) if ((colours[c] >> 24) == 255) order[n++] = c;
+    for (int k = 0; k < ncol; k++) remap[order[k]] = (uint8_t)k;
+    if (ntrans) for (size_t i = 0; i < npix; i++) idx[i] = remap[idx[i]];
+    info.plte.resize((size_t)ncol * 3); info.trns.resize((size_t)ntrans);
+    for (int k = 0; k < ncol; k++) {
+        const uint32_t v = colours[order[k]];
+        info.plte[3 * k] = (uint8_t)v; info.plte[3 * k + 1] = (uint8_t)(v >> 8); info.plte[3 * k + 2] = (uint8_t)(v >> 16);
+        if (k < ntrans) info.trns[k] = (uint8_t)(v >> 24);
+    }
+    info.color_type = 3; info.channels = 1; info.bits_per_pixel = 8; info.bpp = 1; info.row_bytes = info.width;
+    raw.swap(idx);
+    return true;
+}
+
 void png_write(const PngInfo &info, const std::vector<uint8_t> &z, std::vector<uint8_t> &out)
 {
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1A, '\n'};

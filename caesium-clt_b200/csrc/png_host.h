@@ -22,6 +22,13 @@ struct PngInfo {
 // Parse + inflate + unfilter.  raw = height * row_bytes bytes of packed samples (no filter bytes).
 bool png_decode(const uint8_t *data, size_t len, bool keep_all_metadata, PngInfo &info, std::vector<uint8_t> &raw, std::string &err);
 
+// oxipng reduction::palette (lossless): an 8-bit RGB / RGBA image with at most 256 distinct pixel values becomes an 8-bit
+// indexed image (PLTE, plus tRNS when some entry is not opaque; entries with alpha < 255 first so that tRNS stays short).
+// Grey images (r == g == b everywhere) are left alone -- the grey / opaque-alpha reductions that follow serve them better --
+// and so are files whose kept chunks depend on the colour type (sBIT, bKGD, hIST) or carry animation frames (acTL).
+// Returns true when info / raw were rewritten.
+bool png_reduce_palette(PngInfo &info, std::vector<uint8_t> &raw);
+
 // RFC 1951 inflate of a complete zlib stream (RFC 1950 wrapper checked, Adler-32 verified)
 bool zlib_inflate(const uint8_t *in, size_t n, std::vector<uint8_t> &out, size_t size_hint, std::string &err);
 

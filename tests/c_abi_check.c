@@ -16,7 +16,7 @@ int main(void)
         (fn)b200_sniff_format, (fn)b200_jpeg_decode_coefficients, (fn)b200_jpeg_output_layout, (fn)b200_jpeg_requantize, (fn)b200_jpeg_encode_coefficients,
         (fn)b200_jpeg_encode_coefficients_device, (fn)b200_jpeg_decode_planes, (fn)b200_jpeg_quant_table, (fn)b200_jpeg_batch_create, (fn)b200_jpeg_batch_upload,
         (fn)b200_jpeg_batch_run, (fn)b200_jpeg_batch_download, (fn)b200_jpeg_batch_time, (fn)b200_jpeg_batch_destroy,
-        (fn)b200_png_decode, (fn)b200_png_filter, (fn)b200_png_lz77, (fn)b200_png_deflate_tokens, (fn)b200_png_level_strategies,
+        (fn)b200_png_decode, (fn)b200_png_decode_reduced, (fn)b200_png_filter, (fn)b200_png_lz77, (fn)b200_png_deflate_tokens, (fn)b200_png_level_strategies,
         (fn)b200_webp_encode_rgb, (fn)b200_webp_write_levels, (fn)b200_webp_qindex,
     };
     size_t i, n = sizeof(all) / sizeof(all[0]);

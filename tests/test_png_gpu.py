@@ -110,6 +110,17 @@ def test_compress_png_reductions(L):
     _check_lossless(L, pil_png(real), expect_mode="RGBA")                    # nothing to reduce
 
 
+def test_compress_png_palette_reduction(L):
+    """<= 256 colours: the file comes back indexed (PLTE + tRNS), pixel-exact, and far smaller than one byte per sample"""
+    for ch in (3, 4):
+        img = synth(150, 220, ch, seed=40 + ch, kind="flat")
+        if ch == 4:
+            img[20:60, 30:90, 3] = 0; img[100:110, :, 3] = 77
+        out, ihdr, filt = _check_lossless(L, pil_png(img), expect_mode="P")
+        assert ihdr[2] == 8 and ihdr[3] == 3 and len(filt) == 150 * (220 + 1)
+        assert len(out) < 150 * 220 // 8
+
+
 def test_compress_png_palette_16bit_and_bilevel(L):
     from PIL import Image
     rng = np.random.default_rng(3)

@@ -1,6 +1,7 @@
 """CPU tests of the PNG lossless leg: the oracle restatement (oracle/png_oracle.c) pinned against
 Pillow/libpng + zlib, and the product's HOST half (container parse, inflate, unfilter, DEFLATE writer) through the C-ABI.
 No device work is called here."""
+import io
 import zlib
 
 import numpy as np
@@ -186,3 +187,48 @@ def test_png_level_strategy_sets(L):
 def test_idat_helper_on_pillow_file():
     ihdr, idat, order = idat_stream(pil_png(synth(8, 8, 3)))
     assert ihdr[:2] == (8, 8) and order[0] == b"IHDR" and order[-1] == b"IEND" and len(zlib.decompress(idat)) == 8 * 25
+
+
+def test_palette_reduction_is_lossless_and_declines_when_it_should(L):
+    """oxipng reduction::palette on the host: <= 256 distinct RGB / RGBA pixels -> 8-bit indices + PLTE (+ tRNS, non-opaque
+    entries first); photographs, grey images, inputs with tRNS / 16-bit / palette stay as decoded."""
+    from PIL import Image
+    rng = np.random.default_rng(21)
+    # flat art, RGB and RGBA (with partly transparent colours)
+    for ch in (3, 4):
+        img = synth(90, 140, ch, seed=5 + ch, kind="flat")
+        if ch == 4:
+            img[10:30, 20:60, 3] = 0; img[40:50, :, 3] = 128
+        info, raw, pal = L.png_decode_reduced(pil_png(img))
+        assert pal is not None and info.color_type == 3 and info.bit_depth == 8 and info.bpp == 1 and info.row_bytes == 140
+        assert len(pal) == len(np.unique(img.reshape(-1, ch), axis=0)) <= 256
+        rgba = pal[raw]                                             # [h, w, 4]
+        want = img if ch == 4 else np.concatenate([img, np.full((90, 140, 1), 255, np.uint8)], axis=2)
+        assert np.array_equal(rgba, want)
+        a = pal[:, 3]
+        assert np.all(a[:np.count_nonzero(a != 255)] != 255)       # the non-opaque entries lead
+    # exactly 256 colours still fits, 257 does not
+    cols = rng.permutation(256 * 256)[:257]
+    base = np.stack([cols % 256, cols // 256, (cols * 7) % 256], axis=1).astype(np.uint8)
+    for n, expect in ((256, True), (257, False)):
+        img = base[rng.integers(0, n, (64, 64))]
+        img.reshape(-1, 3)[:n] = base[:n]
+        info, raw, pal = L.png_decode_reduced(pil_png(img))
+        assert (pal is not None) == expect
+        if expect:
+            assert np.array_equal(pal[raw][:, :, :3], img)
+        else:
+            assert info.color_type == 2 and np.array_equal(raw.reshape(64, 64, 3), img)
+    # declined: photograph, grey RGB (left to the grey reduction), grey+alpha, 16-bit, palette input, RGB with a tRNS colour
+    assert L.png_decode_reduced(pil_png(synth(50, 60, 3, seed=1)))[2] is None
+    g = synth(50, 60, 1, seed=2, kind="flat")
+    assert L.png_decode_reduced(pil_png(np.repeat(g, 3, axis=2)))[2] is None
+    assert L.png_decode_reduced(pil_png(np.concatenate([g, g], axis=2)))[2] is None
+    assert L.png_decode_reduced(pil_png(Image.fromarray((g[:, :, 0].astype(np.uint16) * 257))))[2] is None
+    im = Image.fromarray((g[:, :, 0] % 4).astype(np.uint8), mode="P"); im.putpalette([0, 0, 0, 255, 0, 0, 0, 255, 0, 0, 0, 255])
+    assert L.png_decode_reduced(pil_png(im))[2] is None
+    b = io.BytesIO(); Image.fromarray(synth(30, 30, 3, seed=3, kind="flat")).save(b, format="PNG", transparency=(255, 255, 255))
+    assert L.png_decode_reduced(b.getvalue())[2] is None
+    # a single pixel, and a single colour
+    info, raw, pal = L.png_decode_reduced(pil_png(np.array([[[9, 200, 30]]], dtype=np.uint8)))
+    assert pal is not None and np.array_equal(pal, [[9, 200, 30, 255]]) and raw.tolist() == [[0]]
