@@ -440,8 +440,17 @@ bool png_reduce_palette(PngInfo &info, std::vector<uint8_t> &raw)
         info.plte[3 * k] = (uint8_t)v; info.plte[3 * k + 1] = (uint8_t)(v >> 8); info.plte[3 * k + 2] = (uint8_t)(v >> 16);
         if (k < ntrans) info.trns[k] = (uint8_t)(v >> 24);
     }
-    info.color_type = 3; info.channels = 1; info.bits_per_pixel = 8; info.bpp = 1; info.row_bytes = info.width;
-    raw.swap(idx);
+    // oxipng reduction::bit_depth for palettes: 16 / 4 / 2 entries fit 4 / 2 / 1 bits per index (rows packed MSB first, padded to bytes)
+    const int depth = ncol <= 2 ? 1 : ncol <= 4 ? 2 : ncol <= 16 ? 4 : 8;
+    info.color_type = 3; info.channels = 1; info.bit_depth = depth; info.bits_per_pixel = depth; info.bpp = 1;
+    info.row_bytes = ((size_t)info.width * depth + 7) / 8;
+    if (depth == 8) { raw.swap(idx); return true; }
+    const int per = 8 / depth;
+    raw.assign(info.row_bytes * info.height, 0);
+    for (uint32_t y = 0; y < info.height; y++) {
+        const uint8_t *src = idx.data() + (size_t)y * info.width; uint8_t *dst = raw.data() + (size_t)y * info.row_bytes;
+        for (uint32_t x = 0; x < info.width; x++) dst[x / per] |= (uint8_t)(src[x] << (8 - depth - (x % per) * depth));
+    }
     return true;
 }
 

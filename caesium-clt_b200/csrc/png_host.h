@@ -23,7 +23,8 @@ struct PngInfo {
 bool png_decode(const uint8_t *data, size_t len, bool keep_all_metadata, PngInfo &info, std::vector<uint8_t> &raw, std::string &err);
 
 // oxipng reduction::palette (lossless): an 8-bit RGB / RGBA image with at most 256 distinct pixel values becomes an 8-bit
-// indexed image (PLTE, plus tRNS when some entry is not opaque; entries with alpha < 255 first so that tRNS stays short).
+// indexed image (PLTE, plus tRNS when some entry is not opaque; entries with alpha < 255 first so that tRNS stays short), packed
+// to 4 / 2 / 1 bits per index when the palette has at most 16 / 4 / 2 entries (oxipng reduction::bit_depth).
 // Grey images (r == g == b everywhere) are left alone -- the grey / opaque-alpha reductions that follow serve them better --
 // and so are files whose kept chunks depend on the colour type (sBIT, bKGD, hIST) or carry animation frames (acTL).
 // Returns true when info / raw were rewritten.

@@ -163,8 +163,9 @@ void b200_jpeg_batch_destroy(b200_jpeg_batch *b);
 typedef struct { uint32_t width, height; int32_t bit_depth, color_type, bpp; uint64_t row_bytes; } b200_png_info;
 b200_status b200_png_decode(const uint8_t *in, size_t in_len, b200_png_info *info, uint8_t **raw);
 /* host: b200_png_decode followed by the lossless path's palette reduction (oxipng reduction::palette: an 8-bit RGB / RGBA image
- * with at most 256 distinct pixels becomes 8-bit indexed).  *npalette = 0: nothing was reduced, info / raw are as decoded;
- * otherwise raw holds one index per pixel and palette_rgba (caller-allocated, 1024 bytes) the entries as R, G, B, A. */
+ * with at most 256 distinct pixels becomes indexed).  *npalette = 0: nothing was reduced, info / raw are as decoded;
+ * otherwise raw holds the packed indices (info->bit_depth = 8, 4, 2 or 1 bits each, rows MSB first and padded to bytes) and
+ * palette_rgba (caller-allocated, 1024 bytes) the entries as R, G, B, A. */
 b200_status b200_png_decode_reduced(const uint8_t *in, size_t in_len, b200_png_info *info, uint8_t **raw, uint8_t *palette_rgba, int *npalette);
 /* device K6: filter raw[h][row_bytes] with `strategy` -> filtered[h][row_bytes + 1] (caller-allocated) */
 b200_status b200_png_filter(const uint8_t *raw, int h, int row_bytes, int bpp, int strategy, uint8_t *filtered);

@@ -117,7 +117,9 @@ def test_compress_png_palette_reduction(L):
         if ch == 4:
             img[20:60, 30:90, 3] = 0; img[100:110, :, 3] = 77
         out, ihdr, filt = _check_lossless(L, pil_png(img), expect_mode="P")
-        assert ihdr[2] == 8 and ihdr[3] == 3 and len(filt) == 150 * (220 + 1)
+        n = len(np.unique(img.reshape(-1, ch), axis=0))
+        depth = 1 if n <= 2 else 2 if n <= 4 else 4 if n <= 16 else 8
+        assert ihdr[2] == depth and ihdr[3] == 3 and len(filt) == 150 * ((220 * depth + 7) // 8 + 1)
         assert len(out) < 150 * 220 // 8
 
 

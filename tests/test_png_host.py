@@ -189,6 +189,15 @@ def test_idat_helper_on_pillow_file():
     assert ihdr[:2] == (8, 8) and order[0] == b"IHDR" and order[-1] == b"IEND" and len(zlib.decompress(idat)) == 8 * 25
 
 
+def _unpack(raw, depth, width):
+    """packed PNG index rows (MSB first) -> [h, width] indices"""
+    if depth == 8:
+        return raw[:, :width]
+    per = 8 // depth
+    shifts = (8 - depth - depth * np.arange(per)).astype(np.uint8)
+    return ((raw[:, :, None] >> shifts) & ((1 << depth) - 1)).reshape(raw.shape[0], -1)[:, :width]
+
+
 def test_palette_reduction_is_lossless_and_declines_when_it_should(L):
     """oxipng reduction::palette on the host: <= 256 distinct RGB / RGBA pixels -> 8-bit indices + PLTE (+ tRNS, non-opaque
     entries first); photographs, grey images, inputs with tRNS / 16-bit / palette stay as decoded."""
@@ -200,13 +209,24 @@ def test_palette_reduction_is_lossless_and_declines_when_it_should(L):
         if ch == 4:
             img[10:30, 20:60, 3] = 0; img[40:50, :, 3] = 128
         info, raw, pal = L.png_decode_reduced(pil_png(img))
-        assert pal is not None and info.color_type == 3 and info.bit_depth == 8 and info.bpp == 1 and info.row_bytes == 140
-        assert len(pal) == len(np.unique(img.reshape(-1, ch), axis=0)) <= 256
-        rgba = pal[raw]                                             # [h, w, 4]
+        n = len(np.unique(img.reshape(-1, ch), axis=0))
+        depth = 1 if n <= 2 else 2 if n <= 4 else 4 if n <= 16 else 8
+        assert pal is not None and info.color_type == 3 and info.bit_depth == depth and info.bpp == 1 and info.row_bytes == (140 * depth + 7) // 8
+        assert len(pal) == n <= 256
+        rgba = pal[_unpack(raw, info.bit_depth, 140)]               # [h, w, 4]
         want = img if ch == 4 else np.concatenate([img, np.full((90, 140, 1), 255, np.uint8)], axis=2)
         assert np.array_equal(rgba, want)
         a = pal[:, 3]
         assert np.all(a[:np.count_nonzero(a != 255)] != 255)       # the non-opaque entries lead
+    # 2, 4, 16, 17 colours -> 1, 2, 4, 8 bits per index; odd widths pad the last byte of a row
+    for n, depth in ((2, 1), (3, 2), (4, 2), (5, 4), (16, 4), (17, 8)):
+        cols = rng.integers(0, 256, (n, 3)).astype(np.uint8); cols[:, 0] = np.arange(n)       # distinct, not grey
+        cols[:, 1] = 255 - cols[:, 0]
+        img = cols[rng.integers(0, n, (23, 37))]
+        img.reshape(-1, 3)[:n] = cols
+        info, raw, pal = L.png_decode_reduced(pil_png(img))
+        assert pal is not None and info.bit_depth == depth and info.row_bytes == (37 * depth + 7) // 8 and len(pal) == n
+        assert np.array_equal(pal[_unpack(raw, depth, 37)][:, :, :3], img)
     # exactly 256 colours still fits, 257 does not
     cols = rng.permutation(256 * 256)[:257]
     base = np.stack([cols % 256, cols // 256, (cols * 7) % 256], axis=1).astype(np.uint8)
@@ -231,4 +251,4 @@ def test_palette_reduction_is_lossless_and_declines_when_it_should(L):
     assert L.png_decode_reduced(b.getvalue())[2] is None
     # a single pixel, and a single colour
     info, raw, pal = L.png_decode_reduced(pil_png(np.array([[[9, 200, 30]]], dtype=np.uint8)))
-    assert pal is not None and np.array_equal(pal, [[9, 200, 30, 255]]) and raw.tolist() == [[0]]
+    assert pal is not None and np.array_equal(pal, [[9, 200, 30, 255]]) and raw.tolist() == [[0]] and info.bit_depth == 1
