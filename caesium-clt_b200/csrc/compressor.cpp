@@ -136,31 +136,15 @@ static std::string status_message(b200_status &s)
     return m;
 }
 
+static bool run_codec(const std::vector<uint8_t> &buf, b200_params &params, const CompressionOptions &options, CompressionResult &result, std::vector<uint8_t> &out);
+
 bool perform_image_compression(const std::string &input_file, const CompressionOptions &options, CompressionResult &result, std::vector<uint8_t> &out)
 {   // compressor.rs:266-315
     std::vector<uint8_t> buf;
     if (!read_file_to_vec(input_file, buf)) { result.message = "Error reading input file"; return false; }
     b200_params params; std::string err;
     if (!build_compression_parameters(options, buf, params, err)) { result.message = "Error building compression parameters: " + err; return false; }
-    uint8_t *o = nullptr; size_t ol = 0;
-    b200_status st;
-    if (options.max_size && options.format != OutputFormat::Original) {
-        uint8_t *c = nullptr; size_t cl = 0;
-        st = b200_convert_in_memory(buf.data(), buf.size(), &params, map_supported_formats(options.format), &c, &cl);
-        if (st.code) { b200_free(st.message); return false; }   // `.ok()?` at :294 swallows the error: empty message, status stays Error
-        st = b200_compress_to_size_in_memory(c, cl, &params, *options.max_size, 1, &o, &ol);
-        b200_free(c);
-    } else if (options.max_size) {
-        st = b200_compress_to_size_in_memory(buf.data(), buf.size(), &params, *options.max_size, 1, &o, &ol);
-    } else if (options.format != OutputFormat::Original) {
-        st = b200_convert_in_memory(buf.data(), buf.size(), &params, map_supported_formats(options.format), &o, &ol);
-    } else {
-        st = b200_compress_in_memory(buf.data(), buf.size(), &params, &o, &ol);
-    }
-    if (st.code) { result.message = "Error compressing file: " + status_message(st); return false; }
-    out.assign(o, o + ol);
-    b200_free(o);
-    return true;
+    return run_codec(buf, params, options, result, out);
 }
 
 static std::string absolute_path(const std::string &p) { std::error_code ec; auto a = fs::absolute(p, ec); return ec ? p : a.lexically_normal().string(); }
@@ -226,55 +210,109 @@ static std::string bytesize_str(uint64_t b)
     char s[64]; snprintf(s, sizeof s, "%.1f %s", v, u[i]); return s;
 }
 
-CompressionResult perform_compression(const std::string &input_file, const CompressionOptions &options, bool dry_run)
-{   // compressor.rs:103-184
-    CompressionResult r; r.original_path = input_file;
-    struct stat st;
-    if (stat(input_file.c_str(), &st) != 0) { r.message = "Error reading file metadata"; return r; }
-    uint64_t original = (uint64_t)st.st_size;
-    if (original > MAX_FILE_SIZE) { r.message = "File exceeds 500Mb, skipping."; r.status = CompressionStatus::Skipped; return r; }
-    r.original_size = original;
+// perform_compression (compressor.rs:103-184) in two halves around the codec call, so that start_compression can hand the codec
+// calls of many files to b200_compress_batch at once.  prepare_compression = everything up to the file read and the parameter
+// mapping (the first lines of perform_image_compression, :266-285); finish_compression = the size policies and the write.
+struct Prepared {
+    CompressionResult r;
+    struct stat st {};
+    uint64_t original = 0;
+    std::vector<uint8_t> buf;          // file bytes, read when the file reaches the codec
+    b200_params params {};
+    bool need_codec = false;           // false: r is final (skipped, dry run, or failed before the codec)
+};
+
+static void prepare_compression(const std::string &input_file, const CompressionOptions &options, bool dry_run, Prepared &pr)
+{
+    CompressionResult &r = pr.r; r = CompressionResult(); r.original_path = input_file; pr.need_codec = false;
+    if (stat(input_file.c_str(), &pr.st) != 0) { r.message = "Error reading file metadata"; return; }
+    const uint64_t original = (uint64_t)pr.st.st_size;
+    if (original > MAX_FILE_SIZE) { r.message = "File exceeds 500Mb, skipping."; r.status = CompressionStatus::Skipped; return; }
+    r.original_size = original; pr.original = original;
     std::string outp;
-    if (!setup_output_path(input_file, options, r, dry_run, outp)) { r.message = "Error setting up output path"; return r; }
+    if (!setup_output_path(input_file, options, r, dry_run, outp)) { r.message = "Error setting up output path"; return; }
     r.output_path = outp;
     std::error_code ec;
     if (options.overwrite_policy == OverwritePolicy::Never && fs::exists(outp, ec)) {   // :243-257
-        r.status = CompressionStatus::Skipped; r.compressed_size = original; r.message = "File already exists, skipped due overwrite policy"; return r;
+        r.status = CompressionStatus::Skipped; r.compressed_size = original; r.message = "File already exists, skipped due overwrite policy"; return;
     }
-    if (dry_run) { r.status = CompressionStatus::Success; r.compressed_size = original; return r; }
-    std::vector<uint8_t> img;
-    if (!perform_image_compression(input_file, options, r, img)) return r;
-    uint64_t outsz = img.size();
+    if (dry_run) { r.status = CompressionStatus::Success; r.compressed_size = original; return; }
+    if (!read_file_to_vec(input_file, pr.buf)) { r.message = "Error reading input file"; return; }
+    std::string err;
+    if (!build_compression_parameters(options, pr.buf, pr.params, err)) { r.message = "Error building compression parameters: " + err; return; }
+    pr.need_codec = true;
+}
+
+static void finish_compression(Prepared &pr, const CompressionOptions &options, const uint8_t *img, size_t img_len)
+{
+    CompressionResult &r = pr.r;
+    const uint64_t original = pr.original, outsz = img_len;
+    const std::string &outp = r.output_path;
+    std::error_code ec;
     if (options.min_savings && original != 0) {   // :317-362
         uint64_t actual = original > outsz ? original - outsz : 0;
         const MinSavingsThreshold &t = *options.min_savings;
         char m[160];
         if (t.is_percentage) {
             double sp = (double)actual / (double)original * 100.0;
-            if (sp < t.percent) { snprintf(m, sizeof m, "Insufficient savings: %.2f%% < %.2f%%, skipped", sp, t.percent); r.status = CompressionStatus::Skipped; r.compressed_size = original; r.message = m; return r; }
+            if (sp < t.percent) { snprintf(m, sizeof m, "Insufficient savings: %.2f%% < %.2f%%, skipped", sp, t.percent); r.status = CompressionStatus::Skipped; r.compressed_size = original; r.message = m; return; }
         } else if (actual < t.bytes) {
             r.status = CompressionStatus::Skipped; r.compressed_size = original;
-            r.message = "Insufficient savings: " + bytesize_str(actual) + " < " + bytesize_str(t.bytes) + ", skipped"; return r;
+            r.message = "Insufficient savings: " + bytesize_str(actual) + " < " + bytesize_str(t.bytes) + ", skipped"; return;
         }
     }
     if (options.overwrite_policy == OverwritePolicy::Bigger && fs::exists(outp, ec)) {   // :364-389
         auto existing = fs::file_size(outp, ec);
         if (ec) r.message = "Error reading existing file metadata";
-        else if (existing <= outsz) { r.status = CompressionStatus::Skipped; r.compressed_size = original; r.message = "File already exists, skipped due overwrite policy"; return r; }
+        else if (existing <= outsz) { r.status = CompressionStatus::Skipped; r.compressed_size = original; r.message = "File already exists, skipped due overwrite policy"; return; }
     }
     {   // write_compressed_file, :391-409
         int fd = open(outp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
-        if (fd < 0) { r.message = "Error creating output file"; return r; }
+        if (fd < 0) { r.message = "Error creating output file"; return; }
         size_t off = 0;
-        while (off < img.size()) { ssize_t n = write(fd, img.data() + off, img.size() - off); if (n <= 0) { close(fd); r.message = "Error writing output file"; return r; } off += (size_t)n; }
+        while (off < img_len) { ssize_t n = write(fd, img + off, img_len - off); if (n <= 0) { close(fd); r.message = "Error writing output file"; return; } off += (size_t)n; }
         if (options.keep_dates) {   // preserve_file_times, :563-588
-            struct timespec ts[2] = {st.st_atim, st.st_mtim};
-            if (futimens(fd, ts) != 0) { close(fd); r.message = "Error preserving file times"; return r; }
+            struct timespec ts[2] = {pr.st.st_atim, pr.st.st_mtim};
+            if (futimens(fd, ts) != 0) { close(fd); r.message = "Error preserving file times"; return; }
         }
         close(fd);
     }
     r.status = CompressionStatus::Success; r.compressed_size = outsz;
-    return r;
+}
+
+// the 4-way dispatch of perform_image_compression (:287-306) on bytes that are already in memory
+static bool run_codec(const std::vector<uint8_t> &buf, b200_params &params, const CompressionOptions &options, CompressionResult &result, std::vector<uint8_t> &out)
+{
+    uint8_t *o = nullptr; size_t ol = 0;
+    b200_status st;
+    if (options.max_size && options.format != OutputFormat::Original) {
+        uint8_t *c = nullptr; size_t cl = 0;
+        st = b200_convert_in_memory(buf.data(), buf.size(), &params, map_supported_formats(options.format), &c, &cl);
+        if (st.code) { b200_free(st.message); return false; }   // `.ok()?` at :294 swallows the error: empty message, status stays Error
+        st = b200_compress_to_size_in_memory(c, cl, &params, *options.max_size, 1, &o, &ol);
+        b200_free(c);
+    } else if (options.max_size) {
+        st = b200_compress_to_size_in_memory(buf.data(), buf.size(), &params, *options.max_size, 1, &o, &ol);
+    } else if (options.format != OutputFormat::Original) {
+        st = b200_convert_in_memory(buf.data(), buf.size(), &params, map_supported_formats(options.format), &o, &ol);
+    } else {
+        st = b200_compress_in_memory(buf.data(), buf.size(), &params, &o, &ol);
+    }
+    if (st.code) { result.message = "Error compressing file: " + status_message(st); return false; }
+    out.assign(o, o + ol);
+    b200_free(o);
+    return true;
+}
+
+CompressionResult perform_compression(const std::string &input_file, const CompressionOptions &options, bool dry_run)
+{   // compressor.rs:103-184
+    Prepared pr;
+    prepare_compression(input_file, options, dry_run, pr);
+    if (!pr.need_codec) return pr.r;
+    std::vector<uint8_t> img;
+    if (!run_codec(pr.buf, pr.params, options, pr.r, img)) return pr.r;
+    finish_compression(pr, options, img.data(), img.size());
+    return pr.r;
 }
 
 static int usable_cores()
@@ -285,17 +323,78 @@ static int usable_cores()
     return (int)hc;
 }
 
+static bool same_params(const b200_params &a, const b200_params &b)      // field by field: the struct has padding
+{
+    return a.keep_metadata == b.keep_metadata && a.jpeg_quality == b.jpeg_quality && a.jpeg_chroma_subsampling == b.jpeg_chroma_subsampling &&
+           a.jpeg_progressive == b.jpeg_progressive && a.jpeg_optimize == b.jpeg_optimize && a.jpeg_preserve_icc == b.jpeg_preserve_icc &&
+           a.png_quality == b.png_quality && a.png_optimization_level == b.png_optimization_level && a.png_force_zopfli == b.png_force_zopfli &&
+           a.png_optimize == b.png_optimize && a.gif_quality == b.gif_quality && a.webp_quality == b.webp_quality && a.webp_lossless == b.webp_lossless &&
+           a.width == b.width && a.height == b.height;
+}
+
+// Runs fn(0..n-1) on `threads` threads (the calling one included).
+template <class Fn> static void parallel_for(size_t n, int threads, Fn fn)
+{
+    std::atomic<size_t> next{0};
+    auto worker = [&] { for (;;) { const size_t i = next.fetch_add(1); if (i >= n) break; fn(i); } };
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, threads), n));
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(worker);
+    worker();
+    for (auto &t : th) t.join();
+}
+
 std::vector<CompressionResult> start_compression(const std::vector<std::string> &files, const CompressionOptions &options, bool dry_run, int threads)
 {   // compressor.rs:74-101: par_iter().map(perform_compression).collect() -- results in input order
     std::vector<CompressionResult> results(files.size());
     int n = threads <= 0 ? usable_cores() : std::min(threads, usable_cores());   // main.rs:287-292 get_parallelism_count
-    n = std::max(1, std::min<int>(n, (int)files.size()));
-    std::atomic<size_t> next{0};
-    auto worker = [&] { for (;;) { size_t i = next.fetch_add(1); if (i >= files.size()) break; results[i] = perform_compression(files[i], options, dry_run); } };
-    std::vector<std::thread> th;
-    for (int t = 1; t < n; t++) th.emplace_back(worker);
-    worker();
-    for (auto &t : th) t.join();
+    n = std::max(1, std::min<int>(n, (int)std::max<size_t>(1, files.size())));
+    // --max-size and --format go through calls that have no batch form: plain per-file map, as the reference does it
+    if (dry_run || options.max_size || options.format != OutputFormat::Original) {
+        parallel_for(files.size(), n, [&](size_t i) { results[i] = perform_compression(files[i], options, dry_run); });
+        return results;
+    }
+    // The plain compress call (:305) of a whole chunk of files goes to b200_compress_batch -- the batch form of this very map,
+    // which packs same-shaped JPEGs into megabatches on the GPU.  Per file the policy code before and after the codec is the
+    // same as in perform_compression; chunks bound the bytes held in memory (inputs + outputs of at most 256 files / 1 GiB).
+    constexpr size_t CHUNK_FILES = 256; constexpr uint64_t CHUNK_BYTES = 1ull << 30;
+    size_t begin = 0;
+    while (begin < files.size()) {
+        size_t end = begin; uint64_t bytes = 0;
+        while (end < files.size() && end - begin < CHUNK_FILES) {
+            struct stat st; const uint64_t sz = stat(files[end].c_str(), &st) == 0 ? (uint64_t)st.st_size : 0;
+            if (end > begin && bytes + sz > CHUNK_BYTES) break;
+            bytes += sz; end++;
+        }
+        const size_t m = end - begin;
+        std::vector<Prepared> pr(m);
+        parallel_for(m, n, [&](size_t k) { prepare_compression(files[begin + k], options, false, pr[k]); });
+        // files whose parameter blocks are identical share one batch call (resize requests can differ per file)
+        std::vector<size_t> todo;
+        for (size_t k = 0; k < m; k++) if (pr[k].need_codec) todo.push_back(k);
+        std::vector<uint8_t *> outs(m, nullptr); std::vector<size_t> out_len(m, 0); std::vector<char> coded(m, 0);
+        std::vector<char> taken(m, 0);
+        for (size_t a = 0; a < todo.size(); a++) {
+            if (taken[todo[a]]) continue;
+            std::vector<size_t> grp;
+            for (size_t b = a; b < todo.size(); b++) if (!taken[todo[b]] && same_params(pr[todo[a]].params, pr[todo[b]].params)) { grp.push_back(todo[b]); taken[todo[b]] = 1; }
+            const int g = (int)grp.size();
+            std::vector<const uint8_t *> ins((size_t)g); std::vector<size_t> lens((size_t)g); std::vector<uint8_t *> go((size_t)g, nullptr); std::vector<size_t> gl((size_t)g, 0);
+            std::vector<b200_status> sts((size_t)g);
+            for (int j = 0; j < g; j++) { ins[(size_t)j] = pr[grp[(size_t)j]].buf.data(); lens[(size_t)j] = pr[grp[(size_t)j]].buf.size(); sts[(size_t)j].code = 0; sts[(size_t)j].message = nullptr; }
+            b200_compress_batch(ins.data(), lens.data(), g, &pr[grp[0]].params, n, go.data(), gl.data(), sts.data());
+            for (int j = 0; j < g; j++) {
+                const size_t k = grp[(size_t)j];
+                if (sts[(size_t)j].code) { pr[k].r.message = "Error compressing file: " + status_message(sts[(size_t)j]); if (go[(size_t)j]) b200_free(go[(size_t)j]); }
+                else { outs[k] = go[(size_t)j]; out_len[k] = gl[(size_t)j]; coded[k] = 1; }
+            }
+        }
+        parallel_for(m, n, [&](size_t k) {
+            if (coded[k]) { std::vector<uint8_t>().swap(pr[k].buf); finish_compression(pr[k], options, outs[k], out_len[k]); b200_free(outs[k]); }
+            results[begin + k] = std::move(pr[k].r);
+        });
+        begin = end;
+    }
     return results;
 }
 
