@@ -83,3 +83,26 @@ def test_cli_lossy_flows(L, O, golden, tmp_path):
     # baseline + 4:4:4 flags reach the codec
     rc, so, _ = _cli("-q", "70", "--jpeg-baseline", "--jpeg-chroma-subsampling", "4:4:4", "-o", str(tmp_path / "bl"), "--json", str(src / "a.jpg"))
     assert (tmp_path / "bl" / "a.jpg").read_bytes() == O.jpeg_lossy(golden("in_420_base_355x237.jpg"), O.params(70, 444, False))
+
+
+def test_cli_batches_same_shaped_files(L, O, tmp_path):
+    """start_compression hands the codec calls to b200_compress_batch: a folder of same-shaped baseline JPEGs goes through the
+    megabatch path (device Huffman decode -> transform -> device Huffman encode, several images per launch), one odd file and a
+    PNG ride along; every output must still be the oracle's file, results in input order."""
+    import io
+    from tools.synth import synth_rgb
+    src = tmp_path / "in"; src.mkdir()
+    datas = {}
+    for i in range(9):
+        b = io.BytesIO(); Image.fromarray(synth_rgb(322, 199, 300 + i), "RGB").save(b, "JPEG", quality=72 + 2 * i, subsampling="4:2:0")
+        datas[f"s{i}.jpg"] = b.getvalue()
+    b = io.BytesIO(); Image.fromarray(synth_rgb(200, 120, 7), "RGB").save(b, "JPEG", quality=85, subsampling="4:4:4")
+    datas["odd.jpg"] = b.getvalue()
+    for name, d in datas.items():
+        (src / name).write_bytes(d)
+    out = tmp_path / "out"
+    rc, so, _ = _cli("-q", "80", "-o", str(out), "--json", "--jpeg-chroma-subsampling", "4:2:0", str(src))
+    d = json.loads(so)
+    assert rc == 0 and d["summary"]["success"] == len(datas), d
+    for name, data in datas.items():
+        assert (out / name).read_bytes() == O.jpeg_lossy(data, O.params(80, 420, True)), name
