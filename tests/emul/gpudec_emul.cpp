@@ -120,3 +120,30 @@ extern "C" long long emul_gpu_dec_table_check(const uint8_t *jpeg, size_t len, i
     }
     return bad;
 }
+
+// build_dec_tables on caller-supplied DHT payloads: `ntab` AC tables (ids 0..ntab-1, all with the same BITS / HUFFVAL) used by an
+// MCU of `ntab` blocks, one shared DC table.  Returns 1 ok / 0 refused; *pool_used = second-level entries in use.  When the tables
+// are accepted every 16-bit pattern is checked against the jdhuff.c search (*bad = disagreements).
+extern "C" int emul_build_tables_raw(const uint8_t *ac_bits, const uint8_t *ac_vals, const uint8_t *dc_bits, const uint8_t *dc_vals, int ntab, int *pool_used, long long *bad)
+{
+    gd::Geometry G{};
+    G.blocks_per_mcu = ntab;
+    for (int q = 0; q < ntab; q++) { G.dc_tbl[q] = 0; G.ac_tbl[q] = q; }
+    const uint8_t *db[8] = {dc_bits, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, *dv[8] = {dc_vals, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int q = 0; q < ntab && q < 4; q++) { db[4 + q] = ac_bits; dv[4 + q] = ac_vals; }
+    std::vector<gd::DecTables> T(1);
+    const bool ok = gd::build_dec_tables(db, dv, G, T[0]);
+    *pool_used = T[0].next; *bad = 0;
+    if (!ok) {
+        for (int i = 0; i < gd::MAX_TABLES * gd::LOOK_N; i++) if (T[0].look[i] != (16 << 8)) (*bad)++;      // refused: all-invalid tables
+        return 0;
+    }
+    gd::DecTable ref; gd::build_dec_table(ac_bits, ac_vals, ref);
+    for (int q = 0; q < ntab; q++) for (uint32_t pat = 0; pat < 65536; pat++) {
+        const uint32_t bits = (pat << 16) | 0x5A5Au;
+        int l; const int sym = gd::decode_symbol(ref, bits, &l);
+        const uint32_t e = gd::lookup_symbol(T[0], T[0].sel[2 * q + 1], bits);
+        if ((int)(e >> 8) != l || (int)(e & 0xFF) != sym) (*bad)++;
+    }
+    return 1;
+}

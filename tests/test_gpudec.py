@@ -87,6 +87,41 @@ def test_kernel_form_tables_equal_the_jdhuff_search(emul, golden):
         assert 0 <= used.value <= 1536
 
 
+def test_adversarial_tables_fit_or_are_refused_cleanly(emul):
+    """DHTs built to spread long codes over many 9-bit prefixes: the second-level pool either holds them (and the lookup equals the
+    jdhuff.c search everywhere) or the table set is refused with an all-invalid, in-bounds result -- the image then goes to the
+    host decoder, like a stream that does not converge."""
+    dc_bits = np.zeros(17, np.uint8); dc_bits[2] = 1; dc_bits[3] = 5; dc_bits[4] = 1; dc_bits[5] = 1; dc_bits[6] = 1; dc_bits[7] = 1; dc_bits[8] = 1; dc_bits[9] = 1
+    dc_vals = np.zeros(256, np.uint8); dc_vals[:12] = np.arange(12)
+    outcomes = set()
+    for counts in ({1: 1, 10: 24, 11: 48, 12: 60, 13: 40, 14: 30, 15: 20, 16: 33},       # many prefixes with 10..16-bit codes
+                   {2: 1, 3: 1, 9: 2, 16: 200},                                            # a block of 16-bit codes
+                   {1: 1, 2: 1, 12: 100, 16: 150},
+                   {8: 255}):                                                              # no long codes at all
+        bits = np.zeros(17, np.uint8)
+        for l, c in counts.items():
+            bits[l] = c
+        vals = np.zeros(256, np.uint8); n = int(bits.sum()); vals[:n] = np.arange(n)
+        kraft = sum(int(bits[l]) * 2.0 ** -l for l in range(1, 17))
+        assert kraft <= 1.0
+        for ntab in (1, 4):
+            used, bad = C.c_int(-1), C.c_longlong(-1)
+            ok = emul.emul_build_tables_raw(bits.ctypes.data_as(C.c_void_p), vals.ctypes.data_as(C.c_void_p), dc_bits.ctypes.data_as(C.c_void_p),
+                                            dc_vals.ctypes.data_as(C.c_void_p), ntab, C.byref(used), C.byref(bad))
+            assert bad.value == 0 and 0 <= used.value <= 1536, (counts, ntab, ok, used.value, bad.value)
+            outcomes.add(ok)
+    assert outcomes == {1}             # up to four such AC tables still fit (<= 368 entries each)
+    # a fifth adversarial table (the DC slot) overflows the pool: refused, nothing out of bounds, tables left all-invalid
+    bits = np.zeros(17, np.uint8)
+    for l, c in {1: 1, 10: 24, 11: 48, 12: 60, 13: 40, 14: 30, 15: 20, 16: 33}.items():
+        bits[l] = c
+    vals = np.arange(256).astype(np.uint8)
+    used, bad = C.c_int(-1), C.c_longlong(-1)
+    ok = emul.emul_build_tables_raw(bits.ctypes.data_as(C.c_void_p), vals.ctypes.data_as(C.c_void_p), bits.ctypes.data_as(C.c_void_p), vals.ctypes.data_as(C.c_void_p),
+                                    4, C.byref(used), C.byref(bad))
+    assert ok == 0 and bad.value == 0 and used.value == 0
+
+
 def test_flat_image_reports_non_convergence_or_matches(L, emul):
     """A constant image is a periodic bit stream: a wrong phase can persist, so the round budget may run out.  Whatever
     the outcome, a 0 return code must mean identical coefficients."""
