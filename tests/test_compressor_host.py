@@ -207,6 +207,27 @@ def test_cli_min_savings_and_same_folder(L, golden, tmp_path):
     assert d["summary"]["success"] == 3 and (src / "a_c.jpg").exists() and (src / "level_1" / "b_c.JPG").exists()
 
 
+def test_cli_many_files_cross_the_batch_chunks_in_order(L, golden, tmp_path):
+    """start_compression hands the codec calls to b200_compress_batch in chunks of 256 files: 300 files (two chunks, several
+    sizes, one unreadable entry in the middle) must come back complete and in input order, each output equal to the single call."""
+    src = tmp_path / "in"; src.mkdir()
+    names = ["in_420_base_355x237.jpg", "in_444_base_355x237.jpg", "in_420_prog_355x237.jpg", "in_gray_base_355x237.jpg"]
+    for i in range(300):
+        (src / f"f{i:03d}.jpg").write_bytes(golden(names[i % 4]))
+    os.chmod(src / "f130.jpg", 0)                                   # read fails (unless running as root)
+    out = tmp_path / "out"
+    rc, so, _ = _cli("--lossless", "-o", str(out), "--json", str(src))
+    d = json.loads(so)
+    assert d["summary"]["total_files"] == 300
+    assert [os.path.basename(f["original_path"]) for f in d["files"]] == [f"f{i:03d}.jpg" for i in range(300)]
+    p = L.default_params(); p.jpeg_optimize = 1
+    want = {n: L.compress_in_memory(golden(n), p) for n in names}
+    bad = [f for f in d["files"] if f["status"] != "success"]
+    assert len(bad) <= 1 and all(os.path.basename(f["original_path"]) == "f130.jpg" and f["message"] == "Error reading input file" for f in bad)
+    for i in (0, 1, 2, 3, 255, 256, 257, 299):
+        assert (out / f"f{i:03d}.jpg").read_bytes() == want[names[i % 4]]
+
+
 def test_cli_flag_groups(L):
     """options.rs:141,181: exactly one compression mode and one destination."""
     assert _cli("-o", "/tmp/x", "f.jpg")[0] == 2
