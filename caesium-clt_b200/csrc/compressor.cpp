@@ -8,6 +8,8 @@
 #include <cstring>
 #include <filesystem>
 #include <fstream>
+#include <future>
+#include <memory>
 #include <thread>
 #include <sys/stat.h>
 #include <fcntl.h>
@@ -357,18 +359,29 @@ std::vector<CompressionResult> start_compression(const std::vector<std::string> 
     // The plain compress call (:305) of a whole chunk of files goes to b200_compress_batch -- the batch form of this very map,
     // which packs same-shaped JPEGs into megabatches on the GPU.  Per file the policy code before and after the codec is the
     // same as in perform_compression; chunks bound the bytes held in memory (inputs + outputs of at most 256 files / 1 GiB).
-    constexpr size_t CHUNK_FILES = 256; constexpr uint64_t CHUNK_BYTES = 1ull << 30;
-    size_t begin = 0;
-    while (begin < files.size()) {
+    constexpr size_t CHUNK_FILES = 256; constexpr uint64_t CHUNK_BYTES = 512ull << 20;
+    std::vector<std::pair<size_t, size_t>> chunks;
+    for (size_t begin = 0; begin < files.size();) {
         size_t end = begin; uint64_t bytes = 0;
         while (end < files.size() && end - begin < CHUNK_FILES) {
             struct stat st; const uint64_t sz = stat(files[end].c_str(), &st) == 0 ? (uint64_t)st.st_size : 0;
             if (end > begin && bytes + sz > CHUNK_BYTES) break;
             bytes += sz; end++;
         }
-        const size_t m = end - begin;
-        std::vector<Prepared> pr(m);
-        parallel_for(m, n, [&](size_t k) { prepare_compression(files[begin + k], options, false, pr[k]); });
+        chunks.emplace_back(begin, end); begin = end;
+    }
+    auto prepare_chunk = [&](size_t c) {
+        auto pr = std::make_unique<std::vector<Prepared>>(chunks[c].second - chunks[c].first);
+        parallel_for(pr->size(), n, [&](size_t k) { prepare_compression(files[chunks[c].first + k], options, false, (*pr)[k]); });
+        return pr;
+    };
+    // read-ahead: while chunk c is in the codec and being written out, chunk c + 1 is stat'ed, read and parameterised
+    std::unique_ptr<std::vector<Prepared>> cur = chunks.empty() ? nullptr : prepare_chunk(0);
+    for (size_t c = 0; c < chunks.size(); c++) {
+        std::future<std::unique_ptr<std::vector<Prepared>>> ahead;
+        if (c + 1 < chunks.size()) ahead = std::async(std::launch::async, prepare_chunk, c + 1);
+        std::vector<Prepared> &pr = *cur;
+        const size_t begin = chunks[c].first, m = pr.size();
         // files whose parameter blocks are identical share one batch call (resize requests can differ per file)
         std::vector<size_t> todo;
         for (size_t k = 0; k < m; k++) if (pr[k].need_codec) todo.push_back(k);
@@ -393,7 +406,7 @@ std::vector<CompressionResult> start_compression(const std::vector<std::string> 
             if (coded[k]) { std::vector<uint8_t>().swap(pr[k].buf); finish_compression(pr[k], options, outs[k], out_len[k]); b200_free(outs[k]); }
             results[begin + k] = std::move(pr[k].r);
         });
-        begin = end;
+        if (ahead.valid()) cur = ahead.get();
     }
     return results;
 }
