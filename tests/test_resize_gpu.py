@@ -87,8 +87,8 @@ def test_cli_lossy_flows(L, O, golden, tmp_path):
 
 def test_cli_batches_same_shaped_files(L, O, tmp_path):
     """start_compression hands the codec calls to b200_compress_batch: a folder of same-shaped baseline JPEGs goes through the
-    megabatch path (device Huffman decode -> transform -> device Huffman encode, several images per launch), one odd file and a
-    PNG ride along; every output must still be the oracle's file, results in input order."""
+    megabatch path (device Huffman decode -> transform -> device Huffman encode, several images per launch), one file of another
+    shape and sampling rides along; every output must still be the oracle's file."""
     import io
     from tools.synth import synth_rgb
     src = tmp_path / "in"; src.mkdir()
