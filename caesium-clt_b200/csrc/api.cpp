@@ -4,6 +4,7 @@
 #include "../../include/b200_caesium.h"
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -576,10 +577,98 @@ uint32_t b200_sniff_format(const uint8_t *d, size_t n)
     return B200_FMT_UNKNOWN;
 }
 
+// ---- call coalescing (opt-in: B200_COALESCE=1) ----------------------------------------------------------------------------------
+// The reference calls the codec one image at a time from every rayon worker (compressor.rs:81-83, :305); the GPU wants several
+// same-shaped JPEGs per launch sequence.  With coalescing on, concurrent b200_compress_in_memory calls on JPEG inputs with equal
+// parameters meet in a queue: the first caller to find no collector waits a few hundred microseconds for company (or until
+// B200_COALESCE_TARGET calls have gathered), takes every matching call out of the queue and runs them as ONE b200_compress_batch
+// on its own thread; the others sleep until their result is in.  Several such batches can be in flight.  Per call the semantics
+// (result bytes, status, ownership) are those of the direct path.  Off by default until its effect is measured on a GPU box.
+namespace {
+struct CoReq { const uint8_t *in; size_t len; uint8_t *out = nullptr; size_t out_len = 0; b200_status st{0, nullptr}; bool done = false; b200_params params; };
+struct Coalescer {
+    std::mutex mu; std::condition_variable cv;
+    std::vector<CoReq *> pending; bool collecting = false;
+};
+Coalescer g_co;
+std::atomic<long> g_co_calls{0}, g_co_batches{0};
+struct CoReport { ~CoReport() { if (getenv("B200_TRACE") && g_co_batches.load()) fprintf(stderr, "[b200 trace] coalescing: %ld calls in %ld batches\n", g_co_calls.load(), g_co_batches.load()); } } g_co_report;
+int coalesce_mode()       // 0 off, 1 on
+{
+    static const int m = [] { const char *e = getenv("B200_COALESCE"); return e && atoi(e) > 0 ? 1 : 0; }();
+    return m;
+}
+bool same_params_abi(const b200_params &a, const b200_params &b)
+{
+    return a.keep_metadata == b.keep_metadata && a.jpeg_quality == b.jpeg_quality && a.jpeg_chroma_subsampling == b.jpeg_chroma_subsampling &&
+           a.jpeg_progressive == b.jpeg_progressive && a.jpeg_optimize == b.jpeg_optimize && a.jpeg_preserve_icc == b.jpeg_preserve_icc &&
+           a.png_quality == b.png_quality && a.png_optimization_level == b.png_optimization_level && a.png_force_zopfli == b.png_force_zopfli &&
+           a.png_optimize == b.png_optimize && a.gif_quality == b.gif_quality && a.webp_quality == b.webp_quality && a.webp_lossless == b.webp_lossless &&
+           a.width == b.width && a.height == b.height;
+}
+b200_status coalesced_compress(const uint8_t *in, size_t in_len, const b200_params *params, uint8_t **out, size_t *out_len)
+{
+    static const int target = [] { const char *e = getenv("B200_COALESCE_TARGET"); const int v = e ? atoi(e) : 0; return v >= 2 && v <= 1024 ? v : 16; }();
+    static const int window_us = [] { const char *e = getenv("B200_COALESCE_US"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 100000 ? v : 400; }();
+    CoReq me; me.in = in; me.len = in_len; me.params = *params;
+    std::unique_lock<std::mutex> lk(g_co.mu);
+    g_co.pending.push_back(&me);
+    g_co.cv.notify_all();                                     // a collector may be waiting for company
+    while (!me.done) {
+        if (g_co.collecting) { g_co.cv.wait(lk); continue; }
+        bool queued = false; for (CoReq *r : g_co.pending) if (r == &me) { queued = true; break; }
+        if (!queued) { g_co.cv.wait(lk); continue; }         // my call is inside somebody's batch
+        // become the collector for calls with my parameters
+        g_co.collecting = true;
+        const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(window_us);
+        for (;;) {
+            int have = 0; for (CoReq *r : g_co.pending) if (same_params_abi(r->params, me.params)) have++;
+            if (have >= target || g_co.cv.wait_until(lk, deadline) == std::cv_status::timeout) break;
+        }
+        std::vector<CoReq *> batch, left;
+        for (CoReq *r : g_co.pending) (same_params_abi(r->params, me.params) && (int)batch.size() < 4 * target ? batch : left).push_back(r);
+        g_co.pending.swap(left);
+        g_co.collecting = false;
+        g_co.cv.notify_all();                                 // leftovers / new arrivals elect their own collector
+        lk.unlock();
+        const int n = (int)batch.size();
+        g_co_calls += n; g_co_batches++;
+        bool ran = false;
+        try {
+            std::vector<const uint8_t *> ins((size_t)n); std::vector<size_t> lens((size_t)n); std::vector<uint8_t *> outs((size_t)n, nullptr); std::vector<size_t> ol((size_t)n, 0);
+            std::vector<b200_status> sts((size_t)n, b200_status{0, nullptr});
+            for (int i = 0; i < n; i++) { ins[(size_t)i] = batch[(size_t)i]->in; lens[(size_t)i] = batch[(size_t)i]->len; }
+            const int rc = b200_compress_batch(ins.data(), lens.data(), n, &me.params, std::min(n, 16), outs.data(), ol.data(), sts.data());
+            lk.lock();
+            for (int i = 0; i < n; i++) {
+                CoReq *r = batch[(size_t)i];
+                if (rc < 0) r->st = make_status(B200_ERR_INVALID_ARGUMENT, "batch call failed");
+                else { r->st = sts[(size_t)i]; r->out = outs[(size_t)i]; r->out_len = ol[(size_t)i]; }
+                r->done = true;
+            }
+            ran = true;
+        } catch (...) {}
+        if (!ran) {                                           // nobody may be left waiting on a batch that died (allocation failure)
+            if (!lk.owns_lock()) lk.lock();
+            for (CoReq *r : batch) if (!r->done) { r->st = make_status(B200_ERR_OUT_OF_MEMORY, "out of memory in the coalesced batch"); r->done = true; }
+        }
+        g_co.cv.notify_all();
+    }
+    lk.unlock();
+    if (me.st.code) { if (me.out) b200_free(me.out); return me.st; }
+    *out = me.out; *out_len = me.out_len;
+    return me.st;
+}
+} // namespace
+
 b200_status b200_compress_in_memory(const uint8_t *in, size_t in_len, const b200_params *params, uint8_t **out, size_t *out_len)
 {
     if (!in || !params || !out || !out_len) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr; *out_len = 0;
+    if (coalesce_mode() && b200_sniff_format(in, in_len) == B200_FMT_JPEG) {
+        try { return coalesced_compress(in, in_len, params, out, out_len); }
+        catch (const std::exception &e) { return make_status(B200_ERR_OUT_OF_MEMORY, e.what()); } catch (...) { return make_status(B200_ERR_INVALID_ARGUMENT, "unexpected failure"); }
+    }
     try {
         std::vector<uint8_t> v;
         b200_status s = compress_dispatch(in, in_len, params, -1, v);
