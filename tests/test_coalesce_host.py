@@ -7,6 +7,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 SCRIPT = r"""
@@ -17,8 +19,11 @@ L = bench.load_pkg()
 G = os.path.join(%(root)r, "tests", "golden")
 names = ["in_420_base_355x237.jpg", "in_444_base_355x237.jpg", "in_420_prog_355x237.jpg", "in_gray_base_355x237.jpg", "in_420_tiny_17x9.jpg"]
 datas = [open(os.path.join(G, n), "rb").read() for n in names]
+LOSSY = %(lossy)d
 def params(prog, meta):
-    p = L.default_params(); p.jpeg_optimize = 1; p.jpeg_progressive = prog; p.keep_metadata = meta
+    p = L.default_params(); p.jpeg_progressive = prog; p.keep_metadata = meta
+    if LOSSY: p.jpeg_quality = 80; p.jpeg_chroma_subsampling = 420
+    else: p.jpeg_optimize = 1
     return p
 variants = [(1, 0), (0, 0), (1, 1)]
 jobs = []
@@ -47,12 +52,12 @@ print(json.dumps(out))
 """
 
 
-def _run(coalesce):
+def _run(coalesce, lossy=False):
     env = dict(os.environ)
     env.pop("B200_COALESCE", None)
     if coalesce:
         env.update(B200_COALESCE="1", B200_COALESCE_TARGET="8", B200_COALESCE_US="2000")
-    r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}], capture_output=True, text=True, env=env, timeout=600)
+    r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT, "lossy": 1 if lossy else 0}], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     return json.loads(r.stdout.strip().splitlines()[-1])
 
@@ -63,3 +68,12 @@ def test_coalesced_calls_return_what_direct_calls_return():
     assert len(direct) == len(merged) == 240
     assert merged == direct
     assert sum(1 for r in direct if r[0] == "ok") > 150 and sum(1 for r in direct if r[0] == "err") > 10
+
+
+@pytest.mark.gpu
+def test_coalesced_lossy_calls_on_the_gpu_return_what_direct_calls_return():
+    """the same on a B200 with the lossy path: the collector's batch takes the megabatch route (same-shaped files decoded,
+    transformed and encoded together), the direct calls the one-image route -- the bytes must not differ"""
+    direct = _run(False, lossy=True)
+    merged = _run(True, lossy=True)
+    assert merged == direct and sum(1 for r in direct if r[0] == "ok") > 150
