@@ -2,12 +2,15 @@
 Pillow/libpng + zlib, and the product's HOST half (container parse, inflate, unfilter, DEFLATE writer) through the C-ABI.
 No device work is called here."""
 import io
+import os
 import zlib
 
 import numpy as np
 import pytest
 
 from pngutil import frame_png, idat_stream, pil_pixels, pil_png, synth
+
+P0_FILTER_HISTOGRAM = [3, 28, 211, 8, 150]      # per-row filter types 0..4 of /root/reference/samples/p0.png (known answer)
 
 CT = {1: 0, 2: 4, 3: 2, 4: 6}     # channels -> PNG colour type
 
@@ -252,3 +255,24 @@ def test_palette_reduction_is_lossless_and_declines_when_it_should(L):
     # a single pixel, and a single colour
     info, raw, pal = L.png_decode_reduced(pil_png(np.array([[[9, 200, 30]]], dtype=np.uint8)))
     assert pal is not None and np.array_equal(pal, [[9, 200, 30, 255]]) and raw.tolist() == [[0]] and info.bit_depth == 1
+
+
+def test_reference_fixture_p0_png_known_answers(L, O):
+    """SURVEY.md §8c KAT-4 on the reference's own fixture (read where it lies; skipped on a box without /root/reference): one IDAT
+    that inflates to 480,400 bytes (400 rows of 400 RGB pixels + filter bytes); the product's host decoder and the oracle's
+    unfilter must both reproduce libpng's pixels; the file's row-filter histogram is the known answer recorded here."""
+    path = "/root/reference/samples/p0.png"
+    if not os.path.exists(path):
+        pytest.skip("reference fixture not present")
+    data = open(path, "rb").read()
+    ihdr, idat, order = idat_stream(data)
+    assert ihdr[:5] == (400, 400, 8, 2, 0) and order.count(b"IDAT") == 1
+    filt = np.frombuffer(zlib.decompress(idat), dtype=np.uint8)
+    assert filt.size == 480400
+    rows = filt.reshape(400, 1201)
+    assert np.bincount(rows[:, 0], minlength=5).tolist() == P0_FILTER_HISTOGRAM
+    want = np.asarray(pil_pixels(data).convert("RGB"))
+    info, raw = L.png_decode(data)
+    assert (info.width, info.height, info.bit_depth, info.color_type, info.bpp, info.row_bytes) == (400, 400, 8, 2, 3, 1200)
+    assert np.array_equal(raw.reshape(400, 400, 3), want)
+    assert np.array_equal(O.png_unfilter(rows, 3).reshape(400, 400, 3), want)
