@@ -40,6 +40,9 @@ b200_status make_status(int code, const std::string &msg)
     return s;
 }
 
+// a header the reader refused: RGB-coded sources are "recognised but not on this path" (code 3), everything else is corrupt input
+b200_status header_status(const std::string &err) { return make_status(err.compare(0, 9, "RGB-coded") == 0 ? B200_ERR_UNSUPPORTED : B200_ERR_CORRUPT_INPUT, err); }
+
 std::once_flag g_once;
 std::string g_init_err;
 int g_forced_device = -1, g_forced_ngpus = 0;
@@ -126,7 +129,7 @@ b200_status jpeg_compress(const uint8_t *in, size_t in_len, const b200_params *p
 {
     std::string err;
     JpegReader rd(in, in_len);
-    if (!rd.read_header(err)) return make_status(B200_ERR_CORRUPT_INPUT, err);
+    if (!rd.read_header(err)) return header_status(err);
     const JpegGeom &gin = rd.geom();
     JpegWriteOptions wo; wo.progressive = p->jpeg_progressive != 0; wo.keep_metadata = p->keep_metadata != 0; wo.preserve_icc = p->jpeg_preserve_icc != 0;
     if (p->jpeg_optimize) {
@@ -342,7 +345,7 @@ b200_status jpeg_to_webp(const uint8_t *in, size_t in_len, const b200_params *p,
 {
     std::string err;
     JpegReader rd(in, in_len);
-    if (!rd.read_header(err)) return make_status(B200_ERR_CORRUPT_INPUT, err);
+    if (!rd.read_header(err)) return header_status(err);
     const JpegGeom &gin = rd.geom();
     if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
     uint32_t nw = (uint32_t)gin.width, nh = (uint32_t)gin.height;
@@ -381,7 +384,7 @@ b200_status jpeg_to_png(const uint8_t *in, size_t in_len, const b200_params *p, 
     if (!p->png_optimize) return make_status(B200_ERR_UNSUPPORTED, "lossy PNG (imagequant) is outside the GPU path (route to caesium::convert_in_memory)");
     std::string err;
     JpegReader rd(in, in_len);
-    if (!rd.read_header(err)) return make_status(B200_ERR_CORRUPT_INPUT, err);
+    if (!rd.read_header(err)) return header_status(err);
     const JpegGeom &gin = rd.geom();
     if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
     uint32_t nw = (uint32_t)gin.width, nh = (uint32_t)gin.height;
@@ -810,7 +813,7 @@ b200_status b200_jpeg_decode_coefficients(const uint8_t *in, size_t in_len, b200
     *coefs = nullptr;
     std::string err;
     JpegReader rd(in, in_len);
-    if (!rd.read_header(err)) return make_status(B200_ERR_CORRUPT_INPUT, err);
+    if (!rd.read_header(err)) return header_status(err);
     int16_t *c = (int16_t *)malloc((size_t)rd.geom().total_coefs * 2 + 16);
     if (!c) return make_status(B200_ERR_OUT_OF_MEMORY, "out of memory");
     if (!rd.decode(c, err)) { free(c); return make_status(B200_ERR_CORRUPT_INPUT, err); }

@@ -425,8 +425,8 @@ std::vector<std::string> scan_files(const std::vector<std::string> &args, bool r
         fs::path in(a);
         if (fs::is_directory(in, ec)) {
             std::vector<std::string> found;
-            if (recursive) { for (auto it = fs::recursive_directory_iterator(in, fs::directory_options::skip_permission_denied, ec); it != fs::recursive_directory_iterator(); it.increment(ec)) if (it->is_regular_file(ec) && valid(it->path())) found.push_back(it->path().string()); }
-            else { for (auto it = fs::directory_iterator(in, ec); it != fs::directory_iterator(); it.increment(ec)) if (it->is_regular_file(ec) && valid(it->path())) found.push_back(it->path().string()); }
+            if (recursive) { for (auto it = fs::recursive_directory_iterator(in, fs::directory_options::skip_permission_denied, ec); it != fs::recursive_directory_iterator(); it.increment(ec)) if (fs::is_regular_file(it->symlink_status(ec)) && valid(it->path())) found.push_back(it->path().string()); }       // WalkDir follow_links(false)
+            else { for (auto it = fs::directory_iterator(in, ec); it != fs::directory_iterator(); it.increment(ec)) if (fs::is_regular_file(it->symlink_status(ec)) && valid(it->path())) found.push_back(it->path().string()); }
             std::sort(found.begin(), found.end());
             files.insert(files.end(), found.begin(), found.end());
         } else if (fs::is_regular_file(in, ec) && valid(in)) files.push_back(a);

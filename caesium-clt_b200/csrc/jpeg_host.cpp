@@ -154,26 +154,6 @@ inline int decode_sym(BitReader &b, const JpegReader::Huff &h)
 
 static unsigned rd16(const uint8_t *p) { return ((unsigned)p[0] << 8) | p[1]; }
 
-static int parse_exif_orientation(const uint8_t *seg, size_t sl)
-{   // APP1 "Exif\0\0" + TIFF header; IFD0 tag 0x0112 (kamadak-exif get_field(Orientation, PRIMARY), compressor.rs:546-553)
-    if (sl < 14 || memcmp(seg, "Exif\0\0", 6)) return 1;
-    const uint8_t *t = seg + 6; size_t tl = sl - 6;
-    bool le = t[0] == 'I' && t[1] == 'I';
-    if (!le && !(t[0] == 'M' && t[1] == 'M')) return 1;
-    auto u16 = [&](size_t o) -> unsigned { return o + 2 <= tl ? (le ? t[o] | (t[o + 1] << 8) : (t[o] << 8) | t[o + 1]) : 0; };
-    auto u32 = [&](size_t o) -> unsigned { return o + 4 <= tl ? (le ? (unsigned)t[o] | (t[o + 1] << 8) | (t[o + 2] << 16) | ((unsigned)t[o + 3] << 24)
-                                                                  : ((unsigned)t[o] << 24) | (t[o + 1] << 16) | (t[o + 2] << 8) | t[o + 3]) : 0; };
-    size_t ifd = u32(4);
-    if (ifd + 2 > tl) return 1;
-    unsigned n = u16(ifd);
-    for (unsigned i = 0; i < n; i++) {
-        size_t e = ifd + 2 + 12 * (size_t)i;
-        if (e + 12 > tl) break;
-        if (u16(e) == 0x0112) { unsigned v = u16(e + 8); return v >= 1 && v <= 8 ? (int)v : 1; }
-    }
-    return 1;
-}
-
 bool JpegReader::parse_segment(unsigned m, const uint8_t *seg, size_t sl, std::string &err)
 {
     if (m == 0xDB) {
@@ -219,10 +199,9 @@ bool JpegReader::parse_segment(unsigned m, const uint8_t *seg, size_t sl, std::s
         const uint8_t *whole = seg - 4; size_t wl = sl + 4;
         if (m == 0xE0 && sl >= 14 && !memcmp(seg, "JFIF\0", 5) && !m_.jfif) { m_.jfif = true; memcpy(m_.jfif_body, seg + 5, 9); m_.jfif_body[7] = m_.jfif_body[8] = 0; }
         else if (m == 0xE0 && m_.jfif) { /* JFXX / duplicate JFIF: dropped */ }
-        else if (m == 0xEE && sl >= 12 && !memcmp(seg, "Adobe", 5)) { /* colour transform flag only; not carried */ }
+        else if (m == 0xEE && sl >= 12 && !memcmp(seg, "Adobe", 5)) { m_.adobe = true; m_.adobe_transform = seg[11]; }     // not re-emitted: see read_header
         else if (m == 0xE2 && sl >= 12 && !memcmp(seg, "ICC_PROFILE\0", 12)) m_.icc_markers.insert(m_.icc_markers.end(), whole, whole + wl);
         else {
-            if (m == 0xE1) { int o = parse_exif_orientation(seg, sl); if (o != 1) m_.exif_orientation = o; }
             m_.app_markers.insert(m_.app_markers.end(), whole, whole + wl);
         }
     } else if (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
@@ -241,7 +220,17 @@ bool JpegReader::read_header(std::string &err)
         if (m == 0xFF) { pos_++; continue; }
         if (m == 0x00 || m == 0x01 || (m >= 0xD0 && m <= 0xD8)) { pos_ += 2; continue; }
         if (m == 0xD9) break;
-        if (m == 0xDA) { if (!have_sof_) { err = "SOS before SOF"; return false; } return true; }
+        if (m == 0xDA) {
+            if (!have_sof_) { err = "SOS before SOF"; return false; }
+            // Colour space, libjpeg's jdapimin.c default_decompress_parms rule: a 3-component file is YCbCr unless an Adobe
+            // marker says transform 0, or (no JFIF, no Adobe) its component ids spell "RGB".  Every output of this path is
+            // written as JFIF / YCbCr, so RGB-coded sources are handed back (the caller routes them to libcaesium) instead of
+            // being re-tagged with the wrong colour space.
+            if (g_.ncomp == 3 && ((m_.adobe && m_.adobe_transform == 0) || (!m_.adobe && !m_.jfif && g_.cid[0] == 'R' && g_.cid[1] == 'G' && g_.cid[2] == 'B'))) {
+                err = "RGB-coded JPEG (Adobe transform 0) is outside the GPU path (route to caesium::compress_in_memory)"; return false;
+            }
+            return true;
+        }
         size_t L = rd16(d_ + pos_ + 2);
         if (L < 2 || pos_ + 2 + L > n_) { err = "truncated marker segment"; return false; }
         if (!parse_segment(m, d_ + pos_ + 4, L - 2, err)) return false;
@@ -275,8 +264,12 @@ bool JpegReader::decode_scan(const uint8_t *seg, size_t sl, const uint8_t *ecs, 
     const int mcus_x = inter ? g.mcux : g.rbw[ci[0]], mcus_y = inter ? g.mcuy : g.rbh[ci[0]];
     // Baseline interleaved scans overwrite every allocated block, so the blocks are zeroed one at a time as they
     // are decoded (cache-hot); anything else needs the whole buffer cleared once up front.
-    const bool zero_per_block = !prog && inter;
-    if (!zero_per_block && !zeroed_) { memset(coefs, 0, (size_t)g.total_coefs * sizeof(int16_t)); zeroed_ = true; }
+    // Only a scan that carries EVERY component does that: a baseline file may spread its components over several scans
+    // (2 + 1, or one each), and then the whole buffer is cleared once, before the first of them -- later scans must not wipe
+    // what earlier ones decoded, and a component no scan ever codes stays zero instead of holding a previous image's data.
+    const bool zero_per_block = !prog && inter && ns == g.ncomp && !zeroed_;
+    if (!zero_per_block && !zeroed_) memset(coefs, 0, (size_t)g.total_coefs * sizeof(int16_t));
+    zeroed_ = true;
 
     BitReader b; b.p = ecs; b.end = d_ + n_;
     int pred[4] = {0, 0, 0, 0}, eobrun = 0, rst = 0;

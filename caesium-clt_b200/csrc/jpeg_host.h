@@ -33,7 +33,7 @@ struct JpegMeta {
     uint8_t jfif_body[9] = {1, 1, 0, 0, 1, 0, 1, 0, 0};  // version, units, densities, thumbnail dims
     std::vector<uint8_t> app_markers;   // APPn/COM verbatim (FF xx len ...), excluding JFIF APP0, Adobe APP14, ICC APP2
     std::vector<uint8_t> icc_markers;   // APP2 ICC_PROFILE chunks verbatim
-    int exif_orientation = 1;
+    bool adobe = false; int adobe_transform = 1;   // APP14 "Adobe": transform 0 = components are RGB (or CMYK), 1 = YCbCr
 };
 
 // Stateful reader: read_header() walks the markers up to the first SOS (tables + frame), decode() entropy-decodes

@@ -145,8 +145,15 @@ bool zlib_inflate(const uint8_t *in, size_t n, std::vector<uint8_t> &out, size_t
     if (n < 6) { err = "zlib stream too short"; return false; }
     if ((in[0] & 0x0F) != 8 || ((in[0] << 8) | in[1]) % 31 != 0 || (in[1] & 0x20)) { err = "bad zlib header"; return false; }
     InfBits b; b.p = in + 2; b.end = in + n;
-    size_t cap = (size_hint ? size_hint : n * 4) + 4096, pos = 0;     // bytes are written through a raw pointer; the vector is trimmed at the end
+    // Bytes are written through a raw pointer; the vector is trimmed at the end.  A caller that knows the decoded size (PNG:
+    // (row_bytes + 1) * height from IHDR) passes it as size_hint and the stream may not inflate to more than that: an IDAT
+    // that claims a 1x1 image and carries megabytes is refused instead of being expanded (decompression bomb).  DEFLATE
+    // cannot expand by more than 1032:1, which bounds the first allocation when IHDR promises more than the input can hold.
+    const size_t limit = size_hint ? size_hint : (size_t)-1;
+    const size_t most = n > ((size_t)-1 >> 12) ? (size_t)-1 >> 1 : n * 1032 + 64;
+    size_t cap = std::min(size_hint ? size_hint : n * 4, most) + 4096, pos = 0;
     out.resize(cap + 16);
+    constexpr size_t MATCH_ROOM = 258 + 8;          // the longest match plus the 8-byte copy granularity
     static thread_local InfTable lit, dist;
     for (;;) {
         const uint32_t final = b.get(1), type = b.get(2);
@@ -157,6 +164,7 @@ bool zlib_inflate(const uint8_t *in, size_t n, std::vector<uint8_t> &out, size_t
             if (b.end - b.p < 4) { err = "truncated stored block"; return false; }
             const uint32_t len = b.p[0] | (b.p[1] << 8), nlen = b.p[2] | (b.p[3] << 8);
             if ((len ^ 0xFFFF) != nlen || (size_t)(b.end - b.p - 4) < len) { err = "bad stored block"; return false; }
+            if (len > limit - std::min(pos, limit)) { err = "IDAT too long"; return false; }
             if (cap - pos < len + 320) { cap = cap * 2 + len + 4096; out.resize(cap + 16); }
             memcpy(out.data() + pos, b.p + 4, len); pos += len; b.p += 4 + len;
         } else if (type == 1 || type == 2) {
@@ -239,8 +247,12 @@ bool zlib_inflate(const uint8_t *in, size_t n, std::vector<uint8_t> &out, size_t
                         op += len;
                     }
                     b.p = ip; b.acc = acc; b.n = nb; pos = (size_t)(op - o);
+                    if (pos > limit) { err = "IDAT too long"; return false; }
                     if (eob) break;
                 }
+                // the fast loop may stop as close as 55 bytes to the end of the buffer: make room for one more whole match
+                // before the checked path writes anything (heap overflow on an IDAT longer than IHDR implies)
+                if (cap - pos < MATCH_ROOM + 64) { cap = cap * 2 + 4096; out.resize(cap + 16); o = out.data(); }
                 int s = inf_decode(b, lit);
                 if (s < 0) { err = "bad literal/length code"; return false; }
                 if (s < 256) o[pos++] = (uint8_t)s;
@@ -258,6 +270,7 @@ bool zlib_inflate(const uint8_t *in, size_t n, std::vector<uint8_t> &out, size_t
                     else for (size_t k = 0; k < len; k++) dst[k] = src[k];
                     pos += len;
                 }
+                if (pos > limit) { err = "IDAT too long"; return false; }
                 if (b.p >= b.end && b.n <= 0) { err = "truncated deflate stream"; return false; }
             }
         } else { err = "bad block type"; return false; }
@@ -325,6 +338,13 @@ bool png_decode(const uint8_t *d, size_t n, bool keep_all, PngInfo &info, std::v
             if (!info.width || !info.height || data[10] || data[11]) { err = "bad IHDR"; return false; }
             static const int ch[7] = {1, 0, 3, 1, 2, 0, 4};
             if (info.color_type > 6 || !ch[info.color_type]) { err = "bad colour type"; return false; }
+            // legal (colour type, bit depth) pairs of PNG 11.2.2 only: anything else would index samples with bd / 8 == 0,
+            // divide by (1 << 0) - 1 or make zero-sized rows further down
+            const int bd = info.bit_depth;
+            const bool depth_ok = info.color_type == 0 ? (bd == 1 || bd == 2 || bd == 4 || bd == 8 || bd == 16)
+                                : info.color_type == 3 ? (bd == 1 || bd == 2 || bd == 4 || bd == 8) : (bd == 8 || bd == 16);
+            if (!depth_ok) { err = "bad bit depth for the colour type"; return false; }
+            if (info.width > 0x7FFFFFFFu || info.height > 0x7FFFFFFFu) { err = "bad IHDR"; return false; }
             info.channels = ch[info.color_type]; info.bits_per_pixel = info.channels * info.bit_depth;
             info.bpp = std::max(1, info.bits_per_pixel / 8);
             info.row_bytes = ((size_t)info.width * info.bits_per_pixel + 7) / 8;
@@ -346,6 +366,7 @@ bool png_decode(const uint8_t *d, size_t n, bool keep_all, PngInfo &info, std::v
     if (info.interlace) { err = "interlaced PNG is not supported on the GPU path"; return false; }
     std::vector<uint8_t> filt;
     const size_t stride = info.row_bytes + 1;
+    if (stride > ((size_t)1 << 40) / info.height) { err = "PNG dimensions too large"; return false; }      // 1 TiB of samples: no overflow below
     if (!zlib_inflate(idat.data(), idat.size(), filt, stride * info.height, err)) return false;
     if (filt.size() < stride * info.height) { err = "IDAT too short"; return false; }
     const size_t nraw = info.row_bytes * info.height;
