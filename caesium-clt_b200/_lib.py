@@ -68,6 +68,7 @@ _SYMBOLS = [
     "b200_jpeg_batch_time", "b200_jpeg_batch_destroy", "b200_jpeg_encode_coefficients_device",
     "b200_png_decode", "b200_png_decode_reduced", "b200_png_filter", "b200_png_lz77", "b200_png_deflate_tokens", "b200_png_level_strategies",
     "b200_webp_encode_rgb", "b200_webp_write_levels", "b200_webp_qindex",
+    "b200_jpeg_pipe_create", "b200_jpeg_pipe_run", "b200_jpeg_pipe_finish", "b200_jpeg_pipe_fetch", "b200_jpeg_pipe_kernel_times", "b200_jpeg_pipe_destroy",
 ]
 
 
@@ -84,12 +85,14 @@ def lib():
                   "b200_jpeg_encode_coefficients", "b200_jpeg_decode_planes", "b200_jpeg_batch_create",
                   "b200_jpeg_batch_upload", "b200_jpeg_batch_run", "b200_jpeg_batch_download", "b200_jpeg_batch_time",
                   "b200_png_decode", "b200_png_decode_reduced", "b200_png_filter", "b200_png_lz77", "b200_png_deflate_tokens",
-                  "b200_webp_encode_rgb", "b200_webp_write_levels", "b200_jpeg_encode_coefficients_device"):
+                  "b200_webp_encode_rgb", "b200_webp_write_levels", "b200_jpeg_encode_coefficients_device",
+                  "b200_jpeg_pipe_create", "b200_jpeg_pipe_run", "b200_jpeg_pipe_finish", "b200_jpeg_pipe_fetch", "b200_jpeg_pipe_kernel_times"):
             getattr(L, f).restype = Status
         L.b200_version.restype = C.c_char_p
         L.b200_sniff_format.restype = C.c_uint32
         L.b200_free.argtypes = [C.c_void_p]
         L.b200_jpeg_batch_destroy.argtypes = [C.c_void_p]
+        L.b200_jpeg_pipe_destroy.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -364,6 +367,55 @@ class JpegBatch:
     def close(self):
         if self.h:
             lib().b200_jpeg_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class JpegPipe:
+    """Device-resident FULL re-encode path (bench.py's `value`): n same-shaped baseline JPEGs uploaded once; run() enqueues
+    Huffman decode -> transform -> Huffman encode for all of them behind `stream` without a host wait."""
+
+    def __init__(self, datas, params, group=8):
+        self.h = C.c_void_p()
+        self.n = len(datas)
+        self._inputs = BatchInputs(datas)
+        _check(lib().b200_jpeg_pipe_create(self._inputs.ins, self._inputs.lens, self.n, C.byref(params), int(group), C.byref(self.h)))
+
+    def run(self, stream=None, which=0):
+        n = C.c_int(0)
+        _check(lib().b200_jpeg_pipe_run(self.h, C.c_void_p(stream), int(which), C.byref(n)))
+        return n.value
+
+    def finish(self):
+        """-> (entropy-coded bytes per image, images not settled by the device decoder, encoder retries)"""
+        sizes = (C.c_size_t * self.n)()
+        bad, retries = C.c_int(0), C.c_int(0)
+        _check(lib().b200_jpeg_pipe_finish(self.h, sizes, C.byref(bad), C.byref(retries)))
+        return list(sizes), bad.value, retries.value
+
+    def fetch(self, index):
+        outp, outl = C.c_void_p(), C.c_size_t()
+        _check(lib().b200_jpeg_pipe_fetch(self.h, int(index), C.byref(outp), C.byref(outl)))
+        return _take(outp, outl)
+
+    def kernel_times(self, iters=3):
+        """{kernel name: (ms per launch, launches per megabatch)} of ONE megabatch run alone with an event after every launch."""
+        buf = C.create_string_buffer(1 << 14)
+        _check(lib().b200_jpeg_pipe_kernel_times(self.h, int(iters), buf, C.c_size_t(len(buf))))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, cnt = line.split()
+            out[name] = (float(ms), int(cnt))
+        return out
+
+    def close(self):
+        if self.h:
+            lib().b200_jpeg_pipe_destroy(self.h)
             self.h = C.c_void_p()
 
     def __del__(self):

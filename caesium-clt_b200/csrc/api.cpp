@@ -12,6 +12,7 @@
 #include <exception>
 #include <fstream>
 #include <functional>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -25,6 +26,7 @@
 #include "png_device.h"
 #include "vp8_host.h"
 #include "webp_device.h"
+#include "jpeg_pipe.h"
 
 using namespace b200;
 
@@ -278,13 +280,9 @@ void jpeg_compress_group(const uint8_t *const *in, const size_t *in_len, const s
             gins[m] = &rd[k]->geom();
         }
         tm.lap(0);
-        if (!slot_decode_group(s, items, err)) break;
-        tm.lap(1);
-        if (!lossless && !slot_transform_group(s, gins.data(), gout, L, err)) break;
-        tm.lap(3);
         JpegWriteOptions wo; wo.progressive = p->jpeg_progressive != 0; wo.keep_metadata = p->keep_metadata != 0; wo.preserve_icc = p->jpeg_preserve_icc != 0;
         wo.copy_jfif = lossless;
-        if (!slot_encode_group(s, gout, wo.progressive, L, err, lossless)) break;
+        if (!slot_run_group(s, items, gins.data(), gout, L, wo.progressive, lossless, err)) break;
         tm.lap(4);
         const int spi = s->enc->plan.scans_per_image;
         for (int m = 0; m < Kg; m++) {
@@ -947,6 +945,51 @@ b200_status b200_jpeg_batch_time(b200_jpeg_batch *b, int which, int iters, float
     return batch_time(b->b, which, iters, ms_per_run, err) ? ok_status() : make_status(B200_ERR_CUDA, err);
 }
 void b200_jpeg_batch_destroy(b200_jpeg_batch *b) { if (b) { batch_destroy(b->b); delete b; } }
+
+// ---- device-resident full path ------------------------------------------------------------------------------------------
+struct b200_jpeg_pipe { JpegPipe *p; };
+b200_status b200_jpeg_pipe_create(const uint8_t *const *in, const size_t *in_len, int n, const b200_params *params, int group, b200_jpeg_pipe **pipe)
+{
+    if (!in || !in_len || !params || !pipe || n <= 0) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid argument");
+    *pipe = nullptr;
+    std::string err;
+    if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
+    try {
+        JpegPipe *P = pipe_create(in, in_len, n, params, group > 0 ? group : 8, err);
+        if (!P) return make_status(B200_ERR_INVALID_ARGUMENT, err);
+        *pipe = new b200_jpeg_pipe{P};
+    } catch (const std::exception &e) { return make_status(B200_ERR_OUT_OF_MEMORY, e.what()); }
+    return ok_status();
+}
+b200_status b200_jpeg_pipe_run(b200_jpeg_pipe *p, void *cuda_stream, int which, int *launches)
+{
+    std::string err; if (!p) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    return pipe_run(p->p, cuda_stream, which, launches, err) ? ok_status() : make_status(B200_ERR_CUDA, err);
+}
+b200_status b200_jpeg_pipe_finish(b200_jpeg_pipe *p, size_t *out_sizes, int *not_settled, int *enc_retries)
+{
+    std::string err; if (!p) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    return pipe_finish(p->p, out_sizes, not_settled, enc_retries, err) ? ok_status() : make_status(B200_ERR_CUDA, err);
+}
+b200_status b200_jpeg_pipe_fetch(b200_jpeg_pipe *p, int index, uint8_t **out, size_t *out_len)
+{
+    std::string err; if (!p || !out || !out_len) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    std::vector<uint8_t> v;
+    if (!pipe_fetch(p->p, index, v, err)) return make_status(B200_ERR_CUDA, err);
+    return give(v, out, out_len);
+}
+b200_status b200_jpeg_pipe_kernel_times(b200_jpeg_pipe *p, int iters, char *text, size_t cap)
+{
+    std::string err; if (!p || !text || !cap || iters <= 0) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid argument");
+    std::map<std::string, std::pair<double, int>> t;
+    if (!pipe_kernel_times(p->p, iters, t, err)) return make_status(B200_ERR_CUDA, err);
+    std::string s;
+    for (auto &kv : t) { char b[160]; snprintf(b, sizeof b, "%s %.6f %d\n", kv.first.c_str(), kv.second.first, kv.second.second); s += b; }
+    if (s.size() + 1 > cap) return make_status(B200_ERR_INVALID_ARGUMENT, "text buffer too small");
+    memcpy(text, s.c_str(), s.size() + 1);
+    return ok_status();
+}
+void b200_jpeg_pipe_destroy(b200_jpeg_pipe *p) { if (p) { pipe_destroy(p->p); delete p; } }
 
 // ---- PNG stage entry points ----------------------------------------------------------------------------------------
 b200_status b200_png_decode(const uint8_t *in, size_t in_len, b200_png_info *info, uint8_t **raw)

@@ -17,8 +17,11 @@
 #include "png_device.h"
 #include "webp_device.h"
 #include "stream_wait.h"
+#include "launch_timer.h"
 
 namespace b200 {
+
+thread_local LaunchTimer *tl_launch_timer = nullptr;
 
 #define CU(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(e_); return false; } } while (0)
 
@@ -93,9 +96,9 @@ int launch_work(const WorkLists &wl, const CompWork *d, void *stream, int which,
     int rc = 0, n = 0;
     const CompWork *p_fused = d, *p_idct = p_fused + wl.fused.size(), *p_c420 = p_idct + wl.idct.size();
     const CompWork *p_up = p_c420 + wl.c420.size(), *p_down = p_up + wl.up.size(), *p_fdct = p_down + wl.down.size();
-    if ((which == 0 || which == 1) && !wl.fused.empty()) { rc = launch_fused_same(p_fused, (int)wl.fused.size(), wl.max_fused, stream); n++; if (rc) return rc; }
-    if ((which == 0 || which == 2) && !wl.idct.empty()) { rc = launch_idct_plane(p_idct, (int)wl.idct.size(), wl.max_idct, stream); n++; if (rc) return rc; }
-    if ((which == 0 || which == 3) && !wl.c420.empty()) { rc = launch_chroma420_refdct(p_c420, (int)wl.c420.size(), wl.max_c420, stream); n++; if (rc) return rc; }
+    if ((which == 0 || which == 1) && !wl.fused.empty()) { rc = launch_fused_same(p_fused, (int)wl.fused.size(), wl.max_fused, stream); n++; LT_MARK("k_fused_same"); if (rc) return rc; }
+    if ((which == 0 || which == 2) && !wl.idct.empty()) { rc = launch_idct_plane(p_idct, (int)wl.idct.size(), wl.max_idct, stream); n++; LT_MARK("k_idct_plane"); if (rc) return rc; }
+    if ((which == 0 || which == 3) && !wl.c420.empty()) { rc = launch_chroma420_refdct(p_c420, (int)wl.c420.size(), wl.max_c420, stream); n++; LT_MARK("k_chroma420_refdct"); if (rc) return rc; }
     if (which == 0 || which == 3) {
         if (!wl.up.empty()) { rc = launch_upsample(p_up, (int)wl.up.size(), wl.max_up_w, wl.max_up_h, stream); n++; if (rc) return rc; }
         if (!wl.down.empty()) { rc = launch_downsample(p_down, (int)wl.down.size(), wl.max_dn_w, wl.max_dn_h, stream); n++; if (rc) return rc; }
@@ -171,6 +174,7 @@ void runtime_shutdown()
 }
 
 int runtime_device_count() { std::lock_guard<std::mutex> lk(g_mu); return g_inited ? (int)g_devs.size() : 0; }
+int runtime_device_ordinal(int i) { return g_devs.empty() ? 0 : g_devs[(size_t)i % g_devs.size()]->ordinal; }
 int runtime_next_device() { size_t n = g_devs.size(); return n ? (int)(g_rr.fetch_add(1) % n) : 0; }
 
 Slot *slot_acquire(int prefer, std::string &err)
@@ -314,6 +318,27 @@ bool slot_transform_group(Slot *s, const JpegGeom *const *gins, const JpegGeom &
 // (Measured and dropped: issuing the decode passes on a highest-priority stream so that their small latency-bound grids cut in
 // front of other megabatches' 24k-CTA encoder grids LOWERED the batch rate by 20 % -- 4,430 -> 3,550 images/s with 8 group
 // workers, 4,690 -> 4,030 with 16.  Everything of a megabatch stays on the slot's one stream.)
+//
+// One megabatch, front to back, with ONE host wait that leaves the GPU idle (the last): entropy decode (fixed number of rounds,
+// flags read afterwards), transform, entropy encode (its sizes come back while the emit kernels run).  Round 1 waited three
+// times per megabatch with an empty stream behind each wait.
+bool slot_run_group(Slot *s, std::vector<GpuDecoder::Item> &items, const JpegGeom *const *gins, const JpegGeom &gout, const GroupLayout &L, bool progressive,
+                    bool lossless, std::string &err)
+{
+    if (!s->dec) s->dec = new GpuDecoder();
+    if (!s->enc) s->enc = new GpuEncoder();
+    if (!s->dec->prepare(items, s->stream, err) || !s->dec->enqueue(s->stream, err)) return false;
+    if (!lossless && !slot_transform_group(s, gins, gout, L, err)) return false;
+    std::vector<int16_t *> bases((size_t)L.K);
+    for (int k = 0; k < L.K; k++) bases[k] = lossless ? reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(s->d_in) + L.in_stride * k)
+                                                      : reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(s->d_out) + L.out_stride * k);
+    // a re-encode at lower quality (or a transcode with optimal tables) does not grow: the inputs' entropy-coded size sizes the output buffers
+    if (!s->enc->prepare(gout, progressive, bases.data(), L.K, s->stream, s->dec->raw_bytes(), err) || !s->enc->enqueue(s->stream, true, err)) return false;
+    if (!s->enc->finish(s->stream, true, err)) return false;
+    s->dec->finish(items);
+    return true;
+}
+
 bool slot_decode_group(Slot *s, std::vector<GpuDecoder::Item> &items, std::string &err)
 {
     if (!s->dec) s->dec = new GpuDecoder();

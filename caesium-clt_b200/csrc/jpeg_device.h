@@ -62,6 +62,7 @@ int  runtime_device_count();
 Slot *slot_acquire(int prefer_dev, std::string &err);               // blocks while all slots of the device are busy
 void slot_release(Slot *s);
 int  runtime_next_device();                                         // round-robin shard assignment
+int  runtime_device_ordinal(int dev_index);                         // CUDA ordinal of the library's device number dev_index
 
 // Run the transform for ONE image whose input coefficients already sit in s->h_in; result lands in s->h_out.
 bool slot_transform(Slot *s, const JpegGeom &gin, const JpegGeom &gout, std::string &err, bool download = true, bool upload = true);
@@ -73,6 +74,10 @@ int slot_gpu_decode(Slot *s, const JpegReader &rd, const JpegReader::DeviceScan 
 struct GroupLayout { int K = 0; size_t in_stride = 0, out_stride = 0, scratch_stride = 0; };
 bool slot_group_layout(Slot *s, const JpegGeom &gin, const JpegGeom &gout, int K, GroupLayout &L, std::string &err);   // sizes + ensure()
 bool slot_decode_group(Slot *s, std::vector<GpuDecoder::Item> &items, std::string &err);      // items[k].d_coefs = d_in + k * in_stride
+// decode -> (transform) -> encode of one megabatch enqueued back to back, one idle host wait at the end; results in s->enc->results,
+// items[k].result says which images the device decoder settled
+bool slot_run_group(Slot *s, std::vector<GpuDecoder::Item> &items, const JpegGeom *const *gins, const JpegGeom &gout, const GroupLayout &L, bool progressive,
+                    bool lossless, std::string &err);
 bool slot_transform_group(Slot *s, const JpegGeom *const *gins, const JpegGeom &gout, const GroupLayout &L, std::string &err);
 // results in s->enc->results; from_input = encode the coefficients in d_in (lossless transcode) instead of d_out
 bool slot_encode_group(Slot *s, const JpegGeom &gout, bool progressive, const GroupLayout &L, std::string &err, bool from_input = false);

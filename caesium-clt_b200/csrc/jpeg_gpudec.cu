@@ -12,6 +12,7 @@
 #include "jpeg_gpudec.h"
 #include "jpeg_gpuenc_plan.h"
 #include "stream_wait.h"
+#include "launch_timer.h"
 
 namespace b200 {
 
@@ -203,14 +204,20 @@ GpuDecoder::~GpuDecoder()
     cudaFree(d_nblk); cudaFree(d_first); cudaFree(d_dc); cudaFree(d_dcs); cudaFree(d_par); cudaFreeHost(h_par); cudaFree(d_temp);
 }
 
-bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &err)
+// prepare(): per-image descriptors, buffers, Huffman tables; entropy-coded bytes and parameters staged in pinned memory and
+// their H2D copies enqueued.  enqueue(): every pass, no host wait -- a fixed number of synchronisation rounds (rounds whose image
+// has already settled leave at once), the per-round "something changed" flags copied back at the end.  finish(): after the
+// caller's wait, says per image whether it settled.  decode() = the three in a row with a wait.
+bool GpuDecoder::prepare(std::vector<Item> &items, void *stream_, std::string &err)
 {
     cudaStream_t st = (cudaStream_t)stream_;
     const int N = (int)items.size();
+    nitems = N;
     if (N == 0) return true;
     // ---- per-image descriptors
-    std::vector<DecImage> imgs((size_t)N);
-    size_t raw_total = 0, stream_total = 0; uint32_t grp_total = 0, sub_total = 0, blk_total = 0, max_grp = 0, max_sub = 0, max_blk = 0;
+    imgs.assign((size_t)N, DecImage());
+    coef_ptrs.resize((size_t)N); coef_bytes.resize((size_t)N);
+    raw_total = 0; size_t stream_total = 0; grp_total = 0; sub_total = 0; blk_total = 0; max_grp = 0; max_sub = 0; max_blk = 0;
     for (int n = 0; n < N; n++) {
         const JpegReader &rd = *items[n].rd; const JpegReader::DeviceScan &ds = *items[n].ds; const JpegGeom &g = rd.geom();
         items[n].result = FAILED;
@@ -236,11 +243,12 @@ bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &er
         im.sub_off = sub_total; sub_total += G.nsub;
         im.blk_off = blk_total; blk_total += G.total_blocks;
         max_grp = std::max(max_grp, im.ngrp); max_sub = std::max(max_sub, G.nsub); max_blk = std::max(max_blk, G.total_blocks);
+        coef_ptrs[n] = items[n].d_coefs; coef_bytes[n] = (size_t)g.total_coefs * 2;
     }
     if (raw_total >= (1ull << 31) || stream_total >= (1ull << 31)) { err = "decode batch too large"; return false; }
     // ---- buffers
-    const size_t o_img = 0, o_tab = align_up(sizeof(DecImage) * N, 256), o_flag = o_tab + align_up(sizeof(DecTables) * N, 256);
-    const size_t par_bytes = o_flag + align_up((size_t)4 * N * (MAX_ROUNDS + 2), 256);
+    o_img = 0; o_tab = align_up(sizeof(DecImage) * N, 256); o_flag = o_tab + align_up(sizeof(DecTables) * N, 256);
+    par_bytes = o_flag + align_up((size_t)4 * N * (MAX_ROUNDS + 2), 256);
     if (!growd(h_raw, cap_hraw, raw_total + 64, true, err) || !growd(d_raw, cap_raw, raw_total + 64, false, err) || !growd(d_stream, cap_stream, stream_total + 64, false, err) ||
         !growd(d_cnt, cap_cnt, (size_t)grp_total * 4 + 4, false, err) || !growd(d_off, cap_off, (size_t)grp_total * 4 + 4, false, err) ||
         !growd(d_A, cap_A, (size_t)sub_total * sizeof(DecState), false, err) ||
@@ -255,7 +263,7 @@ bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &er
     if (!growd(d_temp, cap_temp, std::max(t1, std::max(t2, t3)) + 256, false, err)) return false;
     // ---- parameters + raw bytes
     DecTables *ht = reinterpret_cast<DecTables *>(h_par + o_tab);
-    std::vector<char> tables_ok((size_t)N, 1);
+    tables_ok.assign((size_t)N, 1);
     for (int n = 0; n < N; n++) {
         const JpegReader &rd = *items[n].rd;
         const uint8_t *db[8], *dv[8];
@@ -267,51 +275,85 @@ bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &er
     }
     memcpy(h_par + o_img, imgs.data(), sizeof(DecImage) * N);
     memset(h_par + o_flag, 0, (size_t)4 * N * (MAX_ROUNDS + 2));
-    CUD(cudaMemcpyAsync(d_par, h_par, par_bytes, cudaMemcpyHostToDevice, st));
+    CUD(cudaMemcpyAsync(d_par, h_par, o_flag, cudaMemcpyHostToDevice, st));
     CUD(cudaMemcpyAsync(d_raw, h_raw, raw_total, cudaMemcpyHostToDevice, st));
+    return true;
+}
+
+bool GpuDecoder::enqueue(void *stream_, std::string &err)
+{
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int N = nitems;
+    if (N == 0) return true;
+    static const int nrounds = [] { const char *e = getenv("B200_DEC_ROUNDS"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= MAX_ROUNDS ? v : (int)ROUNDS; }();
     const DecImage *dI = reinterpret_cast<const DecImage *>(d_par + o_img);
     const DecTables *dT = reinterpret_cast<const DecTables *>(d_par + o_tab);
     uint32_t *dF = reinterpret_cast<uint32_t *>(d_par + o_flag);
     uint32_t *hF = reinterpret_cast<uint32_t *>(h_par + o_flag);
+    CUD(cudaMemsetAsync(dF, 0, (size_t)4 * N * (MAX_ROUNDS + 2), st));
+    LT_MARK("memset");
     // ---- unstuff
     const dim3 gg(cdiv(max_grp, 128), N);
     k_gd_unstuff_count<<<gg, 128, 0, st>>>(dI, d_raw, d_cnt);
+    LT_MARK("k_gd_unstuff_count");
     size_t tb = cap_temp;
     cub::DeviceScan::ExclusiveSum(d_temp, tb, d_cnt, d_off, (int)grp_total, st);
+    LT_MARK("cub_scan");
     k_gd_unstuff_scatter<<<gg, 128, 0, st>>>(dI, d_raw, d_off, d_stream);
-    for (int n = 0; n < N; n++) CUD(cudaMemsetAsync(items[n].d_coefs, 0, (size_t)items[n].rd->geom().total_coefs * 2, st));
+    LT_MARK("k_gd_unstuff_scatter");
+    for (int n = 0; n < N; n++) CUD(cudaMemsetAsync(coef_ptrs[n], 0, coef_bytes[n], st));
     // ---- rounds
     const dim3 gs(cdiv(max_sub, 64), N);
     const size_t ncta = (size_t)N * gs.x;                    // dirty flags: two buffers of one byte per CTA, by round parity
     CUD(cudaMemsetAsync(d_chgB, 0, 2 * ncta, st));
+    LT_MARK("memset");
     k_gd_round0<<<gs, 64, 0, st>>>(dI, d_stream, dT, d_A, d_chgA, d_nblk);
-    DecState *A = d_A;
-    int rounds = 0; std::vector<char> conv((size_t)N, 0); int nconv = 0;
-    while (nconv < N && rounds < MAX_ROUNDS) {
-        const int first_round = rounds;
-        for (int r = 0; r < ROUNDS_PER_GROUP && rounds < MAX_ROUNDS; r++, rounds++) {
-            const int rn = rounds + 1;                        // round number: reads dirty[rn & 1], writes dirty[(rn + 1) & 1]
-            k_gd_round<<<gs, 64, 0, st>>>(dI, d_stream, dT, d_A, d_chgA, d_chgB + (size_t)(rn & 1) * ncta, d_chgB + (size_t)((rn + 1) & 1) * ncta, d_nblk,
-                                          dF + (size_t)rounds * N, rounds ? dF + (size_t)(rounds - 1) * N : nullptr, rn);
-        }
-        CUD(cudaMemcpyAsync(hF + (size_t)first_round * N, dF + (size_t)first_round * N, (size_t)4 * N * (rounds - first_round), cudaMemcpyDeviceToHost, st));
-        CUD(stream_wait(st));
-        for (int n = 0; n < N; n++) if (!conv[n]) for (int r = first_round; r < rounds; r++) if (hF[(size_t)r * N + n] == 0) { conv[n] = 1; nconv++; break; }
+    LT_MARK("k_gd_round0");
+    for (int rounds = 0; rounds < nrounds; rounds++) {
+        const int rn = rounds + 1;                            // round number: reads dirty[rn & 1], writes dirty[(rn + 1) & 1]
+        k_gd_round<<<gs, 64, 0, st>>>(dI, d_stream, dT, d_A, d_chgA, d_chgB + (size_t)(rn & 1) * ncta, d_chgB + (size_t)((rn + 1) & 1) * ncta, d_nblk,
+                                      dF + (size_t)rounds * N, rounds ? dF + (size_t)(rounds - 1) * N : nullptr, rn);
+        LT_MARK("k_gd_round");
     }
-    rounds_used = rounds;
-    for (int n = 0; n < N; n++) items[n].result = conv[n] && tables_ok[n] ? OK : NOT_CONVERGED;
-    if (nconv == 0) return true;
+    rounds_used = nrounds;
+    CUD(cudaMemcpyAsync(hF, dF, (size_t)4 * N * nrounds, cudaMemcpyDeviceToHost, st));
     // ---- block counts -> first block of each subsequence -> write -> DC (images that did not converge produce garbage
     //      that their caller discards)
     tb = cap_temp;
     cub::DeviceScan::ExclusiveSum(d_temp, tb, d_nblk, d_first, (int)sub_total, st);
-    k_gd_write<<<gs, 64, 0, st>>>(dI, d_stream, dT, A, d_first);
+    LT_MARK("cub_scan");
+    k_gd_write<<<gs, 64, 0, st>>>(dI, d_stream, dT, d_A, d_first);
+    LT_MARK("k_gd_write");
     const dim3 gb(cdiv(max_blk, 128), N);
     k_gd_dc_gather<<<gb, 128, 0, st>>>(dI, d_dc, d_A, d_first, d_nblk);
+    LT_MARK("k_gd_dc_gather");
     tb = cap_temp;
     cub::DeviceScan::InclusiveSum(d_temp, tb, d_dc, d_dcs, (int)blk_total, st);
+    LT_MARK("cub_scan");
     k_gd_dc_scatter<<<gb, 128, 0, st>>>(dI, d_dcs);
+    LT_MARK("k_gd_dc_scatter");
     CUD(cudaGetLastError());
+    launches = 10 + nrounds;
+    return true;
+}
+
+void GpuDecoder::finish(std::vector<Item> &items)
+{   // the caller has waited for the stream: an image settled iff some round changed nothing in it
+    const int N = nitems;
+    const uint32_t *hF = reinterpret_cast<const uint32_t *>(h_par + o_flag);
+    for (int n = 0; n < N && n < (int)items.size(); n++) {
+        bool conv = false;
+        for (int r = 0; r < rounds_used && !conv; r++) conv = hF[(size_t)r * N + n] == 0;
+        items[n].result = conv && tables_ok[n] ? OK : NOT_CONVERGED;
+    }
+}
+
+bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &err)
+{
+    if (items.empty()) return true;
+    if (!prepare(items, stream_, err) || !enqueue(stream_, err)) return false;
+    CUD(stream_wait((cudaStream_t)stream_));
+    finish(items);
     return true;
 }
 

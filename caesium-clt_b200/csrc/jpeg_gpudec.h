@@ -34,11 +34,23 @@ public:
     // decodes that image on the host instead).  Returns false on a CUDA failure.  Asynchronous work on `stream`, with one
     // short host sync per group of rounds.
     bool decode(std::vector<Item> &items, void *stream, std::string &err);
-    int rounds_used = 0;
+    // the same in steps: prepare() stages inputs and descriptors (H2D enqueued), enqueue() launches every pass without a host
+    // wait (repeatable on unchanged inputs), finish() -- after the caller has waited for the stream -- fills items[].result
+    bool prepare(std::vector<Item> &items, void *stream, std::string &err);
+    bool enqueue(void *stream, std::string &err);
+    void finish(std::vector<Item> &items);
+    size_t raw_bytes() const { return raw_total; }          // entropy-coded bytes staged by the last prepare()
+    int rounds_used = 0, launches = 0;
     // subsequence size: swept 512 .. 8192 on the 4K bench set under full batch load (tools/throughput.py): 512 -> 3,400
     // images/s, 1024 -> 3,750, 2048 -> 3,970, 4096 -> 3,865, 8192 -> 3,560 (B200_DEC_SUBSEQ overrides)
-    static constexpr int SUBSEQ_BITS = 2048, ROUNDS_PER_GROUP = 16, MAX_ROUNDS = 64;
+    // ROUNDS: synchronisation rounds launched per batch, without a host check in between (a round whose image settled in an earlier
+    // one leaves at once: ~2 us); the 4K bench set settles in <= 14.  An image that needs more is decoded on the host.
+    static constexpr int SUBSEQ_BITS = 2048, ROUNDS = 24, MAX_ROUNDS = 64;
 private:
+    int nitems = 0;
+    std::vector<DecImage> imgs; std::vector<int16_t *> coef_ptrs; std::vector<size_t> coef_bytes; std::vector<char> tables_ok;
+    size_t raw_total = 0, o_img = 0, o_tab = 0, o_flag = 0, par_bytes = 0;
+    uint32_t grp_total = 0, sub_total = 0, blk_total = 0, max_grp = 0, max_sub = 0, max_blk = 0;
     uint8_t *h_raw = nullptr; size_t cap_hraw = 0;          // pinned staging of the entropy-coded segments
     uint8_t *d_raw = nullptr, *d_stream = nullptr; size_t cap_raw = 0, cap_stream = 0;
     uint32_t *d_cnt = nullptr, *d_off = nullptr; size_t cap_cnt = 0, cap_off = 0;

@@ -5,14 +5,15 @@
 //
 // Passes (one launch each for ANY number of images x scans; blockIdx.y = scan):
 //   classify -> [max-scan: previous event] [sum-scan: trailing correction bits] -> groups -> histogram -> tables ->
-//   lengths -> [sum-scan: bit offsets] -> totals | host sync: sizes | zero -> emit -> ffcount -> [sum-scan] -> layout ->
-//   scatter (byte stuffing) | D2H: stuffed scans + DHT payloads.
+//   lengths -> [sum-scan: bit offsets] -> scan sizes / buffer layout (on the device) -> zero -> emit -> ffcount -> [sum-scan] ->
+//   layout -> scatter (byte stuffing) | D2H: stuffed scans + DHT payloads.  No host wait in between: see "host orchestration".
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <cstring>
 #include "jpeg_gpuenc.h"
 #include "stream_wait.h"
+#include "launch_timer.h"
 
 namespace b200 {
 
@@ -99,20 +100,39 @@ __global__ void k_ge_tables(const uint32_t *__restrict__ hist, Table *__restrict
     }
 }
 
-__global__ void k_ge_totals(const Scan *__restrict__ scans, int nscans, const uint32_t *__restrict__ bitlen, const uint32_t *__restrict__ bitoff, uint32_t *__restrict__ total)
+// Sizes on the device: bits per scan from the bit-offset scan, then every scan's place in the group's bit buffer (word_base),
+// its byte / 16-byte-group counts and the group index base -- what the host used to compute between two halves of the pipeline
+// (one stream wait per megabatch less).  The buffers are sized from an ESTIMATE of the output (the input's size for a re-encode);
+// if the real sizes do not fit, flags[0] is raised, every scan is given zero length so the back half does nothing, and the host
+// re-runs the back half with exact sizes (flags[1..2] = words / groups needed).  One warp; scans in chunks of 32.
+__global__ void k_ge_scanout(const Scan *__restrict__ scans, int nscans, const uint32_t *__restrict__ bitlen, const uint32_t *__restrict__ bitoff, uint32_t *__restrict__ total,
+                             ScanOut *__restrict__ so, uint32_t words_cap, uint32_t groups_cap, uint32_t *__restrict__ flags)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nscans) return;
-    const Scan s = scans[i];
-    const long long last = s.unit_base + s.nblocks - 1;
-    total[i] = s.nblocks ? bitoff[last] + bitlen[last] - bitoff[s.unit_base] : 0;
+    const int lane = threadIdx.x;
+    uint32_t wbase = 0, gbase = 0;
+    for (int c0 = 0; c0 < nscans; c0 += 32) {
+        const int i = c0 + lane;
+        uint32_t tb = 0;
+        if (i < nscans) { const Scan s = scans[i]; const long long last = s.unit_base + s.nblocks - 1; tb = s.nblocks ? bitoff[last] + bitlen[last] - bitoff[s.unit_base] : 0; }
+        const uint32_t nbytes = (tb + 7) / 8, ng = (nbytes + 15) / 16, nw = i < nscans ? (tb + 31) / 32 + 1 : 0;
+        uint32_t wi = nw, gi = i < nscans ? ng : 0;                  // inclusive warp scans
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, wi, d), b = __shfl_up_sync(0xFFFFFFFFu, gi, d); if (lane >= d) { wi += a; gi += b; } }
+        if (i < nscans) { total[i] = tb; ScanOut o; o.total_bits = tb; o.nbytes = nbytes; o.ngroups = ng; o.group_base = gbase + gi - ng; o.word_base = wbase + wi - nw; o.pad_ = 0; so[i] = o; }
+        wbase += __shfl_sync(0xFFFFFFFFu, wi, 31); gbase += __shfl_sync(0xFFFFFFFFu, gi, 31);
+    }
+    __syncwarp();
+    const bool ovf = wbase > words_cap || gbase > groups_cap;
+    if (lane == 0) { flags[0] = ovf ? 1u : 0u; flags[1] = wbase; flags[2] = gbase; flags[3] = 0; flags[4] = 0; }
+    if (ovf) for (int i = lane; i < nscans; i += 32) { so[i].total_bits = 0; so[i].nbytes = 0; so[i].ngroups = 0; so[i].group_base = 0; so[i].word_base = 0; }
 }
 
-__global__ void k_ge_zero(const Scan *__restrict__ scans, const ScanOut *__restrict__ so, uint32_t *__restrict__ words)
+__global__ void k_ge_zero(const ScanOut *__restrict__ so, uint32_t *__restrict__ words)
 {
-    const Scan s = scans[blockIdx.y];
-    const long long n = ((long long)so[blockIdx.y].total_bits + 31) / 32 + 1;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n && i < s.word_cap; i += (long long)gridDim.x * blockDim.x) words[s.word_base + i] = 0;
+    const ScanOut o = so[blockIdx.y];
+    if (!o.total_bits) return;
+    const uint32_t n = (o.total_bits + 31) / 32 + 1;
+    uint32_t *w = words + o.word_base;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) w[i] = 0;
 }
 
 // ---- block-major passes: one thread per block; the block is read (and its threshold masks built) once per pass and
@@ -209,8 +229,10 @@ __global__ void k_geb_len(const BlockComp *__restrict__ comps, const Scan *__res
 }
 
 __global__ void k_geb_emit(const BlockComp *__restrict__ comps, const Scan *__restrict__ scans, const uint32_t *__restrict__ gcount, const Table *__restrict__ tabs,
-                           const uint32_t *__restrict__ bitoff, uint32_t *__restrict__ words, const Masks3 *__restrict__ masks)
+                           const uint32_t *__restrict__ bitoff, uint32_t *__restrict__ words, const Masks3 *__restrict__ masks, const ScanOut *__restrict__ so,
+                           const uint32_t *__restrict__ flags)
 {
+    if (flags[0]) return;                   // the bit buffer is too small for this batch: the host re-runs this half with exact sizes
     const BlockComp bc = comps[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= bc.bw * bc.bh) return;
@@ -222,7 +244,7 @@ __global__ void k_geb_emit(const BlockComp *__restrict__ comps, const Scan *__re
         const Scan &s = scans[bc.scan_idx[j]];
         const int u = unit_of(s, bc, row, col);
         if (u < 0) continue;
-        EmitSink<decltype(orw)> sk(tabs + s.tab_base, orw, s.word_base, (unsigned long long)(bitoff[s.unit_base + u] - bitoff[s.unit_base]));
+        EmitSink<decltype(orw)> sk(tabs + s.tab_base, orw, (long long)so[bc.scan_idx[j]].word_base, (unsigned long long)(bitoff[s.unit_base + u] - bitoff[s.unit_base]));
         gen_block_m(s, ref_of(s, u, blk), M, gcount[s.unit_base + u], sk);
         sk.finish();
     }
@@ -236,20 +258,29 @@ __device__ __forceinline__ uint32_t scan_byte(const uint32_t *__restrict__ w, ui
     return b;
 }
 
-__global__ void k_ge_ffcount(const Scan *__restrict__ scans, const ScanOut *__restrict__ so, const uint32_t *__restrict__ words, uint32_t *__restrict__ ffcount)
+// 0xFF count per 16-byte group.  Grid (X, nscans + 1): row y < nscans strides over scan y's groups; the extra row zero-fills the
+// group slots past the batch's last group, because the prefix sum that follows runs over the whole (capacity-sized) array.
+__global__ void k_ge_ffcount(const ScanOut *__restrict__ so, int nscans, const uint32_t *__restrict__ words, uint32_t *__restrict__ ffcount, uint32_t groups_cap,
+                             const uint32_t *__restrict__ flags)
 {
+    if ((int)blockIdx.y == nscans) {
+        const uint32_t used = flags[0] ? 0u : flags[2];
+        for (uint32_t g = used + blockIdx.x * blockDim.x + threadIdx.x; g < groups_cap; g += gridDim.x * blockDim.x) ffcount[g] = 0;
+        return;
+    }
     const ScanOut o = so[blockIdx.y];
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= o.ngroups) return;
-    const uint32_t *w = words + scans[blockIdx.y].word_base;
-    uint32_t n = 0;
-    for (uint32_t i = g * 16; i < g * 16 + 16 && i < o.nbytes; i++) n += scan_byte(w, i, o.nbytes, o.total_bits) == 0xFF;
-    ffcount[o.group_base + g] = n;
+    const uint32_t *w = words + o.word_base;
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < o.ngroups; g += gridDim.x * blockDim.x) {
+        uint32_t n = 0;
+        for (uint32_t i = g * 16; i < g * 16 + 16 && i < o.nbytes; i++) n += scan_byte(w, i, o.nbytes, o.total_bits) == 0xFF;
+        ffcount[o.group_base + g] = n;
+    }
 }
 
-// per image: lay its scans out back to back in the output buffer; out_off / out_len per scan
+// per image: lay its scans out back to back in the image's output region; out_off / out_len per scan; an image that outgrows its
+// region raises flags[0] (and flags[3] = the largest image size seen, so the host can size the retry)
 __global__ void k_ge_layout(const ScanOut *__restrict__ so, int scans_per_image, int nimages, const uint32_t *__restrict__ ffcount, const uint32_t *__restrict__ ffoff,
-                            uint32_t *__restrict__ out_off, uint32_t *__restrict__ out_len)
+                            uint32_t *__restrict__ out_off, uint32_t *__restrict__ out_len, uint32_t out_image_stride, uint32_t *__restrict__ flags)
 {
     const int im = blockIdx.x * blockDim.x + threadIdx.x;
     if (im >= nimages) return;
@@ -262,20 +293,24 @@ __global__ void k_ge_layout(const ScanOut *__restrict__ so, int scans_per_image,
         out_off[si] = off; out_len[si] = o.nbytes + ff;
         off += o.nbytes + ff;
     }
+    atomicMax(&flags[3], off);
+    if (off > out_image_stride) atomicOr(&flags[4], 1u);
 }
 
-__global__ void k_ge_scatter(const Scan *__restrict__ scans, const ScanOut *__restrict__ so, const uint32_t *__restrict__ words, const uint32_t *__restrict__ ffoff,
-                             const uint32_t *__restrict__ out_off, uint8_t *__restrict__ out, int scans_per_image, size_t out_image_stride)
+__global__ void k_ge_scatter(const ScanOut *__restrict__ so, const uint32_t *__restrict__ words, const uint32_t *__restrict__ ffoff,
+                             const uint32_t *__restrict__ out_off, uint8_t *__restrict__ out, int scans_per_image, size_t out_image_stride, const uint32_t *__restrict__ flags)
 {
+    if (flags[4]) return;                   // some image does not fit its output region: nothing is written, the host retries
     const ScanOut o = so[blockIdx.y];
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= o.ngroups) return;
-    const uint32_t *w = words + scans[blockIdx.y].word_base;
-    uint8_t *dst = out + (size_t)(blockIdx.y / scans_per_image) * out_image_stride + out_off[blockIdx.y] + (size_t)g * 16 + (ffoff[o.group_base + g] - ffoff[o.group_base]);
-    for (uint32_t i = g * 16; i < g * 16 + 16 && i < o.nbytes; i++) {
-        const uint32_t b = scan_byte(w, i, o.nbytes, o.total_bits);
-        *dst++ = (uint8_t)b;
-        if (b == 0xFF) *dst++ = 0;
+    const uint32_t *w = words + o.word_base;
+    uint8_t *base = out + (size_t)(blockIdx.y / scans_per_image) * out_image_stride + out_off[blockIdx.y];
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < o.ngroups; g += gridDim.x * blockDim.x) {
+        uint8_t *dst = base + (size_t)g * 16 + (ffoff[o.group_base + g] - ffoff[o.group_base]);
+        for (uint32_t i = g * 16; i < g * 16 + 16 && i < o.nbytes; i++) {
+            const uint32_t b = scan_byte(w, i, o.nbytes, o.total_bits);
+            *dst++ = (uint8_t)b;
+            if (b == 0xFF) *dst++ = 0;
+        }
     }
 }
 
@@ -296,6 +331,12 @@ __global__ void k_ge_fill_dummy(int16_t *__restrict__ coef, long long comp_off, 
 }
 
 // ---- host orchestration ---------------------------------------------------------------------------------------------
+// Three steps so that a megabatch costs the host one wait that overlaps device work plus the final one, and so that a caller with
+// everything resident in HBM (bench.py's device-only figure) can enqueue the whole pass sequence without any wait:
+//   prepare()  plan + buffers (sized from an estimate of the output) + H2D of the descriptors
+//   enqueue()  every kernel; D2H of the sizes right after the bit-offset scan (event), D2H of DHT payloads / stuffed lengths at the end
+//   finish()   wait for the sizes (the emit / stuffing kernels are still running), size and enqueue the D2H of the stuffed scans,
+//              final wait; a batch that outgrew the estimate re-runs the back half with exact sizes
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
@@ -318,25 +359,47 @@ GpuEncoder::~GpuEncoder()
     cudaFree(d_scans); cudaFree(d_comps); cudaFree(d_meta); cudaFree(d_evkey); cudaFree(d_prev); cudaFree(d_tail); cudaFree(d_tsum); cudaFree(d_gcount);
     cudaFree(d_bitlen); cudaFree(d_bitoff); cudaFree(d_hist); cudaFree(d_tabs); cudaFree(d_dht); cudaFree(d_total); cudaFree(d_so);
     cudaFree(d_words); cudaFree(d_masks); cudaFree(d_ffcount); cudaFree(d_ffoff); cudaFree(d_outoff); cudaFree(d_outlen); cudaFree(d_out); cudaFree(d_temp);
+    cudaFree(d_flags);
     cudaFreeHost(h_small); cudaFreeHost(h_out);
+    if (ev_sizes) cudaEventDestroy((cudaEvent_t)ev_sizes);
 }
 
-bool GpuEncoder::encode(const JpegGeom &g, bool progressive, int16_t *const *d_coefs, int nimages, void *stream_, bool fill_dummy, std::string &err)
+bool GpuEncoder::size_back_buffers(size_t image_bytes, std::string &err)
+{   // everything whose size follows the OUTPUT: bit buffer, 16-byte group arrays, stuffed bytes
+    const int NS = (int)plan.scans.size();
+    est_image_bytes = image_bytes;
+    words_cap = (uint32_t)std::min<size_t>((size_t)nimg * (image_bytes / 4 + 1) + 2 * (size_t)NS + 64, 0xFFFFFF00u);
+    groups_cap = (uint32_t)((size_t)words_cap / 4 + NS + 1);
+    out_stride = align_up(image_bytes + image_bytes / 8 + 1024, 256);
+    size_t c;
+    c = cap_words; if (!grow(d_words, c, (size_t)words_cap * 4 + 64, false, err)) return false; cap_words = c;
+    c = cap_ff[0]; if (!grow(d_ffcount, c, (size_t)groups_cap * 4 + 4, false, err)) return false; cap_ff[0] = c;
+    c = cap_ff[1]; if (!grow(d_ffoff, c, (size_t)groups_cap * 4 + 4, false, err)) return false; cap_ff[1] = c;
+    c = cap_out; if (!grow(d_out, c, out_stride * nimg, false, err)) return false; cap_out = c;
+    size_t tb3 = 0; cub::DeviceScan::ExclusiveSum((void *)nullptr, tb3, d_ffcount, d_ffoff, (int)groups_cap, (cudaStream_t)0);
+    c = cap_temp; if (tb3 + 256 > c) { if (!grow(d_temp, c, tb3 + 256, false, err)) return false; cap_temp = c; }
+    return true;
+}
+
+bool GpuEncoder::prepare(const JpegGeom &g, bool progressive, int16_t *const *d_coefs, int nimages, void *stream_, size_t out_bytes_hint, std::string &err)
 {
     cudaStream_t st = (cudaStream_t)stream_;
+    geom = g; prog = progressive;
     std::vector<const int16_t *> bases(d_coefs, d_coefs + nimages);
+    coef_bases.assign(d_coefs, d_coefs + nimages);
     gpuenc_plan(g, progressive, bases.data(), nimages, plan);
     nimg = nimages;
     const int NS = (int)plan.scans.size();
     const long long U = plan.total_units;
     if (U >= (1ll << 31)) { err = "batch too large for the entropy encoder"; return false; }
-    int max_units = 0; for (auto &s : plan.scans) max_units = std::max(max_units, s.nblocks);
-    // ---- buffers
+    overflow = false;
+    for (auto &sc_ : plan.scans) if (!masks_cover(sc_.mode, sc_.Al)) { err = "scan script outside the device encoder's mask range"; overflow = true; return false; }
+    if (!ev_sizes) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | (stream_wait_mode() == 0 ? 0 : cudaEventBlockingSync))); ev_sizes = e; }
+    // ---- buffers whose size follows the INPUT
     size_t c;
     c = cap_scans; if (!grow(d_scans, c, NS * sizeof(Scan), false, err)) return false; cap_scans = c;
     const int NC = (int)plan.comps.size();
     c = cap_comps; if (!grow(d_comps, c, NC * sizeof(BlockComp), false, err)) return false; cap_comps = c;
-    for (auto &sc_ : plan.scans) if (!masks_cover(sc_.mode, sc_.Al)) { err = "scan script outside the device encoder's mask range"; overflow = true; return false; }
     c = cap_u[0]; if (!grow(d_meta, c, U * 4, false, err)) return false; cap_u[0] = c;
     c = cap_u[1]; if (!grow(d_evkey, c, U * 4, false, err)) return false; cap_u[1] = c;
     c = cap_u[2]; if (!grow(d_prev, c, U * 4, false, err)) return false; cap_u[2] = c;
@@ -352,110 +415,166 @@ bool GpuEncoder::encode(const JpegGeom &g, bool progressive, int16_t *const *d_c
     c = cap_so; if (!grow(d_so, c, (size_t)NS * sizeof(ScanOut), false, err)) return false; cap_so = c;
     c = cap_oo; if (!grow(d_outoff, c, (size_t)NS * 4, false, err)) return false; cap_oo = c;
     c = cap_ol; if (!grow(d_outlen, c, (size_t)NS * 4, false, err)) return false; cap_ol = c;
-    c = cap_words; if (!grow(d_words, c, (size_t)plan.total_words * 4, false, err)) return false; cap_words = c;
+    c = cap_flags; if (!grow(d_flags, c, 64, false, err)) return false; cap_flags = c;
     c = cap_masks; if (!grow(d_masks, c, (size_t)plan.total_comp_blocks * sizeof(Masks3), false, err)) return false; cap_masks = c;
-    const size_t small_bytes = align_up((size_t)NS * sizeof(Scan), 256) + align_up((size_t)NS * sizeof(ScanOut), 256) + align_up((size_t)NS * 4, 256) * 2 + align_up((size_t)NS * 4 * sizeof(DhtOut), 256) +
-                               align_up((size_t)NC * sizeof(BlockComp), 256);
+    o_scans = 0; o_total = o_scans + align_up((size_t)NS * sizeof(Scan), 256); o_outlen = o_total + align_up((size_t)NS * 4, 256);
+    o_dht = o_outlen + align_up((size_t)NS * 4, 256); o_comps = o_dht + align_up((size_t)NS * 4 * sizeof(DhtOut), 256);
+    o_flags = o_comps + align_up((size_t)NC * sizeof(BlockComp), 256);
+    const size_t small_bytes = o_flags + 256;
     c = cap_small; if (!grow(h_small, c, small_bytes, true, err)) return false; cap_small = c;
     size_t tb1 = 0, tb2 = 0;
     cub::DeviceScan::ExclusiveScan((void *)nullptr, tb1, d_evkey, d_prev, cub::Max(), -1, (int)U, st);
     cub::DeviceScan::ExclusiveSum((void *)nullptr, tb2, d_tail, d_tsum, (int)U, st);
     c = cap_temp; if (!grow(d_temp, c, std::max(tb1, tb2) + 256, false, err)) return false; cap_temp = c;
-    uint8_t *hp = h_small;
-    Scan *h_scans = reinterpret_cast<Scan *>(hp); hp += align_up((size_t)NS * sizeof(Scan), 256);
-    ScanOut *h_so = reinterpret_cast<ScanOut *>(hp); hp += align_up((size_t)NS * sizeof(ScanOut), 256);
-    uint32_t *h_total = reinterpret_cast<uint32_t *>(hp); hp += align_up((size_t)NS * 4, 256);
-    uint32_t *h_outlen = reinterpret_cast<uint32_t *>(hp); hp += align_up((size_t)NS * 4, 256);
-    DhtOut *h_dht = reinterpret_cast<DhtOut *>(hp); hp += align_up((size_t)NS * 4 * sizeof(DhtOut), 256);
-    BlockComp *h_comps = reinterpret_cast<BlockComp *>(hp);
-    memcpy(h_scans, plan.scans.data(), NS * sizeof(Scan));
-    memcpy(h_comps, plan.comps.data(), NC * sizeof(BlockComp));
-    CU(cudaMemcpyAsync(d_scans, h_scans, NS * sizeof(Scan), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d_comps, h_comps, NC * sizeof(BlockComp), cudaMemcpyHostToDevice, st));
+    // ---- buffers whose size follows the OUTPUT: estimate now, exact on a retry.  A re-encode at lower quality does not grow, so
+    // the caller's hint is the input's entropy-coded size; without a hint a third of the coefficient bytes (~ 1 byte / pixel).
+    const size_t coef_bytes = (size_t)g.total_coefs * 2;
+    if (coef_bytes != learned_for) { learned_for = coef_bytes; learned_image_bytes = 0; }
+    size_t est = out_bytes_hint ? out_bytes_hint / nimages + out_bytes_hint / nimages / 4 : coef_bytes / 3;
+    est = std::max(est, learned_image_bytes + learned_image_bytes / 8) + 8192;
+    est = std::min(est, coef_bytes * 2 + (size_t)plan.scans_per_image * 64 + 8192);      // worst case: 128 B per block and scan... bounded by the retry anyway
+    if (!size_back_buffers(est, err)) return false;
+    memcpy(h_small + o_scans, plan.scans.data(), NS * sizeof(Scan));
+    memcpy(h_small + o_comps, plan.comps.data(), NC * sizeof(BlockComp));
+    CU(cudaMemcpyAsync(d_scans, h_small + o_scans, NS * sizeof(Scan), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_comps, h_small + o_comps, NC * sizeof(BlockComp), cudaMemcpyHostToDevice, st));
+    return true;
+}
+
+bool GpuEncoder::enqueue_back(void *stream_, std::string &err)
+{
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int NS = (int)plan.scans.size(), NC = (int)plan.comps.size();
+    uint32_t *h_total = reinterpret_cast<uint32_t *>(h_small + o_total), *h_flags = reinterpret_cast<uint32_t *>(h_small + o_flags);
+    k_ge_scanout<<<1, 32, 0, st>>>(d_scans, NS, d_bitlen, d_bitoff, d_total, d_so, words_cap, groups_cap, d_flags);
+    LT_MARK("k_ge_scanout");
+    CU(cudaMemcpyAsync(h_total, d_total, (size_t)NS * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_flags, d_flags, 12, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord((cudaEvent_t)ev_sizes, st));
+    LT_MARK("copy");
+    const dim3 gb(cdiv(plan.max_comp_blocks, 128), NC);
+    k_ge_zero<<<dim3(64, NS), 256, 0, st>>>(d_so, d_words);
+    LT_MARK("k_ge_zero");
+    k_geb_emit<<<gb, 128, 0, st>>>(d_comps, d_scans, d_gcount, d_tabs, d_bitoff, d_words, d_masks, d_so, d_flags);
+    LT_MARK("k_geb_emit");
+    k_ge_ffcount<<<dim3(32, NS + 1), 128, 0, st>>>(d_so, NS, d_words, d_ffcount, groups_cap, d_flags);
+    LT_MARK("k_ge_ffcount");
+    size_t tb = cap_temp;
+    cub::DeviceScan::ExclusiveSum(d_temp, tb, d_ffcount, d_ffoff, (int)groups_cap, st);
+    LT_MARK("cub_scan");
+    k_ge_layout<<<cdiv(nimg, 64), 64, 0, st>>>(d_so, plan.scans_per_image, nimg, d_ffcount, d_ffoff, d_outoff, d_outlen, (uint32_t)out_stride, d_flags);
+    LT_MARK("k_ge_layout");
+    k_ge_scatter<<<dim3(32, NS), 128, 0, st>>>(d_so, d_words, d_ffoff, d_outoff, d_out, plan.scans_per_image, out_stride, d_flags);
+    LT_MARK("k_ge_scatter");
+    CU(cudaMemcpyAsync(h_small + o_outlen, d_outlen, (size_t)NS * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_small + o_dht, d_dht, (size_t)NS * 4 * sizeof(DhtOut), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_flags + 4, d_flags, 32, cudaMemcpyDeviceToHost, st));         // second snapshot: image-level overflow (flags[3..4])
+    CU(cudaGetLastError());
+    launches += 7;
+    return true;
+}
+
+bool GpuEncoder::enqueue(void *stream_, bool fill_dummy, std::string &err)
+{
+    cudaStream_t st = (cudaStream_t)stream_;
+    const JpegGeom &g = geom;
+    const int NS = (int)plan.scans.size(), NC = (int)plan.comps.size();
+    const long long U = plan.total_units;
+    int max_units = 0; for (auto &s : plan.scans) max_units = std::max(max_units, s.nblocks);
+    launches = 0;
     const dim3 gb(cdiv(plan.max_comp_blocks, 128), NC);
     if (fill_dummy) {
-        for (int im = 0; im < nimages; im++) for (int cc = 0; cc < g.ncomp; cc++) {
+        for (int im = 0; im < nimg; im++) for (int cc = 0; cc < g.ncomp; cc++) {
             if (g.rbw[cc] == g.bw[cc] && g.rbh[cc] == g.bh[cc]) continue;
-            k_ge_fill_dummy<<<cdiv((long long)g.bw[cc] * g.bh[cc], 256), 256, 0, st>>>(d_coefs[im], g.comp_offset[cc], g.bw[cc], g.bh[cc], g.rbw[cc], g.rbh[cc], g.hs[cc]);
+            k_ge_fill_dummy<<<cdiv((long long)g.bw[cc] * g.bh[cc], 256), 256, 0, st>>>(coef_bases[im], g.comp_offset[cc], g.bw[cc], g.bh[cc], g.rbw[cc], g.rbh[cc], g.hs[cc]);
+            LT_MARK("k_ge_fill_dummy");
+            launches++;
         }
     }
-    const dim3 gu(cdiv(max_units, 128), NS), gu1(cdiv(max_units + 1, 128), NS);
+    const dim3 gu1(cdiv(max_units + 1, 128), NS);
     k_geb_classify<<<gb, 128, 0, st>>>(d_comps, d_scans, d_meta, d_evkey, d_tail, d_masks);
+    LT_MARK("k_geb_classify");
     size_t tb = cap_temp;
     cub::DeviceScan::ExclusiveScan(d_temp, tb, d_evkey, d_prev, cub::Max(), -1, (int)U, st);
+    LT_MARK("cub_scan");
     tb = cap_temp;
     cub::DeviceScan::ExclusiveSum(d_temp, tb, d_tail, d_tsum, (int)U, st);
+    LT_MARK("cub_scan");
     CU(cudaMemsetAsync(d_gcount, 0, U * 4, st));
+    LT_MARK("memset");
     k_ge_groups<<<gu1, 128, 0, st>>>(d_scans, d_meta, d_evkey, d_prev, d_tsum, d_gcount);
+    LT_MARK("k_ge_groups");
     CU(cudaMemsetAsync(d_hist, 0, (size_t)NS * 4 * 256 * 4, st));
+    LT_MARK("memset");
     k_geb_hist<<<dim3(cdiv(plan.max_comp_blocks, HIST_THREADS), NC), HIST_THREADS, 0, st>>>(d_comps, d_scans, d_gcount, d_hist, d_masks);
+    LT_MARK("k_geb_hist");
     k_ge_tables<<<NS * 4, 32, 0, st>>>(d_hist, d_tabs, d_dht);
+    LT_MARK("k_ge_tables");
     k_geb_len<<<gb, 128, 0, st>>>(d_comps, d_scans, d_gcount, d_tabs, d_bitlen, d_masks);
+    LT_MARK("k_geb_len");
     tb = cap_temp;
     cub::DeviceScan::ExclusiveSum(d_temp, tb, d_bitlen, d_bitoff, (int)U, st);
-    k_ge_totals<<<cdiv(NS, 128), 128, 0, st>>>(d_scans, NS, d_bitlen, d_bitoff, d_total);
-    CU(cudaMemcpyAsync(h_total, d_total, (size_t)NS * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaGetLastError());
-    CU(stream_wait(st));
-    // ---- sizes are known: lay out the stuffing stage
-    uint32_t groups = 0; size_t img_bytes_max = 0, img_bytes = 0; uint32_t max_groups = 0; long long max_words = 0;
-    for (int si = 0; si < NS; si++) {
-        if ((long long)((h_total[si] + 31) / 32) + 1 > plan.scans[si].word_cap) { err = "entropy-coded scan exceeds its device buffer"; overflow = true; return false; }
-        ScanOut &o = h_so[si];
-        o.total_bits = h_total[si]; o.nbytes = (h_total[si] + 7) / 8; o.ngroups = (o.nbytes + 15) / 16; o.group_base = groups;
-        groups += o.ngroups; max_groups = std::max(max_groups, o.ngroups); max_words = std::max<long long>(max_words, (h_total[si] + 31) / 32 + 1);
-        img_bytes += o.nbytes;
-        if ((si + 1) % plan.scans_per_image == 0) { img_bytes_max = std::max(img_bytes_max, img_bytes); img_bytes = 0; }
-    }
-    overflow = false;
-    out_stride = align_up(img_bytes_max * 2 + 64, 256);            // worst case: every byte stuffed
-    copy_bytes = std::min(out_stride, align_up(img_bytes_max + img_bytes_max / 8 + 256, 256));
-    c = cap_ff[0]; if (!grow(d_ffcount, c, (size_t)groups * 4 + 4, false, err)) return false; cap_ff[0] = c;
-    c = cap_ff[1]; if (!grow(d_ffoff, c, (size_t)groups * 4 + 4, false, err)) return false; cap_ff[1] = c;
-    c = cap_out; if (!grow(d_out, c, out_stride * nimages, false, err)) return false; cap_out = c;
-    c = cap_hout; if (!grow(h_out, c, copy_bytes * nimages, true, err)) return false; cap_hout = c;
-    size_t tb3 = 0; cub::DeviceScan::ExclusiveSum((void *)nullptr, tb3, d_ffcount, d_ffoff, (int)groups, st);
-    c = cap_temp; if (!grow(d_temp, c, tb3 + 256, false, err)) return false; cap_temp = c;
-    CU(cudaMemcpyAsync(d_so, h_so, (size_t)NS * sizeof(ScanOut), cudaMemcpyHostToDevice, st));
-    k_ge_zero<<<dim3(std::max(1, std::min(cdiv(max_words, 256), 256)), NS), 256, 0, st>>>(d_scans, d_so, d_words);
-    k_geb_emit<<<gb, 128, 0, st>>>(d_comps, d_scans, d_gcount, d_tabs, d_bitoff, d_words, d_masks);
-    if (groups) {
-        const dim3 gg(cdiv(max_groups, 128), NS);
-        k_ge_ffcount<<<gg, 128, 0, st>>>(d_scans, d_so, d_words, d_ffcount);
-        tb = cap_temp;
-        cub::DeviceScan::ExclusiveSum(d_temp, tb, d_ffcount, d_ffoff, (int)groups, st);
-        k_ge_layout<<<cdiv(nimages, 64), 64, 0, st>>>(d_so, plan.scans_per_image, nimages, d_ffcount, d_ffoff, d_outoff, d_outlen);
-        k_ge_scatter<<<gg, 128, 0, st>>>(d_scans, d_so, d_words, d_ffoff, d_outoff, d_out, plan.scans_per_image, out_stride);
-    } else {
-        k_ge_layout<<<cdiv(nimages, 64), 64, 0, st>>>(d_so, plan.scans_per_image, nimages, d_ffcount, d_ffoff, d_outoff, d_outlen);
-    }
-    CU(cudaMemcpyAsync(h_outlen, d_outlen, (size_t)NS * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h_dht, d_dht, (size_t)NS * 4 * sizeof(DhtOut), cudaMemcpyDeviceToHost, st));
-    for (int im = 0; im < nimages; im++) CU(cudaMemcpyAsync(h_out + (size_t)im * copy_bytes, d_out + (size_t)im * out_stride, copy_bytes, cudaMemcpyDeviceToHost, st));
-    CU(cudaGetLastError());
-    CU(stream_wait(st));
-    // rare: an image stuffed more than the copied margin -> fetch the rest
-    for (int im = 0; im < nimages; im++) {
-        size_t tot = 0; for (int k = 0; k < plan.scans_per_image; k++) tot += h_outlen[im * plan.scans_per_image + k];
-        if (tot > copy_bytes) {
-            c = cap_hout; // grow keeps no data: re-copy everything at full stride
-            std::vector<uint8_t> keep;  (void)keep;
-            if (!grow(h_out, c, out_stride * nimages, true, err)) return false; cap_hout = c;
-            copy_bytes = out_stride;
-            for (int j = 0; j < nimages; j++) CU(cudaMemcpyAsync(h_out + (size_t)j * copy_bytes, d_out + (size_t)j * out_stride, copy_bytes, cudaMemcpyDeviceToHost, st));
+    LT_MARK("cub_scan");
+    launches += 8;
+    return enqueue_back(st, err);
+}
+
+bool GpuEncoder::finish(void *stream_, bool fetch, std::string &err)
+{
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int NS = (int)plan.scans.size(), spi = plan.scans_per_image;
+    uint32_t *h_total = reinterpret_cast<uint32_t *>(h_small + o_total), *h_flags = reinterpret_cast<uint32_t *>(h_small + o_flags);
+    uint32_t *h_outlen = reinterpret_cast<uint32_t *>(h_small + o_outlen);
+    const DhtOut *h_dht = reinterpret_cast<const DhtOut *>(h_small + o_dht);
+    for (int attempt = 0;; attempt++) {
+        // sizes are on the host while the emit / stuffing kernels still run
+        if (fetch) { CU(event_wait((cudaEvent_t)ev_sizes)); } else { CU(stream_wait(st)); }
+        size_t img_max = 0, img = 0;
+        for (int si = 0; si < NS; si++) { img += (h_total[si] + 7) / 8; if ((si + 1) % spi == 0) { img_max = std::max(img_max, img); img = 0; } }
+        if (h_flags[0]) {                                       // the estimate was too small for the bit buffer: exact sizes, back half again
+            if (attempt >= 3) { err = "entropy encoder could not size its buffers"; return false; }
             CU(stream_wait(st));
-            break;
+            if (!size_back_buffers(img_max + img_max / 16 + 4096, err)) return false;
+            retries++;
+            if (!enqueue_back(st, err)) return false;
+            continue;
         }
+        if (fetch) {
+            copy_bytes = std::min(out_stride, align_up(img_max + img_max / 8 + 256, 256));
+            size_t c = cap_hout; if (!grow(h_out, c, copy_bytes * nimg, true, err)) return false; cap_hout = c;
+            for (int im = 0; im < nimg; im++) CU(cudaMemcpyAsync(h_out + (size_t)im * copy_bytes, d_out + (size_t)im * out_stride, copy_bytes, cudaMemcpyDeviceToHost, st));
+            CU(cudaGetLastError());
+            CU(stream_wait(st));
+        }
+        if (h_flags[4 + 4]) {                                   // an image stuffed past its output region (more 0xFF bytes than one in eight)
+            if (attempt >= 3) { err = "entropy encoder could not size its output"; return false; }
+            if (!size_back_buffers((size_t)h_flags[4 + 3] + 4096, err)) return false;
+            retries++;
+            if (!enqueue_back(st, err)) return false;
+            continue;
+        }
+        learned_image_bytes = std::max<size_t>(learned_image_bytes, h_flags[4 + 3]);
+        if (fetch) {   // rare: an image stuffed more than the copied margin -> fetch everything at full stride
+            bool shortc = false;
+            for (int im = 0; im < nimg && !shortc; im++) { size_t tot = 0; for (int k = 0; k < spi; k++) tot += h_outlen[im * spi + k]; shortc = tot > copy_bytes; }
+            if (shortc) {
+                size_t c = cap_hout; if (!grow(h_out, c, out_stride * nimg, true, err)) return false; cap_hout = c;
+                copy_bytes = out_stride;
+                for (int j = 0; j < nimg; j++) CU(cudaMemcpyAsync(h_out + (size_t)j * copy_bytes, d_out + (size_t)j * out_stride, copy_bytes, cudaMemcpyDeviceToHost, st));
+                CU(stream_wait(st));
+            }
+        }
+        break;
     }
     // ---- describe the result
     results.assign((size_t)NS, EncodedScan());
     for (int si = 0; si < NS; si++) {
         EncodedScan &e = results[si];
-        const int im = si / plan.scans_per_image, k = si % plan.scans_per_image;
+        const int im = si / spi, k = si % spi;
         e.def = plan.defs[k];
-        size_t off = 0; for (int j = 0; j < k; j++) off += h_outlen[im * plan.scans_per_image + j];
-        e.data = h_out + (size_t)im * copy_bytes + off; e.len = h_outlen[si];
-        bool need[2][2]; jpeg_scan_tables_needed(g, progressive, e.def, need);
+        size_t off = 0; for (int j = 0; j < k; j++) off += h_outlen[im * spi + j];
+        e.data = fetch ? h_out + (size_t)im * copy_bytes + off : nullptr; e.len = h_outlen[si];
+        bool need[2][2]; jpeg_scan_tables_needed(geom, prog, e.def, need);
         for (int kind = 0; kind < 2; kind++) for (int t = 0; t < 2; t++) {
             e.has_tab[kind][t] = need[kind][t];
             const DhtOut &D = h_dht[(size_t)si * 4 + kind * 2 + t];
@@ -463,6 +582,11 @@ bool GpuEncoder::encode(const JpegGeom &g, bool progressive, int16_t *const *d_c
         }
     }
     return true;
+}
+
+bool GpuEncoder::encode(const JpegGeom &g, bool progressive, int16_t *const *d_coefs, int nimages, void *stream_, bool fill_dummy, std::string &err, size_t out_bytes_hint)
+{
+    return prepare(g, progressive, d_coefs, nimages, stream_, out_bytes_hint, err) && enqueue(stream_, fill_dummy, err) && finish(stream_, true, err);
 }
 
 } // namespace b200

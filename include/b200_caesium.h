@@ -156,6 +156,25 @@ b200_status b200_jpeg_batch_download(b200_jpeg_batch *b, int index, int16_t *out
 b200_status b200_jpeg_batch_time(b200_jpeg_batch *b, int which, int iters, float *ms_per_run);
 void b200_jpeg_batch_destroy(b200_jpeg_batch *b);
 
+/* ---- device-resident FULL path (bench "value": scan bytes in HBM -> scan bytes in HBM) ------------------
+ * n baseline single-scan JPEGs of one shape: parsed and uploaded once at create; every run enqueues Huffman decode ->
+ * dequant/IDCT/resample/FDCT/quantise -> Huffman encode (optimal tables, stuffing) for all of them, `group` images per launch
+ * sequence, each group on its own stream, joined back into `cuda_stream`; no host wait inside run.  params as for
+ * b200_compress_in_memory (jpeg_optimize = 1: the lossless transcode, no transform). */
+typedef struct b200_jpeg_pipe b200_jpeg_pipe;
+b200_status b200_jpeg_pipe_create(const uint8_t *const *in, const size_t *in_len, int n, const b200_params *params, int group, b200_jpeg_pipe **pipe);
+/* which: 0 whole path, 1 entropy decode, 2 transform, 3 entropy encode (stage timing; 2 / 3 reuse the last whole run's data) */
+b200_status b200_jpeg_pipe_run(b200_jpeg_pipe *p, void *cuda_stream, int which, int *launches);
+/* after the caller has synchronised: out_sizes[n] = entropy-coded bytes per image; *not_settled = images the device decoder
+ * would hand to the host decoder; *enc_retries = encoder back halves repeated because an output estimate was too small */
+b200_status b200_jpeg_pipe_finish(b200_jpeg_pipe *p, size_t *out_sizes, int *not_settled, int *enc_retries);
+/* the complete output file of image `index` (for parity checks); after finish */
+b200_status b200_jpeg_pipe_fetch(b200_jpeg_pipe *p, int index, uint8_t **out, size_t *out_len);
+/* one group alone on its stream, an event after every launch: writes up to `cap` records "name ms_per_launch launches\n" into
+ * `text` (NUL-terminated); the per-kernel table behind bench.py's roofline object */
+b200_status b200_jpeg_pipe_kernel_times(b200_jpeg_pipe *p, int iters, char *text, size_t cap);
+void b200_jpeg_pipe_destroy(b200_jpeg_pipe *p);
+
 /* ---- PNG stage entry points (lossless path: libcaesium png::lossless -> oxipng, compressor.rs:428,436-437) ------- */
 /* Row-filter strategies (oxipng RowFilter order): 0 None 1 Sub 2 Up 3 Average 4 Paeth 5 MinSum 6 Entropy 7 Bigrams 8 BigEnt 9 Brute */
 /* host: parse + inflate + unfilter.  *raw (library-allocated) = height * row_bytes packed samples.  info: width, height,

@@ -53,3 +53,43 @@ def synth_jpeg(width, height, index=0, quality=90, subsampling="4:2:0", progress
     b = io.BytesIO()
     Image.fromarray(synth_rgb(width, height, index), "RGB").save(b, "JPEG", quality=quality, subsampling=subsampling, progressive=progressive)
     return b.getvalue()
+
+
+def synth_png_rgba(width, height, index=0, level=6):
+    """Source PNG as BASELINE config 4 specifies: the same generator + a smooth-gradient alpha channel (every
+    tenth image fully opaque), 8-bit RGBA, every row Paeth-filtered, zlib level 6, one IDAT."""
+    import struct
+    import zlib
+    rgb = synth_rgb(width, height, index)
+    rng = np.random.default_rng(SEED0 + 7919 * (index + 1))
+    if index % 10 == 9:
+        alpha = np.full((height, width), 255, np.uint8)
+    else:
+        gx, gy = rng.random() * 2 - 1, rng.random() * 2 - 1
+        x = np.arange(width, dtype=np.float32)[None, :] / max(width - 1, 1)
+        y = np.arange(height, dtype=np.float32)[:, None] / max(height - 1, 1)
+        a = 160.0 + 90.0 * (gx * (x - 0.5) + gy * (y - 0.5))
+        alpha = np.clip(a + 0.5, 0, 255).astype(np.uint8)
+    img = np.concatenate([rgb, alpha[:, :, None]], axis=2)
+    co = zlib.compressobj(level)
+    parts = []
+    strip = 128
+    prev = np.zeros((1, width, 4), np.int16)
+    for y0 in range(0, height, strip):
+        cur = img[y0:y0 + strip].astype(np.int16)
+        up = np.concatenate([prev, cur[:-1]], axis=0)
+        left = np.concatenate([np.zeros((cur.shape[0], 1, 4), np.int16), cur[:, :-1]], axis=1)
+        upleft = np.concatenate([np.zeros((cur.shape[0], 1, 4), np.int16), up[:, :-1]], axis=1)
+        p = left + up - upleft
+        pa, pb, pc = np.abs(p - left), np.abs(p - up), np.abs(p - upleft)
+        pred = np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, up, upleft))
+        f = ((cur - pred) & 0xFF).astype(np.uint8).reshape(cur.shape[0], width * 4)
+        rows = np.concatenate([np.full((cur.shape[0], 1), 4, np.uint8), f], axis=1)
+        parts.append(co.compress(rows.tobytes()))
+        prev = cur[-1:]
+    parts.append(co.flush())
+    z = b"".join(parts)
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+    return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", width, height, 8, 6, 0, 0, 0)) + chunk(b"IDAT", z) + chunk(b"IEND", b"")
