@@ -27,6 +27,7 @@
 #include "vp8_host.h"
 #include "webp_device.h"
 #include "jpeg_pipe.h"
+#include "topology.h"
 
 using namespace b200;
 
@@ -742,7 +743,7 @@ int b200_compress_batch(const uint8_t *const *in, const size_t *in_len, int n, c
     if (!in || !in_len || !params || !out || !out_len || !status || n < 0) return -1;
     if (n_threads <= 0) n_threads = usable_cores();
     if (n_threads > n) n_threads = n;
-    std::atomic<int> next{0}, failed{0}, chunk_id{0};
+    std::atomic<int> failed{0};
     { std::string e; ensure_runtime(e); }
     const int ndev = std::max(1, runtime_device_count());
     if (g_entropy_mode.load() < 0) { const char *e = getenv("B200_ENTROPY"); g_entropy_mode.store(!e ? 3 : !strcmp(e, "host") ? 0 : !strcmp(e, "gpuenc") ? 1 : !strcmp(e, "gpudec") ? 2 : 3); }
@@ -766,8 +767,10 @@ int b200_compress_batch(const uint8_t *const *in, const size_t *in_len, int n, c
         fn();
         for (auto &t : th) t.join();
     };
-    // phase 1: JPEGs, K at a time, on a few group workers (each group is one long launch sequence; more workers than this only
-    // queue behind each other on the GPU).  Whatever a group could not take is left for phase 2.
+    // phase 1: JPEGs, K at a time (one megabatch = one long launch sequence on one slot of one device).  Megabatches are sharded
+    // over the devices by bytes -- longest-processing-time-first: largest megabatch to the least loaded device --
+    // and every device gets its own workers, bound to the CPUs of the device's NUMA node; a worker whose device runs dry takes
+    // work from the most loaded one.  Whatever a megabatch could not take is left for phase 2.
     std::vector<int> rest;
     if (grouped) {
         std::vector<int> jpegs;
@@ -775,13 +778,32 @@ int b200_compress_batch(const uint8_t *const *in, const size_t *in_len, int n, c
         if (jpegs.size() < 2) { rest.insert(rest.end(), jpegs.begin(), jpegs.end()); jpegs.clear(); }
         const int nj = (int)jpegs.size();
         if (nj) {
+            const int nchunks = (nj + K - 1) / K;
+            std::vector<size_t> cbytes((size_t)nchunks, 0);
+            for (int c = 0; c < nchunks; c++) for (int j = c * K; j < std::min(nj, c * K + K); j++) cbytes[(size_t)c] += in_len[jpegs[(size_t)j]];
+            std::vector<int> order((size_t)nchunks); for (int c = 0; c < nchunks; c++) order[(size_t)c] = c;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cbytes[(size_t)a] > cbytes[(size_t)b]; });
+            std::vector<std::vector<int>> devq((size_t)ndev); std::vector<size_t> load((size_t)ndev, 0);
+            for (int c : order) { int d = 0; for (int e = 1; e < ndev; e++) if (load[(size_t)e] < load[(size_t)d]) d = e; devq[(size_t)d].push_back(c); load[(size_t)d] += cbytes[(size_t)c]; }
+            std::vector<std::atomic<int>> cursor((size_t)ndev); for (auto &c : cursor) c.store(0);
             std::mutex rest_mu;
             int max_workers = 16; { const char *e = getenv("B200_GROUP_WORKERS"); if (e) max_workers = std::max(1, std::min(32, atoi(e))); }
+            std::atomic<int> worker_id{0};
             auto group_worker = [&]() {
+                const int home = worker_id.fetch_add(1) % ndev;
+                AffinityGuard pin(runtime_device_ordinal(home));
                 for (;;) {
-                    const int j0 = next.fetch_add(K);
-                    if (j0 >= nj) break;
-                    const int j1 = std::min(nj, j0 + K), dev = chunk_id.fetch_add(1) % ndev;
+                    int dev = home, c = -1;
+                    { const int k = cursor[(size_t)home].fetch_add(1); if (k < (int)devq[(size_t)home].size()) c = devq[(size_t)home][(size_t)k]; }
+                    if (c < 0) {           // home queue empty: help the device with the most work left
+                        int best = -1, left = 0;
+                        for (int e = 0; e < ndev; e++) { const int l = (int)devq[(size_t)e].size() - cursor[(size_t)e].load(); if (l > left) { left = l; best = e; } }
+                        if (best < 0) break;
+                        const int k = cursor[(size_t)best].fetch_add(1);
+                        if (k >= (int)devq[(size_t)best].size()) continue;
+                        c = devq[(size_t)best][(size_t)k]; dev = best;
+                    }
+                    const int j0 = c * K, j1 = std::min(nj, j0 + K);
                     std::vector<int> idx(jpegs.begin() + j0, jpegs.begin() + j1);
                     std::vector<char> done(idx.size(), 0);
                     try { jpeg_compress_group(in, in_len, idx, params, dev, out, out_len, status, done); } catch (...) {}
@@ -791,7 +813,7 @@ int b200_compress_batch(const uint8_t *const *in, const size_t *in_len, int n, c
                     }
                 }
             };
-            run_threads(std::max(1, std::min(n_threads, std::min(max_workers, (nj + K - 1) / K))), group_worker);
+            run_threads(std::max(1, std::min(n_threads, std::min(max_workers * ndev, nchunks))), group_worker);
         }
     } else for (int i = 0; i < n; i++) rest.push_back(i);
     // phase 2: one image per call on every thread the caller allows (PNG, conversions' sources, progressive JPEGs, ...)
@@ -799,7 +821,12 @@ int b200_compress_batch(const uint8_t *const *in, const size_t *in_len, int n, c
         std::sort(rest.begin(), rest.end());
         std::atomic<int> nr{0};
         const int total = (int)rest.size();
-        run_threads(std::min(n_threads, total), [&]() { for (;;) { const int r = nr.fetch_add(1); if (r >= total) break; one(rest[r], rest[r] % ndev); } });
+        std::atomic<int> tid{0};
+        run_threads(std::min(n_threads, total), [&]() {
+            const int home = tid.fetch_add(1) % ndev;            // thread t serves device t % ndev from that device's NUMA node
+            AffinityGuard pin(runtime_device_ordinal(home));
+            for (;;) { const int r = nr.fetch_add(1); if (r >= total) break; one(rest[r], home); }
+        });
     }
     return failed.load();
 }
