@@ -68,7 +68,7 @@ _SYMBOLS = [
     "b200_jpeg_batch_time", "b200_jpeg_batch_destroy", "b200_jpeg_encode_coefficients_device",
     "b200_png_decode", "b200_png_decode_reduced", "b200_png_filter", "b200_png_lz77", "b200_png_deflate_tokens", "b200_png_level_strategies",
     "b200_webp_encode_rgb", "b200_webp_write_levels", "b200_webp_qindex",
-    "b200_jpeg_pipe_create", "b200_jpeg_pipe_run", "b200_jpeg_pipe_finish", "b200_jpeg_pipe_fetch", "b200_jpeg_pipe_kernel_times", "b200_jpeg_pipe_destroy",
+    "b200_jpeg_pipe_create", "b200_jpeg_pipe_run", "b200_jpeg_pipe_finish", "b200_jpeg_pipe_fetch", "b200_jpeg_pipe_kernel_times", "b200_jpeg_pipe_destroy", "b200_device_jobs", "b200_device_numa_node",
 ]
 
 
@@ -93,6 +93,7 @@ def lib():
         L.b200_free.argtypes = [C.c_void_p]
         L.b200_jpeg_batch_destroy.argtypes = [C.c_void_p]
         L.b200_jpeg_pipe_destroy.argtypes = [C.c_void_p]
+        L.b200_device_jobs.restype = C.c_longlong
         _lib = L
     return _lib
 

@@ -549,6 +549,90 @@ b200_status compress_dispatch(const uint8_t *in, size_t in_len, const b200_param
     }
 }
 
+// libcaesium compress_to_size: quality bisection in [1, 100] from 80, at most 10 tries, 2 % tolerance, the largest result under
+// the limit wins.  `size_at(q, keep)` runs one try: it returns the output size at quality q and, when `keep` says so (the try
+// is the best so far, or the smallest so far for return_smallest), leaves the file in `cur`.
+template <class SizeAt>
+static b200_status bisect_quality(SizeAt size_at, size_t max_output_size, bool return_smallest, uint32_t *quality_out, std::vector<uint8_t> &result)
+{
+    const size_t tolerance = max_output_size / 50;
+    int lo = 1, hi = 100, q = 80;
+    std::vector<uint8_t> best, smallest, cur; size_t best_size = 0, smallest_size = (size_t)-1;
+    for (int tries = 0; tries < 10 && lo <= hi; tries++) {
+        size_t sz = 0;
+        auto want = [&](size_t size) { return (size <= max_output_size && size > best_size) || (return_smallest && size < smallest_size); };
+        b200_status s = size_at(q, want, sz, cur);
+        if (s.code) return s;
+        if (sz < smallest_size) { smallest_size = sz; if (return_smallest) smallest = cur; }
+        if (sz <= max_output_size) {
+            if (sz > best_size) { best_size = sz; best.swap(cur); if (quality_out) *quality_out = (uint32_t)q; }
+            if (max_output_size - sz <= tolerance) break;
+            lo = q + 1;
+        } else hi = q - 1;
+        q = (lo + hi) / 2;
+    }
+    if (best_size) { result.swap(best); return ok_status(); }
+    if (return_smallest && !smallest.empty()) { result.swap(smallest); return ok_status(); }
+    return make_status(B200_ERR_TOO_LARGE, "Cannot compress to desired size");
+}
+
+// JPEG: the source is entropy-decoded ONCE, its coefficients stay in HBM, and every try re-runs only dequant/IDCT/resample/FDCT/
+// quantise at the try's tables plus the device Huffman encoder; the encoder reports the scan lengths from the device and the
+// stuffed bytes are fetched only for tries that become the answer ("decode once, re-quantise many").
+static b200_status jpeg_to_size(const uint8_t *in, size_t in_len, b200_params *params, size_t max_output_size, bool return_smallest, std::vector<uint8_t> &result)
+{
+    std::string err;
+    JpegReader rd(in, in_len);
+    if (!rd.read_header(err)) return header_status(err);
+    const JpegGeom &gin = rd.geom();
+    if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
+    if (g_entropy_mode.load() < 0) { const char *e = getenv("B200_ENTROPY"); g_entropy_mode.store(!e ? 3 : !strcmp(e, "host") ? 0 : !strcmp(e, "gpuenc") ? 1 : !strcmp(e, "gpudec") ? 2 : 3); }
+    if (params->width || params->height || (g_entropy_mode.load() & 1) == 0) {
+        // resize, or the host-entropy mode: every try is a whole compress call (the resized planes are not kept between tries)
+        auto size_at = [&](int q, auto want, size_t &sz, std::vector<uint8_t> &cur) {
+            b200_params p = *params; p.jpeg_quality = (uint32_t)q; p.jpeg_optimize = 0;
+            b200_status s = compress_dispatch(in, in_len, &p, -1, cur);
+            sz = cur.size(); (void)want;
+            return s;
+        };
+        return bisect_quality(size_at, max_output_size, return_smallest, &params->jpeg_quality, result);
+    }
+    Slot *s = slot_acquire(runtime_next_device(), err);
+    if (!s) return make_status(B200_ERR_CUDA, err);
+    b200_status st = ok_status();
+    do {
+        JpegGeom g0;
+        if (!jpeg_output_geom(gin, 80, (int)params->jpeg_chroma_subsampling, g0, err)) { st = make_status(B200_ERR_INVALID_ARGUMENT, err); break; }
+        ImagePlan plan;
+        if (!plan_image(gin, g0, plan, err)) { st = make_status(B200_ERR_UNSUPPORTED, err); break; }
+        if (!s->ensure(plan.in_bytes, plan.out_bytes, plan.scratch_bytes(), 1 << 14, err)) { st = make_status(B200_ERR_OUT_OF_MEMORY, err); break; }
+        bool resident = false;                      // coefficients already in s->d_in?
+        JpegReader::DeviceScan ds;
+        if ((g_entropy_mode.load() & 2) && rd.device_decodable(ds)) {
+            const int r = slot_gpu_decode(s, rd, ds, err);
+            if (r == 0) resident = true; else if (r != 1) { st = make_status(B200_ERR_CUDA, err); break; }
+        }
+        if (!resident && !rd.decode(s->h_in, err)) { st = make_status(B200_ERR_CORRUPT_INPUT, err); break; }
+        JpegWriteOptions wo; wo.progressive = params->jpeg_progressive != 0; wo.keep_metadata = params->keep_metadata != 0; wo.preserve_icc = params->jpeg_preserve_icc != 0;
+        auto size_at = [&](int q, auto want, size_t &sz, std::vector<uint8_t> &cur) -> b200_status {
+            JpegGeom gout; std::string e2;
+            if (!jpeg_output_geom(gin, q, (int)params->jpeg_chroma_subsampling, gout, e2)) return make_status(B200_ERR_INVALID_ARGUMENT, e2);
+            if (!slot_transform(s, gin, gout, e2, false, !resident)) return make_status(B200_ERR_CUDA, e2);
+            resident = true;                        // the first try uploaded them if the host decoded
+            if (!slot_gpu_encode_sizes(s, gout, wo.progressive, e2)) return make_status(B200_ERR_CUDA, e2);
+            sz = jpeg_assembled_size(gout, wo, &rd.meta(), s->enc->results.data(), (int)s->enc->results.size());
+            if (want(sz)) {
+                if (!slot_gpu_fetch(s, e2)) return make_status(B200_ERR_CUDA, e2);
+                if (!jpeg_assemble(gout, wo, &rd.meta(), s->enc->results.data(), (int)s->enc->results.size(), cur, e2)) return make_status(B200_ERR_INVALID_ARGUMENT, e2);
+            }
+            return ok_status();
+        };
+        st = bisect_quality(size_at, max_output_size, return_smallest, &params->jpeg_quality, result);
+    } while (0);
+    slot_release(s);
+    return st;
+}
+
 } // namespace
 
 extern "C" {
@@ -564,6 +648,8 @@ int b200_init(int n_gpus) { g_forced_ngpus = n_gpus; std::string e; return ensur
 int b200_init_device(int ordinal) { g_forced_device = ordinal; std::string e; return ensure_runtime(e) ? B200_OK : B200_ERR_NO_DEVICE; }
 void b200_shutdown(void) { print_trace(); runtime_shutdown(); }
 int b200_device_count(void) { return runtime_device_count(); }
+long long b200_device_jobs(int index) { return runtime_device_jobs(index); }
+int b200_device_numa_node(int index) { return index < 0 || index >= runtime_device_count() ? -1 : device_numa_node(runtime_device_ordinal(index)); }
 const char *b200_version(void) { return "b200-caesium 0.1.0 (sm_100a)"; }
 void b200_free(void *p) { free(p); }
 int b200_set_entropy_mode(int mode) { if (mode < 0 || mode > 3) return B200_ERR_INVALID_ARGUMENT; g_entropy_mode.store(mode); return B200_OK; }
@@ -711,29 +797,16 @@ b200_status b200_compress_to_size_in_memory(const uint8_t *in, size_t in_len, b2
     if (!in || !params || !out || !out_len) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr; *out_len = 0;
     try {
-        // libcaesium compress_to_size: input already small enough is returned unchanged; otherwise bisect quality in
-        // [1, 100] from 80 (at most 10 tries, 2 % tolerance), keeping the largest result under the limit.
+        // input already small enough is returned unchanged
         if (in_len <= max_output_size) { std::vector<uint8_t> v(in, in + in_len); return give(v, out, out_len); }
         uint32_t fmt = b200_sniff_format(in, in_len);
-        if (fmt != B200_FMT_JPEG) return make_status(fmt == B200_FMT_UNKNOWN ? B200_ERR_UNKNOWN_FORMAT : B200_ERR_UNSUPPORTED, "compress_to_size is implemented for JPEG only on the GPU path");
-        const size_t tolerance = max_output_size / 50;
-        int lo = 1, hi = 100, q = 80;
-        std::vector<uint8_t> best, smallest, cur;
-        for (int tries = 0; tries < 10 && lo <= hi; tries++) {
-            b200_params p = *params; p.jpeg_quality = (uint32_t)q; p.jpeg_optimize = 0;
-            b200_status s = compress_dispatch(in, in_len, &p, -1, cur);
-            if (s.code) return s;
-            if (smallest.empty() || cur.size() < smallest.size()) smallest = cur;
-            if (cur.size() <= max_output_size) {
-                if (cur.size() > best.size()) { best = cur; params->jpeg_quality = (uint32_t)q; }
-                if (max_output_size - cur.size() <= tolerance) break;
-                lo = q + 1;
-            } else hi = q - 1;
-            q = (lo + hi) / 2;
-        }
-        if (!best.empty()) return give(best, out, out_len);
-        if (return_smallest && !smallest.empty()) return give(smallest, out, out_len);
-        return make_status(B200_ERR_TOO_LARGE, "Cannot compress to desired size");
+        std::vector<uint8_t> result;
+        b200_status s;
+        if (fmt == B200_FMT_JPEG) s = jpeg_to_size(in, in_len, params, max_output_size, return_smallest != 0, result);
+        else if (fmt == B200_FMT_PNG) s = make_status(B200_ERR_UNSUPPORTED, "compress_to_size on a PNG bisects the lossy (imagequant) quality, which is outside the GPU path (route to caesium::compress_to_size_in_memory)");
+        else s = make_status(fmt == B200_FMT_UNKNOWN ? B200_ERR_UNKNOWN_FORMAT : B200_ERR_UNSUPPORTED, "compress_to_size for this format is outside the GPU path (route to caesium::compress_to_size_in_memory)");
+        if (s.code) return s;
+        return give(result, out, out_len);
     } catch (const std::exception &e) { return make_status(B200_ERR_OUT_OF_MEMORY, e.what()); } catch (...) { return make_status(B200_ERR_INVALID_ARGUMENT, "unexpected failure"); }
 }
 

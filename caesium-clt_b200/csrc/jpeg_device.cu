@@ -116,6 +116,7 @@ struct DevicePool {
     int ordinal = 0;
     std::mutex mu; std::condition_variable cv;
     std::vector<Slot *> free_slots; int created = 0; int max_slots = 48;
+    std::atomic<long long> jobs{0};             // slot acquisitions (a megabatch or a single image each)
 };
 std::mutex g_mu;
 std::vector<DevicePool *> g_devs;
@@ -174,6 +175,7 @@ void runtime_shutdown()
 }
 
 int runtime_device_count() { std::lock_guard<std::mutex> lk(g_mu); return g_inited ? (int)g_devs.size() : 0; }
+long long runtime_device_jobs(int i) { return g_devs.empty() || i < 0 || i >= (int)g_devs.size() ? 0 : g_devs[(size_t)i]->jobs.load(); }
 int runtime_device_ordinal(int i) { return g_devs.empty() ? 0 : g_devs[(size_t)i % g_devs.size()]->ordinal; }
 int runtime_next_device() { size_t n = g_devs.size(); return n ? (int)(g_rr.fetch_add(1) % n) : 0; }
 
@@ -181,6 +183,7 @@ Slot *slot_acquire(int prefer, std::string &err)
 {
     if (g_devs.empty()) { err = "library not initialised (no CUDA device)"; return nullptr; }
     DevicePool *d = g_devs[(size_t)prefer % g_devs.size()];
+    d->jobs++;
     std::unique_lock<std::mutex> lk(d->mu);
     for (;;) {
         if (!d->free_slots.empty()) { Slot *s = d->free_slots.back(); d->free_slots.pop_back(); lk.unlock(); cudaSetDevice(d->ordinal); return s; }
@@ -384,6 +387,14 @@ bool slot_gpu_encode(Slot *s, const JpegGeom &gout, bool progressive, std::strin
     int16_t *base = from_input ? s->d_in : s->d_out;
     return s->enc->encode(gout, progressive, &base, 1, s->stream, true, err);
 }
+
+bool slot_gpu_encode_sizes(Slot *s, const JpegGeom &gout, bool progressive, std::string &err)
+{
+    if (!s->enc) s->enc = new GpuEncoder();
+    int16_t *base = s->d_out;
+    return s->enc->prepare(gout, progressive, &base, 1, s->stream, 0, err) && s->enc->enqueue(s->stream, true, err) && s->enc->finish(s->stream, false, err);
+}
+bool slot_gpu_fetch(Slot *s, std::string &err) { return s->enc && s->enc->finish(s->stream, true, err); }
 
 bool slot_fetch_planes(Slot *s, uint8_t *const *d_planes, int nplanes, size_t n, uint8_t *host, std::string &err)
 {

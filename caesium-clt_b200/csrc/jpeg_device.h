@@ -62,6 +62,7 @@ int  runtime_device_count();
 Slot *slot_acquire(int prefer_dev, std::string &err);               // blocks while all slots of the device are busy
 void slot_release(Slot *s);
 int  runtime_next_device();                                         // round-robin shard assignment
+long long runtime_device_jobs(int dev_index);                       // slot acquisitions on that device so far
 int  runtime_device_ordinal(int dev_index);                         // CUDA ordinal of the library's device number dev_index
 
 // Run the transform for ONE image whose input coefficients already sit in s->h_in; result lands in s->h_out.
@@ -85,6 +86,9 @@ bool slot_encode_group(Slot *s, const JpegGeom &gout, bool progressive, const Gr
 bool slot_upload_out_coefs(Slot *s, size_t bytes, std::string &err);
 // Entropy-code the output coefficients sitting in s->d_out on the device; result in s->enc->results
 bool slot_gpu_encode(Slot *s, const JpegGeom &gout, bool progressive, std::string &err, bool from_input = false);
+// the same without fetching the stuffed scans (results carry lengths only); slot_gpu_fetch() brings them over afterwards
+bool slot_gpu_encode_sizes(Slot *s, const JpegGeom &gout, bool progressive, std::string &err);
+bool slot_gpu_fetch(Slot *s, std::string &err);
 // Resize path (CSParameters.width/height): gout carries the TARGET dimensions; decode -> RGB -> Lanczos3 -> YCbCr -> encode.
 // rgb_out != nullptr: stop after the resize and hand back the three device planes (R, G, B of the TARGET size, pitch = target
 // width; a greyscale source returns its single plane three times) -- the front end of the format-conversion paths.

@@ -830,6 +830,21 @@ bool jpeg_assemble_malloc(const JpegGeom &g, const JpegWriteOptions &opt, const 
     return true;
 }
 
+size_t jpeg_assembled_size(const JpegGeom &g, const JpegWriteOptions &opt, const JpegMeta *meta, const EncodedScan *scans, int nscans)
+{   // the length jpeg_assemble would produce, without touching the scans' bytes (compress_to_size only needs sizes for most tries)
+    std::vector<uint8_t> head; head.reserve(4096 + (meta ? meta->app_markers.size() + meta->icc_markers.size() : 0));
+    { ByteSink w(head); write_file_header(w, g, opt, meta); }
+    size_t total = head.size() + 2;
+    std::vector<uint8_t> pre;
+    for (int si = 0; si < nscans; si++) {
+        const EncodedScan &e = scans[si];
+        for (int t = 0; t < 2; t++) for (int kind = 0; kind < 2; kind++) if (e.has_tab[kind][t]) total += 2 + 2 + 1 + 16 + (size_t)e.nvals[kind][t];
+        pre.clear(); { ByteSink w(pre); write_sos(w, g, opt.progressive, e.def); }
+        total += pre.size() + e.len;
+    }
+    return total;
+}
+
 bool jpeg_assemble(const JpegGeom &g, const JpegWriteOptions &opt, const JpegMeta *meta, const EncodedScan *scans, int nscans,
                    std::vector<uint8_t> &out, std::string &err)
 {

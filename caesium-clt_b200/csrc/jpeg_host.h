@@ -106,6 +106,9 @@ struct EncodedScan {
 bool jpeg_assemble(const JpegGeom &g, const JpegWriteOptions &opt, const JpegMeta *meta, const EncodedScan *scans, int nscans,
                    std::vector<uint8_t> &out, std::string &err);
 
+// length of the file jpeg_assemble would write (scan data is not read)
+size_t jpeg_assembled_size(const JpegGeom &g, const JpegWriteOptions &opt, const JpegMeta *meta, const EncodedScan *scans, int nscans);
+
 bool jpeg_assemble_malloc(const JpegGeom &g, const JpegWriteOptions &opt, const JpegMeta *meta, const EncodedScan *scans, int nscans,
                           uint8_t **out, size_t *out_len, std::string &err);
 

@@ -79,6 +79,10 @@ int  b200_init(int n_gpus);
 int  b200_init_device(int device_ordinal);
 void b200_shutdown(void);
 int  b200_device_count(void);         /* devices the library is driving (0 before init / without GPU) */
+/* jobs (megabatches or single images) device `index` (0 .. b200_device_count()-1) has been handed so far, and the NUMA node its
+ * worker threads are bound to (-1: unknown / binding off) -- how b200_compress_batch's sharding can be observed */
+long long b200_device_jobs(int index);
+int  b200_device_numa_node(int index);
 const char *b200_version(void);
 void b200_free(void *p);
 /* Where JPEG entropy coding runs.  Bit 0: Huffman ENCODE on the device; bit 1: Huffman DECODE on the device (baseline

@@ -247,13 +247,75 @@ def test_megabatch_device_resident(L, O, golden):
     b.close()
 
 
-def test_compress_to_size(L, golden):
-    data = golden("in_420_base_640x480.jpg")
-    p = _params(L, 80, 420, True)
-    target = len(data) // 3
-    out = L.compress_to_size_in_memory(data, p, target)
-    assert len(out) <= target
+def _oracle_to_size(O, data, ss, prog, max_size, return_smallest=True):
+    """libcaesium's quality bisection restated around the oracle's lossy encoder (one full encode per try)."""
+    if len(data) <= max_size:
+        return data, None
+    tol = max_size // 50
+    lo, hi, q = 1, 100, 80
+    best = smallest = None
+    best_q = None
+    for _ in range(10):
+        if lo > hi:
+            break
+        cur = O.jpeg_lossy(data, O.params(q, ss, prog))
+        if smallest is None or len(cur) < len(smallest):
+            smallest = cur
+        if len(cur) <= max_size:
+            if best is None or len(cur) > len(best):
+                best, best_q = cur, q
+            if max_size - len(cur) <= tol:
+                break
+            lo = q + 1
+        else:
+            hi = q - 1
+        q = (lo + hi) // 2
+    if best is not None:
+        return best, best_q
+    return (smallest if return_smallest else None), None
+
+
+@pytest.mark.parametrize("name,ss,prog", [("in_420_base_640x480.jpg", 420, True), ("in_444_base_355x237.jpg", 0, True), ("in_420_prog_355x237.jpg", 420, False),
+                                          ("in_gray_base_355x237.jpg", 0, True)])
+def test_compress_to_size_decode_once_matches_oracle_bisection(L, O, golden, name, ss, prog):
+    """compress_to_size_in_memory (compressor.rs:295,298): the source is decoded once and only transform + encode re-run per
+    try; the file it answers with -- and the quality it leaves in the parameters -- are those of the restated bisection."""
+    data = golden(name)
+    for frac in (0.8, 0.45, 0.2, 0.07):
+        target = int(len(data) * frac)
+        p = _params(L, 80, ss, prog)
+        want, want_q = _oracle_to_size(O, data, ss, prog, target)
+        out = L.compress_to_size_in_memory(data, p, target)
+        assert out == want, (name, frac)
+        if want_q is not None:
+            assert p.jpeg_quality == want_q and len(out) <= target
+    p = _params(L, 80, ss, prog)
     assert L.compress_to_size_in_memory(data, p, len(data) + 10) == data
+    # unreachable size: smallest result with return_smallest, code 9 without
+    p = _params(L, 80, ss, prog)
+    tiny, _ = _oracle_to_size(O, data, ss, prog, 300)
+    assert L.compress_to_size_in_memory(data, p, 300, True) == tiny
+    with pytest.raises(L.B200Error) as e:
+        L.compress_to_size_in_memory(data, _params(L, 80, ss, prog), 300, False)
+    assert e.value.code == L.ERR_TOO_LARGE
+
+
+def test_compress_to_size_4k_costs_less_than_repeated_compress(L, O):
+    """Decode-once bisection on a 3840x2160 source: same answer as the restated bisection, and the whole call costs less than
+    the tries would as separate compress calls (each of which would parse, upload and entropy-decode the source again)."""
+    import time
+    from tools.synth import synth_jpeg
+    data = synth_jpeg(3840, 2160, 5)
+    target = len(data) // 4
+    p = _params(L, 80, 420, True)
+    L.compress_to_size_in_memory(data, p, target)          # warm buffers
+    p = _params(L, 80, 420, True)
+    t0 = time.perf_counter(); out = L.compress_to_size_in_memory(data, p, target); t_size = time.perf_counter() - t0
+    want, want_q = _oracle_to_size(O, data, 420, True, target)
+    assert out == want and p.jpeg_quality == want_q
+    t0 = time.perf_counter(); L.compress_in_memory(data, _params(L, 80, 420, True)); t_one = time.perf_counter() - t0
+    print(f"compress_to_size: {t_size * 1e3:.1f} ms for the bisection, one compress {t_one * 1e3:.1f} ms")
+    assert t_size < 10 * t_one
 
 
 def test_errors_do_not_abort(L, golden):
