@@ -254,11 +254,53 @@ def time_pipe(torch, dist, world, pipe, stream, steps, warmup, which=0):
     return float(t.item()), launches
 
 
+def jpeg_e2e(args, L, torch, dist, world, datas, params, threads, e2e_threads):
+    # ---- end to end through the C-ABI with host buffers
+    Be = args.e2e_batch
+    ework = [datas[i % len(datas)] for i in range(Be)]
+    bi = L.BatchInputs(ework)                                  # pointer/length arrays built once: the timed call is the C-ABI call
+    L.compress_batch(ework[:max(threads, 8)], params, e2e_threads, copy=False)      # warm slot pools / pinned buffers
+    for _ in range(max(2, args.warmup)):
+        L.compress_batch(bi, params, e2e_threads, copy=False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    out_bytes = 0
+    for _ in range(args.steps):
+        # copy=False: outputs are read where the library malloc'ed them (length + SOI marker) and freed; duplicating
+        # every file into a Python bytes object is ctypes overhead, not part of the C-ABI a host program calls
+        res = L.compress_batch(bi, params, e2e_threads, copy=False)
+        assert all(r[1] == 0 and r[3] == b"\xff\xd8" for r in res), [r[2] for r in res if r[1]][:1]
+        out_bytes = sum(r[0] for r in res)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    e2e_val = world * Be * MP_PER_IMAGE * args.steps / dt
+    in_bytes = sum(len(w) for w in ework)
+    e2e = {"value": round(e2e_val, 2), "unit": "MP/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+           "images_per_sec": round(e2e_val / MP_PER_IMAGE, 2), "images_per_step_per_gpu": Be, "host_threads": e2e_threads, "host_cores": threads,
+           "in_bytes_per_step": in_bytes, "out_bytes_per_step": out_bytes,
+           "megabatch": int(os.environ.get("B200_MEGABATCH", "8")), "group_workers": min(e2e_threads, int(os.environ.get("B200_GROUP_WORKERS", "16"))),
+           "note": "JPEG files in host memory -> JPEG files in host memory via b200_compress_batch (the batch form of start_compression's par_iter), all inside the timed region: marker parsing, pinned H2D of the entropy-coded scans, device Huffman decode, transform kernels, device Huffman encode (statistics, optimal tables, bit packing, stuffing), D2H of the scans, file assembly."}
+    return e2e
+
+
+def jpeg_e2e_only(args, L, torch, dist, world, datas, params, threads, e2e_threads):
+    e2e = jpeg_e2e(args, L, torch, dist, world, datas, params, threads, e2e_threads)
+    return {"value": e2e["value"], "ms_total": 0.0, "launches": 0, "roofline": None, "e2e": e2e, "not_settled": 0, "encoder_retries": 0, "out_bytes_per_image": 0, "in_bytes_per_image": 0}
+
+
 def jpeg_workload(args, L, torch, dist, world, rank, datas, params, lossless, threads, e2e_threads, with_kernels=True):
     """Resident full-path rate (`value`), per-kernel table, and the C-ABI rate (`e2e`) of one JPEG re-encode configuration."""
     px = W4K * H4K
     B = args.batch
     work = [datas[i % len(datas)] for i in range(B)]
+    if args.only_e2e:
+        return jpeg_e2e_only(args, L, torch, dist, world, datas, params, threads, e2e_threads)
     stream = torch.cuda.Stream()            # a real (non-NULL) stream: the pipe forks from / joins into it and the events are recorded on it
     pipe = L.JpegPipe(work, params, group=args.group)
     ms_total, launches = time_pipe(torch, dist, world, pipe, stream, args.steps, args.warmup)
@@ -302,37 +344,7 @@ def jpeg_workload(args, L, torch, dist, world, rank, datas, params, lossless, th
         except Exception:
             pass
 
-    # ---- end to end through the C-ABI with host buffers
-    Be = args.e2e_batch
-    ework = [datas[i % len(datas)] for i in range(Be)]
-    bi = L.BatchInputs(ework)                                  # pointer/length arrays built once: the timed call is the C-ABI call
-    L.compress_batch(ework[:max(threads, 8)], params, e2e_threads, copy=False)      # warm slot pools / pinned buffers
-    for _ in range(max(2, args.warmup)):
-        L.compress_batch(bi, params, e2e_threads, copy=False)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    out_bytes = 0
-    for _ in range(args.steps):
-        # copy=False: outputs are read where the library malloc'ed them (length + SOI marker) and freed; duplicating
-        # every file into a Python bytes object is ctypes overhead, not part of the C-ABI a host program calls
-        res = L.compress_batch(bi, params, e2e_threads, copy=False)
-        assert all(r[1] == 0 and r[3] == b"\xff\xd8" for r in res), [r[2] for r in res if r[1]][:1]
-        out_bytes = sum(r[0] for r in res)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    tt = torch.tensor([dt], device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dt = float(tt.item())
-    e2e_val = world * Be * MP_PER_IMAGE * args.steps / dt
-    in_bytes = sum(len(w) for w in ework)
-    e2e = {"value": round(e2e_val, 2), "unit": "MP/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-           "images_per_sec": round(e2e_val / MP_PER_IMAGE, 2), "images_per_step_per_gpu": Be, "host_threads": e2e_threads, "host_cores": threads,
-           "in_bytes_per_step": in_bytes, "out_bytes_per_step": out_bytes,
-           "megabatch": int(os.environ.get("B200_MEGABATCH", "8")), "group_workers": min(e2e_threads, int(os.environ.get("B200_GROUP_WORKERS", "16"))),
-           "note": "JPEG files in host memory -> JPEG files in host memory via b200_compress_batch (the batch form of start_compression's par_iter), all inside the timed region: marker parsing, pinned H2D of the entropy-coded scans, device Huffman decode, transform kernels, device Huffman encode (statistics, optimal tables, bit packing, stuffing), D2H of the scans, file assembly."}
+    e2e = jpeg_e2e(args, L, torch, dist, world, datas, params, threads, e2e_threads)
     return {"value": value, "ms_total": ms_total, "launches": launches, "roofline": roofline, "e2e": e2e,
             "not_settled": not_settled, "encoder_retries": retries, "out_bytes_per_image": s_out, "in_bytes_per_image": s_in}
 
@@ -398,6 +410,8 @@ def main():
     ap.add_argument("--webp-unique", type=int, default=8); ap.add_argument("--webp-batch", type=int, default=64)
     ap.add_argument("--cpu-seconds", type=float, default=6.0, help="minimum CPU work per cpu_baseline sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-threads", type=int, default=0, help="host threads per rank for the C-ABI leg (default: the rank's share of the usable cores, at least 8)")
+    ap.add_argument("--only-e2e", action="store_true", help="diagnostics: skip the device-resident leg and the per-kernel table")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -412,7 +426,7 @@ def main():
     png_datas = make_inputs(args.png_unique, 0, "png4096") if 3 in which else None
     webp_datas = make_inputs(args.webp_unique, 0, "jpeg24mp") if 4 in which else None
     # batch workers mostly wait for their stream: on a box with few cores per GPU a rank still keeps eight megabatches in flight
-    e2e_threads = max(threads, 8)
+    e2e_threads = args.e2e_threads if args.e2e_threads > 0 else max(threads, 8)
 
     import torch
     import torch.distributed as dist
@@ -484,6 +498,8 @@ def main():
             "decoder_not_settled": r1["not_settled"], "encoder_retries": r1["encoder_retries"],
             "configs": sub,
         }))
+    if os.environ.get("B200_TRACE"):
+        L.lib().b200_shutdown()             # prints the per-stage wall-clock table
     if world > 1:
         dist.destroy_process_group()
 

@@ -4,6 +4,9 @@
 // HBM buffers; images are sharded round-robin over the initialised GPUs (no cross-GPU traffic on this path).
 #include <cuda_runtime.h>
 #include <malloc.h>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <condition_variable>
 #include <cstring>
@@ -159,8 +162,10 @@ int runtime_init(int n_gpus, int only_device, std::string &err)
     return (int)g_devs.size();
 }
 
+static void print_group_trace();
 void runtime_shutdown()
 {
+    print_group_trace();
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto *d : g_devs) {
         cudaSetDevice(d->ordinal);
@@ -325,20 +330,43 @@ bool slot_transform_group(Slot *s, const JpegGeom *const *gins, const JpegGeom &
 // One megabatch, front to back, with ONE host wait that leaves the GPU idle (the last): entropy decode (fixed number of rounds,
 // flags read afterwards), transform, entropy encode (its sizes come back while the emit kernels run).  Round 1 waited three
 // times per megabatch with an empty stream behind each wait.
+// B200_TRACE: host wall-clock per megabatch, summed: staging (copy into pinned + tables), launching, the two waits
+static std::atomic<long long> g_grp_ns[5];
+static std::atomic<long long> g_grp_n{0};
+static const bool g_grp_trace = getenv("B200_TRACE") != nullptr;
+static void print_group_trace()
+{
+    const long long n = g_grp_n.load();
+    if (!g_grp_trace || !n) return;
+    static const char *names[] = {"stage inputs (memcpy to pinned, tables, H2D enqueue)", "enqueue decode + transform + encode (launch overhead)", "wait: sizes (GPU still busy)", "wait: final (after D2H enqueue)", "whole megabatch on the host"};
+    fprintf(stderr, "[b200 trace] %lld megabatches; mean host ms per megabatch:\n", n);
+    for (int i = 0; i < 5; i++) fprintf(stderr, "[b200 trace]   %-58s %8.3f\n", names[i], g_grp_ns[i].load() / 1e6 / (double)n);
+}
+
 bool slot_run_group(Slot *s, std::vector<GpuDecoder::Item> &items, const JpegGeom *const *gins, const JpegGeom &gout, const GroupLayout &L, bool progressive,
                     bool lossless, std::string &err)
 {
     if (!s->dec) s->dec = new GpuDecoder();
     if (!s->enc) s->enc = new GpuEncoder();
-    if (!s->dec->prepare(items, s->stream, err) || !s->dec->enqueue(s->stream, err)) return false;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!s->dec->prepare(items, s->stream, err)) return false;
+    const auto t1 = std::chrono::steady_clock::now();
+    if (!s->dec->enqueue(s->stream, err)) return false;
     if (!lossless && !slot_transform_group(s, gins, gout, L, err)) return false;
     std::vector<int16_t *> bases((size_t)L.K);
     for (int k = 0; k < L.K; k++) bases[k] = lossless ? reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(s->d_in) + L.in_stride * k)
                                                       : reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(s->d_out) + L.out_stride * k);
     // a re-encode at lower quality (or a transcode with optimal tables) does not grow: the inputs' entropy-coded size sizes the output buffers
     if (!s->enc->prepare(gout, progressive, bases.data(), L.K, s->stream, s->dec->raw_bytes(), err) || !s->enc->enqueue(s->stream, true, err)) return false;
+    const auto t2 = std::chrono::steady_clock::now();
     if (!s->enc->finish(s->stream, true, err)) return false;
     s->dec->finish(items);
+    if (g_grp_trace) {
+        const auto t3 = std::chrono::steady_clock::now();
+        auto ns = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count(); };
+        g_grp_ns[0] += ns(t0, t1); g_grp_ns[1] += ns(t1, t2); g_grp_ns[2] += (long long)(s->enc->wait_sizes_ms * 1e6); g_grp_ns[3] += (long long)(s->enc->wait_final_ms * 1e6);
+        g_grp_ns[4] += ns(t0, t3); g_grp_n++;
+    }
     return true;
 }
 

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include "jpeg_gpuenc.h"
 #include "stream_wait.h"
@@ -528,7 +529,9 @@ bool GpuEncoder::finish(void *stream_, bool fetch, std::string &err)
     const DhtOut *h_dht = reinterpret_cast<const DhtOut *>(h_small + o_dht);
     for (int attempt = 0;; attempt++) {
         // sizes are on the host while the emit / stuffing kernels still run
+        const auto tw0 = std::chrono::steady_clock::now();
         if (fetch) { CU(event_wait((cudaEvent_t)ev_sizes)); } else { CU(stream_wait(st)); }
+        wait_sizes_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count();
         size_t img_max = 0, img = 0;
         for (int si = 0; si < NS; si++) { img += (h_total[si] + 7) / 8; if ((si + 1) % spi == 0) { img_max = std::max(img_max, img); img = 0; } }
         if (h_flags[0]) {                                       // the estimate was too small for the bit buffer: exact sizes, back half again
@@ -544,7 +547,9 @@ bool GpuEncoder::finish(void *stream_, bool fetch, std::string &err)
             size_t c = cap_hout; if (!grow(h_out, c, copy_bytes * nimg, true, err)) return false; cap_hout = c;
             for (int im = 0; im < nimg; im++) CU(cudaMemcpyAsync(h_out + (size_t)im * copy_bytes, d_out + (size_t)im * out_stride, copy_bytes, cudaMemcpyDeviceToHost, st));
             CU(cudaGetLastError());
+            const auto tw1 = std::chrono::steady_clock::now();
             CU(stream_wait(st));
+            wait_final_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw1).count();
         }
         if (h_flags[4 + 4]) {                                   // an image stuffed past its output region (more 0xFF bytes than one in eight)
             if (attempt >= 3) { err = "entropy encoder could not size its output"; return false; }

@@ -30,6 +30,7 @@ public:
     bool enqueue(void *stream, bool fill_dummy, std::string &err);
     bool finish(void *stream, bool fetch, std::string &err);
     int retries = 0;            // back halves repeated because the output estimate was too small
+    double wait_sizes_ms = 0, wait_final_ms = 0;   // host time spent in finish()'s two waits (tracing)
     std::vector<EncodedScan> results;
     GpuEncPlan plan;
     bool overflow = false;      // the failure was "scan larger than its buffer": the caller may use the host encoder

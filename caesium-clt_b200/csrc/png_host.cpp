@@ -2,6 +2,7 @@
 // duties of oxipng 9.1.5 + libdeflate (Cargo.lock:1161, :917) behind libcaesium png::lossless: decode the source, keep
 // the chunks StripChunks::Safe keeps, and wrap the re-compressed image data.
 #include "png_host.h"
+#include "dfl_core.h"
 #include <emmintrin.h>
 #include <algorithm>
 #include <cstring>
@@ -515,137 +516,28 @@ struct BitOut {                 // LSB-first bit writer over a vector grown in b
     inline void flush() { if (n > 0) { o[pos++] = (uint8_t)acc; } acc = 0; n = 0; o.resize(pos); }
 };
 
-// length-limited Huffman code lengths: plain Huffman, then the IJG/zlib style overflow repair, then lengths handed out by rank
-void huff_lengths(const uint32_t *freq, int n, int limit, uint8_t *len)
-{
-    struct Node { uint64_t w; int l, r; };
-    std::vector<Node> nodes; std::vector<int> alive;
-    for (int i = 0; i < n; i++) { len[i] = 0; if (freq[i]) { nodes.push_back({freq[i], -1, i}); alive.push_back((int)nodes.size() - 1); } }
-    if (alive.empty()) return;
-    if (alive.size() == 1) { len[nodes[alive[0]].r] = 1; return; }
-    auto cmp = [&](int a, int b) { return nodes[a].w > nodes[b].w || (nodes[a].w == nodes[b].w && a > b); };
-    std::make_heap(alive.begin(), alive.end(), cmp);
-    while (alive.size() > 1) {
-        std::pop_heap(alive.begin(), alive.end(), cmp); int a = alive.back(); alive.pop_back();
-        std::pop_heap(alive.begin(), alive.end(), cmp); int b = alive.back(); alive.pop_back();
-        nodes.push_back({nodes[a].w + nodes[b].w, a, b});
-        alive.push_back((int)nodes.size() - 1); std::push_heap(alive.begin(), alive.end(), cmp);
-    }
-    // depths
-    std::vector<int> depth(nodes.size(), 0); std::vector<int> order;
-    std::vector<int> stack{alive[0]};
-    int bl[64] = {0};
-    std::vector<std::pair<uint32_t, int>> leaves;   // (freq, symbol)
-    while (!stack.empty()) {
-        int x = stack.back(); stack.pop_back();
-        if (nodes[x].l < 0) { bl[std::min(depth[x], 63)]++; leaves.push_back({freq[nodes[x].r], nodes[x].r}); }
-        else { depth[nodes[x].l] = depth[nodes[x].r] = depth[x] + 1; stack.push_back(nodes[x].l); stack.push_back(nodes[x].r); }
-    }
-    for (int i = 63; i > limit; i--) while (bl[i] > 0) {
-        int j = i - 2; while (bl[j] == 0) j--;
-        bl[i] -= 2; bl[i - 1]++; bl[j + 1] += 2; bl[j]--;
-    }
-    // most frequent symbols get the shortest lengths
-    std::sort(leaves.begin(), leaves.end(), [](const std::pair<uint32_t, int> &a, const std::pair<uint32_t, int> &b) { return a.first > b.first || (a.first == b.first && a.second < b.second); });
-    size_t k = 0;
-    for (int l = 1; l <= limit; l++) for (int c = 0; c < bl[l]; c++) len[leaves[k++].second] = (uint8_t)l;
-}
-
-void canon_codes(const uint8_t *len, int n, uint16_t *code)
-{   // RFC 1951 3.2.2, stored bit-reversed for LSB-first output
-    int cnt[16] = {0}, next[16];
-    for (int i = 0; i < n; i++) cnt[len[i]]++;
-    cnt[0] = 0; int c = 0;
-    for (int l = 1; l <= 15; l++) { c = (c + cnt[l - 1]) << 1; next[l] = c; }
-    for (int i = 0; i < n; i++) if (len[i]) {
-        int v = next[len[i]]++, r = 0;
-        for (int b = 0; b < len[i]; b++) if (v & (1 << b)) r |= 1 << (len[i] - 1 - b);
-        code[i] = (uint16_t)r;
-    }
-}
-
-inline int len_sym(int len) { int s = 0; while (s < 28 && kLenBase[s + 1] <= len) s++; return s; }
-inline int dist_sym(int d)      // RFC 1951 distance code of d = 1..32768 in closed form: two codes per power of two above 4
-{
-    const unsigned x = (unsigned)d - 1u;
-    if (x < 4u) return (int)x;
-    const int nb = 31 - __builtin_clz(x);
-    return 2 * nb + (int)((x >> (nb - 1)) & 1u);
-}
 } // namespace
 
 void deflate_tokens(const uint32_t *tok, size_t nt, uint32_t adler, std::vector<uint8_t> &out, size_t block_tokens)
-{
+{   // the block coder itself is dfl_core.h (shared with the device writer, png_deflate.cu); this is its sequential driver
     out.clear(); out.reserve(nt + nt / 4 + 1024);
     out.push_back(0x78); out.push_back(0xDA);
     BitOut bw(out);
-    static uint8_t lsym[259]; static bool init = false;
-    if (!init) { for (int l = 3; l <= 258; l++) lsym[l] = (uint8_t)len_sym(l); init = true; }
-    auto dsym = [&](int d) { return dist_sym(d); };
     size_t pos = 0;
     bw.reserve(64);
     if (nt == 0) { bw.put(1, 1); bw.put(1, 2); bw.put(0, 7); }
+    static thread_local dfl::BlockTables T; static thread_local dfl::HuffScratch S; static thread_local dfl::EmitTables E;
+    auto put = [&](uint32_t v, int k) { bw.put(v, k); };
     while (pos < nt) {
         const size_t end = std::min(nt, pos + block_tokens);
-        uint32_t lf[286] = {0}, df[30] = {0};
-        for (size_t i = pos; i < end; i++) {
-            const uint32_t t = tok[i];
-            if (t & 0x80000000u) { lf[257 + lsym[((t >> 16) & 0xFF) + 3]]++; df[dsym((int)(t & 0xFFFF) + 1)]++; } else lf[t & 0xFF]++;
-        }
-        lf[256] = 1;
-        uint8_t ll[286], dl[30]; uint16_t lc[286], dc[30];
-        huff_lengths(lf, 286, 15, ll); huff_lengths(df, 30, 15, dl);
-        int ndist = 0; for (int i = 0; i < 30; i++) if (dl[i]) ndist++;
-        if (ndist == 0) dl[0] = 1;                          // at least one distance code must be described
-        canon_codes(ll, 286, lc); canon_codes(dl, 30, dc);
-        int hlit = 286; while (hlit > 257 && !ll[hlit - 1]) hlit--;
-        int hdist = 30; while (hdist > 1 && !dl[hdist - 1]) hdist--;
-        // run-length code the two length arrays (RFC 1951 3.2.7)
-        uint8_t seq[320]; int ns = 0;
-        for (int i = 0; i < hlit; i++) seq[ns++] = ll[i];
-        for (int i = 0; i < hdist; i++) seq[ns++] = dl[i];
-        struct Cl { uint8_t sym, extra; }; Cl cls[320]; int ncl = 0; uint32_t cf[19] = {0};
-        for (int i = 0; i < ns;) {
-            int v = seq[i], run = 1; while (i + run < ns && seq[i + run] == v) run++;
-            int left = run;
-            if (v == 0) {
-                while (left >= 11) { int r = std::min(left, 138); cls[ncl++] = {18, (uint8_t)(r - 11)}; cf[18]++; left -= r; }
-                if (left >= 3) { cls[ncl++] = {17, (uint8_t)(left - 3)}; cf[17]++; left = 0; }
-                while (left--) { cls[ncl++] = {0, 0}; cf[0]++; }
-            } else {
-                cls[ncl++] = {(uint8_t)v, 0}; cf[v]++; left--;
-                while (left >= 3) { int r = std::min(left, 6); cls[ncl++] = {16, (uint8_t)(r - 3)}; cf[16]++; left -= r; }
-                while (left-- > 0) { cls[ncl++] = {(uint8_t)v, 0}; cf[v]++; }
-            }
-            i += run;
-        }
-        uint8_t cll[19]; uint16_t clc[19];
-        huff_lengths(cf, 19, 7, cll); canon_codes(cll, 19, clc);
-        int hclen = 19; while (hclen > 4 && !cll[kClOrder[hclen - 1]]) hclen--;
+        uint32_t lf[dfl::NLIT] = {0}, df[dfl::NDIST] = {0};
+        for (size_t i = pos; i < end; i++) dfl::token_count(tok[i], lf, df);
+        dfl::build_block_tables(lf, df, T, S);
         bw.reserve(512 + (end - pos) * 6);                  // header < 400 bytes; a token is at most 15 + 5 + 15 + 13 bits
-        bw.put(end == nt ? 1 : 0, 1); bw.put(2, 2);
-        bw.put((uint32_t)(hlit - 257), 5); bw.put((uint32_t)(hdist - 1), 5); bw.put((uint32_t)(hclen - 4), 4);
-        for (int i = 0; i < hclen; i++) bw.put(cll[kClOrder[i]], 3);
-        for (int i = 0; i < ncl; i++) {
-            bw.put(clc[cls[i].sym], cll[cls[i].sym]);
-            if (cls[i].sym == 16) bw.put(cls[i].extra, 2); else if (cls[i].sym == 17) bw.put(cls[i].extra, 3); else if (cls[i].sym == 18) bw.put(cls[i].extra, 7);
-        }
-        // per-block emit tables: literal -> (code, bits); match length 3..258 -> code and extra bits as one piece (<= 20 bits)
-        uint32_t lit_cb[256], len_cb[256]; uint8_t lit_nb[256], len_nb[256];
-        for (int c = 0; c < 256; c++) { lit_cb[c] = lc[c]; lit_nb[c] = ll[c]; }
-        for (int l = 3; l <= 258; l++) {
-            const int ls = lsym[l], sym = 257 + ls;
-            len_cb[l - 3] = (uint32_t)lc[sym] | ((uint32_t)(l - kLenBase[ls]) << ll[sym]); len_nb[l - 3] = (uint8_t)(ll[sym] + kLenExtra[ls]);
-        }
-        for (size_t i = pos; i < end; i++) {
-            const uint32_t t = tok[i];
-            if (t & 0x80000000u) {
-                const int li = (int)((t >> 16) & 0xFF), d = (int)(t & 0xFFFF) + 1, ds = dsym(d);
-                const uint64_t dpiece = (uint64_t)dc[ds] | ((uint64_t)(d - kDistBase[ds]) << dl[ds]);                  // <= 15 + 13 bits
-                bw.put((uint64_t)len_cb[li] | (dpiece << len_nb[li]), len_nb[li] + dl[ds] + kDistExtra[ds]);           // <= 20 + 28 bits
-            } else bw.put(lit_cb[t & 0xFF], lit_nb[t & 0xFF]);
-        }
-        bw.put(lc[256], ll[256]);
+        dfl::write_block_header(T, end == nt, put);
+        for (int i = 0; i < 256; i++) dfl::fill_emit_entry(T, E, i);
+        for (size_t i = pos; i < end; i++) { uint32_t nb; const uint64_t piece = dfl::token_piece(E, tok[i], &nb); bw.put(piece, (int)nb); }
+        bw.put(E.eob_code, E.eob_len);
         pos = end;
     }
     bw.reserve(16);

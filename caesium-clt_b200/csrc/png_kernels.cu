@@ -204,6 +204,88 @@ __global__ void k_png_repack(const uint8_t *__restrict__ raw, uint8_t *__restric
     for (int c = 0; c < channels; c++) if (keep_mask & (1 << c)) q[o++] = p[c];
 }
 
+// ---- un-filtering (PNG 9.2 reconstruction) on the device ------------------------------------------------------------------------
+// Reconstruction is the one sequential piece of PNG: Sub / Average / Paeth need the reconstructed pixel to the left, Up / Average /
+// Paeth the reconstructed row above.  Swept as a wavefront: one warp owns 32 consecutive rows, lane l works on row 32 g + l, and
+// at step t it reconstructs pixel t - l of its row -- one pixel behind the lane above, so what it needs from the row above (pixel
+// x and pixel x - 1) are that lane's results of the previous two steps and arrive by shuffle.  Lane 0's "row above" is the last
+// row of the previous group, read back from HBM behind that group's progress counter; groups are handed out by an atomic ticket,
+// so a waiting warp only ever waits for a warp that is already running (the K8 pattern).  BPP = filter distance in bytes (1..8).
+template <int BPP>
+__global__ void __launch_bounds__(32) k_png_unfilter(const uint8_t *__restrict__ filt, uint8_t *raw, int h, int rb, uint32_t *__restrict__ ticket,
+                                                     volatile uint32_t *__restrict__ progress, uint32_t *__restrict__ bad)
+{
+    const int lane = threadIdx.x;
+    int g = 0;
+    if (lane == 0) g = (int)atomicAdd(ticket, 1u);
+    g = __shfl_sync(0xFFFFFFFFu, g, 0);
+    const int y = g * 32 + lane;
+    const bool live = y < h;
+    const int npix = (rb + BPP - 1) / BPP;
+    const uint8_t *f = filt + (size_t)(live ? y : 0) * (rb + 1);
+    uint8_t *r = raw + (size_t)(live ? y : 0) * rb;
+    const uint8_t *above = y > 0 ? raw + (size_t)(y - 1) * rb : nullptr;       // lane 0 only reads it
+    const int ft = live ? f[0] : 0;
+    if (live && ft > 4) atomicOr(bad, 1u);
+    f++;
+    int a[BPP], b[BPP], c[BPP];
+#pragma unroll
+    for (int k = 0; k < BPP; k++) a[k] = b[k] = c[k] = 0;
+    uint32_t known = 0;                                   // pixels of the row above known to be finished (lane 0)
+    const int steps = npix + 31;
+    for (int t = 0; t < steps; t++) {
+        const int x = t - lane;
+        const bool on = live && x >= 0 && x < npix;
+        // the row above: lane l - 1's pixel of the previous step; lane 0 fetches it from the previous group's last row
+        int up[BPP];
+#pragma unroll
+        for (int k = 0; k < BPP; k++) up[k] = __shfl_up_sync(0xFFFFFFFFu, a[k], 1);
+        if (lane == 0) {
+            if (on && above) {
+                while (known <= (uint32_t)x) { known = progress[g - 1]; if (known <= (uint32_t)x) __nanosleep(40); }
+                __threadfence();
+#pragma unroll
+                for (int k = 0; k < BPP; k++) up[k] = x * BPP + k < rb ? __ldcg(above + x * BPP + k) : 0;      // L2: this SM's L1 may hold the line from before it was written
+            } else {
+#pragma unroll
+                for (int k = 0; k < BPP; k++) up[k] = 0;
+            }
+        }
+        if (on) {
+#pragma unroll
+            for (int k = 0; k < BPP; k++) { c[k] = b[k]; b[k] = up[k]; }
+            const int o = x * BPP;
+#pragma unroll
+            for (int k = 0; k < BPP; k++) if (o + k < rb) {
+                const int p = ft == 0 ? 0 : ft == 1 ? a[k] : ft == 2 ? b[k] : ft == 3 ? ((a[k] + b[k]) >> 1) : paeth_pred(a[k], b[k], c[k]);
+                a[k] = (f[o + k] + p) & 0xFF;
+                r[o + k] = (uint8_t)a[k];
+            }
+        }
+        // the last live lane publishes its progress for the next group
+        if (lane == 31 && on && ((x & 15) == 15 || x == npix - 1)) { __threadfence(); progress[g] = (uint32_t)(x + 1); }
+    }
+}
+
+// ---- palette probe: does the image have at most 256 distinct pixel values?  (8-bit RGB / RGBA; oxipng reduction::palette) -----------
+// Open-addressing set of 1024 slots in global memory; the kernel gives up as soon as the 257th value appears, which for a
+// photograph is within the first few hundred pixels of every CTA.  flags[2] = distinct values found (saturates above 256).
+__global__ void k_png_colours(const uint8_t *__restrict__ raw, size_t npix, int channels, unsigned long long *__restrict__ set /*1024 slots, zeroed*/, uint32_t *__restrict__ flags)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+        if (*(volatile uint32_t *)&flags[2] > 256u) return;
+        const uint8_t *p = raw + i * channels;
+        const uint32_t v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)(channels == 4 ? p[3] : 255) << 24);
+        const unsigned long long key = (1ull << 32) | v;                            // never zero: zero marks an empty slot
+        uint32_t hslot = (v * 2654435761u) >> 22;
+        for (int probe = 0; probe < 1024; probe++, hslot = (hslot + 1) & 1023u) {
+            unsigned long long cur = *(volatile unsigned long long *)&set[hslot];
+            if (cur == 0ull) { cur = atomicCAS(&set[hslot], 0ull, key); if (cur == 0ull) { atomicAdd(&flags[2], 1u); break; } }
+            if (cur == key) break;
+        }
+    }
+}
+
 static inline unsigned cdivu(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
 int launch_png_filter(const uint8_t *d_raw, uint8_t *d_filt, int h, int rb, int bpp, int strategy, const uint32_t *d_tlog, void *stream)
@@ -237,6 +319,29 @@ int launch_png_adler(const uint8_t *d_filt, size_t n, unsigned long long *d_sums
 int launch_png_probe(const uint8_t *d_raw, size_t npixels, int channels, uint32_t *d_flags, void *stream)
 {
     k_png_probe<<<cdivu(npixels, 256), 256, 0, (cudaStream_t)stream>>>(d_raw, npixels, channels, d_flags);
+    return (int)cudaGetLastError();
+}
+int launch_png_unfilter(const uint8_t *d_filt, uint8_t *d_raw, int h, int rb, int bpp, uint32_t *d_sync /*2 + ceil(h/32) words*/, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    const int groups = (h + 31) / 32;
+    cudaMemsetAsync(d_sync, 0, (size_t)(groups + 2) * 4, st);
+    uint32_t *ticket = d_sync, *bad = d_sync + 1, *progress = d_sync + 2;
+    switch (bpp) {
+        case 1: k_png_unfilter<1><<<groups, 32, 0, st>>>(d_filt, d_raw, h, rb, ticket, progress, bad); break;
+        case 2: k_png_unfilter<2><<<groups, 32, 0, st>>>(d_filt, d_raw, h, rb, ticket, progress, bad); break;
+        case 3: k_png_unfilter<3><<<groups, 32, 0, st>>>(d_filt, d_raw, h, rb, ticket, progress, bad); break;
+        case 4: k_png_unfilter<4><<<groups, 32, 0, st>>>(d_filt, d_raw, h, rb, ticket, progress, bad); break;
+        case 6: k_png_unfilter<6><<<groups, 32, 0, st>>>(d_filt, d_raw, h, rb, ticket, progress, bad); break;
+        case 8: k_png_unfilter<8><<<groups, 32, 0, st>>>(d_filt, d_raw, h, rb, ticket, progress, bad); break;
+        default: return (int)cudaErrorInvalidValue;
+    }
+    return (int)cudaGetLastError();
+}
+int launch_png_colours(const uint8_t *d_raw, size_t npixels, int channels, uint32_t *d_set /*2048 words, 8-byte aligned*/, uint32_t *d_flags, void *stream)
+{
+    cudaMemsetAsync(d_set, 0, 2048 * 4, (cudaStream_t)stream);
+    k_png_colours<<<296, 256, 0, (cudaStream_t)stream>>>(d_raw, npixels, channels, reinterpret_cast<unsigned long long *>(d_set), d_flags);
     return (int)cudaGetLastError();
 }
 int launch_png_repack(const uint8_t *d_raw, uint8_t *d_out, size_t npixels, int channels, int keep_mask, void *stream)

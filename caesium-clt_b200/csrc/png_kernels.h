@@ -26,6 +26,10 @@ int launch_png_compact(const uint32_t *d_tokens, const uint32_t *d_counts, const
 int launch_png_adler(const uint8_t *d_filt, size_t n, unsigned long long *d_sums, void *stream);
 // alpha / grey reduction probes: flags[0] |= 1 if some alpha != 255 (8-bit RGBA / GA), flags[1] |= 1 if some pixel has r != g or g != b
 int launch_png_probe(const uint8_t *d_raw, size_t npixels, int channels, uint32_t *d_flags, void *stream);
+// wavefront un-filtering: filtered [h][rb + 1] -> raw [h][rb]; d_sync[1] != 0 afterwards = a row had a filter type > 4
+int launch_png_unfilter(const uint8_t *d_filt, uint8_t *d_raw, int h, int rb, int bpp, uint32_t *d_sync /*2 + ceil(h/32) words*/, void *stream);
+// palette probe (8-bit RGB / RGBA): flags[2] = number of distinct pixel values, saturating above 256
+int launch_png_colours(const uint8_t *d_raw, size_t npixels, int channels, uint32_t *d_set /*2048 words*/, uint32_t *d_flags, void *stream);
 // repack pixels keeping `keep_mask` channels (bit c = keep channel c) : 8-bit samples only
 int launch_png_repack(const uint8_t *d_raw, uint8_t *d_out, size_t npixels, int channels, int keep_mask, void *stream);
 
