@@ -250,7 +250,7 @@ void jpeg_compress_group(const uint8_t *const *in, const size_t *in_len, const s
         const int i = idx[k];
         if (b200_sniff_format(in[i], in_len[i]) != B200_FMT_JPEG) continue;
         rd[k].reset(new JpegReader(in[i], in_len[i]));
-        if (!rd[k]->read_header(err) || !rd[k]->device_decodable(ds[k])) continue;
+        if (!rd[k]->read_header(err) || !rd[k]->device_decodable(ds[k], true)) continue;      // the entropy-coded segment is walked on the device
         if (!members.empty()) {
             const JpegGeom &a = rd[members[0]]->geom(), &b = rd[k]->geom();
             bool same = a.width == b.width && a.height == b.height && a.ncomp == b.ncomp;
@@ -310,29 +310,36 @@ b200_status png_compress(const uint8_t *in, size_t in_len, const b200_params *p,
     if (!p->png_optimize) return make_status(B200_ERR_UNSUPPORTED, "lossy PNG (imagequant) is outside the GPU path (route to caesium::compress_in_memory)");
     if (p->width || p->height) return make_status(B200_ERR_UNSUPPORTED, "PNG resize is outside the GPU path (route to caesium::compress_in_memory)");
     std::string err;
-    PngInfo info; std::vector<uint8_t> raw;
+    PngInfo info; PngIdat idat;
     static const bool verbose = getenv("B200_TRACE") && atoi(getenv("B200_TRACE")) >= 2;
     const auto t0 = std::chrono::steady_clock::now();
-    if (!png_decode(in, in_len, p->keep_metadata != 0, info, raw, err)) return make_status(err.find("interlace") != std::string::npos ? B200_ERR_UNSUPPORTED : B200_ERR_CORRUPT_INPUT, err);
-    const auto t1 = std::chrono::steady_clock::now();
+    if (!png_parse_chunks(in, in_len, p->keep_metadata != 0, info, idat, err)) return make_status(err.find("interlace") != std::string::npos ? B200_ERR_UNSUPPORTED : B200_ERR_CORRUPT_INPUT, err);
     if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
-    png_reduce_palette(info, raw);                   // <= 256 colours: indexed samples go to the device (oxipng reduction::palette)
     Slot *s = slot_acquire(prefer_dev < 0 ? runtime_next_device() : prefer_dev, err);
     if (!s) return make_status(B200_ERR_CUDA, err);
     if (!s->png) s->png = new PngDevice();
+    // the IDAT stream is inflated straight into the slot's pinned staging buffer; from there on everything is device work
+    // (un-filter, checksum, reductions, filter trials, LZ77, DEFLATE coding) until the finished zlib stream comes back
+    const size_t nin = (info.row_bytes + 1) * (size_t)info.height;
+    size_t cap = 0, got = 0; uint32_t stored_adler = 0;
+    uint8_t *buf = s->png->input_buffer(nin, cap, err);
+    if (!buf) { slot_release(s); return make_status(B200_ERR_OUT_OF_MEMORY, err); }
+    if (!zlib_inflate_to(idat.p, idat.n, buf, cap, nin, &got, &stored_adler, err)) { slot_release(s); return make_status(B200_ERR_CORRUPT_INPUT, err); }
+    if (got < nin) { slot_release(s); return make_status(B200_ERR_CORRUPT_INPUT, "IDAT too short"); }
+    const auto t1 = std::chrono::steady_clock::now();
     std::vector<uint8_t> z;
     int level = (int)p->png_optimization_level; if (level > 6) level = 6;
-    const auto t2 = std::chrono::steady_clock::now();
-    const bool ok = s->png->compress(info, raw, level, s->stream, z, nullptr, err);
+    const bool ok = s->png->compress_filtered(info, got, stored_adler, level, s->stream, z, nullptr, err);
+    const bool corrupt = s->png->corrupt;
     const double deflate_ms = s->png->last_deflate_ms;
     slot_release(s);
-    if (!ok) return make_status(B200_ERR_CUDA, err);
+    if (!ok) return make_status(corrupt ? B200_ERR_CORRUPT_INPUT : B200_ERR_CUDA, err);
     const auto t3 = std::chrono::steady_clock::now();
     png_write(info, z, out);
     if (verbose) {
         auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-        fprintf(stderr, "[b200 trace] png %ux%u: host inflate+unfilter %.1f ms, slot wait %.1f ms, device filter/LZ77 + host Huffman %.1f ms (Huffman %.1f), container %.1f ms\n",
-                info.width, info.height, ms(t0, t1), ms(t1, t2), ms(t2, t3), deflate_ms, ms(t3, std::chrono::steady_clock::now()));
+        fprintf(stderr, "[b200 trace] png %ux%u: parse + inflate %.1f ms, device (un-filter, filter trials, LZ77, DEFLATE coding; host Huffman %.1f) %.1f ms, container %.1f ms\n",
+                info.width, info.height, ms(t0, t1), deflate_ms, ms(t1, t3), ms(t3, std::chrono::steady_clock::now()));
     }
     return ok_status();
 }

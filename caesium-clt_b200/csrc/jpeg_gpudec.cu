@@ -13,6 +13,7 @@
 #include "jpeg_gpuenc_plan.h"
 #include "stream_wait.h"
 #include "launch_timer.h"
+#include "host_copy.h"
 
 namespace b200 {
 
@@ -21,26 +22,40 @@ using namespace gd;
 #define CUD(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(e_); return false; } } while (0)
 
 // ---- un-stuffing: drop the 0x00 that follows every 0xFF -----------------------------------------------------------------
-__global__ void k_gd_unstuff_count(const DecImage *__restrict__ imgs, const uint8_t *__restrict__ raw_all, uint32_t *__restrict__ cnt)
+__global__ void k_gd_unstuff_count(const DecImage *__restrict__ imgs, const uint8_t *__restrict__ raw_all, uint32_t *__restrict__ cnt, uint32_t *__restrict__ marker)
 {
     const DecImage &im = imgs[blockIdx.y];
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= im.ngrp) return;
     const uint8_t *raw = raw_all + im.raw_off;
-    uint32_t c = 0;
-    for (uint32_t j = g * 16; j < g * 16 + 16 && j < im.nraw; j++) c += (j > 0 && raw[j] == 0 && raw[j - 1] == 0xFF);
+    uint32_t c = 0; bool mark = false;
+    for (uint32_t j = g * 16; j < g * 16 + 16 && j < im.nraw; j++) {
+        c += (j > 0 && raw[j] == 0 && raw[j - 1] == 0xFF);
+        // an 0xFF followed by anything but the stuffed zero is a marker (RSTn, DNL, a second image's EOI ...) or fill: not ours
+        mark |= im.verify && raw[j] == 0xFF && j + 1 < im.nraw && raw[j + 1] != 0x00;
+    }
     cnt[im.grp_off + g] = c;
+    if (mark) marker[blockIdx.y] = 1;
 }
-__global__ void k_gd_unstuff_scatter(const DecImage *__restrict__ imgs, const uint8_t *__restrict__ raw_all, const uint32_t *__restrict__ off, uint8_t *__restrict__ stream_all)
+// (for images the host did not walk, the thread of the last group also publishes the true stream length: g.nbits and g.nsub in
+// the device copy of the descriptor were upper bounds taken from the raw length)
+__global__ void k_gd_unstuff_scatter(DecImage *imgs, const uint8_t *__restrict__ raw_all, const uint32_t *__restrict__ off, const uint32_t *__restrict__ cnt, uint8_t *__restrict__ stream_all)
 {
-    const DecImage &im = imgs[blockIdx.y];
+    DecImage &im = imgs[blockIdx.y];
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= im.ngrp) return;
     const uint8_t *raw = raw_all + im.raw_off;
     uint8_t *out = stream_all + im.stream_off;
     uint32_t o = g * 16 - (off[im.grp_off + g] - off[im.grp_off]);
     for (uint32_t j = g * 16; j < g * 16 + 16 && j < im.nraw; j++) { if (j > 0 && raw[j] == 0 && raw[j - 1] == 0xFF) continue; out[o++] = raw[j]; }
-    if (g == im.ngrp - 1) { const uint32_t ns = im.g.nbits >> 3; for (uint32_t j = ns; j < ((ns + 3) & ~3u) + 16; j++) out[j] = 0xFF; }   // pad: peek32 reads whole words past the end
+    if (g == im.ngrp - 1) {
+        uint32_t ns = im.g.nbits >> 3;
+        if (im.verify) {
+            ns = im.nraw - (off[im.grp_off + g] - off[im.grp_off] + cnt[im.grp_off + g]);
+            im.g.nbits = ns * 8; im.g.nsub = (ns * 8 + im.g.subseq_bits - 1) / im.g.subseq_bits;
+        }
+        for (uint32_t j = ns; j < ((ns + 3) & ~3u) + 16; j++) out[j] = 0xFF;          // pad: peek32 reads whole words past the end
+    }
 }
 
 // ---- synchronisation rounds ------------------------------------------------------------------------------------------------
@@ -224,7 +239,8 @@ bool GpuDecoder::prepare(std::vector<Item> &items, void *stream_, std::string &e
         DecImage &im = imgs[n]; memset(&im, 0, sizeof(im));
         const size_t nraw = ds.ecs_end - ds.ecs_begin;
         if (nraw >= (1ull << 28)) { err = "entropy-coded segment too large for the device decoder"; return false; }
-        const uint32_t nstream = (uint32_t)(nraw - ds.stuffed);
+        const uint32_t nstream = (uint32_t)(ds.verified ? nraw - ds.stuffed : nraw);      // unverified: upper bound, the device finds the real length
+        im.verify = ds.verified ? 0u : 1u;
         Geometry &G = im.g;
         int q = 0;
         for (int c = 0; c < g.ncomp; c++) for (int k = 0; k < (g.ncomp == 1 ? 1 : g.hs[c] * g.vs[c]); k++) { if (q >= 10) { err = "MCU too large"; return false; } G.dc_tbl[q] = ds.td[c]; G.ac_tbl[q] = ds.ta[c]; q++; }
@@ -248,7 +264,8 @@ bool GpuDecoder::prepare(std::vector<Item> &items, void *stream_, std::string &e
     if (raw_total >= (1ull << 31) || stream_total >= (1ull << 31)) { err = "decode batch too large"; return false; }
     // ---- buffers
     o_img = 0; o_tab = align_up(sizeof(DecImage) * N, 256); o_flag = o_tab + align_up(sizeof(DecTables) * N, 256);
-    par_bytes = o_flag + align_up((size_t)4 * N * (MAX_ROUNDS + 2), 256);
+    o_mark = o_flag + align_up((size_t)4 * N * (MAX_ROUNDS + 2), 256);
+    par_bytes = o_mark + align_up((size_t)4 * N, 256);
     if (!growd(h_raw, cap_hraw, raw_total + 64, true, err) || !growd(d_raw, cap_raw, raw_total + 64, false, err) || !growd(d_stream, cap_stream, stream_total + 64, false, err) ||
         !growd(d_cnt, cap_cnt, (size_t)grp_total * 4 + 4, false, err) || !growd(d_off, cap_off, (size_t)grp_total * 4 + 4, false, err) ||
         !growd(d_A, cap_A, (size_t)sub_total * sizeof(DecState), false, err) ||
@@ -271,7 +288,7 @@ bool GpuDecoder::prepare(std::vector<Item> &items, void *stream_, std::string &e
         // tables that do not fit the second-level pool: the kernels run on an all-invalid table set and the image is reported
         // NOT_CONVERGED, which sends it to the host decoder
         tables_ok[n] = build_dec_tables(db, dv, imgs[n].g, ht[n]) ? 1 : 0;
-        memcpy(h_raw + imgs[n].raw_off, rd.data() + items[n].ds->ecs_begin, imgs[n].nraw);
+        stream_copy(h_raw + imgs[n].raw_off, rd.data() + items[n].ds->ecs_begin, imgs[n].nraw);      // pinned staging: read next by the DMA engine only
     }
     memcpy(h_par + o_img, imgs.data(), sizeof(DecImage) * N);
     memset(h_par + o_flag, 0, (size_t)4 * N * (MAX_ROUNDS + 2));
@@ -286,20 +303,21 @@ bool GpuDecoder::enqueue(void *stream_, std::string &err)
     const int N = nitems;
     if (N == 0) return true;
     static const int nrounds = [] { const char *e = getenv("B200_DEC_ROUNDS"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= MAX_ROUNDS ? v : (int)ROUNDS; }();
-    const DecImage *dI = reinterpret_cast<const DecImage *>(d_par + o_img);
+    DecImage *dIw = reinterpret_cast<DecImage *>(d_par + o_img);
+    const DecImage *dI = dIw;
     const DecTables *dT = reinterpret_cast<const DecTables *>(d_par + o_tab);
-    uint32_t *dF = reinterpret_cast<uint32_t *>(d_par + o_flag);
+    uint32_t *dF = reinterpret_cast<uint32_t *>(d_par + o_flag), *dM = reinterpret_cast<uint32_t *>(d_par + o_mark);
     uint32_t *hF = reinterpret_cast<uint32_t *>(h_par + o_flag);
-    CUD(cudaMemsetAsync(dF, 0, (size_t)4 * N * (MAX_ROUNDS + 2), st));
+    CUD(cudaMemsetAsync(dF, 0, (o_mark - o_flag) + (size_t)4 * N, st));                 // round flags + marker flags
     LT_MARK("memset");
     // ---- unstuff
     const dim3 gg(cdiv(max_grp, 128), N);
-    k_gd_unstuff_count<<<gg, 128, 0, st>>>(dI, d_raw, d_cnt);
+    k_gd_unstuff_count<<<gg, 128, 0, st>>>(dI, d_raw, d_cnt, dM);
     LT_MARK("k_gd_unstuff_count");
     size_t tb = cap_temp;
     cub::DeviceScan::ExclusiveSum(d_temp, tb, d_cnt, d_off, (int)grp_total, st);
     LT_MARK("cub_scan");
-    k_gd_unstuff_scatter<<<gg, 128, 0, st>>>(dI, d_raw, d_off, d_stream);
+    k_gd_unstuff_scatter<<<gg, 128, 0, st>>>(dIw, d_raw, d_off, d_cnt, d_stream);
     LT_MARK("k_gd_unstuff_scatter");
     for (int n = 0; n < N; n++) CUD(cudaMemsetAsync(coef_ptrs[n], 0, coef_bytes[n], st));
     // ---- rounds
@@ -317,6 +335,7 @@ bool GpuDecoder::enqueue(void *stream_, std::string &err)
     }
     rounds_used = nrounds;
     CUD(cudaMemcpyAsync(hF, dF, (size_t)4 * N * nrounds, cudaMemcpyDeviceToHost, st));
+    CUD(cudaMemcpyAsync(h_par + o_mark, dM, (size_t)4 * N, cudaMemcpyDeviceToHost, st));
     // ---- block counts -> first block of each subsequence -> write -> DC (images that did not converge produce garbage
     //      that their caller discards)
     tb = cap_temp;
@@ -340,11 +359,11 @@ bool GpuDecoder::enqueue(void *stream_, std::string &err)
 void GpuDecoder::finish(std::vector<Item> &items)
 {   // the caller has waited for the stream: an image settled iff some round changed nothing in it
     const int N = nitems;
-    const uint32_t *hF = reinterpret_cast<const uint32_t *>(h_par + o_flag);
+    const uint32_t *hF = reinterpret_cast<const uint32_t *>(h_par + o_flag), *hM = reinterpret_cast<const uint32_t *>(h_par + o_mark);
     for (int n = 0; n < N && n < (int)items.size(); n++) {
         bool conv = false;
         for (int r = 0; r < rounds_used && !conv; r++) conv = hF[(size_t)r * N + n] == 0;
-        items[n].result = conv && tables_ok[n] ? OK : NOT_CONVERGED;
+        items[n].result = conv && tables_ok[n] && !hM[n] ? OK : NOT_CONVERGED;           // a marker inside the segment: the host decoder's business
     }
 }
 

@@ -16,6 +16,8 @@ struct DecImage {               // one image of a decode batch (device-visible)
     uint32_t grp_off, ngrp;     // 16-byte groups of the raw segment (un-stuffing)
     uint32_t sub_off;           // first subsequence of this image in the state arrays
     uint32_t blk_off;           // first block of this image in the DC arrays
+    uint32_t verify;            // 1: the host did not walk the segment -- the un-stuff pass counts stuffed bytes (g.nbits / g.nsub are
+                                // upper bounds until it has) and reports markers inside the segment
     gd::Geometry g;
     ge::Scan scan;              // output addressing (scan.coef = this image's coefficient buffer)
     gd::Walk walk;              // the same, in the division-free form the write pass steps through
@@ -49,7 +51,7 @@ public:
 private:
     int nitems = 0;
     std::vector<DecImage> imgs; std::vector<int16_t *> coef_ptrs; std::vector<size_t> coef_bytes; std::vector<char> tables_ok;
-    size_t raw_total = 0, o_img = 0, o_tab = 0, o_flag = 0, par_bytes = 0;
+    size_t raw_total = 0, o_img = 0, o_tab = 0, o_flag = 0, o_mark = 0, par_bytes = 0;
     uint32_t grp_total = 0, sub_total = 0, blk_total = 0, max_grp = 0, max_sub = 0, max_blk = 0;
     uint8_t *h_raw = nullptr; size_t cap_hraw = 0;          // pinned staging of the entropy-coded segments
     uint8_t *d_raw = nullptr, *d_stream = nullptr; size_t cap_raw = 0, cap_stream = 0;

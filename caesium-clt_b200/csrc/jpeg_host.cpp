@@ -3,6 +3,7 @@
 // jdhuff.c / jdphuff.c (entropy decode), jchuff.c / jcphuff.c (entropy encode, optimised tables),
 // jcmarker.c (file layout), jccoefct.c / jctrans.c (dummy blocks), jcparam.c (quality scaling, sampling).
 #include "jpeg_host.h"
+#include "host_copy.h"
 #include <cstring>
 #include <cstdlib>
 #include <emmintrin.h>
@@ -383,7 +384,7 @@ bool JpegReader::decode_scan(const uint8_t *seg, size_t sl, const uint8_t *ecs, 
     return true;
 }
 
-bool JpegReader::device_decodable(DeviceScan &ds)
+bool JpegReader::device_decodable(DeviceScan &ds, bool scan_on_device)
 {
     if (!have_sof_ || g_.progressive || restart_interval_ != 0) return false;
     if (pos_ + 4 > n_ || d_[pos_] != 0xFF || d_[pos_ + 1] != 0xDA) return false;
@@ -401,9 +402,17 @@ bool JpegReader::device_decodable(DeviceScan &ds)
     }
     for (int c = 0; c < g_.ncomp; c++) if (!g_.qt_present[g_.tq[c]]) return false;
     ds.ecs_begin = pos_ + 2 + L;
+    ds.stuffed = 0; ds.verified = !scan_on_device;
+    if (scan_on_device) {
+        // the last EOI of the file, searched from the end (trailing garbage after it is tolerated, like the forward walk does)
+        size_t e = n_;
+        while (e >= ds.ecs_begin + 2 && !(d_[e - 2] == 0xFF && d_[e - 1] == 0xD9)) e--;
+        if (e < ds.ecs_begin + 2) return false;
+        ds.ecs_end = e - 2;
+        return ds.ecs_end > ds.ecs_begin;
+    }
     // the segment ends at the first marker that is not a stuffed zero; anything but EOI right there disqualifies the file
     size_t q = ds.ecs_begin;
-    ds.stuffed = 0;
     {   // 16 bytes at a time: find 0xFF bytes, count the stuffed zeros behind them, stop at the first real marker
         const __m128i ff = _mm_set1_epi8((char)0xFF);
         bool found = false;
@@ -824,7 +833,7 @@ bool jpeg_assemble_malloc(const JpegGeom &g, const JpegWriteOptions &opt, const 
     if (!p) { err = "out of memory"; return false; }
     uint8_t *q = p;
     memcpy(q, head.data(), head.size()); q += head.size();
-    for (int si = 0; si < nscans; si++) { memcpy(q, pre[si].data(), pre[si].size()); q += pre[si].size(); memcpy(q, scans[si].data, scans[si].len); q += scans[si].len; }
+    for (int si = 0; si < nscans; si++) { memcpy(q, pre[si].data(), pre[si].size()); q += pre[si].size(); stream_copy(q, scans[si].data, scans[si].len); q += scans[si].len; }
     *q++ = 0xFF; *q++ = 0xD9;
     *out = p; *out_len = total;
     return true;

@@ -49,8 +49,11 @@ public:
     // that carries every component, no restart interval.)  Fills the scan's table selectors and the byte range of its
     // entropy-coded segment; on true, the reader is positioned after the scan so later markers are still parsed by
     // finish_after_device_decode().
-    struct DeviceScan { int ns; int ci[4], td[4], ta[4]; size_t ecs_begin, ecs_end, stuffed; };
-    bool device_decodable(DeviceScan &ds);
+    // verified = the host walked the entropy-coded segment (stuffed zeros counted, no marker inside, EOI right behind it).
+    // scan_on_device: skip that walk -- the segment is taken to end at the file's last EOI and the device decoder counts the stuffed
+    // bytes and looks for markers itself while it un-stuffs (a marker inside sends the image to the host decoder).
+    struct DeviceScan { int ns; int ci[4], td[4], ta[4]; size_t ecs_begin, ecs_end, stuffed; bool verified; };
+    bool device_decodable(DeviceScan &ds, bool scan_on_device = false);
     const uint8_t *dht_bits(int kind, int id) const { return kind ? ac_[id].bits : dc_[id].bits; }
     const uint8_t *dht_vals(int kind, int id) const { return kind ? ac_[id].vals : dc_[id].vals; }
     bool dht_present(int kind, int id) const { return kind ? ac_[id].present : dc_[id].present; }

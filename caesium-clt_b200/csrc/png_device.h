@@ -20,10 +20,20 @@ struct PngDevice {
     uint32_t *h_tok = nullptr;
     size_t cap_raw = 0, cap_raw2 = 0, cap_filt = 0, cap_best = 0, cap_tok = 0, cap_out = 0, cap_counts = 0, cap_offsets = 0, cap_hist = 0, cap_sums = 0,
            cap_tlog = 0, cap_temp = 0, cap_small = 0, cap_htok = 0, cap_hraw = 0;
+    uint8_t *d_fin = nullptr, *d_dfl = nullptr, *d_z = nullptr, *h_z = nullptr; uint32_t *d_sync = nullptr; unsigned long long *d_sums_in = nullptr;
+    size_t cap_fin = 0, cap_dfl = 0, cap_z = 0, cap_hz = 0, cap_sync = 0, cap_sums_in = 0, z_cap = 0;
+    bool corrupt = false;                                // the last failure was the INPUT's fault (bad filter byte, Adler-32 mismatch)
     size_t tlog_n = 0;
     double last_deflate_ms = 0;                          // host Huffman/bit-packing time of the last compress() (tracing)
     ~PngDevice();
 
+    // The lossless path: the caller inflates the IDAT stream into input_buffer() (pinned, `bytes` = height * (row_bytes + 1); the
+    // buffer has 4096 bytes of slack for the inflate) and hands over its length and the stream's stored Adler-32; un-filtering,
+    // checksum verification, reductions, K6 / K7 and the DEFLATE coding run on the device.
+    uint8_t *input_buffer(size_t bytes, size_t &cap, std::string &err);
+    bool compress_filtered(PngInfo &info, size_t nfilt, uint32_t stored_adler, int level, void *stream, std::vector<uint8_t> &zlib_stream, int *chosen_strategy, std::string &err);
+    bool ensure_buffers(size_t nraw, size_t nmax, size_t rb, void *stream, std::string &err);
+    bool reduce_and_code(PngInfo &info, bool probed, const uint32_t *h_flags, int level, void *stream, std::vector<uint8_t> &zlib_stream, int *chosen_strategy, std::string &err);
     // info/raw from png_decode; may rewrite info (colour-type reductions).  Produces the zlib stream of the re-filtered image.
     bool compress(PngInfo &info, const std::vector<uint8_t> &raw, int level, void *stream, std::vector<uint8_t> &zlib_stream, int *chosen_strategy, std::string &err);
     // filter + match + parse of d_raw with one strategy (results in d_filt / d_tok / d_counts / d_hist)

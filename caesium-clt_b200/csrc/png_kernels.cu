@@ -7,6 +7,7 @@
 // (pixel-multiple distances and the row above); parsing is sequential inside 4 KiB chunks, parallel across them.
 // All integer/byte work, HBM-bound; no tensor cores.
 #include <cuda_runtime.h>
+#include <cub/block/block_radix_sort.cuh>
 #include <cmath>
 #include <cstdint>
 #include "png_kernels.h"
@@ -122,6 +123,62 @@ __global__ void k_png_match(const uint8_t *__restrict__ s, uint32_t *__restrict_
         }
     }
     best[i] = bl >= 3 ? ((uint32_t)bl << 16) | (uint32_t)bd : 0u;
+}
+
+// ---- K7, hash part: matches at ARBITRARY distances (north_star: "LZ77 match-find over a device hash table") ---------------------
+// The fixed candidate set above finds what filtering leaves in photographs (pixel- and row-periodic repeats).  Flat art, text,
+// dithering and UI screenshots repeat at arbitrary distances: for those every position is hashed by its next three bytes and looks
+// at the nearest earlier positions with the same hash -- zlib's hash chains, built without a sequential insert loop: one CTA owns a
+// segment of 16,384 positions, sorts (hash, position) with a stable block radix sort in shared memory, and the chain of a position
+// is then simply the run of equal hashes in front of it (nearest first).  Chains do not cross segment starts; the fixed candidates
+// (which reach back a whole row or two) do.  A hash candidate replaces the current best only if it is strictly longer, so the
+// result is deterministic: the oracle twin walks ordinary head / prev chains and arrives at the same matches.
+constexpr int HM_SEG = 16384, HM_THREADS = 512, HM_ITEMS = HM_SEG / HM_THREADS, HM_DEPTH = 4;
+__device__ __forceinline__ uint32_t hash3(const uint8_t *__restrict__ p) { return (((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16)) * 2654435761u) >> 16; }
+
+__global__ void __launch_bounds__(HM_THREADS) k_png_hashmatch(const uint8_t *__restrict__ s, uint32_t *__restrict__ best, size_t n, int chunk)
+{
+    using Sort = cub::BlockRadixSort<uint16_t, HM_THREADS, HM_ITEMS, uint16_t>;
+    extern __shared__ __align__(16) unsigned char hm_smem[];
+    typename Sort::TempStorage &temp = *reinterpret_cast<typename Sort::TempStorage *>(hm_smem);
+    uint16_t *sh_key = reinterpret_cast<uint16_t *>(hm_smem + ((sizeof(typename Sort::TempStorage) + 15) / 16) * 16), *sh_pos = sh_key + HM_SEG;
+    const size_t seg0 = (size_t)blockIdx.x * HM_SEG;
+    uint16_t keys[HM_ITEMS], vals[HM_ITEMS];
+#pragma unroll
+    for (int j = 0; j < HM_ITEMS; j++) {
+        const int local = threadIdx.x * HM_ITEMS + j;
+        const size_t p = seg0 + local;
+        const bool ok = p + 3 <= n;
+        keys[j] = ok ? (uint16_t)hash3(s + p) : (uint16_t)0xFFFF;
+        vals[j] = ok ? (uint16_t)local : (uint16_t)0xFFFF;
+    }
+    Sort(temp).Sort(keys, vals);                       // stable LSD radix sort on the 16 hash bits: equal hashes stay in position order
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < HM_ITEMS; j++) { sh_key[threadIdx.x * HM_ITEMS + j] = keys[j]; sh_pos[threadIdx.x * HM_ITEMS + j] = vals[j]; }
+    __syncthreads();
+    for (int j = 0; j < HM_ITEMS; j++) {
+        const int k = threadIdx.x * HM_ITEMS + j;
+        const uint32_t local = sh_pos[k];
+        if (local == 0xFFFFu) continue;
+        const size_t i = seg0 + local;
+        const size_t chunk_end = (i / chunk + 1) * (size_t)chunk;
+        const int maxlen = (int)min((size_t)258, min(n, chunk_end) - i);
+        if (maxlen < 3) continue;
+        const uint32_t cur = best[i];
+        int bl = (int)(cur >> 16), bd = (int)(cur & 0xFFFF);
+        if (bl == maxlen) continue;
+        const uint16_t key = sh_key[k];
+        for (int c = 1; c <= HM_DEPTH && k - c >= 0; c++) {
+            if (sh_key[k - c] != key) break;
+            const int d = (int)local - (int)sh_pos[k - c];
+            if (bl > 0 && s[i + bl] != s[i + bl - d]) continue;      // cannot beat the current best
+            const int l = match_len(s, i, d, maxlen);
+            if (l > bl) { bl = l; bd = d; }
+            if (bl == maxlen) break;
+        }
+        best[i] = bl >= 3 ? ((uint32_t)bl << 16) | (uint32_t)bd : 0u;
+    }
 }
 
 __device__ __forceinline__ int len_symbol(int len)
@@ -298,6 +355,14 @@ int launch_png_filter(const uint8_t *d_raw, uint8_t *d_filt, int h, int rb, int 
 int launch_png_match(const uint8_t *d_filt, uint32_t *d_best, size_t n, int bpp, int stride, void *stream)
 {
     k_png_match<<<cdivu(n, 256), 256, 0, (cudaStream_t)stream>>>(d_filt, d_best, n, bpp, stride, PARSE_CHUNK_MAX);
+    return (int)cudaGetLastError();
+}
+int launch_png_hashmatch(const uint8_t *d_filt, uint32_t *d_best, size_t n, void *stream)
+{
+    using Sort = cub::BlockRadixSort<uint16_t, HM_THREADS, HM_ITEMS, uint16_t>;
+    const size_t smem = ((sizeof(typename Sort::TempStorage) + 15) / 16) * 16 + (size_t)HM_SEG * 4;
+    cudaFuncSetAttribute(k_png_hashmatch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      // per device; cheap to repeat
+    k_png_hashmatch<<<cdivu(n, HM_SEG), HM_THREADS, smem, (cudaStream_t)stream>>>(d_filt, d_best, n, PARSE_CHUNK_MAX);
     return (int)cudaGetLastError();
 }
 int launch_png_parse(const uint32_t *d_best, const uint8_t *d_filt, size_t n, int chunk, uint32_t *d_tokens, uint32_t *d_counts, uint32_t *d_hist, void *stream)

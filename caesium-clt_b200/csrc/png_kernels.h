@@ -17,6 +17,9 @@ void png_make_tlog(uint32_t *tlog, size_t n);
 int launch_png_filter(const uint8_t *d_raw, uint8_t *d_filt, int h, int rb, int bpp, int strategy, const uint32_t *d_tlog, void *stream);
 // K7 phase 1: best (length << 16 | distance) per position of the filtered stream (0 = no match of length >= 3).
 int launch_png_match(const uint8_t *d_filt, uint32_t *d_best, size_t n, int bpp, int stride, void *stream);
+// K7 phase 1b: hash-chain candidates at arbitrary distances (nearest 4 earlier positions with the same 3-byte hash inside a
+// 16,384-position segment) improve d_best where they are strictly longer
+int launch_png_hashmatch(const uint8_t *d_filt, uint32_t *d_best, size_t n, void *stream);
 // K7 phase 2: greedy/lazy parse per chunk of `chunk` positions into tokens (chunk-local slots) + per-chunk counts,
 // plus the litlen/dist symbol histogram (316 counters) used to estimate the DEFLATE size of the strategy.
 int launch_png_parse(const uint32_t *d_best, const uint8_t *d_filt, size_t n, int chunk, uint32_t *d_tokens, uint32_t *d_counts, uint32_t *d_hist, void *stream);

@@ -143,6 +143,39 @@ static uint32_t best_match(const uint8_t *s, size_t n, size_t i, int bpp, int st
     return bl >= 3 ? ((uint32_t)bl << 16) | (uint32_t)bd : 0;
 }
 
+/* Matches at arbitrary distances: zlib-style hash chains over the next three bytes, confined to segments of 16,384 positions
+ * (a chain never crosses a segment start), at most the 4 nearest earlier positions with the same hash; a chain candidate replaces
+ * the fixed-candidate result only when it is strictly longer.  (The device builds the same chains by sorting (hash, position)
+ * pairs per segment -- caesium-clt_b200/csrc/png_kernels.cu k_png_hashmatch.) */
+#define HM_SEG 16384
+#define HM_DEPTH 4
+static void hash_chain_matches(const uint8_t *s, size_t n, uint32_t *best)
+{
+    int32_t *head = (int32_t *)malloc(65536 * 4), *prev = (int32_t *)malloc(HM_SEG * 4);
+    for (size_t seg0 = 0; seg0 < n; seg0 += HM_SEG) {
+        memset(head, 0xFF, 65536 * 4);
+        size_t seg_end = seg0 + HM_SEG < n ? seg0 + HM_SEG : n;
+        for (size_t i = seg0; i < seg_end; i++) {
+            if (i + 3 > n) break;
+            uint32_t h = (((uint32_t)s[i] | ((uint32_t)s[i + 1] << 8) | ((uint32_t)s[i + 2] << 16)) * 2654435761u) >> 16;
+            size_t chunk_end = (i / CHUNK + 1) * (size_t)CHUNK; if (chunk_end > n) chunk_end = n;
+            int maxlen = chunk_end - i > 258 ? 258 : (int)(chunk_end - i);
+            if (maxlen >= 3) {
+                int bl = (int)(best[i] >> 16), bd = (int)(best[i] & 0xFFFF);
+                int32_t q = head[h];
+                for (int c = 0; c < HM_DEPTH && q >= 0 && bl < maxlen; c++, q = prev[q]) {
+                    int d = (int)(i - seg0) - q, l = 0;
+                    while (l < maxlen && s[i + l] == s[i + l - d]) l++;
+                    if (l > bl) { bl = l; bd = d; }
+                }
+                best[i] = bl >= 3 ? ((uint32_t)bl << 16) | (uint32_t)bd : 0;
+            }
+            prev[i - seg0] = head[h]; head[h] = (int32_t)(i - seg0);
+        }
+    }
+    free(head); free(prev);
+}
+
 /* tokens must hold n entries; hist 316 counters (286 litlen + 30 dist; end-of-block not counted); returns token count */
 size_t orc_png_lz77(const uint8_t *s, size_t n, int bpp, int stride, uint32_t *tokens, uint32_t *hist)
 {
@@ -150,6 +183,7 @@ size_t orc_png_lz77(const uint8_t *s, size_t n, int bpp, int stride, uint32_t *t
     memset(hist, 0, 316 * 4);
     uint32_t *best = (uint32_t *)malloc((n + 1) * 4);
     for (size_t i = 0; i < n; i++) best[i] = best_match(s, n, i, bpp, stride);
+    hash_chain_matches(s, n, best);
     for (size_t begin = 0; begin < n; begin += CHUNK) {
         size_t end = begin + CHUNK < n ? begin + CHUNK : n, i = begin;
         while (i < end) {

@@ -335,3 +335,36 @@ def test_errors_do_not_abort(L, golden):
         assert e2.code == L.ERR_CORRUPT_INPUT
     # and the library is still usable afterwards
     assert L.compress_in_memory(data, p)[:2] == b"\xff\xd8"
+
+
+def test_group_path_walks_the_scan_on_the_device(L, O, golden):
+    """b200_compress_batch no longer walks every entropy-coded segment on the host: the segment is taken to end at the file's last
+    EOI and the device counts stuffed bytes and looks for markers while it un-stuffs.  Files whose segment is not what it seems --
+    a second image appended behind the first (MPF style: the last EOI is not ours), trailing bytes after EOI, a restart marker
+    without a DRI segment -- must come out exactly as the oracle writes them (the host decoder takes the odd ones)."""
+    base = [golden(n) for n in ("in_420_base_640x480.jpg", "in_420_base_355x237.jpg")]
+    a = base[0]
+    appended = a + base[1]                                   # two images back to back: the first is the picture
+    trailing = a + b"\x00\x01\x02trailing bytes after EOI" * 50
+    sos = a.index(b"\xff\xda")
+    body = bytearray(a)
+    k = len(a) // 2
+    while body[k] == 0xFF or body[k - 1] == 0xFF or body[k + 1] == 0xFF:
+        k += 1
+    stray = bytes(body[:k]) + b"\xff\xd0" + bytes(body[k:])    # a marker in the middle of the scan
+    assert k > sos
+    work = [a, appended, a, trailing, a, a, a, a, a, a]
+    p = _params(L, 80, 420, True)
+    po = O.params(80, 420, True)
+    res = L.compress_batch(work, p, n_threads=4)
+    for i, (out, code, msg) in enumerate(res):
+        assert code == 0, (i, msg)
+        assert out == O.jpeg_lossy(work[i], po), i
+    # the stray marker: whatever the host decoder makes of it (libjpeg resynchronises), the batch and the single call agree
+    single = None
+    try:
+        single = L.compress_in_memory(stray, p)
+    except L.B200Error as e:
+        single = e.code
+    out, code, msg = L.compress_batch([a, stray, a, a], p, n_threads=2)[1]
+    assert (out if code == 0 else code) == single

@@ -193,3 +193,75 @@ def test_compress_batch_mixes_png_and_jpeg(L, golden):
             assert data[:2] == b"\xff\xd8"
         else:
             assert np.array_equal(np.asarray(pil_pixels(src)), np.asarray(pil_pixels(data)))
+
+
+# ---- round 2: un-filtering, checksum verification and DEFLATE coding moved to the device -------------------------------------------
+def _mixed_filter_png(O, img, bit_depth=8, seed=0):
+    """A PNG whose rows use random filter types 0..4 (oracle filters, framed by zlib): every reconstruction branch of the wavefront."""
+    h = img.shape[0]
+    raw = img.reshape(h, -1)
+    ch = {1: 0, 2: 4, 3: 2, 4: 6}[img.shape[2] // (bit_depth // 8 if bit_depth >= 8 else 1)] if bit_depth >= 8 else 0
+    bpp = max(1, img.shape[2]) if bit_depth >= 8 else 1
+    per = [O.png_filter(raw, bpp, s) for s in range(5)]
+    rng = np.random.default_rng(seed)
+    pick = rng.integers(0, 5, h)
+    rows = np.stack([per[pick[y]][y] for y in range(h)])
+    from pngutil import frame_png
+    width = img.shape[1] if bit_depth >= 8 else img.shape[1] * 8 // bit_depth
+    return frame_png(width, h, bit_depth, ch, zlib.compress(rows.tobytes(), 6)), pick
+
+
+@pytest.mark.parametrize("shape,channels,depth", [((67, 131), 3, 8), ((200, 97), 4, 8), ((33, 500), 1, 8), ((90, 64), 2, 8), ((40, 70), 6, 16), ((35, 45), 8, 16),
+                                                   ((129, 33), 3, 8), ((1, 1), 4, 8), ((32, 1), 3, 8), ((31, 2), 1, 8), ((64, 40), 1, 2)])
+def test_device_unfilter_every_filter_type_and_pixel_size(L, O, shape, channels, depth):
+    h, w = shape
+    rng = np.random.default_rng(h * w + channels)
+    img = rng.integers(0, 256, (h, w, channels)).astype(np.uint8)
+    # smooth-ish content so that Paeth / Average predictions matter
+    img = (img // 8 + (np.add.outer(np.arange(h), np.arange(w))[:, :, None] * 3) % 200).astype(np.uint8)
+    src, pick = _mixed_filter_png(O, img, depth, seed=h)
+    assert len(set(pick.tolist())) >= min(5, h) or h < 5
+    out = L.compress_in_memory(src, lossless_params(L, 2))
+    a, b = pil_pixels(src), pil_pixels(out)
+    assert a.size == b.size
+    conv = "RGBA" if a.mode in ("RGBA", "LA", "P") or b.mode in ("RGBA", "LA", "P") else a.mode
+    if depth == 16 or a.mode.startswith("I"):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    else:
+        assert np.array_equal(np.asarray(a.convert(conv)), np.asarray(b.convert(conv)))
+
+
+def test_device_checks_of_the_input_stream(L, O):
+    """Adler-32 of the inflated IDAT is verified on the device; a filter byte > 4 is refused: both are corrupt input (code 4)."""
+    from pngutil import frame_png
+    img = synth(40, 50, 3, seed=4)
+    rows = O.png_filter(img.reshape(40, -1), 3, 4)
+    z = bytearray(zlib.compress(rows.tobytes(), 6))
+    z[-1] ^= 0x55                                                   # break the stored Adler-32 only
+    with pytest.raises(L.B200Error) as e:
+        L.compress_in_memory(frame_png(50, 40, 8, 2, bytes(z)), lossless_params(L))
+    assert e.value.code == 4 and "Adler" in str(e.value)
+    bad = rows.copy(); bad[7, 0] = 9
+    with pytest.raises(L.B200Error) as e:
+        L.compress_in_memory(frame_png(50, 40, 8, 2, zlib.compress(bad.tobytes(), 6)), lossless_params(L))
+    assert e.value.code == 4 and "filter" in str(e.value)
+    assert L.compress_in_memory(frame_png(50, 40, 8, 2, zlib.compress(rows.tobytes(), 6)), lossless_params(L))[:4] == b"\x89PNG"
+
+
+@pytest.mark.parametrize("kind,shape", [("photo", (300, 400)), ("flat", (257, 300)), ("noise", (120, 90)), ("photo", (1, 3))])
+def test_device_deflate_writer_equals_host_writer(L, O, kind, shape):
+    """The zlib stream the device writes (k_dfl_*: per-block statistics, code lengths, header, bit packing) is bit for bit the
+    stream the host writer (deflate_tokens, the same dfl_core.h bodies run sequentially) makes from the same tokens."""
+    h, w = shape
+    img = synth(h, w, 3, seed=h + w, kind=kind)
+    src = pil_png(img, compress_level=1)
+    out = L.compress_in_memory(src, lossless_params(L, 3))
+    ihdr, idat, _ = idat_stream(out)
+    filt = np.frombuffer(zlib.decompress(idat), np.uint8)
+    channels = {2: 3, 6: 4, 0: 1, 4: 2, 3: 1}[ihdr[3]]
+    if ihdr[3] == 3:
+        pytest.skip("palette-reduced: the indexed stream takes the raw-sample entry point (covered by the palette tests)")
+    stride = w * channels + 1
+    tok, _ = L.png_lz77(filt, channels, stride)
+    want = L.png_deflate_tokens(tok, zlib.adler32(filt.tobytes()))
+    assert idat == want
