@@ -306,6 +306,12 @@ def jpeg_workload(args, L, torch, dist, world, rank, datas, params, lossless, th
     ms_total, launches = time_pipe(torch, dist, world, pipe, stream, args.steps, args.warmup)
     sizes, not_settled, retries = pipe.finish()
     value = world * B * MP_PER_IMAGE * args.steps / (ms_total / 1e3)
+    if args.only_value:
+        if rank == 0:
+            _emit({"only_value": True, "value": round(value, 1), "images_per_sec": round(value / MP_PER_IMAGE, 1), "group": args.group, "batch": B, "not_settled": not_settled,
+                   "rounds": os.environ.get("B200_DEC_ROUNDS"), "launches_per_step": launches})
+        pipe.close()
+        raise SystemExit(0)
     stage = {}
     for which, name in ((1, "entropy_decode"), (2, "transform"), (3, "entropy_encode")):
         if lossless and which == 2:
@@ -351,11 +357,32 @@ def jpeg_workload(args, L, torch, dist, world, rank, datas, params, lossless, th
 
 # ---- configs[3]: 4096x4096 RGBA PNG, --lossless --png-opt-level 3 -----------------------------------------------------------------
 def png_stage_times(L, png):
-    """Device stages of the PNG path on one resident 4096x4096 image, CUDA-event timed inside the library (B200 stage API)."""
+    """Device side of the PNG path on one 4096x4096 image with an event after every launch (b200_png_device_times): the
+    device-busy rate (sum of the kernels' own durations; PCIe copies and host decision waits listed but not counted) and the
+    per-kernel roofline table on SURVEY 8d's algorithmic bytes (K6: 8 B/px-byte per strategy; K7 >= 4)."""
     try:
-        return L.png_device_times(png, 3)
-    except Exception as e:      # the stage-timing entry point is optional
+        t = L.png_device_times(png, 3, 2)
+    except Exception as e:
         return {"error": str(e)[:200]}
+    peak, peak_src = _peaks()
+    n = 4096 * (4096 * 4 + 1)                      # bytes of the filtered stream (the unit every PNG kernel works on)
+    alg = {"k_png_unfilter": 2 * n, "k_png_filter": 2 * n, "k_png_match": n + 4 * n, "k_png_hashmatch": n + 8 * n, "k_png_parse": 4 * n + 4 * n, "k_png_adler": n,
+           "k_png_compact": 8 * n, "k_png_probe": n, "k_png_colours": n, "k_dfl_hist": 4 * n, "k_dfl_len": 4 * n, "k_dfl_emit": 4 * n + n}
+    table, busy = {}, 0.0
+    for name, (ms, cnt) in sorted(t.items()):
+        e = {"ms": round(ms, 4), "launches": cnt}
+        if name.startswith("k_") or name in ("cub_scan", "memset"):
+            busy += ms * cnt
+        if name in alg:
+            gbs = alg[name] / (ms / 1e3) / 1e9
+            e["GBps"] = round(gbs, 1); e["frac"] = round(gbs / peak, 4)
+        table[name] = e
+    named = {k: v for k, v in table.items() if "frac" in v}
+    dom = max(named, key=lambda k: named[k]["ms"] * named[k]["launches"]) if named else None
+    return {"value": round(16.777216 / (busy / 1e3), 1) if busy else None, "device_busy_ms_per_image": round(busy, 3),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": named[dom]["GBps"] if dom else None, "peak": peak, "unit": "GB/s", "frac": named[dom]["frac"] if dom else None,
+                         "traffic": None, "peak_source": peak_src, "ms_per_launch": named[dom]["ms"] if dom else None, "all_kernels": table},
+            "value_scope": "device-busy rate of one image's whole launch sequence (un-filter, checksum, probes, 4 filter trials + winner with K6 / K7 fixed + hash candidates / parse, DEFLATE coding): sum of kernel durations from events after every launch; inflate (host) and PCIe copies are in e2e only"}
 
 
 def cpu_png(datas, L, cores, seconds):
@@ -412,6 +439,7 @@ def main():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-threads", type=int, default=0, help="host threads per rank for the C-ABI leg (default: the rank's share of the usable cores, at least 8)")
     ap.add_argument("--only-e2e", action="store_true", help="diagnostics: skip the device-resident leg and the per-kernel table")
+    ap.add_argument("--only-value", action="store_true", help="diagnostics: the device-resident leg only (prints a short JSON line)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -525,7 +553,7 @@ def config_png_run(args, L, cores, datas):
     in_bytes = sum(len(x) for x in work)
     stage = png_stage_times(L, datas[0])
     rec = {"workload": "configs[3]: 4096x4096 RGBA8 PNG (Paeth rows, zlib 6) -> --lossless --png-opt-level 3", "metric": "megapixels/sec lossless PNG re-encode", "unit": "MP/s",
-           "value": stage.get("value") if isinstance(stage, dict) else None, "stages": stage,
+           "value": stage.get("value") if isinstance(stage, dict) else None, "device": stage, "roofline": stage.get("roofline") if isinstance(stage, dict) else None,
            "e2e": {"value": round(rate, 2), "unit": "MP/s", "images_per_sec": round(rate / mp, 3), "h2d_bytes_per_step": n * w * h * 4, "d2h_bytes_per_step": out_bytes,
                    "in_bytes_per_step": in_bytes, "out_bytes_per_step": out_bytes, "images_per_step": n, "steps": steps, "host_threads": nt,
                    "note": "PNG files in host memory -> PNG files in host memory via b200_compress_batch: container parse + inflate + unfilter, device row-filter selection (K6) and LZ77 (K7), entropy coding, container"},

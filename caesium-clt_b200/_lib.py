@@ -68,7 +68,7 @@ _SYMBOLS = [
     "b200_jpeg_batch_time", "b200_jpeg_batch_destroy", "b200_jpeg_encode_coefficients_device",
     "b200_png_decode", "b200_png_decode_reduced", "b200_png_filter", "b200_png_lz77", "b200_png_deflate_tokens", "b200_png_level_strategies",
     "b200_webp_encode_rgb", "b200_webp_write_levels", "b200_webp_qindex",
-    "b200_jpeg_pipe_create", "b200_jpeg_pipe_run", "b200_jpeg_pipe_finish", "b200_jpeg_pipe_fetch", "b200_jpeg_pipe_kernel_times", "b200_jpeg_pipe_destroy", "b200_device_jobs", "b200_device_numa_node",
+    "b200_jpeg_pipe_create", "b200_jpeg_pipe_run", "b200_jpeg_pipe_finish", "b200_jpeg_pipe_fetch", "b200_jpeg_pipe_kernel_times", "b200_jpeg_pipe_destroy", "b200_device_jobs", "b200_device_numa_node", "b200_png_device_times",
 ]
 
 
@@ -86,7 +86,7 @@ def lib():
                   "b200_jpeg_batch_upload", "b200_jpeg_batch_run", "b200_jpeg_batch_download", "b200_jpeg_batch_time",
                   "b200_png_decode", "b200_png_decode_reduced", "b200_png_filter", "b200_png_lz77", "b200_png_deflate_tokens",
                   "b200_webp_encode_rgb", "b200_webp_write_levels", "b200_jpeg_encode_coefficients_device",
-                  "b200_jpeg_pipe_create", "b200_jpeg_pipe_run", "b200_jpeg_pipe_finish", "b200_jpeg_pipe_fetch", "b200_jpeg_pipe_kernel_times"):
+                  "b200_jpeg_pipe_create", "b200_jpeg_pipe_run", "b200_jpeg_pipe_finish", "b200_jpeg_pipe_fetch", "b200_jpeg_pipe_kernel_times", "b200_png_device_times"):
             getattr(L, f).restype = Status
         L.b200_version.restype = C.c_char_p
         L.b200_sniff_format.restype = C.c_uint32
@@ -294,6 +294,17 @@ def png_deflate_tokens(tokens, adler):
     outp, outl = C.POINTER(C.c_uint8)(), C.c_size_t()
     _check(lib().b200_png_deflate_tokens(tokens.ctypes.data_as(C.c_void_p), C.c_size_t(tokens.size), C.c_uint32(adler), C.byref(outp), C.byref(outl)))
     return _take(outp, outl)
+
+
+def png_device_times(data, level=3, iters=2):
+    """{kernel: (ms per launch, launches per image)} of the PNG device pipeline on one image (b200_png_device_times)."""
+    buf = C.create_string_buffer(1 << 14)
+    _check(lib().b200_png_device_times(data, C.c_size_t(len(data)), int(level), int(iters), buf, C.c_size_t(len(buf))))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, ms, cnt = line.split()
+        out[name] = (float(ms), int(cnt))
+    return out
 
 
 def png_level_strategies(level):

@@ -28,6 +28,7 @@
 #include "webp_device.h"
 #include "jpeg_pipe.h"
 #include "topology.h"
+#include "launch_timer.h"
 
 using namespace b200;
 
@@ -1192,6 +1193,44 @@ int b200_webp_qindex(int quality, int factors[6])
     const int q = vp8_qindex(quality < 0 ? 0 : quality > 100 ? 100 : quality);
     if (factors) vp8_quant_factors(q, factors);
     return q;
+}
+
+b200_status b200_png_device_times(const uint8_t *in, size_t in_len, int level, int iters, char *text, size_t cap)
+{
+    if (!in || !text || !cap || iters <= 0) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid argument");
+    std::string err;
+    PngInfo info0; PngIdat idat;
+    if (!png_parse_chunks(in, in_len, false, info0, idat, err)) return make_status(B200_ERR_CORRUPT_INPUT, err);
+    if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
+    Slot *s = slot_acquire(runtime_next_device(), err);
+    if (!s) return make_status(B200_ERR_CUDA, err);
+    if (!s->png) s->png = new PngDevice();
+    b200_status st = ok_status();
+    std::map<std::string, std::pair<double, int>> acc;
+    do {
+        const size_t nin = (info0.row_bytes + 1) * (size_t)info0.height;
+        size_t bcap = 0, got = 0; uint32_t adler = 0;
+        uint8_t *buf = s->png->input_buffer(nin, bcap, err);
+        if (!buf) { st = make_status(B200_ERR_OUT_OF_MEMORY, err); break; }
+        if (!zlib_inflate_to(idat.p, idat.n, buf, bcap, nin, &got, &adler, err) || got < nin) { st = make_status(B200_ERR_CORRUPT_INPUT, err.empty() ? "IDAT too short" : err); break; }
+        std::vector<uint8_t> z;
+        for (int it = 0; it <= iters; it++) {          // iteration 0 warms buffers up and is not counted
+            PngInfo info = info0;
+            LaunchTimer lt; lt.begin((cudaStream_t)s->stream);
+            tl_launch_timer = it ? &lt : nullptr;
+            const bool ok = s->png->compress_filtered(info, got, adler, level < 0 ? 0 : level > 6 ? 6 : level, s->stream, z, nullptr, err);
+            tl_launch_timer = nullptr;
+            if (!ok) { st = make_status(B200_ERR_CUDA, err); break; }
+            if (it) lt.collect(acc);
+        }
+    } while (0);
+    slot_release(s);
+    if (st.code) return st;
+    std::string out;
+    for (auto &kv : acc) { char b[160]; snprintf(b, sizeof b, "%s %.6f %d\n", kv.first.c_str(), kv.second.first / kv.second.second, kv.second.second / iters); out += b; }
+    if (out.size() + 1 > cap) return make_status(B200_ERR_INVALID_ARGUMENT, "text buffer too small");
+    memcpy(text, out.c_str(), out.size() + 1);
+    return ok_status();
 }
 
 int b200_png_level_strategies(int level, int *out)

@@ -202,6 +202,10 @@ GE_HD DecState decode_subsequence(const uint8_t *__restrict__ stream, const Geom
     uint32_t wi = p >> 5;
     uint32_t w0 = load_be32(stream, wi), w1 = load_be32(stream, wi + 1), w2 = load_be32(stream, wi + 2);
     const int bpm = g.blocks_per_mcu;
+    // table selectors of the MCU's blocks packed into two registers (3 bits per block: the first-level table slot), so that the
+    // per-symbol table choice is a shift and a mask instead of a dependent shared-memory read in front of the table lookup
+    uint32_t sel_dc = 0, sel_ac = 0;
+    for (int q = 0; q < bpm && q < 10; q++) { sel_dc |= (uint32_t)(T.sel[2 * q] >> LOOK_BITS) << (3 * q); sel_ac |= (uint32_t)(T.sel[2 * q + 1] >> LOOK_BITS) << (3 * q); }
     while (p < end) {
         if ((p >> 5) != wi) { wi = p >> 5; w0 = w1; w1 = w2; w2 = load_be32(stream, wi + 2); }
         const uint32_t sh = p & 31;
@@ -213,7 +217,7 @@ GE_HD DecState decode_subsequence(const uint8_t *__restrict__ stream, const Geom
         // One uniform body for DC and AC symbols (a DC symbol is "run 0, category s at index 0"), selects instead of
         // branches: the lanes of a warp sit at unrelated points of their blocks, so divergent paths would serialise.
         const bool dc = k == 0;
-        const uint32_t e = lookup_symbol(T, T.sel[2 * b + (dc ? 0 : 1)], bits);
+        const uint32_t e = lookup_symbol(T, (((dc ? sel_dc : sel_ac) >> (3 * b)) & 7u) << LOOK_BITS, bits);
         const int len = (int)(e >> 8), sym = (int)(e & 0xFF);
         const int r = dc ? 0 : (sym >> 4), s = sym & 15;
         const uint32_t ext = s ? (bits << len) >> (32 - s) : 0u;

@@ -13,6 +13,7 @@
 #include <chrono>
 #include <cstdlib>
 #include "stream_wait.h"
+#include "launch_timer.h"
 
 namespace b200 {
 
@@ -37,7 +38,7 @@ PngDevice::~PngDevice()
 {
     cudaFree(d_raw); cudaFree(d_raw2); cudaFree(d_filt); cudaFree(d_best); cudaFree(d_tok); cudaFree(d_out); cudaFree(d_counts); cudaFree(d_offsets);
     cudaFree(d_hist); cudaFree(d_sums); cudaFree(d_tlog); cudaFree(d_temp); cudaFreeHost(h_small); cudaFreeHost(h_tok); cudaFreeHost(h_raw);
-    cudaFree(d_fin); cudaFree(d_sums_in); cudaFree(d_sync); cudaFree(d_dfl); cudaFree(d_z); cudaFreeHost(h_z);
+    cudaFree(d_filt_all); cudaFree(d_fin); cudaFree(d_sums_in); cudaFree(d_sync); cudaFree(d_dfl); cudaFree(d_z); cudaFreeHost(h_z);
 }
 
 // oxipng presets: which row-filter strategies each optimisation level tries
@@ -66,16 +67,19 @@ static double estimate_bits(const uint32_t *h)
     return bits;
 }
 
-bool PngDevice::run_strategy(int strategy, int h, int rb, int bpp, void *stream_, std::string &err)
+// One strategy: K6 into `filt` (skipped when the stream is already there), K7 over it.  Trials run the fixed-distance candidates only
+// (enough to rank the strategies by their token statistics); the winner's stream then gets the hash candidates as well.
+bool PngDevice::run_strategy(int strategy, int h, int rb, int bpp, void *stream_, std::string &err, uint8_t *filt, bool do_filter, bool with_hash)
 {
     cudaStream_t st = (cudaStream_t)stream_;
     const size_t n = (size_t)h * (rb + 1);
-    int rc = launch_png_filter(d_raw, d_filt, h, rb, bpp, strategy, d_tlog, st);
-    if (!rc) rc = launch_png_match(d_filt, d_best, n, bpp, rb + 1, st);
-    if (!rc) rc = launch_png_hashmatch(d_filt, d_best, n, st);
+    if (!filt) filt = d_filt;
+    int rc = do_filter ? launch_png_filter(d_raw, filt, h, rb, bpp, strategy, d_tlog, st) : 0;
+    if (!rc) rc = launch_png_match(filt, d_best, n, bpp, rb + 1, st);
+    if (!rc && with_hash) rc = launch_png_hashmatch(filt, d_best, n, st);
     if (rc) { err = std::string("png kernels: ") + cudaGetErrorString((cudaError_t)rc); return false; }
     CUP(cudaMemsetAsync(d_hist, 0, 316 * 4, st));
-    rc = launch_png_parse(d_best, d_filt, n, kChunk, d_tok, d_counts, d_hist, st);
+    rc = launch_png_parse(d_best, filt, n, kChunk, d_tok, d_counts, d_hist, st);
     if (rc) { err = std::string("png parse: ") + cudaGetErrorString((cudaError_t)rc); return false; }
     return true;
 }
@@ -138,7 +142,7 @@ bool PngDevice::compress_filtered(PngInfo &info, size_t nfilt, uint32_t stored_a
     if (nfilt < nin) { err = "IDAT too short"; corrupt = true; return false; }
     const size_t nmax = nin + 64;
     if (!ensure_buffers(nraw, nmax, rb, st, err) || !growp(d_fin, cap_fin, nmax + 64, false, err)) return false;
-    CUP(cudaMemcpyAsync(d_fin, h_raw, nin, cudaMemcpyHostToDevice, st));
+    CUP(cudaMemcpyAsync(d_fin, h_raw, nin, cudaMemcpyHostToDevice, st)); LT_MARK("h2d");
     int rc = launch_png_adler(d_fin, nin, d_sums_in, st);
     uint32_t *d_un = d_sync, *d_flags = d_hist;
     uint32_t *d_set = reinterpret_cast<uint32_t *>(((uintptr_t)(d_sync + ((size_t)(h + 31) / 32 + 8)) + 7) & ~(uintptr_t)7);
@@ -157,7 +161,7 @@ bool PngDevice::compress_filtered(PngInfo &info, size_t nfilt, uint32_t stored_a
     CUP(cudaMemcpyAsync(h_flags, d_flags, 16, cudaMemcpyDeviceToHost, st));
     CUP(cudaMemcpyAsync(h_flags + 4, d_un, 8, cudaMemcpyDeviceToHost, st));
     CUP(cudaMemcpyAsync(h_sums_in, d_sums_in, npieces_in * 16, cudaMemcpyDeviceToHost, st));
-    CUP(stream_wait(st));
+    CUP(stream_wait(st)); LT_MARK("host_wait");
     if (h_flags[5]) { err = "bad filter type"; corrupt = true; return false; }
     if (combine_adler(h_sums_in, nin) != stored_adler) { err = "Adler-32 mismatch"; corrupt = true; return false; }
     if (probe_pal && h_flags[2] <= 256) {
@@ -188,7 +192,7 @@ bool PngDevice::compress(PngInfo &info, const std::vector<uint8_t> &raw_in, int 
         CUP(cudaMemsetAsync(d_flags, 0, 16, st));
         if (launch_png_probe(d_raw, (size_t)info.width * info.height, info.channels, d_flags, st)) { err = "png probe launch failed"; return false; }
         CUP(cudaMemcpyAsync(h_flags, d_flags, 16, cudaMemcpyDeviceToHost, st));
-        CUP(stream_wait(st));
+        CUP(stream_wait(st)); LT_MARK("host_wait");
     }
     return reduce_and_code(info, probe_ag, h_flags, level, stream_, zlib_stream, chosen, err);
 }
@@ -221,25 +225,30 @@ bool PngDevice::reduce_and_code(PngInfo &info, bool probed, const uint32_t *h_fl
     const size_t nchunks = (n + kChunk - 1) / kChunk;
     // ---- try every strategy of the preset; keep the one whose token histogram promises the smallest stream
     const std::vector<int> strategies = png_level_strategies(level);
-    int best_s = strategies[0]; double best_bits = -1;
+    int best_s = strategies[0]; double best_bits = -1; size_t best_k = 0;
+    const size_t fstride = (n + 64 + 255) / 256 * 256;
     if (strategies.size() > 1) {
+        // every trial keeps its filtered stream (K6 is not repeated for the winner)
+        if (!growp(d_filt_all, cap_filt_all, fstride * strategies.size() + 64, false, err)) return false;
         for (size_t k = 0; k < strategies.size(); k++) {
-            if (!run_strategy(strategies[k], h, (int)rb, bpp, st, err)) return false;
+            if (!run_strategy(strategies[k], h, (int)rb, bpp, st, err, d_filt_all + k * fstride, true, false)) return false;
             CUP(cudaMemcpyAsync(h_small + 1024 + k * 316 * 4, d_hist, 316 * 4, cudaMemcpyDeviceToHost, st));
         }
-        CUP(stream_wait(st));
+        CUP(stream_wait(st)); LT_MARK("host_wait");
         for (size_t k = 0; k < strategies.size(); k++) {
             const double bits = estimate_bits(reinterpret_cast<const uint32_t *>(h_small + 1024 + k * 316 * 4));
-            if (best_bits < 0 || bits < best_bits) { best_bits = bits; best_s = strategies[k]; }
+            if (best_bits < 0 || bits < best_bits) { best_bits = bits; best_s = strategies[k]; best_k = k; }
         }
     }
     if (chosen) *chosen = best_s;
-    // ---- the winner, for real: tokens compacted, Adler-32 pieces of the filtered stream, DEFLATE coding -- all on the device
-    if (!run_strategy(best_s, h, (int)rb, bpp, st, err)) return false;
+    // ---- the winner, for real: full match search (fixed + hash candidates), tokens compacted, Adler-32 pieces of the filtered
+    //      stream, DEFLATE coding -- all on the device
+    uint8_t *const wfilt = strategies.size() > 1 ? d_filt_all + best_k * fstride : d_filt;
+    if (!run_strategy(best_s, h, (int)rb, bpp, st, err, wfilt, strategies.size() <= 1, true)) return false;
     size_t tb = cap_temp;
-    cub::DeviceScan::ExclusiveSum(d_temp, tb, d_counts, d_offsets, (int)nchunks, st);
+    cub::DeviceScan::ExclusiveSum(d_temp, tb, d_counts, d_offsets, (int)nchunks, st); LT_MARK("cub_scan");
     int rc = launch_png_compact(d_tok, d_counts, d_offsets, nchunks, kChunk, d_out, st);
-    if (!rc) rc = launch_png_adler(d_filt, n, d_sums, st);
+    if (!rc) rc = launch_png_adler(wfilt, n, d_sums, st);
     if (rc) { err = std::string("png compact/adler: ") + cudaGetErrorString((cudaError_t)rc); return false; }
     unsigned long long *d_total = reinterpret_cast<unsigned long long *>(d_hist + 1024);          // [0] payload bits, [1] tokens
     uint32_t *d_ntok = d_hist + 1032;
@@ -253,11 +262,11 @@ bool PngDevice::reduce_and_code(PngInfo &info, bool probed, const uint32_t *h_fl
         if (rc) { err = std::string("png deflate: ") + cudaGetErrorString((cudaError_t)rc); return false; }
         CUP(cudaMemcpyAsync(h_total, d_total, 16, cudaMemcpyDeviceToHost, st));
         CUP(cudaMemcpyAsync(h_sums, d_sums, npieces * 16, cudaMemcpyDeviceToHost, st));
-        CUP(stream_wait(st));
+        CUP(stream_wait(st)); LT_MARK("host_wait");
         const size_t zbytes = (size_t)((h_total[0] + 7) / 8);
         if (zbytes + 8 <= z_cap) {
-            CUP(cudaMemcpyAsync(h_z, d_z, zbytes, cudaMemcpyDeviceToHost, st));
-            CUP(stream_wait(st));
+            CUP(cudaMemcpyAsync(h_z, d_z, zbytes, cudaMemcpyDeviceToHost, st)); LT_MARK("d2h");
+            CUP(stream_wait(st)); LT_MARK("host_wait");
             const uint32_t adler = combine_adler(h_sums, n);
             zlib_stream.resize(zbytes + 4);
             memcpy(zlib_stream.data(), h_z, zbytes);
@@ -270,13 +279,13 @@ bool PngDevice::reduce_and_code(PngInfo &info, bool probed, const uint32_t *h_fl
     } else {
         CUP(cudaMemcpyAsync(h_total + 1, d_ntok, 4, cudaMemcpyDeviceToHost, st));
         CUP(cudaMemcpyAsync(h_sums, d_sums, npieces * 16, cudaMemcpyDeviceToHost, st));
-        CUP(stream_wait(st));
+        CUP(stream_wait(st)); LT_MARK("host_wait");
         h_total[1] &= 0xFFFFFFFFull;
     }
     const size_t ntok = (size_t)h_total[1];
     if (!growp(h_tok, cap_htok, (n + 64) * 4 + 64, true, err)) return false;
     CUP(cudaMemcpyAsync(h_tok, d_out, ntok * 4, cudaMemcpyDeviceToHost, st));
-    CUP(stream_wait(st));
+    CUP(stream_wait(st)); LT_MARK("host_wait");
     const auto td = std::chrono::steady_clock::now();
     deflate_tokens(h_tok, ntok, combine_adler(h_sums, n), zlib_stream);
     last_deflate_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - td).count();

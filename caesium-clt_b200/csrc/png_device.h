@@ -37,7 +37,8 @@ struct PngDevice {
     // info/raw from png_decode; may rewrite info (colour-type reductions).  Produces the zlib stream of the re-filtered image.
     bool compress(PngInfo &info, const std::vector<uint8_t> &raw, int level, void *stream, std::vector<uint8_t> &zlib_stream, int *chosen_strategy, std::string &err);
     // filter + match + parse of d_raw with one strategy (results in d_filt / d_tok / d_counts / d_hist)
-    bool run_strategy(int strategy, int h, int rb, int bpp, void *stream, std::string &err);
+    bool run_strategy(int strategy, int h, int rb, int bpp, void *stream, std::string &err, uint8_t *filt = nullptr, bool do_filter = true, bool with_hash = true);
+    uint8_t *d_filt_all = nullptr; size_t cap_filt_all = 0;          // the trials' filtered streams, one after another
 };
 
 // allocate-run-free stage helpers behind b200_png_filter / b200_png_lz77 (current device)

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdint>
 #include "png_kernels.h"
+#include "launch_timer.h"
 
 namespace b200 {
 
@@ -134,6 +135,10 @@ __global__ void k_png_match(const uint8_t *__restrict__ s, uint32_t *__restrict_
 // (which reach back a whole row or two) do.  A hash candidate replaces the current best only if it is strictly longer, so the
 // result is deterministic: the oracle twin walks ordinary head / prev chains and arrives at the same matches.
 constexpr int HM_SEG = 16384, HM_THREADS = 512, HM_ITEMS = HM_SEG / HM_THREADS, HM_DEPTH = 4;
+// A match at an arbitrary distance has to pay for its distance code: in noisy (photographic) residuals three or four bytes repeat
+// by chance all the time, and coding those as far matches costs more bits than the literals would (and flattens the distance
+// statistics for the matches that matter).  zlib's TOO_FAR rule, extended: the farther, the longer a hash match must be.
+__device__ __forceinline__ int hash_min_len(int d) { return d <= 512 ? 4 : d <= 4096 ? 5 : 6; }
 __device__ __forceinline__ uint32_t hash3(const uint8_t *__restrict__ p) { return (((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16)) * 2654435761u) >> 16; }
 
 __global__ void __launch_bounds__(HM_THREADS) k_png_hashmatch(const uint8_t *__restrict__ s, uint32_t *__restrict__ best, size_t n, int chunk)
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(HM_THREADS) k_png_hashmatch(const uint8_t *__r
             const int d = (int)local - (int)sh_pos[k - c];
             if (bl > 0 && s[i + bl] != s[i + bl - d]) continue;      // cannot beat the current best
             const int l = match_len(s, i, d, maxlen);
-            if (l > bl) { bl = l; bd = d; }
+            if (l > bl && l >= hash_min_len(d)) { bl = l; bd = d; }
             if (bl == maxlen) break;
         }
         best[i] = bl >= 3 ? ((uint32_t)bl << 16) | (uint32_t)bd : 0u;
@@ -195,34 +200,76 @@ __device__ __forceinline__ int dist_symbol(int d)
     return hb * 2 + ((v >> (hb - 1)) & 1);
 }
 
-__global__ void __launch_bounds__(64) k_png_parse(const uint32_t *__restrict__ best, const uint8_t *__restrict__ s, size_t n, int chunk,
-                                                  uint32_t *__restrict__ tokens, uint32_t *__restrict__ counts, uint32_t *__restrict__ hist)
+// Greedy parse with one-step lazy matching (zlib's rule) of one chunk, in parallel: the step every position WOULD take if the
+// parse arrived there (its match length after the TOO_FAR and lazy rules, else 1) depends only on best[i] and best[i + 1], so all
+// steps are computed at once; the positions the sequential parse actually visits are those reachable from the chunk's first
+// position, found by pointer doubling in shared memory (12 rounds for 4,096 positions); a block scan over the visited flags gives
+// every token its slot.  Same tokens, same order, same histogram as the sequential walk (the oracle's orc_png_lz77 loop).
+constexpr int PARSE_THREADS = 256, PARSE_PER = PARSE_CHUNK_MAX / PARSE_THREADS;
+__global__ void __launch_bounds__(PARSE_THREADS) k_png_parse(const uint32_t *__restrict__ best, const uint8_t *__restrict__ s, size_t n, int chunk,
+                                                             uint32_t *__restrict__ tokens, uint32_t *__restrict__ counts, uint32_t *__restrict__ hist)
 {
+    __shared__ uint16_t jump[PARSE_CHUNK_MAX + 1];
+    __shared__ uint8_t visited[PARSE_CHUNK_MAX + 1];
     __shared__ uint32_t h[316];
-    for (int k = threadIdx.x; k < 316; k += blockDim.x) h[k] = 0;
-    __syncthreads();
-    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t begin = c * (size_t)chunk;
-    if (begin < n) {
-        const size_t end = min(n, begin + (size_t)chunk);
-        uint32_t *out = tokens + begin;
-        uint32_t nt = 0;
-        size_t i = begin;
-        while (i < end) {
-            const uint32_t b = best[i];
-            int len = (int)(b >> 16), d = (int)(b & 0xFFFF);
-            if (len == 3 && d > 4096) len = 0;                                   // zlib's TOO_FAR rule
-            if (len >= 3 && i + 1 < end) { const uint32_t b1 = best[i + 1]; if ((int)(b1 >> 16) > len) len = 0; }   // one-step lazy matching
-            if (len >= 3) {
-                out[nt++] = 0x80000000u | ((uint32_t)(len - 3) << 16) | (uint32_t)(d - 1);
-                atomicAdd(&h[257 + len_symbol(len)], 1u); atomicAdd(&h[286 + dist_symbol(d)], 1u);
-                i += (size_t)len;
-            } else { const uint32_t v = s[i]; out[nt++] = v; atomicAdd(&h[v], 1u); i++; }
+    __shared__ uint32_t part[PARSE_THREADS];
+    const size_t begin = (size_t)blockIdx.x * (size_t)chunk;
+    if (begin >= n) return;
+    const int len_chunk = (int)min((size_t)chunk, n - begin);
+    for (int k = threadIdx.x; k < 316; k += PARSE_THREADS) h[k] = 0;
+    // steps
+    for (int j = threadIdx.x; j <= chunk; j += PARSE_THREADS) {
+        int nx = len_chunk;
+        if (j < len_chunk) {
+            const uint32_t b = best[begin + j];
+            int len = (int)(b >> 16); const int d = (int)(b & 0xFFFF);
+            if (len == 3 && d > 4096) len = 0;                                                      // zlib's TOO_FAR rule
+            if (len >= 3 && j + 1 < len_chunk && (int)(best[begin + j + 1] >> 16) > len) len = 0;   // one-step lazy matching
+            nx = min(len_chunk, j + (len >= 3 ? len : 1));
         }
-        counts[c] = nt;
+        jump[j] = (uint16_t)nx; visited[j] = j == 0;
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < 316; k += blockDim.x) if (h[k]) atomicAdd(&hist[k], h[k]);
+    // reachability from position 0 by pointer doubling: after round r every visited position has marked its 2^r-th successor
+    for (int r = 0; (1 << r) < len_chunk; r++) {
+        uint16_t nj[PARSE_PER + 1]; int cnt = 0;
+        for (int j = threadIdx.x; j <= chunk; j += PARSE_THREADS, cnt++) {
+            const uint16_t t = jump[j];
+            if (j < len_chunk && visited[j]) visited[t] = 1;          // benign race: every writer writes 1
+            nj[cnt] = jump[t];
+        }
+        __syncthreads();
+        cnt = 0;
+        for (int j = threadIdx.x; j <= chunk; j += PARSE_THREADS, cnt++) jump[j] = nj[cnt];
+        __syncthreads();
+    }
+    // slots: thread t owns positions [t * PARSE_PER, (t + 1) * PARSE_PER)
+    const int p0 = threadIdx.x * PARSE_PER;
+    uint32_t mine = 0;
+    for (int j = p0; j < p0 + PARSE_PER && j < len_chunk; j++) mine += visited[j];
+    part[threadIdx.x] = mine;
+    __syncthreads();
+    uint32_t v = mine;
+    for (int dd = 1; dd < PARSE_THREADS; dd <<= 1) {
+        const uint32_t add = threadIdx.x >= (unsigned)dd ? part[threadIdx.x - dd] : 0u;
+        __syncthreads();
+        v += add; part[threadIdx.x] = v;
+        __syncthreads();
+    }
+    uint32_t slot = v - mine;
+    uint32_t *out = tokens + begin;
+    for (int j = p0; j < p0 + PARSE_PER && j < len_chunk; j++) {
+        if (!visited[j]) continue;
+        const uint32_t b = best[begin + j];
+        int len = (int)(b >> 16); const int d = (int)(b & 0xFFFF);
+        if (len == 3 && d > 4096) len = 0;
+        if (len >= 3 && j + 1 < len_chunk && (int)(best[begin + j + 1] >> 16) > len) len = 0;
+        if (len >= 3) { out[slot++] = 0x80000000u | ((uint32_t)(len - 3) << 16) | (uint32_t)(d - 1); atomicAdd(&h[257 + len_symbol(len)], 1u); atomicAdd(&h[286 + dist_symbol(d)], 1u); }
+        else { const uint32_t lit = s[begin + j]; out[slot++] = lit; atomicAdd(&h[lit], 1u); }
+    }
+    if (threadIdx.x == PARSE_THREADS - 1) counts[blockIdx.x] = v;
+    __syncthreads();
+    for (int k = threadIdx.x; k < 316; k += PARSE_THREADS) if (h[k]) atomicAdd(&hist[k], h[k]);
 }
 
 __global__ void k_png_compact(const uint32_t *__restrict__ tokens, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ offsets, int chunk, uint32_t *__restrict__ out)
@@ -272,6 +319,7 @@ template <int BPP>
 __global__ void __launch_bounds__(32) k_png_unfilter(const uint8_t *__restrict__ filt, uint8_t *raw, int h, int rb, uint32_t *__restrict__ ticket,
                                                      volatile uint32_t *__restrict__ progress, uint32_t *__restrict__ bad)
 {
+    __shared__ uint8_t sh_up[2][32 * BPP];               // the row above lane 0, 32 pixels at a time, double buffered
     const int lane = threadIdx.x;
     int g = 0;
     if (lane == 0) g = (int)atomicAdd(ticket, 1u);
@@ -281,32 +329,37 @@ __global__ void __launch_bounds__(32) k_png_unfilter(const uint8_t *__restrict__
     const int npix = (rb + BPP - 1) / BPP;
     const uint8_t *f = filt + (size_t)(live ? y : 0) * (rb + 1);
     uint8_t *r = raw + (size_t)(live ? y : 0) * rb;
-    const uint8_t *above = y > 0 ? raw + (size_t)(y - 1) * rb : nullptr;       // lane 0 only reads it
+    const uint8_t *above = g > 0 ? raw + (size_t)(g * 32 - 1) * rb : nullptr;       // last row of the previous group
     const int ft = live ? f[0] : 0;
     if (live && ft > 4) atomicOr(bad, 1u);
     f++;
     int a[BPP], b[BPP], c[BPP];
 #pragma unroll
     for (int k = 0; k < BPP; k++) a[k] = b[k] = c[k] = 0;
-    uint32_t known = 0;                                   // pixels of the row above known to be finished (lane 0)
     const int steps = npix + 31;
     for (int t = 0; t < steps; t++) {
+        if ((t & 31) == 0 && above && t < npix) {
+            // the next 32 pixels of the row above the group: one poll of the previous group's progress per 32 steps (not per
+            // step -- a poll is an L2 round trip and a fence, and the whole warp would wait for lane 0 on every pixel), then a
+            // coalesced read through L2 (this SM's L1 may hold the lines from before they were written)
+            const uint32_t need = (uint32_t)min(t + 32, npix);
+            if (lane == 0) { while (progress[g - 1] < need) __nanosleep(100); }
+            __syncwarp();
+            __threadfence();
+            const int px = t + lane;
+#pragma unroll
+            for (int k = 0; k < BPP; k++) sh_up[(t >> 5) & 1][lane * BPP + k] = (px < npix && px * BPP + k < rb) ? __ldcg(above + px * BPP + k) : (uint8_t)0;
+            __syncwarp();
+        }
         const int x = t - lane;
         const bool on = live && x >= 0 && x < npix;
-        // the row above: lane l - 1's pixel of the previous step; lane 0 fetches it from the previous group's last row
+        // the row above: lane l - 1's pixel of the previous step; lane 0 takes it from the staged copy of the previous group's last row
         int up[BPP];
 #pragma unroll
         for (int k = 0; k < BPP; k++) up[k] = __shfl_up_sync(0xFFFFFFFFu, a[k], 1);
         if (lane == 0) {
-            if (on && above) {
-                while (known <= (uint32_t)x) { known = progress[g - 1]; if (known <= (uint32_t)x) __nanosleep(40); }
-                __threadfence();
 #pragma unroll
-                for (int k = 0; k < BPP; k++) up[k] = x * BPP + k < rb ? __ldcg(above + x * BPP + k) : 0;      // L2: this SM's L1 may hold the line from before it was written
-            } else {
-#pragma unroll
-                for (int k = 0; k < BPP; k++) up[k] = 0;
-            }
+            for (int k = 0; k < BPP; k++) up[k] = (above && t < npix) ? sh_up[(t >> 5) & 1][(t & 31) * BPP + k] : 0;
         }
         if (on) {
 #pragma unroll
@@ -319,8 +372,8 @@ __global__ void __launch_bounds__(32) k_png_unfilter(const uint8_t *__restrict__
                 r[o + k] = (uint8_t)a[k];
             }
         }
-        // the last live lane publishes its progress for the next group
-        if (lane == 31 && on && ((x & 15) == 15 || x == npix - 1)) { __threadfence(); progress[g] = (uint32_t)(x + 1); }
+        // the last lane publishes its progress for the next group, 32 pixels at a time
+        if (lane == 31 && on && ((x & 31) == 31 || x == npix - 1)) { __threadfence(); progress[g] = (uint32_t)(x + 1); }
     }
 }
 
@@ -350,11 +403,13 @@ int launch_png_filter(const uint8_t *d_raw, uint8_t *d_filt, int h, int rb, int 
     size_t smem = strategy == PNGF_BIGRAMS ? 5 * 2048 * 4 : (strategy == PNGF_BIGENT ? 5 * 4096 * 4 : (strategy >= 5 && strategy != PNGF_MINSUM ? 5 * 256 * 4 : 0));
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_png_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 4096 * 4);   // per device, cheap
     k_png_filter<<<h, 256, smem, (cudaStream_t)stream>>>(d_raw, d_filt, h, rb, bpp, strategy, d_tlog);
+    LT_MARK("k_png_filter");
     return (int)cudaGetLastError();
 }
 int launch_png_match(const uint8_t *d_filt, uint32_t *d_best, size_t n, int bpp, int stride, void *stream)
 {
     k_png_match<<<cdivu(n, 256), 256, 0, (cudaStream_t)stream>>>(d_filt, d_best, n, bpp, stride, PARSE_CHUNK_MAX);
+    LT_MARK("k_png_match");
     return (int)cudaGetLastError();
 }
 int launch_png_hashmatch(const uint8_t *d_filt, uint32_t *d_best, size_t n, void *stream)
@@ -363,27 +418,33 @@ int launch_png_hashmatch(const uint8_t *d_filt, uint32_t *d_best, size_t n, void
     const size_t smem = ((sizeof(typename Sort::TempStorage) + 15) / 16) * 16 + (size_t)HM_SEG * 4;
     cudaFuncSetAttribute(k_png_hashmatch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      // per device; cheap to repeat
     k_png_hashmatch<<<cdivu(n, HM_SEG), HM_THREADS, smem, (cudaStream_t)stream>>>(d_filt, d_best, n, PARSE_CHUNK_MAX);
+    LT_MARK("k_png_hashmatch");
     return (int)cudaGetLastError();
 }
 int launch_png_parse(const uint32_t *d_best, const uint8_t *d_filt, size_t n, int chunk, uint32_t *d_tokens, uint32_t *d_counts, uint32_t *d_hist, void *stream)
 {
     const size_t nchunks = (n + chunk - 1) / chunk;
-    k_png_parse<<<cdivu(nchunks, 64), 64, 0, (cudaStream_t)stream>>>(d_best, d_filt, n, chunk, d_tokens, d_counts, d_hist);
+    if (chunk > PARSE_CHUNK_MAX || chunk % PARSE_THREADS) return (int)cudaErrorInvalidValue;
+    k_png_parse<<<(unsigned)nchunks, PARSE_THREADS, 0, (cudaStream_t)stream>>>(d_best, d_filt, n, chunk, d_tokens, d_counts, d_hist);
+    LT_MARK("k_png_parse");
     return (int)cudaGetLastError();
 }
 int launch_png_compact(const uint32_t *d_tokens, const uint32_t *d_counts, const uint32_t *d_offsets, size_t nchunks, int chunk, uint32_t *d_out, void *stream)
 {
     k_png_compact<<<(unsigned)nchunks, 128, 0, (cudaStream_t)stream>>>(d_tokens, d_counts, d_offsets, chunk, d_out);
+    LT_MARK("k_png_compact");
     return (int)cudaGetLastError();
 }
 int launch_png_adler(const uint8_t *d_filt, size_t n, unsigned long long *d_sums, void *stream)
 {
     k_png_adler<<<cdivu((n + 4095) / 4096, 64), 64, 0, (cudaStream_t)stream>>>(d_filt, n, d_sums);
+    LT_MARK("k_png_adler");
     return (int)cudaGetLastError();
 }
 int launch_png_probe(const uint8_t *d_raw, size_t npixels, int channels, uint32_t *d_flags, void *stream)
 {
     k_png_probe<<<cdivu(npixels, 256), 256, 0, (cudaStream_t)stream>>>(d_raw, npixels, channels, d_flags);
+    LT_MARK("k_png_probe");
     return (int)cudaGetLastError();
 }
 int launch_png_unfilter(const uint8_t *d_filt, uint8_t *d_raw, int h, int rb, int bpp, uint32_t *d_sync /*2 + ceil(h/32) words*/, void *stream)
@@ -401,18 +462,21 @@ int launch_png_unfilter(const uint8_t *d_filt, uint8_t *d_raw, int h, int rb, in
         case 8: k_png_unfilter<8><<<groups, 32, 0, st>>>(d_filt, d_raw, h, rb, ticket, progress, bad); break;
         default: return (int)cudaErrorInvalidValue;
     }
+    LT_MARK("k_png_unfilter");
     return (int)cudaGetLastError();
 }
 int launch_png_colours(const uint8_t *d_raw, size_t npixels, int channels, uint32_t *d_set /*2048 words, 8-byte aligned*/, uint32_t *d_flags, void *stream)
 {
     cudaMemsetAsync(d_set, 0, 2048 * 4, (cudaStream_t)stream);
-    k_png_colours<<<296, 256, 0, (cudaStream_t)stream>>>(d_raw, npixels, channels, reinterpret_cast<unsigned long long *>(d_set), d_flags);
+    k_png_colours<<<64, 256, 0, (cudaStream_t)stream>>>(d_raw, npixels, channels, reinterpret_cast<unsigned long long *>(d_set), d_flags);
+    LT_MARK("k_png_colours");
     return (int)cudaGetLastError();
 }
 int launch_png_repack(const uint8_t *d_raw, uint8_t *d_out, size_t npixels, int channels, int keep_mask, void *stream)
 {
     int kept = 0; for (int c = 0; c < channels; c++) if (keep_mask & (1 << c)) kept++;
     k_png_repack<<<cdivu(npixels, 256), 256, 0, (cudaStream_t)stream>>>(d_raw, d_out, npixels, channels, keep_mask, kept);
+    LT_MARK("k_png_repack");
     return (int)cudaGetLastError();
 }
 

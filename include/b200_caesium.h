@@ -197,6 +197,11 @@ b200_status b200_png_filter(const uint8_t *raw, int h, int row_bytes, int bpp, i
 b200_status b200_png_lz77(const uint8_t *filtered, size_t n, int bpp, int stride, uint32_t **tokens, size_t *ntokens, uint32_t *hist);
 /* host: DEFLATE (dynamic Huffman) + zlib framing of a token stream; adler = Adler-32 of the bytes the tokens expand to */
 b200_status b200_png_deflate_tokens(const uint32_t *tokens, size_t ntokens, uint32_t adler, uint8_t **out, size_t *out_len);
+/* the device side of b200_compress_in_memory on ONE PNG, timed: the file is parsed and inflated once, then the device pipeline
+ * (un-filter, checksum, probes, K6 / K7 per strategy, DEFLATE coding, H2D / D2H around it) runs `iters` times with a CUDA event
+ * after every launch.  text receives "name ms_per_launch launches\n" records (NUL-terminated, cap bytes); host decision waits between
+ * launches are listed as host_wait and are NOT device time.  bench.py's device-resident figure for BASELINE configs[3]. */
+b200_status b200_png_device_times(const uint8_t *in, size_t in_len, int level, int iters, char *text, size_t cap);
 /* strategies tried for an optimisation level (returns the count; out[] holds up to 10) */
 int b200_png_level_strategies(int level, int *out);
 

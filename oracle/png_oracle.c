@@ -166,7 +166,7 @@ static void hash_chain_matches(const uint8_t *s, size_t n, uint32_t *best)
                 for (int c = 0; c < HM_DEPTH && q >= 0 && bl < maxlen; c++, q = prev[q]) {
                     int d = (int)(i - seg0) - q, l = 0;
                     while (l < maxlen && s[i + l] == s[i + l - d]) l++;
-                    if (l > bl) { bl = l; bd = d; }
+                    if (l > bl && l >= (d <= 512 ? 4 : d <= 4096 ? 5 : 6)) { bl = l; bd = d; }      /* far matches must be long enough to pay for their distance code */
                 }
                 best[i] = bl >= 3 ? ((uint32_t)bl << 16) | (uint32_t)bd : 0;
             }
