@@ -68,7 +68,7 @@ _SYMBOLS = [
     "b200_jpeg_batch_time", "b200_jpeg_batch_destroy", "b200_jpeg_encode_coefficients_device",
     "b200_png_decode", "b200_png_decode_reduced", "b200_png_filter", "b200_png_lz77", "b200_png_deflate_tokens", "b200_png_level_strategies",
     "b200_webp_encode_rgb", "b200_webp_write_levels", "b200_webp_qindex",
-    "b200_jpeg_pipe_create", "b200_jpeg_pipe_run", "b200_jpeg_pipe_finish", "b200_jpeg_pipe_fetch", "b200_jpeg_pipe_kernel_times", "b200_jpeg_pipe_destroy", "b200_device_jobs", "b200_device_numa_node", "b200_png_device_times",
+    "b200_jpeg_pipe_create", "b200_jpeg_pipe_run", "b200_jpeg_pipe_finish", "b200_jpeg_pipe_fetch", "b200_jpeg_pipe_kernel_times", "b200_jpeg_pipe_destroy", "b200_device_jobs", "b200_device_numa_node", "b200_png_device_times", "b200_webp_decode",
 ]
 
 
@@ -86,7 +86,7 @@ def lib():
                   "b200_jpeg_batch_upload", "b200_jpeg_batch_run", "b200_jpeg_batch_download", "b200_jpeg_batch_time",
                   "b200_png_decode", "b200_png_decode_reduced", "b200_png_filter", "b200_png_lz77", "b200_png_deflate_tokens",
                   "b200_webp_encode_rgb", "b200_webp_write_levels", "b200_jpeg_encode_coefficients_device",
-                  "b200_jpeg_pipe_create", "b200_jpeg_pipe_run", "b200_jpeg_pipe_finish", "b200_jpeg_pipe_fetch", "b200_jpeg_pipe_kernel_times", "b200_png_device_times"):
+                  "b200_jpeg_pipe_create", "b200_jpeg_pipe_run", "b200_jpeg_pipe_finish", "b200_jpeg_pipe_fetch", "b200_jpeg_pipe_kernel_times", "b200_png_device_times", "b200_webp_decode"):
             getattr(L, f).restype = Status
         L.b200_version.restype = C.c_char_p
         L.b200_sniff_format.restype = C.c_uint32
@@ -326,6 +326,15 @@ def webp_encode_rgb(rgb, quality, want_stage=False):
                                       levels.ctypes.data_as(C.c_void_p) if want_stage else None, modes.ctypes.data_as(C.c_void_p) if want_stage else None))
     data = _take(outp, outl)
     return (data, levels, modes) if want_stage else data
+
+
+def webp_decode(data):
+    """Host VP8 decoder (bit-exact with libwebp): lossy .webp bytes -> uint8 [h, w, 3]."""
+    w, h, ptr = C.c_int(), C.c_int(), C.POINTER(C.c_uint8)()
+    _check(lib().b200_webp_decode(data, C.c_size_t(len(data)), C.byref(w), C.byref(h), C.byref(ptr)))
+    arr = np.frombuffer(C.string_at(ptr, 3 * w.value * h.value), dtype=np.uint8).reshape(3, h.value, w.value).transpose(1, 2, 0).copy()
+    lib().b200_free(ptr)
+    return arr
 
 
 def webp_write_levels(w, h, quality, levels, modes):

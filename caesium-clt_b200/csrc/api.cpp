@@ -26,6 +26,7 @@
 #include "png_device.h"
 #include "vp8_host.h"
 #include "webp_device.h"
+#include "vp8_decode.h"
 #include "jpeg_pipe.h"
 #include "topology.h"
 #include "launch_timer.h"
@@ -461,24 +462,20 @@ void png_expand_planar(const PngInfo &info, const std::vector<uint8_t> &raw, boo
     }
 }
 
-// PNG -> JPEG: the expanded samples are uploaded in place of the JPEG decode front end and take the resize path's back end
-// (K3 Lanczos3 when width/height are set, RGB -> YCbCr, K4 box downsample, K5 FDCT + quantise) and the device Huffman encoder.
-b200_status png_to_jpeg(const uint8_t *in, size_t in_len, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
+// Planar 8-bit samples on the host ([nc][H][W]: RGB or one grey plane) -> JPEG: they take the resize path's back end (K3 Lanczos3 when
+// width/height are set, RGB -> YCbCr, K4 box downsample, K5 FDCT + quantise) and the device Huffman encoder.
+b200_status planes_to_jpeg(const std::vector<uint8_t> &planes, uint32_t w, uint32_t h, int nc, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
 {
     std::string err;
-    PngInfo info; std::vector<uint8_t> raw;
-    if (!png_decode(in, in_len, false, info, raw, err)) return make_status(err.find("interlace") != std::string::npos ? B200_ERR_UNSUPPORTED : B200_ERR_CORRUPT_INPUT, err);
-    if (info.width > 65535 || info.height > 65535) return make_status(B200_ERR_INVALID_ARGUMENT, "image too large for JPEG");
-    std::vector<uint8_t> planes; int nc = 3;
-    png_expand_planar(info, raw, true, planes, nc);
-    JpegGeom gin; gin.width = (int)info.width; gin.height = (int)info.height; gin.ncomp = nc;
+    if (w > 65535 || h > 65535) return make_status(B200_ERR_INVALID_ARGUMENT, "image too large for JPEG");
+    JpegGeom gin; gin.width = (int)w; gin.height = (int)h; gin.ncomp = nc;
     for (int c = 0; c < nc; c++) { gin.cid[c] = c + 1; gin.hs[c] = gin.vs[c] = 1; gin.tq[c] = 0; }
     gin.finalize();
     JpegGeom gout;
     if (!jpeg_output_geom(gin, (int)p->jpeg_quality, (int)p->jpeg_chroma_subsampling, gout, err)) return make_status(B200_ERR_INVALID_ARGUMENT, err);
     if (p->width || p->height) {
         uint32_t nw = 0, nh = 0;
-        compute_resize_dimensions(info.width, info.height, p->width, p->height, nw, nh);
+        compute_resize_dimensions(w, h, p->width, p->height, nw, nh);
         if (nw == 0 || nh == 0 || nw > 65535 || nh > 65535) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid target dimensions");
         gout.width = (int)nw; gout.height = (int)nh; gout.finalize();
     }
@@ -500,6 +497,61 @@ b200_status png_to_jpeg(const uint8_t *in, size_t in_len, const b200_params *p, 
     } while (0);
     slot_release(s);
     return st;
+}
+
+b200_status png_to_jpeg(const uint8_t *in, size_t in_len, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
+{
+    std::string err;
+    PngInfo info; std::vector<uint8_t> raw;
+    if (!png_decode(in, in_len, false, info, raw, err)) return make_status(err.find("interlace") != std::string::npos ? B200_ERR_UNSUPPORTED : B200_ERR_CORRUPT_INPUT, err);
+    std::vector<uint8_t> planes; int nc = 3;
+    png_expand_planar(info, raw, true, planes, nc);
+    return planes_to_jpeg(planes, info.width, info.height, nc, p, prefer_dev, out);
+}
+
+// Planar RGB on the host -> lossy WebP (K3 resize when width / height are set, then K8)
+b200_status rgb_to_webp(const std::vector<uint8_t> &rgb, uint32_t w, uint32_t h, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
+{
+    std::string err;
+    uint32_t nw = w, nh = h;
+    if (p->width || p->height) compute_resize_dimensions(w, h, p->width, p->height, nw, nh);
+    if (nw == 0 || nh == 0 || nw > 16383 || nh > 16383 || w > 65535 || h > 65535) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid dimensions for WebP");
+    if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
+    Slot *s = slot_acquire(prefer_dev < 0 ? runtime_next_device() : prefer_dev, err);
+    if (!s) return make_status(B200_ERR_CUDA, err);
+    if (!s->webp) s->webp = new WebpDevice();
+    bool ok;
+    if (nw == w && nh == h) ok = s->webp->encode_host_rgb(rgb.data(), (int)nw, (int)nh, (int)p->webp_quality, s->stream, out, err);
+    else {   // through the resize leg (K3 Lanczos3) first
+        JpegGeom gin; gin.width = (int)w; gin.height = (int)h; gin.ncomp = 3;
+        for (int c = 0; c < 3; c++) { gin.cid[c] = c + 1; gin.hs[c] = gin.vs[c] = 1; gin.tq[c] = 0; }
+        gin.finalize();
+        JpegGeom gout = gin; gout.width = (int)nw; gout.height = (int)nh; gout.finalize();
+        uint8_t *planes[3] = {nullptr, nullptr, nullptr};
+        ok = slot_transform_resized(s, gin, gout, err, false, false, planes, rgb.data()) &&
+             s->webp->encode_planes(planes[0], planes[1], planes[2], (int)nw, (int)nh, (int)p->webp_quality, s->stream, out, err);
+    }
+    slot_release(s);
+    return ok ? ok_status() : make_status(B200_ERR_CUDA, err);
+}
+
+// WebP input (libcaesium webp::compress: decode, optional resize, re-encode at webp.quality): the VP8 bitstream is decoded on the
+// calling thread (format plumbing, bit-exact with libwebp's decoder -- vp8_decode.cpp), the RGB goes through K3 / K8 like any other source.
+b200_status webp_decode_status(const uint8_t *in, size_t in_len, WebpInfo &info, std::vector<uint8_t> &rgb)
+{
+    std::string err;
+    const int rc = webp_decode_rgb(in, in_len, info, rgb, err);
+    if (rc == 1) return make_status(B200_ERR_UNSUPPORTED, err);
+    if (rc) return make_status(B200_ERR_CORRUPT_INPUT, err);
+    return ok_status();
+}
+b200_status webp_compress(const uint8_t *in, size_t in_len, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
+{
+    if (p->webp_lossless) return make_status(B200_ERR_UNSUPPORTED, "lossless WebP (VP8L) is outside the GPU path (route to caesium::compress_in_memory)");
+    WebpInfo info; std::vector<uint8_t> rgb;
+    b200_status st = webp_decode_status(in, in_len, info, rgb);
+    if (st.code) return st;
+    return rgb_to_webp(rgb, (uint32_t)info.width, (uint32_t)info.height, p, prefer_dev, out);
 }
 
 // PNG source: samples are expanded to 8-bit RGB on the host (palette, grey, 16-bit -> high byte; an opaque alpha channel is
@@ -526,23 +578,45 @@ b200_status png_to_webp(const uint8_t *in, size_t in_len, const b200_params *p, 
     }
     std::vector<uint8_t> rgb; int nc = 3;
     png_expand_planar(info, raw, false, rgb, nc);
+    return rgb_to_webp(rgb, info.width, info.height, p, prefer_dev, out);
+}
+
+// Planar RGB on the host -> lossless PNG (K3 resize when asked, then the PNG leg's raw-sample entry point)
+b200_status rgb_to_png(const std::vector<uint8_t> &rgb, uint32_t w, uint32_t h, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
+{
+    std::string err;
+    uint32_t nw = w, nh = h;
+    if (p->width || p->height) compute_resize_dimensions(w, h, p->width, p->height, nw, nh);
+    if (nw == 0 || nh == 0 || nw > 65535 || nh > 65535 || w > 65535 || h > 65535) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid target dimensions");
     if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
     Slot *s = slot_acquire(prefer_dev < 0 ? runtime_next_device() : prefer_dev, err);
     if (!s) return make_status(B200_ERR_CUDA, err);
-    if (!s->webp) s->webp = new WebpDevice();
-    bool ok;
-    if (nw == info.width && nh == info.height) ok = s->webp->encode_host_rgb(rgb.data(), (int)nw, (int)nh, (int)p->webp_quality, s->stream, out, err);
-    else {   // through the resize leg (K3 Lanczos3) first
-        JpegGeom gin; gin.width = (int)info.width; gin.height = (int)info.height; gin.ncomp = 3;
-        for (int c = 0; c < 3; c++) { gin.cid[c] = c + 1; gin.hs[c] = gin.vs[c] = 1; gin.tq[c] = 0; }
-        gin.finalize();
-        JpegGeom gout = gin; gout.width = (int)nw; gout.height = (int)nh; gout.finalize();
-        uint8_t *planes[3] = {nullptr, nullptr, nullptr};
-        ok = slot_transform_resized(s, gin, gout, err, false, false, planes, rgb.data()) &&
-             s->webp->encode_planes(planes[0], planes[1], planes[2], (int)nw, (int)nh, (int)p->webp_quality, s->stream, out, err);
-    }
+    b200_status st = ok_status();
+    const size_t n = (size_t)nw * nh;
+    std::vector<uint8_t> planes, raw(3 * n);
+    const uint8_t *src = rgb.data();
+    do {
+        if (nw != w || nh != h) {
+            JpegGeom gin; gin.width = (int)w; gin.height = (int)h; gin.ncomp = 3;
+            for (int c = 0; c < 3; c++) { gin.cid[c] = c + 1; gin.hs[c] = gin.vs[c] = 1; gin.tq[c] = 0; }
+            gin.finalize();
+            JpegGeom gout = gin; gout.width = (int)nw; gout.height = (int)nh; gout.finalize();
+            uint8_t *dp[3] = {nullptr, nullptr, nullptr};
+            planes.resize(3 * n);
+            if (!slot_transform_resized(s, gin, gout, err, false, false, dp, rgb.data()) || !slot_fetch_planes(s, dp, 3, n, planes.data(), err)) { st = make_status(B200_ERR_CUDA, err); break; }
+            src = planes.data();
+        }
+        for (size_t i = 0; i < n; i++) { raw[3 * i] = src[i]; raw[3 * i + 1] = src[n + i]; raw[3 * i + 2] = src[2 * n + i]; }
+        PngInfo info; info.width = nw; info.height = nh; info.bit_depth = 8; info.color_type = 2; info.channels = 3; info.bits_per_pixel = 24; info.bpp = 3; info.row_bytes = (size_t)nw * 3;
+        png_reduce_palette(info, raw);
+        if (!s->png) s->png = new PngDevice();
+        std::vector<uint8_t> z;
+        int level = (int)p->png_optimization_level; if (level > 6) level = 6;
+        if (!s->png->compress(info, raw, level, s->stream, z, nullptr, err)) { st = make_status(B200_ERR_CUDA, err); break; }
+        png_write(info, z, out);
+    } while (0);
     slot_release(s);
-    return ok ? ok_status() : make_status(B200_ERR_CUDA, err);
+    return st;
 }
 
 b200_status compress_dispatch(const uint8_t *in, size_t in_len, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
@@ -550,7 +624,7 @@ b200_status compress_dispatch(const uint8_t *in, size_t in_len, const b200_param
     switch (b200_sniff_format(in, in_len)) {
         case B200_FMT_JPEG: return jpeg_compress(in, in_len, p, prefer_dev, out);
         case B200_FMT_PNG: return png_compress(in, in_len, p, prefer_dev, out);
-        case B200_FMT_WEBP: return make_status(B200_ERR_UNSUPPORTED, "WebP is not implemented on the GPU path yet");
+        case B200_FMT_WEBP: return webp_compress(in, in_len, p, prefer_dev, out);
         case B200_FMT_GIF: return make_status(B200_ERR_UNSUPPORTED, "GIF is outside the GPU path (route to caesium::compress_in_memory)");
         case B200_FMT_TIFF: return make_status(B200_ERR_UNSUPPORTED, "TIFF is outside the GPU path (route to caesium::compress_in_memory)");
         default: return make_status(B200_ERR_UNKNOWN_FORMAT, "Unknown file type");
@@ -785,6 +859,19 @@ b200_status b200_convert_in_memory(const uint8_t *in, size_t in_len, const b200_
         try { std::vector<uint8_t> v; b200_status s = jpeg_to_png(in, in_len, params, -1, v); if (s.code) return s; return give(v, out, out_len); }
         catch (const std::exception &e) { return make_status(B200_ERR_OUT_OF_MEMORY, e.what()); }
     }
+    if (src == B200_FMT_WEBP && (fmt == B200_FMT_JPEG || fmt == B200_FMT_PNG)) {
+        // WebP source: decoded on the calling thread (vp8_decode.cpp), then the same back ends as a PNG source
+        try {
+            if (fmt == B200_FMT_JPEG && params->jpeg_optimize) return make_status(B200_ERR_UNSUPPORTED, "lossless conversion to JPEG is outside the GPU path (route to caesium::convert_in_memory)");
+            if (fmt == B200_FMT_PNG && !params->png_optimize) return make_status(B200_ERR_UNSUPPORTED, "lossy PNG (imagequant) is outside the GPU path (route to caesium::convert_in_memory)");
+            WebpInfo wi; std::vector<uint8_t> rgb, v;
+            b200_status s = webp_decode_status(in, in_len, wi, rgb);
+            if (s.code) return s;
+            s = fmt == B200_FMT_JPEG ? planes_to_jpeg(rgb, (uint32_t)wi.width, (uint32_t)wi.height, 3, params, -1, v) : rgb_to_png(rgb, (uint32_t)wi.width, (uint32_t)wi.height, params, -1, v);
+            if (s.code) return s;
+            return give(v, out, out_len);
+        } catch (const std::exception &e) { return make_status(B200_ERR_OUT_OF_MEMORY, e.what()); }
+    }
     if (!to_webp && !png_to_jpg) return make_status(B200_ERR_UNSUPPORTED, "this conversion is outside the GPU path (route to caesium::convert_in_memory)");
     if (to_webp && params->webp_lossless) return make_status(B200_ERR_UNSUPPORTED, "lossless WebP (VP8L) is outside the GPU path (route to caesium::convert_in_memory)");
     if (png_to_jpg && params->jpeg_optimize) return make_status(B200_ERR_UNSUPPORTED, "lossless conversion to JPEG is outside the GPU path (route to caesium::convert_in_memory)");
@@ -799,6 +886,42 @@ b200_status b200_convert_in_memory(const uint8_t *in, size_t in_len, const b200_
     } catch (const std::exception &e) { return make_status(B200_ERR_OUT_OF_MEMORY, e.what()); }
 }
 
+// WebP: the source is decoded once, its RGB uploaded once (resized once if asked); every try runs K8 at the try's quality and the
+// host boolean coder.
+static b200_status webp_to_size(const uint8_t *in, size_t in_len, b200_params *params, size_t max_output_size, bool return_smallest, std::vector<uint8_t> &result)
+{
+    if (params->webp_lossless) return make_status(B200_ERR_UNSUPPORTED, "lossless WebP (VP8L) is outside the GPU path (route to caesium::compress_to_size_in_memory)");
+    std::string err;
+    WebpInfo wi; std::vector<uint8_t> rgb;
+    b200_status st = webp_decode_status(in, in_len, wi, rgb);
+    if (st.code) return st;
+    uint32_t w = (uint32_t)wi.width, h = (uint32_t)wi.height, nw = w, nh = h;
+    if (params->width || params->height) compute_resize_dimensions(w, h, params->width, params->height, nw, nh);
+    if (nw == 0 || nh == 0 || nw > 16383 || nh > 16383) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid dimensions for WebP");
+    if (!ensure_runtime(err)) return make_status(B200_ERR_NO_DEVICE, err);
+    Slot *s = slot_acquire(runtime_next_device(), err);
+    if (!s) return make_status(B200_ERR_CUDA, err);
+    if (!s->webp) s->webp = new WebpDevice();
+    do {
+        uint8_t *planes[3] = {nullptr, nullptr, nullptr};
+        JpegGeom gin; gin.width = (int)w; gin.height = (int)h; gin.ncomp = 3;
+        for (int c = 0; c < 3; c++) { gin.cid[c] = c + 1; gin.hs[c] = gin.vs[c] = 1; gin.tq[c] = 0; }
+        gin.finalize();
+        JpegGeom gout = gin; gout.width = (int)nw; gout.height = (int)nh; gout.finalize();
+        // the (possibly resized) RGB planes stay in the slot's scratch memory for all tries
+        if (!slot_transform_resized(s, gin, gout, err, false, false, planes, rgb.data())) { st = make_status(B200_ERR_CUDA, err); break; }
+        auto size_at = [&](int q, auto want, size_t &sz, std::vector<uint8_t> &cur) -> b200_status {
+            std::string e2; (void)want;
+            if (!s->webp->encode_planes(planes[0], planes[1], planes[2], (int)nw, (int)nh, q, s->stream, cur, e2)) return make_status(B200_ERR_CUDA, e2);
+            sz = cur.size();
+            return ok_status();
+        };
+        st = bisect_quality(size_at, max_output_size, return_smallest, &params->webp_quality, result);
+    } while (0);
+    slot_release(s);
+    return st;
+}
+
 b200_status b200_compress_to_size_in_memory(const uint8_t *in, size_t in_len, b200_params *params, size_t max_output_size, uint8_t return_smallest,
                                             uint8_t **out, size_t *out_len)
 {
@@ -811,6 +934,7 @@ b200_status b200_compress_to_size_in_memory(const uint8_t *in, size_t in_len, b2
         std::vector<uint8_t> result;
         b200_status s;
         if (fmt == B200_FMT_JPEG) s = jpeg_to_size(in, in_len, params, max_output_size, return_smallest != 0, result);
+        else if (fmt == B200_FMT_WEBP) s = webp_to_size(in, in_len, params, max_output_size, return_smallest != 0, result);
         else if (fmt == B200_FMT_PNG) s = make_status(B200_ERR_UNSUPPORTED, "compress_to_size on a PNG bisects the lossy (imagequant) quality, which is outside the GPU path (route to caesium::compress_to_size_in_memory)");
         else s = make_status(fmt == B200_FMT_UNKNOWN ? B200_ERR_UNKNOWN_FORMAT : B200_ERR_UNSUPPORTED, "compress_to_size for this format is outside the GPU path (route to caesium::compress_to_size_in_memory)");
         if (s.code) return s;
@@ -1180,6 +1304,19 @@ b200_status b200_webp_encode_rgb(const uint8_t *rgb, int w, int h, int quality, 
     const bool ok = s->webp->encode_host_rgb(rgb, w, h, quality, s->stream, v, err, levels, modes);
     slot_release(s);
     return ok ? give(v, out, out_len) : make_status(B200_ERR_CUDA, err);
+}
+b200_status b200_webp_decode(const uint8_t *in, size_t in_len, int *width, int *height, uint8_t **rgb)
+{
+    if (!in || !width || !height || !rgb) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    *rgb = nullptr;
+    try {
+        WebpInfo wi; std::vector<uint8_t> v;
+        b200_status s = webp_decode_status(in, in_len, wi, v);
+        if (s.code) return s;
+        *width = wi.width; *height = wi.height;
+        size_t n = 0;
+        return give(v, rgb, &n);
+    } catch (const std::exception &e) { return make_status(B200_ERR_OUT_OF_MEMORY, e.what()); }
 }
 b200_status b200_webp_write_levels(int w, int h, int quality, const int16_t *levels, const uint8_t *modes, uint8_t **out, size_t *out_len)
 {

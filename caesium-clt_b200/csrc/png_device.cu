@@ -76,7 +76,7 @@ bool PngDevice::run_strategy(int strategy, int h, int rb, int bpp, void *stream_
     if (!filt) filt = d_filt;
     int rc = do_filter ? launch_png_filter(d_raw, filt, h, rb, bpp, strategy, d_tlog, st) : 0;
     if (!rc) rc = launch_png_match(filt, d_best, n, bpp, rb + 1, st);
-    if (!rc && with_hash) rc = launch_png_hashmatch(filt, d_best, n, st);
+    if (!rc && with_hash) rc = launch_png_hashmatch(filt, d_best, n, d_hist + 2048, st);
     if (rc) { err = std::string("png kernels: ") + cudaGetErrorString((cudaError_t)rc); return false; }
     CUP(cudaMemsetAsync(d_hist, 0, 316 * 4, st));
     rc = launch_png_parse(d_best, filt, n, kChunk, d_tok, d_counts, d_hist, st);
@@ -321,11 +321,11 @@ bool png_stage_lz77(const uint8_t *filtered, size_t n, int bpp, int stride, std:
         size_t tb = 0; cub::DeviceScan::ExclusiveSum((void *)nullptr, tb, d_counts, d_offsets, (int)nchunks);
         if (cudaMalloc(&d_filt, n + 64) != cudaSuccess || cudaMalloc(&d_best, n * 4 + 64) != cudaSuccess || cudaMalloc(&d_tok, n * 4 + 64) != cudaSuccess ||
             cudaMalloc(&d_out, n * 4 + 64) != cudaSuccess || cudaMalloc(&d_counts, nchunks * 4 + 4) != cudaSuccess || cudaMalloc(&d_offsets, nchunks * 4 + 4) != cudaSuccess ||
-            cudaMalloc(&d_hist, 316 * 4) != cudaSuccess || cudaMalloc(&d_temp, tb + 256) != cudaSuccess) { err = "cudaMalloc failed"; break; }
+            cudaMalloc(&d_hist, (320 + 544) * 4) != cudaSuccess || cudaMalloc(&d_temp, tb + 256) != cudaSuccess) { err = "cudaMalloc failed"; break; }
         cudaMemset(d_filt + n, 0, 64);
         cudaMemcpy(d_filt, filtered, n, cudaMemcpyHostToDevice);
         cudaMemset(d_hist, 0, 316 * 4);
-        if (launch_png_match(d_filt, d_best, n, bpp, stride, nullptr) || launch_png_hashmatch(d_filt, d_best, n, nullptr) || launch_png_parse(d_best, d_filt, n, kChunk, d_tok, d_counts, d_hist, nullptr)) { err = "png lz77 launch failed"; break; }
+        if (launch_png_match(d_filt, d_best, n, bpp, stride, nullptr) || launch_png_hashmatch(d_filt, d_best, n, d_hist + 320, nullptr) || launch_png_parse(d_best, d_filt, n, kChunk, d_tok, d_counts, d_hist, nullptr)) { err = "png lz77 launch failed"; break; }
         cub::DeviceScan::ExclusiveSum(d_temp, tb, d_counts, d_offsets, (int)nchunks);
         if (launch_png_compact(d_tok, d_counts, d_offsets, nchunks, kChunk, d_out, nullptr)) { err = "png compact launch failed"; break; }
         uint32_t last[2];

@@ -135,14 +135,49 @@ __global__ void k_png_match(const uint8_t *__restrict__ s, uint32_t *__restrict_
 // (which reach back a whole row or two) do.  A hash candidate replaces the current best only if it is strictly longer, so the
 // result is deterministic: the oracle twin walks ordinary head / prev chains and arrives at the same matches.
 constexpr int HM_SEG = 16384, HM_THREADS = 512, HM_ITEMS = HM_SEG / HM_THREADS, HM_DEPTH = 4;
-// A match at an arbitrary distance has to pay for its distance code: in noisy (photographic) residuals three or four bytes repeat
-// by chance all the time, and coding those as far matches costs more bits than the literals would (and flattens the distance
-// statistics for the matches that matter).  zlib's TOO_FAR rule, extended: the farther, the longer a hash match must be.
-__device__ __forceinline__ int hash_min_len(int d) { return d <= 512 ? 4 : d <= 4096 ? 5 : 6; }
+// A match at an arbitrary distance has to pay for its distance code, and what it saves depends on how cheap the literals it
+// replaces are: in photographic residuals (3 - 4 bits per byte after Huffman coding) a 5-byte repeat 10,000 bytes back costs more
+// than its literals and flattens the distance statistics of the matches that matter; in text or flat art the bytes a repeat covers
+// are the rare, expensive ones.  So the stream is measured first -- a byte histogram, from it the order-0 cost of every byte value
+// in 1024ths of a bit (integer arithmetic, the same on the device and in the oracle) -- and a hash candidate is accepted when the
+// literals it would replace cost at least 1.25 x (7 bits of length code + 5 of distance code + the distance's extra bits).
+// (zlib's TOO_FAR rule, made proportional.)  The fixed pixel / row candidates are not subject to it.
+__host__ __device__ inline uint32_t log2_q10(unsigned long long x)
+{   // 1024 * log2(x), piecewise linear between powers of two (exact at them, at most 0.09 low in between); x >= 1
+    int e = 63; while (!((x >> e) & 1ull)) e--;
+    const unsigned long long frac = e >= 10 ? (x >> (e - 10)) & 1023ull : (x << (10 - e)) & 1023ull;
+    return (uint32_t)e * 1024u + (uint32_t)frac;
+}
+// cost[0..255] = literal costs, cost[256..285] = match cost per distance code
+__host__ __device__ inline void hash_cost_tables(const uint32_t *hist256, unsigned long long n, uint32_t *cost /*286*/)
+{
+    const uint32_t ln = log2_q10(n ? n : 1);
+    for (int v = 0; v < 256; v++) { const uint32_t c = hist256[v] ? ln - log2_q10(hist256[v]) : 16u * 1024u; cost[v] = c < 256u ? 256u : c; }
+    for (int ds = 0; ds < 30; ds++) cost[256 + ds] = (uint32_t)(7 + 5 + (ds < 4 ? 0 : (ds >> 1) - 1)) * 1280u;
+}
+__global__ void __launch_bounds__(256) k_png_bytehist(const uint8_t *__restrict__ s, size_t n, uint32_t *__restrict__ hist)
+{
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (size_t)gridDim.x * blockDim.x * 4) {
+        if (i + 4 <= n) { const uint32_t w = *reinterpret_cast<const uint32_t *>(s + i); atomicAdd(&h[w & 0xFF], 1u); atomicAdd(&h[(w >> 8) & 0xFF], 1u); atomicAdd(&h[(w >> 16) & 0xFF], 1u); atomicAdd(&h[w >> 24], 1u); }
+        else for (size_t k = i; k < n; k++) atomicAdd(&h[s[k]], 1u);
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+}
+__global__ void k_png_costs(const uint32_t *__restrict__ hist, size_t n, uint32_t *__restrict__ cost)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) hash_cost_tables(hist, n, cost);
+}
+__device__ __forceinline__ int dist_symbol_early(int d) { if (d <= 4) return d - 1; const int v = d - 1, hb = 31 - __clz(v); return hb * 2 + ((v >> (hb - 1)) & 1); }
 __device__ __forceinline__ uint32_t hash3(const uint8_t *__restrict__ p) { return (((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16)) * 2654435761u) >> 16; }
 
-__global__ void __launch_bounds__(HM_THREADS) k_png_hashmatch(const uint8_t *__restrict__ s, uint32_t *__restrict__ best, size_t n, int chunk)
+__global__ void __launch_bounds__(HM_THREADS) k_png_hashmatch(const uint8_t *__restrict__ s, uint32_t *__restrict__ best, size_t n, int chunk, const uint32_t *__restrict__ cost_tab)
 {
+    __shared__ uint32_t cost[286];
+    if (threadIdx.x < 286) cost[threadIdx.x] = cost_tab[threadIdx.x];
     using Sort = cub::BlockRadixSort<uint16_t, HM_THREADS, HM_ITEMS, uint16_t>;
     extern __shared__ __align__(16) unsigned char hm_smem[];
     typename Sort::TempStorage &temp = *reinterpret_cast<typename Sort::TempStorage *>(hm_smem);
@@ -179,7 +214,11 @@ __global__ void __launch_bounds__(HM_THREADS) k_png_hashmatch(const uint8_t *__r
             const int d = (int)local - (int)sh_pos[k - c];
             if (bl > 0 && s[i + bl] != s[i + bl - d]) continue;      // cannot beat the current best
             const int l = match_len(s, i, d, maxlen);
-            if (l > bl && l >= hash_min_len(d)) { bl = l; bd = d; }
+            if (l > bl && l >= 4) {        // the literals it replaces must cost at least what the match costs
+                const uint32_t need = cost[256 + dist_symbol_early(d)]; uint32_t worth = 0;
+                for (int k2 = 0; k2 < l && worth < need; k2++) worth += cost[s[i + k2]];
+                if (worth >= need) { bl = l; bd = d; }
+            }
             if (bl == maxlen) break;
         }
         best[i] = bl >= 3 ? ((uint32_t)bl << 16) | (uint32_t)bd : 0u;
@@ -412,12 +451,17 @@ int launch_png_match(const uint8_t *d_filt, uint32_t *d_best, size_t n, int bpp,
     LT_MARK("k_png_match");
     return (int)cudaGetLastError();
 }
-int launch_png_hashmatch(const uint8_t *d_filt, uint32_t *d_best, size_t n, void *stream)
+int launch_png_hashmatch(const uint8_t *d_filt, uint32_t *d_best, size_t n, uint32_t *d_work /*256 + 286 words*/, void *stream)
 {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(d_work, 0, 256 * 4, st);
+    k_png_bytehist<<<296, 256, 0, st>>>(d_filt, n, d_work);
+    k_png_costs<<<1, 32, 0, st>>>(d_work, n, d_work + 256);
+    LT_MARK("k_png_bytehist");
     using Sort = cub::BlockRadixSort<uint16_t, HM_THREADS, HM_ITEMS, uint16_t>;
     const size_t smem = ((sizeof(typename Sort::TempStorage) + 15) / 16) * 16 + (size_t)HM_SEG * 4;
     cudaFuncSetAttribute(k_png_hashmatch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      // per device; cheap to repeat
-    k_png_hashmatch<<<cdivu(n, HM_SEG), HM_THREADS, smem, (cudaStream_t)stream>>>(d_filt, d_best, n, PARSE_CHUNK_MAX);
+    k_png_hashmatch<<<cdivu(n, HM_SEG), HM_THREADS, smem, st>>>(d_filt, d_best, n, PARSE_CHUNK_MAX, d_work + 256);
     LT_MARK("k_png_hashmatch");
     return (int)cudaGetLastError();
 }

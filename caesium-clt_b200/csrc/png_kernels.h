@@ -18,8 +18,9 @@ int launch_png_filter(const uint8_t *d_raw, uint8_t *d_filt, int h, int rb, int 
 // K7 phase 1: best (length << 16 | distance) per position of the filtered stream (0 = no match of length >= 3).
 int launch_png_match(const uint8_t *d_filt, uint32_t *d_best, size_t n, int bpp, int stride, void *stream);
 // K7 phase 1b: hash-chain candidates at arbitrary distances (nearest 4 earlier positions with the same 3-byte hash inside a
-// 16,384-position segment) improve d_best where they are strictly longer
-int launch_png_hashmatch(const uint8_t *d_filt, uint32_t *d_best, size_t n, void *stream);
+// 16,384-position segment) improve d_best where they are strictly longer AND long enough to pay for their distance code given
+// how cheap the stream's literals are (order-0 entropy of the stream, measured first)
+int launch_png_hashmatch(const uint8_t *d_filt, uint32_t *d_best, size_t n, uint32_t *d_work /*544 words: byte histogram + cost tables*/, void *stream);
 // K7 phase 2: greedy/lazy parse per chunk of `chunk` positions into tokens (chunk-local slots) + per-chunk counts,
 // plus the litlen/dist symbol histogram (316 counters) used to estimate the DEFLATE size of the strategy.
 int launch_png_parse(const uint32_t *d_best, const uint8_t *d_filt, size_t n, int chunk, uint32_t *d_tokens, uint32_t *d_counts, uint32_t *d_hist, void *stream);

@@ -211,6 +211,10 @@ int b200_png_level_strategies(int level, int *out);
  * zigzag order), modes [mbh*mbw][4] = {ymode, uvmode, skip, 0} with modes 0 DC, 1 TM, 2 V, 3 H; mbw = ceil(w/16). */
 b200_status b200_webp_encode_rgb(const uint8_t *rgb, int w, int h, int quality, uint8_t **out, size_t *out_len,
                                  int16_t *levels, uint8_t *modes);
+/* host: decode a lossy (VP8) still WebP to planar RGB [3][h][w] exactly as libwebp's WebPDecodeRGB does -- the front end of
+ * compress_in_memory / convert_in_memory / compress_to_size_in_memory on WebP inputs (lossless, alpha, animation: code 3).
+ * *rgb is library-allocated. */
+b200_status b200_webp_decode(const uint8_t *in, size_t in_len, int *width, int *height, uint8_t **rgb);
 /* host only: boolean-code levels + modes (layout above) into a .webp file -- the entropy-coding half on its own */
 b200_status b200_webp_write_levels(int w, int h, int quality, const int16_t *levels, const uint8_t *modes, uint8_t **out, size_t *out_len);
 /* libwebp's quality -> quantiser index curve and the six dequantisation factors (y1 dc/ac, y2 dc/ac, uv dc/ac) it selects */

@@ -149,8 +149,29 @@ static uint32_t best_match(const uint8_t *s, size_t n, size_t i, int bpp, int st
  * pairs per segment -- caesium-clt_b200/csrc/png_kernels.cu k_png_hashmatch.) */
 #define HM_SEG 16384
 #define HM_DEPTH 4
+#define COSTF 1280u          /* 1.25 x 1024 */
+/* 1024 * log2(x), piecewise linear between powers of two; x >= 1 (the product's log2_q10) */
+static uint32_t log2_q10(unsigned long long x)
+{
+    int e = 63; while (!((x >> e) & 1ull)) e--;
+    unsigned long long frac = e >= 10 ? (x >> (e - 10)) & 1023ull : (x << (10 - e)) & 1023ull;
+    return (uint32_t)e * 1024u + (uint32_t)frac;
+}
+/* What a hash match must be worth: the order-0 cost (1024ths of a bit) of every byte value of this stream, and the cost of a match
+ * per distance code (7 bits of length code + 5 of distance code + the extra bits, x 1.25).  A candidate is accepted when the
+ * literals it replaces would cost at least that much. */
+static void hash_cost_tables(const uint8_t *s, size_t n, uint32_t *litcost /*256*/, uint32_t *matchcost /*30*/)
+{
+    uint32_t hist[256]; memset(hist, 0, sizeof hist);
+    for (size_t i = 0; i < n; i++) hist[s[i]]++;
+    uint32_t ln = log2_q10(n ? n : 1);
+    for (int v = 0; v < 256; v++) { uint32_t c = hist[v] ? ln - log2_q10(hist[v]) : 16 * 1024; litcost[v] = c < 256 ? 256 : c; }
+    for (int ds = 0; ds < 30; ds++) matchcost[ds] = (uint32_t)(7 + 5 + (ds < 4 ? 0 : (ds >> 1) - 1)) * COSTF;
+}
+
 static void hash_chain_matches(const uint8_t *s, size_t n, uint32_t *best)
 {
+    uint32_t litcost[256], matchcost[30]; hash_cost_tables(s, n, litcost, matchcost);
     int32_t *head = (int32_t *)malloc(65536 * 4), *prev = (int32_t *)malloc(HM_SEG * 4);
     for (size_t seg0 = 0; seg0 < n; seg0 += HM_SEG) {
         memset(head, 0xFF, 65536 * 4);
@@ -166,7 +187,11 @@ static void hash_chain_matches(const uint8_t *s, size_t n, uint32_t *best)
                 for (int c = 0; c < HM_DEPTH && q >= 0 && bl < maxlen; c++, q = prev[q]) {
                     int d = (int)(i - seg0) - q, l = 0;
                     while (l < maxlen && s[i + l] == s[i + l - d]) l++;
-                    if (l > bl && l >= (d <= 512 ? 4 : d <= 4096 ? 5 : 6)) { bl = l; bd = d; }      /* far matches must be long enough to pay for their distance code */
+                    if (l > bl && l >= 4) {      /* the literals it replaces must cost at least what the match costs */
+                        uint32_t worth = 0, need = matchcost[dist_symbol(d)];
+                        for (int k = 0; k < l && worth < need; k++) worth += litcost[s[i + k]];
+                        if (worth >= need) { bl = l; bd = d; }
+                    }      /* far matches must be long enough to pay for their distance code */
                 }
                 best[i] = bl >= 3 ? ((uint32_t)bl << 16) | (uint32_t)bd : 0;
             }

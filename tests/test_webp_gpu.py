@@ -192,3 +192,53 @@ def test_convert_full_size_config5_shape(L, O):
     assert out == O.webp_encode(rgb, 85)[0]
     dec = pil_decode(out)
     assert dec.shape == (nh, nw, 3) and np.abs(dec.astype(int) - rgb.transpose(1, 2, 0).astype(int)).mean() < 3.0
+
+
+# ---- round 2: WebP input ----------------------------------------------------------------------------------------------------------
+def _sample(name):
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_samples", name), "rb") as f:
+        return f.read()
+
+
+@pytest.mark.parametrize("name", ["w0.webp", "w1.webp"])
+def test_compress_webp_input_matches_oracle(L, O, name):
+    """caesium::compress_in_memory on a WebP (the reference's own samples): decode (host, == libwebp) -> K8 at webp.quality; the
+    file is the oracle's encoding of libwebp's decode, also with a resize in between."""
+    data = _sample(name)
+    rgb = planar(pil_decode(data))
+    for q in (80, 40):
+        p = L.default_params(); p.webp_quality = q
+        assert L.compress_in_memory(data, p) == O.webp_encode(rgb, q)[0], (name, q)
+    p = L.default_params(); p.webp_quality = 75; p.width = 200
+    nw, nh = O.compute_dimensions(rgb.shape[2], rgb.shape[1], 200, 0)
+    want = O.webp_encode(np.stack([O.resize_plane(np.ascontiguousarray(rgb[c]), nw, nh) for c in range(3)]), 75)[0]
+    assert L.compress_in_memory(data, p) == want
+
+
+def test_convert_from_webp_and_compress_to_size(L, O):
+    data = _sample("w0.webp")
+    rgb = planar(pil_decode(data))
+    # WebP -> JPEG: the PNG -> JPEG back end on the decoded pixels
+    p = L.default_params(); p.jpeg_quality, p.jpeg_chroma_subsampling, p.jpeg_progressive = 80, 420, 1
+    op = O.params(80, 420, True)
+    assert L.convert_in_memory(data, p, FMT_JPEG) == O.write(O.forward(O.rgb_to_ycc(rgb), op), op)
+    # WebP -> lossless PNG: holds exactly the decoded pixels
+    from pngutil import pil_pixels
+    p = L.default_params(); p.png_optimize = 1
+    out = L.convert_in_memory(data, p, FMT_PNG)
+    assert np.array_equal(np.asarray(pil_pixels(out).convert("RGB")).transpose(2, 0, 1), rgb)
+    # compress_to_size on a WebP: quality bisection with the pixels resident on the device; the answer is the oracle's file at the
+    # quality the call reports
+    target = len(data) // 2
+    p = L.default_params(); p.webp_quality = 80
+    out = L.compress_to_size_in_memory(data, p, target)
+    assert len(out) <= target and out[:4] == b"RIFF"
+    assert out == O.webp_encode(rgb, int(p.webp_quality))[0]
+    # the convert-then-size arm of the reference (compressor.rs:288-299): JPEG -> WebP, then to size
+    src = _sample("j1.jpg")
+    p = L.default_params(); p.webp_quality = 80; p.width = 400
+    conv = L.convert_in_memory(src, p, FMT_WEBP)
+    p2 = L.default_params(); p2.webp_quality = 80
+    sized = L.compress_to_size_in_memory(conv, p2, len(conv) // 2)
+    assert len(sized) <= len(conv) // 2 and pil_decode(sized).shape == pil_decode(conv).shape

@@ -101,3 +101,60 @@ def test_host_writer_extreme_levels(L):
     data = L.webp_write_levels(w, h, 50, levels, modes)
     dec = pil_decode(data)                      # libwebp must parse it to the last macroblock without error
     assert dec.shape == (h, w, 3)
+
+
+# ---- round 2: WebP INPUT -- the host VP8 decoder in front of the device encoder -------------------------------------------------
+import io
+import os
+
+SAMPLES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_samples")
+
+
+def _pil_rgb(data):
+    from PIL import Image
+    return np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+
+
+@pytest.mark.parametrize("name", ["w0.webp", "w1.webp"])
+def test_vp8_decoder_equals_libwebp_on_the_reference_samples(L, name):
+    """compress_in_memory on samples/w0.webp must succeed (compressor.rs:769-787); its first step is this decode: RIFF / VP8X
+    container, RFC 6386 key frame (segments, B_PRED sub-block modes, token partitions, normal / simple loop filter), libwebp's fancy
+    upsampling and fixed-point YUV -> RGB.  Bit-exact with libwebp (through Pillow)."""
+    with open(os.path.join(SAMPLES, name), "rb") as f:
+        data = f.read()
+    got = L.webp_decode(data)
+    assert np.array_equal(got, _pil_rgb(data))
+
+
+@pytest.mark.parametrize("h,w", [(1, 1), (16, 16), (17, 33), (237, 355), (301, 77)])
+def test_vp8_decoder_equals_libwebp_on_libwebp_encodings(L, h, w):
+    from PIL import Image
+    for kind in ("photo", "flat", "noise"):
+        img = synth(h, w, 3, seed=h * 7 + w, kind=kind)
+        for q, m in ((0, 0), (20, 2), (50, 4), (75, 6), (90, 4), (100, 3)):
+            b = io.BytesIO(); Image.fromarray(img).save(b, "WEBP", quality=q, method=m)
+            data = b.getvalue()
+            assert np.array_equal(L.webp_decode(data), _pil_rgb(data)), (kind, q, m)
+
+
+def test_vp8_decoder_refuses_what_it_does_not_decode(L):
+    from PIL import Image
+    img = synth(20, 30, 4, seed=1)
+    b = io.BytesIO(); Image.fromarray(img).save(b, "WEBP", lossless=True)
+    with pytest.raises(L.B200Error) as e:
+        L.webp_decode(b.getvalue())
+    assert e.value.code == 3
+    b = io.BytesIO(); Image.fromarray(img).save(b, "WEBP", quality=80)      # lossy with an alpha plane (VP8X + ALPH)
+    with pytest.raises(L.B200Error) as e:
+        L.webp_decode(b.getvalue())
+    assert e.value.code == 3 and "alpha" in str(e.value)
+    ok = io.BytesIO(); Image.fromarray(img[:, :, :3]).save(ok, "WEBP", quality=80)
+    data = ok.getvalue()
+    for cut in (len(data) // 2, 40, 25):
+        try:
+            L.webp_decode(data[:cut])                   # truncated token partitions decode as zeros (libwebp would report an error)
+        except L.B200Error as e2:
+            assert e2.code == 4
+    with pytest.raises(L.B200Error) as e:
+        L.webp_decode(b"RIFF\x10\x00\x00\x00WEBPVP8 \x04\x00\x00\x00abcd")
+    assert e.value.code == 4
