@@ -33,7 +33,89 @@ __device__ __forceinline__ void five_filters(const uint8_t *__restrict__ row, co
     v[0] = (uint8_t)cur; v[1] = (uint8_t)(cur - a); v[2] = (uint8_t)(cur - b); v[3] = (uint8_t)(cur - ((a + b) >> 1)); v[4] = (uint8_t)(cur - paeth_pred(a, b, c));
 }
 
-__global__ void __launch_bounds__(256) k_png_filter(const uint8_t *__restrict__ raw, uint8_t *__restrict__ filt, int h, int rb, int bpp, int strategy, const uint32_t *__restrict__ tlog)
+// One CTA per row.  The row and the row above are staged in shared memory with 16-byte loads (the five candidate filters read
+// four neighbours per byte: from global memory that was four scattered byte loads per byte and kept the kernel at 1 % of the HBM
+// roofline); scoring and the final write then work out of shared memory.
+__device__ __forceinline__ void five_filters_sm(const uint8_t *__restrict__ row, const uint8_t *__restrict__ up, int x, int bpp, uint8_t v[5])
+{   // row / up point at byte 0 of the staged rows, which are preceded by 16 zero bytes (so x - bpp may run off the left edge)
+    const int cur = row[x], a = row[x - bpp], b = up[x], c = up[x - bpp];
+    v[0] = (uint8_t)cur; v[1] = (uint8_t)(cur - a); v[2] = (uint8_t)(cur - b); v[3] = (uint8_t)(cur - ((a + b) >> 1)); v[4] = (uint8_t)(cur - paeth_pred(a, b, c));
+}
+__global__ void __launch_bounds__(256) k_png_filter(const uint8_t *__restrict__ raw, uint8_t *__restrict__ filt, int h, int rb, int bpp, int strategy, const uint32_t *__restrict__ tlog,
+                                                    int row_pitch)
+{
+    extern __shared__ __align__(16) uint32_t sm_all[];
+    __shared__ unsigned long long score[5];
+    __shared__ int chosen;
+    uint8_t *srow = reinterpret_cast<uint8_t *>(sm_all) + 16, *sup = srow + row_pitch;       // 16 zero bytes in front of each staged row
+    uint32_t *sm = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(sm_all) + 2 * row_pitch);
+    const int y = blockIdx.x;
+    const uint8_t *grow = raw + (size_t)y * rb, *gup = y ? grow - rb : nullptr;
+    // stage with aligned 32-bit loads (rows start at arbitrary byte offsets: align the global side down, drop the bytes outside)
+    for (int i = threadIdx.x; i < 4; i += blockDim.x) { reinterpret_cast<uint32_t *>(srow - 16)[i] = 0; reinterpret_cast<uint32_t *>(sup - 16)[i] = 0; }
+    {
+        const int lead = (int)((uintptr_t)grow & 3), nwords = (lead + rb + 3) / 4;
+        const uint32_t *gw = reinterpret_cast<const uint32_t *>(grow - lead);
+        for (int j = threadIdx.x; j < nwords; j += blockDim.x) {
+            const uint32_t w = gw[j];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const int idx = 4 * j + k - lead; if (idx >= 0 && idx < rb) srow[idx] = (uint8_t)(w >> (8 * k)); }
+        }
+        if (gup) {
+            const int lead2 = (int)((uintptr_t)gup & 3), nw2 = (lead2 + rb + 3) / 4;
+            const uint32_t *gw2 = reinterpret_cast<const uint32_t *>(gup - lead2);
+            for (int j = threadIdx.x; j < nw2; j += blockDim.x) {
+                const uint32_t w = gw2[j];
+#pragma unroll
+                for (int k = 0; k < 4; k++) { const int idx = 4 * j + k - lead2; if (idx >= 0 && idx < rb) sup[idx] = (uint8_t)(w >> (8 * k)); }
+            }
+        } else for (int i = threadIdx.x; i < rb; i += blockDim.x) sup[i] = 0;
+    }
+    __syncthreads();
+    uint8_t *out = filt + (size_t)y * (rb + 1);
+    int f = strategy;
+    if (strategy >= 5) {
+        if (threadIdx.x < 5) score[threadIdx.x] = 0;
+        const int words = strategy == PNGF_MINSUM ? 0 : (strategy == PNGF_BIGRAMS ? 5 * 2048 : (strategy == PNGF_BIGENT ? 5 * 4096 : 5 * 256));
+        for (int i = threadIdx.x; i < words; i += blockDim.x) sm[i] = 0;
+        __syncthreads();
+        if (strategy == PNGF_MINSUM) {
+            unsigned long long s5[5] = {0, 0, 0, 0, 0};
+            for (int x = threadIdx.x; x < rb; x += blockDim.x) { uint8_t v[5]; five_filters_sm(srow, sup, x, bpp, v); for (int k = 0; k < 5; k++) s5[k] += (unsigned)abs((int)(int8_t)v[k]); }
+            for (int k = 0; k < 5; k++) atomicAdd(&score[k], s5[k]);
+        } else if (strategy == PNGF_ENTROPY || strategy == PNGF_BRUTE) {
+            for (int x = threadIdx.x; x < rb; x += blockDim.x) { uint8_t v[5]; five_filters_sm(srow, sup, x, bpp, v); for (int k = 0; k < 5; k++) atomicAdd(&sm[k * 256 + v[k]], 1u); }
+            __syncthreads();
+            for (int i = threadIdx.x; i < 5 * 256; i += blockDim.x) if (sm[i]) atomicAdd(&score[i >> 8], (unsigned long long)tlog[sm[i]]);
+        } else {
+            for (int x = threadIdx.x; x + 1 < rb; x += blockDim.x) {
+                uint8_t v[5], w[5]; five_filters_sm(srow, sup, x, bpp, v); five_filters_sm(srow, sup, x + 1, bpp, w);
+                for (int k = 0; k < 5; k++) {
+                    const unsigned bg = ((unsigned)v[k] << 8) | w[k];
+                    if (strategy == PNGF_BIGRAMS) atomicOr(&sm[k * 2048 + (bg >> 5)], 1u << (bg & 31));
+                    else atomicAdd(&sm[k * 4096 + (((bg * 2654435761u) >> 20) & 4095u)], 1u);
+                }
+            }
+            __syncthreads();
+            if (strategy == PNGF_BIGRAMS) { for (int i = threadIdx.x; i < 5 * 2048; i += blockDim.x) if (sm[i]) atomicAdd(&score[i >> 11], (unsigned long long)__popc(sm[i])); }
+            else for (int i = threadIdx.x; i < 5 * 4096; i += blockDim.x) if (sm[i]) atomicAdd(&score[i >> 12], (unsigned long long)tlog[min(sm[i], (uint32_t)rb)]);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const bool want_max = strategy == PNGF_ENTROPY || strategy == PNGF_BRUTE || strategy == PNGF_BIGENT;   // sum c*log2(c): larger = lower entropy
+            int best = 0;
+            for (int k = 1; k < 5; k++) if (want_max ? score[k] > score[best] : score[k] < score[best]) best = k;
+            chosen = best;
+        }
+        __syncthreads();
+        f = chosen;
+    }
+    if (threadIdx.x == 0) out[0] = (uint8_t)f;
+    for (int x = threadIdx.x; x < rb; x += blockDim.x) { uint8_t v[5]; five_filters_sm(srow, sup, x, bpp, v); out[1 + x] = v[f]; }
+}
+
+// the same from global memory, for rows too long to stage (more than ~58 KB)
+__global__ void __launch_bounds__(256) k_png_filter_wide(const uint8_t *__restrict__ raw, uint8_t *__restrict__ filt, int h, int rb, int bpp, int strategy, const uint32_t *__restrict__ tlog)
 {
     extern __shared__ uint32_t sm[];
     __shared__ unsigned long long score[5];
@@ -104,21 +186,52 @@ __device__ __forceinline__ int match_len(const uint8_t *__restrict__ s, size_t i
     return l;
 }
 
-__global__ void k_png_match(const uint8_t *__restrict__ s, uint32_t *__restrict__ best, size_t n, int bpp, int stride, int chunk)
+// One thread per position, 256 positions per CTA.  Everything a CTA compares lies in three short windows of the stream -- the
+// positions themselves (+ the 24 bytes before them: distances up to three pixels), the same stretch one row up (+- one pixel) and
+// two rows up -- which are staged in shared memory once; the candidate loops then never leave it (from global memory the kernel ran
+// at 3 % of the HBM roofline on L1 / L2 latency).
+constexpr int MATCH_T = 256, MATCH_W = 552;
+__device__ __forceinline__ int match_len_sm(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, int maxlen)
+{   // a = bytes at the position, b = bytes at position - distance (both in shared memory)
+    int l = 0;
+    while (l + 4 <= maxlen) {
+        const uint32_t x = load32u(a + l) ^ load32u(b + l);
+        if (x) return l + ((__ffs((int)x) - 1) >> 3);
+        l += 4;
+    }
+    while (l < maxlen && a[l] == b[l]) l++;
+    return l;
+}
+__global__ void __launch_bounds__(MATCH_T) k_png_match(const uint8_t *__restrict__ s, uint32_t *__restrict__ best, size_t n, int bpp, int stride, int chunk)
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ __align__(16) uint8_t w0[MATCH_W], w1[MATCH_W], w2[MATCH_W];
+    const long long i0 = (long long)blockIdx.x * MATCH_T;
+    const long long b0 = i0 - 24, b1 = i0 - stride - 8, b2 = i0 - 2ll * stride;
+    for (int k = threadIdx.x; k < MATCH_W; k += MATCH_T) {
+        const long long p0 = b0 + k, p1 = b1 + k, p2 = b2 + k;
+        w0[k] = (p0 >= 0 && p0 < (long long)n) ? s[p0] : (uint8_t)0;
+        w1[k] = (p1 >= 0 && p1 < (long long)n) ? s[p1] : (uint8_t)0;
+        w2[k] = (p2 >= 0 && p2 < (long long)n) ? s[p2] : (uint8_t)0;
+    }
+    __syncthreads();
+    const size_t i = (size_t)i0 + threadIdx.x;
     if (i >= n) return;
     const size_t chunk_end = (i / chunk + 1) * (size_t)chunk;
     const int maxlen = (int)min((size_t)258, min(n, chunk_end) - i);
     int bl = 0, bd = 0;
     if (maxlen >= 3) {
+        const uint8_t *cur = w0 + 24 + threadIdx.x;
         const int cand[10] = {bpp, 1, 2 * bpp, stride, stride - bpp, stride + bpp, 3 * bpp, 2, 3, 2 * stride};
 #pragma unroll
         for (int c = 0; c < 10; c++) {
             const int d = cand[c];
             if (d < 1 || d > 32768 || (size_t)d > i) continue;
-            if (bl > 0 && s[i + bl] != s[i + bl - d]) continue;      // cannot beat the current best
-            const int l = match_len(s, i, d, maxlen);
+            // which window holds position i - d: the near one (d <= 24), the row above (c = 3, 4, 5) or two rows up (c = 9)
+            const uint8_t *src = (c >= 3 && c <= 5) ? w1 + ((long long)i - d - b1) : c == 9 ? w2 + ((long long)i - d - b2) : cur - d;
+            if ((c >= 3 && c <= 5 && (stride - d > 8 || d - stride > 8)) || (c != 9 && !(c >= 3 && c <= 5) && d > 24)) src = nullptr;   // (cannot happen: bpp <= 8)
+            if (!src) continue;
+            if (bl > 0 && cur[bl] != src[bl]) continue;               // cannot beat the current best
+            const int l = match_len_sm(cur, src, maxlen);
             if (l > bl) { bl = l; bd = d; }                           // earlier candidate wins ties
             if (bl == maxlen) break;
         }
@@ -439,9 +552,17 @@ static inline unsigned cdivu(size_t a, size_t b) { return (unsigned)((a + b - 1)
 
 int launch_png_filter(const uint8_t *d_raw, uint8_t *d_filt, int h, int rb, int bpp, int strategy, const uint32_t *d_tlog, void *stream)
 {
-    size_t smem = strategy == PNGF_BIGRAMS ? 5 * 2048 * 4 : (strategy == PNGF_BIGENT ? 5 * 4096 * 4 : (strategy >= 5 && strategy != PNGF_MINSUM ? 5 * 256 * 4 : 0));
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_png_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 4096 * 4);   // per device, cheap
-    k_png_filter<<<h, 256, smem, (cudaStream_t)stream>>>(d_raw, d_filt, h, rb, bpp, strategy, d_tlog);
+    const size_t hist = strategy == PNGF_BIGRAMS ? 5 * 2048 * 4 : (strategy == PNGF_BIGENT ? 5 * 4096 * 4 : (strategy >= 5 && strategy != PNGF_MINSUM ? 5 * 256 * 4 : 0));
+    const int row_pitch = ((rb + 16 + 15) / 16) * 16;                       // 16 zero bytes + the row, 16-byte multiple
+    const size_t smem = (size_t)2 * row_pitch + hist + 16;
+    if (smem > 200 * 1024) {                                               // very long rows: the unstaged kernel
+        if (hist > 48 * 1024) cudaFuncSetAttribute(k_png_filter_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 4096 * 4);
+        k_png_filter_wide<<<h, 256, hist, (cudaStream_t)stream>>>(d_raw, d_filt, h, rb, bpp, strategy, d_tlog);
+        LT_MARK("k_png_filter");
+        return (int)cudaGetLastError();
+    }
+    cudaFuncSetAttribute(k_png_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   // per device, cheap
+    k_png_filter<<<h, 256, smem, (cudaStream_t)stream>>>(d_raw, d_filt, h, rb, bpp, strategy, d_tlog, row_pitch);
     LT_MARK("k_png_filter");
     return (int)cudaGetLastError();
 }
