@@ -163,6 +163,7 @@ int runtime_init(int n_gpus, int only_device, std::string &err)
 }
 
 static void print_group_trace();
+static void drop_graphs(Slot *s);
 void runtime_shutdown()
 {
     print_group_trace();
@@ -171,6 +172,7 @@ void runtime_shutdown()
         cudaSetDevice(d->ordinal);
         for (Slot *s : d->free_slots) {
             if (s->stream) cudaStreamDestroy((cudaStream_t)s->stream);
+            drop_graphs(s);
             cudaFreeHost(s->h_in); cudaFreeHost(s->h_out); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_scratch); cudaFreeHost(s->h_par); cudaFree(s->d_par); delete s->enc; delete s->dec; delete s->png; delete s->webp;
             delete s;
         }
@@ -298,14 +300,14 @@ bool slot_group_layout(Slot *s, const JpegGeom &gin, const JpegGeom &gout, int K
     return s->ensure_device(L.in_stride * K, L.out_stride * K, L.scratch_stride * K, par, err);
 }
 
-bool slot_transform_group(Slot *s, const JpegGeom *const *gins, const JpegGeom &gout, const GroupLayout &L, std::string &err)
+// host half: quantiser constants, per-image dequantisation tables and the work descriptors into the slot's pinned parameter block
+bool slot_transform_group_prepare(Slot *s, const JpegGeom *const *gins, const JpegGeom &gout, const GroupLayout &L, std::string &err)
 {
-    cudaStream_t st = (cudaStream_t)s->stream;
     const int K = L.K;
     const size_t o_q = 0, o_dq = align_up(sizeof(QuantDev) * 4, 256), o_work = o_dq + align_up(sizeof(uint16_t) * 256 * K, 256);
     QuantDev *q = reinterpret_cast<QuantDev *>(s->h_par + o_q);
     for (int t = 0; t < 4; t++) if (gout.qt_present[t]) make_quant_dev(gout.qt[t], &q[t]);
-    WorkLists wl;
+    WorkLists &wl = s->group_wl; wl.clear();
     for (int k = 0; k < K; k++) {
         const JpegGeom &gin = *gins[k];
         ImagePlan plan;
@@ -317,10 +319,21 @@ bool slot_transform_group(Slot *s, const JpegGeom *const *gins, const JpegGeom &
                           reinterpret_cast<const uint16_t *>(s->d_par + o_dq) + 256 * k, reinterpret_cast<const QuantDev *>(s->d_par + o_q), wl);
     }
     const size_t nw = flatten_work(wl, reinterpret_cast<CompWork *>(s->h_par + o_work));
-    CU(cudaMemcpyAsync(s->d_par, s->h_par, o_work + nw * sizeof(CompWork), cudaMemcpyHostToDevice, st));
-    int rc = launch_work(wl, reinterpret_cast<const CompWork *>(s->d_par + o_work), st, 0, nullptr);
+    s->group_par_bytes = o_work + nw * sizeof(CompWork); s->group_work_off = o_work;
+    return true;
+}
+// stream half: parameter block up, the transform kernels
+bool slot_transform_group_enqueue(Slot *s, std::string &err)
+{
+    cudaStream_t st = (cudaStream_t)s->stream;
+    CU(cudaMemcpyAsync(s->d_par, s->h_par, s->group_par_bytes, cudaMemcpyHostToDevice, st));
+    int rc = launch_work(s->group_wl, reinterpret_cast<const CompWork *>(s->d_par + s->group_work_off), st, 0, nullptr);
     if (rc) { err = std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)rc); return false; }
     return true;
+}
+bool slot_transform_group(Slot *s, const JpegGeom *const *gins, const JpegGeom &gout, const GroupLayout &L, std::string &err)
+{
+    return slot_transform_group_prepare(s, gins, gout, L, err) && slot_transform_group_enqueue(s, err);
 }
 
 // (Measured and dropped: issuing the decode passes on a highest-priority stream so that their small latency-bound grids cut in
@@ -343,23 +356,73 @@ static void print_group_trace()
     for (int i = 0; i < 5; i++) fprintf(stderr, "[b200 trace]   %-58s %8.3f\n", names[i], g_grp_ns[i].load() / 1e6 / (double)n);
 }
 
+// The launch sequence of a megabatch is ~70 driver calls (kernels, CUB scans, memsets, small copies).  Sixteen worker threads
+// issuing them concurrently spend more time in the driver's process-wide lock than the kernels take to run (B200_TRACE showed
+// 1.8 ms of pure enqueue time per megabatch, 24 us per call), and that -- not the GPU -- capped the C-ABI rate at 85 % of the
+// device-resident rate.  The sequence is the same from megabatch to megabatch (sizes are high-water marks, buffers are reused), so
+// it is captured once per slot as two CUDA graphs -- everything up to the scan sizes, and the bit-packing / stuffing half -- and
+// replayed: three driver calls per megabatch.  A changed signature (other geometry, a grown buffer, a new high-water mark)
+// re-captures.  B200_GRAPHS=0 issues the calls directly.
+static bool graphs_enabled() { static const bool on = [] { const char *e = getenv("B200_GRAPHS"); return !(e && !strcmp(e, "0")); }(); return on; }
+static void drop_graphs(Slot *s)
+{
+    if (s->graph_front) { cudaGraphExecDestroy((cudaGraphExec_t)s->graph_front); s->graph_front = nullptr; }
+    if (s->graph_back) { cudaGraphExecDestroy((cudaGraphExec_t)s->graph_back); s->graph_back = nullptr; }
+    s->graph_sig = 0;
+}
+template <class Fn> static bool capture_graph(cudaStream_t st, void *&exec_out, Fn fn, std::string &err)
+{
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
+    const bool ok = fn();
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (!ok || e != cudaSuccess || !g) { if (g) cudaGraphDestroy(g); cudaGetLastError(); if (err.empty()) err = "graph capture failed"; return false; }
+    cudaGraphExec_t ex = nullptr;
+    const cudaError_t ei = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    if (ei != cudaSuccess) { cudaGetLastError(); err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ei); return false; }
+    exec_out = ex;
+    return true;
+}
+
 bool slot_run_group(Slot *s, std::vector<GpuDecoder::Item> &items, const JpegGeom *const *gins, const JpegGeom &gout, const GroupLayout &L, bool progressive,
                     bool lossless, std::string &err)
 {
     if (!s->dec) s->dec = new GpuDecoder();
     if (!s->enc) s->enc = new GpuEncoder();
+    cudaStream_t st = (cudaStream_t)s->stream;
     const auto t0 = std::chrono::steady_clock::now();
-    if (!s->dec->prepare(items, s->stream, err)) return false;
-    const auto t1 = std::chrono::steady_clock::now();
-    if (!s->dec->enqueue(s->stream, err)) return false;
-    if (!lossless && !slot_transform_group(s, gins, gout, L, err)) return false;
+    // ---- host half of all three stages (pinned staging, descriptors, plans); nothing touches the stream yet
+    if (!s->dec->prepare(items, st, err)) return false;
+    if (!lossless && !slot_transform_group_prepare(s, gins, gout, L, err)) return false;
     std::vector<int16_t *> bases((size_t)L.K);
     for (int k = 0; k < L.K; k++) bases[k] = lossless ? reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(s->d_in) + L.in_stride * k)
                                                       : reinterpret_cast<int16_t *>(reinterpret_cast<uint8_t *>(s->d_out) + L.out_stride * k);
     // a re-encode at lower quality (or a transcode with optimal tables) does not grow: the inputs' entropy-coded size sizes the output buffers
-    if (!s->enc->prepare(gout, progressive, bases.data(), L.K, s->stream, s->dec->raw_bytes(), err) || !s->enc->enqueue(s->stream, true, err)) return false;
+    if (!s->enc->prepare(gout, progressive, bases.data(), L.K, st, s->dec->raw_bytes(), err)) return false;
+    const auto t1 = std::chrono::steady_clock::now();
+    auto front = [&]() { return s->dec->upload(st, err) && s->dec->enqueue(st, err) && (lossless || slot_transform_group_enqueue(s, err)) &&
+                                s->enc->upload(st, err) && s->enc->enqueue_front(st, true, err) && s->enc->enqueue_sizes(st, err); };
+    auto back = [&]() { return s->enc->enqueue_back(st, err); };
+    bool launched = false;
+    if (graphs_enabled() && !s->graphs_broken) {
+        unsigned long long sig = s->dec->signature() * 1099511628211ull ^ s->enc->signature();
+        sig = (sig ^ (unsigned long long)(uintptr_t)s->d_par ^ ((unsigned long long)s->group_par_bytes << 20) ^ (lossless ? 0x9e3779b97f4a7c15ull : 0)) * 1099511628211ull + (unsigned long long)L.K;
+        if (!s->graph_front || s->graph_sig != sig) {
+            drop_graphs(s);
+            std::string gerr;
+            if (capture_graph(st, s->graph_front, front, gerr) && capture_graph(st, s->graph_back, back, gerr)) s->graph_sig = sig;
+            else { drop_graphs(s); s->graphs_broken = true; }      // capture not possible here: issue the calls directly from now on
+        }
+        if (s->graph_front && s->graph_back) {
+            if (cudaGraphLaunch((cudaGraphExec_t)s->graph_front, st) != cudaSuccess || !s->enc->mark_sizes(st, err) ||
+                cudaGraphLaunch((cudaGraphExec_t)s->graph_back, st) != cudaSuccess) { err = std::string("cudaGraphLaunch: ") + cudaGetErrorString(cudaGetLastError()); return false; }
+            launched = true;
+        }
+    }
+    if (!launched && !(front() && s->enc->mark_sizes(st, err) && back())) return false;
     const auto t2 = std::chrono::steady_clock::now();
-    if (!s->enc->finish(s->stream, true, err)) return false;
+    if (!s->enc->finish(st, true, err)) return false;
     s->dec->finish(items);
     if (g_grp_trace) {
         const auto t3 = std::chrono::steady_clock::now();
@@ -420,7 +483,7 @@ bool slot_gpu_encode_sizes(Slot *s, const JpegGeom &gout, bool progressive, std:
 {
     if (!s->enc) s->enc = new GpuEncoder();
     int16_t *base = s->d_out;
-    return s->enc->prepare(gout, progressive, &base, 1, s->stream, 0, err) && s->enc->enqueue(s->stream, true, err) && s->enc->finish(s->stream, false, err);
+    return s->enc->prepare(gout, progressive, &base, 1, s->stream, 0, err) && s->enc->upload(s->stream, err) && s->enc->enqueue(s->stream, true, err) && s->enc->finish(s->stream, false, err);
 }
 bool slot_gpu_fetch(Slot *s, std::string &err) { return s->enc && s->enc->finish(s->stream, true, err); }
 

@@ -52,6 +52,10 @@ struct Slot {
     class GpuDecoder *dec = nullptr;                                                     // device entropy decoder (lazy)
     struct PngDevice *png = nullptr;                                                     // lossless PNG state (lazy, png_device.cu)
     struct WebpDevice *webp = nullptr;                                                   // WebP / VP8 state (lazy, webp_device.cu)
+    // megabatch path: transform work lists of the current megabatch, and the captured launch sequence (two CUDA graphs, see
+    // slot_run_group) with the signature it was captured for
+    WorkLists group_wl; size_t group_par_bytes = 0, group_work_off = 0;
+    void *graph_front = nullptr, *graph_back = nullptr; unsigned long long graph_sig = 0; bool graphs_broken = false;
     bool ensure(size_t in_bytes, size_t out_bytes, size_t scratch_bytes, size_t par_bytes, std::string &err);
     bool ensure_device(size_t in_bytes, size_t out_bytes, size_t scratch_bytes, size_t par_bytes, std::string &err);
 };

@@ -199,9 +199,11 @@ __global__ void k_gd_dc_scatter(const DecImage *__restrict__ imgs, const int32_t
 // ---- host ---------------------------------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static thread_local unsigned long long *tl_generation = nullptr;       // bumped on every reallocation (captured graphs hold the old pointers)
 template <typename T> static bool growd(T *&p, size_t &cap, size_t need, bool host, std::string &err)
 {
     if (need <= cap) return true;
+    if (tl_generation) ++*tl_generation;
     if (p) { if (host) cudaFreeHost(p); else cudaFree(p); }
     p = nullptr; cap = 0;
     // sizes here depend on image CONTENT (bytes of entropy-coded data); round up to a power of two with headroom so a
@@ -229,6 +231,7 @@ bool GpuDecoder::prepare(std::vector<Item> &items, void *stream_, std::string &e
     const int N = (int)items.size();
     nitems = N;
     if (N == 0) return true;
+    tl_generation = &generation;
     // ---- per-image descriptors
     imgs.assign((size_t)N, DecImage());
     coef_ptrs.resize((size_t)N); coef_bytes.resize((size_t)N);
@@ -262,21 +265,28 @@ bool GpuDecoder::prepare(std::vector<Item> &items, void *stream_, std::string &e
         coef_ptrs[n] = items[n].d_coefs; coef_bytes[n] = (size_t)g.total_coefs * 2;
     }
     if (raw_total >= (1ull << 31) || stream_total >= (1ull << 31)) { err = "decode batch too large"; return false; }
+    // ---- launch-side sizes are HIGH-WATER marks, not this batch's exact sizes: grids, scan lengths and the H2D size of the pass
+    //      sequence then stay the same from batch to batch (kernels test against the per-image sizes in the descriptors), which is
+    //      what lets the caller replay the sequence as a CUDA graph instead of ~70 driver calls per megabatch
+    auto hw = [](size_t &mark, size_t need) { if (need > mark) mark = need + need / 8 + 64; };
+    if (N != hw_n) { hw_n = N; hw_raw = hw_stream = hw_grp = hw_sub = hw_blk = hw_mgrp = hw_msub = hw_mblk = 0; }
+    hw(hw_raw, raw_total); hw(hw_stream, stream_total); hw(hw_grp, grp_total); hw(hw_sub, sub_total); hw(hw_blk, blk_total);
+    hw(hw_mgrp, max_grp); hw(hw_msub, max_sub); hw(hw_mblk, max_blk);
     // ---- buffers
     o_img = 0; o_tab = align_up(sizeof(DecImage) * N, 256); o_flag = o_tab + align_up(sizeof(DecTables) * N, 256);
     o_mark = o_flag + align_up((size_t)4 * N * (MAX_ROUNDS + 2), 256);
     par_bytes = o_mark + align_up((size_t)4 * N, 256);
-    if (!growd(h_raw, cap_hraw, raw_total + 64, true, err) || !growd(d_raw, cap_raw, raw_total + 64, false, err) || !growd(d_stream, cap_stream, stream_total + 64, false, err) ||
-        !growd(d_cnt, cap_cnt, (size_t)grp_total * 4 + 4, false, err) || !growd(d_off, cap_off, (size_t)grp_total * 4 + 4, false, err) ||
-        !growd(d_A, cap_A, (size_t)sub_total * sizeof(DecState), false, err) ||
-        !growd(d_chgA, cap_chgA, sub_total, false, err) || !growd(d_chgB, cap_chgB, (size_t)2 * N * cdiv(max_sub, 64) + 64, false, err) ||
-        !growd(d_nblk, cap_nblk, (size_t)sub_total * 4, false, err) || !growd(d_first, cap_first, (size_t)sub_total * 4, false, err) ||
-        !growd(d_dc, cap_dc, (size_t)blk_total * 4, false, err) || !growd(d_dcs, cap_dcs, (size_t)blk_total * 4, false, err) ||
+    if (!growd(h_raw, cap_hraw, hw_raw + 64, true, err) || !growd(d_raw, cap_raw, hw_raw + 64, false, err) || !growd(d_stream, cap_stream, hw_stream + 64, false, err) ||
+        !growd(d_cnt, cap_cnt, hw_grp * 4 + 4, false, err) || !growd(d_off, cap_off, hw_grp * 4 + 4, false, err) ||
+        !growd(d_A, cap_A, hw_sub * sizeof(DecState), false, err) ||
+        !growd(d_chgA, cap_chgA, hw_sub, false, err) || !growd(d_chgB, cap_chgB, (size_t)2 * N * cdiv((long long)hw_msub, 64) + 64, false, err) ||
+        !growd(d_nblk, cap_nblk, hw_sub * 4, false, err) || !growd(d_first, cap_first, hw_sub * 4, false, err) ||
+        !growd(d_dc, cap_dc, hw_blk * 4, false, err) || !growd(d_dcs, cap_dcs, hw_blk * 4, false, err) ||
         !growd(d_par, cap_par, par_bytes, false, err) || !growd(h_par, cap_hpar, par_bytes, true, err)) return false;
     size_t t1 = 0, t2 = 0, t3 = 0;
-    cub::DeviceScan::ExclusiveSum((void *)nullptr, t1, d_cnt, d_off, (int)grp_total, st);
-    cub::DeviceScan::ExclusiveSum((void *)nullptr, t2, d_nblk, d_first, (int)sub_total, st);
-    cub::DeviceScan::InclusiveSum((void *)nullptr, t3, d_dc, d_dcs, (int)blk_total, st);
+    cub::DeviceScan::ExclusiveSum((void *)nullptr, t1, d_cnt, d_off, (int)hw_grp, st);
+    cub::DeviceScan::ExclusiveSum((void *)nullptr, t2, d_nblk, d_first, (int)hw_sub, st);
+    cub::DeviceScan::InclusiveSum((void *)nullptr, t3, d_dc, d_dcs, (int)hw_blk, st);
     if (!growd(d_temp, cap_temp, std::max(t1, std::max(t2, t3)) + 256, false, err)) return false;
     // ---- parameters + raw bytes
     DecTables *ht = reinterpret_cast<DecTables *>(h_par + o_tab);
@@ -292,9 +302,29 @@ bool GpuDecoder::prepare(std::vector<Item> &items, void *stream_, std::string &e
     }
     memcpy(h_par + o_img, imgs.data(), sizeof(DecImage) * N);
     memset(h_par + o_flag, 0, (size_t)4 * N * (MAX_ROUNDS + 2));
-    CUD(cudaMemcpyAsync(d_par, h_par, o_flag, cudaMemcpyHostToDevice, st));
-    CUD(cudaMemcpyAsync(d_raw, h_raw, raw_total, cudaMemcpyHostToDevice, st));
+    tl_generation = nullptr;
     return true;
+}
+
+// H2D of what prepare() staged: descriptors + tables, and the entropy-coded bytes (high-water size: the tail past this batch's
+// bytes is stale and unused)
+bool GpuDecoder::upload(void *stream_, std::string &err)
+{
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (nitems == 0) return true;
+    CUD(cudaMemcpyAsync(d_par, h_par, o_flag, cudaMemcpyHostToDevice, st));
+    CUD(cudaMemcpyAsync(d_raw, h_raw, hw_raw, cudaMemcpyHostToDevice, st));
+    return true;
+}
+
+unsigned long long GpuDecoder::signature() const
+{   // everything a captured launch sequence bakes in: counts, high-water sizes, buffer identities
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { h = (h ^ v) * 1099511628211ull; };
+    mix((unsigned long long)nitems); mix(hw_raw); mix(hw_grp); mix(hw_sub); mix(hw_blk); mix(hw_mgrp); mix(hw_msub); mix(hw_mblk); mix(generation);
+    mix(o_flag); mix(o_mark);
+    for (size_t n = 0; n < coef_ptrs.size(); n++) { mix((unsigned long long)(uintptr_t)coef_ptrs[n]); mix(coef_bytes[n]); }
+    return h;
 }
 
 bool GpuDecoder::enqueue(void *stream_, std::string &err)
@@ -311,17 +341,17 @@ bool GpuDecoder::enqueue(void *stream_, std::string &err)
     CUD(cudaMemsetAsync(dF, 0, (o_mark - o_flag) + (size_t)4 * N, st));                 // round flags + marker flags
     LT_MARK("memset");
     // ---- unstuff
-    const dim3 gg(cdiv(max_grp, 128), N);
+    const dim3 gg(cdiv((long long)hw_mgrp, 128), N);
     k_gd_unstuff_count<<<gg, 128, 0, st>>>(dI, d_raw, d_cnt, dM);
     LT_MARK("k_gd_unstuff_count");
     size_t tb = cap_temp;
-    cub::DeviceScan::ExclusiveSum(d_temp, tb, d_cnt, d_off, (int)grp_total, st);
+    cub::DeviceScan::ExclusiveSum(d_temp, tb, d_cnt, d_off, (int)hw_grp, st);
     LT_MARK("cub_scan");
     k_gd_unstuff_scatter<<<gg, 128, 0, st>>>(dIw, d_raw, d_off, d_cnt, d_stream);
     LT_MARK("k_gd_unstuff_scatter");
     for (int n = 0; n < N; n++) CUD(cudaMemsetAsync(coef_ptrs[n], 0, coef_bytes[n], st));
     // ---- rounds
-    const dim3 gs(cdiv(max_sub, 64), N);
+    const dim3 gs(cdiv((long long)hw_msub, 64), N);
     const size_t ncta = (size_t)N * gs.x;                    // dirty flags: two buffers of one byte per CTA, by round parity
     CUD(cudaMemsetAsync(d_chgB, 0, 2 * ncta, st));
     LT_MARK("memset");
@@ -339,15 +369,15 @@ bool GpuDecoder::enqueue(void *stream_, std::string &err)
     // ---- block counts -> first block of each subsequence -> write -> DC (images that did not converge produce garbage
     //      that their caller discards)
     tb = cap_temp;
-    cub::DeviceScan::ExclusiveSum(d_temp, tb, d_nblk, d_first, (int)sub_total, st);
+    cub::DeviceScan::ExclusiveSum(d_temp, tb, d_nblk, d_first, (int)hw_sub, st);
     LT_MARK("cub_scan");
     k_gd_write<<<gs, 64, 0, st>>>(dI, d_stream, dT, d_A, d_first);
     LT_MARK("k_gd_write");
-    const dim3 gb(cdiv(max_blk, 128), N);
+    const dim3 gb(cdiv((long long)hw_mblk, 128), N);
     k_gd_dc_gather<<<gb, 128, 0, st>>>(dI, d_dc, d_A, d_first, d_nblk);
     LT_MARK("k_gd_dc_gather");
     tb = cap_temp;
-    cub::DeviceScan::InclusiveSum(d_temp, tb, d_dc, d_dcs, (int)blk_total, st);
+    cub::DeviceScan::InclusiveSum(d_temp, tb, d_dc, d_dcs, (int)hw_blk, st);
     LT_MARK("cub_scan");
     k_gd_dc_scatter<<<gb, 128, 0, st>>>(dI, d_dcs);
     LT_MARK("k_gd_dc_scatter");
@@ -370,7 +400,7 @@ void GpuDecoder::finish(std::vector<Item> &items)
 bool GpuDecoder::decode(std::vector<Item> &items, void *stream_, std::string &err)
 {
     if (items.empty()) return true;
-    if (!prepare(items, stream_, err) || !enqueue(stream_, err)) return false;
+    if (!prepare(items, stream_, err) || !upload(stream_, err) || !enqueue(stream_, err)) return false;
     CUD(stream_wait((cudaStream_t)stream_));
     finish(items);
     return true;

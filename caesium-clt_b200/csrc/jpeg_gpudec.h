@@ -38,8 +38,12 @@ public:
     bool decode(std::vector<Item> &items, void *stream, std::string &err);
     // the same in steps: prepare() stages inputs and descriptors (H2D enqueued), enqueue() launches every pass without a host
     // wait (repeatable on unchanged inputs), finish() -- after the caller has waited for the stream -- fills items[].result
-    bool prepare(std::vector<Item> &items, void *stream, std::string &err);
+    bool prepare(std::vector<Item> &items, void *stream, std::string &err);       // host work only: nothing is put on the stream
+    bool upload(void *stream, std::string &err);                                  // H2D of the staged inputs
     bool enqueue(void *stream, std::string &err);
+    // identity of the launch sequence upload() + enqueue() would issue: equal signatures = the same driver calls with the same
+    // arguments (sizes are high-water marks), i.e. a captured CUDA graph of them can be replayed
+    unsigned long long signature() const;
     void finish(std::vector<Item> &items);
     size_t raw_bytes() const { return raw_total; }          // entropy-coded bytes staged by the last prepare()
     int rounds_used = 0, launches = 0;
@@ -52,6 +56,8 @@ private:
     int nitems = 0;
     std::vector<DecImage> imgs; std::vector<int16_t *> coef_ptrs; std::vector<size_t> coef_bytes; std::vector<char> tables_ok;
     size_t raw_total = 0, o_img = 0, o_tab = 0, o_flag = 0, o_mark = 0, par_bytes = 0;
+    size_t hw_raw = 0, hw_stream = 0, hw_grp = 0, hw_sub = 0, hw_blk = 0, hw_mgrp = 0, hw_msub = 0, hw_mblk = 0; int hw_n = 0;
+    unsigned long long generation = 0;
     uint32_t grp_total = 0, sub_total = 0, blk_total = 0, max_grp = 0, max_sub = 0, max_blk = 0;
     uint8_t *h_raw = nullptr; size_t cap_hraw = 0;          // pinned staging of the entropy-coded segments
     uint8_t *d_raw = nullptr, *d_stream = nullptr; size_t cap_raw = 0, cap_stream = 0;

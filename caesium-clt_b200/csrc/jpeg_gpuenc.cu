@@ -341,9 +341,11 @@ __global__ void k_ge_fill_dummy(int16_t *__restrict__ coef, long long comp_off, 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+static thread_local unsigned long long *tl_enc_generation = nullptr;   // bumped on every reallocation (captured graphs hold the old pointers)
 template <typename T> static bool grow(T *&p, size_t &cap, size_t need, bool host, std::string &err)
 {
     if (need <= cap) return true;
+    if (tl_enc_generation) ++*tl_enc_generation;
     if (p) { if (host) cudaFreeHost(p); else cudaFree(p); }
     p = nullptr; cap = 0;
     // several sizes depend on image CONTENT (bytes of entropy-coded output); round up to a power of two with headroom so
@@ -368,10 +370,16 @@ GpuEncoder::~GpuEncoder()
 bool GpuEncoder::size_back_buffers(size_t image_bytes, std::string &err)
 {   // everything whose size follows the OUTPUT: bit buffer, 16-byte group arrays, stuffed bytes
     const int NS = (int)plan.scans.size();
-    est_image_bytes = image_bytes;
+    // capacities only grow (per image count): they are kernel arguments of the launch sequence, and a sequence whose arguments do
+    // not change from megabatch to megabatch can be replayed as a CUDA graph
+    if (nimg != cap_nimg) { cap_nimg = nimg; est_image_bytes = 0; }
+    if (image_bytes <= est_image_bytes && words_cap) return true;
+    est_image_bytes = image_bytes + image_bytes / 8;
+    image_bytes = est_image_bytes;
     words_cap = (uint32_t)std::min<size_t>((size_t)nimg * (image_bytes / 4 + 1) + 2 * (size_t)NS + 64, 0xFFFFFF00u);
     groups_cap = (uint32_t)((size_t)words_cap / 4 + NS + 1);
     out_stride = align_up(image_bytes + image_bytes / 8 + 1024, 256);
+    tl_enc_generation = &generation;
     size_t c;
     c = cap_words; if (!grow(d_words, c, (size_t)words_cap * 4 + 64, false, err)) return false; cap_words = c;
     c = cap_ff[0]; if (!grow(d_ffcount, c, (size_t)groups_cap * 4 + 4, false, err)) return false; cap_ff[0] = c;
@@ -379,6 +387,7 @@ bool GpuEncoder::size_back_buffers(size_t image_bytes, std::string &err)
     c = cap_out; if (!grow(d_out, c, out_stride * nimg, false, err)) return false; cap_out = c;
     size_t tb3 = 0; cub::DeviceScan::ExclusiveSum((void *)nullptr, tb3, d_ffcount, d_ffoff, (int)groups_cap, (cudaStream_t)0);
     c = cap_temp; if (tb3 + 256 > c) { if (!grow(d_temp, c, tb3 + 256, false, err)) return false; cap_temp = c; }
+    tl_enc_generation = nullptr;
     return true;
 }
 
@@ -394,6 +403,7 @@ bool GpuEncoder::prepare(const JpegGeom &g, bool progressive, int16_t *const *d_
     const long long U = plan.total_units;
     if (U >= (1ll << 31)) { err = "batch too large for the entropy encoder"; return false; }
     overflow = false;
+    tl_enc_generation = &generation;
     for (auto &sc_ : plan.scans) if (!masks_cover(sc_.mode, sc_.Al)) { err = "scan script outside the device encoder's mask range"; overflow = true; return false; }
     if (!ev_sizes) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | (stream_wait_mode() == 0 ? 0 : cudaEventBlockingSync))); ev_sizes = e; }
     // ---- buffers whose size follows the INPUT
@@ -434,11 +444,53 @@ bool GpuEncoder::prepare(const JpegGeom &g, bool progressive, int16_t *const *d_
     size_t est = out_bytes_hint ? out_bytes_hint / nimages + out_bytes_hint / nimages / 4 : coef_bytes / 3;
     est = std::max(est, learned_image_bytes + learned_image_bytes / 8) + 8192;
     est = std::min(est, coef_bytes * 2 + (size_t)plan.scans_per_image * 64 + 8192);      // worst case: 128 B per block and scan... bounded by the retry anyway
+    tl_enc_generation = nullptr;
     if (!size_back_buffers(est, err)) return false;
     memcpy(h_small + o_scans, plan.scans.data(), NS * sizeof(Scan));
     memcpy(h_small + o_comps, plan.comps.data(), NC * sizeof(BlockComp));
+    (void)st;
+    return true;
+}
+
+bool GpuEncoder::upload(void *stream_, std::string &err)
+{   // H2D of the scan / component descriptors prepare() wrote into pinned memory
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int NS = (int)plan.scans.size(), NC = (int)plan.comps.size();
     CU(cudaMemcpyAsync(d_scans, h_small + o_scans, NS * sizeof(Scan), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_comps, h_small + o_comps, NC * sizeof(BlockComp), cudaMemcpyHostToDevice, st));
+    return true;
+}
+
+unsigned long long GpuEncoder::signature() const
+{   // everything upload() + enqueue_front() + enqueue_sizes() + enqueue_back() bake into their driver calls
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { h = (h ^ v) * 1099511628211ull; };
+    mix((unsigned long long)nimg); mix((unsigned long long)plan.scans.size()); mix((unsigned long long)plan.comps.size()); mix((unsigned long long)plan.total_units);
+    mix((unsigned long long)plan.max_comp_blocks); mix((unsigned long long)plan.scans_per_image); mix(words_cap); mix(groups_cap); mix(out_stride); mix(generation);
+    mix((unsigned long long)geom.width); mix((unsigned long long)geom.height); mix(prog ? 1 : 0);
+    for (int c = 0; c < geom.ncomp; c++) { mix((unsigned long long)geom.bw[c]); mix((unsigned long long)geom.bh[c]); mix((unsigned long long)geom.rbw[c]); mix((unsigned long long)geom.rbh[c]); mix((unsigned long long)geom.hs[c]); }
+    for (auto pb : coef_bases) mix((unsigned long long)(uintptr_t)pb);
+    int max_units = 0; for (auto &sc : plan.scans) max_units = std::max(max_units, sc.nblocks);
+    mix((unsigned long long)max_units);
+    return h;
+}
+
+// scan sizes / buffer layout on the device, and their way back to the host
+bool GpuEncoder::enqueue_sizes(void *stream_, std::string &err)
+{
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int NS = (int)plan.scans.size();
+    uint32_t *h_total = reinterpret_cast<uint32_t *>(h_small + o_total), *h_flags = reinterpret_cast<uint32_t *>(h_small + o_flags);
+    k_ge_scanout<<<1, 32, 0, st>>>(d_scans, NS, d_bitlen, d_bitoff, d_total, d_so, words_cap, groups_cap, d_flags);
+    LT_MARK("k_ge_scanout");
+    CU(cudaMemcpyAsync(h_total, d_total, (size_t)NS * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_flags, d_flags, 12, cudaMemcpyDeviceToHost, st));
+    LT_MARK("copy");
+    return true;
+}
+bool GpuEncoder::mark_sizes(void *stream_, std::string &err)
+{   // the event finish() waits for before it sizes the D2H of the scans (kept out of captured graphs: a plain stream operation)
+    CU(cudaEventRecord((cudaEvent_t)ev_sizes, (cudaStream_t)stream_));
     return true;
 }
 
@@ -446,13 +498,7 @@ bool GpuEncoder::enqueue_back(void *stream_, std::string &err)
 {
     cudaStream_t st = (cudaStream_t)stream_;
     const int NS = (int)plan.scans.size(), NC = (int)plan.comps.size();
-    uint32_t *h_total = reinterpret_cast<uint32_t *>(h_small + o_total), *h_flags = reinterpret_cast<uint32_t *>(h_small + o_flags);
-    k_ge_scanout<<<1, 32, 0, st>>>(d_scans, NS, d_bitlen, d_bitoff, d_total, d_so, words_cap, groups_cap, d_flags);
-    LT_MARK("k_ge_scanout");
-    CU(cudaMemcpyAsync(h_total, d_total, (size_t)NS * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h_flags, d_flags, 12, cudaMemcpyDeviceToHost, st));
-    CU(cudaEventRecord((cudaEvent_t)ev_sizes, st));
-    LT_MARK("copy");
+    uint32_t *h_flags = reinterpret_cast<uint32_t *>(h_small + o_flags);
     const dim3 gb(cdiv(plan.max_comp_blocks, 128), NC);
     k_ge_zero<<<dim3(64, NS), 256, 0, st>>>(d_so, d_words);
     LT_MARK("k_ge_zero");
@@ -476,6 +522,11 @@ bool GpuEncoder::enqueue_back(void *stream_, std::string &err)
 }
 
 bool GpuEncoder::enqueue(void *stream_, bool fill_dummy, std::string &err)
+{
+    return enqueue_front(stream_, fill_dummy, err) && enqueue_sizes(stream_, err) && mark_sizes(stream_, err) && enqueue_back(stream_, err);
+}
+
+bool GpuEncoder::enqueue_front(void *stream_, bool fill_dummy, std::string &err)
 {
     cudaStream_t st = (cudaStream_t)stream_;
     const JpegGeom &g = geom;
@@ -517,7 +568,8 @@ bool GpuEncoder::enqueue(void *stream_, bool fill_dummy, std::string &err)
     cub::DeviceScan::ExclusiveSum(d_temp, tb, d_bitlen, d_bitoff, (int)U, st);
     LT_MARK("cub_scan");
     launches += 8;
-    return enqueue_back(st, err);
+    CU(cudaGetLastError());
+    return true;
 }
 
 bool GpuEncoder::finish(void *stream_, bool fetch, std::string &err)
@@ -539,7 +591,7 @@ bool GpuEncoder::finish(void *stream_, bool fetch, std::string &err)
             CU(stream_wait(st));
             if (!size_back_buffers(img_max + img_max / 16 + 4096, err)) return false;
             retries++;
-            if (!enqueue_back(st, err)) return false;
+            if (!enqueue_sizes(st, err) || !mark_sizes(st, err) || !enqueue_back(st, err)) return false;
             continue;
         }
         if (fetch) {
@@ -555,7 +607,7 @@ bool GpuEncoder::finish(void *stream_, bool fetch, std::string &err)
             if (attempt >= 3) { err = "entropy encoder could not size its output"; return false; }
             if (!size_back_buffers((size_t)h_flags[4 + 3] + 4096, err)) return false;
             retries++;
-            if (!enqueue_back(st, err)) return false;
+            if (!enqueue_sizes(st, err) || !mark_sizes(st, err) || !enqueue_back(st, err)) return false;
             continue;
         }
         learned_image_bytes = std::max<size_t>(learned_image_bytes, h_flags[4 + 3]);
@@ -591,7 +643,7 @@ bool GpuEncoder::finish(void *stream_, bool fetch, std::string &err)
 
 bool GpuEncoder::encode(const JpegGeom &g, bool progressive, int16_t *const *d_coefs, int nimages, void *stream_, bool fill_dummy, std::string &err, size_t out_bytes_hint)
 {
-    return prepare(g, progressive, d_coefs, nimages, stream_, out_bytes_hint, err) && enqueue(stream_, fill_dummy, err) && finish(stream_, true, err);
+    return prepare(g, progressive, d_coefs, nimages, stream_, out_bytes_hint, err) && upload(stream_, err) && enqueue(stream_, fill_dummy, err) && finish(stream_, true, err);
 }
 
 } // namespace b200

@@ -26,8 +26,16 @@ public:
     // The same in three steps (see jpeg_gpuenc.cu): prepare() sizes buffers and uploads descriptors, enqueue() launches every pass
     // without waiting (may be repeated on unchanged inputs), finish() waits, fetches the stuffed scans (fetch = false: leaves them
     // in HBM; results[].data == nullptr, lengths valid) and describes the result.
-    bool prepare(const JpegGeom &g, bool progressive, int16_t *const *d_coefs, int nimages, void *stream, size_t out_bytes_hint, std::string &err);
-    bool enqueue(void *stream, bool fill_dummy, std::string &err);
+    bool prepare(const JpegGeom &g, bool progressive, int16_t *const *d_coefs, int nimages, void *stream, size_t out_bytes_hint, std::string &err);   // host work only
+    bool upload(void *stream, std::string &err);                       // H2D of the descriptors
+    bool enqueue(void *stream, bool fill_dummy, std::string &err);     // = front + sizes + mark + back
+    // the pieces, for callers that replay the sequence as CUDA graphs (front + sizes in one graph, mark_sizes as a plain event
+    // record, back in a second graph); signature() identifies the driver calls they would make
+    bool enqueue_front(void *stream, bool fill_dummy, std::string &err);
+    bool enqueue_sizes(void *stream, std::string &err);
+    bool mark_sizes(void *stream, std::string &err);
+    bool enqueue_back(void *stream, std::string &err);
+    unsigned long long signature() const;
     bool finish(void *stream, bool fetch, std::string &err);
     int retries = 0;            // back halves repeated because the output estimate was too small
     double wait_sizes_ms = 0, wait_final_ms = 0;   // host time spent in finish()'s two waits (tracing)
@@ -36,8 +44,8 @@ public:
     bool overflow = false;      // the failure was "scan larger than its buffer": the caller may use the host encoder
     int launches = 0;
 private:
-    bool enqueue_back(void *stream, std::string &err);
     bool size_back_buffers(size_t image_bytes, std::string &err);
+    unsigned long long generation = 0; int cap_nimg = 0;
     int nimg = 0;
     JpegGeom geom; bool prog = false;
     std::vector<int16_t *> coef_bases;

@@ -97,8 +97,8 @@ JpegPipe *pipe_create(const uint8_t *const *in, const size_t *in_len, int n, con
             raw += P->ds[i].ecs_end - P->ds[i].ecs_begin;
         }
         G->slot.dec = new GpuDecoder(); G->slot.enc = new GpuEncoder();
-        if (!G->slot.dec->prepare(G->items, st, err)) return nullptr;                       // entropy-coded bytes + tables go up here, once
-        if (!G->slot.enc->prepare(P->gout, P->progressive, G->bases.data(), Kg, st, raw, err)) return nullptr;
+        if (!G->slot.dec->prepare(G->items, st, err) || !G->slot.dec->upload(st, err)) return nullptr;       // entropy-coded bytes + tables go up here, once
+        if (!G->slot.enc->prepare(P->gout, P->progressive, G->bases.data(), Kg, st, raw, err) || !G->slot.enc->upload(st, err)) return nullptr;
         if (cudaStreamSynchronize(st) != cudaSuccess) { err = "upload failed"; return nullptr; }
         P->groups.push_back(std::move(G));
     }
