@@ -68,25 +68,32 @@ def _gen_one(job):
     raise ValueError(kind)
 
 
-def make_inputs(n_unique, first_index, kind="jpeg4k", procs=None):
+def make_inputs(n_unique, first_index, kind="jpeg4k", procs=None, indices=None):
     """n_unique seeded sources: 4K JPEGs (q=90, 4:2:0, baseline, Annex-K tables via Pillow/libjpeg-turbo), 6000x4000 JPEGs of
-    the same kind, or 4096x4096 RGBA PNGs (Paeth rows, zlib level 6)."""
+    the same kind, or 4096x4096 RGBA PNGs (Paeth rows, zlib level 6).  indices: explicit seed indices (a rank's shard)."""
     import multiprocessing as mp
+    if indices is not None:
+        n_unique = len(indices)
     procs = min(n_unique, procs or usable_cores())
-    jobs = [(kind, first_index + i) for i in range(n_unique)]
+    jobs = [(kind, i) for i in indices] if indices is not None else [(kind, first_index + i) for i in range(n_unique)]
     if procs <= 1:
         return [_gen_one(j) for j in jobs]
     with mp.get_context("fork").Pool(procs) as pool:
         return pool.map(_gen_one, jobs)
 
 
-def load_pkg():
+def load_pkg_shallow():
+    """register the package (its directory name is not an identifier) without loading the shared library"""
     pkg_dir = os.path.join(ROOT, "caesium-clt_b200")
     if "caesium_clt_b200" not in sys.modules:
         spec = importlib.util.spec_from_file_location("caesium_clt_b200", os.path.join(pkg_dir, "__init__.py"), submodule_search_locations=[pkg_dir])
         mod = importlib.util.module_from_spec(spec)
         sys.modules["caesium_clt_b200"] = mod
         spec.loader.exec_module(mod)
+
+
+def load_pkg():
+    load_pkg_shallow()
     import caesium_clt_b200._lib as lib
     lib.lib()
     return lib
@@ -430,7 +437,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="images per step per GPU, device-resident leg (128 x ~1.5 MB of scan bytes > L2)")
     ap.add_argument("--group", type=int, default=8, help="images per launch sequence (megabatch) in the device-resident leg")
-    ap.add_argument("--e2e-batch", type=int, default=256, help="images per step per GPU (C-ABI leg)")
+    ap.add_argument("--e2e-batch", type=int, default=1024, help="images per step per GPU (C-ABI leg); one blocking b200_compress_batch call per step, so every step pays one pipeline fill and drain (~8 ms): 256 images per step under-reports the steady-state rate by ~10 %")
     ap.add_argument("--unique", type=int, default=64, help="unique synthetic sources per rank, cycled to fill a batch")
     ap.add_argument("--configs", default=None, help="comma list of BASELINE configs to run (1 = the headline; 2,3,4 = sub-records); default 1,2,3,4 on one GPU, 1 under torchrun")
     ap.add_argument("--png-unique", type=int, default=4); ap.add_argument("--png-batch", type=int, default=16)
@@ -450,7 +457,13 @@ def main():
     # ---- inputs first (fork pool must run before CUDA is initialised in this process)
     cores = usable_cores()
     threads = max(1, cores // max(1, world))
-    datas = make_inputs(args.unique, rank * args.unique, "jpeg4k", procs=threads)
+    # the data set is world x unique seeded sources; each rank owns a shard of it (caesium-clt_b200/sharding.py: the same code the
+    # world_size-2 gloo test runs on CPU); no image ever crosses ranks
+    from importlib import import_module
+    load_pkg_shallow()
+    S = import_module("caesium_clt_b200.sharding")
+    shard = S.shard_indices([1] * (world * args.unique), world, rank, policy="rr")
+    datas = make_inputs(len(shard), 0, "jpeg4k", procs=threads, indices=shard)
     png_datas = make_inputs(args.png_unique, 0, "png4096") if 3 in which else None
     webp_datas = make_inputs(args.webp_unique, 0, "jpeg24mp") if 4 in which else None
     # batch workers mostly wait for their stream: on a box with few cores per GPU a rank still keeps eight megabatches in flight
@@ -465,10 +478,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     # quant tables: computed on rank 0, broadcast over NCCL (the only collective of this path), checked locally
-    qt = torch.tensor(L.jpeg_quant_table(QUALITY, 0).astype(np.int32), device="cuda")
-    if world > 1:
-        dist.broadcast(qt, 0)
-    assert np.array_equal(qt.cpu().numpy().astype(np.uint16), L.jpeg_quant_table(QUALITY, 0)), "quant-table handshake failed"
+    got = S.broadcast_quant_table(L.jpeg_quant_table(QUALITY, 0), dist if world > 1 else None, 0, device="cuda")
+    assert np.array_equal(got, L.jpeg_quant_table(QUALITY, 0)), "quant-table handshake failed"
 
     p = L.default_params()
     p.jpeg_quality, p.jpeg_chroma_subsampling, p.jpeg_progressive = QUALITY, SUBSAMPLING, 1

@@ -1,6 +1,8 @@
 """N > 1 path on CPU: two gloo ranks shard an image list, each runs the (host-only) lossless JPEG transcode on its shard
 through the C-ABI, the quantisation-table handshake goes over the process group, and the gathered results equal the
-single-process run in input order.  This is the same sharding code bench.py uses under torchrun with NCCL."""
+single-process run in input order.  bench.py takes its per-rank shard of the synthetic set and does the quantisation-table
+handshake through the same module (caesium-clt_b200/sharding.py) under torchrun with NCCL; inside one process the library shards
+megabatches over its devices itself (api.cpp, LPT by bytes)."""
 import hashlib
 import os
 import sys
