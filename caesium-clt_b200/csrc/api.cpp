@@ -367,6 +367,9 @@ b200_status jpeg_to_webp(const uint8_t *in, size_t in_len, const b200_params *p,
     Slot *s = slot_acquire(prefer_dev < 0 ? runtime_next_device() : prefer_dev, err);
     if (!s) return make_status(B200_ERR_CUDA, err);
     b200_status st = ok_status();
+    static const bool verbose = getenv("B200_TRACE") && atoi(getenv("B200_TRACE")) >= 2;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto t1 = t0, t2 = t0;
     do {
         if (!s->ensure((size_t)gin.total_coefs * 2, (size_t)gout.total_coefs * 2, 0, 1 << 14, err)) { st = make_status(B200_ERR_OUT_OF_MEMORY, err); break; }
         bool on_device = false;
@@ -376,10 +379,17 @@ b200_status jpeg_to_webp(const uint8_t *in, size_t in_len, const b200_params *p,
             if (r == 0) on_device = true; else if (r != 1) { st = make_status(B200_ERR_CUDA, err); break; }
         }
         if (!on_device && !rd.decode(s->h_in, err)) { st = make_status(B200_ERR_CORRUPT_INPUT, err); break; }
+        t1 = std::chrono::steady_clock::now();
         uint8_t *rgb[3] = {nullptr, nullptr, nullptr};
         if (!slot_transform_resized(s, gin, gout, err, false, !on_device, rgb)) { st = make_status(B200_ERR_CUDA, err); break; }
+        t2 = std::chrono::steady_clock::now();
         if (!s->webp) s->webp = new WebpDevice();
         if (!s->webp->encode_planes(rgb[0], rgb[1], rgb[2], (int)nw, (int)nh, (int)p->webp_quality, s->stream, out, err)) { st = make_status(B200_ERR_CUDA, err); break; }
+        if (verbose) {
+            auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+            fprintf(stderr, "[b200 trace] jpeg %dx%d -> webp %ux%u: segment walk + entropy decode (device %d) %.1f ms, transform + resize launch %.1f ms, VP8 (wait for the device %.1f ms, boolean coder %.1f ms) %.1f ms\n",
+                    gin.width, gin.height, nw, nh, (int)on_device, ms(t0, t1), ms(t1, t2), s->webp->last_wait_ms, s->webp->last_code_ms, ms(t2, std::chrono::steady_clock::now()));
+        }
     } while (0);
     slot_release(s);
     return st;

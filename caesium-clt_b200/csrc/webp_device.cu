@@ -1,6 +1,7 @@
 // webp_device.cu -- see webp_device.h.  caesium::convert_in_memory(.., WebP) (/root/reference/src/compressor.rs:288-292).
 #include <cuda_runtime.h>
 #include <cstring>
+#include <chrono>
 #include "webp_device.h"
 #include "vp8_kernels.h"
 #include "vp8_host.h"
@@ -49,7 +50,10 @@ bool WebpDevice::encode_planes(const uint8_t *d_r, const uint8_t *d_g, const uin
     if (rc) { err = std::string("vp8 kernels: ") + cudaGetErrorString((cudaError_t)rc); return false; }
     CUW(cudaMemcpyAsync(h_out, d_levels, lv_bytes, cudaMemcpyDeviceToHost, st));
     CUW(cudaMemcpyAsync(h_out + lv_bytes, d_modes, md_bytes, cudaMemcpyDeviceToHost, st));
+    const auto t0 = std::chrono::steady_clock::now();
     CUW(stream_wait(st));
+    const auto t1 = std::chrono::steady_clock::now();
+    struct Lap { WebpDevice *d; std::chrono::steady_clock::time_point a, b; ~Lap() { d->last_wait_ms = std::chrono::duration<double, std::milli>(b - a).count(); d->last_code_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - b).count(); } } lap{this, t0, t1};
     if (levels_out) memcpy(levels_out, h_out, lv_bytes);
     if (modes_out) memcpy(modes_out, h_out + lv_bytes, md_bytes);
     if (!vp8_write_file(w, h, qi, reinterpret_cast<const int16_t *>(h_out), h_out + lv_bytes, out)) { err = "VP8 frame cannot be framed (first partition too large)"; return false; }

@@ -15,6 +15,7 @@ struct WebpDevice {
     int *d_progress = nullptr; size_t cap_progress = 0;
     uint8_t *h_out = nullptr; size_t cap_hout = 0;             // pinned: levels | modes
     uint8_t *h_rgb = nullptr; size_t cap_hrgb = 0;             // pinned staging for host RGB
+    double last_wait_ms = 0, last_code_ms = 0;                 // tracing: wait for the kernels + D2H, host boolean coder of the last encode
     ~WebpDevice();
     // d_r/d_g/d_b: device planes (pitch w).  Produces the .webp file; optionally also hands back the levels/modes (tests).
     bool encode_planes(const uint8_t *d_r, const uint8_t *d_g, const uint8_t *d_b, int w, int h, int quality, void *stream,
