@@ -386,9 +386,14 @@ def png_stage_times(L, png):
         table[name] = e
     named = {k: v for k, v in table.items() if "frac" in v}
     dom = max(named, key=lambda k: named[k]["ms"] * named[k]["launches"]) if named else None
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{dom}_bytes_per_launch")
+    except Exception:
+        pass
     return {"value": round(16.777216 / (busy / 1e3), 1) if busy else None, "device_busy_ms_per_image": round(busy, 3),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": named[dom]["GBps"] if dom else None, "peak": peak, "unit": "GB/s", "frac": named[dom]["frac"] if dom else None,
-                         "traffic": None, "peak_source": peak_src, "ms_per_launch": named[dom]["ms"] if dom else None, "all_kernels": table},
+                         "traffic": traffic, "peak_source": peak_src, "ms_per_launch": named[dom]["ms"] if dom else None, "all_kernels": table},
             "value_scope": "device-busy rate of one image's whole launch sequence (un-filter, checksum, probes, 4 filter trials + winner with K6 / K7 fixed + hash candidates / parse, DEFLATE coding): sum of kernel durations from events after every launch; inflate (host) and PCIe copies are in e2e only"}
 
 

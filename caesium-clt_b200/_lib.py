@@ -68,7 +68,7 @@ _SYMBOLS = [
     "b200_jpeg_batch_time", "b200_jpeg_batch_destroy", "b200_jpeg_encode_coefficients_device",
     "b200_png_decode", "b200_png_decode_reduced", "b200_png_filter", "b200_png_lz77", "b200_png_deflate_tokens", "b200_png_level_strategies",
     "b200_webp_encode_rgb", "b200_webp_write_levels", "b200_webp_qindex",
-    "b200_jpeg_pipe_create", "b200_jpeg_pipe_run", "b200_jpeg_pipe_finish", "b200_jpeg_pipe_fetch", "b200_jpeg_pipe_kernel_times", "b200_jpeg_pipe_destroy", "b200_device_jobs", "b200_device_numa_node", "b200_png_device_times", "b200_webp_decode",
+    "b200_jpeg_pipe_create", "b200_jpeg_pipe_run", "b200_jpeg_pipe_finish", "b200_jpeg_pipe_fetch", "b200_jpeg_pipe_kernel_times", "b200_jpeg_pipe_destroy", "b200_device_jobs", "b200_device_numa_node", "b200_png_device_times", "b200_webp_decode", "b200_webp_alpha_chunk", "b200_webp_wrap_alpha", "b200_webp_decode_rgba",
 ]
 
 
@@ -86,7 +86,7 @@ def lib():
                   "b200_jpeg_batch_upload", "b200_jpeg_batch_run", "b200_jpeg_batch_download", "b200_jpeg_batch_time",
                   "b200_png_decode", "b200_png_decode_reduced", "b200_png_filter", "b200_png_lz77", "b200_png_deflate_tokens",
                   "b200_webp_encode_rgb", "b200_webp_write_levels", "b200_jpeg_encode_coefficients_device",
-                  "b200_jpeg_pipe_create", "b200_jpeg_pipe_run", "b200_jpeg_pipe_finish", "b200_jpeg_pipe_fetch", "b200_jpeg_pipe_kernel_times", "b200_png_device_times", "b200_webp_decode"):
+                  "b200_jpeg_pipe_create", "b200_jpeg_pipe_run", "b200_jpeg_pipe_finish", "b200_jpeg_pipe_fetch", "b200_jpeg_pipe_kernel_times", "b200_png_device_times", "b200_webp_decode", "b200_webp_alpha_chunk", "b200_webp_wrap_alpha", "b200_webp_decode_rgba"):
             getattr(L, f).restype = Status
         L.b200_version.restype = C.c_char_p
         L.b200_sniff_format.restype = C.c_uint32
@@ -296,6 +296,21 @@ def png_deflate_tokens(tokens, adler):
     return _take(outp, outl)
 
 
+def webp_alpha_chunk(tokens, width, height):
+    """Host: ALPH chunk payload (VP8L-coded alpha plane) from the plane's LZ77 tokens."""
+    tokens = np.ascontiguousarray(tokens, dtype=np.uint32)
+    outp, outl = C.POINTER(C.c_uint8)(), C.c_size_t()
+    _check(lib().b200_webp_alpha_chunk(tokens.ctypes.data_as(C.c_void_p), C.c_size_t(tokens.size), int(width), int(height), C.byref(outp), C.byref(outl)))
+    return _take(outp, outl)
+
+
+def webp_wrap_alpha(simple_file, alph, width, height):
+    """Host: VP8X + ALPH + VP8 container from a simple lossy file and an ALPH payload."""
+    outp, outl = C.POINTER(C.c_uint8)(), C.c_size_t()
+    _check(lib().b200_webp_wrap_alpha(bytes(simple_file), C.c_size_t(len(simple_file)), bytes(alph), C.c_size_t(len(alph)), int(width), int(height), C.byref(outp), C.byref(outl)))
+    return _take(outp, outl)
+
+
 def png_device_times(data, level=3, iters=2):
     """{kernel: (ms per launch, launches per image)} of the PNG device pipeline on one image (b200_png_device_times)."""
     buf = C.create_string_buffer(1 << 14)
@@ -335,6 +350,19 @@ def webp_decode(data):
     arr = np.frombuffer(C.string_at(ptr, 3 * w.value * h.value), dtype=np.uint8).reshape(3, h.value, w.value).transpose(1, 2, 0).copy()
     lib().b200_free(ptr)
     return arr
+
+
+def webp_decode_rgba(data):
+    """Host WebP decoder incl. lossless files and alpha planes: bytes -> (uint8 [h, w, 3], uint8 [h, w] or None when opaque)."""
+    w, h, ptr, ap = C.c_int(), C.c_int(), C.POINTER(C.c_uint8)(), C.POINTER(C.c_uint8)()
+    _check(lib().b200_webp_decode_rgba(data, C.c_size_t(len(data)), C.byref(w), C.byref(h), C.byref(ptr), C.byref(ap)))
+    arr = np.frombuffer(C.string_at(ptr, 3 * w.value * h.value), dtype=np.uint8).reshape(3, h.value, w.value).transpose(1, 2, 0).copy()
+    lib().b200_free(ptr)
+    alpha = None
+    if ap:
+        alpha = np.frombuffer(C.string_at(ap, w.value * h.value), dtype=np.uint8).reshape(h.value, w.value).copy()
+        lib().b200_free(ap)
+    return arr, alpha
 
 
 def webp_write_levels(w, h, quality, levels, modes):

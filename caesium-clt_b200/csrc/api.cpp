@@ -27,6 +27,7 @@
 #include "vp8_host.h"
 #include "webp_device.h"
 #include "vp8_decode.h"
+#include "vp8l_alpha.h"
 #include "jpeg_pipe.h"
 #include "topology.h"
 #include "launch_timer.h"
@@ -520,7 +521,10 @@ b200_status png_to_jpeg(const uint8_t *in, size_t in_len, const b200_params *p, 
 }
 
 // Planar RGB on the host -> lossy WebP (K3 resize when width / height are set, then K8)
-b200_status rgb_to_webp(const std::vector<uint8_t> &rgb, uint32_t w, uint32_t h, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
+// alpha (optional): one 8-bit plane of the source's size.  It is resized like the colour planes, its LZ77 tokens come from K7 on the
+// device, and the file becomes VP8X + ALPH (VP8L-coded, lossless -- libwebp's default alpha_quality 100) + VP8.
+b200_status rgb_to_webp(const std::vector<uint8_t> &rgb, uint32_t w, uint32_t h, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out,
+                        const std::vector<uint8_t> *alpha = nullptr)
 {
     std::string err;
     uint32_t nw = w, nh = h;
@@ -541,16 +545,75 @@ b200_status rgb_to_webp(const std::vector<uint8_t> &rgb, uint32_t w, uint32_t h,
         ok = slot_transform_resized(s, gin, gout, err, false, false, planes, rgb.data()) &&
              s->webp->encode_planes(planes[0], planes[1], planes[2], (int)nw, (int)nh, (int)p->webp_quality, s->stream, out, err);
     }
+    if (ok && alpha) {
+        const size_t n = (size_t)nw * nh;
+        std::vector<uint8_t> resized;
+        const uint8_t *ap = alpha->data();
+        if (nw != w || nh != h) {
+            JpegGeom gin; gin.width = (int)w; gin.height = (int)h; gin.ncomp = 1; gin.cid[0] = 1; gin.hs[0] = gin.vs[0] = 1; gin.tq[0] = 0; gin.finalize();
+            JpegGeom gout = gin; gout.width = (int)nw; gout.height = (int)nh; gout.finalize();
+            uint8_t *planes[3] = {nullptr, nullptr, nullptr};
+            resized.resize(n);
+            ok = slot_transform_resized(s, gin, gout, err, false, false, planes, alpha->data()) && slot_fetch_planes(s, planes, 1, n, resized.data(), err);
+            ap = resized.data();
+        }
+        bool opaque = true;
+        for (size_t i = 0; ok && i < n; i++) if (ap[i] != 0xFF) { opaque = false; break; }
+        if (ok && !opaque) {
+            if (!s->png) s->png = new PngDevice();
+            std::vector<uint32_t> tokens; std::vector<uint8_t> alph, wrapped;
+            ok = s->png->plane_tokens(ap, n, (int)nw, s->stream, tokens, err);
+            if (ok && !(vp8l_alpha_from_tokens(tokens.data(), tokens.size(), (int)nw, (int)nh, alph) && webp_wrap_alpha(out, alph, (int)nw, (int)nh, wrapped))) { ok = false; err = "alpha plane could not be coded"; }
+            if (ok) out.swap(wrapped);
+        }
+    }
     slot_release(s);
     return ok ? ok_status() : make_status(B200_ERR_CUDA, err);
 }
 
+// The transparency of decoded PNG samples as one 8-bit plane (alpha channel: high byte of a 16-bit sample; tRNS: the palette's
+// per-entry alpha or the colour key).  false: every pixel is opaque.
+bool png_extract_alpha(const PngInfo &info, const std::vector<uint8_t> &raw, std::vector<uint8_t> &alpha)
+{
+    const size_t w = info.width, h = info.height;
+    const int bd = info.bit_depth, ct = info.color_type;
+    const bool channel = ct == 4 || ct == 6;
+    if (!channel && info.trns.empty()) return false;
+    alpha.assign(w * h, 0xFF);
+    bool any = false;
+    const size_t bps = bd >= 8 ? (size_t)bd / 8 : 1;
+    for (size_t y = 0; y < h; y++) {
+        const uint8_t *row = raw.data() + y * info.row_bytes;
+        uint8_t *a = alpha.data() + y * w;
+        for (size_t x = 0; x < w; x++) {
+            uint8_t v = 0xFF;
+            if (channel) v = row[(x * info.channels + info.channels - 1) * bps];
+            else if (ct == 3) { const unsigned idx = (row[(x * bd) >> 3] >> (8 - bd - ((x * bd) & 7))) & ((1u << bd) - 1); if (idx < info.trns.size()) v = info.trns[idx]; }
+            else if (ct == 0 && info.trns.size() >= 2) {
+                const unsigned key = ((unsigned)info.trns[0] << 8) | info.trns[1];
+                const unsigned sv = bd == 16 ? (((unsigned)row[2 * x] << 8) | row[2 * x + 1]) : bd == 8 ? row[x] : (row[(x * bd) >> 3] >> (8 - bd - ((x * bd) & 7))) & ((1u << bd) - 1);
+                if (sv == key) v = 0;
+            } else if (ct == 2 && info.trns.size() >= 6) {
+                bool eq = true;
+                for (int c = 0; c < 3 && eq; c++) {
+                    const unsigned key = ((unsigned)info.trns[2 * c] << 8) | info.trns[2 * c + 1];
+                    const unsigned sv = bd == 16 ? (((unsigned)row[(3 * x + c) * 2] << 8) | row[(3 * x + c) * 2 + 1]) : row[3 * x + c];
+                    eq = sv == key;
+                }
+                if (eq) v = 0;
+            }
+            a[x] = v; any |= v != 0xFF;
+        }
+    }
+    return any;
+}
+
 // WebP input (libcaesium webp::compress: decode, optional resize, re-encode at webp.quality): the VP8 bitstream is decoded on the
 // calling thread (format plumbing, bit-exact with libwebp's decoder -- vp8_decode.cpp), the RGB goes through K3 / K8 like any other source.
-b200_status webp_decode_status(const uint8_t *in, size_t in_len, WebpInfo &info, std::vector<uint8_t> &rgb)
+b200_status webp_decode_status(const uint8_t *in, size_t in_len, WebpInfo &info, std::vector<uint8_t> &rgb, std::vector<uint8_t> *alpha = nullptr)
 {
     std::string err;
-    const int rc = webp_decode_rgb(in, in_len, info, rgb, err);
+    const int rc = webp_decode_rgb(in, in_len, info, rgb, err, alpha);
     if (rc == 1) return make_status(B200_ERR_UNSUPPORTED, err);
     if (rc) return make_status(B200_ERR_CORRUPT_INPUT, err);
     return ok_status();
@@ -558,14 +621,14 @@ b200_status webp_decode_status(const uint8_t *in, size_t in_len, WebpInfo &info,
 b200_status webp_compress(const uint8_t *in, size_t in_len, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
 {
     if (p->webp_lossless) return make_status(B200_ERR_UNSUPPORTED, "lossless WebP (VP8L) is outside the GPU path (route to caesium::compress_in_memory)");
-    WebpInfo info; std::vector<uint8_t> rgb;
-    b200_status st = webp_decode_status(in, in_len, info, rgb);
+    WebpInfo info; std::vector<uint8_t> rgb, alpha;
+    b200_status st = webp_decode_status(in, in_len, info, rgb, &alpha);
     if (st.code) return st;
-    return rgb_to_webp(rgb, (uint32_t)info.width, (uint32_t)info.height, p, prefer_dev, out);
+    return rgb_to_webp(rgb, (uint32_t)info.width, (uint32_t)info.height, p, prefer_dev, out, alpha.empty() ? nullptr : &alpha);
 }
 
-// PNG source: samples are expanded to 8-bit RGB on the host (palette, grey, 16-bit -> high byte; an opaque alpha channel is
-// discarded, a transparent one is refused below) and go through the same K8.
+// PNG source: samples are expanded to 8-bit RGB on the host (palette, grey, 16-bit -> high byte) and go through the same K8; an
+// opaque alpha channel is discarded, real transparency becomes the file's alpha plane.
 b200_status png_to_webp(const uint8_t *in, size_t in_len, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
 {
     std::string err;
@@ -574,25 +637,17 @@ b200_status png_to_webp(const uint8_t *in, size_t in_len, const b200_params *p, 
     uint32_t nw = info.width, nh = info.height;
     if (p->width || p->height) compute_resize_dimensions(info.width, info.height, p->width, p->height, nw, nh);
     if (nw == 0 || nh == 0 || nw > 16383 || nh > 16383 || info.width > 65535 || info.height > 65535) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid dimensions for WebP");
-    // Transparency would need the VP8X container with an ALPH chunk (VP8L-coded alpha), which this path does not write: a PNG
-    // whose alpha is not fully opaque goes back to the host with code 3 rather than silently losing its transparency.
-    if (!info.trns.empty()) return make_status(B200_ERR_UNSUPPORTED, "PNG transparency needs the WebP alpha plane, outside the GPU path (route to caesium::convert_in_memory)");
-    if (info.color_type == 4 || info.color_type == 6) {
-        const size_t bps = (size_t)info.bit_depth / 8, px = (size_t)info.channels * bps;
-        bool opaque = true;
-        for (size_t y = 0; y < info.height && opaque; y++) {
-            const uint8_t *a = raw.data() + y * info.row_bytes + px - bps;
-            for (size_t x = 0; x < info.width; x++, a += px) if (a[0] != 0xFF || (bps == 2 && a[1] != 0xFF)) { opaque = false; break; }
-        }
-        if (!opaque) return make_status(B200_ERR_UNSUPPORTED, "PNG transparency needs the WebP alpha plane, outside the GPU path (route to caesium::convert_in_memory)");
-    }
+    // transparency (alpha channel, tRNS) travels as the file's alpha plane: VP8X + ALPH next to the lossy frame
+    std::vector<uint8_t> alpha;
+    const bool has_alpha = png_extract_alpha(info, raw, alpha);
     std::vector<uint8_t> rgb; int nc = 3;
     png_expand_planar(info, raw, false, rgb, nc);
-    return rgb_to_webp(rgb, info.width, info.height, p, prefer_dev, out);
+    return rgb_to_webp(rgb, info.width, info.height, p, prefer_dev, out, has_alpha ? &alpha : nullptr);
 }
 
 // Planar RGB on the host -> lossless PNG (K3 resize when asked, then the PNG leg's raw-sample entry point)
-b200_status rgb_to_png(const std::vector<uint8_t> &rgb, uint32_t w, uint32_t h, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out)
+b200_status rgb_to_png(const std::vector<uint8_t> &rgb, uint32_t w, uint32_t h, const b200_params *p, int prefer_dev, std::vector<uint8_t> &out,
+                       const std::vector<uint8_t> *alpha = nullptr)
 {
     std::string err;
     uint32_t nw = w, nh = h;
@@ -616,8 +671,26 @@ b200_status rgb_to_png(const std::vector<uint8_t> &rgb, uint32_t w, uint32_t h, 
             if (!slot_transform_resized(s, gin, gout, err, false, false, dp, rgb.data()) || !slot_fetch_planes(s, dp, 3, n, planes.data(), err)) { st = make_status(B200_ERR_CUDA, err); break; }
             src = planes.data();
         }
-        for (size_t i = 0; i < n; i++) { raw[3 * i] = src[i]; raw[3 * i + 1] = src[n + i]; raw[3 * i + 2] = src[2 * n + i]; }
-        PngInfo info; info.width = nw; info.height = nh; info.bit_depth = 8; info.color_type = 2; info.channels = 3; info.bits_per_pixel = 24; info.bpp = 3; info.row_bytes = (size_t)nw * 3;
+        PngInfo info; info.width = nw; info.height = nh; info.bit_depth = 8;
+        if (!alpha) {
+            for (size_t i = 0; i < n; i++) { raw[3 * i] = src[i]; raw[3 * i + 1] = src[n + i]; raw[3 * i + 2] = src[2 * n + i]; }
+            info.color_type = 2; info.channels = 3; info.bits_per_pixel = 24; info.bpp = 3; info.row_bytes = (size_t)nw * 3;
+        } else {
+            // transparency stays: RGBA samples (the alpha plane takes the same Lanczos3 as the colour planes)
+            std::vector<uint8_t> ra;
+            const uint8_t *ap = alpha->data();
+            if (nw != w || nh != h) {
+                JpegGeom gin; gin.width = (int)w; gin.height = (int)h; gin.ncomp = 1; gin.cid[0] = 1; gin.hs[0] = gin.vs[0] = 1; gin.tq[0] = 0; gin.finalize();
+                JpegGeom gout = gin; gout.width = (int)nw; gout.height = (int)nh; gout.finalize();
+                uint8_t *dp[3] = {nullptr, nullptr, nullptr};
+                ra.resize(n);
+                if (!slot_transform_resized(s, gin, gout, err, false, false, dp, alpha->data()) || !slot_fetch_planes(s, dp, 1, n, ra.data(), err)) { st = make_status(B200_ERR_CUDA, err); break; }
+                ap = ra.data();
+            }
+            raw.resize(4 * n);
+            for (size_t i = 0; i < n; i++) { raw[4 * i] = src[i]; raw[4 * i + 1] = src[n + i]; raw[4 * i + 2] = src[2 * n + i]; raw[4 * i + 3] = ap[i]; }
+            info.color_type = 6; info.channels = 4; info.bits_per_pixel = 32; info.bpp = 4; info.row_bytes = (size_t)nw * 4;
+        }
         png_reduce_palette(info, raw);
         if (!s->png) s->png = new PngDevice();
         std::vector<uint8_t> z;
@@ -874,10 +947,12 @@ b200_status b200_convert_in_memory(const uint8_t *in, size_t in_len, const b200_
         try {
             if (fmt == B200_FMT_JPEG && params->jpeg_optimize) return make_status(B200_ERR_UNSUPPORTED, "lossless conversion to JPEG is outside the GPU path (route to caesium::convert_in_memory)");
             if (fmt == B200_FMT_PNG && !params->png_optimize) return make_status(B200_ERR_UNSUPPORTED, "lossy PNG (imagequant) is outside the GPU path (route to caesium::convert_in_memory)");
-            WebpInfo wi; std::vector<uint8_t> rgb, v;
-            b200_status s = webp_decode_status(in, in_len, wi, rgb);
+            WebpInfo wi; std::vector<uint8_t> rgb, alpha, v;
+            b200_status s = webp_decode_status(in, in_len, wi, rgb, &alpha);
             if (s.code) return s;
-            s = fmt == B200_FMT_JPEG ? planes_to_jpeg(rgb, (uint32_t)wi.width, (uint32_t)wi.height, 3, params, -1, v) : rgb_to_png(rgb, (uint32_t)wi.width, (uint32_t)wi.height, params, -1, v);
+            // a JPEG has no alpha (the image crate's to_rgb8 drops it); a PNG keeps it as an RGBA image
+            s = fmt == B200_FMT_JPEG ? planes_to_jpeg(rgb, (uint32_t)wi.width, (uint32_t)wi.height, 3, params, -1, v)
+                                     : rgb_to_png(rgb, (uint32_t)wi.width, (uint32_t)wi.height, params, -1, v, alpha.empty() ? nullptr : &alpha);
             if (s.code) return s;
             return give(v, out, out_len);
         } catch (const std::exception &e) { return make_status(B200_ERR_OUT_OF_MEMORY, e.what()); }
@@ -902,9 +977,10 @@ static b200_status webp_to_size(const uint8_t *in, size_t in_len, b200_params *p
 {
     if (params->webp_lossless) return make_status(B200_ERR_UNSUPPORTED, "lossless WebP (VP8L) is outside the GPU path (route to caesium::compress_to_size_in_memory)");
     std::string err;
-    WebpInfo wi; std::vector<uint8_t> rgb;
-    b200_status st = webp_decode_status(in, in_len, wi, rgb);
+    WebpInfo wi; std::vector<uint8_t> rgb, alpha;
+    b200_status st = webp_decode_status(in, in_len, wi, rgb, &alpha);
     if (st.code) return st;
+    if (!alpha.empty()) return make_status(B200_ERR_UNSUPPORTED, "compress_to_size on a WebP with an alpha plane is outside the GPU path (route to caesium::compress_to_size_in_memory)");
     uint32_t w = (uint32_t)wi.width, h = (uint32_t)wi.height, nw = w, nh = h;
     if (params->width || params->height) compute_resize_dimensions(w, h, params->width, params->height, nw, nh);
     if (nw == 0 || nh == 0 || nw > 16383 || nh > 16383) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid dimensions for WebP");
@@ -1300,6 +1376,26 @@ b200_status b200_png_deflate_tokens(const uint32_t *tokens, size_t ntokens, uint
     memcpy(*out, z.data(), z.size()); *out_len = z.size();
     return ok_status();
 }
+b200_status b200_webp_alpha_chunk(const uint32_t *tokens, size_t ntokens, int width, int height, uint8_t **out, size_t *out_len)
+{
+    if (!tokens || !out || !out_len || width < 1 || height < 1 || width > 16383 || height > 16383) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid argument");
+    std::vector<uint8_t> a;
+    if (!vp8l_alpha_from_tokens(tokens, ntokens, width, height, a)) return make_status(B200_ERR_INVALID_ARGUMENT, "the tokens do not cover the plane");
+    *out = (uint8_t *)malloc(a.size() + 1);
+    if (!*out) return make_status(B200_ERR_OUT_OF_MEMORY, "malloc failed");
+    memcpy(*out, a.data(), a.size()); *out_len = a.size();
+    return ok_status();
+}
+b200_status b200_webp_wrap_alpha(const uint8_t *simple_file, size_t file_len, const uint8_t *alph, size_t alph_len, int width, int height, uint8_t **out, size_t *out_len)
+{
+    if (!simple_file || !alph || !out || !out_len || width < 1 || height < 1 || width > 16383 || height > 16383) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid argument");
+    std::vector<uint8_t> f(simple_file, simple_file + file_len), a(alph, alph + alph_len), o;
+    if (!webp_wrap_alpha(f, a, width, height, o)) return make_status(B200_ERR_INVALID_ARGUMENT, "not a simple lossy WebP file");
+    *out = (uint8_t *)malloc(o.size() + 1);
+    if (!*out) return make_status(B200_ERR_OUT_OF_MEMORY, "malloc failed");
+    memcpy(*out, o.data(), o.size()); *out_len = o.size();
+    return ok_status();
+}
 // ---- WebP stage entry points -----------------------------------------------------------------------------------------
 b200_status b200_webp_encode_rgb(const uint8_t *rgb, int w, int h, int quality, uint8_t **out, size_t *out_len, int16_t *levels, uint8_t *modes)
 {
@@ -1320,12 +1416,28 @@ b200_status b200_webp_decode(const uint8_t *in, size_t in_len, int *width, int *
     if (!in || !width || !height || !rgb) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
     *rgb = nullptr;
     try {
-        WebpInfo wi; std::vector<uint8_t> v;
-        b200_status s = webp_decode_status(in, in_len, wi, v);
+        WebpInfo wi; std::vector<uint8_t> v, a;
+        b200_status s = webp_decode_status(in, in_len, wi, v, &a);
         if (s.code) return s;
         *width = wi.width; *height = wi.height;
         size_t n = 0;
         return give(v, rgb, &n);
+    } catch (const std::exception &e) { return make_status(B200_ERR_OUT_OF_MEMORY, e.what()); }
+}
+b200_status b200_webp_decode_rgba(const uint8_t *in, size_t in_len, int *width, int *height, uint8_t **rgb, uint8_t **alpha)
+{
+    if (!in || !width || !height || !rgb || !alpha) return make_status(B200_ERR_INVALID_ARGUMENT, "null argument");
+    *rgb = nullptr; *alpha = nullptr;
+    try {
+        WebpInfo wi; std::vector<uint8_t> v, a;
+        b200_status s = webp_decode_status(in, in_len, wi, v, &a);
+        if (s.code) return s;
+        *width = wi.width; *height = wi.height;
+        size_t n = 0;
+        if (!a.empty()) { s = give(a, alpha, &n); if (s.code) return s; }
+        s = give(v, rgb, &n);
+        if (s.code) { free(*alpha); *alpha = nullptr; }
+        return s;
     } catch (const std::exception &e) { return make_status(B200_ERR_OUT_OF_MEMORY, e.what()); }
 }
 b200_status b200_webp_write_levels(int w, int h, int quality, const int16_t *levels, const uint8_t *modes, uint8_t **out, size_t *out_len)

@@ -292,6 +292,40 @@ bool PngDevice::reduce_and_code(PngInfo &info, bool probed, const uint32_t *h_fl
     return true;
 }
 
+// LZ77 tokens of a byte plane that sits on the host (the alpha plane of a WebP with transparency: bpp 1, stride = width): K7 with
+// its pixel / row candidates and the hash chains, parallel parse, compaction; the tokens come back to the host (vp8l_alpha.cpp codes them).
+bool PngDevice::plane_tokens(const uint8_t *plane, size_t n, int stride, void *stream_, std::vector<uint32_t> &tokens, std::string &err)
+{
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (!n || stride < 1) { err = "empty plane"; return false; }
+    if (!ensure_buffers(n, n, (size_t)stride, st, err)) return false;
+    if (!growp(h_raw, cap_hraw, n + 4096 + 64, true, err) || !growp(h_tok, cap_htok, (n + 64) * 4 + 64, true, err)) return false;
+    memcpy(h_raw, plane, n);
+    CUP(cudaMemcpyAsync(d_filt, h_raw, n, cudaMemcpyHostToDevice, st));
+    const size_t nchunks = (n + kChunk - 1) / kChunk;
+    int rc = launch_png_match(d_filt, d_best, n, 1, stride, st);
+    if (!rc) rc = launch_png_hashmatch(d_filt, d_best, n, d_hist + 2048, st);
+    if (rc) { err = std::string("png kernels: ") + cudaGetErrorString((cudaError_t)rc); return false; }
+    CUP(cudaMemsetAsync(d_hist, 0, 316 * 4, st));
+    rc = launch_png_parse(d_best, d_filt, n, kChunk, d_tok, d_counts, d_hist, st);
+    if (rc) { err = std::string("png parse: ") + cudaGetErrorString((cudaError_t)rc); return false; }
+    size_t tb = cap_temp;
+    cub::DeviceScan::ExclusiveSum(d_temp, tb, d_counts, d_offsets, (int)nchunks, st);
+    rc = launch_png_compact(d_tok, d_counts, d_offsets, nchunks, kChunk, d_out, st);
+    if (rc) { err = std::string("png compact: ") + cudaGetErrorString((cudaError_t)rc); return false; }
+    uint32_t *d_ntok = d_hist + 1032;
+    k_png_ntok<<<1, 32, 0, st>>>(d_counts, d_offsets, nchunks, d_ntok);
+    uint32_t *h_n = reinterpret_cast<uint32_t *>(h_small + 64);
+    CUP(cudaMemcpyAsync(h_n, d_ntok, 4, cudaMemcpyDeviceToHost, st));
+    CUP(stream_wait(st));
+    const size_t ntok = *h_n;
+    if (ntok > n) { err = "token count out of range"; return false; }
+    CUP(cudaMemcpyAsync(h_tok, d_out, ntok * 4, cudaMemcpyDeviceToHost, st));
+    CUP(stream_wait(st));
+    tokens.assign(h_tok, h_tok + ntok);
+    return true;
+}
+
 // ---- stage entry points (b200_png_filter / b200_png_lz77): plain allocate-run-free, used by the parity tests ----------------
 bool png_stage_filter(const uint8_t *raw, int h, int rb, int bpp, int strategy, uint8_t *filtered, std::string &err)
 {

@@ -38,6 +38,8 @@ struct PngDevice {
     bool compress(PngInfo &info, const std::vector<uint8_t> &raw, int level, void *stream, std::vector<uint8_t> &zlib_stream, int *chosen_strategy, std::string &err);
     // filter + match + parse of d_raw with one strategy (results in d_filt / d_tok / d_counts / d_hist)
     bool run_strategy(int strategy, int h, int rb, int bpp, void *stream, std::string &err, uint8_t *filt = nullptr, bool do_filter = true, bool with_hash = true);
+    // K7 over a byte plane on the host (bpp 1, stride = width) -> compacted LZ77 tokens on the host
+    bool plane_tokens(const uint8_t *plane, size_t n, int stride, void *stream, std::vector<uint32_t> &tokens, std::string &err);
     uint8_t *d_filt_all = nullptr; size_t cap_filt_all = 0;          // the trials' filtered streams, one after another
 };
 

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdint>
 #include "png_kernels.h"
+#include "png_match_core.h"
 #include "launch_timer.h"
 
 namespace b200 {
@@ -41,7 +42,7 @@ __device__ __forceinline__ void five_filters_sm(const uint8_t *__restrict__ row,
     const int cur = row[x], a = row[x - bpp], b = up[x], c = up[x - bpp];
     v[0] = (uint8_t)cur; v[1] = (uint8_t)(cur - a); v[2] = (uint8_t)(cur - b); v[3] = (uint8_t)(cur - ((a + b) >> 1)); v[4] = (uint8_t)(cur - paeth_pred(a, b, c));
 }
-__global__ void __launch_bounds__(256) k_png_filter(const uint8_t *__restrict__ raw, uint8_t *__restrict__ filt, int h, int rb, int bpp, int strategy, const uint32_t *__restrict__ tlog,
+__global__ void __launch_bounds__(1024) k_png_filter(const uint8_t *__restrict__ raw, uint8_t *__restrict__ filt, int h, int rb, int bpp, int strategy, const uint32_t *__restrict__ tlog,
                                                     int row_pitch)
 {
     extern __shared__ __align__(16) uint32_t sm_all[];
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(256) k_png_filter(const uint8_t *__restrict__ 
     if (strategy >= 5) {
         if (threadIdx.x < 5) score[threadIdx.x] = 0;
         const int words = strategy == PNGF_MINSUM ? 0 : (strategy == PNGF_BIGRAMS ? 5 * 2048 : (strategy == PNGF_BIGENT ? 5 * 4096 : 5 * 256));
-        for (int i = threadIdx.x; i < words; i += blockDim.x) sm[i] = 0;
+        for (int i = threadIdx.x; i < words / 4; i += blockDim.x) reinterpret_cast<uint4 *>(sm)[i] = make_uint4(0, 0, 0, 0);      // sm is 16-byte aligned, words % 4 == 0
         __syncthreads();
         if (strategy == PNGF_MINSUM) {
             unsigned long long s5[5] = {0, 0, 0, 0, 0};
@@ -186,57 +187,109 @@ __device__ __forceinline__ int match_len(const uint8_t *__restrict__ s, size_t i
     return l;
 }
 
-// One thread per position, 256 positions per CTA.  Everything a CTA compares lies in three short windows of the stream -- the
-// positions themselves (+ the 24 bytes before them: distances up to three pixels), the same stretch one row up (+- one pixel) and
-// two rows up -- which are staged in shared memory once; the candidate loops then never leave it (from global memory the kernel ran
-// at 3 % of the HBM roofline on L1 / L2 latency).
-constexpr int MATCH_T = 256, MATCH_W = 552;
-__device__ __forceinline__ int match_len_sm(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, int maxlen)
-{   // a = bytes at the position, b = bytes at position - distance (both in shared memory)
-    int l = 0;
-    while (l + 4 <= maxlen) {
-        const uint32_t x = load32u(a + l) ^ load32u(b + l);
-        if (x) return l + ((__ffs((int)x) - 1) >> 3);
-        l += 4;
-    }
-    while (l < maxlen && a[l] == b[l]) l++;
-    return l;
-}
-__global__ void __launch_bounds__(MATCH_T) k_png_match(const uint8_t *__restrict__ s, uint32_t *__restrict__ best, size_t n, int bpp, int stride, int chunk)
+// One thread per position, 256 positions per CTA (png_match_core.h).  Everything a CTA compares lies in three short windows of the
+// stream -- the stretch itself (+ the 24 bytes before it: distances up to three pixels), the same stretch one row up (+- one pixel)
+// and two rows up -- staged in shared memory once.  Per candidate distance the byte comparisons of the whole stretch are then made
+// once (one ballot per 32 bytes) and kept as a bit array; a position's match length is the run of ones that starts at its bit.
+// (The first version compared bytes per position and candidate: ~1,040 instructions per position, issue-bound at 2.2 ms per
+// 4096 x 4096 RGBA stream.)
+// All three windows live in one shared array of 32-bit words (byte offsets OFF0 / OFF1 / OFF2; one spare word behind each for the
+// funnel shift of an unaligned read), addressed by integer offsets so that every access is a plain shared-memory load.
+namespace pmk {
+using namespace pm;
+constexpr int OFF0 = 0, OFF1 = OFF0 + WIN0 + 4, OFF2 = OFF1 + WIN1 + 4, WIN_BYTES = OFF2 + WIN2 + 4;
+static_assert(WIN0 % 4 == 0 && WIN1 % 4 == 0 && WIN2 % 4 == 0, "windows are whole words");
+// stream bytes [b, b + nbytes) -> win[off / 4 ...], zero outside [0, n): aligned 32-bit loads + one funnel shift per word where the
+// word and the aligned pair it is cut from lie inside the stream, bytes elsewhere (the two ends of the stream only)
+__device__ __forceinline__ void stage(uint32_t *__restrict__ win, int off, int nbytes, const uint8_t *__restrict__ s, long long b, long long n)
 {
-    __shared__ __align__(16) uint8_t w0[MATCH_W], w1[MATCH_W], w2[MATCH_W];
+    const int lo = b < 0 ? (int)min(-b, (long long)nbytes) : 0;                      // first window byte inside the stream
+    const int hi = (int)max(0ll, min((long long)nbytes, n - b));                      // one past the last
+    const uint8_t *base = s + b;                                                     // (may point before s: only dereferenced inside [lo, hi))
+    const int mis = (int)((uintptr_t)base & 3);
+    const uint32_t *ab = reinterpret_cast<const uint32_t *>(base - mis);
+    const int sh = 8 * mis;
+    for (int j = threadIdx.x; j < nbytes / 4; j += MATCH_T) {
+        uint32_t v;
+        if (4 * j >= lo + 4 && 4 * j + 8 <= hi) v = __funnelshift_r(ab[j], ab[j + 1], sh);       // (the pair ab[j], ab[j + 1] spans bytes 4j - mis .. 4j + 7 - mis)
+        else {
+            v = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const int q = 4 * j + k; if (q >= lo && q < hi) v |= (uint32_t)base[q] << (8 * k); }
+        }
+        win[(off >> 2) + j] = v;
+    }
+    if (threadIdx.x == 0) win[(off + nbytes) >> 2] = 0;
+}
+// the same for a window that lies wholly inside the stream with eight bytes to spare on either side (every CTA but the first and last few)
+__device__ __forceinline__ void stage_inside(uint32_t *__restrict__ win, int off, int nbytes, const uint8_t *__restrict__ base)
+{
+    const int mis = (int)((uintptr_t)base & 3);
+    const uint32_t *ab = reinterpret_cast<const uint32_t *>(base - mis);
+    const int sh = 8 * mis;
+    for (int j = threadIdx.x; j <= nbytes / 4; j += MATCH_T) win[(off >> 2) + j] = __funnelshift_r(ab[j], ab[j + 1], sh);     // (<=: the spare word too)
+}
+__device__ __forceinline__ uint32_t word_at(const uint32_t *__restrict__ win, int byte_off)
+{
+    const int k = byte_off >> 2;
+    return __funnelshift_r(win[k], win[k + 1], 8 * (byte_off & 3));
+}
+} // namespace pmk
+
+__global__ void __launch_bounds__(pm::MATCH_T) k_png_match(const uint8_t *__restrict__ s, uint32_t *__restrict__ best, size_t n, int bpp, int stride, int chunk)
+{
+    using namespace pm;
+    using namespace pmk;
+    __shared__ __align__(16) uint32_t win[WIN_BYTES / 4];
+    __shared__ uint32_t eq[NCAND][MATCH_WORDS];
+    __shared__ int s_src[NCAND];                                                   // byte offset of "stretch byte 0 minus the distance" per candidate, -1: unusable
     const long long i0 = (long long)blockIdx.x * MATCH_T;
-    const long long b0 = i0 - 24, b1 = i0 - stride - 8, b2 = i0 - 2ll * stride;
-    for (int k = threadIdx.x; k < MATCH_W; k += MATCH_T) {
-        const long long p0 = b0 + k, p1 = b1 + k, p2 = b2 + k;
-        w0[k] = (p0 >= 0 && p0 < (long long)n) ? s[p0] : (uint8_t)0;
-        w1[k] = (p1 >= 0 && p1 < (long long)n) ? s[p1] : (uint8_t)0;
-        w2[k] = (p2 >= 0 && p2 < (long long)n) ? s[p2] : (uint8_t)0;
+    const long long b0 = i0 - NEAR_BACK, b1 = i0 - stride - ROW_SLACK, b2 = i0 - 2ll * stride;
+    if (min(b1, b2) >= 8 && i0 + WIN0 + 16 <= (long long)n) {                       // block-uniform
+        stage_inside(win, OFF0, WIN0, s + b0); stage_inside(win, OFF1, WIN1, s + b1); stage_inside(win, OFF2, WIN2, s + b2);
+    } else {
+        stage(win, OFF0, WIN0, s, b0, (long long)n); stage(win, OFF1, WIN1, s, b1, (long long)n); stage(win, OFF2, WIN2, s, b2, (long long)n);
+    }
+    int cand[NCAND];
+    candidates(bpp, stride, cand);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int c = 0; c < NCAND; c++) {
+            const int d = cand[c];
+            s_src[c] = (d >= 1 && d <= 32768) ? (window_of(c) == 1 ? OFF1 : window_of(c) == 2 ? OFF2 : OFF0) + window_base(c, d, stride) : -1;
+        }
+    }
+    __syncthreads();
+    // comparison bit arrays: task (c, st) = candidate c, bytes 512 st .. 512 st + 511 of the stretch; a lane compares sixteen bytes
+    // (four eq_nibble), two lanes make one 32-bit word
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int STEPS = (MATCH_BITS + 511) / 512;
+    for (int task = warp; task < NCAND * STEPS; task += MATCH_T / 32) {
+        const int c = task / STEPS, st = task - c * STEPS;
+        const int so = s_src[c];
+        const int q = 512 * st + 16 * lane;
+        uint32_t v = 0;
+        if (q < MATCH_BITS && so >= 0) {
+            const int cw = (OFF0 + NEAR_BACK + q) >> 2, sw = (so + q) >> 2, sh = 8 * ((so + q) & 3);
+            uint32_t a = win[sw];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t b = win[sw + k + 1];
+                v |= eq_nibble(win[cw + k], __funnelshift_r(a, b, sh)) << (4 * k);
+                a = b;
+            }
+            v <<= 16 * (lane & 1);
+        }
+        v |= __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+        const int k = 16 * st + (lane >> 1);
+        if ((lane & 1) == 0 && k < MATCH_WORDS) eq[c][k] = v;
     }
     __syncthreads();
     const size_t i = (size_t)i0 + threadIdx.x;
     if (i >= n) return;
-    const size_t chunk_end = (i / chunk + 1) * (size_t)chunk;
-    const int maxlen = (int)min((size_t)258, min(n, chunk_end) - i);
-    int bl = 0, bd = 0;
-    if (maxlen >= 3) {
-        const uint8_t *cur = w0 + 24 + threadIdx.x;
-        const int cand[10] = {bpp, 1, 2 * bpp, stride, stride - bpp, stride + bpp, 3 * bpp, 2, 3, 2 * stride};
-#pragma unroll
-        for (int c = 0; c < 10; c++) {
-            const int d = cand[c];
-            if (d < 1 || d > 32768 || (size_t)d > i) continue;
-            // which window holds position i - d: the near one (d <= 24), the row above (c = 3, 4, 5) or two rows up (c = 9)
-            const uint8_t *src = (c >= 3 && c <= 5) ? w1 + ((long long)i - d - b1) : c == 9 ? w2 + ((long long)i - d - b2) : cur - d;
-            if ((c >= 3 && c <= 5 && (stride - d > 8 || d - stride > 8)) || (c != 9 && !(c >= 3 && c <= 5) && d > 24)) src = nullptr;   // (cannot happen: bpp <= 8)
-            if (!src) continue;
-            if (bl > 0 && cur[bl] != src[bl]) continue;               // cannot beat the current best
-            const int l = match_len_sm(cur, src, maxlen);
-            if (l > bl) { bl = l; bd = d; }                           // earlier candidate wins ties
-            if (bl == maxlen) break;
-        }
-    }
-    best[i] = bl >= 3 ? ((uint32_t)bl << 16) | (uint32_t)bd : 0u;
+    const size_t chunk_end = ((size_t)i0 / chunk + 1) * (size_t)chunk;            // MATCH_T divides the chunk size: one value per CTA
+    const int maxlen = (int)min((size_t)MATCH_MAX, min(n, chunk_end) - i);
+    best[i] = best_of(eq, cand, (int)threadIdx.x, (unsigned long long)i, maxlen);
 }
 
 // ---- K7, hash part: matches at ARBITRARY distances (north_star: "LZ77 match-find over a device hash table") ---------------------
@@ -305,13 +358,14 @@ __global__ void __launch_bounds__(HM_THREADS) k_png_hashmatch(const uint8_t *__r
         keys[j] = ok ? (uint16_t)hash3(s + p) : (uint16_t)0xFFFF;
         vals[j] = ok ? (uint16_t)local : (uint16_t)0xFFFF;
     }
-    Sort(temp).Sort(keys, vals);                       // stable LSD radix sort on the 16 hash bits: equal hashes stay in position order
+    Sort(temp).SortBlockedToStriped(keys, vals);       // stable LSD radix sort on the 16 hash bits: equal hashes stay in position order
     __syncthreads();
+    // striped from here on (item j of thread t = rank j * HM_THREADS + t): consecutive lanes touch consecutive shared-memory entries
 #pragma unroll
-    for (int j = 0; j < HM_ITEMS; j++) { sh_key[threadIdx.x * HM_ITEMS + j] = keys[j]; sh_pos[threadIdx.x * HM_ITEMS + j] = vals[j]; }
+    for (int j = 0; j < HM_ITEMS; j++) { sh_key[j * HM_THREADS + threadIdx.x] = keys[j]; sh_pos[j * HM_THREADS + threadIdx.x] = vals[j]; }
     __syncthreads();
     for (int j = 0; j < HM_ITEMS; j++) {
-        const int k = threadIdx.x * HM_ITEMS + j;
+        const int k = j * HM_THREADS + threadIdx.x;
         const uint32_t local = sh_pos[k];
         if (local == 0xFFFFu) continue;
         const size_t i = seg0 + local;
@@ -562,7 +616,8 @@ int launch_png_filter(const uint8_t *d_raw, uint8_t *d_filt, int h, int rb, int 
         return (int)cudaGetLastError();
     }
     cudaFuncSetAttribute(k_png_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   // per device, cheap
-    k_png_filter<<<h, 256, smem, (cudaStream_t)stream>>>(d_raw, d_filt, h, rb, bpp, strategy, d_tlog, row_pitch);
+    const int threads = 256;            // (1,024-thread CTAs for the bigram strategies were measured 20 % slower: four times the contention on the shared counters)
+    k_png_filter<<<h, threads, smem, (cudaStream_t)stream>>>(d_raw, d_filt, h, rb, bpp, strategy, d_tlog, row_pitch);
     LT_MARK("k_png_filter");
     return (int)cudaGetLastError();
 }

@@ -2,6 +2,7 @@
 // intra modes (16x16, and 4x4 "B_PRED" with its 10 sub-block modes and contextual mode probabilities), DCT token partitions, inverse
 // WHT / DCT, intra prediction with libwebp's frame-border conventions, simple and normal loop filters, then libwebp's output stage.
 #include "vp8_decode.h"
+#include "vp8l_decode.h"
 #include <algorithm>
 #include <cstring>
 #include "vp8_tables.h"
@@ -309,7 +310,8 @@ inline uint32_t rd24(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1]
 inline uint32_t rd32(const uint8_t *p) { return rd24(p) | ((uint32_t)p[3] << 24); }
 
 // the VP8 payload of a RIFF/WEBP file; flags what else is in there
-bool find_vp8(const uint8_t *d, size_t n, const uint8_t **vp8, size_t *vp8_len, WebpInfo &info, std::string &err)
+struct OtherChunks { const uint8_t *alph = nullptr, *vp8l = nullptr; size_t alph_len = 0, vp8l_len = 0; };
+bool find_vp8(const uint8_t *d, size_t n, const uint8_t **vp8, size_t *vp8_len, WebpInfo &info, std::string &err, OtherChunks *oc = nullptr)
 {
     if (n < 20 || memcmp(d, "RIFF", 4) || memcmp(d + 8, "WEBP", 4)) { err = "not a WebP file"; return false; }
     size_t i = 12; *vp8 = nullptr;
@@ -317,8 +319,8 @@ bool find_vp8(const uint8_t *d, size_t n, const uint8_t **vp8, size_t *vp8_len, 
         const uint8_t *tag = d + i; const size_t sz = rd32(d + i + 4);
         if (sz > n - i - 8) { err = "truncated WebP chunk"; return false; }
         if (!memcmp(tag, "VP8 ", 4) && !*vp8) { *vp8 = d + i + 8; *vp8_len = sz; }
-        else if (!memcmp(tag, "VP8L", 4)) info.lossless = true;
-        else if (!memcmp(tag, "ALPH", 4)) info.has_alpha = true;
+        else if (!memcmp(tag, "VP8L", 4)) { info.lossless = true; if (oc && !oc->vp8l) { oc->vp8l = d + i + 8; oc->vp8l_len = sz; } }
+        else if (!memcmp(tag, "ALPH", 4)) { info.has_alpha = true; if (oc && !oc->alph) { oc->alph = d + i + 8; oc->alph_len = sz; } }
         else if (!memcmp(tag, "ANIM", 4) || !memcmp(tag, "ANMF", 4)) info.animated = true;
         else if (!memcmp(tag, "VP8X", 4) && sz >= 10) { info.width = 1 + (int)rd24(d + i + 12); info.height = 1 + (int)rd24(d + i + 15); }
         i += 8 + sz + (sz & 1);
@@ -339,14 +341,32 @@ bool webp_probe(const uint8_t *data, size_t len, WebpInfo &info, std::string &er
     return find_vp8(data, len, &v, &vl, info, err);
 }
 
-int webp_decode_rgb(const uint8_t *data, size_t len, WebpInfo &info, std::vector<uint8_t> &rgb, std::string &err)
+int webp_decode_rgb(const uint8_t *data, size_t len, WebpInfo &info, std::vector<uint8_t> &rgb, std::string &err, std::vector<uint8_t> *alpha)
 {
     const uint8_t *f; size_t flen = 0;
+    OtherChunks oc;
     info = WebpInfo();
-    if (!find_vp8(data, len, &f, &flen, info, err)) return 2;
-    if (info.lossless && !f) { err = "lossless WebP (VP8L) input is outside the GPU path (route to caesium::compress_in_memory)"; return 1; }
+    if (alpha) alpha->clear();
+    if (!find_vp8(data, len, &f, &flen, info, err, &oc)) return 2;
     if (info.animated) { err = "animated WebP is outside the GPU path (route to caesium::compress_in_memory)"; return 1; }
-    if (info.has_alpha) { err = "WebP with an alpha plane is outside the GPU path (route to caesium::compress_in_memory)"; return 1; }
+    if (info.lossless && !f) {
+        // lossless file: the VP8L decoder gives ARGB; the alpha plane is reported only if some pixel is not opaque
+        std::vector<uint32_t> argb; int W = 0, H = 0; bool hint = false;
+        if (!vp8l_decode_file_chunk(oc.vp8l, oc.vp8l_len, W, H, hint, argb, err)) return 2;
+        info.width = W; info.height = H;
+        const size_t n = (size_t)W * H;
+        rgb.resize(3 * n);
+        bool any = false;
+        for (size_t i = 0; i < n; i++) { const uint32_t p = argb[i]; rgb[i] = (uint8_t)(p >> 16); rgb[n + i] = (uint8_t)(p >> 8); rgb[2 * n + i] = (uint8_t)p; any |= (p >> 24) != 0xFFu; }
+        info.has_alpha = any;
+        if (any) {
+            if (!alpha) { err = "WebP with an alpha plane: the caller did not ask for it"; return 1; }
+            alpha->resize(n);
+            for (size_t i = 0; i < n; i++) (*alpha)[i] = (uint8_t)(argb[i] >> 24);
+        }
+        return 0;
+    }
+    if (info.has_alpha && !alpha) { err = "WebP with an alpha plane: the caller did not ask for it"; return 1; }
     if (!f || flen < 10) { err = "no VP8 bitstream in the WebP file"; return 2; }
     // ---- frame tag + key-frame header (RFC 6386 9.1)
     const uint32_t tag = rd24(f);
@@ -617,6 +637,13 @@ int webp_decode_rgb(const uint8_t *data, size_t len, WebpInfo &info, std::vector
             G[x] = c8(y1 - ((u * 6419) >> 8) - ((v * 13320) >> 8) + 8708);
             B[x] = c8(y1 + ((u * 33050) >> 8) - 17685);
         }
+    }
+    if (info.has_alpha) {
+        // the ALPH chunk describes the canvas, which for a still image is the frame
+        if (!webp_alpha_decode(oc.alph, oc.alph_len, W, H, *alpha, err)) return 2;
+        bool any = false;
+        for (uint8_t a : *alpha) if (a != 0xFF) { any = true; break; }
+        if (!any) { alpha->clear(); info.has_alpha = false; }
     }
     return 0;
 }

@@ -2,6 +2,9 @@
 #include "vp8_host.h"
 #include <cmath>
 #include <cstring>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include "vp8_tables.h"
 
 namespace b200 {
@@ -28,31 +31,45 @@ namespace {
 // already written.
 class BoolWriter {
 public:
-    std::vector<uint8_t> bytes;
-    void put(int bit, int prob)
+    // `low_` is the RFC's 32-bit `bottom` kept in 64 bits so that a whole renormalisation (1..7 bit positions) is one shift: the byte that
+    // completes sits above bit 24 + k with its carry on top (k = positions shifted past the byte boundary), exactly where the bit-by-bit
+    // loop of the RFC would have found them.  Output goes through a raw pointer into a buffer sized up front (reserve()): one decision
+    // yields at most 8 bits.
+    explicit BoolWriter(size_t decisions = 4096) { buf_.resize(decisions + 16); p_ = buf_.data(); }
+    void reserve_more(size_t decisions) { const size_t used = size(); if (used + decisions + 16 > buf_.size()) { buf_.resize(used + decisions + 16 + buf_.size() / 2); p_ = buf_.data() + used; } }
+    size_t size() const { return (size_t)(p_ - buf_.data()); }
+    const uint8_t *data() const { return buf_.data(); }
+    inline void put(int bit, int prob)
     {
         const uint32_t split = 1 + (((range_ - 1) * (uint32_t)prob) >> 8);
-        if (bit) { low_ += split; range_ -= split; } else range_ = split;
-        int shift = __builtin_clz(range_) - 24;            // range < 128  <=>  shift > 0
-        range_ <<= shift;
-        while (shift-- > 0) {
-            if (low_ & 0x80000000u) carry();
-            low_ <<= 1;
-            if (--count_ == 0) { bytes.push_back((uint8_t)(low_ >> 24)); low_ &= 0xFFFFFFu; count_ = 8; }
+        const uint32_t m = 0u - (uint32_t)(bit & 1);                  // the decision is data: no branch on it
+        low_ += split & m;
+        range_ = split ^ ((split ^ (range_ - split)) & m);
+        const int shift = __builtin_clz(range_) - 24;                  // 0 when the range is still >= 128
+        range_ <<= shift; low_ <<= shift; count_ -= shift;
+        if (count_ <= 0) {
+            const int k = -count_;
+            const uint32_t v = (uint32_t)(low_ >> (24 + k));
+            if (v & 0x100u) carry();
+            *p_++ = (uint8_t)v;
+            low_ &= (1ull << (24 + k)) - 1ull;
+            count_ += 8;
         }
     }
-    void literal(int value, int nbits) { for (int i = nbits - 1; i >= 0; i--) put((value >> i) & 1, 128); }
+    void literal(int value, int nbits) { reserve_more((size_t)nbits); for (int i = nbits - 1; i >= 0; i--) put((value >> i) & 1, 128); }
     void finish()
     {
-        int c = count_; uint32_t v = low_;
-        if (v & (1u << (32 - c))) carry();
+        reserve_more(8);
+        int c = count_; uint32_t v = (uint32_t)low_;
+        if (low_ & (1ull << (32 - c))) carry();
         v <<= c & 7;
         for (c >>= 3; c > 0; c--) v <<= 8;
-        for (int i = 0; i < 4; i++, v <<= 8) bytes.push_back((uint8_t)(v >> 24));
+        for (int i = 0; i < 4; i++, v <<= 8) *p_++ = (uint8_t)(v >> 24);
     }
 private:
-    uint32_t range_ = 255, low_ = 0; int count_ = 24;
-    void carry() { size_t i = bytes.size(); while (i > 0 && bytes[i - 1] == 0xFF) bytes[--i] = 0; if (i > 0) bytes[i - 1]++; }
+    std::vector<uint8_t> buf_; uint8_t *p_;
+    uint32_t range_ = 255; uint64_t low_ = 0; int count_ = 24;
+    void carry() { uint8_t *q = p_; while (q > buf_.data() && q[-1] == 0xFF) *--q = 0; if (q > buf_.data()) q[-1]++; }
 };
 
 const uint8_t kBands[17] = {0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 0};
@@ -63,22 +80,47 @@ inline int slot(int type, int band, int ctx) { return ((type * 8 + band) * 3 + c
 // zeros and ones per slot (the statistics the probability update is chosen from).
 struct TokenWriter {
     BoolWriter &w; const uint8_t *probs;
+    void begin_mb() { w.reserve_more(7300); }
     void node(int s, bool bit) { w.put(bit, probs[s]); }
     void fixed(bool bit, int prob) { w.put(bit, prob); }
 };
 struct TokenCounter {
     uint32_t (*count)[2];
+    void begin_mb() {}
     void node(int s, bool bit) { count[s][bit ? 1 : 0]++; }
     void fixed(bool, int) {}
 };
+// The frame is walked ONCE: every decision is tallied and appended to a list (bit 0: the decision; bit 15: fixed probability in bits
+// 1..8, else the slot in bits 1..11); the writer then replays the list against the probabilities chosen from the tallies.
+struct TokenRecorder {
+    uint32_t (*count)[2]; std::vector<uint16_t> &list; uint16_t *q = nullptr; size_t room = 0;
+    // room for one macroblock's worth of decisions (25 blocks x at most 1 + 16 x 18) is made before the macroblock is walked
+    void begin_mb() { const size_t used = q ? (size_t)(q - list.data()) : 0; if (used + 7300 > list.size()) { list.resize(list.size() * 2 + 7300 * 64); } q = list.data() + used; }
+    size_t size() const { return q ? (size_t)(q - list.data()) : 0; }
+    void node(int s, bool bit) { count[s][bit ? 1 : 0]++; *q++ = (uint16_t)((s << 1) | (bit ? 1 : 0)); }
+    void fixed(bool bit, int prob) { *q++ = (uint16_t)(0x8000u | ((unsigned)prob << 1) | (bit ? 1u : 0u)); }
+};
+// index of the last non-zero level at or after `first`, -1 if none (most blocks of a frame are empty: one compare per half block)
+inline int last_nonzero(const int16_t *lv, int first)
+{
+#if defined(__SSE2__)
+    const __m128i z = _mm_setzero_si128();
+    const __m128i a = _mm_cmpeq_epi16(_mm_loadu_si128(reinterpret_cast<const __m128i *>(lv)), z), b = _mm_cmpeq_epi16(_mm_loadu_si128(reinterpret_cast<const __m128i *>(lv + 8)), z);
+    unsigned nz = ~(unsigned)_mm_movemask_epi8(_mm_packs_epi16(a, b)) & 0xFFFFu;        // bit i: lv[i] != 0
+    nz &= ~((1u << first) - 1u);
+    return nz ? 31 - __builtin_clz(nz) : -1;
+#else
+    for (int i = 15; i >= first; i--) if (lv[i]) return i;
+    return -1;
+#endif
+}
 
 // RFC 6386 13.2: one block's tokens; `lv` = 16 levels in zigzag order.  Returns the "has coded coefficients" context flag.
 template <class Sink> int put_block(Sink &w, const int16_t *lv, int type, int first, int ctx)
 {
     static const uint8_t kCat3[] = {173, 148, 140}, kCat4[] = {176, 155, 140, 135}, kCat5[] = {180, 157, 141, 134, 130},
                          kCat6[] = {254, 254, 243, 230, 196, 177, 153, 140, 133, 130, 129};
-    int last = -1;
-    for (int i = 15; i >= first; i--) if (lv[i]) { last = i; break; }
+    const int last = last_nonzero(lv, first);
     int p = slot(type, kBands[first], ctx);
     w.node(p, last >= 0);
     if (last < 0) return 0;
@@ -126,6 +168,7 @@ template <class Sink> void walk_tokens(Sink &sk, int mbw, int mbh, bool use_skip
             uint8_t *t = &top[(size_t)mx * 9];
             if (use_skip && modes[4 * mb + 2]) { memset(t, 0, 9); memset(left, 0, 9); continue; }
             const int16_t *lv = levels + mb * 400;
+            sk.begin_mb();
             t[8] = left[8] = (uint8_t)put_block(sk, lv, 1, 0, t[8] + left[8]);
             for (int b = 0; b < 16; b++) { const int x = b & 3, y = b >> 2; t[x] = left[y] = (uint8_t)put_block(sk, lv + 16 * (1 + b), 0, 1, t[x] + left[y]); }
             for (int c = 0; c < 2; c++)
@@ -152,10 +195,13 @@ bool vp8_write_file(int width, int height, int qindex, const int16_t *levels, co
     // ---- token probabilities (13.4): count the tree decisions of this frame, then replace a default wherever the frame's
     //      own estimate (libwebp's 255 - ones * 255 / total) saves more than the flag + 8-bit update costs
     std::vector<uint8_t> probs(VP8_COEF_PROBS, VP8_COEF_PROBS + kNumProbs), updated(kNumProbs, 0);
+    std::vector<uint16_t> tokens;
     {
         std::vector<uint32_t> cnt((size_t)kNumProbs * 2, 0);
-        TokenCounter tc{reinterpret_cast<uint32_t (*)[2]>(cnt.data())};
+        tokens.resize((size_t)nmb * 128 + 7300);
+        TokenRecorder tc{reinterpret_cast<uint32_t (*)[2]>(cnt.data()), tokens};
         walk_tokens(tc, mbw, mbh, use_skip, levels, modes);
+        tokens.resize(tc.size());
         for (int i = 0; i < kNumProbs; i++) {
             const uint64_t c0 = cnt[2 * i], c1 = cnt[2 * i + 1], total = c0 + c1;
             if (!total) continue;
@@ -167,7 +213,7 @@ bool vp8_write_file(int width, int height, int qindex, const int16_t *levels, co
         }
     }
     // ---- first partition: frame header (RFC 6386 9.2-9.11, 19.2) and the per-macroblock modes (19.3)
-    BoolWriter hd;
+    BoolWriter hd((size_t)kNumProbs * 9 + (size_t)nmb * 8 + 256);
     hd.literal(0, 1);                   // color_space
     hd.literal(0, 1);                   // clamping_type
     hd.literal(0, 1);                   // segmentation_enabled
@@ -193,20 +239,20 @@ bool vp8_write_file(int width, int height, int qindex, const int16_t *levels, co
         if (uvm != 0) { hd.put(uvm != 2, 114); if (uvm != 2) hd.put(uvm != 3, 183); }
     }
     hd.finish();
-    if (hd.bytes.size() >= (1u << 19)) return false;
+    if (hd.size() >= (1u << 19)) return false;
     // ---- token partition, coded with the table chosen above
-    BoolWriter tk;
-    { TokenWriter tw{tk, probs.data()}; walk_tokens(tw, mbw, mbh, use_skip, levels, modes); }
+    BoolWriter tk(tokens.size() + 64);
+    for (const uint16_t t : tokens) tk.put(t & 1, (t & 0x8000u) ? (t >> 1) & 0xFF : probs[t >> 1]);
     tk.finish();
     // ---- RIFF container (WebP simple lossy format)
-    const size_t vp8_size = 10 + hd.bytes.size() + tk.bytes.size(), riff_payload = 4 + 8 + vp8_size + (vp8_size & 1);
+    const size_t vp8_size = 10 + hd.size() + tk.size(), riff_payload = 4 + 8 + vp8_size + (vp8_size & 1);
     out.clear(); out.reserve(8 + riff_payload);
     out.insert(out.end(), {'R', 'I', 'F', 'F'}); put_le(out, (uint32_t)riff_payload, 4);
     out.insert(out.end(), {'W', 'E', 'B', 'P', 'V', 'P', '8', ' '}); put_le(out, (uint32_t)vp8_size, 4);
-    put_le(out, (1u << 4) | ((uint32_t)hd.bytes.size() << 5), 3);      // key frame (bit 0 clear), version 0, show_frame, first partition size
+    put_le(out, (1u << 4) | ((uint32_t)hd.size() << 5), 3);      // key frame (bit 0 clear), version 0, show_frame, first partition size
     out.insert(out.end(), {0x9d, 0x01, 0x2a}); put_le(out, (uint32_t)width, 2); put_le(out, (uint32_t)height, 2);
-    out.insert(out.end(), hd.bytes.begin(), hd.bytes.end());
-    out.insert(out.end(), tk.bytes.begin(), tk.bytes.end());
+    out.insert(out.end(), hd.data(), hd.data() + hd.size());
+    out.insert(out.end(), tk.data(), tk.data() + tk.size());
     if (vp8_size & 1) out.push_back(0);
     return true;
 }

@@ -211,10 +211,18 @@ int b200_png_level_strategies(int level, int *out);
  * zigzag order), modes [mbh*mbw][4] = {ymode, uvmode, skip, 0} with modes 0 DC, 1 TM, 2 V, 3 H; mbw = ceil(w/16). */
 b200_status b200_webp_encode_rgb(const uint8_t *rgb, int w, int h, int quality, uint8_t **out, size_t *out_len,
                                  int16_t *levels, uint8_t *modes);
-/* host: decode a lossy (VP8) still WebP to planar RGB [3][h][w] exactly as libwebp's WebPDecodeRGB does -- the front end of
- * compress_in_memory / convert_in_memory / compress_to_size_in_memory on WebP inputs (lossless, alpha, animation: code 3).
- * *rgb is library-allocated. */
+/* host: the ALPH chunk payload (header byte + VP8L image stream: WebP lossless bitstream, alpha in green, no transforms) of a
+ * width x height alpha plane given its LZ77 tokens in b200_png_lz77's format (bpp 1, stride = width) -- the alpha plane libwebp's
+ * WebPEncodeRGBA writes next to the lossy frame (compressor.rs:288-292 on an image with transparency). */
+b200_status b200_webp_alpha_chunk(const uint32_t *tokens, size_t ntokens, int width, int height, uint8_t **out, size_t *out_len);
+/* host: RIFF / VP8X container with alpha from a simple lossy file (RIFF + one 'VP8 ' chunk) and an ALPH payload */
+b200_status b200_webp_wrap_alpha(const uint8_t *simple_file, size_t file_len, const uint8_t *alph, size_t alph_len, int width, int height, uint8_t **out, size_t *out_len);
+/* host: decode a still WebP to planar RGB [3][h][w] exactly as libwebp's WebPDecodeRGB does -- the front end of compress_in_memory /
+ * convert_in_memory / compress_to_size_in_memory on WebP inputs: lossy (VP8 key frame) and lossless (VP8L) files; animation: code 3.
+ * An alpha plane is dropped here; b200_webp_decode_rgba returns it as well (*alpha = NULL when every pixel is opaque).
+ * *rgb / *alpha are library-allocated. */
 b200_status b200_webp_decode(const uint8_t *in, size_t in_len, int *width, int *height, uint8_t **rgb);
+b200_status b200_webp_decode_rgba(const uint8_t *in, size_t in_len, int *width, int *height, uint8_t **rgb, uint8_t **alpha);
 /* host only: boolean-code levels + modes (layout above) into a .webp file -- the entropy-coding half on its own */
 b200_status b200_webp_write_levels(int w, int h, int quality, const int16_t *levels, const uint8_t *modes, uint8_t **out, size_t *out_len);
 /* libwebp's quality -> quantiser index curve and the six dequantisation factors (y1 dc/ac, y2 dc/ac, uv dc/ac) it selects */

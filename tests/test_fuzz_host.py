@@ -222,3 +222,30 @@ def test_adobe_rgb_jpeg_is_handed_back_not_retagged(L, golden):
     with pytest.raises(L.B200Error) as e:
         L.compress_in_memory(b"\xff\xd8" + bytes(rgb_ids), p)
     assert e.value.code == 3
+
+
+@pytest.mark.parametrize("seed", [3, 4])
+def test_mutated_webp_files_never_crash(L, seed):
+    """The WebP front end (container, VP8 key-frame decoder, VP8L decoder, ALPH chunk): mutated lossless files, lossy files with an alpha
+    plane and plain lossy files come back as pixels or as a status."""
+    import io
+    from PIL import Image
+    rng = random.Random(seed)
+    rgba = synth(40, 56, 4, seed=seed, kind="photo")
+    pal = np.random.default_rng(seed).integers(0, 256, (4, 3), dtype=np.uint8)[np.random.default_rng(seed + 1).integers(0, 4, (40, 56))]
+    srcs = []
+    for img, kw in ((rgba, dict(lossless=True, method=4)), (pal, dict(lossless=True, method=6)), (rgba, dict(quality=70, alpha_quality=50)), (rgba[:, :, :3].copy(), dict(quality=60))):
+        b = io.BytesIO(); Image.fromarray(img).save(b, "WEBP", **kw); srcs.append(b.getvalue())
+    done = 0
+    for k in range(600):
+        src = srcs[k % len(srcs)]
+        data = _mutate(rng, src)
+        if k % 3 == 0 and len(data) > 40:        # keep the container intact, damage the payload only
+            data = src[:30] + data[30:]
+        try:
+            rgb, alpha = L.webp_decode_rgba(data)
+            assert rgb.ndim == 3 and (alpha is None or alpha.shape == rgb.shape[:2])
+        except L.B200Error as e:
+            assert e.code in (3, 4, 5), e
+        done += 1
+    assert done == 600

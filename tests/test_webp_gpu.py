@@ -86,10 +86,6 @@ def test_convert_png_to_webp_matches_oracle(L, O):
     assert L.convert_in_memory(pil_png(rgb), p, FMT_WEBP) == O.webp_encode(planar(rgb), 80)[0]
     opaque = np.concatenate([rgb, np.full((90, 120, 1), 255, np.uint8)], axis=2)        # fully opaque alpha carries nothing
     assert L.convert_in_memory(pil_png(opaque), p, FMT_WEBP) == O.webp_encode(planar(rgb), 80)[0]
-    rgba = np.concatenate([rgb, synth(90, 120, 1, seed=5)], axis=2)                   # real transparency: not this path's to drop
-    with pytest.raises(L.B200Error) as e:
-        L.convert_in_memory(pil_png(rgba), p, FMT_WEBP)
-    assert e.value.code == 3
     grey = synth(50, 70, 1, seed=6)
     assert L.convert_in_memory(pil_png(grey), p, FMT_WEBP) == O.webp_encode(planar(np.repeat(grey, 3, axis=2)), 80)[0]
     idx = rng.integers(0, 16, (40, 60)).astype(np.uint8)
@@ -242,3 +238,114 @@ def test_convert_from_webp_and_compress_to_size(L, O):
     p2 = L.default_params(); p2.webp_quality = 80
     sized = L.compress_to_size_in_memory(conv, p2, len(conv) // 2)
     assert len(sized) <= len(conv) // 2 and pil_decode(sized).shape == pil_decode(conv).shape
+
+
+def _chunks(f):
+    assert f[:4] == b"RIFF" and f[8:12] == b"WEBP" and int.from_bytes(f[4:8], "little") == len(f) - 8
+    out, pos = {}, 12
+    while pos < len(f):
+        n = int.from_bytes(f[pos + 4:pos + 8], "little")
+        out[f[pos:pos + 4]] = f[pos + 8:pos + 8 + n]
+        pos += 8 + n + (n & 1)
+    return out
+
+
+def _soft_alpha(h, w, seed):
+    yy, xx = np.mgrid[:h, :w]
+    a = np.clip(300 - np.hypot(yy - h / 2, xx - w / 2) * 600 / max(h, w), 0, 255).astype(np.uint8)
+    a[: h // 8] = 0; a[:, : w // 10] = 255
+    rng = np.random.default_rng(seed); a[h // 2:h // 2 + 4] = rng.integers(0, 256, (min(4, h - h // 2), w), dtype=np.uint8)
+    return a
+
+
+@pytest.mark.parametrize("h,w", [(90, 120), (1, 1), (257, 33), (600, 800)])
+def test_convert_transparent_png_to_webp_keeps_the_alpha_plane(L, O, h, w):
+    """PNG with real transparency -> VP8X file: the colour frame is the oracle's, the alpha plane is lossless (libwebp decodes it back
+    exactly) and its ALPH chunk is the host coder's output for the ORACLE's LZ77 tokens of the plane (so K7's tokens == the twin's)."""
+    import io
+    from PIL import Image
+    rgb, a = synth(h, w, 3, seed=h + w), _soft_alpha(h, w, 5)
+    p = L.default_params(); p.webp_quality = 80
+    out = L.convert_in_memory(pil_png(np.concatenate([rgb, a[:, :, None]], axis=2)), p, FMT_WEBP)
+    ch = _chunks(out)
+    assert set(ch) == {b"VP8X", b"ALPH", b"VP8 "} and ch[b"VP8X"][0] == 0x10
+    assert int.from_bytes(ch[b"VP8X"][4:7], "little") == w - 1 and int.from_bytes(ch[b"VP8X"][7:10], "little") == h - 1
+    assert ch[b"VP8 "] == _chunks(O.webp_encode(planar(rgb), 80)[0])[b"VP8 "]
+    tok, _ = O.png_lz77(a.reshape(-1), 1, w)
+    assert ch[b"ALPH"] == L.webp_alpha_chunk(tok, w, h)
+    got = np.asarray(Image.open(io.BytesIO(out)).convert("RGBA"))
+    assert np.array_equal(got[:, :, 3], a)
+    assert np.array_equal(got[:, :, :3], pil_decode(O.webp_encode(planar(rgb), 80)[0]))
+
+
+def test_convert_transparent_png_to_webp_with_resize_and_trns(L, O):
+    import io
+    from PIL import Image
+    h, w = 240, 320
+    rgb, a = synth(h, w, 3, seed=9), _soft_alpha(h, w, 6)
+    p = L.default_params(); p.webp_quality = 75; p.width = 100
+    out = L.convert_in_memory(pil_png(np.concatenate([rgb, a[:, :, None]], axis=2)), p, FMT_WEBP)
+    nw, nh = O.compute_dimensions(w, h, 100, 0)
+    got = np.asarray(Image.open(io.BytesIO(out)).convert("RGBA"))
+    assert got.shape == (nh, nw, 4)
+    assert np.array_equal(got[:, :, 3], O.resize_plane(a, nw, nh))            # the alpha plane takes the same Lanczos3 as the colour planes
+    want_rgb = np.stack([O.resize_plane(rgb[:, :, c].copy(), nw, nh) for c in range(3)])
+    assert _chunks(out)[b"VP8 "] == _chunks(O.webp_encode(want_rgb, 75)[0])[b"VP8 "]
+    # an alpha channel that becomes opaque ... stays a simple file; a palette with tRNS carries per-entry alpha
+    rng = np.random.default_rng(4)
+    idx = rng.integers(0, 16, (40, 60)).astype(np.uint8)
+    im = Image.fromarray(idx, mode="P"); im.putpalette([int(v) for v in rng.integers(0, 256, 48)])
+    trns = bytes(int(v) for v in rng.integers(0, 256, 10))
+    b = io.BytesIO(); im.save(b, "PNG", transparency=trns)
+    p = L.default_params(); p.webp_quality = 80
+    out = L.convert_in_memory(b.getvalue(), p, FMT_WEBP)
+    got = np.asarray(Image.open(io.BytesIO(out)).convert("RGBA"))
+    lut = np.full(256, 255, np.uint8); lut[:10] = np.frombuffer(trns, np.uint8)
+    assert np.array_equal(got[:, :, 3], lut[idx])
+    # colour key on a grey image
+    g = rng.integers(0, 4, (30, 50)).astype(np.uint8) * 85
+    b = io.BytesIO(); Image.fromarray(g, mode="L").save(b, "PNG", transparency=85)
+    got = np.asarray(Image.open(io.BytesIO(L.convert_in_memory(b.getvalue(), p, FMT_WEBP))).convert("RGBA"))
+    assert np.array_equal(got[:, :, 3], np.where(g == 85, 0, 255).astype(np.uint8))
+
+
+def test_compress_webp_inputs_with_alpha_and_lossless(L, O):
+    """WebP sources the VP8 decoder alone does not cover: a lossy file with an alpha plane is re-encoded with its alpha plane intact,
+    a lossless (VP8L) file is decoded and re-encoded lossy; converted to PNG the transparency stays (RGBA); to JPEG it is dropped."""
+    import io
+    from PIL import Image
+    from pngutil import pil_pixels
+    h, w = 150, 210
+    a = _soft_alpha(h, w, 3)
+    img = np.concatenate([synth(h, w, 3, seed=12, kind="photo"), a[:, :, None]], axis=2)
+    b = io.BytesIO(); Image.fromarray(img).save(b, "WEBP", quality=85, alpha_quality=100); lossy_alpha = b.getvalue()
+    b = io.BytesIO(); Image.fromarray(img).save(b, "WEBP", lossless=True, exact=True); lossless_alpha = b.getvalue()
+    b = io.BytesIO(); Image.fromarray(img[:, :, :3].copy()).save(b, "WEBP", lossless=True); lossless_rgb = b.getvalue()
+    p = L.default_params(); p.webp_quality = 70
+    for src in (lossy_alpha, lossless_alpha):
+        dec = np.asarray(Image.open(io.BytesIO(src)).convert("RGBA"))
+        out = L.compress_in_memory(src, p)
+        ch = _chunks(out)
+        assert set(ch) == {b"VP8X", b"ALPH", b"VP8 "}
+        assert ch[b"VP8 "] == _chunks(O.webp_encode(planar(dec[:, :, :3]), 70)[0])[b"VP8 "]
+        got = np.asarray(Image.open(io.BytesIO(out)).convert("RGBA"))
+        assert np.array_equal(got[:, :, 3], dec[:, :, 3])
+        # -> PNG keeps the transparency, -> JPEG drops it
+        pp = L.default_params(); pp.png_optimize = 1
+        png = np.asarray(pil_pixels(L.convert_in_memory(src, pp, FMT_PNG)).convert("RGBA"))
+        assert np.array_equal(png, dec)
+        pj = L.default_params(); pj.jpeg_quality, pj.jpeg_chroma_subsampling, pj.jpeg_progressive = 80, 420, 1
+        op = O.params(80, 420, True)
+        assert L.convert_in_memory(src, pj, FMT_JPEG) == O.write(O.forward(O.rgb_to_ycc(planar(dec[:, :, :3])), op), op)
+    dec = np.asarray(Image.open(io.BytesIO(lossless_rgb)).convert("RGB"))
+    assert L.compress_in_memory(lossless_rgb, p) == O.webp_encode(planar(dec), 70)[0]
+    # resized: colour and alpha planes take the same Lanczos3
+    p.width = 100
+    nw, nh = O.compute_dimensions(w, h, 100, 0)
+    dec = np.asarray(Image.open(io.BytesIO(lossy_alpha)).convert("RGBA"))
+    got = np.asarray(Image.open(io.BytesIO(L.compress_in_memory(lossy_alpha, p))).convert("RGBA"))
+    assert np.array_equal(got[:, :, 3], O.resize_plane(np.ascontiguousarray(dec[:, :, 3]), nw, nh))
+    pp = L.default_params(); pp.png_optimize = 1; pp.width = 100
+    png = np.asarray(pil_pixels(L.convert_in_memory(lossy_alpha, pp, FMT_PNG)).convert("RGBA"))
+    assert np.array_equal(png[:, :, 3], O.resize_plane(np.ascontiguousarray(dec[:, :, 3]), nw, nh))
+    assert np.array_equal(png[:, :, 0], O.resize_plane(np.ascontiguousarray(dec[:, :, 0]), nw, nh))

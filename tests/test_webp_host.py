@@ -70,19 +70,52 @@ def test_host_writer_reproduces_oracle_file_from_oracle_stage_output(L, O, h, w,
     assert L.webp_write_levels(w, h, q, levels, modes) == want
 
 
-def test_transparent_png_is_not_silently_flattened(L):
-    """A PNG with real transparency cannot become a simple-format WebP without losing it: the call hands it back (code 3)
-    before touching the device; the same goes for lossless WebP."""
+def test_lossless_webp_is_handed_back(L):
+    """webp.lossless selects libwebp's VP8L encoder for the colour planes, which is outside this path: code 3 before the device is touched."""
     from pngutil import pil_png
-    rgba = np.concatenate([synth(20, 30, 3, seed=1), synth(20, 30, 1, seed=2)], axis=2)
     p = L.default_params()
-    with pytest.raises(L.B200Error) as e:
-        L.convert_in_memory(pil_png(rgba), p, 3)
-    assert e.value.code == 3 and "alpha" in str(e.value)
     p.webp_lossless = 1
     with pytest.raises(L.B200Error) as e:
-        L.convert_in_memory(pil_png(rgba[:, :, :3].copy()), p, 3)
+        L.convert_in_memory(pil_png(synth(20, 30, 3, seed=1)), p, 3)
     assert e.value.code == 3
+
+
+def _alpha_planes():
+    rng = np.random.default_rng(1)
+    yy, xx = np.mgrid[:200, :317]
+    boxes = np.zeros((512, 640), np.uint8); boxes[100:400, 50:600] = 255; boxes[200:300, 200:300] = 128
+    return {
+        "flat": np.full((37, 53), 255, np.uint8), "one": np.full((1, 1), 7, np.uint8),
+        "row": (np.arange(300) % 256).astype(np.uint8).reshape(1, 300), "col": (np.arange(300) % 256).astype(np.uint8).reshape(300, 1),
+        "disc": np.clip(255 - np.hypot(yy - 100, xx - 150) * 2, 0, 255).astype(np.uint8), "noise": rng.integers(0, 256, (129, 257), dtype=np.uint8),
+        "boxes": boxes, "tile": np.tile(rng.integers(0, 256, (8, 8), dtype=np.uint8), (40, 50)), "narrow": (rng.integers(0, 3, (400, 5)) * 100).astype(np.uint8),
+        "ramp": (np.mgrid[:600, :1024][1] // 4).astype(np.uint8), "two": rng.integers(0, 2, (64, 64), dtype=np.uint8) * 255,
+    }
+
+
+@pytest.mark.parametrize("name", sorted(_alpha_planes()))
+def test_alpha_chunk_is_decoded_by_libwebp_to_the_plane(L, O, name):
+    """The ALPH chunk writer (VP8L image stream from LZ77 tokens) and the VP8X container, pinned by libwebp's decoder: the alpha
+    plane comes back exactly, the colour frame is untouched.  Tokens come from the oracle's K7 twin (the GPU test feeds K7's own)."""
+    import io
+    from PIL import Image
+    a = _alpha_planes()[name]
+    h, w = a.shape
+    tok, _ = O.png_lz77(a.reshape(-1), 1, w)
+    alph = L.webp_alpha_chunk(tok, w, h)
+    assert alph[0] == 1                                              # lossless compression, no filter, no pre-processing
+    rgb = synth(h, w, 3, seed=h + w)
+    b = io.BytesIO(); Image.fromarray(rgb).save(b, "WEBP", quality=80); simple = b.getvalue()
+    f = L.webp_wrap_alpha(simple, alph, w, h)
+    assert f[12:16] == b"VP8X" and f[20] == 0x10 and len(f) % 2 == 0 and int.from_bytes(f[4:8], "little") == len(f) - 8
+    im = Image.open(io.BytesIO(f)); im.load()
+    got = np.asarray(im.convert("RGBA"))
+    assert np.array_equal(got[:, :, 3], a)
+    assert np.array_equal(got[:, :, :3], np.asarray(Image.open(io.BytesIO(simple)).convert("RGB")))
+    if name in ("flat", "boxes", "ramp", "tile"):
+        assert len(alph) < a.size // 20                               # copies are merged across K7's 258-byte / chunk limits
+    with pytest.raises(L.B200Error):
+        L.webp_alpha_chunk(tok[:-1], w, h)                            # tokens that do not cover the plane
 
 
 def test_host_writer_extreme_levels(L):
@@ -137,17 +170,80 @@ def test_vp8_decoder_equals_libwebp_on_libwebp_encodings(L, h, w):
             assert np.array_equal(L.webp_decode(data), _pil_rgb(data)), (kind, q, m)
 
 
+def _pil_rgba(data):
+    from PIL import Image
+    return np.asarray(Image.open(io.BytesIO(data)).convert("RGBA"))
+
+
+def _lossless_sources():
+    rng = np.random.default_rng(11)
+    yy, xx = np.mgrid[:97, :131]
+    pal = lambda n: rng.integers(0, 256, (n, 3), dtype=np.uint8)[rng.integers(0, n, (97, 131))]
+    ramp = np.stack([xx * 2 % 256, yy * 2 % 256, (xx + yy) % 256], axis=2).astype(np.uint8)
+    return {
+        "photo": synth(97, 131, 3, seed=1, kind="photo"), "flat": synth(64, 64, 3, seed=2, kind="flat"), "noise": synth(33, 47, 3, seed=3, kind="noise"),
+        "pal2": pal(2), "pal4": pal(4), "pal16": pal(16), "pal200": pal(200), "ramp": ramp, "one": synth(1, 1, 3, seed=4), "wide": synth(3, 700, 3, seed=5, kind="photo"),
+        "rgba": np.concatenate([synth(97, 131, 3, seed=6, kind="photo"), (np.hypot(yy - 48, xx - 65) * 4).clip(0, 255).astype(np.uint8)[:, :, None]], axis=2),
+        "rgba_noise": synth(40, 50, 4, seed=7, kind="noise"), "big": synth(400, 600, 3, seed=8, kind="photo"),
+    }
+
+
+@pytest.mark.parametrize("name", sorted(_lossless_sources()))
+def test_vp8l_decoder_equals_libwebp_on_lossless_files(L, name):
+    """Lossless WebP input (VP8L): prefix codes, LZ77 with the neighbourhood distance codes, colour cache, meta prefix image and the
+    four transforms (predictor, cross-colour, subtract-green, colour indexing with pixel bundling), against libwebp on files libwebp
+    wrote at every effort level (the level decides which of those tools a file uses)."""
+    from PIL import Image
+    img = _lossless_sources()[name]
+    for method, quality in ((0, 0), (1, 25), (3, 50), (4, 75), (6, 100)):
+        b = io.BytesIO(); Image.fromarray(img).save(b, "WEBP", lossless=True, method=method, quality=quality, exact=True)
+        data = b.getvalue()
+        rgb, alpha = L.webp_decode_rgba(data)
+        want = _pil_rgba(data)
+        assert np.array_equal(rgb, want[:, :, :3]), (name, method)
+        if (want[:, :, 3] != 255).any(): assert np.array_equal(alpha, want[:, :, 3]), (name, method)
+        else: assert alpha is None
+        assert np.array_equal(L.webp_decode(data), want[:, :, :3])                 # the RGB-only entry point drops the alpha plane
+
+
+@pytest.mark.parametrize("kind", ["disc", "noise", "steps", "text"])
+def test_alpha_plane_of_lossy_files_equals_libwebp(L, kind):
+    """VP8X + ALPH input: raw / VP8L-coded planes, level-quantised (alpha_quality < 100) or exact, with whichever prediction filter
+    libwebp picked (none / horizontal / vertical / gradient)."""
+    from PIL import Image
+    rng = np.random.default_rng(5)
+    h, w = 120, 167
+    yy, xx = np.mgrid[:h, :w]
+    a = {"disc": (np.hypot(yy - 60, xx - 80) * 3).clip(0, 255), "noise": rng.integers(0, 256, (h, w)), "steps": (xx // 8 * 16) % 256,
+         "text": np.where(rng.random((h, w)) < 0.1, 0, 255)}[kind].astype(np.uint8)
+    img = np.concatenate([synth(h, w, 3, seed=2, kind="photo"), a[:, :, None]], axis=2)
+    seen_filters = set()
+    for aq, method in ((100, 4), (100, 6), (60, 4), (20, 2), (0, 0)):
+        b = io.BytesIO(); Image.fromarray(img).save(b, "WEBP", quality=75, alpha_quality=aq, method=method)
+        data = b.getvalue()
+        i = data.find(b"ALPH"); assert i > 0
+        seen_filters.add((data[i + 8] >> 2) & 3)
+        rgb, alpha = L.webp_decode_rgba(data)
+        want = _pil_rgba(data)
+        assert np.array_equal(alpha, want[:, :, 3]), (kind, aq)
+        assert np.array_equal(rgb, want[:, :, :3]), (kind, aq)
+    assert seen_filters                                                             # (which filters occur depends on the content)
+
+
 def test_vp8_decoder_refuses_what_it_does_not_decode(L):
     from PIL import Image
     img = synth(20, 30, 4, seed=1)
+    frames = [Image.fromarray(synth(20, 30, 3, seed=s)) for s in (1, 2)]
+    b = io.BytesIO(); frames[0].save(b, "WEBP", save_all=True, append_images=frames[1:], duration=100)
+    with pytest.raises(L.B200Error) as e:
+        L.webp_decode(b.getvalue())
+    assert e.value.code == 3 and "animated" in str(e.value)
     b = io.BytesIO(); Image.fromarray(img).save(b, "WEBP", lossless=True)
-    with pytest.raises(L.B200Error) as e:
-        L.webp_decode(b.getvalue())
-    assert e.value.code == 3
-    b = io.BytesIO(); Image.fromarray(img).save(b, "WEBP", quality=80)      # lossy with an alpha plane (VP8X + ALPH)
-    with pytest.raises(L.B200Error) as e:
-        L.webp_decode(b.getvalue())
-    assert e.value.code == 3 and "alpha" in str(e.value)
+    data = b.getvalue()
+    for cut in (len(data) // 2, len(data) - 3, 30):
+        with pytest.raises(L.B200Error) as e:
+            L.webp_decode(data[:cut])                     # a truncated lossless stream is corrupt, not zero-filled
+        assert e.value.code == 4
     ok = io.BytesIO(); Image.fromarray(img[:, :, :3]).save(ok, "WEBP", quality=80)
     data = ok.getvalue()
     for cut in (len(data) // 2, 40, 25):

@@ -27,4 +27,14 @@ p = L.default_params(); p.jpeg_quality = 80; p.width = 200
 print("jpeg resize", len(L.compress_in_memory(d, p)))
 p.webp_quality = 80
 print("jpeg -> webp", len(L.convert_in_memory(d, p, 3)))
+rgba = synth(120, 170, 4, seed=3); rgba[:, :40, 3] = 255; rgba[:30, :, 3] = 0
+p = L.default_params(); p.webp_quality = 75
+out = L.convert_in_memory(pil_png(rgba), p, 3)
+print("png with alpha -> webp (K7 over the alpha plane)", len(out), out[12:16])
+print("webp with alpha -> webp", len(L.compress_in_memory(out, p)))
+p = L.default_params(); p.png_optimize = 1; p.png_optimization_level = 2
+print("png lossless, wider rows", len(L.compress_in_memory(pil_png(synth(70, 1100, 3, seed=4, kind="photo")), p)))
+p = L.default_params(); p.jpeg_quality = 80
+res = L.compress_to_size_in_memory(d, p, len(d) // 3, True) if hasattr(L, "compress_to_size_in_memory") else None
+print("jpeg compress_to_size", None if res is None else len(res[0]) if isinstance(res, tuple) else len(res))
 L.lib().b200_shutdown()

@@ -25,7 +25,10 @@ def summarise(rep, title, dst):
     seen = set(); res = {}
     for r in rows:
         name = r[hdr.index("Kernel Name")].split("(")[0]
-        if name in seen: continue
+        if name in seen:                                   # the same kernel launched again (PNG: once per strategy): keep every launch
+            k = 2
+            while f"{name} #{k}" in seen: k += 1
+            name = f"{name} #{k}"
         seen.add(name)
         lines.append(f"== {name}")
         for w in WANT:
@@ -44,19 +47,34 @@ def to_bytes(v, unit):
     return f * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
 
 
-t = summarise(os.path.join(G, f"{tag}_transform.ncu-rep"), f"{tag} -- transform kernels, one launch each inside `python bench.py --steps 1 --warmup 3` (64 images of 3840x2160 per launch)", os.path.join(P, f"{tag}_ncu_transform_full.txt"))
-summarise(os.path.join(G, f"{tag}_entropy.ncu-rep"), f"{tag} -- entropy kernels of one megabatch (8 images of 3840x2160) through b200_compress_batch (tools/profile_group.py 8)", os.path.join(P, f"{tag}_ncu_entropy_full.txt"))
+def merged(*reps_titles_dst):
+    res = {}
+    for rep, title, dst in reps_titles_dst:
+        if os.path.exists(rep): res.update(summarise(rep, title, dst))
+    return res
+
+
+t = summarise(os.path.join(G, f"{tag}_transform.ncu-rep"), f"{tag} -- transform kernels, one launch each inside `python bench.py --only-value` (one megabatch: 8 images of 3840x2160 per launch)", os.path.join(P, f"{tag}_ncu_transform_full.txt"))
+e = summarise(os.path.join(G, f"{tag}_entropy.ncu-rep"), f"{tag} -- entropy kernels of one megabatch (8 images of 3840x2160) through b200_compress_batch (tools/profile_group.py 8)", os.path.join(P, f"{tag}_ncu_entropy_full.txt"))
+o = merged((os.path.join(G, f"{tag}_png.ncu-rep"), f"{tag} -- PNG leg, one 4096x4096 RGBA image at --png-opt-level 3 (tools/profile_legs.py png): un-filter wavefront, K6 per strategy, K7 match / parse", os.path.join(P, f"{tag}_ncu_png_full.txt")),
+           (os.path.join(G, f"{tag}i_png2.ncu-rep"), f"{tag} -- PNG leg, same image: K7 match after the bit-array rewrite, hash-chain candidates, DEFLATE coder kernels", os.path.join(P, f"{tag}_ncu_png2_full.txt")),
+           (os.path.join(G, f"{tag}_webp.ncu-rep"), f"{tag} -- resize leg of 6000x4000 JPEG -> 1920-wide WebP (tools/profile_legs.py webp): YCbCr -> RGB, K3 Lanczos3 passes", os.path.join(P, f"{tag}_ncu_resize_full.txt")),
+           (os.path.join(G, f"{tag}i_webp2.ncu-rep"), f"{tag} -- K8: RGB -> YUV and the VP8 wavefront kernel on a 1920x1280 frame", os.path.join(P, f"{tag}_ncu_vp8_full.txt")))
 k = next(v for n, v in t.items() if "k_fused_same" in n)
-traffic = to_bytes(k["dram__bytes_read.sum"], k["units"]["dram__bytes_read.sum"]) + to_bytes(k["dram__bytes_write.sum"], k["units"]["dram__bytes_write.sum"])
 fl = lambda key: float(k[key].replace(",", ""))
-json.dump({"source": f"profiles/{tag}_ncu_transform_full.txt (ncu --set full, one k_fused_same launch over 64 images)", "k_fused_same_bytes_per_launch": traffic, "images_per_launch": 64,
-           "k_fused_same_bytes_per_image": traffic / 64,
-           "k_fused_same_pipes": {"warp_instructions_per_launch": fl("smsp__inst_executed.sum"), "issue_active_pct": fl("smsp__issue_active.avg.pct_of_peak_sustained_active"),
-                                  "alu_pct": fl("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"), "fma_pct": fl("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
-                                  "fmaheavy_cycles_pct": fl("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"), "registers": fl("launch__registers_per_thread")}},
-          open(os.path.join(P, "traffic.json"), "w"), indent=1)
-for f in (f"{tag}_launches_bench.csv", f"{tag}_launches_group.csv", f"{tag}_bench.json", f"{tag}_bench_reference.json"):
-    shutil.copy(os.path.join(G, f), os.path.join(P, f))
+tr = {"source": f"profiles/{tag}_ncu_*_full.txt (ncu --set full --clock-control none, one launch per kernel; dram__bytes_read.sum + dram__bytes_write.sum)",
+      "images_per_launch": {"jpeg kernels": 8, "png kernels": 1, "resize / vp8 kernels": 1}}
+for name, v in list(t.items()) + list(e.items()) + list(o.items()):
+    short = name.replace("void ", "").split("<")[0]
+    if "dram__bytes_read.sum" in v:
+        tr[short + "_bytes_per_launch"] = to_bytes(v["dram__bytes_read.sum"], v["units"]["dram__bytes_read.sum"]) + to_bytes(v["dram__bytes_write.sum"], v["units"]["dram__bytes_write.sum"])
+tr["k_fused_same_pipes"] = {"warp_instructions_per_launch": fl("smsp__inst_executed.sum"), "issue_active_pct": fl("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                            "alu_pct": fl("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"), "fma_pct": fl("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                            "fmaheavy_cycles_pct": fl("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"), "registers": fl("launch__registers_per_thread")}
+json.dump(tr, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+for f in (f"{tag}_launches_bench.csv", f"{tag}_launches_group.csv", f"{tag}_launches_legs.csv", f"{tag}_bench.json", f"{tag}_bench_reference.json", f"{tag}_pytest_gpu.log",
+          f"{tag}_coalesce0.json", f"{tag}_coalesce1.json"):
+    if os.path.exists(os.path.join(G, f)): shutil.copy(os.path.join(G, f), os.path.join(P, f))
 # per-kernel table of one megabatch
 rows = list(csv.reader(open(os.path.join(G, f"{tag}_launches_group.csv"))))
 i0 = next(i for i, r in enumerate(rows) if "Kernel Name" in r); h = rows[i0]
