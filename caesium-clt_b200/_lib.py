@@ -68,7 +68,7 @@ _SYMBOLS = [
     "b200_jpeg_batch_time", "b200_jpeg_batch_destroy", "b200_jpeg_encode_coefficients_device",
     "b200_png_decode", "b200_png_decode_reduced", "b200_png_filter", "b200_png_lz77", "b200_png_deflate_tokens", "b200_png_level_strategies",
     "b200_webp_encode_rgb", "b200_webp_write_levels", "b200_webp_qindex",
-    "b200_jpeg_pipe_create", "b200_jpeg_pipe_run", "b200_jpeg_pipe_finish", "b200_jpeg_pipe_fetch", "b200_jpeg_pipe_kernel_times", "b200_jpeg_pipe_destroy", "b200_device_jobs", "b200_device_numa_node", "b200_png_device_times", "b200_webp_decode", "b200_webp_alpha_chunk", "b200_webp_wrap_alpha", "b200_webp_decode_rgba",
+    "b200_jpeg_pipe_create", "b200_jpeg_pipe_run", "b200_jpeg_pipe_finish", "b200_jpeg_pipe_fetch", "b200_jpeg_pipe_kernel_times", "b200_jpeg_pipe_destroy", "b200_device_jobs", "b200_device_numa_node", "b200_png_device_times", "b200_webp_decode", "b200_webp_alpha_chunk", "b200_webp_wrap_alpha", "b200_webp_decode_rgba", "b200_webp_alpha_filter",
 ]
 
 
@@ -296,11 +296,19 @@ def png_deflate_tokens(tokens, adler):
     return _take(outp, outl)
 
 
-def webp_alpha_chunk(tokens, width, height):
-    """Host: ALPH chunk payload (VP8L-coded alpha plane) from the plane's LZ77 tokens."""
+def webp_alpha_filter(alpha):
+    """Host: (filter id 0..3, residual plane) the alpha plane is coded with."""
+    a = np.ascontiguousarray(alpha, dtype=np.uint8)
+    out = np.empty_like(a)
+    k = lib().b200_webp_alpha_filter(a.ctypes.data_as(C.c_void_p), int(a.shape[1]), int(a.shape[0]), out.ctypes.data_as(C.c_void_p))
+    return k, out
+
+
+def webp_alpha_chunk(tokens, width, height, filter=0):
+    """Host: ALPH chunk payload (VP8L-coded alpha plane) from the (filtered) plane's LZ77 tokens."""
     tokens = np.ascontiguousarray(tokens, dtype=np.uint32)
     outp, outl = C.POINTER(C.c_uint8)(), C.c_size_t()
-    _check(lib().b200_webp_alpha_chunk(tokens.ctypes.data_as(C.c_void_p), C.c_size_t(tokens.size), int(width), int(height), C.byref(outp), C.byref(outl)))
+    _check(lib().b200_webp_alpha_chunk(tokens.ctypes.data_as(C.c_void_p), C.c_size_t(tokens.size), int(width), int(height), int(filter), C.byref(outp), C.byref(outl)))
     return _take(outp, outl)
 
 

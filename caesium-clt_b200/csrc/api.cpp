@@ -561,9 +561,10 @@ b200_status rgb_to_webp(const std::vector<uint8_t> &rgb, uint32_t w, uint32_t h,
         for (size_t i = 0; ok && i < n; i++) if (ap[i] != 0xFF) { opaque = false; break; }
         if (ok && !opaque) {
             if (!s->png) s->png = new PngDevice();
-            std::vector<uint32_t> tokens; std::vector<uint8_t> alph, wrapped;
-            ok = s->png->plane_tokens(ap, n, (int)nw, s->stream, tokens, err);
-            if (ok && !(vp8l_alpha_from_tokens(tokens.data(), tokens.size(), (int)nw, (int)nh, alph) && webp_wrap_alpha(out, alph, (int)nw, (int)nh, wrapped))) { ok = false; err = "alpha plane could not be coded"; }
+            std::vector<uint32_t> tokens; std::vector<uint8_t> alph, wrapped, residual;
+            const int filter = webp_alpha_choose_filter(ap, (int)nw, (int)nh, residual);
+            ok = s->png->plane_tokens(filter ? residual.data() : ap, n, (int)nw, s->stream, tokens, err);
+            if (ok && !(vp8l_alpha_from_tokens(tokens.data(), tokens.size(), (int)nw, (int)nh, alph, filter) && webp_wrap_alpha(out, alph, (int)nw, (int)nh, wrapped))) { ok = false; err = "alpha plane could not be coded"; }
             if (ok) out.swap(wrapped);
         }
     }
@@ -1376,11 +1377,19 @@ b200_status b200_png_deflate_tokens(const uint32_t *tokens, size_t ntokens, uint
     memcpy(*out, z.data(), z.size()); *out_len = z.size();
     return ok_status();
 }
-b200_status b200_webp_alpha_chunk(const uint32_t *tokens, size_t ntokens, int width, int height, uint8_t **out, size_t *out_len)
+int b200_webp_alpha_filter(const uint8_t *alpha, int width, int height, uint8_t *filtered)
 {
-    if (!tokens || !out || !out_len || width < 1 || height < 1 || width > 16383 || height > 16383) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid argument");
+    if (!alpha || !filtered || width < 1 || height < 1) return -1;
+    std::vector<uint8_t> f;
+    const int k = webp_alpha_choose_filter(alpha, width, height, f);
+    memcpy(filtered, k ? f.data() : alpha, (size_t)width * height);
+    return k;
+}
+b200_status b200_webp_alpha_chunk(const uint32_t *tokens, size_t ntokens, int width, int height, int filter, uint8_t **out, size_t *out_len)
+{
+    if (!tokens || !out || !out_len || width < 1 || height < 1 || width > 16383 || height > 16383 || filter < 0 || filter > 3) return make_status(B200_ERR_INVALID_ARGUMENT, "invalid argument");
     std::vector<uint8_t> a;
-    if (!vp8l_alpha_from_tokens(tokens, ntokens, width, height, a)) return make_status(B200_ERR_INVALID_ARGUMENT, "the tokens do not cover the plane");
+    if (!vp8l_alpha_from_tokens(tokens, ntokens, width, height, a, filter)) return make_status(B200_ERR_INVALID_ARGUMENT, "the tokens do not cover the plane");
     *out = (uint8_t *)malloc(a.size() + 1);
     if (!*out) return make_status(B200_ERR_OUT_OF_MEMORY, "malloc failed");
     memcpy(*out, a.data(), a.size()); *out_len = a.size();

@@ -113,7 +113,7 @@ void write_code(BitsLsb &bw, const PrefixCode &pc, dfl::HuffScratch &S)
 
 } // namespace
 
-bool vp8l_alpha_from_tokens(const uint32_t *tok, size_t ntok, int width, int height, std::vector<uint8_t> &alph)
+bool vp8l_alpha_from_tokens(const uint32_t *tok, size_t ntok, int width, int height, std::vector<uint8_t> &alph, int filter)
 {
     const size_t npix = (size_t)width * height;
     // ---- tokens -> operations: consecutive copies at the same distance continue each other (K7 cuts matches at 258 and at its
@@ -144,9 +144,9 @@ bool vp8l_alpha_from_tokens(const uint32_t *tok, size_t ntok, int width, int hei
     PrefixCode green, dist, zero;
     make_code(gf, green, S); make_code(df, dist, S);
     zero.len.assign(256, 0); zero.code.assign(256, 0); zero.used = 0;
-    // ---- the chunk: header byte (no pre-processing, no filter, lossless compression) + image stream
+    // ---- the chunk: header byte (no pre-processing, the caller's prediction filter, lossless compression) + image stream
     alph.clear(); alph.reserve(npix / 8 + 64);
-    alph.push_back(0x01);
+    alph.push_back((uint8_t)(0x01 | ((filter & 3) << 2)));
     BitsLsb bw(alph);
     bw.put(0, 1);                       // no transform
     bw.put(0, 1);                       // no colour cache
@@ -162,6 +162,44 @@ bool vp8l_alpha_from_tokens(const uint32_t *tok, size_t ntok, int width, int hei
     }
     bw.flush();
     return true;
+}
+
+// residual of one row under filter f (1 horizontal, 2 vertical, 3 gradient); prev = the row above (unfiltered), nullptr for row 0.
+// The first row is always predicted from the left, the first column of later rows from above (the conventions the decoder undoes).
+static void alpha_filter_row(int f, const uint8_t *row, const uint8_t *prev, int w, uint8_t *out)
+{
+    if (!prev) { out[0] = row[0]; for (int x = 1; x < w; x++) out[x] = (uint8_t)(row[x] - row[x - 1]); return; }
+    out[0] = (uint8_t)(row[0] - prev[0]);
+    if (f == 1) for (int x = 1; x < w; x++) out[x] = (uint8_t)(row[x] - row[x - 1]);
+    else if (f == 2) for (int x = 1; x < w; x++) out[x] = (uint8_t)(row[x] - prev[x]);
+    else for (int x = 1; x < w; x++) { const int g = (int)row[x - 1] + prev[x] - prev[x - 1]; out[x] = (uint8_t)(row[x] - (g < 0 ? 0 : g > 255 ? 255 : g)); }
+}
+
+int webp_alpha_choose_filter(const uint8_t *alpha, int width, int height, std::vector<uint8_t> &filtered)
+{
+    // order-0 cost of the residuals of every fourth row, per filter, in 1/1024 bit (integer log2 as the PNG leg's literal costs)
+    uint32_t hist[4][256];
+    memset(hist, 0, sizeof(hist));
+    std::vector<uint8_t> tmp((size_t)width);
+    size_t rows = 0;
+    for (int y = 0; y < height; y += 4, rows++) {
+        const uint8_t *row = alpha + (size_t)y * width, *prev = y ? row - width : nullptr;
+        for (int x = 0; x < width; x++) hist[0][row[x]]++;
+        for (int f = 1; f < 4; f++) { alpha_filter_row(f, row, prev, width, tmp.data()); for (int x = 0; x < width; x++) hist[f][tmp[x]]++; }
+    }
+    const unsigned long long total = (unsigned long long)rows * width;
+    auto log2q = [](unsigned long long v) { int e = 63; while (!((v >> e) & 1ull)) e--; const unsigned long long fr = e >= 10 ? (v >> (e - 10)) & 1023ull : (v << (10 - e)) & 1023ull; return (unsigned long long)e * 1024ull + fr; };
+    int best = 0; unsigned long long best_cost = ~0ull;
+    for (int f = 0; f < 4; f++) {
+        unsigned long long cost = 0;
+        for (int v = 0; v < 256; v++) if (hist[f][v]) cost += hist[f][v] * (log2q(total) - log2q(hist[f][v]));
+        if (cost < best_cost) { best_cost = cost; best = f; }            // ties: the simpler filter
+    }
+    if (best) {
+        filtered.resize((size_t)width * height);
+        for (int y = 0; y < height; y++) alpha_filter_row(best, alpha + (size_t)y * width, y ? alpha + (size_t)(y - 1) * width : nullptr, width, filtered.data() + (size_t)y * width);
+    }
+    return best;
 }
 
 bool webp_wrap_alpha(const std::vector<uint8_t> &f, const std::vector<uint8_t> &alph, int width, int height, std::vector<uint8_t> &out)

@@ -211,10 +211,13 @@ int b200_png_level_strategies(int level, int *out);
  * zigzag order), modes [mbh*mbw][4] = {ymode, uvmode, skip, 0} with modes 0 DC, 1 TM, 2 V, 3 H; mbw = ceil(w/16). */
 b200_status b200_webp_encode_rgb(const uint8_t *rgb, int w, int h, int quality, uint8_t **out, size_t *out_len,
                                  int16_t *levels, uint8_t *modes);
+/* host: the prediction filter the alpha plane is coded with (0 none, 1 horizontal, 2 vertical, 3 gradient: lowest order-0 cost of the
+ * residuals) and the residual plane (`filtered`, caller-allocated, width * height; a copy of the plane for filter 0) */
+int b200_webp_alpha_filter(const uint8_t *alpha, int width, int height, uint8_t *filtered);
 /* host: the ALPH chunk payload (header byte + VP8L image stream: WebP lossless bitstream, alpha in green, no transforms) of a
- * width x height alpha plane given its LZ77 tokens in b200_png_lz77's format (bpp 1, stride = width) -- the alpha plane libwebp's
- * WebPEncodeRGBA writes next to the lossy frame (compressor.rs:288-292 on an image with transparency). */
-b200_status b200_webp_alpha_chunk(const uint32_t *tokens, size_t ntokens, int width, int height, uint8_t **out, size_t *out_len);
+ * width x height (filtered) alpha plane given its LZ77 tokens in b200_png_lz77's format (bpp 1, stride = width) -- the alpha plane
+ * libwebp's WebPEncodeRGBA writes next to the lossy frame (compressor.rs:288-292 on an image with transparency). */
+b200_status b200_webp_alpha_chunk(const uint32_t *tokens, size_t ntokens, int width, int height, int filter, uint8_t **out, size_t *out_len);
 /* host: RIFF / VP8X container with alpha from a simple lossy file (RIFF + one 'VP8 ' chunk) and an ALPH payload */
 b200_status b200_webp_wrap_alpha(const uint8_t *simple_file, size_t file_len, const uint8_t *alph, size_t alph_len, int width, int height, uint8_t **out, size_t *out_len);
 /* host: decode a still WebP to planar RGB [3][h][w] exactly as libwebp's WebPDecodeRGB does -- the front end of compress_in_memory /

@@ -271,8 +271,9 @@ def test_convert_transparent_png_to_webp_keeps_the_alpha_plane(L, O, h, w):
     assert set(ch) == {b"VP8X", b"ALPH", b"VP8 "} and ch[b"VP8X"][0] == 0x10
     assert int.from_bytes(ch[b"VP8X"][4:7], "little") == w - 1 and int.from_bytes(ch[b"VP8X"][7:10], "little") == h - 1
     assert ch[b"VP8 "] == _chunks(O.webp_encode(planar(rgb), 80)[0])[b"VP8 "]
-    tok, _ = O.png_lz77(a.reshape(-1), 1, w)
-    assert ch[b"ALPH"] == L.webp_alpha_chunk(tok, w, h)
+    k, res = L.webp_alpha_filter(a)
+    tok, _ = O.png_lz77(res.reshape(-1), 1, w)
+    assert ch[b"ALPH"] == L.webp_alpha_chunk(tok, w, h, k)
     got = np.asarray(Image.open(io.BytesIO(out)).convert("RGBA"))
     assert np.array_equal(got[:, :, 3], a)
     assert np.array_equal(got[:, :, :3], pil_decode(O.webp_encode(planar(rgb), 80)[0]))

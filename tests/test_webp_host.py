@@ -93,6 +93,19 @@ def _alpha_planes():
     }
 
 
+def _alpha_residual(a, f):
+    """numpy restatement of the ALPH prediction filters (row 0 from the left, column 0 from above)"""
+    a = a.astype(np.int32); h, w = a.shape
+    if f == 0: return a.astype(np.uint8)
+    out = np.zeros_like(a)
+    out[0, 0] = a[0, 0]; out[0, 1:] = a[0, 1:] - a[0, :-1]
+    out[1:, 0] = a[1:, 0] - a[:-1, 0]
+    if f == 1: out[1:, 1:] = a[1:, 1:] - a[1:, :-1]
+    elif f == 2: out[1:, 1:] = a[1:, 1:] - a[:-1, 1:]
+    else: out[1:, 1:] = a[1:, 1:] - np.clip(a[1:, :-1] + a[:-1, 1:] - a[:-1, :-1], 0, 255)
+    return (out & 255).astype(np.uint8)
+
+
 @pytest.mark.parametrize("name", sorted(_alpha_planes()))
 def test_alpha_chunk_is_decoded_by_libwebp_to_the_plane(L, O, name):
     """The ALPH chunk writer (VP8L image stream from LZ77 tokens) and the VP8X container, pinned by libwebp's decoder: the alpha
@@ -101,9 +114,12 @@ def test_alpha_chunk_is_decoded_by_libwebp_to_the_plane(L, O, name):
     from PIL import Image
     a = _alpha_planes()[name]
     h, w = a.shape
-    tok, _ = O.png_lz77(a.reshape(-1), 1, w)
-    alph = L.webp_alpha_chunk(tok, w, h)
-    assert alph[0] == 1                                              # lossless compression, no filter, no pre-processing
+    k, res = L.webp_alpha_filter(a)                                  # the prediction filter with the cheapest residuals, and the residuals
+    tok, _ = O.png_lz77(res.reshape(-1), 1, w)
+    alph = L.webp_alpha_chunk(tok, w, h, k)
+    assert alph[0] == (1 | (k << 2))                                 # lossless compression, that filter, no pre-processing
+    if name in ("disc", "ramp"): assert k != 0                       # smooth planes are predicted
+    if name in ("flat", "noise"): assert k == 0
     rgb = synth(h, w, 3, seed=h + w)
     b = io.BytesIO(); Image.fromarray(rgb).save(b, "WEBP", quality=80); simple = b.getvalue()
     f = L.webp_wrap_alpha(simple, alph, w, h)
@@ -115,7 +131,13 @@ def test_alpha_chunk_is_decoded_by_libwebp_to_the_plane(L, O, name):
     if name in ("flat", "boxes", "ramp", "tile"):
         assert len(alph) < a.size // 20                               # copies are merged across K7's 258-byte / chunk limits
     with pytest.raises(L.B200Error):
-        L.webp_alpha_chunk(tok[:-1], w, h)                            # tokens that do not cover the plane
+        L.webp_alpha_chunk(tok[:-1], w, h, k)                         # tokens that do not cover the plane
+    for f in (0, 1, 2, 3):                                            # every filter, whatever the chooser says: libwebp undoes it
+        if f == k: continue
+        resf = _alpha_residual(a, f)
+        tokf, _ = O.png_lz77(resf.reshape(-1), 1, w)
+        g = np.asarray(Image.open(io.BytesIO(L.webp_wrap_alpha(simple, L.webp_alpha_chunk(tokf, w, h, f), w, h))).convert("RGBA"))
+        assert np.array_equal(g[:, :, 3], a), f
 
 
 def test_host_writer_extreme_levels(L):
