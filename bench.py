@@ -446,12 +446,14 @@ def main():
     ap.add_argument("--unique", type=int, default=64, help="unique synthetic sources per rank, cycled to fill a batch")
     ap.add_argument("--configs", default=None, help="comma list of BASELINE configs to run (1 = the headline; 2,3,4 = sub-records); default 1,2,3,4 on one GPU, 1 under torchrun")
     ap.add_argument("--png-unique", type=int, default=4); ap.add_argument("--png-batch", type=int, default=16)
+    ap.add_argument("--png-threads", type=int, default=0, help="callers in flight for the PNG leg (default: the usable cores, at least 8)")
     ap.add_argument("--webp-unique", type=int, default=8); ap.add_argument("--webp-batch", type=int, default=64)
     ap.add_argument("--cpu-seconds", type=float, default=6.0, help="minimum CPU work per cpu_baseline sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-threads", type=int, default=0, help="host threads per rank for the C-ABI leg (default: the rank's share of the usable cores, at least 8)")
     ap.add_argument("--only-e2e", action="store_true", help="diagnostics: skip the device-resident leg and the per-kernel table")
     ap.add_argument("--only-value", action="store_true", help="diagnostics: the device-resident leg only (prints a short JSON line)")
+    ap.add_argument("--only-configs", action="store_true", help="diagnostics: skip configs[1]; prints {\"configs\": {...}} for the sub-records named by --configs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -468,7 +470,7 @@ def main():
     load_pkg_shallow()
     S = import_module("caesium_clt_b200.sharding")
     shard = S.shard_indices([1] * (world * args.unique), world, rank, policy="rr")
-    datas = make_inputs(len(shard), 0, "jpeg4k", procs=threads, indices=shard)
+    datas = make_inputs(len(shard), 0, "jpeg4k", procs=threads, indices=shard if not args.only_configs else shard[:2])
     png_datas = make_inputs(args.png_unique, 0, "png4096") if 3 in which else None
     webp_datas = make_inputs(args.webp_unique, 0, "jpeg24mp") if 4 in which else None
     # batch workers mostly wait for their stream: on a box with few cores per GPU a rank still keeps eight megabatches in flight
@@ -491,7 +493,7 @@ def main():
 
     clocks = ClockSampler(local_rank)
     clocks.start()
-    r1 = jpeg_workload(args, L, torch, dist, world, rank, datas, p, False, threads, e2e_threads)
+    r1 = None if args.only_configs else jpeg_workload(args, L, torch, dist, world, rank, datas, p, False, threads, e2e_threads)
     clk = clocks.stop()
 
     sub = {}
@@ -527,7 +529,9 @@ def main():
             cpu = {"value": round(v, 2), "unit": "MP/s", "cores": cores, "kind": "port",
                    "sample": f"{k} of the same 4K inputs ({len(datas)} unique), {cores} threads, oracle jpeg_lossy (restated reference: progressive + optimised Huffman, no trellis/scan search), {cdt:.1f} s"}
 
-    if rank == 0:
+    if rank == 0 and args.only_configs:
+        _emit({"configs": sub})
+    elif rank == 0:
         B = args.batch
         _emit(({
             "metric": METRIC, "value": round(r1["value"], 1), "unit": "MP/s", "n_gpus": world,
@@ -554,7 +558,7 @@ def config_png_run(args, L, cores, datas):
     p = L.default_params(); p.png_optimize = 1; p.png_optimization_level = 3
     n = args.png_batch
     work = [datas[i % len(datas)] for i in range(n)]
-    nt = max(cores, 8)
+    nt = args.png_threads if args.png_threads > 0 else max(cores, 8)
     L.compress_batch(work[:min(n, nt)], p, nt, copy=False)
     bi = L.BatchInputs(work)
     steps = max(1, args.steps // 5)
