@@ -24,7 +24,7 @@ def summarise(rep, title, dst):
     lines = [title, f"report: gpurun_out/{os.path.basename(rep)} (scratch, not committed); ncu --set full --clock-control none --import-source on", ""]
     seen = set(); res = {}
     for r in rows:
-        name = r[hdr.index("Kernel Name")].split("(")[0]
+        name = r[hdr.index("Kernel Name")].replace("<unnamed>::", "").replace("unnamed>::", "").replace("(anonymous namespace)::", "").replace("b200::", "").split("(")[0]
         if name in seen:                                   # the same kernel launched again (PNG: once per strategy): keep every launch
             k = 2
             while f"{name} #{k}" in seen: k += 1
@@ -58,6 +58,7 @@ t = summarise(os.path.join(G, f"{tag}_transform.ncu-rep"), f"{tag} -- transform 
 e = summarise(os.path.join(G, f"{tag}_entropy.ncu-rep"), f"{tag} -- entropy kernels of one megabatch (8 images of 3840x2160) through b200_compress_batch (tools/profile_group.py 8)", os.path.join(P, f"{tag}_ncu_entropy_full.txt"))
 o = merged((os.path.join(G, f"{tag}_png.ncu-rep"), f"{tag} -- PNG leg, one 4096x4096 RGBA image at --png-opt-level 3 (tools/profile_legs.py png): un-filter wavefront, K6 per strategy, K7 match / parse", os.path.join(P, f"{tag}_ncu_png_full.txt")),
            (os.path.join(G, f"{tag}i_png2.ncu-rep"), f"{tag} -- PNG leg, same image: K7 match after the bit-array rewrite, hash-chain candidates, DEFLATE coder kernels", os.path.join(P, f"{tag}_ncu_png2_full.txt")),
+           (os.path.join(G, f"{tag}l_png3.ncu-rep"), f"{tag} -- PNG leg, same image, final K7 match (sixteen bytes per lane, one window array: 1.08 G warp instructions, 1.19 ms) and the register-array variant of the parse that was measured slower and dropped", os.path.join(P, f"{tag}_ncu_png3_full.txt")),
            (os.path.join(G, f"{tag}_webp.ncu-rep"), f"{tag} -- resize leg of 6000x4000 JPEG -> 1920-wide WebP (tools/profile_legs.py webp): YCbCr -> RGB, K3 Lanczos3 passes", os.path.join(P, f"{tag}_ncu_resize_full.txt")),
            (os.path.join(G, f"{tag}i_webp2.ncu-rep"), f"{tag} -- K8: RGB -> YUV and the VP8 wavefront kernel on a 1920x1280 frame", os.path.join(P, f"{tag}_ncu_vp8_full.txt")))
 k = next(v for n, v in t.items() if "k_fused_same" in n)
