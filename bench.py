@@ -593,17 +593,19 @@ def config_webp_run(args, L, cores, datas):
     with ThreadPoolExecutor(nt) as ex:
         list(ex.map(conv, work[:nt]))
         steps = max(1, args.steps // 3)
+        d2h0 = L.lib().b200_webp_d2h_bytes()
         t0 = time.perf_counter()
         out_bytes = 0
         for _ in range(steps):
             out_bytes = sum(ex.map(conv, work))
         dt = time.perf_counter() - t0
+        d2h = (L.lib().b200_webp_d2h_bytes() - d2h0) // steps
     rate = n * steps * mp / dt
     rec = {"workload": "configs[4]: 6000x4000 JPEG q90 4:2:0 -> -q 85 --width 1920 --format webp (1920x1280 lossy VP8)", "metric": "input megapixels/sec JPEG -> resized WebP", "unit": "MP/s",
            "value": None,
-           "e2e": {"value": round(rate, 2), "unit": "MP/s", "images_per_sec": round(rate / mp, 2), "h2d_bytes_per_step": sum(len(x) for x in work), "d2h_bytes_per_step": n * 9600 * 804,
+           "e2e": {"value": round(rate, 2), "unit": "MP/s", "images_per_sec": round(rate / mp, 2), "h2d_bytes_per_step": sum(len(x) for x in work), "d2h_bytes_per_step": int(d2h),
                    "out_bytes_per_step": out_bytes, "images_per_step": n, "steps": steps, "host_threads": nt,
-                   "note": "JPEG file in host memory -> WebP file in host memory via b200_convert_in_memory on a thread pool: device Huffman decode, IDCT, upsample, YCbCr->RGB, Lanczos3 (K3), VP8 wavefront (K8); D2H of levels + modes; host boolean coder"}}
+                   "note": "JPEG file in host memory -> WebP file in host memory via b200_convert_in_memory on a thread pool: device Huffman decode, IDCT, upsample, YCbCr->RGB, Lanczos3 (K3), VP8 wavefront (K8), residual token pass; D2H of the frame's decision records + tallies + modes; host boolean coder"}}
     return rec, datas
 
 

@@ -1456,6 +1456,7 @@ b200_status b200_webp_write_levels(int w, int h, int quality, const int16_t *lev
     if (!vp8_write_file(w, h, vp8_qindex(quality < 0 ? 0 : quality > 100 ? 100 : quality), levels, modes, v)) return make_status(B200_ERR_INVALID_ARGUMENT, "frame cannot be written as VP8");
     return give(v, out, out_len);
 }
+unsigned long long b200_webp_d2h_bytes(void) { return webp_d2h_bytes_total(); }
 int b200_webp_qindex(int quality, int factors[6])
 {
     const int q = vp8_qindex(quality < 0 ? 0 : quality > 100 ? 100 : quality);

@@ -2,10 +2,8 @@
 #include "vp8_host.h"
 #include <cmath>
 #include <cstring>
-#if defined(__SSE2__)
-#include <emmintrin.h>
-#endif
 #include "vp8_tables.h"
+#include "vp8_tokens_core.h"
 
 namespace b200 {
 
@@ -72,109 +70,36 @@ private:
     void carry() { uint8_t *q = p_; while (q > buf_.data() && q[-1] == 0xFF) *--q = 0; if (q > buf_.data()) q[-1]++; }
 };
 
-const uint8_t kBands[17] = {0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 0};
-constexpr int kNumProbs = 4 * 8 * 3 * 11;
-inline int slot(int type, int band, int ctx) { return ((type * 8 + band) * 3 + ctx) * 11; }
+using vt::kNumProbs;
 
-// Two consumers of the token walk: the writer codes each tree decision with the slot's probability; the counter only tallies
-// zeros and ones per slot (the statistics the probability update is chosen from).
-struct TokenWriter {
-    BoolWriter &w; const uint8_t *probs;
-    void begin_mb() { w.reserve_more(7300); }
-    void node(int s, bool bit) { w.put(bit, probs[s]); }
-    void fixed(bool bit, int prob) { w.put(bit, prob); }
-};
-struct TokenCounter {
-    uint32_t (*count)[2];
-    void begin_mb() {}
-    void node(int s, bool bit) { count[s][bit ? 1 : 0]++; }
-    void fixed(bool, int) {}
-};
-// The frame is walked ONCE: every decision is tallied and appended to a list (bit 0: the decision; bit 15: fixed probability in bits
-// 1..8, else the slot in bits 1..11); the writer then replays the list against the probabilities chosen from the tallies.
+// host side of the token pass (the device runs k_vp8_tokens instead): every decision is tallied and appended to a list; the writer
+// replays the list against the probabilities chosen from the tallies
 struct TokenRecorder {
-    uint32_t (*count)[2]; std::vector<uint16_t> &list; uint16_t *q = nullptr; size_t room = 0;
-    // room for one macroblock's worth of decisions (25 blocks x at most 1 + 16 x 18) is made before the macroblock is walked
-    void begin_mb() { const size_t used = q ? (size_t)(q - list.data()) : 0; if (used + 7300 > list.size()) { list.resize(list.size() * 2 + 7300 * 64); } q = list.data() + used; }
+    uint32_t (*count)[2]; std::vector<uint16_t> &list; uint16_t *q = nullptr;
+    // room for one macroblock's worth of decisions is made before the macroblock is walked
+    void begin_mb() { const size_t used = q ? (size_t)(q - list.data()) : 0; if (used + vt::kMaxDecisionsPerMb > list.size()) list.resize(list.size() * 2 + (size_t)vt::kMaxDecisionsPerMb * 64); q = list.data() + used; }
     size_t size() const { return q ? (size_t)(q - list.data()) : 0; }
-    void node(int s, bool bit) { count[s][bit ? 1 : 0]++; *q++ = (uint16_t)((s << 1) | (bit ? 1 : 0)); }
-    void fixed(bool bit, int prob) { *q++ = (uint16_t)(0x8000u | ((unsigned)prob << 1) | (bit ? 1u : 0u)); }
+    void node(int s, bool bit) { count[s][bit ? 1 : 0]++; *q++ = vt::rec_node(s, bit); }
+    void fixed(bool bit, int prob) { *q++ = vt::rec_fixed(bit, prob); }
 };
-// index of the last non-zero level at or after `first`, -1 if none (most blocks of a frame are empty: one compare per half block)
-inline int last_nonzero(const int16_t *lv, int first)
-{
-#if defined(__SSE2__)
-    const __m128i z = _mm_setzero_si128();
-    const __m128i a = _mm_cmpeq_epi16(_mm_loadu_si128(reinterpret_cast<const __m128i *>(lv)), z), b = _mm_cmpeq_epi16(_mm_loadu_si128(reinterpret_cast<const __m128i *>(lv + 8)), z);
-    unsigned nz = ~(unsigned)_mm_movemask_epi8(_mm_packs_epi16(a, b)) & 0xFFFFu;        // bit i: lv[i] != 0
-    nz &= ~((1u << first) - 1u);
-    return nz ? 31 - __builtin_clz(nz) : -1;
-#else
-    for (int i = 15; i >= first; i--) if (lv[i]) return i;
-    return -1;
-#endif
-}
 
-// RFC 6386 13.2: one block's tokens; `lv` = 16 levels in zigzag order.  Returns the "has coded coefficients" context flag.
-template <class Sink> int put_block(Sink &w, const int16_t *lv, int type, int first, int ctx)
+// the frame's decisions from its levels: masks of every macroblock first (a skipped one counts as empty), then one independent walk
+// per macroblock -- the same two steps the device takes (k_vp8_mbmask, k_vp8_tokens)
+void host_tokens(int mbw, int mbh, bool use_skip, const int16_t *levels, const uint8_t *modes, uint32_t *cnt /*[kNumProbs][2]*/, std::vector<uint16_t> &tokens)
 {
-    static const uint8_t kCat3[] = {173, 148, 140}, kCat4[] = {176, 155, 140, 135}, kCat5[] = {180, 157, 141, 134, 130},
-                         kCat6[] = {254, 254, 243, 230, 196, 177, 153, 140, 133, 130, 129};
-    const int last = last_nonzero(lv, first);
-    int p = slot(type, kBands[first], ctx);
-    w.node(p, last >= 0);
-    if (last < 0) return 0;
-    for (int n = first; n < 16;) {
-        const int c = lv[n++], v = c < 0 ? -c : c;
-        w.node(p + 1, v != 0);
-        if (!v) { p = slot(type, kBands[n], 0); continue; }           // a zero is never followed by an end-of-block check
-        w.node(p + 2, v > 1);
-        if (v == 1) p = slot(type, kBands[n], 1);
-        else {
-            w.node(p + 3, v > 4);
-            if (v <= 4) { w.node(p + 4, v != 2); if (v != 2) w.node(p + 5, v == 4); }
-            else {
-                w.node(p + 6, v > 10);
-                if (v <= 10) {
-                    w.node(p + 7, v > 6);
-                    if (v <= 6) w.fixed(v == 6, 159); else { w.fixed(v >= 9, 165); w.fixed(!(v & 1), 145); }
-                } else {
-                    const int cat = v < 19 ? 0 : v < 35 ? 1 : v < 67 ? 2 : 3;       // DCT_CAT3..6: bases 11, 19, 35, 67
-                    static const uint8_t *const tabs[4] = {kCat3, kCat4, kCat5, kCat6};
-                    static const int nbits[4] = {3, 4, 5, 11}, base[4] = {11, 19, 35, 67};
-                    w.node(p + 8, cat >> 1); w.node(p + 9 + (cat >> 1), cat & 1);
-                    for (int i = nbits[cat] - 1, t = 0; i >= 0; i--, t++) w.fixed(((v - base[cat]) >> i) & 1, tabs[cat][t]);
-                }
-            }
-            p = slot(type, kBands[n], 2);
-        }
-        w.fixed(c < 0, 128);
-        if (n == 16) break;
-        w.node(p, n <= last);
-        if (n > last) break;
-    }
-    return 1;
-}
-
-// every residual block of the frame in coding order (13): contexts are the "has coefficients" flags of the blocks above and
-// to the left; a skipped macroblock clears them
-template <class Sink> void walk_tokens(Sink &sk, int mbw, int mbh, bool use_skip, const int16_t *levels, const uint8_t *modes)
-{
-    std::vector<uint8_t> top((size_t)mbw * 9, 0);
-    for (int my = 0; my < mbh; my++) {
-        uint8_t left[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const size_t nmb = (size_t)mbw * mbh;
+    std::vector<uint32_t> mask(nmb);
+    for (size_t mb = 0; mb < nmb; mb++) mask[mb] = (use_skip && modes[4 * mb + 2]) ? 0u : vt::mb_mask(levels + mb * 400);
+    tokens.resize(nmb * 128 + vt::kMaxDecisionsPerMb);
+    TokenRecorder tc{reinterpret_cast<uint32_t (*)[2]>(cnt), tokens};
+    for (int my = 0; my < mbh; my++)
         for (int mx = 0; mx < mbw; mx++) {
             const size_t mb = (size_t)my * mbw + mx;
-            uint8_t *t = &top[(size_t)mx * 9];
-            if (use_skip && modes[4 * mb + 2]) { memset(t, 0, 9); memset(left, 0, 9); continue; }
-            const int16_t *lv = levels + mb * 400;
-            sk.begin_mb();
-            t[8] = left[8] = (uint8_t)put_block(sk, lv, 1, 0, t[8] + left[8]);
-            for (int b = 0; b < 16; b++) { const int x = b & 3, y = b >> 2; t[x] = left[y] = (uint8_t)put_block(sk, lv + 16 * (1 + b), 0, 1, t[x] + left[y]); }
-            for (int c = 0; c < 2; c++)
-                for (int b = 0; b < 4; b++) { const int x = 4 + 2 * c + (b & 1), y = 4 + 2 * c + (b >> 1); t[x] = left[y] = (uint8_t)put_block(sk, lv + 16 * (17 + 4 * c + b), 2, 0, t[x] + left[y]); }
+            if (use_skip && modes[4 * mb + 2]) continue;
+            tc.begin_mb();
+            vt::walk_mb(tc, levels + mb * 400, my ? mask[mb - mbw] : 0u, mx ? mask[mb - 1] : 0u);
         }
-    }
+    tokens.resize(tc.size());
 }
 
 // price of one decision coded with probability-of-zero p/256, in 1/256 bit
@@ -184,7 +109,24 @@ void put_le(std::vector<uint8_t> &o, uint32_t v, int nbytes) { for (int i = 0; i
 
 } // namespace
 
+bool vp8_frame_uses_skip(int width, int height, const uint8_t *modes)
+{
+    const int nmb = ((width + 15) >> 4) * ((height + 15) >> 4);
+    for (int i = 0; i < nmb; i++) if (modes[4 * i + 2]) return true;
+    return false;
+}
+
 bool vp8_write_file(int width, int height, int qindex, const int16_t *levels, const uint8_t *modes, std::vector<uint8_t> &out)
+{
+    if (width < 1 || height < 1 || width > 16383 || height > 16383) return false;
+    const int mbw = (width + 15) >> 4, mbh = (height + 15) >> 4;
+    std::vector<uint32_t> cnt((size_t)kNumProbs * 2, 0);
+    std::vector<uint16_t> tokens;
+    host_tokens(mbw, mbh, vp8_frame_uses_skip(width, height, modes), levels, modes, cnt.data(), tokens);
+    return vp8_write_file_tokens(width, height, qindex, modes, cnt.data(), tokens.data(), tokens.size(), out);
+}
+
+bool vp8_write_file_tokens(int width, int height, int qindex, const uint8_t *modes, const uint32_t *cnt, const uint16_t *tokens, size_t ntokens, std::vector<uint8_t> &out)
 {
     const int mbw = (width + 15) >> 4, mbh = (height + 15) >> 4, nmb = mbw * mbh;
     if (width < 1 || height < 1 || width > 16383 || height > 16383) return false;
@@ -192,25 +134,17 @@ bool vp8_write_file(int width, int height, int qindex, const int16_t *levels, co
     for (int i = 0; i < nmb; i++) nskip += modes[4 * i + 2];
     const bool use_skip = nskip > 0;
     int skip_p = (int)(((long long)(nmb - nskip) * 255) / nmb); if (skip_p < 1) skip_p = 1; if (skip_p > 255) skip_p = 255;
-    // ---- token probabilities (13.4): count the tree decisions of this frame, then replace a default wherever the frame's
+    // ---- token probabilities (13.4): from the tallies of this frame's tree decisions, replace a default wherever the frame's
     //      own estimate (libwebp's 255 - ones * 255 / total) saves more than the flag + 8-bit update costs
     std::vector<uint8_t> probs(VP8_COEF_PROBS, VP8_COEF_PROBS + kNumProbs), updated(kNumProbs, 0);
-    std::vector<uint16_t> tokens;
-    {
-        std::vector<uint32_t> cnt((size_t)kNumProbs * 2, 0);
-        tokens.resize((size_t)nmb * 128 + 7300);
-        TokenRecorder tc{reinterpret_cast<uint32_t (*)[2]>(cnt.data()), tokens};
-        walk_tokens(tc, mbw, mbh, use_skip, levels, modes);
-        tokens.resize(tc.size());
-        for (int i = 0; i < kNumProbs; i++) {
-            const uint64_t c0 = cnt[2 * i], c1 = cnt[2 * i + 1], total = c0 + c1;
-            if (!total) continue;
-            const int oldp = probs[i], u = VP8_COEF_UPDATE_PROBS[i];
-            int newp = 255 - (int)(c1 * 255 / total); if (newp < 1) newp = 1;
-            const uint64_t keep = c0 * bit_cost(oldp) + c1 * bit_cost(256 - oldp) + bit_cost(u);
-            const uint64_t change = c0 * bit_cost(newp) + c1 * bit_cost(256 - newp) + bit_cost(256 - u) + 8 * 256;
-            if (newp != oldp && change < keep) { probs[i] = (uint8_t)newp; updated[i] = 1; }
-        }
+    for (int i = 0; i < kNumProbs; i++) {
+        const uint64_t c0 = cnt[2 * i], c1 = cnt[2 * i + 1], total = c0 + c1;
+        if (!total) continue;
+        const int oldp = probs[i], u = VP8_COEF_UPDATE_PROBS[i];
+        int newp = 255 - (int)(c1 * 255 / total); if (newp < 1) newp = 1;
+        const uint64_t keep = c0 * bit_cost(oldp) + c1 * bit_cost(256 - oldp) + bit_cost(u);
+        const uint64_t change = c0 * bit_cost(newp) + c1 * bit_cost(256 - newp) + bit_cost(256 - u) + 8 * 256;
+        if (newp != oldp && change < keep) { probs[i] = (uint8_t)newp; updated[i] = 1; }
     }
     // ---- first partition: frame header (RFC 6386 9.2-9.11, 19.2) and the per-macroblock modes (19.3)
     BoolWriter hd((size_t)kNumProbs * 9 + (size_t)nmb * 8 + 256);
@@ -241,8 +175,8 @@ bool vp8_write_file(int width, int height, int qindex, const int16_t *levels, co
     hd.finish();
     if (hd.size() >= (1u << 19)) return false;
     // ---- token partition, coded with the table chosen above
-    BoolWriter tk(tokens.size() + 64);
-    for (const uint16_t t : tokens) tk.put(t & 1, (t & 0x8000u) ? (t >> 1) & 0xFF : probs[t >> 1]);
+    BoolWriter tk(ntokens + 64);
+    for (size_t k = 0; k < ntokens; k++) { const uint16_t t = tokens[k]; tk.put(t & 1, (t & 0x8000u) ? (t >> 1) & 0xFF : probs[t >> 1]); }
     tk.finish();
     // ---- RIFF container (WebP simple lossy format)
     const size_t vp8_size = 10 + hd.size() + tk.size(), riff_payload = 4 + 8 + vp8_size + (vp8_size & 1);

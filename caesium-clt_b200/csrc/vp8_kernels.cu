@@ -5,8 +5,10 @@
 // 4x4 block k, lanes 16..19 / 20..23 own the U / V blocks, lane 24 does the 16-point Walsh-Hadamard of the luma DCs.
 // Integer arithmetic only; every inverse step is the normative RFC 6386 one, so a decoder reproduces RY/RU/RV exactly.
 #include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
 #include <cstdint>
 #include "vp8_kernels.h"
+#include "vp8_tokens_core.h"
 
 namespace b200 {
 
@@ -236,6 +238,87 @@ __global__ void __launch_bounds__(32) k_vp8_encode(const Vp8Frame f)
 }
 
 } // namespace
+
+// ---- token pass on the device (vp8_tokens_core.h): one thread per macroblock -------------------------------------------------------
+// A block's context is whether the blocks above / to its left have coded coefficients -- a property of the levels alone -- so with a
+// 25-bit mask per macroblock every macroblock's decision list is independent: masks, then a counting walk (list length per
+// macroblock + the frame's tallies per probability slot), an exclusive scan, and the same walk again writing 16-bit decision records
+// at the macroblock's offset.  The host is left with choosing the probabilities and the (sequential) boolean coder.
+namespace {
+struct TokenCountSink {
+    uint32_t n; uint32_t *hist;                          // hist: shared memory, [slot][bit]
+    __device__ __forceinline__ void node(int s, bool bit) { n++; atomicAdd(&hist[2 * s + (bit ? 1 : 0)], 1u); }
+    __device__ __forceinline__ void fixed(bool, int) { n++; }
+};
+struct TokenWriteSink {
+    uint16_t *q;
+    __device__ __forceinline__ void node(int s, bool bit) { *q++ = vt::rec_node(s, bit); }
+    __device__ __forceinline__ void fixed(bool bit, int prob) { *q++ = vt::rec_fixed(bit, prob); }
+};
+
+__global__ void k_vp8_mbmask(const int16_t *__restrict__ levels, const uint8_t *__restrict__ modes, int nmb, uint32_t *__restrict__ mask)
+{
+    const int mb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mb < nmb) mask[mb] = modes[4 * mb + 2] ? 0u : vt::mb_mask(levels + (size_t)mb * VP8_MB_COEFS);      // a skipped macroblock has no coefficients
+}
+
+__global__ void __launch_bounds__(64) k_vp8_token_count(const int16_t *__restrict__ levels, const uint8_t *__restrict__ modes, const uint32_t *__restrict__ mask, int mbw, int nmb,
+                                                        uint32_t *__restrict__ counts /*[nmb + 1], the last one 0*/, uint32_t *__restrict__ hist /*[kNumProbs][2]*/)
+{
+    __shared__ uint32_t h[vt::kNumProbs * 2];
+    for (int i = threadIdx.x; i < vt::kNumProbs * 2; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    const int mb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mb < nmb) {
+        uint32_t n = 0;
+        if (!modes[4 * mb + 2]) {
+            const int my = mb / mbw, mx = mb - my * mbw;
+            TokenCountSink sk{0u, h};
+            vt::walk_mb(sk, levels + (size_t)mb * VP8_MB_COEFS, my ? mask[mb - mbw] : 0u, mx ? mask[mb - 1] : 0u);
+            n = sk.n;
+        }
+        counts[mb] = n;
+        if (mb == nmb - 1) counts[nmb] = 0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < vt::kNumProbs * 2; i += blockDim.x) if (h[i]) atomicAdd(&hist[i], h[i]);
+}
+
+__global__ void __launch_bounds__(64) k_vp8_token_write(const int16_t *__restrict__ levels, const uint8_t *__restrict__ modes, const uint32_t *__restrict__ mask, int mbw, int nmb,
+                                                        const uint32_t *__restrict__ offsets /*[nmb + 1]*/, uint16_t *__restrict__ tokens, uint32_t capacity)
+{
+    const int mb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mb >= nmb || modes[4 * mb + 2] || offsets[mb + 1] > capacity) return;
+    const int my = mb / mbw, mx = mb - my * mbw;
+    TokenWriteSink sk{tokens + offsets[mb]};
+    vt::walk_mb(sk, levels + (size_t)mb * VP8_MB_COEFS, my ? mask[mb - mbw] : 0u, mx ? mask[mb - 1] : 0u);
+}
+} // namespace
+
+size_t vp8_tokens_temp_bytes(int nmb)
+{
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum((void *)nullptr, tb, (const uint32_t *)nullptr, (uint32_t *)nullptr, nmb + 1, (cudaStream_t)0);
+    return tb;
+}
+int launch_vp8_token_count(const Vp8Frame &f, uint32_t *d_mask, uint32_t *d_counts, uint32_t *d_offsets, uint32_t *d_hist, void *d_temp, size_t temp_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nmb = f.mbw * f.mbh;
+    cudaError_t e = cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * vt::kNumProbs * 2, st);
+    if (e != cudaSuccess) return (int)e;
+    k_vp8_mbmask<<<(nmb + 127) / 128, 128, 0, st>>>(f.levels, f.modes, nmb, d_mask);
+    k_vp8_token_count<<<(nmb + 63) / 64, 64, 0, st>>>(f.levels, f.modes, d_mask, f.mbw, nmb, d_counts, d_hist);
+    e = cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_counts, d_offsets, nmb + 1, st);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaGetLastError();
+}
+int launch_vp8_token_write(const Vp8Frame &f, const uint32_t *d_mask, const uint32_t *d_offsets, uint16_t *d_tokens, uint32_t capacity, void *stream)
+{
+    const int nmb = f.mbw * f.mbh;
+    k_vp8_token_write<<<(nmb + 63) / 64, 64, 0, (cudaStream_t)stream>>>(f.levels, f.modes, d_mask, f.mbw, nmb, d_offsets, d_tokens, capacity);
+    return (int)cudaGetLastError();
+}
 
 int launch_vp8_rgb_to_yuv(const uint8_t *r, const uint8_t *g, const uint8_t *b, int w, int h, uint8_t *Y, uint8_t *U, uint8_t *V, void *stream)
 {

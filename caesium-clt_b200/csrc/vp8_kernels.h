@@ -24,5 +24,13 @@ struct Vp8Frame {
 int launch_vp8_rgb_to_yuv(const uint8_t *r, const uint8_t *g, const uint8_t *b, int w, int h, uint8_t *Y, uint8_t *U, uint8_t *V, void *stream);
 // wavefront over macroblocks: one warp per macroblock row, rows released in ticket order
 int launch_vp8_encode(const Vp8Frame &f, void *stream);
+// The residual token pass (RFC 6386 section 13) on the device, one thread per macroblock (vp8_tokens_core.h): masks of the blocks with
+// coded coefficients, a counting walk (decisions per macroblock -> d_counts[nmb + 1]; tallies per probability slot -> d_hist[kNumProbs * 2]),
+// exclusive scan into d_offsets[nmb + 1] (the last entry = decisions in the frame) ...
+size_t vp8_tokens_temp_bytes(int nmb);
+int launch_vp8_token_count(const Vp8Frame &f, uint32_t *d_mask, uint32_t *d_counts, uint32_t *d_offsets, uint32_t *d_hist, void *d_temp, size_t temp_bytes, void *stream);
+// ... and the same walk writing the 16-bit decision records at every macroblock's offset (macroblocks whose records would pass `capacity` are left out:
+// the caller sizes the buffer from d_offsets[nmb] first)
+int launch_vp8_token_write(const Vp8Frame &f, const uint32_t *d_mask, const uint32_t *d_offsets, uint16_t *d_tokens, uint32_t capacity, void *stream);
 
 } // namespace b200

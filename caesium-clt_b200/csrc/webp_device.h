@@ -7,6 +7,9 @@
 
 namespace b200 {
 
+// bytes this leg has copied device -> host so far, all devices (diagnostics: bench.py reports the per-step figure from it)
+unsigned long long webp_d2h_bytes_total();
+
 struct WebpDevice {
     uint8_t *d_planes = nullptr; size_t cap_planes = 0;        // Y,U,V source + RY,RU,RV reconstruction, macroblock-padded
     uint8_t *d_rgb = nullptr; size_t cap_rgb = 0;              // staging for callers whose RGB starts on the host
@@ -15,6 +18,10 @@ struct WebpDevice {
     int *d_progress = nullptr; size_t cap_progress = 0;
     uint8_t *h_out = nullptr; size_t cap_hout = 0;             // pinned: levels | modes
     uint8_t *h_rgb = nullptr; size_t cap_hrgb = 0;             // pinned staging for host RGB
+    uint32_t *d_tokwork = nullptr; size_t cap_tokwork = 0;     // mask | counts | offsets | tallies
+    void *d_toktemp = nullptr; size_t cap_toktemp = 0;         // scan scratch
+    uint16_t *d_tokens = nullptr; size_t cap_tokens = 0;       // the frame's decision records
+    uint8_t *h_tokens = nullptr; size_t cap_htokens = 0;       // pinned: records
     double last_wait_ms = 0, last_code_ms = 0;                 // tracing: wait for the kernels + D2H, host boolean coder of the last encode
     ~WebpDevice();
     // d_r/d_g/d_b: device planes (pitch w).  Produces the .webp file; optionally also hands back the levels/modes (tests).

@@ -18,7 +18,7 @@ int main(void)
         (fn)b200_jpeg_batch_run, (fn)b200_jpeg_batch_download, (fn)b200_jpeg_batch_time, (fn)b200_jpeg_batch_destroy,
         (fn)b200_png_decode, (fn)b200_png_decode_reduced, (fn)b200_png_filter, (fn)b200_png_lz77, (fn)b200_png_deflate_tokens, (fn)b200_png_level_strategies,
         (fn)b200_webp_encode_rgb, (fn)b200_webp_write_levels, (fn)b200_webp_qindex,
-        (fn)b200_jpeg_pipe_create, (fn)b200_jpeg_pipe_run, (fn)b200_jpeg_pipe_finish, (fn)b200_jpeg_pipe_fetch, (fn)b200_jpeg_pipe_kernel_times, (fn)b200_jpeg_pipe_destroy, (fn)b200_device_jobs, (fn)b200_device_numa_node, (fn)b200_png_device_times, (fn)b200_webp_decode, (fn)b200_webp_alpha_chunk, (fn)b200_webp_wrap_alpha, (fn)b200_webp_decode_rgba, (fn)b200_webp_alpha_filter,
+        (fn)b200_jpeg_pipe_create, (fn)b200_jpeg_pipe_run, (fn)b200_jpeg_pipe_finish, (fn)b200_jpeg_pipe_fetch, (fn)b200_jpeg_pipe_kernel_times, (fn)b200_jpeg_pipe_destroy, (fn)b200_device_jobs, (fn)b200_device_numa_node, (fn)b200_png_device_times, (fn)b200_webp_decode, (fn)b200_webp_alpha_chunk, (fn)b200_webp_wrap_alpha, (fn)b200_webp_decode_rgba, (fn)b200_webp_alpha_filter, (fn)b200_webp_d2h_bytes,
     };
     size_t i, n = sizeof(all) / sizeof(all[0]);
     b200_params p;
