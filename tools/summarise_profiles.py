@@ -60,6 +60,7 @@ o = merged((os.path.join(G, f"{tag}_png.ncu-rep"), f"{tag} -- PNG leg, one 4096x
            (os.path.join(G, f"{tag}i_png2.ncu-rep"), f"{tag} -- PNG leg, same image: K7 match after the bit-array rewrite, hash-chain candidates, DEFLATE coder kernels", os.path.join(P, f"{tag}_ncu_png2_full.txt")),
            (os.path.join(G, f"{tag}l_png3.ncu-rep"), f"{tag} -- PNG leg, same image, final K7 match (sixteen bytes per lane, one window array: 1.08 G warp instructions, 1.19 ms) and the register-array variant of the parse that was measured slower and dropped", os.path.join(P, f"{tag}_ncu_png3_full.txt")),
            (os.path.join(G, f"{tag}_webp.ncu-rep"), f"{tag} -- resize leg of 6000x4000 JPEG -> 1920-wide WebP (tools/profile_legs.py webp): YCbCr -> RGB, K3 Lanczos3 passes", os.path.join(P, f"{tag}_ncu_resize_full.txt")),
+           (os.path.join(G, f"{tag}r_vp8tok.ncu-rep"), f"{tag} -- VP8 residual token pass on the device, 1920x1280 frame: per-macroblock masks, counting walk, writing walk (one thread per macroblock)", os.path.join(P, f"{tag}_ncu_vp8tok_full.txt")),
            (os.path.join(G, f"{tag}i_webp2.ncu-rep"), f"{tag} -- K8: RGB -> YUV and the VP8 wavefront kernel on a 1920x1280 frame", os.path.join(P, f"{tag}_ncu_vp8_full.txt")))
 k = next(v for n, v in t.items() if "k_fused_same" in n)
 fl = lambda key: float(k[key].replace(",", ""))
