@@ -166,8 +166,9 @@ struct Quant { int y1[2], y2[2], uv[2]; };
 struct FInfo { uint8_t limit, ilevel, inner, hev; };
 
 // ---- inverse transforms (libwebp TransformOne / TransformWHT: the RFC's exact integer arithmetic) --------------------------------
-inline int mul1(int a) { return ((a * 20091) >> 16) + a; }
-inline int mul2(int a) { return (a * 35468) >> 16; }
+// (64-bit products: corrupt streams can carry coefficients whose 32-bit product overflows; valid ones never get near)
+inline int mul1(int a) { return (int)(((long long)a * 20091) >> 16) + a; }
+inline int mul2(int a) { return (int)(((long long)a * 35468) >> 16); }
 void idct_add(const int16_t *in, uint8_t *dst, int stride)
 {
     int C[16], *tmp = C;
